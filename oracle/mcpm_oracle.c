@@ -1,0 +1,521 @@
+/* TEST INFRASTRUCTURE — NOT PART OF THE PRODUCT.  See mcpm_oracle.h for the pinning statement.
+ *
+ * Plain-C restatement (scalar, single-threaded, SoA storage) of the reference's per-trial energy
+ * evaluation and of the Metropolis moves that call it.  It follows the reference's arithmetic
+ * (sqrt distance, repeated-multiply powers, round() minimum image, position-inequality
+ * self-exclusion) so that it can be pinned against the compiled reference to rounding level.
+ */
+#include "mcpm_oracle.h"
+
+#include <limits.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+/* MC.h:16-18 */
+#define ORC_KB 1.380649e-23
+#define ORC_NA 6.02214076e23
+#define ORC_PLANCK 6.62607015e-34
+#define ORC_NBINS 100 /* MC.h:11 */
+
+enum { RNG_MT = 0, RNG_REPLAY = 1, RNG_PHILOX = 2 };
+
+struct orc_chain {
+    orc_system sys;
+    int pbc[3];
+    double volume;
+    int cap, n;
+    double *x, *y, *z;
+    /* energies stored in the particle records by EnergyOfParticle (MC.h:53-55) */
+    double *pe_pair, *pe_wall, *pe_tot;
+    double sx, sy, sz, s_pair, s_wall, s_tot; /* slot 0: saved old particle, moves.cpp:152 */
+    /* box running energies, as shipped (Box::energy etc., MC.h:75-76) */
+    double b_pair, b_many, b_wall, b_energy, b_old;
+    /* exact bookkeeping (Q3/Q4 fixed) — what the product keeps */
+    double e_pair, e_wall, e_energy;
+    double dr;
+    /* per-set stats (MC.h:35-44, MC.cpp:81-98) */
+    long long acceptance, rejection, n_displacements, accept_swap, reject_swap, n_swaps;
+    /* run totals */
+    long long tot_disp, tot_disp_acc, tot_swap, tot_swap_acc, recomputes;
+    unsigned long long pair_evals;
+    double sum_n, sum_n2, sum_e, sum_e2;
+    long long samples;
+    /* Widom (MC.h:41-42) */
+    long long widom_insertions, widom_deletions;
+    double widom_insert, widom_delete, bar_c, mu_ex, mu_tot;
+    double rdf[ORC_NBINS + 1];
+    /* uniform source */
+    int rng_mode;
+    uint64_t mt[312];
+    int mti;
+    const double* replay;
+    size_t replay_n, draws;
+    uint64_t ph_seed, ph_step;
+    uint32_t ph_chain;
+    int ph_slot;
+};
+
+/* ---------------------------------------------------------------- uniform sources ---------- */
+
+static void mt_seed(orc_chain* c, uint64_t seed) {
+    c->mt[0] = seed;
+    for (int i = 1; i < 312; i++) c->mt[i] = 6364136223846793005ULL * (c->mt[i - 1] ^ (c->mt[i - 1] >> 62)) + (uint64_t)i;
+    c->mti = 312;
+}
+static uint64_t mt_next(orc_chain* c) {
+    if (c->mti >= 312) {
+        for (int i = 0; i < 312; i++) {
+            uint64_t y = (c->mt[i] & 0xFFFFFFFF80000000ULL) | (c->mt[(i + 1) % 312] & 0x7FFFFFFFULL);
+            c->mt[i] = c->mt[(i + 156) % 312] ^ (y >> 1) ^ ((y & 1ULL) ? 0xB5026F5AA96619E9ULL : 0ULL);
+        }
+        c->mti = 0;
+    }
+    uint64_t x = c->mt[c->mti++];
+    x ^= (x >> 29) & 0x5555555555555555ULL;
+    x ^= (x << 17) & 0x71D67FFFEDA60000ULL;
+    x ^= (x << 37) & 0xFFF7EEE000000000ULL;
+    x ^= (x >> 43);
+    return x;
+}
+/* MC::Random(), MC.h:33,123: libstdc++ generate_canonical<double,53> over one 64-bit draw, then
+ * (b-a)*c + a with a=0, b=0.9999 (quirk Q1). */
+static double q1_map(uint64_t v) {
+    double cnl = (double)v * 5.42101086242752217e-20; /* 2^-64 */
+    if (cnl >= 1.0) cnl = 1.0 - 1.1102230246251565e-16; /* nextafter(1,0) */
+    return 0.9999 * cnl + 0.0;
+}
+
+void orc_philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint32_t out[4]) {
+    uint32_t c0 = ctr_in[0], c1 = ctr_in[1], c2 = ctr_in[2], c3 = ctr_in[3];
+    uint32_t k0 = key_in[0], k1 = key_in[1];
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+/* The product's device stream (csrc/mcpm_rng.cuh): call = 4*step + slot/2;
+ * ctr = (call_lo, call_hi, chain, 'MCPM'), key = (seed_lo, seed_hi); 53-bit mantissas; x0.9999. */
+double orc_philox_uniform(uint64_t seed, uint32_t chain_id, uint64_t step, int slot) {
+    uint64_t call = 4ULL * step + (uint64_t)(slot >> 1);
+    uint32_t ctr[4] = {(uint32_t)call, (uint32_t)(call >> 32), chain_id, 0x4D43504Du};
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t r[4];
+    orc_philox4x32_10(ctr, key, r);
+    uint64_t w = (slot & 1) ? (((uint64_t)r[3] << 32) | r[2]) : (((uint64_t)r[1] << 32) | r[0]);
+    return 0.9999 * ((double)(w >> 11) * 1.1102230246251565e-16);
+}
+
+void orc_rng_mt(orc_chain* c, uint64_t seed) { c->rng_mode = RNG_MT; mt_seed(c, seed); c->draws = 0; }
+void orc_rng_replay(orc_chain* c, const double* u, size_t n) {
+    c->rng_mode = RNG_REPLAY; c->replay = u; c->replay_n = n; c->draws = 0;
+}
+void orc_rng_philox(orc_chain* c, uint64_t seed, uint32_t chain_id, uint64_t first_step) {
+    c->rng_mode = RNG_PHILOX; c->ph_seed = seed; c->ph_chain = chain_id; c->ph_step = first_step;
+    c->ph_slot = 0; c->draws = 0;
+}
+double orc_random(orc_chain* c) {
+    c->draws++;
+    if (c->rng_mode == RNG_MT) return q1_map(mt_next(c));
+    if (c->rng_mode == RNG_REPLAY) return (c->draws <= c->replay_n) ? c->replay[c->draws - 1] : 0.0;
+    return orc_philox_uniform(c->ph_seed, c->ph_chain, c->ph_step, c->ph_slot++);
+}
+size_t orc_draws(const orc_chain* c) { return c->draws; }
+void orc_mt_fill(uint64_t seed, double* u, size_t n) {
+    orc_chain* t = (orc_chain*)calloc(1, sizeof(orc_chain));
+    mt_seed(t, seed);
+    for (size_t i = 0; i < n; i++) u[i] = q1_map(mt_next(t));
+    free(t);
+}
+
+/* ---------------------------------------------------------------- potentials --------------- */
+
+/* Tools::Pow, tools.h:53-58 */
+static double ipow(double v, int p) {
+    double r = 1.;
+    for (int i = 1; i <= p; i++) r *= v;
+    return r;
+}
+/* MC::ComputeVolume, read.cpp:26-35 (slit and bulk branches) */
+double orc_volume(const orc_system* s) {
+    if (s->geometry == 1) return s->width[0] * s->width[1] * s->width[2];
+    return ipow(s->width[2], 3);
+}
+/* SwapParticle's activity, moves.cpp:296-298 */
+double orc_swap_zz(const orc_system* s) {
+    double particleMass = s->molar_mass / ORC_NA * 1e-3;
+    double thermalWL = ORC_PLANCK / sqrt(2.0 * M_PI * particleMass * ORC_KB * s->temperature) * 1e10;
+    return exp(s->mu / s->temperature) / ipow(thermalWL, 3);
+}
+/* MC::NeighDistance, potentials.cpp:22-33 */
+static double neigh_distance(const orc_chain* c, double xi, double yi, double zi, double xj, double yj, double zj) {
+    double dx = xi - xj, dy = yi - yj, dz = zi - zj;
+    if (c->pbc[0]) dx -= round(dx / c->sys.width[0]) * c->sys.width[0];
+    if (c->pbc[1]) dy -= round(dy / c->sys.width[1]) * c->sys.width[1];
+    if (c->pbc[2]) dz -= round(dz / c->sys.width[2]) * c->sys.width[2];
+    return sqrt(dx * dx + dy * dy + dz * dz);
+}
+/* MC::LJ126_Pot, potentials.cpp:55-73 — partner scan over the live particles 0..n-1, self skipped
+ * by POSITION inequality (MC.h:56-60, quirk Q7), inclusive cutoff (Q8), no shift, no tail. */
+static double lj126(orc_chain* c, double xi, double yi, double zi) {
+    double eps = c->sys.eps_ff, sig = c->sys.sig_ff, rcut = c->sys.rcut, energy = 0.;
+    for (int j = 0; j < c->n; j++) {
+        if (xi != c->x[j] || yi != c->y[j] || zi != c->z[j]) {
+            double rij = neigh_distance(c, xi, yi, zi, c->x[j], c->y[j], c->z[j]);
+            if (rij <= rcut) energy += 4. * eps * (ipow(sig / rij, 12) - ipow(sig / rij, 6));
+        }
+    }
+    c->pair_evals += (unsigned long long)c->n;
+    return energy;
+}
+/* MC::SlitLJ_Pot, potentials.cpp:381-402 */
+double orc_slit_wall(const orc_system* s, double zabs) {
+    int nLayers = s->n_layers;
+    double sizeR = s->width[2] * 0.5, dens = s->rho_s, eps = s->eps_sf, sig = s->sig_sf, delta = s->delta;
+    double usf = 0;
+    double z = zabs - sizeR;
+    for (int i = 0; i < nLayers; i++) {
+        double t1 = ipow(sig / (sizeR + i * delta + z), 10);
+        double t2 = ipow(sig / (sizeR + i * delta - z), 10);
+        double t3 = ipow(sig / (sizeR + i * delta + z), 4);
+        double t4 = ipow(sig / (sizeR + i * delta - z), 4);
+        usf += 0.2 * (t1 + t2) - 0.5 * (t3 + t4);
+    }
+    usf *= 4. * M_PI * eps * dens * sig * sig;
+    return usf;
+}
+/* MC::EnergyOfParticle, energy.cpp:43-105 for a position (x,y,z): out-of-pore guard adds the FINITE
+ * INT_MAX and the wall term is still added (Q6); pair term from LJ126_Pot. */
+static void energy_at(orc_chain* c, double x, double y, double z, double* pair, double* wall) {
+    double boxE = 0., sqrDist = 0.;
+    double sqrPoreRadius = c->sys.width[2] * c->sys.width[2] * 0.25;
+    double zPos = z - 0.5 * c->sys.width[2];
+    if (c->sys.geometry == 1) sqrDist = zPos * zPos;
+    if ((sqrDist > sqrPoreRadius) || (sqrDist < 0)) boxE = INT_MAX;
+    if (c->sys.wall_kind == 1 && c->sys.geometry == 1) boxE += orc_slit_wall(&c->sys, z);
+    *pair = lj126(c, x, y, z);
+    *wall = boxE;
+}
+/* EnergyOfParticle on a stored slot: results are written into the particle record (energy.cpp:102-104). */
+static void energy_of_slot(orc_chain* c, int slot) {
+    double p, w;
+    energy_at(c, c->x[slot], c->y[slot], c->z[slot], &p, &w);
+    c->pe_pair[slot] = p; c->pe_wall[slot] = w; c->pe_tot[slot] = p + 0. + w;
+}
+
+void orc_particle_energy(orc_chain* c, int index0, double out[4]) {
+    energy_of_slot(c, index0);
+    out[0] = c->pe_pair[index0]; out[1] = 0.; out[2] = c->pe_wall[index0]; out[3] = c->pe_tot[index0];
+}
+void orc_trial_energy(orc_chain* c, double x, double y, double z, double out[4]) {
+    int slot = c->n; /* first free slot, moves.cpp:302-304 */
+    c->x[slot] = x; c->y[slot] = y; c->z[slot] = z;
+    energy_of_slot(c, slot);
+    out[0] = c->pe_pair[slot]; out[1] = 0.; out[2] = c->pe_wall[slot]; out[3] = c->pe_tot[slot];
+}
+void orc_moved_energy(orc_chain* c, int i, double x, double y, double z, double out[4]) {
+    double ox = c->x[i], oy = c->y[i], oz = c->z[i], op = c->pe_pair[i], ow = c->pe_wall[i], ot = c->pe_tot[i];
+    c->x[i] = x; c->y[i] = y; c->z[i] = z; /* moves.cpp:163-165 */
+    energy_of_slot(c, i);
+    out[0] = c->pe_pair[i]; out[1] = 0.; out[2] = c->pe_wall[i]; out[3] = c->pe_tot[i];
+    c->x[i] = ox; c->y[i] = oy; c->z[i] = oz; c->pe_pair[i] = op; c->pe_wall[i] = ow; c->pe_tot[i] = ot;
+}
+/* MC::BoxEnergy, energy.cpp:106-124 */
+static void box_energy(orc_chain* c) {
+    double pairPotE = 0., boxE = 0.;
+    for (int j = 0; j < c->n; j++) {
+        energy_of_slot(c, j);
+        pairPotE += c->pe_pair[j];
+        boxE += c->pe_wall[j];
+    }
+    c->b_many = 0.;
+    c->b_pair = 0.5 * pairPotE;
+    c->b_wall = boxE;
+    c->b_energy = 0. + 0.5 * pairPotE + boxE;
+}
+void orc_box_energy(orc_chain* c, double out[4], double* per_pair, double* per_wall) {
+    box_energy(c);
+    out[0] = c->b_pair; out[1] = 0.; out[2] = c->b_wall; out[3] = c->b_energy;
+    c->e_pair = c->b_pair; c->e_wall = c->b_wall; c->e_energy = c->b_energy;
+    for (int j = 0; j < c->n; j++) {
+        if (per_pair) per_pair[j] = c->pe_pair[j];
+        if (per_wall) per_wall[j] = c->pe_wall[j];
+    }
+}
+/* MC::CorrectEnergy, energy.cpp:35-42 (quirk Q4) */
+static void correct_energy(orc_chain* c) {
+    double rel = c->b_energy / c->b_old;
+    if (rel > 1) { box_energy(c); c->recomputes++; }
+}
+/* MC::PBC, energy.cpp:126-130 */
+static void wrap(const orc_chain* c, double* x, double* y, double* z) {
+    if (c->pbc[0]) *x -= floor(*x / c->sys.width[0]) * c->sys.width[0];
+    if (c->pbc[1]) *y -= floor(*y / c->sys.width[1]) * c->sys.width[1];
+    if (c->pbc[2]) *z -= floor(*z / c->sys.width[2]) * c->sys.width[2];
+}
+
+/* ---------------------------------------------------------------- moves -------------------- */
+
+/* MC::InsertParticle slit/bulk branches, moves.cpp:46-54: x,y,z = u*width, three draws in that order. */
+static void insert_particle(orc_chain* c, int slot) {
+    c->x[slot] = orc_random(c) * c->sys.width[0];
+    c->y[slot] = orc_random(c) * c->sys.width[1];
+    c->z[slot] = orc_random(c) * c->sys.width[2];
+}
+void orc_initial_config(orc_chain* c, int n) {
+    c->n = n;
+    for (int k = 0; k < n; k++) insert_particle(c, k);
+}
+/* MC::MoveParticle, moves.cpp:118-186.  Seven draws: box, species, index, dx, dy, dz, accept. */
+static int move_particle(orc_chain* c) {
+    double T = c->sys.temperature;
+    (void)(int)(orc_random(c) * c->n); /* box selection, :128-137 — single box */
+    (void)(int)(orc_random(c) * c->n); /* species selection, :138-147 — single species */
+    c->n_displacements++; c->tot_disp++;
+    c->b_old = c->b_energy;
+    int i = (int)(orc_random(c) * c->n); /* reference: int(u*n)+1 on 1-based slots, :150.  n==0 -> stale slot (Q12) */
+    /* ithPart = particle(index); particle(0) = ithPart — the COPY precedes the energy call, :151-152 */
+    c->sx = c->x[i]; c->sy = c->y[i]; c->sz = c->z[i];
+    c->s_pair = c->pe_pair[i]; c->s_wall = c->pe_wall[i]; c->s_tot = c->pe_tot[i];
+    energy_of_slot(c, i);
+    double oldPair = c->pe_pair[i], oldWall = c->pe_wall[i], oldEnergy = c->pe_tot[i];
+    double nx = c->sx, ny = c->sy, nz = c->sz;
+    nx += (orc_random(c) - 0.5) * c->dr;
+    ny += (orc_random(c) - 0.5) * c->dr;
+    nz += (orc_random(c) - 0.5) * c->dr;
+    wrap(c, &nx, &ny, &nz);
+    c->x[i] = nx; c->y[i] = ny; c->z[i] = nz;
+    c->pe_pair[i] = c->s_pair; c->pe_wall[i] = c->s_wall; c->pe_tot[i] = c->s_tot; /* record copied whole, :163 */
+    energy_of_slot(c, i);
+    double newPair = c->pe_pair[i], newWall = c->pe_wall[i], newEnergy = c->pe_tot[i];
+    double arg = (newEnergy - oldEnergy) / T;
+    if (orc_random(c) < exp(-arg)) {
+        c->acceptance++; c->tot_disp_acc++;
+        double dPair = newPair - oldPair, dWall = newWall - oldWall;
+        c->b_pair += 0.5 * dPair; c->b_wall += dWall; c->b_energy += 0. + 0.5 * dPair + dWall;
+        c->e_pair += 0.5 * dPair; c->e_wall += dWall; c->e_energy += 0.5 * dPair + dWall;
+        return 1;
+    }
+    c->rejection++;
+    c->x[i] = c->sx; c->y[i] = c->sy; c->z[i] = c->sz;
+    c->pe_pair[i] = c->s_pair; c->pe_wall[i] = c->s_wall; c->pe_tot[i] = c->s_tot;
+    return 0;
+}
+/* MC::SwapParticle single-box branch, moves.cpp:284-341.  Returns (kind<<1)|accepted. */
+static int swap_particle(orc_chain* c) {
+    double T = c->sys.temperature;
+    (void)(int)(orc_random(c) * c->n); /* species selection, :285-294 */
+    c->b_old = c->b_energy;
+    double zz = orc_swap_zz(&c->sys); /* recomputed every call in the reference, :296-298 */
+    if (orc_random(c) < 0.5) {
+        c->n_swaps++; c->tot_swap++;
+        int in = c->n;
+        insert_particle(c, in);
+        energy_of_slot(c, in);
+        double inEnergy = c->pe_tot[in];
+        double arg = zz * c->volume * exp(-inEnergy / T) / (c->n + 1);
+        if (orc_random(c) < arg) {
+            c->accept_swap++; c->tot_swap_acc++;
+            c->n++;
+            double pairE = 0.5 * c->pe_pair[in], wallE = c->pe_wall[in];
+            c->b_pair += pairE; c->b_wall += wallE; c->b_energy += 0. + pairE + wallE;
+            c->e_pair += pairE; c->e_wall += wallE; c->e_energy += pairE + wallE;
+            return (1 << 1) | 1;
+        }
+        c->reject_swap++;
+        return (1 << 1);
+    } else if (c->n > 0) {
+        c->n_swaps++; c->tot_swap++;
+        int out = (int)(orc_random(c) * c->n + 1) - 1; /* int(u*n+1) on 1-based slots, :323 */
+        energy_of_slot(c, out);
+        double outEnergy = c->pe_tot[out];
+        double arg = c->n * exp(outEnergy / T) / (zz * c->volume);
+        if (orc_random(c) < arg) {
+            c->accept_swap++; c->tot_swap_acc++;
+            double fPair = 0.5 * c->pe_pair[out], fWall = c->pe_wall[out]; /* fresh, for exact bookkeeping */
+            int last = c->n - 1;
+            c->x[out] = c->x[last]; c->y[out] = c->y[last]; c->z[out] = c->z[last]; /* :329 swap-with-last */
+            c->pe_pair[out] = c->pe_pair[last]; c->pe_wall[out] = c->pe_wall[last]; c->pe_tot[out] = c->pe_tot[last];
+            c->n--;
+            /* as shipped (Q3): the record at `out` is read AFTER the overwrite, :333-339 */
+            double pairE = 0.5 * c->pe_pair[out], wallE = c->pe_wall[out];
+            c->b_pair -= pairE; c->b_wall -= wallE; c->b_energy -= 0. + pairE + wallE;
+            c->e_pair -= fPair; c->e_wall -= fWall; c->e_energy -= fPair + fWall;
+            return (2 << 1) | 1;
+        }
+        c->reject_swap++;
+        return (2 << 1);
+    }
+    return (3 << 1);
+}
+/* Body of the step loop, main.cpp:67-71 (volume moves are out of scope: n_vol must be 0). */
+int orc_step(orc_chain* c, int correct) {
+    int nD = c->sys.n_disp, nV = c->sys.n_vol, nS = c->sys.n_swap, code = 0;
+    if (c->rng_mode == RNG_PHILOX) c->ph_slot = 0;
+    double r = orc_random(c) * (nD + nV + nS);
+    if (r <= nD) code = move_particle(c);
+    else if (r <= nD + nV) code = (4 << 1);
+    else if (r <= nD + nV + nS) code = swap_particle(c);
+    if (correct) correct_energy(c);
+    if (c->rng_mode == RNG_PHILOX) c->ph_step++;
+    return code;
+}
+long long orc_run(orc_chain* c, long long nsteps, int correct, unsigned char* trace) {
+    long long acc = 0;
+    for (long long s = 0; s < nsteps; s++) {
+        int code = orc_step(c, correct);
+        if (trace) trace[s] = (unsigned char)code;
+        acc += code & 1;
+    }
+    return acc;
+}
+/* MC::ResetStats, MC.cpp:81-98 — note nDisplacements and nSwaps restart at ONE. */
+void orc_reset_stats(orc_chain* c) {
+    c->accept_swap = c->reject_swap = 0;
+    c->n_swaps = 1;
+    c->bar_c = 1.;
+    c->widom_insertions = c->widom_deletions = 1;
+    c->widom_insert = c->widom_delete = 0.;
+    c->acceptance = c->rejection = 0;
+    c->n_displacements = 1;
+}
+/* MC::AdjustMCMoves displacement part, moves.cpp:68-78 */
+void orc_adjust(orc_chain* c, int set) {
+    if (c->n > 0) {
+        if (set <= c->sys.n_equil_sets) {
+            double ratio = c->acceptance * 1. / (1. * c->n_displacements);
+            if (ratio < 0.2) c->dr /= 1.1;
+            else c->dr *= 1.1;
+        }
+    }
+}
+void orc_run_sets(orc_chain* c, int first_set, int n_sets, long long steps_per_set, int correct, unsigned char* trace) {
+    for (int set = first_set; set < first_set + n_sets; set++) {
+        orc_reset_stats(c);
+        for (long long s = 0; s < steps_per_set; s++) {
+            int code = orc_step(c, correct);
+            if (trace) *trace++ = (unsigned char)code;
+            if (set > c->sys.n_equil_sets) {
+                double n = (double)c->n, e = c->e_energy;
+                c->sum_n += n; c->sum_n2 += n * n; c->sum_e += e; c->sum_e2 += e * e;
+                c->samples++;
+            }
+        }
+        orc_adjust(c, set);
+    }
+}
+
+/* ---------------------------------------------------------------- sampling (next rows) ----- */
+
+/* MC::BarWeight, moves.cpp:409 */
+static double bar_weight(const orc_chain* c, double barC, double energy) {
+    return 1. / cosh(0.5 * (energy - barC) / c->sys.temperature);
+}
+/* MC::ComputeWidom, moves.cpp:410-449, NVT branch (no volume moves). Ghost slot = outside 0..n-1.
+ * Deletion picks int(u*n) on 1-based slots: slot 0 = the saved-old-particle scratch (Q14). */
+void orc_widom(orc_chain* c, double out[2], long long iout[2]) {
+    double T = c->sys.temperature, pair, wall, energy;
+    if (c->sys.n_swap == 0) {
+        (void)(int)(orc_random(c) * 1);
+        if (orc_random(c) < 0.5) {
+            c->widom_insertions++;
+            double gx = orc_random(c) * c->sys.width[0];
+            double gy = orc_random(c) * c->sys.width[1];
+            double gz = orc_random(c) * c->sys.width[2];
+            energy_at(c, gx, gy, gz, &pair, &wall);
+            energy = pair + wall;
+            c->widom_insert += bar_weight(c, c->bar_c, energy) * exp(-0.5 * energy / T);
+        } else {
+            c->widom_deletions++;
+            int slot1 = (int)(orc_random(c) * c->n);
+            if (slot1 == 0) energy_at(c, c->sx, c->sy, c->sz, &pair, &wall);
+            else energy_at(c, c->x[slot1 - 1], c->y[slot1 - 1], c->z[slot1 - 1], &pair, &wall);
+            energy = pair + wall;
+            if (exp(0.5 * energy / T) < 1) c->widom_delete += bar_weight(c, c->bar_c, energy) * exp(0.5 * energy / T);
+            else c->widom_delete += bar_weight(c, c->bar_c, energy) * exp(-0.5 * energy / T);
+        }
+    }
+    if (out) { out[0] = c->widom_insert; out[1] = c->widom_delete; }
+    if (iout) { iout[0] = c->widom_insertions; iout[1] = c->widom_deletions; }
+}
+/* MC::ComputeChemicalPotential, moves.cpp:453-465 */
+void orc_chem_pot(orc_chain* c, double out[2]) {
+    double T = c->sys.temperature;
+    double particleMass = c->sys.molar_mass / ORC_NA * 1e-3;
+    double thermalWL = ORC_PLANCK / sqrt(2.0 * M_PI * particleMass * ORC_KB * T) * 1e10;
+    double widomParam = (c->widom_insert / c->widom_insertions) / (c->widom_delete / c->widom_deletions);
+    double muIdeal = T * log(ipow(thermalWL, 3) * (c->n + 1) / c->volume);
+    double muExcess = -T * log(widomParam);
+    c->mu_ex = muExcess; c->mu_tot = muIdeal + muExcess;
+    out[0] = c->mu_ex; out[1] = c->mu_tot;
+}
+/* MC::ComputeRDF same-species branch, sample.cpp:21-31 */
+void orc_rdf(orc_chain* c, double* hist) {
+    double deltaR = c->sys.rcut / (1. * ORC_NBINS);
+    for (int i = 0; i < c->n - 1; i++)
+        for (int j = i + 1; j < c->n; j++) {
+            int bin = (int)(neigh_distance(c, c->x[i], c->y[i], c->z[i], c->x[j], c->y[j], c->z[j]) / deltaR) + 1;
+            if (bin < ORC_NBINS) c->rdf[bin] += 2;
+        }
+    if (hist) memcpy(hist, c->rdf, sizeof(double) * ORC_NBINS);
+}
+void orc_rdf_reset(orc_chain* c) { memset(c->rdf, 0, sizeof(c->rdf)); }
+
+/* ---------------------------------------------------------------- lifecycle ---------------- */
+
+orc_chain* orc_create(const orc_system* sys, int capacity) {
+    orc_chain* c = (orc_chain*)calloc(1, sizeof(orc_chain));
+    c->sys = *sys;
+    /* PBC flags from the geometry, read.cpp:146-162 */
+    c->pbc[0] = 1; c->pbc[1] = 1; c->pbc[2] = (sys->geometry == 1) ? 0 : 1;
+    c->volume = orc_volume(sys);
+    c->cap = capacity + 2;
+    size_t bytes = sizeof(double) * (size_t)c->cap;
+    c->x = (double*)calloc(1, bytes); c->y = (double*)calloc(1, bytes); c->z = (double*)calloc(1, bytes);
+    c->pe_pair = (double*)calloc(1, bytes); c->pe_wall = (double*)calloc(1, bytes); c->pe_tot = (double*)calloc(1, bytes);
+    c->dr = sys->dr;
+    c->bar_c = 1.; c->widom_insertions = c->widom_deletions = 1; /* MC.cpp:25-28 */
+    orc_rng_mt(c, 5489ULL);
+    return c;
+}
+void orc_destroy(orc_chain* c) {
+    if (!c) return;
+    free(c->x); free(c->y); free(c->z); free(c->pe_pair); free(c->pe_wall); free(c->pe_tot);
+    free(c);
+}
+void orc_set_positions(orc_chain* c, int n, const double* x, const double* y, const double* z) {
+    if (n > c->cap - 2) n = c->cap - 2;
+    memcpy(c->x, x, sizeof(double) * (size_t)n);
+    memcpy(c->y, y, sizeof(double) * (size_t)n);
+    memcpy(c->z, z, sizeof(double) * (size_t)n);
+    memset(c->pe_pair, 0, sizeof(double) * (size_t)c->cap);
+    memset(c->pe_wall, 0, sizeof(double) * (size_t)c->cap);
+    memset(c->pe_tot, 0, sizeof(double) * (size_t)c->cap);
+    c->n = n;
+}
+int orc_get_positions(const orc_chain* c, double* x, double* y, double* z) {
+    memcpy(x, c->x, sizeof(double) * (size_t)c->n);
+    memcpy(y, c->y, sizeof(double) * (size_t)c->n);
+    memcpy(z, c->z, sizeof(double) * (size_t)c->n);
+    return c->n;
+}
+void orc_get_state(const orc_chain* c, double d[16], long long i[16]) {
+    d[0] = c->b_pair; d[1] = c->b_many; d[2] = c->b_wall; d[3] = c->b_energy;
+    d[4] = c->dr; d[5] = c->volume; d[6] = c->b_old; d[7] = c->sys.temperature;
+    d[8] = c->e_pair; d[9] = c->e_wall; d[10] = c->e_energy;
+    d[11] = c->sum_n; d[12] = c->sum_n2; d[13] = c->sum_e; d[14] = c->sum_e2; d[15] = (double)c->samples;
+    i[0] = c->n; i[1] = c->acceptance; i[2] = c->rejection; i[3] = c->n_displacements;
+    i[4] = c->accept_swap; i[5] = c->reject_swap; i[6] = c->n_swaps; i[7] = c->n;
+    i[8] = c->tot_disp; i[9] = c->tot_disp_acc; i[10] = c->tot_swap; i[11] = c->tot_swap_acc;
+    i[12] = c->recomputes; i[13] = (long long)(c->pair_evals & 0x7FFFFFFFFFFFFFFFULL); i[14] = 0; i[15] = 0;
+}
