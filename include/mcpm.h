@@ -1,0 +1,176 @@
+/* mcpm.h — C ABI of the B200-native Monte Carlo adsorption engine (libmcpm.so).
+ *
+ * Drop-in boundary for ONE hot path of salflorom/MC-PorousMaterials: the per-trial-move energy
+ * evaluation and the Metropolis translation / insertion / deletion loop that drives it.
+ * The reference has no plugin or FFI layer; its seam is a pair of C++ member functions that
+ * communicate through side effects on the monolithic `MC` object (reference src/MC.h:111-112).
+ * Each entry point below names the reference interface it replaces (file:line under
+ * /root/reference).  INTEGRATION.md shows the reference-side binding a maintainer would add.
+ *
+ * Conventions: plain C types only; opaque context handle; every call returns an int status
+ * (MCPM_OK == 0) and never throws across the boundary; mcpm_last_error() gives the message of the
+ * last failing call on the calling thread.  One context owns one GPU and one CUDA stream; calls on
+ * one context are not thread-safe, different contexts may be used from different host threads.
+ * Particle indices are 0-based and order-preserving (the reference's slots 1..n, src/MC.h:12).
+ * Energies are in kelvin (E/kB), lengths in angstrom, exactly as in the reference.
+ * All arithmetic is fp64.  There is NO CPU fallback: without a CUDA device every compute entry
+ * point fails with MCPM_ERR_CUDA.
+ */
+#ifndef MCPM_H
+#define MCPM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCPM_VERSION 100
+
+enum {
+    MCPM_OK = 0,
+    MCPM_ERR_ARG = 1,       /* bad argument (null pointer, index out of range, unsupported option) */
+    MCPM_ERR_CUDA = 2,      /* CUDA runtime error or no device */
+    MCPM_ERR_CAPACITY = 3,  /* a chain outgrew its particle capacity */
+    MCPM_ERR_UNSUPPORTED = 4,
+    MCPM_ERR_IO = 5
+};
+
+enum { MCPM_GEOM_BULK = 0, MCPM_GEOM_SLIT = 1 };      /* Box::geometry, src/read.cpp:74, :146-162 */
+enum { MCPM_WALL_NONE = 0, MCPM_WALL_SLIT_LJ = 1 };   /* wall dispatch, src/energy.cpp:69-77      */
+enum { MCPM_RNG_PHILOX = 0, MCPM_RNG_REPLAY = 1 };
+
+typedef struct mcpm_ctx mcpm_ctx; /* opaque */
+
+/* One thermodynamic state point = one chain's system (single box, single species).
+ * Field meaning = the reference's parsed input (src/read.cpp:50-121) after its post-processing
+ * (src/read.cpp:122-168): width[0..1] are the derived lateral sizes, dr the translation amplitude. */
+typedef struct mcpm_system_desc {
+    int geometry;        /* MCPM_GEOM_*;  PBC flags follow the geometry as in src/read.cpp:146-162 */
+    int wall_kind;       /* MCPM_WALL_*;  SLIT_LJ = SlitLJ_Pot, src/potentials.cpp:381-402 */
+    int n_layers;        /* Box::nLayersPerWall */
+    int n_disp, n_vol, n_swap; /* move weights, src/main.cpp:67-70 (n_vol must be 0: volume moves out of scope) */
+    int n_equil_sets;    /* sets during which dr adapts and nothing is sampled, src/moves.cpp:74, src/main.cpp:72 */
+    int reserved;
+    double width[3];     /* Box::width, angstrom; width[2] is the pore size H */
+    double temperature;  /* K */
+    double eps_ff, sig_ff, rcut;    /* Fluid::{epsilon,sigma,rcut}(0), src/potentials.cpp:62-64 */
+    double molar_mass, mu;          /* g/mol; full chemical potential mu/kB in K, src/moves.cpp:296-298 */
+    double eps_sf, sig_sf, rho_s, delta; /* Box::fluid(0).{epsilon,sigma}(0), solidDens, deltaLayers, src/potentials.cpp:384-389 */
+    double dr;           /* Simulation::dr, src/read.cpp:168 */
+} mcpm_system_desc;
+
+/* Energies of one particle, as MC::EnergyOfParticle leaves them in the particle record
+ * (src/energy.cpp:49-51,102-104): {pairPotE, manyBodyE (always 0 here), boxE, energy}. */
+typedef struct mcpm_particle_energy_t {
+    double pair, many_body, wall, energy;
+} mcpm_particle_energy_t;
+
+/* Box totals, as MC::BoxEnergy leaves them (src/energy.cpp:119-122): pair is ALREADY halved. */
+typedef struct mcpm_box_energy_t {
+    double pair, many_body, wall, energy;
+} mcpm_box_energy_t;
+
+typedef struct mcpm_run_params {
+    int first_set;             /* 1-based index of the first set of this call (src/main.cpp:63) */
+    int n_sets;
+    long long steps_per_set;   /* Simulation::nStepsPerSet */
+    int rng_mode;              /* MCPM_RNG_PHILOX: device Philox4x32-10 keyed by (seed, chain id, step);
+                                  MCPM_RNG_REPLAY: consume replay_u exactly as the reference consumes
+                                  MC::Random() (1 + 7/6/4/2 draws per step) */
+    unsigned long long seed;
+    const double* replay_u;    /* HOST pointer, n_chains * replay_stride uniforms (REPLAY only) */
+    size_t replay_stride;
+    unsigned char* trace;      /* HOST pointer or NULL: n_chains * n_sets*steps_per_set bytes,
+                                  (move<<1)|accepted; move 0 translation, 1 insertion, 2 deletion,
+                                  3 deletion branch on an empty box */
+    int threads_per_chain;     /* CTA size, multiple of 32 up to 1024; 0 = choose from the loadings */
+    int check_energy;          /* !=0: recompute the full box energy on the device at the end (drift check) */
+} mcpm_run_params;
+
+/* Per-chain result of mcpm_run.  Per-set counters follow MC::Stats after the LAST set of the call
+ * (src/MC.h:35-44; ResetStats starts n_displacements and n_swaps at 1, src/MC.cpp:81-98). */
+typedef struct mcpm_chain_stats {
+    int n;                     /* current number of particles */
+    int overflow;              /* !=0: the chain hit its capacity and stopped */
+    double dr;                 /* current translation amplitude (after AdjustMCMoves) */
+    double pair, wall, energy; /* running box energies by exact bookkeeping (pair halved) */
+    double pair_check, wall_check, energy_check; /* full recompute at the end if check_energy */
+    long long acceptance, rejection, n_displacements;
+    long long accept_swap, reject_swap, n_swaps;
+    long long tot_disp, tot_disp_acc, tot_ins, tot_ins_acc, tot_del, tot_del_acc, tot_empty;
+    unsigned long long pair_evals;  /* iterations of the partner loop src/potentials.cpp:65-71 */
+    unsigned long long steps_done;  /* chain's global step counter (= Philox step index) */
+    /* production accumulators (set > n_equil_sets), one sample per step */
+    double sum_n, sum_n2, sum_e, sum_e2;
+    long long samples;
+} mcpm_chain_stats;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int mcpm_version(void);
+const char* mcpm_last_error(void);
+int mcpm_device_count(int* count);
+
+/* ---- context: n_chains independent systems, each with room for `capacity` particles ------- */
+/* Replaces the MC constructor's fixed-capacity arrays (src/MC.cpp:13-80, src/MC.h:68,79). */
+int mcpm_create(int device, int n_chains, int capacity, mcpm_ctx** out);
+int mcpm_destroy(mcpm_ctx* ctx);
+int mcpm_n_chains(const mcpm_ctx* ctx, int* n_chains, int* capacity);
+
+/* chain = -1 applies the description to every chain.  Replaces ReadInputFile's state (src/read.cpp:36-172). */
+int mcpm_set_system(mcpm_ctx* ctx, int chain, const mcpm_system_desc* desc);
+int mcpm_get_system(const mcpm_ctx* ctx, int chain, mcpm_system_desc* desc);
+
+/* SoA fp64 positions of one chain (host pointers). Replaces box(b).fluid(s).particle(1..n).{x,y,z}. */
+int mcpm_set_positions(mcpm_ctx* ctx, int chain, int n, const double* x, const double* y, const double* z);
+int mcpm_get_positions(mcpm_ctx* ctx, int chain, int* n, double* x, double* y, double* z);
+/* All chains at once: n[n_chains]; x,y,z are [n_chains][capacity] row-major host arrays. */
+int mcpm_set_positions_all(mcpm_ctx* ctx, const int* n, const double* x, const double* y, const double* z);
+int mcpm_get_positions_all(mcpm_ctx* ctx, int* n, double* x, double* y, double* z);
+
+/* ---- K1: single-particle energy == MC::EnergyOfParticle (src/energy.cpp:43-105) ------------ *
+ * index >= 0, trial == NULL : energy of stored particle `index`                 -> cur
+ * index >= 0, trial != NULL : also the energy of that particle displaced to trial[3]
+ *                             (what MoveParticle evaluates, src/moves.cpp:153,165) -> cur and moved
+ * index == -1, trial != NULL: energy of a ghost / inserted particle at trial[3]
+ *                             (src/moves.cpp:304, :421)                          -> moved
+ * Either output pointer may be NULL. One launch evaluates both positions in one pass over j. */
+int mcpm_particle_energy(mcpm_ctx* ctx, int chain, int index, const double* trial,
+                         mcpm_particle_energy_t* cur, mcpm_particle_energy_t* moved);
+
+/* ---- K3: full box energy == MC::BoxEnergy (src/energy.cpp:106-124) ------------------------- *
+ * per_pair / per_wall (nullable, n doubles each) receive every particle's pairPotE / boxE, as
+ * BoxEnergy leaves them in the particle records.  Also resets the chain's running energies. */
+int mcpm_box_energy(mcpm_ctx* ctx, int chain, mcpm_box_energy_t* out, double* per_pair, double* per_wall);
+int mcpm_box_energy_all(mcpm_ctx* ctx, mcpm_box_energy_t* out /* [n_chains] */);
+
+/* ---- state mutation for a host-driven loop (src/moves.cpp:163,184 / :302-311 / :329-332) --- */
+int mcpm_apply_move(mcpm_ctx* ctx, int chain, int index, const double xyz[3]);
+int mcpm_append(mcpm_ctx* ctx, int chain, const double xyz[3]);
+int mcpm_remove_swap_last(mcpm_ctx* ctx, int chain, int index);
+
+/* ---- K2: batched persistent chains == the step loop src/main.cpp:63-84 with MoveParticle
+ *      (src/moves.cpp:118-186), SwapParticle single-box branch (:284-341), AdjustMCMoves (:68-78)
+ *      and ResetStats (src/MC.cpp:81-98), one CTA per chain, no host round trip per move. ------- */
+int mcpm_run(mcpm_ctx* ctx, const mcpm_run_params* params, mcpm_chain_stats* stats /* [n_chains], nullable */);
+int mcpm_get_stats(mcpm_ctx* ctx, mcpm_chain_stats* stats /* [n_chains] */);
+int mcpm_reset_accumulators(mcpm_ctx* ctx);
+/* Override a chain's translation amplitude / global step counter (restart, tests). */
+int mcpm_set_dr(mcpm_ctx* ctx, int chain, double dr);
+int mcpm_set_step_counter(mcpm_ctx* ctx, int chain, unsigned long long step);
+
+/* ---- measurement support ------------------------------------------------------------------ */
+/* Device time (CUDA events on the context's stream) and launch count of the last compute call. */
+int mcpm_last_kernel_ms(const mcpm_ctx* ctx, float* ms);
+int mcpm_launch_count(const mcpm_ctx* ctx, unsigned long long* launches);
+/* FP64 FMA microbenchmark on `device`: the roofline denominator for these kernels (TFLOP/s). */
+int mcpm_fp64_peak(int device, double* tflops, double* ms);
+/* The device Philox stream, for tests: uniform of (seed, chain, step, slot). */
+int mcpm_philox_uniforms(mcpm_ctx* ctx, unsigned long long seed, unsigned int chain,
+                         unsigned long long first_step, int n_steps, double* out /* n_steps*8 */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCPM_H */

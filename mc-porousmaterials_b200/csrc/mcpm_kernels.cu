@@ -1,0 +1,529 @@
+// CUDA kernels of the engine (sm_100a, fp64):
+//   K1 k1_particle_energy   — MC::EnergyOfParticle, one particle (stored and/or displaced) vs all
+//   K2 k2_chains            — persistent batched Metropolis chains, one CTA per chain
+//   K3 k3_box_energy        — MC::BoxEnergy, per-particle and box totals, O(N^2) tiled through smem
+//   fp64_peak_kernel        — DFMA microbenchmark for the roofline denominator
+#include "mcpm_device.cuh"
+#include "mcpm_kernels.h"
+
+namespace mcpm {
+
+// ================================================================================================
+// K2 — batched persistent chains.
+//
+// One CTA advances one chain for n_sets*steps_per_set trial moves without any host round trip:
+// the body of the reference step loop (src/main.cpp:66-71) with MoveParticle (src/moves.cpp:118-186),
+// SwapParticle's single-box branch (src/moves.cpp:284-341), ResetStats (src/MC.cpp:81-98) and
+// AdjustMCMoves (src/moves.cpp:68-78).  CorrectEnergy's heuristic recompute (src/energy.cpp:35-42,
+// quirk Q4) is replaced by exact bookkeeping plus an optional full recompute at the end.
+//
+// Layout: positions live in shared memory as SoA fp64 (x[cap] | y[cap] | z[cap]); thread t owns the
+// slots j == t (mod T) — it is the only thread that reads them in the partner loop and the only one
+// that writes them.  Uniforms, the Metropolis decision and all scalar state are computed
+// REDUNDANTLY by every thread from identical inputs (same uniform stream, partial sums added in the
+// same order), so the decision needs no broadcast and a step costs ONE __syncthreads:
+//   phase A  select the move, read the selected particle (all cross-thread position reads happen
+//            here; a slot written in the previous phase D is forwarded from registers instead);
+//   phase B  partner loop over the thread's own slots, warp xor-reduction, partials -> smem[parity];
+//   barrier
+//   phase D  every thread sums the W partials, decides, owner thread writes the slot.
+// ================================================================================================
+
+struct Fwd {
+    int slot;
+    double x, y, z;
+};
+
+__device__ __forceinline__ void load_slot(const double* xs, const double* ys, const double* zs, int i, const Fwd& f,
+                                          double& x, double& y, double& z) {
+    if (i == f.slot) { x = f.x; y = f.y; z = f.z; }
+    else { x = xs[i]; y = ys[i]; z = zs[i]; }
+}
+
+// Partner loops.  `self` is the index excluded as "the particle itself" (-1: none).
+template <bool FAST>
+__device__ __forceinline__ void pair_sum2(const double* xs, const double* ys, const double* zs, int n, int self, const PairGeom& g,
+                                          double xa, double ya, double za, double xb, double yb, double zb,
+                                          int tid, int T, double& ea, double& eb) {
+    double sa = 0.0, sb = 0.0;
+#pragma unroll 2
+    for (int j = tid; j < n; j += T) {
+        double xj = xs[j], yj = ys[j], zj = zs[j];
+        bool ns = (j != self);
+        sa += pair_masked(dist2<FAST>(g, xa, ya, za, xj, yj, zj), g, ns);
+        sb += pair_masked(dist2<FAST>(g, xb, yb, zb, xj, yj, zj), g, ns);
+    }
+    ea = sa; eb = sb;
+}
+template <bool FAST>
+__device__ __forceinline__ double pair_sum1(const double* xs, const double* ys, const double* zs, int n, int self, const PairGeom& g,
+                                            double xa, double ya, double za, int tid, int T) {
+    double s0 = 0.0, s1 = 0.0;
+    int j = tid;
+    for (; j + T < n; j += 2 * T) {
+        s0 += pair_masked(dist2<FAST>(g, xa, ya, za, xs[j], ys[j], zs[j]), g, j != self);
+        s1 += pair_masked(dist2<FAST>(g, xa, ya, za, xs[j + T], ys[j + T], zs[j + T]), g, (j + T) != self);
+    }
+    if (j < n) s0 += pair_masked(dist2<FAST>(g, xa, ya, za, xs[j], ys[j], zs[j]), g, j != self);
+    return s0 + s1;
+}
+
+// All-reduce of NV per-thread values over the CTA; every thread returns the same bits.
+template <int NV>
+__device__ __forceinline__ void cta_allsum(double (&v)[NV], double* partials, int parity, int W, int warp, int lane) {
+#pragma unroll
+    for (int k = 0; k < NV; k++) v[k] = warp_allsum(v[k]);
+    if (W == 1) { __syncwarp(); return; }
+    double* p = partials + parity * 64;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) p[warp * 2 + k] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        double s = 0.0;
+        for (int w = 0; w < W; w++) s += p[w * 2 + k];
+        v[k] = s;
+    }
+}
+
+// Full energy of the chain held in shared memory: per-particle sums as MC::BoxEnergy forms them
+// (src/energy.cpp:106-124; every pair is visited twice and the pair total halved).
+template <bool FAST>
+__device__ void cta_box_energy(const double* xs, const double* ys, const double* zs, int n, const ChainParams& P, const PairGeom& g,
+                               double* partials, int W, int warp, int lane, int tid, int T, double& pair_half, double& wall) {
+    double v[2] = {0.0, 0.0};
+    for (int i = tid; i < n; i += T) {
+        double xi = xs[i], yi = ys[i], zi = zs[i];
+        double s = 0.0;
+        for (int j = 0; j < n; j++) s += pair_masked(dist2<FAST>(g, xi, yi, zi, xs[j], ys[j], zs[j]), g, j != i);
+        v[0] += s;
+        v[1] += wall_one(P, zi);
+    }
+    __syncthreads();
+    cta_allsum<2>(v, partials, 0, W, warp, lane);
+    __syncthreads();
+    pair_half = 0.5 * (P.eps4 * v[0]);
+    wall = v[1];
+}
+
+template <class Source, bool FAST>
+__device__ void chain_loop(ChainParams& P, ChainState& S, Source& rng, double* xs, double* ys, double* zs, double* partials,
+                           const RunArgs& a, unsigned char* trace, int cap) {
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
+    const int tmask = T - 1;  // T is a power of two
+    const bool lead = (tid == 0);
+    const PairGeom g = make_geom(P);
+    // Counters, running energies and accumulators live in shared memory and are touched by thread 0
+    // only; n, dr and the decision itself are replicated in every thread's registers.
+    mcpm_chain_stats& st = S.st;
+
+    int n = st.n;
+    double dr = st.dr;
+    unsigned long long step = st.steps_done;
+    int overflow = 0;
+    const double wsum = (double)(P.n_disp + P.n_vol + P.n_swap);
+    const double thr_disp = (double)P.n_disp, thr_vol = (double)(P.n_disp + P.n_vol);
+    const double temp = P.T, eps4 = P.eps4, zzV = P.zzV;
+    Fwd fwd; fwd.slot = -1; fwd.x = fwd.y = fwd.z = 0.0;
+    int parity = 0;
+
+    for (int set = a.first_set; set < a.first_set + a.n_sets && !overflow; set++) {
+        // MC::ResetStats, src/MC.cpp:81-98 (nDisplacements and nSwaps restart at ONE)
+        int acceptance = 0, n_disp = 1;   // replicated: they drive AdjustMCMoves
+        if (lead) { st.acceptance = st.rejection = 0; st.n_displacements = 1; st.accept_swap = st.reject_swap = 0; st.n_swaps = 1; }
+        const bool production = set > P.n_equil;
+        for (long long s = 0; s < a.steps_per_set; s++) {
+            rng.begin_step(step, lane);
+            step++;
+            int code;
+            Fwd nf = fwd;  // stays valid across steps that execute no barrier
+            const double r = rng.draw() * wsum;                                   // src/main.cpp:67
+            if (r <= thr_disp) {
+                // ---------------- MoveParticle, src/moves.cpp:118-186 ----------------
+                (void)rng.draw();                                                 // box selection draw
+                (void)rng.draw();                                                 // species selection draw
+                n_disp++;
+                const int i = (int)(rng.draw() * (double)n);                      // int(u*n)+1 on 1-based slots; n==0 -> stale slot (Q12)
+                double xo, yo, zo;
+                load_slot(xs, ys, zs, i, fwd, xo, yo, zo);
+                double xn = __dadd_rn(xo, __dmul_rn(rng.draw() - 0.5, dr));
+                double yn = __dadd_rn(yo, __dmul_rn(rng.draw() - 0.5, dr));
+                double zn = __dadd_rn(zo, __dmul_rn(rng.draw() - 0.5, dr));
+                if (P.pbc[0]) xn = wrap_floor(xn, P.L[0]);                        // MC::PBC
+                if (P.pbc[1]) yn = wrap_floor(yn, P.L[1]);
+                if (P.pbc[2]) zn = wrap_floor(zn, P.L[2]);
+                double v[2];
+                pair_sum2<FAST>(xs, ys, zs, n, i, g, xo, yo, zo, xn, yn, zn, tid, T, v[0], v[1]);
+                double wo, wn;
+                wall_two(P, zo, zn, wo, wn, lane);
+                cta_allsum<2>(v, partials, parity, W, warp, lane); parity ^= 1;
+                nf.slot = -1;
+                const double po = eps4 * v[0], pn = eps4 * v[1];
+                const double e_old = po + wo, e_new = pn + wn;
+                const double arg = (e_new - e_old) / temp;
+                const bool acc = rng.draw() < exp(-arg);
+                if (acc) {
+                    acceptance++;
+                    if ((i & tmask) == tid) { xs[i] = xn; ys[i] = yn; zs[i] = zn; }
+                    nf.slot = i; nf.x = xn; nf.y = yn; nf.z = zn;
+                }
+                if (lead) {
+                    st.n_displacements++; st.tot_disp++; st.pair_evals += 2ull * (unsigned long long)n;
+                    if (acc) {
+                        st.acceptance++; st.tot_disp_acc++;
+                        const double dp = pn - po, dw = wn - wo;
+                        // exact bookkeeping: the halved box total moves by the FULL dp (i's own term plus every
+                        // partner's); the reference's 0.5*dp (src/moves.cpp:178,313,334) is quirk Q16
+                        st.pair += dp; st.wall += dw; st.energy += dp + dw;
+                    } else st.rejection++;
+                }
+                code = acc ? 1 : 0;
+            } else if (r <= thr_vol) {
+                code = (4 << 1);  // volume moves are out of scope (n_vol is rejected by the host API)
+            } else {
+                // ---------------- SwapParticle, single box, src/moves.cpp:284-341 ----------------
+                (void)rng.draw();                                                 // species selection draw
+                if (rng.draw() < 0.5) {
+                    if (n >= cap) { overflow = 1; break; }
+                    const double xi = rng.draw() * P.L[0];                        // InsertParticle, src/moves.cpp:46-54
+                    const double yi = rng.draw() * P.L[1];
+                    const double zi = rng.draw() * P.L[2];
+                    // the trial position is written to the first free slot even if rejected (src/moves.cpp:302-303)
+                    if ((n & tmask) == tid) { xs[n] = xi; ys[n] = yi; zs[n] = zi; }
+                    double v[1];
+                    v[0] = pair_sum1<FAST>(xs, ys, zs, n, -1, g, xi, yi, zi, tid, T);
+                    double wi, wdummy;
+                    wall_two(P, zi, zi, wi, wdummy, lane);
+                    cta_allsum<1>(v, partials, parity, W, warp, lane); parity ^= 1;
+                    nf.slot = -1;
+                    const double pi_ = eps4 * v[0];
+                    const double e_in = pi_ + wi;
+                    const double arg = zzV * exp(-e_in / temp) / (double)(n + 1);
+                    const bool acc = rng.draw() < arg;
+                    if (lead) {
+                        st.n_swaps++; st.tot_ins++; st.pair_evals += (unsigned long long)n;
+                        if (acc) {
+                            st.accept_swap++; st.tot_ins_acc++;
+                            st.pair += pi_; st.wall += wi; st.energy += pi_ + wi;
+                        } else st.reject_swap++;
+                    }
+                    if (acc) n++;
+                    code = (1 << 1) | (acc ? 1 : 0);
+                } else if (n > 0) {
+                    const int o = (int)(rng.draw() * (double)n + 1.0) - 1;        // int(u*n+1) on 1-based slots
+                    double xo, yo, zo, xl, yl, zl;
+                    load_slot(xs, ys, zs, o, fwd, xo, yo, zo);
+                    load_slot(xs, ys, zs, n - 1, fwd, xl, yl, zl);                // the particle that would fill the hole
+                    double v[1];
+                    v[0] = pair_sum1<FAST>(xs, ys, zs, n, o, g, xo, yo, zo, tid, T);
+                    double wo, wdummy;
+                    wall_two(P, zo, zo, wo, wdummy, lane);
+                    cta_allsum<1>(v, partials, parity, W, warp, lane); parity ^= 1;
+                    nf.slot = -1;
+                    const double po = eps4 * v[0];
+                    const double e_out = po + wo;
+                    const double arg = (double)n * exp(e_out / temp) / zzV;
+                    const bool acc = rng.draw() < arg;
+                    if (lead) {
+                        st.n_swaps++; st.tot_del++; st.pair_evals += (unsigned long long)n;
+                        if (acc) {
+                            st.accept_swap++; st.tot_del_acc++;
+                            st.pair -= po; st.wall -= wo; st.energy -= po + wo;   // exact bookkeeping (quirks Q3, Q16 fixed)
+                        } else st.reject_swap++;
+                    }
+                    if (acc) {
+                        if ((o & tmask) == tid) { xs[o] = xl; ys[o] = yl; zs[o] = zl; }  // swap-with-last, src/moves.cpp:329
+                        nf.slot = o; nf.x = xl; nf.y = yl; nf.z = zl;
+                        n--;
+                    }
+                    code = (2 << 1) | (acc ? 1 : 0);
+                } else {
+                    if (lead) st.tot_empty++;
+                    code = (3 << 1);
+                }
+            }
+            fwd = nf;
+            if (lead) {
+                if (trace) trace[(unsigned long long)(set - a.first_set) * (unsigned long long)a.steps_per_set + (unsigned long long)s] = (unsigned char)code;
+                if (production) {
+                    const double dn = (double)n, e = st.energy;
+                    st.sum_n += dn; st.sum_n2 += dn * dn; st.sum_e += e; st.sum_e2 += e * e;
+                    st.samples++;
+                }
+            }
+        }
+        // MC::AdjustMCMoves displacement part, src/moves.cpp:68-78
+        if (!overflow && n > 0 && set <= P.n_equil) {
+            const double ratio = (double)acceptance * 1. / (1. * (double)n_disp);
+            if (ratio < 0.2) dr /= 1.1;
+            else dr *= 1.1;
+        }
+    }
+    __syncthreads();
+
+    double c_pair = 0.0, c_wall = 0.0;
+    if (a.check_energy) cta_box_energy<FAST>(xs, ys, zs, n, P, g, partials, W, warp, lane, tid, T, c_pair, c_wall);
+
+    if (lead) {
+        st.n = n; st.overflow = overflow; st.dr = dr; st.steps_done = step;
+        if (a.check_energy) { st.pair_check = c_pair; st.wall_check = c_wall; st.energy_check = c_pair + c_wall; }
+        S.replay_pos = rng.cursor();
+    }
+}
+
+template <int RNG_MODE, int MAXT>
+__global__ void __launch_bounds__(MAXT) k2_chains(const ChainParams* __restrict__ params, ChainState* __restrict__ states,
+                                                  const int* __restrict__ order, double* __restrict__ X, double* __restrict__ Y,
+                                                  double* __restrict__ Z, RunArgs a) {
+    extern __shared__ double smem[];
+    const int chain = order[blockIdx.x];
+    const int cap = a.cap;
+    double* xs = smem;
+    double* ys = xs + cap;
+    double* zs = ys + cap;
+    double* partials = zs + cap;  // 2 parities x 32 warps x 2 values
+    __shared__ ChainParams P;
+    __shared__ ChainState S;
+    const int tid = threadIdx.x, T = blockDim.x;
+    if (tid == 0) { P = params[chain]; S = states[chain]; }
+    __syncthreads();
+    const size_t off = (size_t)chain * (size_t)cap;
+    // stage every slot (not only the n live ones): stale slots are observable through quirk Q12
+    for (int j = tid; j < cap; j += T) { xs[j] = X[off + j]; ys[j] = Y[off + j]; zs[j] = Z[off + j]; }
+    __syncthreads();
+
+    unsigned char* trace = a.trace ? a.trace + (unsigned long long)chain * a.trace_stride : nullptr;
+    if (RNG_MODE == MCPM_RNG_PHILOX) {
+        PhiloxSource rng; rng.init(a.seed, (uint32_t)chain);
+        if (S.fast_image) chain_loop<PhiloxSource, true>(P, S, rng, xs, ys, zs, partials, a, trace, cap);
+        else chain_loop<PhiloxSource, false>(P, S, rng, xs, ys, zs, partials, a, trace, cap);
+    } else {
+        ReplaySource rng; rng.init(a.replay_u + (unsigned long long)chain * a.replay_stride, 0ull, a.replay_stride);
+        if (S.fast_image) chain_loop<ReplaySource, true>(P, S, rng, xs, ys, zs, partials, a, trace, cap);
+        else chain_loop<ReplaySource, false>(P, S, rng, xs, ys, zs, partials, a, trace, cap);
+    }
+    __syncthreads();
+    for (int j = tid; j < cap; j += T) { X[off + j] = xs[j]; Y[off + j] = ys[j]; Z[off + j] = zs[j]; }
+    if (tid == 0) states[chain] = S;
+}
+
+// ================================================================================================
+// K1 — single-particle energy (MC::EnergyOfParticle, src/energy.cpp:43-105).
+// Evaluates up to two positions against all n stored particles in ONE pass over j:
+//   A = stored particle `index` (if index >= 0), B = trial position (if has_trial).
+// grid.x CTAs each take a contiguous slice of j; partial sums go to scratch and the last CTA to
+// finish adds them in CTA order (deterministic) and writes out[8] = {pairA,0,wallA,EA, pairB,0,wallB,EB}.
+// ================================================================================================
+template <bool FAST>
+__global__ void __launch_bounds__(256) k1_particle_energy(const ChainParams* __restrict__ params, const ChainState* __restrict__ states,
+                                                          const double* __restrict__ X, const double* __restrict__ Y, const double* __restrict__ Z,
+                                                          int chain, int cap, int index, int has_trial, double tx, double ty, double tz,
+                                                          double* __restrict__ scratch, unsigned int* __restrict__ counter, double* __restrict__ out) {
+    __shared__ ChainParams P;
+    __shared__ double red[2][8];
+    __shared__ bool last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) P = params[chain];
+    __syncthreads();
+    const PairGeom g = make_geom(P);
+    const int n = states[chain].st.n;
+    const size_t off = (size_t)chain * (size_t)cap;
+    const double* xs = X + off; const double* ys = Y + off; const double* zs = Z + off;
+    double xa = 0, ya = 0, za = 0;
+    if (index >= 0) { xa = xs[index]; ya = ys[index]; za = zs[index]; }
+    if (!has_trial) { tx = xa; ty = ya; tz = za; }
+    double sa = 0.0, sb = 0.0;
+    for (int j = blockIdx.x * blockDim.x + tid; j < n; j += gridDim.x * blockDim.x) {
+        double xj = xs[j], yj = ys[j], zj = zs[j];
+        bool ns = (j != index);
+        sa += pair_masked(dist2<FAST>(g, xa, ya, za, xj, yj, zj), g, ns);
+        sb += pair_masked(dist2<FAST>(g, tx, ty, tz, xj, yj, zj), g, ns);
+    }
+    sa = warp_allsum(sa); sb = warp_allsum(sb);
+    if (lane == 0) { red[0][warp] = sa; red[1][warp] = sb; }
+    __syncthreads();
+    if (tid == 0) {
+        double ta = 0, tb = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { ta += red[0][w]; tb += red[1][w]; }
+        scratch[2 * blockIdx.x] = ta; scratch[2 * blockIdx.x + 1] = tb;
+        __threadfence();
+        last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && warp == 0) {
+        __threadfence();
+        double ta = 0, tb = 0;
+        if (lane == 0) {
+            for (unsigned b = 0; b < gridDim.x; b++) { ta += ((volatile double*)scratch)[2 * b]; tb += ((volatile double*)scratch)[2 * b + 1]; }
+        }
+        double wa, wb;
+        wall_two(P, za, tz, wa, wb, lane);
+        if (lane == 0) {
+            double pa = P.eps4 * ta, pb = P.eps4 * tb;
+            if (index < 0) { pa = 0; wa = 0; }
+            out[0] = pa; out[1] = 0.0; out[2] = wa; out[3] = pa + wa;
+            out[4] = pb; out[5] = 0.0; out[6] = wb; out[7] = pb + wb;
+            *counter = 0u;
+        }
+    }
+}
+
+// ================================================================================================
+// K3 — full box energy (MC::BoxEnergy, src/energy.cpp:106-124).
+// grid = (i-tiles, chains).  Thread t of a CTA owns particle i = tile*blockDim + t in registers and
+// streams all j through shared-memory tiles (every thread reads the same j: smem broadcast).
+// Per-particle pairPotE / boxE are written out as BoxEnergy leaves them in the particle records;
+// CTA partial sums go to scratch, the last CTA of each chain adds them in tile order.
+// ================================================================================================
+#define K3_TILE 512
+template <bool FAST>
+__global__ void __launch_bounds__(128) k3_box_energy(const ChainParams* __restrict__ params, ChainState* __restrict__ states,
+                                                     const double* __restrict__ X, const double* __restrict__ Y, const double* __restrict__ Z,
+                                                     int cap, int chain0, double* __restrict__ per_pair, double* __restrict__ per_wall,
+                                                     double* __restrict__ scratch, unsigned int* __restrict__ counters, double* __restrict__ out,
+                                                     int want_fast) {
+    __shared__ ChainParams P;
+    __shared__ double tx[K3_TILE], ty[K3_TILE], tz[K3_TILE];
+    __shared__ double red[2][4];
+    __shared__ bool last;
+    const int chain = chain0 + blockIdx.y;
+    if (states[chain].fast_image != want_fast) return;   // the other instantiation handles this chain
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) P = params[chain];
+    __syncthreads();
+    const PairGeom g = make_geom(P);
+    const int n = states[chain].st.n;
+    const int tiles = (n + blockDim.x - 1) / blockDim.x;
+    const size_t off = (size_t)chain * (size_t)cap;
+    const double* xs = X + off; const double* ys = Y + off; const double* zs = Z + off;
+    double* sc = scratch + (size_t)blockIdx.y * 2 * gridDim.x;
+    const int i = blockIdx.x * blockDim.x + tid;
+    const bool live = (i < n) && ((int)blockIdx.x < tiles);
+    double pair_i = 0.0, wall_i = 0.0;
+    if ((int)blockIdx.x < tiles) {
+        double xi = 0, yi = 0, zi = 0;
+        if (live) { xi = xs[i]; yi = ys[i]; zi = zs[i]; }
+        double s0 = 0.0, s1 = 0.0;
+        for (int j0 = 0; j0 < n; j0 += K3_TILE) {
+            const int m = min(K3_TILE, n - j0);
+            __syncthreads();
+            for (int k = tid; k < m; k += blockDim.x) { tx[k] = xs[j0 + k]; ty[k] = ys[j0 + k]; tz[k] = zs[j0 + k]; }
+            __syncthreads();
+            int k = 0;
+            for (; k + 1 < m; k += 2) {
+                s0 += pair_masked(dist2<FAST>(g, xi, yi, zi, tx[k], ty[k], tz[k]), g, (j0 + k) != i);
+                s1 += pair_masked(dist2<FAST>(g, xi, yi, zi, tx[k + 1], ty[k + 1], tz[k + 1]), g, (j0 + k + 1) != i);
+            }
+            if (k < m) s0 += pair_masked(dist2<FAST>(g, xi, yi, zi, tx[k], ty[k], tz[k]), g, (j0 + k) != i);
+        }
+        if (live) {
+            pair_i = P.eps4 * (s0 + s1);
+            wall_i = wall_one(P, zi);
+            if (per_pair) per_pair[(size_t)blockIdx.y * cap + i] = pair_i;
+            if (per_wall) per_wall[(size_t)blockIdx.y * cap + i] = wall_i;
+        }
+    }
+    double sp = warp_allsum(live ? pair_i : 0.0), sw = warp_allsum(live ? wall_i : 0.0);
+    if (lane == 0) { red[0][warp] = sp; red[1][warp] = sw; }
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0, b = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { a += red[0][w]; b += red[1][w]; }
+        sc[2 * blockIdx.x] = a; sc[2 * blockIdx.x + 1] = b;
+        __threadfence();
+        last = (atomicAdd(&counters[blockIdx.y], 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && tid == 0) {
+        __threadfence();
+        double a = 0, b = 0;
+        for (unsigned t = 0; t < gridDim.x; t++) { a += ((volatile double*)sc)[2 * t]; b += ((volatile double*)sc)[2 * t + 1]; }
+        double* o = out + 4 * (size_t)blockIdx.y;
+        const double ph = 0.5 * a;                       // box.pairPotE += 0.5*pairPotE, src/energy.cpp:120
+        o[0] = ph; o[1] = 0.0; o[2] = b; o[3] = ph + b;
+        mcpm_chain_stats& st = states[chain].st;         // BoxEnergy also resets the running box energies
+        st.pair = ph; st.wall = b; st.energy = ph + b;
+        st.pair_check = ph; st.wall_check = b; st.energy_check = ph + b;
+        counters[blockIdx.y] = 0u;
+    }
+}
+
+// ================================================================================================
+__global__ void fp64_peak_kernel(double* out, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.9999999, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+__global__ void philox_fill_kernel(unsigned long long seed, unsigned int chain, unsigned long long first_step, int n_steps, double* out) {
+    const int lane = threadIdx.x & 31;
+    PhiloxSource rng; rng.init(seed, chain);
+    for (int s = 0; s < n_steps; s++) {
+        rng.begin_step(first_step + (unsigned long long)s, lane);
+        for (int k = 0; k < 8; k++) {
+            double v = rng.draw();
+            if (lane == (s & 31)) out[(size_t)s * 8 + k] = v;
+        }
+    }
+}
+
+// ================================================================================================
+// launchers
+// ================================================================================================
+static size_t k2_smem_bytes(int cap) { return (size_t)(3 * cap + 128) * sizeof(double); }
+
+cudaError_t launch_k2(int rng_mode, int n_chains, int threads, const ChainParams* params, ChainState* states, const int* order,
+                      double* X, double* Y, double* Z, const RunArgs& a, cudaStream_t stream) {
+    size_t smem = k2_smem_bytes(a.cap);
+    cudaError_t err;
+    auto go = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<n_chains, threads, smem, stream>>>(params, states, order, X, Y, Z, a);
+        return cudaSuccess;
+    };
+    if (rng_mode == MCPM_RNG_PHILOX) err = threads <= 256 ? go(k2_chains<MCPM_RNG_PHILOX, 256>) : go(k2_chains<MCPM_RNG_PHILOX, 1024>);
+    else err = threads <= 256 ? go(k2_chains<MCPM_RNG_REPLAY, 256>) : go(k2_chains<MCPM_RNG_REPLAY, 1024>);
+    if (err != cudaSuccess) return err;
+    return cudaGetLastError();
+}
+
+size_t k2_smem_limit_cap(int max_smem_optin) { return ((size_t)max_smem_optin / sizeof(double) - 128 - 64) / 3; }
+
+cudaError_t launch_k1(bool fast, int blocks, const ChainParams* params, const ChainState* states, const double* X, const double* Y,
+                      const double* Z, int chain, int cap, int index, int has_trial, const double* t, double* scratch,
+                      unsigned int* counter, double* out, cudaStream_t stream) {
+    double tx = t ? t[0] : 0, ty = t ? t[1] : 0, tz = t ? t[2] : 0;
+    if (fast) k1_particle_energy<true><<<blocks, 256, 0, stream>>>(params, states, X, Y, Z, chain, cap, index, has_trial, tx, ty, tz, scratch, counter, out);
+    else k1_particle_energy<false><<<blocks, 256, 0, stream>>>(params, states, X, Y, Z, chain, cap, index, has_trial, tx, ty, tz, scratch, counter, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_k3(int tiles, int n_chains, int chain0, const ChainParams* params, ChainState* states, const double* X, const double* Y,
+                      const double* Z, int cap, double* per_pair, double* per_wall, double* scratch, unsigned int* counters, double* out,
+                      cudaStream_t stream) {
+    dim3 grid(tiles, n_chains);
+    // two instantiations (fast / general minimum image); each CTA exits at once if the chain is the other kind
+    k3_box_energy<true><<<grid, 128, 0, stream>>>(params, states, X, Y, Z, cap, chain0, per_pair, per_wall, scratch, counters, out, 1);
+    k3_box_energy<false><<<grid, 128, 0, stream>>>(params, states, X, Y, Z, cap, chain0, per_pair, per_wall, scratch, counters, out, 0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fp64_peak(double* out, int blocks, int threads, int iters, cudaStream_t stream) {
+    fp64_peak_kernel<<<blocks, threads, 0, stream>>>(out, iters, 1.0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_philox_fill(unsigned long long seed, unsigned int chain, unsigned long long first_step, int n_steps, double* out,
+                               cudaStream_t stream) {
+    philox_fill_kernel<<<1, 32, 0, stream>>>(seed, chain, first_step, n_steps, out);
+    return cudaGetLastError();
+}
+
+}  // namespace mcpm

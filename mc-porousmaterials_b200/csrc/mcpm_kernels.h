@@ -1,0 +1,25 @@
+// Host-callable launchers of the kernels in mcpm_kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "mcpm_types.h"
+
+namespace mcpm {
+
+cudaError_t launch_k2(int rng_mode, int n_chains, int threads, const ChainParams* params, ChainState* states, const int* order,
+                      double* X, double* Y, double* Z, const RunArgs& a, cudaStream_t stream);
+size_t k2_smem_limit_cap(int max_smem_optin);
+
+cudaError_t launch_k1(bool fast, int blocks, const ChainParams* params, const ChainState* states, const double* X, const double* Y,
+                      const double* Z, int chain, int cap, int index, int has_trial, const double* trial, double* scratch,
+                      unsigned int* counter, double* out, cudaStream_t stream);
+
+cudaError_t launch_k3(int tiles, int n_chains, int chain0, const ChainParams* params, ChainState* states, const double* X, const double* Y,
+                      const double* Z, int cap, double* per_pair, double* per_wall, double* scratch, unsigned int* counters, double* out,
+                      cudaStream_t stream);
+
+cudaError_t launch_fp64_peak(double* out, int blocks, int threads, int iters, cudaStream_t stream);
+cudaError_t launch_philox_fill(unsigned long long seed, unsigned int chain, unsigned long long first_step, int n_steps, double* out,
+                               cudaStream_t stream);
+
+}  // namespace mcpm

@@ -1,0 +1,42 @@
+// Device-resident per-chain records shared by the host API (mcpm_api.cu) and the kernels.
+#pragma once
+#include "../../include/mcpm.h"
+
+// Immutable during a run: what the reference keeps in Box / Fluid / ThermodynamicSystem
+// (src/MC.h:62-85) for one box and one species, pre-digested for the kernels.
+struct ChainParams {
+    double L[3];          // Box::width
+    double invL[3];
+    double halfH;         // 0.5*width[2]           (sizeR, src/potentials.cpp:384)
+    double sqr_pore_r;    // width[2]^2*0.25         (src/energy.cpp:53)
+    double T;             // ThermodynamicSystem::temp
+    double sig2;          // sigma_ff^2
+    double eps4;          // 4*epsilon_ff
+    double rc2;           // rcut^2
+    double zzV;           // zz*volume, zz = exp(mu/T)/Lambda^3 (src/moves.cpp:296-298)
+    double wall_pref;     // 4*pi*eps_sf*rho_s*sig_sf^2 (src/potentials.cpp:400)
+    double sig_sf, delta;
+    int geometry, wall_kind, n_layers;
+    int pbc[3];
+    int n_disp, n_vol, n_swap, n_equil;
+};
+
+// Mutable chain state; `st` is exactly what mcpm_run reports.
+struct ChainState {
+    mcpm_chain_stats st;
+    int fast_image;                 // all positions lie in [0,L] on periodic axes
+    int energy_valid;               // running box energies were initialised by a full K3 evaluation
+    unsigned long long replay_pos;  // cursor into the replay stream (REPLAY mode)
+};
+
+struct RunArgs {
+    int first_set, n_sets;
+    long long steps_per_set;
+    unsigned long long seed;
+    const double* replay_u;      // device pointer
+    unsigned long long replay_stride;
+    unsigned char* trace;        // device pointer or null
+    unsigned long long trace_stride;
+    int check_energy;
+    int cap;
+};

@@ -1,0 +1,138 @@
+"""ctypes declarations of include/mcpm.h (one to one)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+RNG_PHILOX, RNG_REPLAY = 0, 1
+GEOM_BULK, GEOM_SLIT = 0, 1
+WALL_NONE, WALL_SLIT_LJ = 0, 1
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class McpmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"mcpm error {code}: {msg}")
+        self.code = code
+
+
+class SystemDesc(C.Structure):
+    _fields_ = [
+        ("geometry", C.c_int), ("wall_kind", C.c_int), ("n_layers", C.c_int),
+        ("n_disp", C.c_int), ("n_vol", C.c_int), ("n_swap", C.c_int),
+        ("n_equil_sets", C.c_int), ("reserved", C.c_int),
+        ("width", C.c_double * 3), ("temperature", C.c_double),
+        ("eps_ff", C.c_double), ("sig_ff", C.c_double), ("rcut", C.c_double),
+        ("molar_mass", C.c_double), ("mu", C.c_double),
+        ("eps_sf", C.c_double), ("sig_sf", C.c_double), ("rho_s", C.c_double), ("delta", C.c_double),
+        ("dr", C.c_double),
+    ]
+
+    @classmethod
+    def from_any(cls, other) -> "SystemDesc":
+        """Copy from any ctypes structure with the same field layout (e.g. the oracle's System)."""
+        if isinstance(other, cls):
+            return other
+        assert C.sizeof(other) == C.sizeof(cls)
+        out = cls()
+        C.memmove(C.byref(out), C.byref(other), C.sizeof(cls))
+        return out
+
+
+class ParticleEnergy(C.Structure):
+    _fields_ = [("pair", C.c_double), ("many_body", C.c_double), ("wall", C.c_double), ("energy", C.c_double)]
+
+
+class BoxEnergy(C.Structure):
+    _fields_ = [("pair", C.c_double), ("many_body", C.c_double), ("wall", C.c_double), ("energy", C.c_double)]
+
+
+class RunParams(C.Structure):
+    _fields_ = [
+        ("first_set", C.c_int), ("n_sets", C.c_int), ("steps_per_set", C.c_longlong),
+        ("rng_mode", C.c_int), ("seed", C.c_ulonglong),
+        ("replay_u", _dp), ("replay_stride", C.c_size_t),
+        ("trace", C.POINTER(C.c_ubyte)),
+        ("threads_per_chain", C.c_int), ("check_energy", C.c_int),
+    ]
+
+
+class ChainStats(C.Structure):
+    _fields_ = [
+        ("n", C.c_int), ("overflow", C.c_int), ("dr", C.c_double),
+        ("pair", C.c_double), ("wall", C.c_double), ("energy", C.c_double),
+        ("pair_check", C.c_double), ("wall_check", C.c_double), ("energy_check", C.c_double),
+        ("acceptance", C.c_longlong), ("rejection", C.c_longlong), ("n_displacements", C.c_longlong),
+        ("accept_swap", C.c_longlong), ("reject_swap", C.c_longlong), ("n_swaps", C.c_longlong),
+        ("tot_disp", C.c_longlong), ("tot_disp_acc", C.c_longlong), ("tot_ins", C.c_longlong),
+        ("tot_ins_acc", C.c_longlong), ("tot_del", C.c_longlong), ("tot_del_acc", C.c_longlong),
+        ("tot_empty", C.c_longlong),
+        ("pair_evals", C.c_ulonglong), ("steps_done", C.c_ulonglong),
+        ("sum_n", C.c_double), ("sum_n2", C.c_double), ("sum_e", C.c_double), ("sum_e2", C.c_double),
+        ("samples", C.c_longlong),
+    ]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+def lib_path() -> str:
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "libmcpm.so")
+
+
+_LIB = None
+
+# name -> (restype, argtypes); every symbol include/mcpm.h declares
+PROTOTYPES = {
+    "mcpm_version": (C.c_int, []),
+    "mcpm_last_error": (C.c_char_p, []),
+    "mcpm_device_count": (C.c_int, [_ip]),
+    "mcpm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "mcpm_destroy": (C.c_int, [C.c_void_p]),
+    "mcpm_n_chains": (C.c_int, [C.c_void_p, _ip, _ip]),
+    "mcpm_set_system": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(SystemDesc)]),
+    "mcpm_get_system": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(SystemDesc)]),
+    "mcpm_set_positions": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp]),
+    "mcpm_get_positions": (C.c_int, [C.c_void_p, C.c_int, _ip, _dp, _dp, _dp]),
+    "mcpm_set_positions_all": (C.c_int, [C.c_void_p, _ip, _dp, _dp, _dp]),
+    "mcpm_get_positions_all": (C.c_int, [C.c_void_p, _ip, _dp, _dp, _dp]),
+    "mcpm_particle_energy": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, C.POINTER(ParticleEnergy), C.POINTER(ParticleEnergy)]),
+    "mcpm_box_energy": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(BoxEnergy), _dp, _dp]),
+    "mcpm_box_energy_all": (C.c_int, [C.c_void_p, C.POINTER(BoxEnergy)]),
+    "mcpm_apply_move": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp]),
+    "mcpm_append": (C.c_int, [C.c_void_p, C.c_int, _dp]),
+    "mcpm_remove_swap_last": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "mcpm_run": (C.c_int, [C.c_void_p, C.POINTER(RunParams), C.POINTER(ChainStats)]),
+    "mcpm_get_stats": (C.c_int, [C.c_void_p, C.POINTER(ChainStats)]),
+    "mcpm_reset_accumulators": (C.c_int, [C.c_void_p]),
+    "mcpm_set_dr": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
+    "mcpm_set_step_counter": (C.c_int, [C.c_void_p, C.c_int, C.c_ulonglong]),
+    "mcpm_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "mcpm_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong)]),
+    "mcpm_fp64_peak": (C.c_int, [C.c_int, _dp, _dp]),
+    "mcpm_philox_uniforms": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_uint, C.c_ulonglong, C.c_int, _dp]),
+}
+
+
+def lib():
+    """Load libmcpm.so (built in-tree by __graft_entry__.build()).  Fails loudly if it is missing."""
+    global _LIB
+    if _LIB is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise McpmError(-1, f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                                "— there is no CPU fallback")
+        L = C.CDLL(path)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def check(rc):
+    if rc != 0:
+        raise McpmError(rc, lib().mcpm_last_error().decode(errors="replace"))

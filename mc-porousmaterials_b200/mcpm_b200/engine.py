@@ -1,0 +1,181 @@
+"""Engine: a context of independent chains (state points / replicas) on one GPU, over the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .abi import (BoxEnergy, ChainStats, ParticleEnergy, RunParams, SystemDesc, check, lib, RNG_PHILOX, RNG_REPLAY)
+
+_dp = C.POINTER(C.c_double)
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    check(lib().mcpm_device_count(C.byref(n)))
+    return n.value
+
+
+def fp64_peak_tflops(device: int = 0):
+    t = C.c_double(0); ms = C.c_double(0)
+    check(lib().mcpm_fp64_peak(device, C.byref(t), C.byref(ms)))
+    return t.value, ms.value
+
+
+class Engine:
+    def __init__(self, n_chains: int, capacity: int, device: int = 0):
+        self.L = lib()
+        h = C.c_void_p()
+        check(self.L.mcpm_create(device, n_chains, capacity, C.byref(h)))
+        self.h = h
+        nc = C.c_int(0); cap = C.c_int(0)
+        check(self.L.mcpm_n_chains(self.h, C.byref(nc), C.byref(cap)))
+        self.n_chains, self.capacity, self.device = nc.value, cap.value, device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.mcpm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- systems and positions
+    def set_system(self, desc, chain: int = -1):
+        d = SystemDesc.from_any(desc)
+        check(self.L.mcpm_set_system(self.h, chain, C.byref(d)))
+
+    def get_system(self, chain: int) -> SystemDesc:
+        d = SystemDesc()
+        check(self.L.mcpm_get_system(self.h, chain, C.byref(d)))
+        return d
+
+    def set_positions(self, chain, x, y, z):
+        x = np.ascontiguousarray(x, dtype=np.float64); y = np.ascontiguousarray(y, dtype=np.float64)
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        check(self.L.mcpm_set_positions(self.h, chain, len(x), _p(x), _p(y), _p(z)))
+
+    def get_positions(self, chain):
+        n = C.c_int(0)
+        x = np.zeros(self.capacity); y = np.zeros(self.capacity); z = np.zeros(self.capacity)
+        check(self.L.mcpm_get_positions(self.h, chain, C.byref(n), _p(x), _p(y), _p(z)))
+        return x[:n.value].copy(), y[:n.value].copy(), z[:n.value].copy()
+
+    def set_positions_all(self, n, x, y, z):
+        """n: int32[n_chains]; x,y,z: float64[n_chains, capacity] (may be pinned)."""
+        n = np.ascontiguousarray(n, dtype=np.int32)
+        assert x.shape == (self.n_chains, self.capacity) and x.dtype == np.float64 and x.flags.c_contiguous
+        check(self.L.mcpm_set_positions_all(self.h, n.ctypes.data_as(C.POINTER(C.c_int)), _p(x), _p(y), _p(z)))
+
+    def get_positions_all(self, x=None, y=None, z=None):
+        if x is None:
+            x = np.zeros((self.n_chains, self.capacity)); y = np.zeros_like(x); z = np.zeros_like(x)
+        n = np.zeros(self.n_chains, dtype=np.int32)
+        check(self.L.mcpm_get_positions_all(self.h, n.ctypes.data_as(C.POINTER(C.c_int)), _p(x), _p(y), _p(z)))
+        return n, x, y, z
+
+    # ---- K1 / K3
+    def particle_energy(self, chain, index, trial=None):
+        """-> (cur, moved) arrays {pair, many_body, wall, energy}; see mcpm_particle_energy."""
+        cur = ParticleEnergy(); mv = ParticleEnergy()
+        t = None
+        if trial is not None:
+            t = np.ascontiguousarray(trial, dtype=np.float64)
+        check(self.L.mcpm_particle_energy(self.h, chain, index, _p(t) if t is not None else None, C.byref(cur), C.byref(mv)))
+        f = lambda e: np.array([e.pair, e.many_body, e.wall, e.energy])
+        return f(cur), f(mv)
+
+    def box_energy(self, chain, per_particle=True):
+        out = BoxEnergy()
+        pp = np.zeros(self.capacity); pw = np.zeros(self.capacity)
+        check(self.L.mcpm_box_energy(self.h, chain, C.byref(out), _p(pp) if per_particle else None, _p(pw) if per_particle else None))
+        n = self.stats()[chain].n
+        return np.array([out.pair, out.many_body, out.wall, out.energy]), pp[:n].copy(), pw[:n].copy()
+
+    def box_energy_all(self):
+        arr = (BoxEnergy * self.n_chains)()
+        check(self.L.mcpm_box_energy_all(self.h, arr))
+        return np.array([[e.pair, e.many_body, e.wall, e.energy] for e in arr])
+
+    # ---- state mutation
+    def apply_move(self, chain, index, xyz):
+        t = np.ascontiguousarray(xyz, dtype=np.float64)
+        check(self.L.mcpm_apply_move(self.h, chain, index, _p(t)))
+
+    def append(self, chain, xyz):
+        t = np.ascontiguousarray(xyz, dtype=np.float64)
+        check(self.L.mcpm_append(self.h, chain, _p(t)))
+
+    def remove_swap_last(self, chain, index):
+        check(self.L.mcpm_remove_swap_last(self.h, chain, index))
+
+    # ---- K2
+    def run(self, first_set, n_sets, steps_per_set, seed=0, replay=None, trace=False, threads=0, check_energy=0):
+        """Advance every chain n_sets*steps_per_set trial moves.  replay: float64[n_chains, stride] or None."""
+        p = RunParams()
+        p.first_set, p.n_sets, p.steps_per_set = first_set, n_sets, steps_per_set
+        p.seed = seed
+        p.threads_per_chain = threads
+        p.check_energy = check_energy
+        keep = []
+        if replay is not None:
+            r = np.ascontiguousarray(replay, dtype=np.float64)
+            if r.ndim == 1:
+                r = r.reshape(1, -1)
+            assert r.shape[0] == self.n_chains
+            p.rng_mode = RNG_REPLAY
+            p.replay_u = _p(r); p.replay_stride = r.shape[1]
+            keep.append(r)
+        else:
+            p.rng_mode = RNG_PHILOX
+        tr = None
+        if trace:
+            tr = np.zeros((self.n_chains, n_sets * steps_per_set), dtype=np.uint8)
+            p.trace = tr.ctypes.data_as(C.POINTER(C.c_ubyte))
+        stats = (ChainStats * self.n_chains)()
+        check(self.L.mcpm_run(self.h, C.byref(p), stats))
+        return (stats, tr) if trace else stats
+
+    def stats(self):
+        stats = (ChainStats * self.n_chains)()
+        check(self.L.mcpm_get_stats(self.h, stats))
+        return stats
+
+    def reset_accumulators(self):
+        check(self.L.mcpm_reset_accumulators(self.h))
+
+    def set_dr(self, chain, dr):
+        check(self.L.mcpm_set_dr(self.h, chain, dr))
+
+    def set_step_counter(self, chain, step):
+        check(self.L.mcpm_set_step_counter(self.h, chain, step))
+
+    # ---- measurement
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float(0)
+        check(self.L.mcpm_last_kernel_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self) -> int:
+        n = C.c_ulonglong(0)
+        check(self.L.mcpm_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def philox_uniforms(self, seed, chain, first_step, n_steps):
+        out = np.zeros((n_steps, 8))
+        check(self.L.mcpm_philox_uniforms(self.h, seed, chain, first_step, n_steps, _p(out)))
+        return out

@@ -303,7 +303,9 @@ static int move_particle(orc_chain* c) {
         c->acceptance++; c->tot_disp_acc++;
         double dPair = newPair - oldPair, dWall = newWall - oldWall;
         c->b_pair += 0.5 * dPair; c->b_wall += dWall; c->b_energy += 0. + 0.5 * dPair + dWall;
-        c->e_pair += 0.5 * dPair; c->e_wall += dWall; c->e_energy += 0.5 * dPair + dWall;
+        /* exact: moving i changes pair_i AND every partner's pair_j, so the halved box total moves by the
+         * FULL dPair; the reference's 0.5*dPair (moves.cpp:178) is quirk Q16 */
+        c->e_pair += dPair; c->e_wall += dWall; c->e_energy += dPair + dWall;
         return 1;
     }
     c->rejection++;
@@ -329,7 +331,7 @@ static int swap_particle(orc_chain* c) {
             c->n++;
             double pairE = 0.5 * c->pe_pair[in], wallE = c->pe_wall[in];
             c->b_pair += pairE; c->b_wall += wallE; c->b_energy += 0. + pairE + wallE;
-            c->e_pair += pairE; c->e_wall += wallE; c->e_energy += pairE + wallE;
+            c->e_pair += c->pe_pair[in]; c->e_wall += wallE; c->e_energy += c->pe_pair[in] + wallE; /* full pair term (Q16) */
             return (1 << 1) | 1;
         }
         c->reject_swap++;
@@ -342,7 +344,7 @@ static int swap_particle(orc_chain* c) {
         double arg = c->n * exp(outEnergy / T) / (zz * c->volume);
         if (orc_random(c) < arg) {
             c->accept_swap++; c->tot_swap_acc++;
-            double fPair = 0.5 * c->pe_pair[out], fWall = c->pe_wall[out]; /* fresh, for exact bookkeeping */
+            double fPair = c->pe_pair[out], fWall = c->pe_wall[out]; /* fresh and un-halved, for exact bookkeeping (Q3, Q16) */
             int last = c->n - 1;
             c->x[out] = c->x[last]; c->y[out] = c->y[last]; c->z[out] = c->z[last]; /* :329 swap-with-last */
             c->pe_pair[out] = c->pe_pair[last]; c->pe_wall[out] = c->pe_wall[last]; c->pe_tot[out] = c->pe_tot[last];

@@ -201,7 +201,7 @@ struct Oracle : public MC {
         if (enable) ComputeRDF();
         if (hist) for (int k = 0; k < NBINS; k++) hist[k] = stats.rdf(k);
     }
-    void rdf_reset() { for (int k = 0; k <= NBINS; k++) stats.rdf(k) = 0.; }
+    void rdf_reset() { for (int k = 0; k < NBINS; k++) stats.rdf(k) = 0.; }  // ctor resizes stats.rdf to NBINS (src/MC.cpp:29)
     // ReadInputFile + derived quantities (src/read.cpp:36-172) for parser parity.
     int read_input(const char* path, mcref_system* s, int* n0, char* proj, char* fname, char* bname,
                    double sets[4]) {

@@ -1,0 +1,155 @@
+"""GPU: K2 (batched persistent chains) through the C ABI.
+
+* replay mode: the reference's own mt19937_64 uniform stream -> identical accept/reject sequence,
+  counters, dr adaptation and final configuration as the compiled reference (golden) and the C oracle;
+* Philox mode: the device stream is bit-identical to its host restatement, and a Philox-driven chain
+  follows the oracle fed with the same stream step for step;
+* bookkeeping: running energies equal a full recompute to 1e-10.
+"""
+import numpy as np
+import pytest
+
+from conftest import O, system_from_meta
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+TRACE_CASES = {"c1t": ("c1_trace", "c1"), "lowt": ("low_trace", "c1"), "bulkt": ("bulk_trace", "bulk")}
+
+
+def first_divergence(a, b):
+    d = np.nonzero(a != b)[0]
+    return int(d[0]) if len(d) else -1
+
+
+@pytest.mark.parametrize("threads", [32, 64, 128, 256, 512])
+@pytest.mark.parametrize("name", ["c1t", "lowt", "bulkt"])
+def test_replay_trace_matches_reference_golden(mcpm, golden, name, threads):
+    arrays, meta = golden
+    mkey, start = TRACE_CASES[name]
+    m = meta[mkey]
+    s = system_from_meta(m["system"])
+    n0, sets, sps = m["n0"], m["sets"], m["steps_per_set"]
+    x, y, z = arrays[start + "_x"][:n0], arrays[start + "_y"][:n0], arrays[start + "_z"][:n0]
+    u = O.mt_uniforms(m["seed"], 8 * sets * sps)
+    with mcpm.Engine(1, 1024) as e:
+        e.set_system(s)
+        e.set_positions(0, x, y, z)
+        per_set, traces = [], []
+        pos = 0
+        for k in range(1, sets + 1):       # one call per set so that per-set counters can be compared
+            stats, tr = e.run(k, 1, sps, replay=u[pos:], trace=True, threads=threads, check_energy=1)
+            st = stats[0]
+            # how many uniforms did this set consume?  1 + 7/6/4/2 per step
+            codes = tr[0]
+            mv = codes >> 1
+            acc = codes & 1
+            pos += int(np.sum(np.where(mv == 0, 8, np.where(mv == 1, 7, np.where(mv == 2, 5, 3)))))
+            traces.append(codes)
+            per_set.append([st.n, st.acceptance, st.rejection, st.n_displacements, st.accept_swap, st.reject_swap,
+                            st.n_swaps, st.dr])
+            assert st.energy == pytest.approx(st.energy_check, rel=RTOL)
+            assert st.pair == pytest.approx(st.pair_check, rel=RTOL, abs=1e-9)
+        got = np.concatenate(traces)
+        div = first_divergence(got, arrays[name + "_trace"])
+        assert div == -1, f"first divergence at step {div}"
+        assert np.array_equal(np.array(per_set, dtype=np.float64), arrays[name + "_per_set"])
+        fx, fy, fz = e.get_positions(0)
+        # positions are produced by the same fp64 operations in the same order: bit-identical
+        assert np.array_equal(fx, arrays[name + "_fx"]) and np.array_equal(fy, arrays[name + "_fy"]) and np.array_equal(fz, arrays[name + "_fz"])
+        box, _, _ = e.box_energy(0)
+        assert np.allclose(box, arrays[name + "_fbox"], rtol=RTOL, atol=0)
+
+
+def test_replay_multi_set_single_launch(mcpm, golden):
+    """All sets in ONE launch (dr adaptation on the device) == the per-set golden sequence."""
+    arrays, meta = golden
+    m = meta["c1_trace"]
+    s = system_from_meta(m["system"])
+    sets, sps = m["sets"], m["steps_per_set"]
+    u = O.mt_uniforms(m["seed"], 8 * sets * sps)
+    with mcpm.Engine(1, 1024) as e:
+        e.set_system(s)
+        e.set_positions(0, arrays["c1_x"], arrays["c1_y"], arrays["c1_z"])
+        stats, tr = e.run(1, sets, sps, replay=u, trace=True, threads=128)
+        assert np.array_equal(tr[0], arrays["c1t_trace"])
+        assert stats[0].dr == arrays["c1t_per_set"][-1][7]
+        assert stats[0].n == int(arrays["c1t_per_set"][-1][0])
+
+
+def test_device_philox_stream_is_the_documented_one(mcpm):
+    with mcpm.Engine(1, 32) as e:
+        e.set_system(O.argon_slit())
+        for seed, chain, first in [(0, 0, 0), (12345, 7, 3), (2 ** 40 + 17, 1023, 2 ** 33 + 5)]:
+            got = e.philox_uniforms(seed, chain, first, 40)
+            want = np.array([[O.philox_uniform(seed, chain, first + s, k) for k in range(8)] for s in range(40)])
+            assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("threads", [32, 128])
+def test_philox_chain_follows_oracle(mcpm, golden, threads):
+    """Device Philox + Metropolis on the GPU == the C oracle fed with the same counter-based stream."""
+    arrays, meta = golden
+    s = system_from_meta(meta["c1"]["system"])
+    s.n_equil_sets = 1
+    x, y, z = arrays["c1_x"], arrays["c1_y"], arrays["c1_z"]
+    seed, nchains, sets, sps = 987654321, 3, 2, 1500
+    with mcpm.Engine(nchains, 1024) as e:
+        e.set_system(s)
+        for c in range(nchains):
+            e.set_positions(c, x, y, z)
+        stats, tr = e.run(1, sets, sps, seed=seed, trace=True, threads=threads, check_energy=1)
+        for c in range(nchains):
+            o = O.COracle(s, 1024)
+            o.set_positions(x, y, z)
+            o.box_energy()
+            o.philox(seed, c, 0)
+            otr = o.run_sets(1, sets, sps, 0, True)
+            div = first_divergence(tr[c], otr)
+            assert div == -1, f"chain {c}: first divergence at step {div}"
+            st, ost = stats[c], o.state()
+            assert st.n == ost["n"] and st.dr == ost["dr"]
+            assert st.tot_disp == ost["tot_disp"] and st.tot_disp_acc == ost["tot_disp_acc"]
+            assert st.tot_ins + st.tot_del == ost["tot_swap"]
+            assert st.pair_evals == ost["pair_evals"]
+            assert st.samples == ost["samples"] == sps
+            assert st.sum_n == ost["sum_n"] and st.sum_n2 == ost["sum_n2"]
+            assert st.sum_e == pytest.approx(ost["sum_e"], rel=RTOL)
+            assert st.energy == pytest.approx(ost["exact_energy"], rel=RTOL)
+            assert st.energy == pytest.approx(st.energy_check, rel=RTOL)
+            gx, gy, gz = e.get_positions(c)
+            ox, oy, oz = o.get_positions()
+            assert np.array_equal(gx, ox) and np.array_equal(gy, oy) and np.array_equal(gz, oz)
+        # chains with different ids decorrelate
+        assert not np.array_equal(tr[0], tr[1])
+
+
+def test_philox_stream_independent_of_launch_partitioning(mcpm, golden):
+    arrays, meta = golden
+    s = system_from_meta(meta["c1"]["system"])
+    x, y, z = arrays["c1_x"], arrays["c1_y"], arrays["c1_z"]
+    out = []
+    for split in (1, 3):
+        with mcpm.Engine(1, 1024) as e:
+            e.set_system(s)
+            e.set_positions(0, x, y, z)
+            trs = []
+            for k in range(split):
+                _, tr = e.run(20, 1, 1203 // split, seed=5, trace=True, threads=64)
+                trs.append(tr[0])
+            out.append((np.concatenate(trs), e.get_positions(0)))
+    assert np.array_equal(out[0][0], out[1][0])
+    for a, b in zip(out[0][1], out[1][1]):
+        assert np.array_equal(a, b)
+
+
+def test_capacity_overflow_is_reported(mcpm):
+    s = O.argon_slit(mu=-900.0)
+    rng = np.random.default_rng(1)
+    with mcpm.Engine(1, 32) as e:
+        e.set_system(s)
+        e.set_positions(0, rng.random(30) * 40, rng.random(30) * 40, 3.0 + rng.random(30) * 14)
+        with pytest.raises(mcpm.McpmError) as ei:
+            e.run(1, 1, 20000, seed=1)
+        assert ei.value.code == 3
+        assert e.stats()[0].overflow == 1

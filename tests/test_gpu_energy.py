@@ -1,0 +1,154 @@
+"""GPU: K1 (EnergyOfParticle) and K3 (BoxEnergy) through the C ABI against the CPU oracle and the
+golden vectors of the compiled reference.  Tolerance: 1e-10 relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from conftest import O, rel_err, system_from_meta
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def close(a, b, rtol=RTOL):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return np.all(np.abs(a - b) <= rtol * np.abs(b) + 1e-300)
+
+
+@pytest.mark.parametrize("name", ["c1", "c1raw", "ch4", "bulk"])
+def test_k3_box_energy_golden(mcpm, golden, name):
+    arrays, meta = golden
+    s = system_from_meta(meta[name]["system"])
+    x, y, z = arrays[name + "_x"], arrays[name + "_y"], arrays[name + "_z"]
+    with mcpm.Engine(1, len(x) + 8) as e:
+        e.set_system(s)
+        e.set_positions(0, x, y, z)
+        box, pp, pw = e.box_energy(0)
+    assert close(box, arrays[name + "_box"])
+    assert close(pp, arrays[name + "_pp"])
+    assert close(pw, arrays[name + "_pw"])
+
+
+@pytest.mark.parametrize("name", ["c1", "c1raw", "ch4", "bulk"])
+def test_k1_particle_energy_golden(mcpm, golden, name):
+    arrays, meta = golden
+    s = system_from_meta(meta[name]["system"])
+    x, y, z = arrays[name + "_x"], arrays[name + "_y"], arrays[name + "_z"]
+    with mcpm.Engine(1, len(x) + 8) as e:
+        e.set_system(s)
+        e.set_positions(0, x, y, z)
+        for k, (i, t) in enumerate(zip(arrays[name + "_idx"], arrays[name + "_trials"])):
+            cur, moved = e.particle_energy(0, int(i), t)
+            assert close(cur, arrays[name + "_cur"][k])
+            assert close(moved, arrays[name + "_moved"][k])
+            _, ghost = e.particle_energy(0, -1, t)
+            assert close(ghost, arrays[name + "_ghost"][k])
+            cur2, _ = e.particle_energy(0, int(i))
+            assert np.array_equal(cur2, cur)
+
+
+def test_known_answers(mcpm, golden):
+    _, meta = golden
+    ka = meta["known_answers"]
+    r0 = 2.0 ** (1.0 / 6.0) * 3.405
+    with mcpm.Engine(1, 32) as e:
+        e.set_system(O.argon_slit())
+        e.set_positions(0, [10.0, 10.0 + r0], [10.0, 10.0], [10.0, 10.0])
+        assert e.particle_energy(0, 0)[0][0] == pytest.approx(-119.8, rel=1e-12)
+        for zv, key in ((3.4025, "wall_z_sigma"), (10.0, "wall_z_center"), (20.5, "wall_outside")):
+            e.set_positions(0, [10.0], [10.0], [zv])
+            assert e.particle_energy(0, 0)[0][2] == pytest.approx(ka[key], rel=RTOL)
+            assert e.box_energy(0)[0][2] == pytest.approx(ka[key], rel=RTOL)
+
+
+def random_config(system, n, seed, spill=0.0):
+    rng = np.random.default_rng(seed)
+    w = np.array(system.width)
+    p = rng.random((n, 3)) * w
+    if spill:
+        p[:, :2] += (rng.random((n, 2)) - 0.5) * spill * w[:2]   # lateral coordinates outside [0,L): general minimum image
+    return p[:, 0].copy(), p[:, 1].copy(), p[:, 2].copy()
+
+
+@pytest.mark.parametrize("system,n,seed,spill", [
+    (O.argon_slit(), 1, 1, 0.0),
+    (O.argon_slit(), 2, 2, 0.0),
+    (O.argon_slit(), 33, 3, 0.0),
+    (O.argon_slit(), 700, 4, 0.0),
+    (O.argon_slit(), 500, 5, 6.0),                       # positions up to 3 box lengths away
+    (O.argon_slit(H=9.0, rcut=14.0, T=77.0), 257, 6, 0.0),
+    (O.methane_slit(rcut=46.0), 2500, 7, 0.0),           # multi-tile K3, multi-CTA K1
+    (O.argon_bulk(size=40.0, rcut=12.0), 1300, 8, 0.0),
+    (O.argon_bulk(size=40.0, rcut=12.0), 600, 9, 4.0),
+    (O.make_system(geometry=1, wall_kind=0, n_layers=0, n_disp=1, n_vol=0, n_swap=0, n_equil_sets=0,
+                   width=(30.0, 30.0, 15.0), temperature=100.0, eps_ff=100.0, sig_ff=3.0, rcut=15.0,
+                   molar_mass=40.0, mu=0.0, eps_sf=0.0, sig_sf=0.0, rho_s=0.0, delta=0.0, dr=1.0), 300, 10, 0.0),
+    (O.make_system(geometry=1, wall_kind=1, n_layers=7, n_disp=1, n_vol=0, n_swap=1, n_equil_sets=0,
+                   width=(30.0, 30.0, 25.0), temperature=100.0, eps_ff=100.0, sig_ff=3.0, rcut=15.0,
+                   molar_mass=40.0, mu=-1000.0, eps_sf=50.0, sig_sf=3.2, rho_s=0.38, delta=3.0, dr=1.0), 300, 11, 0.0),
+])
+def test_k1_k3_vs_oracle_random(mcpm, system, n, seed, spill):
+    x, y, z = random_config(system, n, seed, spill)
+    c = O.COracle(system, n + 8)
+    c.set_positions(x, y, z)
+    obox, opp, opw = c.box_energy()
+    rng = np.random.default_rng(seed + 100)
+    with mcpm.Engine(2, n + 8) as e:
+        e.set_system(system)
+        e.set_positions(1, x, y, z)          # chain 1: exercises the chain offset
+        e.set_positions(0, x[:1], y[:1], z[:1])
+        box, pp, pw = e.box_energy(1)
+        assert close(box, obox) and close(pp, opp) and close(pw, opw)
+        allbox = e.box_energy_all()
+        assert close(allbox[1], obox)
+        for _ in range(6):
+            i = int(rng.integers(0, n))
+            t = rng.random(3) * np.array(system.width)
+            if spill:
+                t[:2] += 2.5 * np.array(system.width)[:2]
+            cur, moved = e.particle_energy(1, i, t)
+            assert close(cur, c.particle_energy(i))
+            assert close(moved, c.moved_energy(i, *t))
+            assert close(e.particle_energy(1, -1, t)[1], c.trial_energy(*t))
+
+
+def test_empty_chain_and_bad_arguments(mcpm):
+    s = O.argon_slit()
+    with mcpm.Engine(1, 64) as e:
+        with pytest.raises(mcpm.McpmError):
+            e.set_positions(0, [1.0], [1.0], [1.0])           # no system yet
+        e.set_system(s)
+        e.set_positions(0, [], [], [])
+        box, pp, pw = e.box_energy(0)
+        assert np.all(box == 0.0) and len(pp) == 0
+        _, ghost = e.particle_energy(0, -1, [5.0, 5.0, 10.0])
+        assert ghost[0] == 0.0 and ghost[2] == pytest.approx(O.COracle(s, 8).slit_wall(10.0), rel=RTOL)
+        with pytest.raises(mcpm.McpmError):
+            e.set_positions(0, np.zeros(100), np.zeros(100), np.zeros(100))   # over capacity
+        with pytest.raises(mcpm.McpmError):
+            e.particle_energy(0, 5)
+        bad = O.argon_slit(); bad.n_vol = 1
+        with pytest.raises(mcpm.McpmError):
+            e.set_system(bad)                                   # volume moves are out of scope
+        bad = O.argon_slit(); bad.geometry = 3
+        with pytest.raises(mcpm.McpmError):
+            e.set_system(bad)
+
+
+def test_state_mutation_matches_reference_semantics(mcpm):
+    """append / remove_swap_last / apply_move mirror src/moves.cpp:302-311, :329-332, :163."""
+    s = O.argon_slit()
+    x, y, z = random_config(s, 50, 21)
+    c = O.COracle(s, 128)
+    c.set_positions(x, y, z)
+    with mcpm.Engine(1, 128) as e:
+        e.set_system(s)
+        e.set_positions(0, x, y, z)
+        e.append(0, [1.0, 2.0, 3.0])
+        e.remove_swap_last(0, 7)
+        e.apply_move(0, 3, [4.0, 5.0, 6.0])
+        gx, gy, gz = e.get_positions(0)
+    ex = np.append(x, 1.0); ey = np.append(y, 2.0); ez = np.append(z, 3.0)
+    ex[7], ey[7], ez[7] = ex[-1], ey[-1], ez[-1]
+    ex, ey, ez = ex[:-1], ey[:-1], ez[:-1]
+    ex[3], ey[3], ez[3] = 4.0, 5.0, 6.0
+    assert np.array_equal(gx, ex) and np.array_equal(gy, ey) and np.array_equal(gz, ez)
