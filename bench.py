@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py — GCMC trial moves/s on BASELINE config C2 (40-point Ar adsorption isotherm).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's B200 engine
+    python bench.py --impl reference [--gpus N] ...              # the reference's CPU path, host cores
+
+A "step" is one SET of the reference's step loop (src/main.cpp:63-84): --steps-per-set trial moves
+(translation / insertion / deletion, 1:1 disp:swap) for EVERY chain.  The workload per GPU is the
+40-point isotherm (mu_k = -1800 + k*666/39 K, C1 system otherwise) with --replicas independent replica
+chains per state point, started from the oracle-equilibrated configurations in
+tests/golden/isotherm_c2_start.npz.  State points / replicas shard over ranks with no collective on the
+data path (weak scaling: every rank runs its own full set of chains with its own Philox seed).
+
+Prints ONE JSON line (rank 0).  `value` = trial moves/s with the chain state resident in HBM, timed on
+the device with CUDA events on the engine's stream (max over ranks); `e2e` = the same through the
+C ABI with HOST buffers (pinned): upload all positions, run the set, download positions + statistics,
+every step.  `roofline` is against the FP64 FMA pipe (measured live with a DFMA microbenchmark —
+MEASURED_PEAKS.json carries no fp64 figure); `cpu_baseline` times the compiled reference on the host
+cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "mc-porousmaterials_b200"))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_PAIR_SLIT = 22      # algorithmic fp64 flop per in-cutoff pair evaluation, 2 periodic axes
+BYTES_PER_PAIR = 24          # x,y,z fp64 of partner j
+METRIC = "gcmc_trial_moves_per_s"
+UNIT = "moves/s"
+
+
+def load_start():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "isotherm_c2_start.npz"))
+    mu = g["mu"]
+    pts = [(float(mu[k]), g[f"x{k}"], g[f"y{k}"], g[f"z{k}"], float(g["dr"][k])) for k in range(len(mu))]
+    return pts
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([v.strip() for v in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group(backend="nccl")
+        dist = dist_mod
+    return world, rank, local, dist
+
+
+def allmax(dist, local, v):
+    if dist is None:
+        return v
+    import torch
+    t = torch.tensor([v], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def allsum(dist, local, v):
+    if dist is None:
+        return v
+    import torch
+    t = torch.tensor([v], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def barrier(dist, local):
+    import torch
+    if dist is not None:
+        dist.barrier(device_ids=[local])
+    torch.cuda.synchronize(local)
+
+
+def cpu_points(pts, sysfn):
+    from mcpm_b200 import workloads  # noqa: F401
+    out = []
+    for k, (mu, x, y, z, dr) in enumerate(pts):
+        s = sysfn(mu)
+        d = {name: (list(getattr(s, name)) if name == "width" else getattr(s, name)) for name, _ in s._fields_ if name != "reserved"}
+        out.append((k, d, x, y, z, dr, 5000 + k))
+    return out
+
+
+def run_cpu_sample(pool, pts, steps, correct=1):
+    from mcpm_b200 import workloads
+    points = cpu_points(pts, lambda mu: workloads.argon_slit(mu=mu, n_equil_sets=0))
+    return pool.time_points(points, steps, correct=correct)
+
+
+def reference_arm(args, world, rank):
+    if rank != 0:
+        return
+    from oracle import cpu_baseline
+    pts = load_start()
+    pool = cpu_baseline.CpuPool()
+    t_all = []
+    res = None
+    for it in range(args.warmup + args.steps):
+        res = run_cpu_sample(pool, pts, args.cpu_steps, correct=1)
+        if it >= args.warmup:
+            t_all.append(res)
+    pool.close()
+    total_steps = sum(r["total_steps"] for r in t_all)
+    cpu_seconds = sum(r["cpu_seconds"] for r in t_all)
+    cores = t_all[0]["cores"]
+    value = total_steps * cores / cpu_seconds
+    sample = f"{len(pts)} state points x {args.cpu_steps} steps of the as-shipped loop (MoveParticle/SwapParticle + CorrectEnergy) per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * cpu_seconds / cores / len(t_all), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2 40-point Ar isotherm (mu_k=-1800+k*666/39 K, H=20A, rcut=20A, T=87K, disp:swap=1:1), reference CPU path",
+                   "steps_per_point": args.cpu_steps, "start": "tests/golden/isotherm_c2_start.npz"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": res["kind"], "sample": sample,
+                         "per_core": total_steps / cpu_seconds, "makespan_rate": res["moves_per_s_makespan"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def gpu_arm(args, world, rank, local, dist):
+    import torch
+    import mcpm_b200 as m
+    from mcpm_b200 import workloads
+
+    pts = load_start()
+    P, R, S = len(pts), args.replicas, args.steps_per_set
+    n_chains = P * R
+    cap = int(-(-int(max(len(p[1]) for p in pts) * 1.2 + 64) // 32) * 32)
+    eng = m.Engine(n_chains, cap, device=local)
+    cap = eng.capacity
+    seed = 20240611 + 7919 * rank           # every rank: its own replicas of the isotherm
+    n0 = np.zeros(n_chains, dtype=np.int32)
+    hx = torch.zeros((n_chains, cap), dtype=torch.float64).pin_memory()
+    hy = torch.zeros_like(hx).pin_memory(); hz = torch.zeros_like(hx).pin_memory()
+    X, Y, Z = hx.numpy(), hy.numpy(), hz.numpy()
+    for c in range(n_chains):
+        mu, x, y, z, dr = pts[c % P]
+        eng.set_system(workloads.argon_slit(mu=mu, n_equil_sets=0), c)
+        eng.set_dr(c, dr)
+        n0[c] = len(x)
+        X[c, :len(x)] = x; Y[c, :len(x)] = y; Z[c, :len(x)] = z
+    eng.set_positions_all(n0, X, Y, Z)
+    flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=f"cuda:{local}")
+
+    def one_step(set_index):
+        return eng.run(set_index, 1, S, seed=seed, threads=args.threads, check_energy=0)
+
+    # ---- device-resident timing -------------------------------------------------------------------
+    set_index = 1
+    for _ in range(args.warmup):
+        one_step(set_index); set_index += 1
+    eng.reset_accumulators()
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local)
+    barrier(dist, local)
+    if rank == 0:
+        sampler.start()
+    dev_ms, kern_ms, evals = [], [], []
+    prev_evals = 0
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()                       # L2 flush between timed iterations (256 MiB write > 126 MB L2)
+        torch.cuda.synchronize(local)
+        eng.timer_start()
+        st = one_step(set_index); set_index += 1
+        dev_ms.append(eng.timer_stop())
+        kern_ms.append(eng.last_kernel_ms())
+        tot = sum(int(s.pair_evals) for s in st)
+        evals.append(tot - prev_evals); prev_evals = tot
+    barrier(dist, local)
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.launch_count() - launches0
+    t_dev = allmax(dist, local, sum(dev_ms) * 1e-3)
+    moves_per_rank = float(n_chains) * S * args.steps
+    value = world * moves_per_rank / t_dev
+    evals_all = allsum(dist, local, float(sum(evals)))
+    stats = eng.stats()
+    mean_n = float(np.mean([s.sum_n / max(s.samples, 1) for s in stats])) if stats[0].samples else float(np.mean([s.n for s in stats]))
+
+    # ---- end to end through the C ABI with host buffers ---------------------------------------------
+    nbuf = np.zeros(n_chains, dtype=np.int32)
+    n_host, _, _, _ = eng.get_positions_all(X, Y, Z)
+    nbuf[:] = n_host
+    barrier(dist, local)
+    e2e_s = 0.0
+    for _ in range(args.steps):
+        torch.cuda.synchronize(local)
+        t0 = time.perf_counter()
+        eng.set_positions_all(nbuf, X, Y, Z)                    # H2D: every chain's positions, pinned host memory
+        st = one_step(set_index); set_index += 1              # K2 (+ the K3 initialisation the upload invalidated)
+        n_host, _, _, _ = eng.get_positions_all(X, Y, Z)        # D2H: positions; statistics came back with run()
+        nbuf[:] = n_host
+        e2e_s += time.perf_counter() - t0
+    barrier(dist, local)
+    e2e_s = allmax(dist, local, e2e_s)
+    e2e_value = world * moves_per_rank / e2e_s
+    h2d = 3 * n_chains * cap * 8 + n_chains * (4 + 320)
+    d2h = 3 * n_chains * cap * 8 + n_chains * 320
+
+    if rank != 0:
+        return
+    # ---- roofline (FP64 pipe) -------------------------------------------------------------------
+    peak_tflops, _ = m.fp64_peak_tflops(local)
+    k_ms = float(np.mean(kern_ms))
+    evals_per_launch = float(np.mean(evals))
+    achieved = FLOP_PER_PAIR_SLIT * evals_per_launch / (k_ms * 1e-3) * 1e-12
+    traffic = None
+    summ = os.path.join(ROOT, "profiles", "k2_ncu_summary.json")
+    if os.path.exists(summ):
+        try:
+            traffic = json.load(open(summ)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
+                "traffic": traffic, "kernel": "k2_chains", "kernel_ms": k_ms,
+                "algorithmic": f"{FLOP_PER_PAIR_SLIT} flop x {evals_per_launch:.4g} pair evals per launch",
+                "peak_source": "mcpm_fp64_peak DFMA microbenchmark, measured live (MEASURED_PEAKS.json has no fp64 figure)",
+                "pair_evals_per_s": evals_per_launch / (k_ms * 1e-3),
+                "smem_bytes_per_s": BYTES_PER_PAIR * evals_per_launch / (k_ms * 1e-3)}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2 40-point Ar isotherm (mu_k=-1800+k*666/39 K, H=20A, rcut=20A, T=87K, disp:swap=1:1)",
+                   "state_points": P, "replicas_per_point_per_gpu": R, "chains_per_gpu": n_chains, "steps_per_set": S,
+                   "capacity": cap, "mean_particles": mean_n, "threads_per_chain": args.threads or "auto",
+                   "start": "tests/golden/isotherm_c2_start.npz", "rng": "device Philox4x32-10",
+                   "l2": "256 MiB device write between timed steps (L2 flush)"},
+        "pair_evals_per_s": evals_all / t_dev,
+        "wall_s_timed_region": t_wall,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu:
+        from oracle import cpu_baseline
+        pool = cpu_baseline.CpuPool()
+        res = run_cpu_sample(pool, pts, args.cpu_steps, correct=1)
+        fair = run_cpu_sample(pool, pts, args.cpu_steps, correct=0)
+        pool.close()
+        line["cpu_baseline"] = {
+            "value": res["moves_per_s"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"],
+            "sample": f"{P} state points x {args.cpu_steps} steps each of the as-shipped loop (MoveParticle/SwapParticle + CorrectEnergy), "
+                      f"one reference process per core, perfectly balanced aggregate",
+            "per_core": res["moves_per_s_per_core"], "makespan_rate": res["moves_per_s_makespan"],
+            "without_correctenergy_recompute": fair["moves_per_s"],
+        }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--replicas", type=int, default=32, help="replica chains per state point per GPU")
+    ap.add_argument("--steps-per-set", type=int, default=10000)
+    ap.add_argument("--threads", type=int, default=0, help="threads per chain (0 = engine heuristic)")
+    ap.add_argument("--cpu-steps", type=int, default=4000, help="steps per state point of the CPU sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+        reference_arm(args, world, rank)
+        return
+    world, rank, local, dist = dist_setup(args.gpus)
+    try:
+        gpu_arm(args, world, rank, local, dist)
+    finally:
+        if dist is not None:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

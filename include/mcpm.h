@@ -164,6 +164,10 @@ int mcpm_set_step_counter(mcpm_ctx* ctx, int chain, unsigned long long step);
 /* Device time (CUDA events on the context's stream) and launch count of the last compute call. */
 int mcpm_last_kernel_ms(const mcpm_ctx* ctx, float* ms);
 int mcpm_launch_count(const mcpm_ctx* ctx, unsigned long long* launches);
+/* CUDA-event stopwatch on the context's stream: start records an event, stop records a second one,
+ * waits for it and returns the device time between the two in milliseconds. */
+int mcpm_timer_start(mcpm_ctx* ctx);
+int mcpm_timer_stop(mcpm_ctx* ctx, float* ms);
 /* FP64 FMA microbenchmark on `device`: the roofline denominator for these kernels (TFLOP/s). */
 int mcpm_fp64_peak(int device, double* tflops, double* ms);
 /* The device Philox stream, for tests: uniform of (seed, chain, step, slot). */

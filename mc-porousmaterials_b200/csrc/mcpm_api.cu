@@ -36,7 +36,7 @@ static int fail(int code, const char* fmt, ...) {
 struct mcpm_ctx {
     int device = 0, n_chains = 0, cap = 0, num_sms = 0, max_smem = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
     ChainParams* d_params = nullptr;
     ChainState* d_state = nullptr;
     double *d_x = nullptr, *d_y = nullptr, *d_z = nullptr;
@@ -146,6 +146,8 @@ int mcpm_create(int device, int n_chains, int capacity, mcpm_ctx** out) {
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
+    CU(cudaEventCreate(&c->tm0));
+    CU(cudaEventCreate(&c->tm1));
     const size_t np = (size_t)n_chains * c->cap;
     CU(cudaMalloc(&c->d_params, sizeof(ChainParams) * n_chains));
     CU(cudaMalloc(&c->d_state, sizeof(ChainState) * n_chains));
@@ -188,6 +190,8 @@ int mcpm_destroy(mcpm_ctx* c) {
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->tm0) cudaEventDestroy(c->tm0);
+    if (c->tm1) cudaEventDestroy(c->tm1);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return MCPM_OK;
@@ -552,6 +556,21 @@ int mcpm_last_kernel_ms(const mcpm_ctx* c, float* ms) {
 int mcpm_launch_count(const mcpm_ctx* c, unsigned long long* launches) {
     if (!c || !launches) return fail(MCPM_ERR_ARG, "null argument");
     *launches = c->launches;
+    return MCPM_OK;
+}
+
+int mcpm_timer_start(mcpm_ctx* c) {
+    if (!c) return fail(MCPM_ERR_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventRecord(c->tm0, c->stream));
+    return MCPM_OK;
+}
+int mcpm_timer_stop(mcpm_ctx* c, float* ms) {
+    if (!c || !ms) return fail(MCPM_ERR_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventRecord(c->tm1, c->stream));
+    CU(cudaEventSynchronize(c->tm1));
+    CU(cudaEventElapsedTime(ms, c->tm0, c->tm1));
     return MCPM_OK;
 }
 

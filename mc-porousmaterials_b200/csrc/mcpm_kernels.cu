@@ -176,7 +176,7 @@ __device__ void chain_loop(ChainParams& P, ChainState& S, Source& rng, double* x
                         const double dp = pn - po, dw = wn - wo;
                         // exact bookkeeping: the halved box total moves by the FULL dp (i's own term plus every
                         // partner's); the reference's 0.5*dp (src/moves.cpp:178,313,334) is quirk Q16
-                        st.pair += dp; st.wall += dw; st.energy += dp + dw;
+                        if (n > 0) { st.pair += dp; st.wall += dw; st.energy += dp + dw; }  // n==0: the moved slot is a ghost (Q12)
                     } else st.rejection++;
                 }
                 code = acc ? 1 : 0;

@@ -111,6 +111,8 @@ PROTOTYPES = {
     "mcpm_set_step_counter": (C.c_int, [C.c_void_p, C.c_int, C.c_ulonglong]),
     "mcpm_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "mcpm_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong)]),
+    "mcpm_timer_start": (C.c_int, [C.c_void_p]),
+    "mcpm_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "mcpm_fp64_peak": (C.c_int, [C.c_int, _dp, _dp]),
     "mcpm_philox_uniforms": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_uint, C.c_ulonglong, C.c_int, _dp]),
 }

@@ -175,6 +175,14 @@ class Engine:
         check(self.L.mcpm_launch_count(self.h, C.byref(n)))
         return n.value
 
+    def timer_start(self):
+        check(self.L.mcpm_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float(0)
+        check(self.L.mcpm_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
     def philox_uniforms(self, seed, chain, first_step, n_steps):
         out = np.zeros((n_steps, 8))
         check(self.L.mcpm_philox_uniforms(self.h, seed, chain, first_step, n_steps, _p(out)))

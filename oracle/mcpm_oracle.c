@@ -305,7 +305,7 @@ static int move_particle(orc_chain* c) {
         c->b_pair += 0.5 * dPair; c->b_wall += dWall; c->b_energy += 0. + 0.5 * dPair + dWall;
         /* exact: moving i changes pair_i AND every partner's pair_j, so the halved box total moves by the
          * FULL dPair; the reference's 0.5*dPair (moves.cpp:178) is quirk Q16 */
-        c->e_pair += dPair; c->e_wall += dWall; c->e_energy += dPair + dWall;
+        if (c->n > 0) { c->e_pair += dPair; c->e_wall += dWall; c->e_energy += dPair + dWall; } /* n==0: the moved slot is a ghost (Q12) */
         return 1;
     }
     c->rejection++;
