@@ -87,6 +87,9 @@ static int digest(const mcpm_system_desc& d, ChainParams& P) {
     }
     if (d.n_swap > 0 && !(zz > 0)) return fail(MCPM_ERR_ARG, "swap moves need molar_mass > 0 and a finite activity");
     P.zzV = zz * volume;
+    P.ln_zzV = P.zzV > 0 ? log(P.zzV) : -INFINITY;
+    P.beta = 1.0 / d.temperature;
+    P.wsum = (double)(d.n_disp + d.n_vol + d.n_swap); P.thr_disp = (double)d.n_disp; P.thr_vol = (double)(d.n_disp + d.n_vol);
     P.wall_pref = 4. * M_PI * d.eps_sf * d.rho_s * d.sig_sf * d.sig_sf;  // src/potentials.cpp:400
     P.sig_sf = d.sig_sf; P.delta = d.delta;
     P.geometry = d.geometry; P.wall_kind = d.wall_kind; P.n_layers = d.n_layers;
@@ -443,7 +446,7 @@ static int pick_threads(const mcpm_ctx* c, int maxn) {
 
 int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     if (!c || !p) return fail(MCPM_ERR_ARG, "null argument");
-    if (p->n_sets < 0 || p->steps_per_set < 0) return fail(MCPM_ERR_ARG, "negative set or step count");
+    if (p->n_sets < 0 || p->steps_per_set < 0 || p->steps_per_set > 2000000000LL) return fail(MCPM_ERR_ARG, "set count must be >= 0 and steps_per_set in [0, 2e9]");
     if (p->rng_mode != MCPM_RNG_PHILOX && p->rng_mode != MCPM_RNG_REPLAY) return fail(MCPM_ERR_ARG, "bad rng_mode %d", p->rng_mode);
     if (p->rng_mode == MCPM_RNG_REPLAY && (!p->replay_u || p->replay_stride == 0)) return fail(MCPM_ERR_ARG, "replay mode needs replay_u");
     int threads = p->threads_per_chain;

@@ -13,18 +13,15 @@
 namespace mcpm {
 
 // ------------------------------------------------------------------------------------------------
-// fp64 reciprocal without the slow-path branch of '/': MUFU.RCP64H seed + Newton steps.
-// The seed is good to ~2^-20 or better; one cubic step (error^3) followed by one quadratic step
-// leaves <= 1 ulp.  r2 == 0 gives inf/NaN — callers mask such pairs out.
+// fp64 reciprocal without the slow-path branch of '/': MUFU.RCP64H seed (measured 2^-19.9 relative on
+// B200, scripts/rcp_probe.cu) + ONE cubic Newton step x(1 + e + e^2), e = 1 - a*x: error e^3 ~ 2^-60
+// before rounding; measured worst case 2.2e-16 relative (<= 1 ulp) over r^2 in [1,1024].
+// r2 == 0 gives inf/NaN — callers mask such pairs out.
 __device__ __forceinline__ double fast_rcp(double a) {
     double x;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
     double e = fma(-a, x, 1.0);
-    double e2 = fma(e, e, e);
-    x = fma(x, e2, x);
-    e = fma(-a, x, 1.0);
-    x = fma(x, e, x);
-    return x;
+    return fma(x, fma(e, e, e), x);
 }
 
 // s6*(s6-1) with s6 = (sigma^2/r^2)^3; the factor 4*eps is applied once per sum.
@@ -36,29 +33,33 @@ __device__ __forceinline__ double lj_core(double r2, double sig2) {
 }
 
 struct PairGeom {
-    double Lx, Ly, Lz, invLx, invLy, invLz, rc2, sig2;
-    int pbz;  // z periodic (bulk)
+    double Lx, Ly, Lz;     // FAST: HALF widths; general: full widths
+    double iLx, iLy, iLz;  // general path only: 1/L
+    double rc2, sig2;
 };
 
+template <bool FAST>
 __device__ __forceinline__ PairGeom make_geom(const ChainParams& P) {
     PairGeom g;
-    g.Lx = P.L[0]; g.Ly = P.L[1]; g.Lz = P.L[2];
-    g.invLx = P.invL[0]; g.invLy = P.invL[1]; g.invLz = P.invL[2];
-    g.rc2 = P.rc2; g.sig2 = P.sig2; g.pbz = P.pbc[2];
+    const double f = FAST ? 0.5 : 1.0;
+    g.Lx = f * P.L[0]; g.Ly = f * P.L[1]; g.Lz = f * P.L[2];
+    g.iLx = P.invL[0]; g.iLy = P.invL[1]; g.iLz = P.invL[2];
+    g.rc2 = P.rc2; g.sig2 = P.sig2;
     return g;
 }
 
 // Minimum image, MC::NeighDistance src/potentials.cpp:22-33.
 //  FAST: both positions lie in [0,L] (true for every chain the engine itself advances: insertion
 //        draws u*L and translations are wrapped by floor, src/moves.cpp:46-54, src/energy.cpp:126-130),
-//        so |d| <= L and the nearest image is min(|d|, L-|d|) — 2 fp64 ops instead of 4.
+//        so a = |d| <= L and the nearest image is min(a, L-a) = L/2 - |a - L/2|: two fp64 adds with
+//        |.| operand modifiers, no compare/select.  (a - L/2 is exact for a >= L/4 by Sterbenz; below
+//        that the result carries an absolute error <= ulp(L/2), ~1e-16 relative at contact distance.)
 //  else: d -= rint(d/L)*L for arbitrary coordinates (rint by the 1.5*2^52 trick; differs from the
 //        reference's round() only at exact ties, where both images are at the same distance).
 template <bool FAST>
 __device__ __forceinline__ double image(double d, double L, double invL) {
     if (FAST) {
-        double a = fabs(d);
-        return fmin(a, L - a);
+        return L - fabs(fabs(d) - L);   // L is the HALF width here
     } else {
         const double M = 6755399441055744.0;
         double n = (d * invL + M) - M;
@@ -66,21 +67,30 @@ __device__ __forceinline__ double image(double d, double L, double invL) {
     }
 }
 
-template <bool FAST>
+// PBZ: z is periodic (bulk geometry); in a slit only x and y are (src/read.cpp:146-162).
+template <bool FAST, bool PBZ>
 __device__ __forceinline__ double dist2(const PairGeom& g, double xi, double yi, double zi, double xj, double yj, double zj) {
-    double dx = image<FAST>(xi - xj, g.Lx, g.invLx);
-    double dy = image<FAST>(yi - yj, g.Ly, g.invLy);
+    double dx = image<FAST>(xi - xj, g.Lx, g.iLx);
+    double dy = image<FAST>(yi - yj, g.Ly, g.iLy);
     double dz = zi - zj;
-    if (g.pbz) dz = image<FAST>(dz, g.Lz, g.invLz);
+    if (PBZ) dz = image<FAST>(dz, g.Lz, g.iLz);
     return fma(dz, dz, fma(dy, dy, dx * dx));
 }
 
-// One partner's contribution.  Inclusive cutoff (quirk Q8); r2 == 0 (self, or exactly coincident
-// distinct particles, which the reference skips by position equality, quirk Q7) is masked out.
-__device__ __forceinline__ double pair_masked(double r2, const PairGeom& g, bool not_self) {
-    bool ok = not_self && (r2 <= g.rc2) && (__double_as_longlong(r2) != 0ll);
-    double e = lj_core(r2, g.sig2);
-    return ok ? e : 0.0;
+// Adds partner j's contribution to acc, fully predicated (no branch, no select):
+//   r2 <= rc2   inclusive cutoff (quirk Q8)
+//   hi(r2) != 0 exactly coincident distinct particles, which the reference skips by position equality
+//               (quirk Q7); only the high word is inspected, i.e. r2 < 2^-1022 counts as coincident
+//   j != self   the particle itself
+__device__ __forceinline__ void pair_acc(double& acc, double r2, const PairGeom& g, int j, int self) {
+    const double e = lj_core(r2, g.sig2);
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.le.f64 p, %1, %2;\n\t"
+        "setp.ne.and.s32 p, %3, 0, p;\n\t"
+        "setp.ne.and.s32 p, %4, %5, p;\n\t"
+        "@p add.f64 %0, %0, %6;\n\t}"
+        : "+d"(acc)
+        : "d"(r2), "d"(g.rc2), "r"(__double2hiint(r2)), "r"(j), "r"(self), "d"(e));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -95,7 +105,7 @@ __device__ __forceinline__ void wall_two(const ChainParams& P, double z_a, doubl
             double zc = ((lane & 8) ? z_b : z_a) - P.halfH;
             if (lane & 1) zc = -zc;
             for (int layer = (lane >> 1) & 3; layer < P.n_layers; layer += 4) {
-                double t = P.sig_sf / (P.halfH + layer * P.delta + zc);
+                double t = P.sig_sf * fast_rcp(P.halfH + layer * P.delta + zc);
                 double t2 = t * t, t4 = t2 * t2;
                 acc += 0.2 * (t4 * t4 * t2) - 0.5 * t4;
             }
@@ -121,8 +131,8 @@ __device__ __forceinline__ double wall_one(const ChainParams& P, double z) {
     if (P.wall_kind == MCPM_WALL_SLIT_LJ && P.geometry == MCPM_GEOM_SLIT) {
         double usf = 0.0;
         for (int i = 0; i < P.n_layers; i++) {
-            double ta = P.sig_sf / (P.halfH + i * P.delta + zc);
-            double tb = P.sig_sf / (P.halfH + i * P.delta - zc);
+            double ta = P.sig_sf * fast_rcp(P.halfH + i * P.delta + zc);
+            double tb = P.sig_sf * fast_rcp(P.halfH + i * P.delta - zc);
             double a2 = ta * ta, a4 = a2 * a2, b2 = tb * tb, b4 = b2 * b2;
             usf += 0.2 * (a4 * a4 * a2 + b4 * b4 * b2) - 0.5 * (a4 + b4);
         }
@@ -161,45 +171,42 @@ __device__ __forceinline__ void philox_call(unsigned long long seed, uint32_t ch
 }
 
 // Warp-batched Philox source: every 8 steps each lane evaluates ONE of the 32 calls of the batch
-// (4 calls x 8 steps); draws are fetched by shuffle.  All lanes of all warps hold the same stream,
-// so every thread takes the same Metropolis decision without any broadcast.
+// (4 calls x 8 steps); a step's k-th draw is fetched by shuffle from lane 4*(step%8) + k/2.  All lanes
+// of all warps hold the same stream, so every thread takes the same Metropolis decision without any
+// broadcast.  Draws are addressed by their position k in the step (not consumed sequentially), so a
+// branch can fetch all the uniforms it needs up front, off the critical path.
 struct PhiloxSource {
-    unsigned long long seed;
-    uint32_t chain;
-    double ua, ub;
-    unsigned long long batch;  // step index of the batch start (multiple of 8), ~0 = none
-    int base, slot;
-    __device__ __forceinline__ void init(unsigned long long s, uint32_t c) { seed = s; chain = c; batch = ~0ull; ua = ub = 0.0; base = slot = 0; }
-    __device__ __forceinline__ void begin_step(unsigned long long step, int lane) {
-        unsigned long long b = step & ~7ull;
-        if (b != batch) {
-            batch = b;
-            philox_call(seed, chain, 4ull * b + (unsigned long long)lane, ua, ub);
-        }
+    double ua, ub;   // this lane's call of the current batch
+    int base;
+    __device__ __forceinline__ void init(unsigned long long seed, uint32_t chain, unsigned long long step, int lane) {
+        refill(seed, chain, step & ~7ull, lane);   // a launch may start in the middle of a batch
+        base = 0;
+    }
+    __device__ __forceinline__ void refill(unsigned long long seed, uint32_t chain, unsigned long long batch_step, int lane) {
+        philox_call(seed, chain, 4ull * batch_step + (unsigned long long)lane, ua, ub);
+    }
+    __device__ __forceinline__ void begin_step(unsigned long long seed, uint32_t chain, unsigned long long step, int lane) {
+        if ((step & 7ull) == 0ull) refill(seed, chain, step, lane);
         base = (int)(step & 7ull) * 4;
-        slot = 0;
     }
-    __device__ __forceinline__ double draw() {
-        double v = (slot & 1) ? ub : ua;
-        v = __shfl_sync(MCPM_FULL_MASK, v, base + (slot >> 1));
-        slot++;
-        return v;
+    template <int K>
+    __device__ __forceinline__ double at() const {
+        return __shfl_sync(MCPM_FULL_MASK, (K & 1) ? ub : ua, base + (K >> 1));
     }
+    __device__ __forceinline__ void end_step(int) {}
     __device__ __forceinline__ unsigned long long cursor() const { return 0ull; }
 };
 
 // Replay source: consumes a caller-supplied uniform stream exactly as the reference consumes
-// MC::Random() — sequentially, 1 + 7/6/4/2 draws per step.
+// MC::Random() — sequentially, 1 + 7/6/4/2 draws per step (SURVEY.md §3).
 struct ReplaySource {
     const double* u;
     unsigned long long pos, n;
     __device__ __forceinline__ void init(const double* p, unsigned long long start, unsigned long long len) { u = p; pos = start; n = len; }
-    __device__ __forceinline__ void begin_step(unsigned long long, int) {}
-    __device__ __forceinline__ double draw() {
-        double v = (pos < n) ? __ldg(u + pos) : 0.0;
-        pos++;
-        return v;
-    }
+    __device__ __forceinline__ void begin_step(unsigned long long, uint32_t, unsigned long long, int) {}
+    template <int K>
+    __device__ __forceinline__ double at() const { return (pos + K < n) ? __ldg(u + pos + K) : 0.0; }
+    __device__ __forceinline__ void end_step(int count) { pos += (unsigned long long)count; }
     __device__ __forceinline__ unsigned long long cursor() const { return pos; }
 };
 
@@ -213,7 +220,18 @@ __device__ __forceinline__ double warp_allsum(double v) {
 // MC::PBC, src/energy.cpp:126-130: x -= floor(x/L)*L, without FMA contraction so that the wrapped
 // coordinate is bit-identical to the host reference.
 __device__ __forceinline__ double wrap_floor(double x, double L) {
-    return __dsub_rn(x, __dmul_rn(floor(__ddiv_rn(x, L)), L));
+    // For -L <= x < 2L the quotient floor(x/L) is -1, 0 or 1 and can be read off by comparison
+    // (x/L rounds to < 1 for every double x < L, and to >= 1 for x >= L), so the IEEE division is only
+    // needed when a (never-capped, src/moves.cpp:77) step size has grown beyond the box.
+    double q;
+    if (x >= -L && x < L + L) q = (x < 0.0) ? -1.0 : ((x >= L) ? 1.0 : 0.0);
+    else q = floor(__ddiv_rn(x, L));
+    return __dsub_rn(x, __dmul_rn(q, L));
 }
+
+// ln(u) for the log-domain Metropolis test  ln u < -dE/T  <=>  u < exp(-dE/T).  u == 0 maps to the log of
+// the smallest positive double, so that (like the reference's `u < exp(-arg)` with an underflowed
+// exponential) a move whose Boltzmann factor underflows is never accepted.
+__device__ __forceinline__ double log_uniform(double u) { return (u > 0.0) ? log(u) : -745.1332191019412; }
 
 }  // namespace mcpm

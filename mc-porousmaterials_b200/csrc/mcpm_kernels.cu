@@ -40,40 +40,51 @@ __device__ __forceinline__ void load_slot(const double* xs, const double* ys, co
     else { x = xs[i]; y = ys[i]; z = zs[i]; }
 }
 
-// Partner loops.  `self` is the index excluded as "the particle itself" (-1: none).
-template <bool FAST>
-__device__ __forceinline__ void pair_sum2(const double* xs, const double* ys, const double* zs, int n, int self, const PairGeom& g,
-                                          double xa, double ya, double za, double xb, double yb, double zb,
-                                          int tid, int T, double& ea, double& eb) {
-    double sa = 0.0, sb = 0.0;
-#pragma unroll 2
-    for (int j = tid; j < n; j += T) {
-        double xj = xs[j], yj = ys[j], zj = zs[j];
-        bool ns = (j != self);
-        sa += pair_masked(dist2<FAST>(g, xa, ya, za, xj, yj, zj), g, ns);
-        sb += pair_masked(dist2<FAST>(g, xb, yb, zb, xj, yj, zj), g, ns);
-    }
-    ea = sa; eb = sb;
-}
-template <bool FAST>
-__device__ __forceinline__ double pair_sum1(const double* xs, const double* ys, const double* zs, int n, int self, const PairGeom& g,
-                                            double xa, double ya, double za, int tid, int T) {
-    double s0 = 0.0, s1 = 0.0;
+// Partner loops over the thread's own slots j == tid (mod T).  `self` is the index excluded as "the
+// particle itself" (-1: none).  Independent accumulators give the scheduler 4 dependent chains to
+// interleave (each pair evaluation is a ~17-deep chain of fp64 ops).
+template <bool FAST, bool PBZ>
+__device__ __forceinline__ void pair_sum2(const double* __restrict__ xs, const double* __restrict__ ys, const double* __restrict__ zs,
+                                          int n, int self, const PairGeom& g, double xa, double ya, double za, double xb, double yb,
+                                          double zb, int tid, int T, double& ea, double& eb) {
+    double a0 = 0.0, b0 = 0.0, a1 = 0.0, b1 = 0.0;
     int j = tid;
     for (; j + T < n; j += 2 * T) {
-        s0 += pair_masked(dist2<FAST>(g, xa, ya, za, xs[j], ys[j], zs[j]), g, j != self);
-        s1 += pair_masked(dist2<FAST>(g, xa, ya, za, xs[j + T], ys[j + T], zs[j + T]), g, (j + T) != self);
+        const double x0 = xs[j], y0 = ys[j], z0 = zs[j];
+        const double x1 = xs[j + T], y1 = ys[j + T], z1 = zs[j + T];
+        pair_acc(a0, dist2<FAST, PBZ>(g, xa, ya, za, x0, y0, z0), g, j, self);
+        pair_acc(b0, dist2<FAST, PBZ>(g, xb, yb, zb, x0, y0, z0), g, j, self);
+        pair_acc(a1, dist2<FAST, PBZ>(g, xa, ya, za, x1, y1, z1), g, j + T, self);
+        pair_acc(b1, dist2<FAST, PBZ>(g, xb, yb, zb, x1, y1, z1), g, j + T, self);
     }
-    if (j < n) s0 += pair_masked(dist2<FAST>(g, xa, ya, za, xs[j], ys[j], zs[j]), g, j != self);
-    return s0 + s1;
+    if (j < n) {
+        const double x0 = xs[j], y0 = ys[j], z0 = zs[j];
+        pair_acc(a0, dist2<FAST, PBZ>(g, xa, ya, za, x0, y0, z0), g, j, self);
+        pair_acc(b0, dist2<FAST, PBZ>(g, xb, yb, zb, x0, y0, z0), g, j, self);
+    }
+    ea = a0 + a1; eb = b0 + b1;
+}
+template <bool FAST, bool PBZ>
+__device__ __forceinline__ double pair_sum1(const double* __restrict__ xs, const double* __restrict__ ys, const double* __restrict__ zs,
+                                            int n, int self, const PairGeom& g, double xa, double ya, double za, int tid, int T) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int j = tid;
+    for (; j + 3 * T < n; j += 4 * T) {
+        pair_acc(s0, dist2<FAST, PBZ>(g, xa, ya, za, xs[j], ys[j], zs[j]), g, j, self);
+        pair_acc(s1, dist2<FAST, PBZ>(g, xa, ya, za, xs[j + T], ys[j + T], zs[j + T]), g, j + T, self);
+        pair_acc(s2, dist2<FAST, PBZ>(g, xa, ya, za, xs[j + 2 * T], ys[j + 2 * T], zs[j + 2 * T]), g, j + 2 * T, self);
+        pair_acc(s3, dist2<FAST, PBZ>(g, xa, ya, za, xs[j + 3 * T], ys[j + 3 * T], zs[j + 3 * T]), g, j + 3 * T, self);
+    }
+    for (; j < n; j += T) pair_acc(s0, dist2<FAST, PBZ>(g, xa, ya, za, xs[j], ys[j], zs[j]), g, j, self);
+    return (s0 + s1) + (s2 + s3);
 }
 
 // All-reduce of NV per-thread values over the CTA; every thread returns the same bits.
-template <int NV>
+template <int NV, bool MULTI>
 __device__ __forceinline__ void cta_allsum(double (&v)[NV], double* partials, int parity, int W, int warp, int lane) {
 #pragma unroll
     for (int k = 0; k < NV; k++) v[k] = warp_allsum(v[k]);
-    if (W == 1) { __syncwarp(); return; }
+    if (!MULTI) { __syncwarp(); return; }
     double* p = partials + parity * 64;
     if (lane == 0) {
 #pragma unroll
@@ -90,191 +101,193 @@ __device__ __forceinline__ void cta_allsum(double (&v)[NV], double* partials, in
 
 // Full energy of the chain held in shared memory: per-particle sums as MC::BoxEnergy forms them
 // (src/energy.cpp:106-124; every pair is visited twice and the pair total halved).
-template <bool FAST>
+template <bool FAST, bool PBZ>
 __device__ void cta_box_energy(const double* xs, const double* ys, const double* zs, int n, const ChainParams& P, const PairGeom& g,
                                double* partials, int W, int warp, int lane, int tid, int T, double& pair_half, double& wall) {
     double v[2] = {0.0, 0.0};
     for (int i = tid; i < n; i += T) {
         double xi = xs[i], yi = ys[i], zi = zs[i];
         double s = 0.0;
-        for (int j = 0; j < n; j++) s += pair_masked(dist2<FAST>(g, xi, yi, zi, xs[j], ys[j], zs[j]), g, j != i);
+        for (int j = 0; j < n; j++) pair_acc(s, dist2<FAST, PBZ>(g, xi, yi, zi, xs[j], ys[j], zs[j]), g, j, i);
         v[0] += s;
         v[1] += wall_one(P, zi);
     }
     __syncthreads();
-    cta_allsum<2>(v, partials, 0, W, warp, lane);
+    cta_allsum<2, true>(v, partials, 0, W, warp, lane);
     __syncthreads();
     pair_half = 0.5 * (P.eps4 * v[0]);
     wall = v[1];
 }
 
-template <class Source, bool FAST>
-__device__ void chain_loop(ChainParams& P, ChainState& S, Source& rng, double* xs, double* ys, double* zs, double* partials,
-                           const RunArgs& a, unsigned char* trace, int cap) {
+// Register diet: only what EVERY thread needs on the critical path lives in registers (n, dr, the step
+// counter, the forwarded slot, the lane's Philox batch).  Counters, running energies and accumulators
+// live in shared memory (S.st) and are touched by thread 0 only; system constants are read from the
+// shared ChainParams where they are used.
+template <class Source, bool FAST, bool MULTI, bool PBZ>
+__device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, double* xs, double* ys, double* zs, double* partials,
+                           const RunArgs& a, unsigned char* trace, int cap, uint32_t chain) {
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
     const int tmask = T - 1;  // T is a power of two
     const bool lead = (tid == 0);
-    const PairGeom g = make_geom(P);
-    // Counters, running energies and accumulators live in shared memory and are touched by thread 0
-    // only; n, dr and the decision itself are replicated in every thread's registers.
-    mcpm_chain_stats& st = S.st;
+    const PairGeom g = make_geom<FAST>(P);
+    mcpm_chain_stats& st = S.st;   // shared memory; written by thread 0 only
 
     int n = st.n;
     double dr = st.dr;
     unsigned long long step = st.steps_done;
     int overflow = 0;
-    const double wsum = (double)(P.n_disp + P.n_vol + P.n_swap);
-    const double thr_disp = (double)P.n_disp, thr_vol = (double)(P.n_disp + P.n_vol);
-    const double temp = P.T, eps4 = P.eps4, zzV = P.zzV;
     Fwd fwd; fwd.slot = -1; fwd.x = fwd.y = fwd.z = 0.0;
     int parity = 0;
+    const int steps_per_set = (int)a.steps_per_set;
 
     for (int set = a.first_set; set < a.first_set + a.n_sets && !overflow; set++) {
         // MC::ResetStats, src/MC.cpp:81-98 (nDisplacements and nSwaps restart at ONE)
-        int acceptance = 0, n_disp = 1;   // replicated: they drive AdjustMCMoves
         if (lead) { st.acceptance = st.rejection = 0; st.n_displacements = 1; st.accept_swap = st.reject_swap = 0; st.n_swaps = 1; }
         const bool production = set > P.n_equil;
-        for (long long s = 0; s < a.steps_per_set; s++) {
-            rng.begin_step(step, lane);
+        for (int s = 0; s < steps_per_set; s++) {
+            rng.begin_step(a.seed, chain, step, lane);
             step++;
             int code;
-            Fwd nf = fwd;  // stays valid across steps that execute no barrier
-            const double r = rng.draw() * wsum;                                   // src/main.cpp:67
-            if (r <= thr_disp) {
+            const double r = rng.template at<0>() * P.wsum;                       // src/main.cpp:67
+            if (r <= P.thr_disp) {
                 // ---------------- MoveParticle, src/moves.cpp:118-186 ----------------
-                (void)rng.draw();                                                 // box selection draw
-                (void)rng.draw();                                                 // species selection draw
-                n_disp++;
-                const int i = (int)(rng.draw() * (double)n);                      // int(u*n)+1 on 1-based slots; n==0 -> stale slot (Q12)
+                // draws 1,2 (box, species selection) are consumed but unused: single box, single species
+                const double u_i = rng.template at<3>(), u_x = rng.template at<4>(), u_y = rng.template at<5>(),
+                             u_z = rng.template at<6>(), u_a = rng.template at<7>();
+                rng.end_step(8);
+                const double lnu = log_uniform(u_a);
+                const int i = (int)(u_i * (double)n);                             // int(u*n)+1 on 1-based slots; n==0 -> stale slot (Q12)
                 double xo, yo, zo;
                 load_slot(xs, ys, zs, i, fwd, xo, yo, zo);
-                double xn = __dadd_rn(xo, __dmul_rn(rng.draw() - 0.5, dr));
-                double yn = __dadd_rn(yo, __dmul_rn(rng.draw() - 0.5, dr));
-                double zn = __dadd_rn(zo, __dmul_rn(rng.draw() - 0.5, dr));
-                if (P.pbc[0]) xn = wrap_floor(xn, P.L[0]);                        // MC::PBC
-                if (P.pbc[1]) yn = wrap_floor(yn, P.L[1]);
-                if (P.pbc[2]) zn = wrap_floor(zn, P.L[2]);
+                double xn = wrap_floor(__dadd_rn(xo, __dmul_rn(u_x - 0.5, dr)), P.L[0]);   // MC::PBC: x and y are always periodic
+                double yn = wrap_floor(__dadd_rn(yo, __dmul_rn(u_y - 0.5, dr)), P.L[1]);
+                double zn = __dadd_rn(zo, __dmul_rn(u_z - 0.5, dr));
+                if (PBZ) zn = wrap_floor(zn, P.L[2]);
                 double v[2];
-                pair_sum2<FAST>(xs, ys, zs, n, i, g, xo, yo, zo, xn, yn, zn, tid, T, v[0], v[1]);
+                pair_sum2<FAST, PBZ>(xs, ys, zs, n, i, g, xo, yo, zo, xn, yn, zn, tid, T, v[0], v[1]);
                 double wo, wn;
                 wall_two(P, zo, zn, wo, wn, lane);
-                cta_allsum<2>(v, partials, parity, W, warp, lane); parity ^= 1;
-                nf.slot = -1;
-                const double po = eps4 * v[0], pn = eps4 * v[1];
-                const double e_old = po + wo, e_new = pn + wn;
-                const double arg = (e_new - e_old) / temp;
-                const bool acc = rng.draw() < exp(-arg);
+                cta_allsum<2, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
+                const double po = P.eps4 * v[0], pn = P.eps4 * v[1];
+                const double dE = (pn + wn) - (po + wo);                          // newEnergy - oldEnergy, src/moves.cpp:169
+                const bool acc = lnu < -(dE * P.beta);                            // u < exp(-dE/T), src/moves.cpp:170-172
+                fwd.slot = -1;
                 if (acc) {
-                    acceptance++;
                     if ((i & tmask) == tid) { xs[i] = xn; ys[i] = yn; zs[i] = zn; }
-                    nf.slot = i; nf.x = xn; nf.y = yn; nf.z = zn;
+                    fwd.slot = i; fwd.x = xn; fwd.y = yn; fwd.z = zn;
                 }
                 if (lead) {
                     st.n_displacements++; st.tot_disp++; st.pair_evals += 2ull * (unsigned long long)n;
                     if (acc) {
                         st.acceptance++; st.tot_disp_acc++;
-                        const double dp = pn - po, dw = wn - wo;
-                        // exact bookkeeping: the halved box total moves by the FULL dp (i's own term plus every
-                        // partner's); the reference's 0.5*dp (src/moves.cpp:178,313,334) is quirk Q16
-                        if (n > 0) { st.pair += dp; st.wall += dw; st.energy += dp + dw; }  // n==0: the moved slot is a ghost (Q12)
+                        // exact bookkeeping: the halved box total moves by the FULL pair change (the reference's
+                        // 0.5*dp, src/moves.cpp:178, is quirk Q16); with n==0 the moved slot is a ghost (Q12)
+                        if (n > 0) { st.pair += pn - po; st.wall += wn - wo; }
                     } else st.rejection++;
                 }
                 code = acc ? 1 : 0;
-            } else if (r <= thr_vol) {
+            } else if (r <= P.thr_vol) {
+                rng.end_step(1);
                 code = (4 << 1);  // volume moves are out of scope (n_vol is rejected by the host API)
             } else {
                 // ---------------- SwapParticle, single box, src/moves.cpp:284-341 ----------------
-                (void)rng.draw();                                                 // species selection draw
-                if (rng.draw() < 0.5) {
+                // draw 1 (species selection) is consumed but unused
+                if (rng.template at<2>() < 0.5) {
                     if (n >= cap) { overflow = 1; break; }
-                    const double xi = rng.draw() * P.L[0];                        // InsertParticle, src/moves.cpp:46-54
-                    const double yi = rng.draw() * P.L[1];
-                    const double zi = rng.draw() * P.L[2];
+                    const double u_x = rng.template at<3>(), u_y = rng.template at<4>(), u_z = rng.template at<5>(), u_a = rng.template at<6>();
+                    rng.end_step(7);
+                    const double lnu = log_uniform(u_a);
+                    const double ln_np1 = log((double)(n + 1));
+                    const double xi = u_x * P.L[0], yi = u_y * P.L[1], zi = u_z * P.L[2];   // InsertParticle, src/moves.cpp:46-54
                     // the trial position is written to the first free slot even if rejected (src/moves.cpp:302-303)
                     if ((n & tmask) == tid) { xs[n] = xi; ys[n] = yi; zs[n] = zi; }
                     double v[1];
-                    v[0] = pair_sum1<FAST>(xs, ys, zs, n, -1, g, xi, yi, zi, tid, T);
+                    v[0] = pair_sum1<FAST, PBZ>(xs, ys, zs, n, -1, g, xi, yi, zi, tid, T);
                     double wi, wdummy;
                     wall_two(P, zi, zi, wi, wdummy, lane);
-                    cta_allsum<1>(v, partials, parity, W, warp, lane); parity ^= 1;
-                    nf.slot = -1;
-                    const double pi_ = eps4 * v[0];
+                    cta_allsum<1, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
+                    const double pi_ = P.eps4 * v[0];
                     const double e_in = pi_ + wi;
-                    const double arg = zzV * exp(-e_in / temp) / (double)(n + 1);
-                    const bool acc = rng.draw() < arg;
+                    // u < zz*V*exp(-E/T)/(N+1), src/moves.cpp:306-307, in the log domain
+                    const bool acc = lnu < (P.ln_zzV - e_in * P.beta) - ln_np1;
+                    fwd.slot = -1;
                     if (lead) {
                         st.n_swaps++; st.tot_ins++; st.pair_evals += (unsigned long long)n;
-                        if (acc) {
-                            st.accept_swap++; st.tot_ins_acc++;
-                            st.pair += pi_; st.wall += wi; st.energy += pi_ + wi;
-                        } else st.reject_swap++;
+                        if (acc) { st.accept_swap++; st.tot_ins_acc++; st.pair += pi_; st.wall += wi; }
+                        else st.reject_swap++;
                     }
                     if (acc) n++;
                     code = (1 << 1) | (acc ? 1 : 0);
                 } else if (n > 0) {
-                    const int o = (int)(rng.draw() * (double)n + 1.0) - 1;        // int(u*n+1) on 1-based slots
+                    const double u_o = rng.template at<3>(), u_a = rng.template at<4>();
+                    rng.end_step(5);
+                    const double lnu = log_uniform(u_a);
+                    const double ln_n = log((double)n);
+                    const int o = (int)(u_o * (double)n + 1.0) - 1;               // int(u*n+1) on 1-based slots
                     double xo, yo, zo, xl, yl, zl;
                     load_slot(xs, ys, zs, o, fwd, xo, yo, zo);
                     load_slot(xs, ys, zs, n - 1, fwd, xl, yl, zl);                // the particle that would fill the hole
                     double v[1];
-                    v[0] = pair_sum1<FAST>(xs, ys, zs, n, o, g, xo, yo, zo, tid, T);
+                    v[0] = pair_sum1<FAST, PBZ>(xs, ys, zs, n, o, g, xo, yo, zo, tid, T);
                     double wo, wdummy;
                     wall_two(P, zo, zo, wo, wdummy, lane);
-                    cta_allsum<1>(v, partials, parity, W, warp, lane); parity ^= 1;
-                    nf.slot = -1;
-                    const double po = eps4 * v[0];
+                    cta_allsum<1, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
+                    const double po = P.eps4 * v[0];
                     const double e_out = po + wo;
-                    const double arg = (double)n * exp(e_out / temp) / zzV;
-                    const bool acc = rng.draw() < arg;
+                    // u < N*exp(E/T)/(zz*V), src/moves.cpp:326-327, in the log domain
+                    const bool acc = lnu < (ln_n + e_out * P.beta) - P.ln_zzV;
+                    fwd.slot = -1;
                     if (lead) {
                         st.n_swaps++; st.tot_del++; st.pair_evals += (unsigned long long)n;
-                        if (acc) {
-                            st.accept_swap++; st.tot_del_acc++;
-                            st.pair -= po; st.wall -= wo; st.energy -= po + wo;   // exact bookkeeping (quirks Q3, Q16 fixed)
-                        } else st.reject_swap++;
+                        // exact bookkeeping with the fresh energies (quirks Q3, Q16 fixed)
+                        if (acc) { st.accept_swap++; st.tot_del_acc++; st.pair -= po; st.wall -= wo; }
+                        else st.reject_swap++;
                     }
                     if (acc) {
                         if ((o & tmask) == tid) { xs[o] = xl; ys[o] = yl; zs[o] = zl; }  // swap-with-last, src/moves.cpp:329
-                        nf.slot = o; nf.x = xl; nf.y = yl; nf.z = zl;
+                        fwd.slot = o; fwd.x = xl; fwd.y = yl; fwd.z = zl;
                         n--;
                     }
                     code = (2 << 1) | (acc ? 1 : 0);
                 } else {
+                    rng.end_step(3);
                     if (lead) st.tot_empty++;
-                    code = (3 << 1);
+                    code = (3 << 1);   // no barrier executed: fwd stays valid
                 }
             }
-            fwd = nf;
             if (lead) {
                 if (trace) trace[(unsigned long long)(set - a.first_set) * (unsigned long long)a.steps_per_set + (unsigned long long)s] = (unsigned char)code;
                 if (production) {
-                    const double dn = (double)n, e = st.energy;
+                    const double dn = (double)n, e = st.pair + st.wall;
                     st.sum_n += dn; st.sum_n2 += dn * dn; st.sum_e += e; st.sum_e2 += e * e;
                     st.samples++;
                 }
             }
         }
-        // MC::AdjustMCMoves displacement part, src/moves.cpp:68-78
-        if (!overflow && n > 0 && set <= P.n_equil) {
-            const double ratio = (double)acceptance * 1. / (1. * (double)n_disp);
-            if (ratio < 0.2) dr /= 1.1;
-            else dr *= 1.1;
+        // MC::AdjustMCMoves displacement part, src/moves.cpp:68-78: thread 0 owns the counters, so it
+        // decides and publishes the new step size (set boundaries are rare: a barrier is fine here)
+        if (lead && !overflow && n > 0 && set <= P.n_equil) {
+            const double ratio = (double)st.acceptance * 1. / (1. * (double)st.n_displacements);
+            st.dr = (ratio < 0.2) ? dr / 1.1 : dr * 1.1;
         }
+        __syncthreads();
+        dr = st.dr;
+        __syncthreads();
     }
-    __syncthreads();
 
     double c_pair = 0.0, c_wall = 0.0;
-    if (a.check_energy) cta_box_energy<FAST>(xs, ys, zs, n, P, g, partials, W, warp, lane, tid, T, c_pair, c_wall);
+    if (a.check_energy) cta_box_energy<FAST, PBZ>(xs, ys, zs, n, P, g, partials, W, warp, lane, tid, T, c_pair, c_wall);
 
     if (lead) {
-        st.n = n; st.overflow = overflow; st.dr = dr; st.steps_done = step;
+        st.n = n; st.overflow = overflow; st.steps_done = step;
+        st.energy = st.pair + st.wall;
         if (a.check_energy) { st.pair_check = c_pair; st.wall_check = c_wall; st.energy_check = c_pair + c_wall; }
         S.replay_pos = rng.cursor();
     }
 }
 
-template <int RNG_MODE, int MAXT>
-__global__ void __launch_bounds__(MAXT) k2_chains(const ChainParams* __restrict__ params, ChainState* __restrict__ states,
+template <int RNG_MODE, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k2_chains(const ChainParams* __restrict__ params, ChainState* __restrict__ states,
                                                   const int* __restrict__ order, double* __restrict__ X, double* __restrict__ Y,
                                                   double* __restrict__ Z, RunArgs a) {
     extern __shared__ double smem[];
@@ -295,15 +308,27 @@ __global__ void __launch_bounds__(MAXT) k2_chains(const ChainParams* __restrict_
     __syncthreads();
 
     unsigned char* trace = a.trace ? a.trace + (unsigned long long)chain * a.trace_stride : nullptr;
+    const bool multi = T > 32, pbz = P.pbc[2] != 0;
+#define MCPM_GO(SRC, F, M, Z) chain_loop<SRC, F, M, Z>(P, S, rng, xs, ys, zs, partials, a, trace, cap, (uint32_t)chain)
+#define MCPM_DISPATCH(SRC)                                                                  \
+    do {                                                                                    \
+        if (S.fast_image) {                                                                 \
+            if (multi) { if (pbz) MCPM_GO(SRC, true, true, true); else MCPM_GO(SRC, true, true, false); }      \
+            else { if (pbz) MCPM_GO(SRC, true, false, true); else MCPM_GO(SRC, true, false, false); }           \
+        } else {                                                                            \
+            if (multi) { if (pbz) MCPM_GO(SRC, false, true, true); else MCPM_GO(SRC, false, true, false); }    \
+            else { if (pbz) MCPM_GO(SRC, false, false, true); else MCPM_GO(SRC, false, false, false); }         \
+        }                                                                                   \
+    } while (0)
     if (RNG_MODE == MCPM_RNG_PHILOX) {
-        PhiloxSource rng; rng.init(a.seed, (uint32_t)chain);
-        if (S.fast_image) chain_loop<PhiloxSource, true>(P, S, rng, xs, ys, zs, partials, a, trace, cap);
-        else chain_loop<PhiloxSource, false>(P, S, rng, xs, ys, zs, partials, a, trace, cap);
+        PhiloxSource rng; rng.init(a.seed, (uint32_t)chain, S.st.steps_done, tid & 31);
+        MCPM_DISPATCH(PhiloxSource);
     } else {
         ReplaySource rng; rng.init(a.replay_u + (unsigned long long)chain * a.replay_stride, 0ull, a.replay_stride);
-        if (S.fast_image) chain_loop<ReplaySource, true>(P, S, rng, xs, ys, zs, partials, a, trace, cap);
-        else chain_loop<ReplaySource, false>(P, S, rng, xs, ys, zs, partials, a, trace, cap);
+        MCPM_DISPATCH(ReplaySource);
     }
+#undef MCPM_DISPATCH
+#undef MCPM_GO
     __syncthreads();
     for (int j = tid; j < cap; j += T) { X[off + j] = xs[j]; Y[off + j] = ys[j]; Z[off + j] = zs[j]; }
     if (tid == 0) states[chain] = S;
@@ -327,7 +352,7 @@ __global__ void __launch_bounds__(256) k1_particle_energy(const ChainParams* __r
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) P = params[chain];
     __syncthreads();
-    const PairGeom g = make_geom(P);
+    const PairGeom g = make_geom<FAST>(P);
     const int n = states[chain].st.n;
     const size_t off = (size_t)chain * (size_t)cap;
     const double* xs = X + off; const double* ys = Y + off; const double* zs = Z + off;
@@ -335,11 +360,18 @@ __global__ void __launch_bounds__(256) k1_particle_energy(const ChainParams* __r
     if (index >= 0) { xa = xs[index]; ya = ys[index]; za = zs[index]; }
     if (!has_trial) { tx = xa; ty = ya; tz = za; }
     double sa = 0.0, sb = 0.0;
-    for (int j = blockIdx.x * blockDim.x + tid; j < n; j += gridDim.x * blockDim.x) {
-        double xj = xs[j], yj = ys[j], zj = zs[j];
-        bool ns = (j != index);
-        sa += pair_masked(dist2<FAST>(g, xa, ya, za, xj, yj, zj), g, ns);
-        sb += pair_masked(dist2<FAST>(g, tx, ty, tz, xj, yj, zj), g, ns);
+    if (P.pbc[2]) {
+        for (int j = blockIdx.x * blockDim.x + tid; j < n; j += gridDim.x * blockDim.x) {
+            double xj = xs[j], yj = ys[j], zj = zs[j];
+            pair_acc(sa, dist2<FAST, true>(g, xa, ya, za, xj, yj, zj), g, j, index);
+            pair_acc(sb, dist2<FAST, true>(g, tx, ty, tz, xj, yj, zj), g, j, index);
+        }
+    } else {
+        for (int j = blockIdx.x * blockDim.x + tid; j < n; j += gridDim.x * blockDim.x) {
+            double xj = xs[j], yj = ys[j], zj = zs[j];
+            pair_acc(sa, dist2<FAST, false>(g, xa, ya, za, xj, yj, zj), g, j, index);
+            pair_acc(sb, dist2<FAST, false>(g, tx, ty, tz, xj, yj, zj), g, j, index);
+        }
     }
     sa = warp_allsum(sa); sb = warp_allsum(sb);
     if (lane == 0) { red[0][warp] = sa; red[1][warp] = sb; }
@@ -393,7 +425,7 @@ __global__ void __launch_bounds__(128) k3_box_energy(const ChainParams* __restri
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) P = params[chain];
     __syncthreads();
-    const PairGeom g = make_geom(P);
+    const PairGeom g = make_geom<FAST>(P);
     const int n = states[chain].st.n;
     const int tiles = (n + blockDim.x - 1) / blockDim.x;
     const size_t off = (size_t)chain * (size_t)cap;
@@ -411,12 +443,21 @@ __global__ void __launch_bounds__(128) k3_box_energy(const ChainParams* __restri
             __syncthreads();
             for (int k = tid; k < m; k += blockDim.x) { tx[k] = xs[j0 + k]; ty[k] = ys[j0 + k]; tz[k] = zs[j0 + k]; }
             __syncthreads();
-            int k = 0;
-            for (; k + 1 < m; k += 2) {
-                s0 += pair_masked(dist2<FAST>(g, xi, yi, zi, tx[k], ty[k], tz[k]), g, (j0 + k) != i);
-                s1 += pair_masked(dist2<FAST>(g, xi, yi, zi, tx[k + 1], ty[k + 1], tz[k + 1]), g, (j0 + k + 1) != i);
+            if (P.pbc[2]) {
+                int k = 0;
+                for (; k + 1 < m; k += 2) {
+                    pair_acc(s0, dist2<FAST, true>(g, xi, yi, zi, tx[k], ty[k], tz[k]), g, j0 + k, i);
+                    pair_acc(s1, dist2<FAST, true>(g, xi, yi, zi, tx[k + 1], ty[k + 1], tz[k + 1]), g, j0 + k + 1, i);
+                }
+                if (k < m) pair_acc(s0, dist2<FAST, true>(g, xi, yi, zi, tx[k], ty[k], tz[k]), g, j0 + k, i);
+            } else {
+                int k = 0;
+                for (; k + 1 < m; k += 2) {
+                    pair_acc(s0, dist2<FAST, false>(g, xi, yi, zi, tx[k], ty[k], tz[k]), g, j0 + k, i);
+                    pair_acc(s1, dist2<FAST, false>(g, xi, yi, zi, tx[k + 1], ty[k + 1], tz[k + 1]), g, j0 + k + 1, i);
+                }
+                if (k < m) pair_acc(s0, dist2<FAST, false>(g, xi, yi, zi, tx[k], ty[k], tz[k]), g, j0 + k, i);
             }
-            if (k < m) s0 += pair_masked(dist2<FAST>(g, xi, yi, zi, tx[k], ty[k], tz[k]), g, (j0 + k) != i);
         }
         if (live) {
             pair_i = P.eps4 * (s0 + s1);
@@ -463,13 +504,11 @@ __global__ void fp64_peak_kernel(double* out, int iters, double seed) {
 
 __global__ void philox_fill_kernel(unsigned long long seed, unsigned int chain, unsigned long long first_step, int n_steps, double* out) {
     const int lane = threadIdx.x & 31;
-    PhiloxSource rng; rng.init(seed, chain);
+    PhiloxSource rng; rng.init(seed, chain, first_step, lane);
     for (int s = 0; s < n_steps; s++) {
-        rng.begin_step(first_step + (unsigned long long)s, lane);
-        for (int k = 0; k < 8; k++) {
-            double v = rng.draw();
-            if (lane == (s & 31)) out[(size_t)s * 8 + k] = v;
-        }
+        rng.begin_step(seed, chain, first_step + (unsigned long long)s, lane);
+        double v[8] = {rng.at<0>(), rng.at<1>(), rng.at<2>(), rng.at<3>(), rng.at<4>(), rng.at<5>(), rng.at<6>(), rng.at<7>()};
+        if (lane == (s & 31)) for (int k = 0; k < 8; k++) out[(size_t)s * 8 + k] = v[k];
     }
 }
 
@@ -488,8 +527,11 @@ cudaError_t launch_k2(int rng_mode, int n_chains, int threads, const ChainParams
         kern<<<n_chains, threads, smem, stream>>>(params, states, order, X, Y, Z, a);
         return cudaSuccess;
     };
-    if (rng_mode == MCPM_RNG_PHILOX) err = threads <= 256 ? go(k2_chains<MCPM_RNG_PHILOX, 256>) : go(k2_chains<MCPM_RNG_PHILOX, 1024>);
-    else err = threads <= 256 ? go(k2_chains<MCPM_RNG_REPLAY, 256>) : go(k2_chains<MCPM_RNG_REPLAY, 1024>);
+    // register budgets by CTA size: <=64 threads -> up to 128 regs, <=256 -> 128, else 64
+    if (rng_mode == MCPM_RNG_PHILOX)
+        err = threads <= 64 ? go(k2_chains<MCPM_RNG_PHILOX, 64, 12>) : threads <= 256 ? go(k2_chains<MCPM_RNG_PHILOX, 256, 2>) : go(k2_chains<MCPM_RNG_PHILOX, 1024, 1>);
+    else
+        err = threads <= 64 ? go(k2_chains<MCPM_RNG_REPLAY, 64, 12>) : threads <= 256 ? go(k2_chains<MCPM_RNG_REPLAY, 256, 2>) : go(k2_chains<MCPM_RNG_REPLAY, 1024, 1>);
     if (err != cudaSuccess) return err;
     return cudaGetLastError();
 }

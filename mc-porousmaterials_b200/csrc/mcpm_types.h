@@ -14,6 +14,8 @@ struct ChainParams {
     double eps4;          // 4*epsilon_ff
     double rc2;           // rcut^2
     double zzV;           // zz*volume, zz = exp(mu/T)/Lambda^3 (src/moves.cpp:296-298)
+    double ln_zzV, beta;  // log(zzV), 1/T: the Metropolis tests run in the log domain
+    double wsum, thr_disp, thr_vol;  // move-type thresholds of src/main.cpp:67-70 as doubles
     double wall_pref;     // 4*pi*eps_sf*rho_s*sig_sf^2 (src/potentials.cpp:400)
     double sig_sf, delta;
     int geometry, wall_kind, n_layers;
