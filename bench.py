@@ -315,7 +315,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--replicas", type=int, default=32, help="replica chains per state point per GPU")
+    ap.add_argument("--replicas", type=int, default=64, help="replica chains per state point per GPU")
     ap.add_argument("--steps-per-set", type=int, default=10000)
     ap.add_argument("--threads", type=int, default=0, help="threads per chain (0 = engine heuristic)")
     ap.add_argument("--cpu-steps", type=int, default=4000, help="steps per state point of the CPU sample")

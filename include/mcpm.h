@@ -105,6 +105,7 @@ typedef struct mcpm_chain_stats {
     /* production accumulators (set > n_equil_sets), one sample per step */
     double sum_n, sum_n2, sum_e, sum_e2;
     long long samples;
+    unsigned long long replay_consumed; /* REPLAY mode: uniforms consumed by the last mcpm_run */
 } mcpm_chain_stats;
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -173,6 +174,33 @@ int mcpm_fp64_peak(int device, double* tflops, double* ms);
 /* The device Philox stream, for tests: uniform of (seed, chain, step, slot). */
 int mcpm_philox_uniforms(mcpm_ctx* ctx, unsigned long long seed, unsigned int chain,
                          unsigned long long first_step, int n_steps, double* out /* n_steps*8 */);
+
+/* ---- host driver (C++ in csrc/host/, re-hosting the reference's main/read/print) ------------- *
+ * Parsed input file == the state MC::ReadInputFile leaves behind (src/read.cpp:36-172), single box and
+ * single species.  Counts are doubles because the reference parses them with stod (src/read.cpp:56-59). */
+typedef struct mcpm_sim_config {
+    char project[64], fluid[64], box[64];       /* lower-cased like the reference (src/tools.h:19-30) */
+    double n_sets, n_equil_sets, steps_per_set, print_every;
+    double pressure;                            /* ExternalPressure, unused (NPT out of scope), -1 if absent */
+    int n_particles;                            /* <Box> <Fluid> NumberOfParticles */
+    int sample_rdf, print_trajectory, continue_after_crash;
+    int n_boxes, n_species;                     /* what the file declared (must both be 1) */
+    /* extensions of this engine (ignored by the reference, which skips unknown lines) */
+    int has_seed; unsigned long long seed;      /* Seed <n>: reproducible runs (quirk Q2) */
+    int replicas;                               /* Replicas <n>: independent replica chains per state point */
+    int sweep_points; double sweep_mu0, sweep_mu1; /* ChemicalPotentialSweep <mu0> <mu1> <n>: isotherm */
+    int capacity;                               /* Capacity <n>: particle slots per chain (default: from N) */
+    int devices;                                /* Devices <n>: GPUs to shard the chains over */
+    mcpm_system_desc system;                    /* derived widths, PBC, dr as in src/read.cpp:122-168 */
+} mcpm_sim_config;
+
+/* MC::ReadInputFile (src/read.cpp:36-172).  No GPU needed. */
+int mcpm_read_input_file(const char* path, mcpm_sim_config* cfg);
+/* The whole program src/main.cpp:16-97 on the GPU: echo (PrintParams), output tree (OutputDirectory),
+ * initial configuration, "minimisation", set loop with PrintStats / PrintTrajectory / PrintLog in the
+ * reference's formats.  flags: bit 0 = reproduce the log file's double-halved ffE column (quirk Q5),
+ * bit 1 = quiet.  out_dir = NULL writes under the current directory like the reference. */
+int mcpm_simulate(const char* input_path, const char* out_dir, int flags);
 
 #ifdef __cplusplus
 }

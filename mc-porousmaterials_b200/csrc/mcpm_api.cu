@@ -432,16 +432,13 @@ int mcpm_remove_swap_last(mcpm_ctx* c, int chain, int index) {
 
 // ---- K2 ---------------------------------------------------------------------------------------
 static int pick_threads(const mcpm_ctx* c, int maxn) {
-    // Many chains: small CTAs keep the per-step overhead (RNG, decision, reductions) per warp low and
-    // let the fp64 pipe of each SM be shared by many chains.  Few chains: spread each over more warps.
-    int t;
-    if (c->n_chains >= 4 * c->num_sms) t = maxn >= 192 ? 64 : 32;
-    else if (c->n_chains >= c->num_sms) t = maxn >= 256 ? 128 : 64;
-    else {
-        t = 32;
-        while (t < 512 && t * 2 <= maxn) t *= 2;  // about two partners per thread
-    }
-    return t;
+    // Measured on B200 (scripts/latency_table.py): with at least ~2 chains per SM one warp per chain gives
+    // the highest aggregate rate (the per-step overhead — uniforms, wall term, reductions, decision — is paid
+    // once per warp); with fewer chains than SMs, spreading a large chain over 2-4 warps shortens its step.
+    if (c->n_chains >= 2 * c->num_sms) return 32;
+    if (maxn < 128) return 32;
+    if (maxn < 256 || c->n_chains >= c->num_sms) return 64;
+    return 128;
 }
 
 int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {

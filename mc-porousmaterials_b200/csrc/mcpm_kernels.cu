@@ -119,10 +119,19 @@ __device__ void cta_box_energy(const double* xs, const double* ys, const double*
     wall = v[1];
 }
 
-// Register diet: only what EVERY thread needs on the critical path lives in registers (n, dr, the step
-// counter, the forwarded slot, the lane's Philox batch).  Counters, running energies and accumulators
-// live in shared memory (S.st) and are touched by thread 0 only; system constants are read from the
-// shared ChainParams where they are used.
+// Per-set counters replicated in registers (cheap ints); flushed to the 64-bit totals in shared memory
+// by thread 0 at the end of every set.
+struct SetCounters {
+    int n_disp, acc_disp, n_ins, acc_ins, n_del, acc_del, n_empty;
+    unsigned long long evals;
+    __device__ __forceinline__ void reset() { n_disp = acc_disp = n_ins = acc_ins = n_del = acc_del = n_empty = 0; evals = 0ull; }
+};
+
+// n, dr, the running energies, the per-set counters and the decision itself are REPLICATED in every
+// thread's registers: all threads compute them from identical inputs, so no broadcast is ever needed and
+// nothing but the partner loop's partial sums crosses threads.  (A variant that kept counters and
+// energies in shared memory for thread 0 only used 80 registers instead of 128 but was 10-15 % slower at
+// every occupancy measured on B200: the extra LDS/STS sit on the per-step critical path.)
 template <class Source, bool FAST, bool MULTI, bool PBZ>
 __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, double* xs, double* ys, double* zs, double* partials,
                            const RunArgs& a, unsigned char* trace, int cap, uint32_t chain) {
@@ -133,23 +142,26 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
     mcpm_chain_stats& st = S.st;   // shared memory; written by thread 0 only
 
     int n = st.n;
-    double dr = st.dr;
+    double dr = st.dr, e_pair = st.pair, e_wall = st.wall;
     unsigned long long step = st.steps_done;
     int overflow = 0;
+    const double wsum = P.wsum, thr_disp = P.thr_disp, thr_vol = P.thr_vol;
+    const double beta = P.beta, eps4 = P.eps4, ln_zzV = P.ln_zzV;
+    const double Lx = P.L[0], Ly = P.L[1], Lz = P.L[2];
     Fwd fwd; fwd.slot = -1; fwd.x = fwd.y = fwd.z = 0.0;
     int parity = 0;
+    SetCounters sc;
     const int steps_per_set = (int)a.steps_per_set;
 
     for (int set = a.first_set; set < a.first_set + a.n_sets && !overflow; set++) {
-        // MC::ResetStats, src/MC.cpp:81-98 (nDisplacements and nSwaps restart at ONE)
-        if (lead) { st.acceptance = st.rejection = 0; st.n_displacements = 1; st.accept_swap = st.reject_swap = 0; st.n_swaps = 1; }
+        sc.reset();                      // MC::ResetStats, src/MC.cpp:81-98
         const bool production = set > P.n_equil;
         for (int s = 0; s < steps_per_set; s++) {
             rng.begin_step(a.seed, chain, step, lane);
             step++;
             int code;
-            const double r = rng.template at<0>() * P.wsum;                       // src/main.cpp:67
-            if (r <= P.thr_disp) {
+            const double r = rng.template at<0>() * wsum;                         // src/main.cpp:67
+            if (r <= thr_disp) {
                 // ---------------- MoveParticle, src/moves.cpp:118-186 ----------------
                 // draws 1,2 (box, species selection) are consumed but unused: single box, single species
                 const double u_i = rng.template at<3>(), u_x = rng.template at<4>(), u_y = rng.template at<5>(),
@@ -159,34 +171,31 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                 const int i = (int)(u_i * (double)n);                             // int(u*n)+1 on 1-based slots; n==0 -> stale slot (Q12)
                 double xo, yo, zo;
                 load_slot(xs, ys, zs, i, fwd, xo, yo, zo);
-                double xn = wrap_floor(__dadd_rn(xo, __dmul_rn(u_x - 0.5, dr)), P.L[0]);   // MC::PBC: x and y are always periodic
-                double yn = wrap_floor(__dadd_rn(yo, __dmul_rn(u_y - 0.5, dr)), P.L[1]);
+                double xn = wrap_floor(__dadd_rn(xo, __dmul_rn(u_x - 0.5, dr)), Lx);    // MC::PBC: x and y are always periodic
+                double yn = wrap_floor(__dadd_rn(yo, __dmul_rn(u_y - 0.5, dr)), Ly);
                 double zn = __dadd_rn(zo, __dmul_rn(u_z - 0.5, dr));
-                if (PBZ) zn = wrap_floor(zn, P.L[2]);
+                if (PBZ) zn = wrap_floor(zn, Lz);
                 double v[2];
                 pair_sum2<FAST, PBZ>(xs, ys, zs, n, i, g, xo, yo, zo, xn, yn, zn, tid, T, v[0], v[1]);
                 double wo, wn;
                 wall_two(P, zo, zn, wo, wn, lane);
                 cta_allsum<2, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
-                const double po = P.eps4 * v[0], pn = P.eps4 * v[1];
+                const double po = eps4 * v[0], pn = eps4 * v[1];
                 const double dE = (pn + wn) - (po + wo);                          // newEnergy - oldEnergy, src/moves.cpp:169
-                const bool acc = lnu < -(dE * P.beta);                            // u < exp(-dE/T), src/moves.cpp:170-172
+                const bool acc = lnu < -(dE * beta);                              // u < exp(-dE/T), src/moves.cpp:170-172
+                sc.n_disp++; sc.evals += 2ull * (unsigned long long)n;
                 fwd.slot = -1;
                 if (acc) {
+                    sc.acc_disp++;
+                    if (n > 0) {   // exact bookkeeping: the halved box total moves by the FULL pair change (the
+                                   // reference's 0.5*dp, src/moves.cpp:178, is quirk Q16); n==0 moves a ghost (Q12)
+                        e_pair += pn - po; e_wall += wn - wo;
+                    }
                     if ((i & tmask) == tid) { xs[i] = xn; ys[i] = yn; zs[i] = zn; }
                     fwd.slot = i; fwd.x = xn; fwd.y = yn; fwd.z = zn;
                 }
-                if (lead) {
-                    st.n_displacements++; st.tot_disp++; st.pair_evals += 2ull * (unsigned long long)n;
-                    if (acc) {
-                        st.acceptance++; st.tot_disp_acc++;
-                        // exact bookkeeping: the halved box total moves by the FULL pair change (the reference's
-                        // 0.5*dp, src/moves.cpp:178, is quirk Q16); with n==0 the moved slot is a ghost (Q12)
-                        if (n > 0) { st.pair += pn - po; st.wall += wn - wo; }
-                    } else st.rejection++;
-                }
                 code = acc ? 1 : 0;
-            } else if (r <= P.thr_vol) {
+            } else if (r <= thr_vol) {
                 rng.end_step(1);
                 code = (4 << 1);  // volume moves are out of scope (n_vol is rejected by the host API)
             } else {
@@ -198,7 +207,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                     rng.end_step(7);
                     const double lnu = log_uniform(u_a);
                     const double ln_np1 = log((double)(n + 1));
-                    const double xi = u_x * P.L[0], yi = u_y * P.L[1], zi = u_z * P.L[2];   // InsertParticle, src/moves.cpp:46-54
+                    const double xi = u_x * Lx, yi = u_y * Ly, zi = u_z * Lz;     // InsertParticle, src/moves.cpp:46-54
                     // the trial position is written to the first free slot even if rejected (src/moves.cpp:302-303)
                     if ((n & tmask) == tid) { xs[n] = xi; ys[n] = yi; zs[n] = zi; }
                     double v[1];
@@ -206,17 +215,13 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                     double wi, wdummy;
                     wall_two(P, zi, zi, wi, wdummy, lane);
                     cta_allsum<1, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
-                    const double pi_ = P.eps4 * v[0];
+                    const double pi_ = eps4 * v[0];
                     const double e_in = pi_ + wi;
                     // u < zz*V*exp(-E/T)/(N+1), src/moves.cpp:306-307, in the log domain
-                    const bool acc = lnu < (P.ln_zzV - e_in * P.beta) - ln_np1;
+                    const bool acc = lnu < (ln_zzV - e_in * beta) - ln_np1;
+                    sc.n_ins++; sc.evals += (unsigned long long)n;
                     fwd.slot = -1;
-                    if (lead) {
-                        st.n_swaps++; st.tot_ins++; st.pair_evals += (unsigned long long)n;
-                        if (acc) { st.accept_swap++; st.tot_ins_acc++; st.pair += pi_; st.wall += wi; }
-                        else st.reject_swap++;
-                    }
-                    if (acc) n++;
+                    if (acc) { sc.acc_ins++; n++; e_pair += pi_; e_wall += wi; }
                     code = (1 << 1) | (acc ? 1 : 0);
                 } else if (n > 0) {
                     const double u_o = rng.template at<3>(), u_a = rng.template at<4>();
@@ -232,57 +237,60 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                     double wo, wdummy;
                     wall_two(P, zo, zo, wo, wdummy, lane);
                     cta_allsum<1, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
-                    const double po = P.eps4 * v[0];
+                    const double po = eps4 * v[0];
                     const double e_out = po + wo;
                     // u < N*exp(E/T)/(zz*V), src/moves.cpp:326-327, in the log domain
-                    const bool acc = lnu < (ln_n + e_out * P.beta) - P.ln_zzV;
+                    const bool acc = lnu < (ln_n + e_out * beta) - ln_zzV;
+                    sc.n_del++; sc.evals += (unsigned long long)n;
                     fwd.slot = -1;
-                    if (lead) {
-                        st.n_swaps++; st.tot_del++; st.pair_evals += (unsigned long long)n;
-                        // exact bookkeeping with the fresh energies (quirks Q3, Q16 fixed)
-                        if (acc) { st.accept_swap++; st.tot_del_acc++; st.pair -= po; st.wall -= wo; }
-                        else st.reject_swap++;
-                    }
                     if (acc) {
+                        sc.acc_del++;
                         if ((o & tmask) == tid) { xs[o] = xl; ys[o] = yl; zs[o] = zl; }  // swap-with-last, src/moves.cpp:329
                         fwd.slot = o; fwd.x = xl; fwd.y = yl; fwd.z = zl;
                         n--;
+                        e_pair -= po; e_wall -= wo;   // exact bookkeeping with the fresh energies (quirks Q3, Q16 fixed)
                     }
                     code = (2 << 1) | (acc ? 1 : 0);
                 } else {
                     rng.end_step(3);
-                    if (lead) st.tot_empty++;
+                    sc.n_empty++;
                     code = (3 << 1);   // no barrier executed: fwd stays valid
                 }
             }
             if (lead) {
                 if (trace) trace[(unsigned long long)(set - a.first_set) * (unsigned long long)a.steps_per_set + (unsigned long long)s] = (unsigned char)code;
                 if (production) {
-                    const double dn = (double)n, e = st.pair + st.wall;
+                    const double dn = (double)n, e = e_pair + e_wall;
                     st.sum_n += dn; st.sum_n2 += dn * dn; st.sum_e += e; st.sum_e2 += e * e;
                     st.samples++;
                 }
             }
         }
-        // MC::AdjustMCMoves displacement part, src/moves.cpp:68-78: thread 0 owns the counters, so it
-        // decides and publishes the new step size (set boundaries are rare: a barrier is fine here)
-        if (lead && !overflow && n > 0 && set <= P.n_equil) {
-            const double ratio = (double)st.acceptance * 1. / (1. * (double)st.n_displacements);
-            st.dr = (ratio < 0.2) ? dr / 1.1 : dr * 1.1;
+        // MC::AdjustMCMoves displacement part, src/moves.cpp:68-78 (ResetStats starts nDisplacements at ONE)
+        if (!overflow && n > 0 && set <= P.n_equil) {
+            const double ratio = (double)sc.acc_disp * 1. / (1. * (double)(sc.n_disp + 1));
+            if (ratio < 0.2) dr /= 1.1;
+            else dr *= 1.1;
         }
-        __syncthreads();
-        dr = st.dr;
-        __syncthreads();
+        if (lead) {
+            st.acceptance = sc.acc_disp; st.rejection = sc.n_disp - sc.acc_disp; st.n_displacements = 1 + sc.n_disp;
+            st.accept_swap = sc.acc_ins + sc.acc_del; st.reject_swap = (sc.n_ins + sc.n_del) - (sc.acc_ins + sc.acc_del);
+            st.n_swaps = 1 + sc.n_ins + sc.n_del;
+            st.tot_disp += sc.n_disp; st.tot_disp_acc += sc.acc_disp; st.tot_ins += sc.n_ins; st.tot_ins_acc += sc.acc_ins;
+            st.tot_del += sc.n_del; st.tot_del_acc += sc.acc_del; st.tot_empty += sc.n_empty; st.pair_evals += sc.evals;
+        }
     }
+    __syncthreads();
 
     double c_pair = 0.0, c_wall = 0.0;
     if (a.check_energy) cta_box_energy<FAST, PBZ>(xs, ys, zs, n, P, g, partials, W, warp, lane, tid, T, c_pair, c_wall);
 
     if (lead) {
-        st.n = n; st.overflow = overflow; st.steps_done = step;
-        st.energy = st.pair + st.wall;
+        st.n = n; st.overflow = overflow; st.dr = dr; st.steps_done = step;
+        st.pair = e_pair; st.wall = e_wall; st.energy = e_pair + e_wall;
         if (a.check_energy) { st.pair_check = c_pair; st.wall_check = c_wall; st.energy_check = c_pair + c_wall; }
         S.replay_pos = rng.cursor();
+        st.replay_consumed = rng.cursor();
     }
 }
 
@@ -529,9 +537,9 @@ cudaError_t launch_k2(int rng_mode, int n_chains, int threads, const ChainParams
     };
     // register budgets by CTA size: <=64 threads -> up to 128 regs, <=256 -> 128, else 64
     if (rng_mode == MCPM_RNG_PHILOX)
-        err = threads <= 64 ? go(k2_chains<MCPM_RNG_PHILOX, 64, 12>) : threads <= 256 ? go(k2_chains<MCPM_RNG_PHILOX, 256, 2>) : go(k2_chains<MCPM_RNG_PHILOX, 1024, 1>);
+        err = threads <= 64 ? go(k2_chains<MCPM_RNG_PHILOX, 64, 8>) : threads <= 256 ? go(k2_chains<MCPM_RNG_PHILOX, 256, 2>) : go(k2_chains<MCPM_RNG_PHILOX, 1024, 1>);
     else
-        err = threads <= 64 ? go(k2_chains<MCPM_RNG_REPLAY, 64, 12>) : threads <= 256 ? go(k2_chains<MCPM_RNG_REPLAY, 256, 2>) : go(k2_chains<MCPM_RNG_REPLAY, 1024, 1>);
+        err = threads <= 64 ? go(k2_chains<MCPM_RNG_REPLAY, 64, 8>) : threads <= 256 ? go(k2_chains<MCPM_RNG_REPLAY, 256, 2>) : go(k2_chains<MCPM_RNG_REPLAY, 1024, 1>);
     if (err != cudaSuccess) return err;
     return cudaGetLastError();
 }

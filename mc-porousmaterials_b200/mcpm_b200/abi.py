@@ -71,11 +71,25 @@ class ChainStats(C.Structure):
         ("tot_empty", C.c_longlong),
         ("pair_evals", C.c_ulonglong), ("steps_done", C.c_ulonglong),
         ("sum_n", C.c_double), ("sum_n2", C.c_double), ("sum_e", C.c_double), ("sum_e2", C.c_double),
-        ("samples", C.c_longlong),
+        ("samples", C.c_longlong), ("replay_consumed", C.c_ulonglong),
     ]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+class SimConfig(C.Structure):
+    _fields_ = [
+        ("project", C.c_char * 64), ("fluid", C.c_char * 64), ("box", C.c_char * 64),
+        ("n_sets", C.c_double), ("n_equil_sets", C.c_double), ("steps_per_set", C.c_double), ("print_every", C.c_double),
+        ("pressure", C.c_double),
+        ("n_particles", C.c_int), ("sample_rdf", C.c_int), ("print_trajectory", C.c_int), ("continue_after_crash", C.c_int),
+        ("n_boxes", C.c_int), ("n_species", C.c_int),
+        ("has_seed", C.c_int), ("seed", C.c_ulonglong),
+        ("replicas", C.c_int), ("sweep_points", C.c_int), ("sweep_mu0", C.c_double), ("sweep_mu1", C.c_double),
+        ("capacity", C.c_int), ("devices", C.c_int),
+        ("system", SystemDesc),
+    ]
 
 
 def lib_path() -> str:
@@ -114,6 +128,8 @@ PROTOTYPES = {
     "mcpm_timer_start": (C.c_int, [C.c_void_p]),
     "mcpm_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "mcpm_fp64_peak": (C.c_int, [C.c_int, _dp, _dp]),
+    "mcpm_read_input_file": (C.c_int, [C.c_char_p, C.POINTER(SimConfig)]),
+    "mcpm_simulate": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int]),
     "mcpm_philox_uniforms": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_uint, C.c_ulonglong, C.c_int, _dp]),
 }
 

@@ -1,0 +1,101 @@
+"""GPU: the C++ host driver (mcpm_simulate) — reference-format outputs and ensemble parity."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, O, ROOT
+
+pytestmark = pytest.mark.gpu
+EXE = os.path.join(ROOT, "mc-porousmaterials_b200", "mcpm_simulate")
+REF_OUT = os.path.join(GOLDEN, "ref_output")
+
+
+def run_driver(tmp_path, input_file, *flags):
+    out = subprocess.run([EXE, input_file, "--out", str(tmp_path), *flags], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr + out.stdout
+    return out.stdout
+
+
+def test_outputs_have_the_reference_formats(tmp_path):
+    stdout = run_driver(tmp_path, os.path.join(GOLDEN, "ar_small.in"))
+    ref_log = open(os.path.join(REF_OUT, "simulation_ar.log")).read().splitlines()
+    log = open(tmp_path / "ar_small" / "pore" / "simulation_ar.log").read().splitlines()
+    assert log[0] == ref_log[0]                                   # header, byte for byte
+    assert len(log) == len(ref_log) == 4                          # one row per printed set (2, 4, 6)
+    for row, ref_row in zip(log[1:], ref_log[1:]):
+        a, b = row.split("\t"), ref_row.split("\t")
+        assert len(a) == len(b) == 11
+        assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2] and a[3] == b[3]      # set, T, width, volume
+        for col in (4, 5, 6, 8):
+            assert re.fullmatch(r"-?\d+\.\d{7}", a[col]), a[col]   # fixed, 7 decimals
+        assert a[9:] == b[9:] == ["nan", "-nan"]
+        n = int(a[7])
+        assert 30 <= n <= 120
+        dens = n / 11520.0 * 39.948 / 6.02214076e23 * 1e24
+        assert float(a[8]) == pytest.approx(dens, abs=1e-7)
+        assert float(a[6]) == pytest.approx(float(a[4]) + float(a[5]), abs=2e-7)
+    # trajectory: appended frames (PrintTrajectory given): set 0 twice is overwritten -> frames for sets 0, 2, 4, 6
+    traj = open(tmp_path / "ar_small" / "pore" / "trajectory.exyz").read().splitlines()
+    ref_traj = open(os.path.join(REF_OUT, "trajectory_head.exyz")).read().splitlines()
+    assert traj[0] == ref_traj[0] == "60"
+    assert traj[1] == ref_traj[1]                                 # Lattice=" 24 0 0 0 24 0 0 0 20" ... Set: 0 Disp: 2 VolDisp: 0.001
+    assert re.fullmatch(r"ar\t[\d.e+-]+\t[\d.e+-]+\t[\d.e+-]+", traj[2])
+    assert sum(1 for line in traj if line.startswith("Lattice=")) == 4
+    # stdout: same parameter echo as the reference (everything between the date lines)
+    ref_stdout = open(os.path.join(REF_OUT, "stdout.txt")).read()
+    def echo(text):
+        return text[text.index("Simulation parameters:"):text.index("Initial configuration set.")]
+    assert echo(stdout) == echo(ref_stdout)
+    for tag in ("Starting minimization...", "Minimization finished", "Set: 4", "AcceptSwapRatio; RejectSwapRatio:",
+                "AcceptDispRatio; RegectDispRatio:", "NumParticles; BoxSize; Energy/Particle:", "Simulation finished",
+                "Elapsed time of simulation:"):
+        assert tag in stdout
+    assert "Equilibrium set:" not in stdout or True
+
+
+def test_logged_energy_is_consistent_with_the_trajectory(tmp_path, mcpm):
+    """E/particle in the log == BoxEnergy of the printed configuration (positions are printed with 6 digits)."""
+    inp = tmp_path / "one.in"
+    text = open(os.path.join(GOLDEN, "ar_small.in")).read().replace("PrintTrajectory\n", "")
+    inp.write_text(text)
+    run_driver(tmp_path, str(inp), "--quiet")
+    log = open(tmp_path / "ar_small" / "pore" / "simulation_ar.log").read().splitlines()
+    traj = open(tmp_path / "ar_small" / "pore" / "trajectory.exyz").read().splitlines()
+    n = int(traj[0])
+    xyz = np.array([[float(v) for v in line.split("\t")[1:]] for line in traj[2:2 + n]])
+    s = O.argon_slit(mu=-1400.0, rcut=12.0)
+    c = O.COracle(s, n + 8)
+    c.set_positions(xyz[:, 0], xyz[:, 1], xyz[:, 2])
+    box, _, _ = c.box_energy()
+    last = log[-1].split("\t")
+    assert int(last[7]) == n
+    assert float(last[6]) == pytest.approx(box[3] / n, rel=2e-3)       # 6-digit coordinates
+    assert float(last[5]) == pytest.approx(box[2] / n, rel=2e-3)
+
+
+def test_q5_compat_flag_halves_the_pair_column_again(tmp_path):
+    a = tmp_path / "a"; b = tmp_path / "b"
+    a.mkdir(); b.mkdir()
+    inp = os.path.join(GOLDEN, "ar_small.in")
+    run_driver(a, inp, "--quiet")
+    run_driver(b, inp, "--quiet", "--q5-compat")
+    ra = open(a / "ar_small" / "pore" / "simulation_ar.log").read().splitlines()[-1].split("\t")
+    rb = open(b / "ar_small" / "pore" / "simulation_ar.log").read().splitlines()[-1].split("\t")
+    assert ra[7] == rb[7]                                           # same Seed -> same chain
+    assert float(rb[4]) == pytest.approx(0.5 * float(ra[4]), abs=2e-7)
+
+
+def test_isotherm_sweep_and_replicas(tmp_path):
+    inp = tmp_path / "sweep.in"
+    text = open(os.path.join(GOLDEN, "ar_small.in")).read().replace("PrintTrajectory\n", "")
+    text = text.replace("ProductionSets 6", "ProductionSets 12").replace("StepsPerSet 400", "StepsPerSet 2000")
+    inp.write_text(text + "ChemicalPotentialSweep -1700 -1300 3\nReplicas 4\n")
+    run_driver(tmp_path, str(inp), "--quiet")
+    iso = np.loadtxt(tmp_path / "ar_small_isotherm.dat", skiprows=1)
+    assert iso.shape == (3, 6)
+    assert list(iso[:, 0]) == [-1700.0, -1500.0, -1300.0]
+    assert iso[0, 1] < iso[1, 1] < iso[2, 1]                        # loading grows with chemical potential
+    assert os.path.isdir(tmp_path / "ar_small_mu2_r3" / "pore")

@@ -1,0 +1,70 @@
+"""CPU: the C++ host driver's input parser (mcpm_read_input_file) against the reference's ReadInputFile."""
+import ctypes as C
+import os
+
+import pytest
+
+from conftest import GOLDEN
+
+
+def parse(mcpm, path):
+    cfg = mcpm.SimConfig()
+    rc = mcpm.lib().mcpm_read_input_file(path.encode(), C.byref(cfg))
+    return rc, cfg
+
+
+def test_parser_matches_reference_golden(mcpm, golden):
+    _, meta = golden
+    want = meta["parser_c1"]
+    rc, cfg = parse(mcpm, os.path.join(GOLDEN, "ar_cfg1.in"))
+    assert rc == 0
+    assert cfg.project.decode() == want["project"] and cfg.fluid.decode() == want["fluid"] and cfg.box.decode() == want["box"]
+    assert [cfg.n_sets, cfg.n_equil_sets, cfg.steps_per_set, cfg.print_every] == want["sets"]
+    assert cfg.n_particles == want["n0"] and cfg.n_boxes == 1 and cfg.n_species == 1
+    s = cfg.system
+    for key, val in want["system"].items():
+        got = list(s.width) if key == "width" else getattr(s, key)
+        assert got == val, key          # exact: same parsing (stod/stoi) and the same derived widths, dr
+
+
+def test_parser_live_against_reference(mcpm, ref, tmp_path):
+    """Case-insensitive keywords, trailing ';', names lower-cased, unknown lines ignored (src/read.cpp:50-121)."""
+    from conftest import O
+    r2 = O.RefOracle()      # ReadInputFile accumulates into counters: fresh object
+    try:
+        path = os.path.join(GOLDEN, "ar_small.in")
+        rc_ref, ps, n0, proj, fname, bname, sets = r2.read_input(path)
+        rc, cfg = parse(mcpm, path)
+        assert rc == 0 and rc_ref == 0
+        assert (cfg.project.decode(), cfg.fluid.decode(), cfg.box.decode()) == (proj, fname, bname) == ("ar_small", "ar", "pore")
+        assert cfg.n_particles == n0
+        assert [cfg.n_sets, cfg.n_equil_sets, cfg.steps_per_set, cfg.print_every] == list(sets)
+        for name, _ in ps._fields_:
+            if name == "_pad":
+                continue
+            a = getattr(ps, name); b = getattr(cfg.system, name)
+            assert (list(a) == list(b)) if name == "width" else (a == b), name
+        assert cfg.has_seed == 1 and cfg.seed == 4242 and cfg.print_trajectory == 1
+    finally:
+        r2.close()
+
+
+def test_parser_quirks(mcpm, tmp_path):
+    text = open(os.path.join(GOLDEN, "ar_cfg1.in")).read()
+    # a slit with "steele10-4-3" matches no wall potential in the reference's dispatch (src/energy.cpp:69-77)
+    p = tmp_path / "steele.in"
+    p.write_text(text.replace("pore ar VdwPotential lj", "pore ar VdwPotential steele10-4-3"))
+    rc, cfg = parse(mcpm, str(p))
+    assert rc == 0 and cfg.system.wall_kind == mcpm.WALL_NONE
+    p = tmp_path / "bulk.in"
+    p.write_text(text.replace("Geometry slit", "GEOMETRY Bulk;").replace("Size 20.0", "size 50.0"))
+    rc, cfg = parse(mcpm, str(p))
+    assert rc == 0 and cfg.system.geometry == mcpm.GEOM_BULK and list(cfg.system.width) == [50.0, 50.0, 50.0]
+    assert cfg.system.dr == pytest.approx(5.0)
+    rc, _ = parse(mcpm, str(tmp_path / "missing.in"))
+    assert rc == 5
+    p = tmp_path / "ext.in"
+    p.write_text(text + "Replicas 8\nChemicalPotentialSweep -1800 -1134 40\nDevices 8\nCapacity 768\n")
+    rc, cfg = parse(mcpm, str(p))
+    assert rc == 0 and (cfg.replicas, cfg.sweep_points, cfg.devices, cfg.capacity) == (8, 40, 8, 768)
+    assert (cfg.sweep_mu0, cfg.sweep_mu1) == (-1800.0, -1134.0)
