@@ -86,7 +86,8 @@ typedef struct mcpm_run_params {
                                   (move<<1)|accepted; move 0 translation, 1 insertion, 2 deletion,
                                   3 deletion branch on an empty box */
     int threads_per_chain;     /* CTA size, multiple of 32 up to 1024; 0 = choose from the loadings */
-    int check_energy;          /* !=0: recompute the full box energy on the device at the end (drift check) */
+    int check_energy;          /* 1: recompute the full box energy on the device at the end (drift check, reported in
+                                  *_check); 2: also adopt it as the running energy, as MC::BoxEnergy does */
 } mcpm_run_params;
 
 /* Per-chain result of mcpm_run.  Per-set counters follow MC::Stats after the LAST set of the call

@@ -433,6 +433,7 @@ extern "C" int mcpm_simulate(const char* input_path, const char* out_dir, int fl
         mcpm_run_params rp;
         memset(&rp, 0, sizeof(rp));
         rp.first_set = set; rp.n_sets = last - set + 1; rp.steps_per_set = steps_per_set; rp.rng_mode = MCPM_RNG_PHILOX; rp.seed = seed;
+        rp.check_energy = 2;   // re-anchor the running energies at every print interval (src/energy.cpp:35-42 in spirit)
         rc = run_all(rp);
         if (rc) return rc;
         if (last % print_every == 0) {

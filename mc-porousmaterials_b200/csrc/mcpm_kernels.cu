@@ -289,6 +289,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
         st.n = n; st.overflow = overflow; st.dr = dr; st.steps_done = step;
         st.pair = e_pair; st.wall = e_wall; st.energy = e_pair + e_wall;
         if (a.check_energy) { st.pair_check = c_pair; st.wall_check = c_wall; st.energy_check = c_pair + c_wall; }
+        if (a.check_energy == 2) { st.pair = c_pair; st.wall = c_wall; st.energy = c_pair + c_wall; }   // adopt, like BoxEnergy does
         S.replay_pos = rng.cursor();
         st.replay_consumed = rng.cursor();
     }
