@@ -454,9 +454,11 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
         if (!c->has_system[k]) return fail(MCPM_ERR_ARG, "set the system of chain %d first", k);
         maxn = std::max(maxn, c->h_state[k].st.n);
     }
-    if ((size_t)c->cap > k2_smem_limit_cap(c->max_smem))
-        return fail(MCPM_ERR_CAPACITY, "capacity %d does not fit the %d-byte shared-memory budget of one CTA", c->cap, c->max_smem);
-    if (threads == 0) threads = pick_threads(c, maxn);
+    const bool global_path = (size_t)c->cap > k2_smem_limit_cap(c->max_smem);   // positions stay in global memory / L2
+    if (threads == 0) threads = global_path ? 1024 : pick_threads(c, maxn);
+    bool all_fast = true;
+    for (int k = 0; k < c->n_chains; k++) all_fast = all_fast && c->h_state[k].fast_image;
+    threads = k2_threads_supported(threads, global_path, all_fast);
     bool need_init = false;
     for (int k = 0; k < c->n_chains; k++) need_init |= !c->h_state[k].energy_valid;
     if (need_init) {  // exact bookkeeping starts from a full BoxEnergy evaluation (src/energy.cpp:20)
@@ -495,7 +497,7 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
         a.trace = c->d_trace; a.trace_stride = nsteps;
     }
     CU(cudaEventRecord(c->ev0, c->stream));
-    CU(launch_k2(p->rng_mode, c->n_chains, threads, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->stream));
+    CU(launch_k2(p->rng_mode, c->n_chains, threads, all_fast, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->max_smem, c->stream));
     CU(cudaEventRecord(c->ev1, c->stream));
     c->launches++;
     if (p->trace) CU(cudaMemcpyAsync(p->trace, c->d_trace, (size_t)c->n_chains * nsteps, cudaMemcpyDeviceToHost, c->stream));

@@ -44,7 +44,7 @@ __device__ __forceinline__ void load_slot(const double* xs, const double* ys, co
 // particle itself" (-1: none).  Independent accumulators give the scheduler 4 dependent chains to
 // interleave (each pair evaluation is a ~17-deep chain of fp64 ops).
 template <bool FAST, bool PBZ>
-__device__ __forceinline__ void pair_sum2(const double* __restrict__ xs, const double* __restrict__ ys, const double* __restrict__ zs,
+__device__ __forceinline__ void pair_sum2(const double* xs, const double* ys, const double* zs,
                                           int n, int self, const PairGeom& g, double xa, double ya, double za, double xb, double yb,
                                           double zb, int tid, int T, double& ea, double& eb) {
     double a0 = 0.0, b0 = 0.0, a1 = 0.0, b1 = 0.0;
@@ -65,7 +65,7 @@ __device__ __forceinline__ void pair_sum2(const double* __restrict__ xs, const d
     ea = a0 + a1; eb = b0 + b1;
 }
 template <bool FAST, bool PBZ>
-__device__ __forceinline__ double pair_sum1(const double* __restrict__ xs, const double* __restrict__ ys, const double* __restrict__ zs,
+__device__ __forceinline__ double pair_sum1(const double* xs, const double* ys, const double* zs,
                                             int n, int self, const PairGeom& g, double xa, double ya, double za, int tid, int T) {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     int j = tid;
@@ -295,39 +295,42 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
     }
 }
 
-template <int RNG_MODE, int MAXT, int MINB>
+// GLOBAL = false: the chain's positions are staged into shared memory for the whole launch (the normal case).
+// GLOBAL = true : chains too large for one CTA's shared memory (capacity > ~9.5k particles, e.g. config C4 with
+//                 N = 20 000) are advanced in place in global memory; their 24 B x N working set stays L2-resident
+//                 (480 KB at N = 20k vs 126 MB of L2).  Plain (coherent) loads: a slot written by its owner thread
+//                 is visible to the CTA after the step's __syncthreads.
+template <int RNG_MODE, int MAXT, int MINB, bool GLOBAL, bool FAST>
 __global__ void __launch_bounds__(MAXT, MINB) k2_chains(const ChainParams* __restrict__ params, ChainState* __restrict__ states,
-                                                  const int* __restrict__ order, double* __restrict__ X, double* __restrict__ Y,
-                                                  double* __restrict__ Z, RunArgs a) {
+                                                  const int* __restrict__ order, double* X, double* Y, double* Z, RunArgs a) {
     extern __shared__ double smem[];
     const int chain = order[blockIdx.x];
     const int cap = a.cap;
-    double* xs = smem;
-    double* ys = xs + cap;
-    double* zs = ys + cap;
-    double* partials = zs + cap;  // 2 parities x 32 warps x 2 values
+    const size_t off = (size_t)chain * (size_t)cap;
+    double* xs = GLOBAL ? X + off : smem;
+    double* ys = GLOBAL ? Y + off : smem + cap;
+    double* zs = GLOBAL ? Z + off : smem + 2 * cap;
+    double* partials = GLOBAL ? smem : smem + 3 * cap;  // 2 parities x 32 warps x 2 values
     __shared__ ChainParams P;
     __shared__ ChainState S;
     const int tid = threadIdx.x, T = blockDim.x;
     if (tid == 0) { P = params[chain]; S = states[chain]; }
     __syncthreads();
-    const size_t off = (size_t)chain * (size_t)cap;
-    // stage every slot (not only the n live ones): stale slots are observable through quirk Q12
-    for (int j = tid; j < cap; j += T) { xs[j] = X[off + j]; ys[j] = Y[off + j]; zs[j] = Z[off + j]; }
-    __syncthreads();
+    if (!GLOBAL) {
+        // stage every slot (not only the n live ones): stale slots are observable through quirk Q12
+        for (int j = tid; j < cap; j += T) { xs[j] = X[off + j]; ys[j] = Y[off + j]; zs[j] = Z[off + j]; }
+        __syncthreads();
+    }
 
     unsigned char* trace = a.trace ? a.trace + (unsigned long long)chain * a.trace_stride : nullptr;
-    const bool multi = T > 32, pbz = P.pbc[2] != 0;
-#define MCPM_GO(SRC, F, M, Z) chain_loop<SRC, F, M, Z>(P, S, rng, xs, ys, zs, partials, a, trace, cap, (uint32_t)chain)
-#define MCPM_DISPATCH(SRC)                                                                  \
-    do {                                                                                    \
-        if (S.fast_image) {                                                                 \
-            if (multi) { if (pbz) MCPM_GO(SRC, true, true, true); else MCPM_GO(SRC, true, true, false); }      \
-            else { if (pbz) MCPM_GO(SRC, true, false, true); else MCPM_GO(SRC, true, false, false); }           \
-        } else {                                                                            \
-            if (multi) { if (pbz) MCPM_GO(SRC, false, true, true); else MCPM_GO(SRC, false, true, false); }    \
-            else { if (pbz) MCPM_GO(SRC, false, false, true); else MCPM_GO(SRC, false, false, false); }         \
-        }                                                                                   \
+    // FAST (all chains of the launch have their coordinates inside the box) is decided by the host per launch;
+    // only the smallest CTA variant can run with a single warp, so MULTI is a compile-time fact elsewhere.
+    const bool multi = (MAXT > 64) || T > 32, pbz = P.pbc[2] != 0;
+#define MCPM_GO(SRC, M, Z) chain_loop<SRC, FAST, M, Z>(P, S, rng, xs, ys, zs, partials, a, trace, cap, (uint32_t)chain)
+#define MCPM_DISPATCH(SRC)                                                                           \
+    do {                                                                                             \
+        if (MAXT > 64 || multi) { if (pbz) MCPM_GO(SRC, true, true); else MCPM_GO(SRC, true, false); } \
+        else { if (pbz) MCPM_GO(SRC, false, true); else MCPM_GO(SRC, false, false); }                  \
     } while (0)
     if (RNG_MODE == MCPM_RNG_PHILOX) {
         PhiloxSource rng; rng.init(a.seed, (uint32_t)chain, S.st.steps_done, tid & 31);
@@ -339,7 +342,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k2_chains(const ChainParams* __res
 #undef MCPM_DISPATCH
 #undef MCPM_GO
     __syncthreads();
-    for (int j = tid; j < cap; j += T) { X[off + j] = xs[j]; Y[off + j] = ys[j]; Z[off + j] = zs[j]; }
+    if (!GLOBAL) for (int j = tid; j < cap; j += T) { X[off + j] = xs[j]; Y[off + j] = ys[j]; Z[off + j] = zs[j]; }
     if (tid == 0) states[chain] = S;
 }
 
@@ -526,26 +529,46 @@ __global__ void philox_fill_kernel(unsigned long long seed, unsigned int chain, 
 // ================================================================================================
 static size_t k2_smem_bytes(int cap) { return (size_t)(3 * cap + 128) * sizeof(double); }
 
-cudaError_t launch_k2(int rng_mode, int n_chains, int threads, const ChainParams* params, ChainState* states, const int* order,
-                      double* X, double* Y, double* Z, const RunArgs& a, cudaStream_t stream) {
-    size_t smem = k2_smem_bytes(a.cap);
-    cudaError_t err;
+size_t k2_smem_limit_cap(int max_smem_optin) { return ((size_t)max_smem_optin / sizeof(double) - 128 - 64) / 3; }
+
+template <int RNG_MODE>
+static cudaError_t launch_k2_rng(int n_chains, int threads, bool global, bool fast, size_t smem, const ChainParams* params,
+                                 ChainState* states, const int* order, double* X, double* Y, double* Z, const RunArgs& a,
+                                 cudaStream_t stream) {
     auto go = [&](auto kern) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         kern<<<n_chains, threads, smem, stream>>>(params, states, order, X, Y, Z, a);
         return cudaSuccess;
     };
-    // register budgets by CTA size: <=64 threads -> up to 128 regs, <=256 -> 128, else 64
-    if (rng_mode == MCPM_RNG_PHILOX)
-        err = threads <= 64 ? go(k2_chains<MCPM_RNG_PHILOX, 64, 8>) : threads <= 256 ? go(k2_chains<MCPM_RNG_PHILOX, 256, 2>) : go(k2_chains<MCPM_RNG_PHILOX, 1024, 1>);
-    else
-        err = threads <= 64 ? go(k2_chains<MCPM_RNG_REPLAY, 64, 8>) : threads <= 256 ? go(k2_chains<MCPM_RNG_REPLAY, 256, 2>) : go(k2_chains<MCPM_RNG_REPLAY, 1024, 1>);
+    // register budgets by CTA size (ptxas: no spills at 128): <=64, <=256, <=512 threads -> 128 regs; 1024 -> 64.
+    // The general-minimum-image kernels (coordinates outside the box) exist for one shared-memory and one
+    // global-memory CTA shape; k2_threads_supported() clamps the thread count accordingly.
+    if (!fast) return global ? go(k2_chains<RNG_MODE, 1024, 1, true, false>) : go(k2_chains<RNG_MODE, 256, 2, false, false>);
+    if (global) return threads <= 512 ? go(k2_chains<RNG_MODE, 512, 1, true, true>) : go(k2_chains<RNG_MODE, 1024, 1, true, true>);
+    if (threads <= 64) return go(k2_chains<RNG_MODE, 64, 8, false, true>);
+    if (threads <= 256) return go(k2_chains<RNG_MODE, 256, 2, false, true>);
+    if (threads <= 512) return go(k2_chains<RNG_MODE, 512, 1, false, true>);
+    return go(k2_chains<RNG_MODE, 1024, 1, false, true>);
+}
+
+int k2_threads_supported(int threads, bool global, bool fast) {
+    if (!fast && !global) return threads < 64 ? 64 : (threads > 256 ? 256 : threads);   // (256,2) kernel: multi-warp only
+    if (!fast && global) return threads < 64 ? 64 : threads;
+    if (global && threads < 64) return 64;
+    return threads;
+}
+
+cudaError_t launch_k2(int rng_mode, int n_chains, int threads, bool fast, const ChainParams* params, ChainState* states, const int* order,
+                      double* X, double* Y, double* Z, const RunArgs& a, int max_smem_optin, cudaStream_t stream) {
+    const bool global = (size_t)a.cap > k2_smem_limit_cap(max_smem_optin);
+    const size_t smem = global ? 128 * sizeof(double) : k2_smem_bytes(a.cap);
+    cudaError_t err = rng_mode == MCPM_RNG_PHILOX
+                          ? launch_k2_rng<MCPM_RNG_PHILOX>(n_chains, threads, global, fast, smem, params, states, order, X, Y, Z, a, stream)
+                          : launch_k2_rng<MCPM_RNG_REPLAY>(n_chains, threads, global, fast, smem, params, states, order, X, Y, Z, a, stream);
     if (err != cudaSuccess) return err;
     return cudaGetLastError();
 }
-
-size_t k2_smem_limit_cap(int max_smem_optin) { return ((size_t)max_smem_optin / sizeof(double) - 128 - 64) / 3; }
 
 cudaError_t launch_k1(bool fast, int blocks, const ChainParams* params, const ChainState* states, const double* X, const double* Y,
                       const double* Z, int chain, int cap, int index, int has_trial, const double* t, double* scratch,

@@ -6,9 +6,10 @@
 
 namespace mcpm {
 
-cudaError_t launch_k2(int rng_mode, int n_chains, int threads, const ChainParams* params, ChainState* states, const int* order,
-                      double* X, double* Y, double* Z, const RunArgs& a, cudaStream_t stream);
+cudaError_t launch_k2(int rng_mode, int n_chains, int threads, bool fast, const ChainParams* params, ChainState* states, const int* order,
+                      double* X, double* Y, double* Z, const RunArgs& a, int max_smem_optin, cudaStream_t stream);
 size_t k2_smem_limit_cap(int max_smem_optin);
+int k2_threads_supported(int threads, bool global, bool fast);
 
 cudaError_t launch_k1(bool fast, int blocks, const ChainParams* params, const ChainState* states, const double* X, const double* Y,
                       const double* Z, int chain, int cap, int index, int has_trial, const double* trial, double* scratch,

@@ -154,3 +154,56 @@ def test_capacity_overflow_is_reported(mcpm):
             e.run(1, 1, 20000, seed=1)
         assert ei.value.code == 3
         assert e.stats()[0].overflow == 1
+
+
+def _replay_vs_oracle(mcpm, system, x, y, z, capacity, threads, nsteps, seed):
+    u = O.mt_uniforms(seed, 8 * nsteps)
+    o = O.COracle(system, capacity)
+    o.set_positions(x, y, z)
+    o.box_energy()
+    o.replay(u)
+    otr = o.run_sets(1, 1, nsteps, 0, True)
+    with mcpm.Engine(1, capacity) as e:
+        e.set_system(system)
+        e.set_positions(0, x, y, z)
+        stats, tr = e.run(1, 1, nsteps, replay=u, trace=True, threads=threads, check_energy=1)
+        gx, gy, gz = e.get_positions(0)
+    div = first_divergence(tr[0], otr)
+    assert div == -1, f"first divergence at step {div}"
+    ox, oy, oz = o.get_positions()
+    assert np.array_equal(gx, ox) and np.array_equal(gy, oy) and np.array_equal(gz, oz)
+    st, ost = stats[0], o.state()
+    assert st.n == ost["n"] and st.replay_consumed == o.draws()
+    assert st.energy == pytest.approx(st.energy_check, rel=RTOL)
+    assert st.energy == pytest.approx(ost["exact_energy"], rel=RTOL)
+
+
+@pytest.mark.parametrize("threads", [32, 64, 256, 512])
+def test_general_minimum_image_chain(mcpm, golden, threads):
+    """Coordinates outside the box (a restart file may hold them): the chain must use the reference's general
+    d -= round(d/L)*L image, and moved particles are wrapped exactly as MC::PBC does."""
+    arrays, meta = golden
+    s = system_from_meta(meta["c1"]["system"])
+    x, y, z = arrays["c1_x"].copy(), arrays["c1_y"].copy(), arrays["c1_z"].copy()
+    rng = np.random.default_rng(5)
+    x += 40.0 * rng.integers(-2, 3, size=len(x)); y += 40.0 * rng.integers(-2, 3, size=len(y))
+    _replay_vs_oracle(mcpm, s, x, y, z, 1024, threads, 3000, 77)
+
+
+@pytest.mark.parametrize("capacity,threads", [(6016, 512), (6016, 1024), (12000, 512), (12000, 1024), (12000, 0)])
+def test_large_chains_shared_and_global_memory_paths(mcpm, capacity, threads):
+    """N = 3000 CH4-like slit: capacity 6016 is staged in shared memory (144 KB), capacity 12000 exceeds one CTA's
+    shared memory and is advanced in place in global memory (the path config C4, N = 20 000, takes)."""
+    s = O.methane_slit(rcut=60.0, mu=-3050.0)
+    rng = np.random.default_rng(11)
+    n = 3000
+    x, y, z = rng.random(n) * 120.0, rng.random(n) * 120.0, 3.5 + rng.random(n) * 13.0
+    _replay_vs_oracle(mcpm, s, x, y, z, capacity, threads, 400, 123)
+
+
+def test_bulk_global_path_translations_only(mcpm):
+    s = O.argon_bulk(size=70.0, rcut=12.0)
+    rng = np.random.default_rng(12)
+    n = 5000
+    x, y, z = rng.random(n) * 70.0, rng.random(n) * 70.0, rng.random(n) * 70.0
+    _replay_vs_oracle(mcpm, s, x, y, z, 10240, 1024, 300, 9)
