@@ -45,6 +45,57 @@ def load_start():
     return pts
 
 
+def build_workload(config, replicas, steps_per_set):
+    """BASELINE.json configs -> dict(points=[(SystemDesc, x, y, z, dr)], replicas, steps_per_set, ...).
+    Chains are laid out replica-major: chain = replica * n_points + point."""
+    from mcpm_b200 import workloads
+    w = {"config": config, "flop_per_pair": FLOP_PER_PAIR_SLIT, "steps_per_set": steps_per_set, "equil_steps": 0}
+    if config in ("c1", "c2"):
+        pts = load_start()
+        if config == "c1":
+            pts = pts[-1:]                       # mu = -1134 K
+            w["workload"] = "C1 Ar in graphite slit, single mu=-1134 K (H=20A, rcut=20A, T=87K, N~560, disp:swap=1:1)"
+            w["replicas"] = replicas or 2048
+        else:
+            w["workload"] = "C2 40-point Ar isotherm (mu_k=-1800+k*666/39 K, H=20A, rcut=20A, T=87K, disp:swap=1:1)"
+            w["replicas"] = replicas or 64
+        w["points"] = [(workloads.argon_slit(mu=mu, n_equil_sets=0), x, y, z, dr) for (mu, x, y, z, dr) in pts]
+        w["start"] = "tests/golden/isotherm_c2_start.npz"
+    elif config == "c3":
+        g = np.load(os.path.join(ROOT, "tests", "golden", "c3_start.npz"))
+        w["workload"] = "C3 CH4 in slit, 300 K, mu=-3050 K, Rcut 92 (L=184A), N~5.4k, disp:swap=1:3"
+        w["points"] = [(workloads.methane_slit(n_equil_sets=0), g["x"], g["y"], g["z"], float(g["dr"]))]
+        w["replicas"] = replicas or 148
+        w["steps_per_set"] = steps_per_set or 2000
+        w["start"] = "tests/golden/c3_start.npz"
+    elif config == "c4":
+        rng = np.random.default_rng(2024)
+        site = np.arange(28) * (100.0 / 28)
+        gx, gy, gz = np.meshgrid(site, site, site, indexing="ij")
+        p = np.column_stack([gx.ravel(), gy.ravel(), gz.ravel()])[:20000] + (rng.random((20000, 3)) - 0.5) * 0.4 + 0.3
+        w["workload"] = "C4 dense NVT LJ argon, bulk L=100A, rcut=12A, T=120K, N=20000, translations only (O(N) scan, global-memory path)"
+        w["points"] = [(workloads.argon_bulk(n_equil_sets=0), p[:, 0].copy(), p[:, 1].copy(), p[:, 2].copy(), 0.5)]
+        w["replicas"] = replicas or 148
+        w["steps_per_set"] = steps_per_set or 500
+        w["flop_per_pair"] = 25
+        w["start"] = "simple-cubic 28^3 lattice, first 20000 sites, +-0.2A jitter (numpy default_rng(2024))"
+    elif config == "c5":
+        rng = np.random.default_rng(12345)
+        pts = []
+        for d in workloads.replica_sweep():
+            n0 = 100
+            pts.append((d, rng.random(n0) * d.width[0], rng.random(n0) * d.width[1], 3.0 + rng.random(n0) * (d.width[2] - 6.0), 0.1 * d.width[2]))
+        w["workload"] = "C5 1024 replica chains per GPU: H in 8..39A x T in 77..139K, Rcut 17 (L=34A), mu(T)=T ln(8.44e-5 Lambda^3), N0=100"
+        w["points"] = pts
+        w["replicas"] = replicas or 1
+        w["equil_steps"] = 200000              # untimed: random start -> equilibrated loadings
+        w["start"] = "100 random particles per chain (numpy default_rng(12345)), 200k untimed equilibration steps on the device"
+    else:
+        raise SystemExit(f"unknown config {config}")
+    w["steps_per_set"] = w["steps_per_set"] or 10000
+    return w
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -128,32 +179,41 @@ def barrier(dist, local):
     torch.cuda.synchronize(local)
 
 
-def cpu_points(pts, sysfn):
-    from mcpm_b200 import workloads  # noqa: F401
+def cpu_points(w, max_points=40):
+    """A bounded sample of the workload's state points for the CPU arm (all of them for C1-C4)."""
+    pts = w["points"]
+    idx = list(range(len(pts))) if len(pts) <= max_points else [int(round(k * (len(pts) - 1) / (max_points - 1))) for k in range(max_points)]
     out = []
-    for k, (mu, x, y, z, dr) in enumerate(pts):
-        s = sysfn(mu)
+    for k in idx:
+        s, x, y, z, dr = pts[k]
         d = {name: (list(getattr(s, name)) if name == "width" else getattr(s, name)) for name, _ in s._fields_ if name != "reserved"}
         out.append((k, d, x, y, z, dr, 5000 + k))
     return out
 
 
-def run_cpu_sample(pool, pts, steps, correct=1):
-    from mcpm_b200 import workloads
-    points = cpu_points(pts, lambda mu: workloads.argon_slit(mu=mu, n_equil_sets=0))
-    return pool.time_points(points, steps, correct=correct)
+def run_cpu_sample(pool, w, steps, correct=1):
+    return pool.time_points(cpu_points(w), steps, correct=correct)
+
+
+def cpu_steps_for(w, args):
+    """Steps per state point of the CPU sample, sized for ~10-30 s of CPU work (cost per step ~ N, N^2 recomputes)."""
+    if args.cpu_steps:
+        return args.cpu_steps
+    nmax = max(len(p[1]) for p in w["points"])
+    return 4000 if nmax < 1000 else (150 if nmax < 10000 else 20)
 
 
 def reference_arm(args, world, rank):
     if rank != 0:
         return
     from oracle import cpu_baseline
-    pts = load_start()
+    w = build_workload(args.config, args.replicas, args.steps_per_set)
+    steps = cpu_steps_for(w, args)
     pool = cpu_baseline.CpuPool()
     t_all = []
     res = None
     for it in range(args.warmup + args.steps):
-        res = run_cpu_sample(pool, pts, args.cpu_steps, correct=1)
+        res = run_cpu_sample(pool, w, steps, correct=1)
         if it >= args.warmup:
             t_all.append(res)
     pool.close()
@@ -161,13 +221,12 @@ def reference_arm(args, world, rank):
     cpu_seconds = sum(r["cpu_seconds"] for r in t_all)
     cores = t_all[0]["cores"]
     value = total_steps * cores / cpu_seconds
-    sample = f"{len(pts)} state points x {args.cpu_steps} steps of the as-shipped loop (MoveParticle/SwapParticle + CorrectEnergy) per step"
+    sample = f"{res['points']} state points x {steps} steps of the as-shipped loop (MoveParticle/SwapParticle + CorrectEnergy) per step"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * cpu_seconds / cores / len(t_all), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2 40-point Ar isotherm (mu_k=-1800+k*666/39 K, H=20A, rcut=20A, T=87K, disp:swap=1:1), reference CPU path",
-                   "steps_per_point": args.cpu_steps, "start": "tests/golden/isotherm_c2_start.npz"},
+        "config": {"workload": w["workload"] + ", reference CPU path", "steps_per_point": steps, "start": w["start"]},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": res["kind"], "sample": sample,
                          "per_core": total_steps / cpu_seconds, "makespan_rate": res["moves_per_s_makespan"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -181,24 +240,31 @@ def gpu_arm(args, world, rank, local, dist):
     import mcpm_b200 as m
     from mcpm_b200 import workloads
 
-    pts = load_start()
-    P, R, S = len(pts), args.replicas, args.steps_per_set
+    w = build_workload(args.config, args.replicas, args.steps_per_set)
+    pts = w["points"]
+    P, R, S = len(pts), w["replicas"], w["steps_per_set"]
     n_chains = P * R
-    cap = int(-(-int(max(len(p[1]) for p in pts) * 1.2 + 64) // 32) * 32)
+    nmax = max(len(p[1]) for p in pts)
+    cap = args.capacity or int(-(-int(nmax * 1.2 + 64) // 32) * 32)
+    if args.config == "c5":
+        cap = args.capacity or 1024
     eng = m.Engine(n_chains, cap, device=local)
     cap = eng.capacity
-    seed = 20240611 + 7919 * rank           # every rank: its own replicas of the isotherm
+    seed = 20240611 + 7919 * rank           # every rank: its own replicas of the workload
     n0 = np.zeros(n_chains, dtype=np.int32)
     hx = torch.zeros((n_chains, cap), dtype=torch.float64).pin_memory()
     hy = torch.zeros_like(hx).pin_memory(); hz = torch.zeros_like(hx).pin_memory()
     X, Y, Z = hx.numpy(), hy.numpy(), hz.numpy()
     for c in range(n_chains):
-        mu, x, y, z, dr = pts[c % P]
-        eng.set_system(workloads.argon_slit(mu=mu, n_equil_sets=0), c)
+        sysd, x, y, z, dr = pts[c % P]
+        eng.set_system(sysd, c)
         eng.set_dr(c, dr)
         n0[c] = len(x)
         X[c, :len(x)] = x; Y[c, :len(x)] = y; Z[c, :len(x)] = z
     eng.set_positions_all(n0, X, Y, Z)
+    if w["equil_steps"]:
+        eng.run(1, 1, w["equil_steps"], seed=seed + 1, threads=args.threads, check_energy=2)
+        eng.reset_accumulators()
     flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=f"cuda:{local}")
 
     def one_step(set_index):
@@ -241,15 +307,18 @@ def gpu_arm(args, world, rank, local, dist):
     nbuf = np.zeros(n_chains, dtype=np.int32)
     n_host, _, _, _ = eng.get_positions_all(X, Y, Z)
     nbuf[:] = n_host
+    e_pair = np.array([s.pair for s in stats]); e_wall = np.array([s.wall for s in stats])   # the host owns the state
     barrier(dist, local)
     e2e_s = 0.0
     for _ in range(args.steps):
         torch.cuda.synchronize(local)
         t0 = time.perf_counter()
         eng.set_positions_all(nbuf, X, Y, Z)                    # H2D: every chain's positions, pinned host memory
-        st = one_step(set_index); set_index += 1              # K2 (+ the K3 initialisation the upload invalidated)
+        eng.set_running_energy(e_pair, e_wall)                  # ... and their running energies (else K3 re-evaluates them)
+        st = one_step(set_index); set_index += 1              # K2
         n_host, _, _, _ = eng.get_positions_all(X, Y, Z)        # D2H: positions; statistics came back with run()
         nbuf[:] = n_host
+        e_pair = np.array([s.pair for s in st]); e_wall = np.array([s.wall for s in st])
         e2e_s += time.perf_counter() - t0
     barrier(dist, local)
     e2e_s = allmax(dist, local, e2e_s)
@@ -263,7 +332,7 @@ def gpu_arm(args, world, rank, local, dist):
     peak_tflops, _ = m.fp64_peak_tflops(local)
     k_ms = float(np.mean(kern_ms))
     evals_per_launch = float(np.mean(evals))
-    achieved = FLOP_PER_PAIR_SLIT * evals_per_launch / (k_ms * 1e-3) * 1e-12
+    achieved = w["flop_per_pair"] * evals_per_launch / (k_ms * 1e-3) * 1e-12
     traffic = None
     summ = os.path.join(ROOT, "profiles", "k2_ncu_summary.json")
     if os.path.exists(summ):
@@ -273,7 +342,7 @@ def gpu_arm(args, world, rank, local, dist):
             traffic = None
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
                 "traffic": traffic, "kernel": "k2_chains", "kernel_ms": k_ms,
-                "algorithmic": f"{FLOP_PER_PAIR_SLIT} flop x {evals_per_launch:.4g} pair evals per launch",
+                "algorithmic": f"{w['flop_per_pair']} flop x {evals_per_launch:.4g} pair evals per launch",
                 "peak_source": "mcpm_fp64_peak DFMA microbenchmark, measured live (MEASURED_PEAKS.json has no fp64 figure)",
                 "pair_evals_per_s": evals_per_launch / (k_ms * 1e-3),
                 "smem_bytes_per_s": BYTES_PER_PAIR * evals_per_launch / (k_ms * 1e-3)}
@@ -281,10 +350,10 @@ def gpu_arm(args, world, rank, local, dist):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2 40-point Ar isotherm (mu_k=-1800+k*666/39 K, H=20A, rcut=20A, T=87K, disp:swap=1:1)",
+        "config": {"workload": w["workload"],
                    "state_points": P, "replicas_per_point_per_gpu": R, "chains_per_gpu": n_chains, "steps_per_set": S,
                    "capacity": cap, "mean_particles": mean_n, "threads_per_chain": args.threads or "auto",
-                   "start": "tests/golden/isotherm_c2_start.npz", "rng": "device Philox4x32-10",
+                   "start": w["start"], "rng": "device Philox4x32-10",
                    "l2": "256 MiB device write between timed steps (L2 flush)"},
         "pair_evals_per_s": evals_all / t_dev,
         "wall_s_timed_region": t_wall,
@@ -296,12 +365,13 @@ def gpu_arm(args, world, rank, local, dist):
     if world == 1 and not args.no_cpu:
         from oracle import cpu_baseline
         pool = cpu_baseline.CpuPool()
-        res = run_cpu_sample(pool, pts, args.cpu_steps, correct=1)
-        fair = run_cpu_sample(pool, pts, args.cpu_steps, correct=0)
+        cs = cpu_steps_for(w, args)
+        res = run_cpu_sample(pool, w, cs, correct=1)
+        fair = run_cpu_sample(pool, w, cs, correct=0)
         pool.close()
         line["cpu_baseline"] = {
             "value": res["moves_per_s"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"],
-            "sample": f"{P} state points x {args.cpu_steps} steps each of the as-shipped loop (MoveParticle/SwapParticle + CorrectEnergy), "
+            "sample": f"{res['points']} state points x {cs} steps each of the as-shipped loop (MoveParticle/SwapParticle + CorrectEnergy), "
                       f"one reference process per core, perfectly balanced aggregate",
             "per_core": res["moves_per_s_per_core"], "makespan_rate": res["moves_per_s_makespan"],
             "without_correctenergy_recompute": fair["moves_per_s"],
@@ -315,10 +385,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--replicas", type=int, default=64, help="replica chains per state point per GPU")
-    ap.add_argument("--steps-per-set", type=int, default=10000)
+    ap.add_argument("--replicas", type=int, default=0, help="replica chains per state point per GPU")
+    ap.add_argument("--steps-per-set", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0, help="threads per chain (0 = engine heuristic)")
-    ap.add_argument("--cpu-steps", type=int, default=4000, help="steps per state point of the CPU sample")
+    ap.add_argument("--cpu-steps", type=int, default=0, help="steps per state point of the CPU sample (0 = sized from N)")
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"], help="BASELINE.json config (default: the isotherm)")
+    ap.add_argument("--capacity", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -86,6 +86,8 @@ typedef struct mcpm_run_params {
                                   (move<<1)|accepted; move 0 translation, 1 insertion, 2 deletion,
                                   3 deletion branch on an empty box */
     int threads_per_chain;     /* CTA size, multiple of 32 up to 1024; 0 = choose from the loadings */
+    int sample_rdf;            /* !=0: MC::ComputeRDF (src/sample.cpp:14-44) after every production step: O(N^2) 100-bin
+                                  histogram out to rcut, accumulated per chain; read it with mcpm_get_rdf */
     int check_energy;          /* 1: recompute the full box energy on the device at the end (drift check, reported in
                                   *_check); 2: also adopt it as the running energy, as MC::BoxEnergy does */
 } mcpm_run_params;
@@ -107,6 +109,10 @@ typedef struct mcpm_chain_stats {
     double sum_n, sum_n2, sum_e, sum_e2;
     long long samples;
     unsigned long long replay_consumed; /* REPLAY mode: uniforms consumed by the last mcpm_run */
+    /* Widom / BAR sampling of the LAST set (MC::ComputeWidom, src/moves.cpp:410-449; active like in the reference when
+     * n_swap == 0, in production sets; ResetStats restarts the counts at ONE and the sums at 0 every set) */
+    double widom_insert, widom_delete;
+    long long widom_insertions, widom_deletions;
 } mcpm_chain_stats;
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -158,6 +164,15 @@ int mcpm_remove_swap_last(mcpm_ctx* ctx, int chain, int index);
 int mcpm_run(mcpm_ctx* ctx, const mcpm_run_params* params, mcpm_chain_stats* stats /* [n_chains], nullable */);
 int mcpm_get_stats(mcpm_ctx* ctx, mcpm_chain_stats* stats /* [n_chains] */);
 int mcpm_reset_accumulators(mcpm_ctx* ctx);
+/* Accumulated pair-distance histogram of one chain: hist[0..99] = MC::Stats::rdf(0..99) (bin 0 is never filled,
+ * each pair adds 2, src/sample.cpp:27-28).  mcpm_reset_accumulators clears it. */
+int mcpm_get_rdf(mcpm_ctx* ctx, int chain, double* hist /* 100 */);
+/* mu_ex and mu (K) from the Widom/BAR sums of the last set == MC::ComputeChemicalPotential, src/moves.cpp:453-465. */
+int mcpm_chemical_potential(mcpm_ctx* ctx, int chain, double* mu_ex, double* mu);
+/* Hand the running box energies (pair already halved, wall) of every chain back to the engine after an upload of
+ * positions whose energies the caller already knows (e.g. from the previous mcpm_run's statistics): skips the
+ * full K3 evaluation that mcpm_run would otherwise do to initialise its exact bookkeeping. */
+int mcpm_set_running_energy(mcpm_ctx* ctx, const double* pair /* [n_chains] */, const double* wall /* [n_chains] */);
 /* Override a chain's translation amplitude / global step counter (restart, tests). */
 int mcpm_set_dr(mcpm_ctx* ctx, int chain, double dr);
 int mcpm_set_step_counter(mcpm_ctx* ctx, int chain, unsigned long long step);

@@ -227,7 +227,8 @@ void print_trajectory(const Outputs& o, const mcpm_sim_config& c, const mcpm_sys
 }
 
 // MC::PrintLog, src/print.cpp:193-233.  q5 = reproduce the double-halved pair column (quirk Q5).
-void print_log(const Outputs& o, const mcpm_sim_config& c, const mcpm_system_desc& d, size_t set, const mcpm_chain_stats* st, bool q5) {
+void print_log(const Outputs& o, const mcpm_sim_config& c, const mcpm_system_desc& d, size_t set, const mcpm_chain_stats* st, bool q5,
+               bool have_mu = false, double mu_ex = 0., double mu = 0.) {
     const std::string name = o.box_dir + "/simulation_" + c.fluid + ".log";
     std::ofstream f;
     if (set == 0) {
@@ -250,7 +251,8 @@ void print_log(const Outputs& o, const mcpm_sim_config& c, const mcpm_system_des
     f << st->n << "\t" << density << "\t";
     // muEx / mu: with swap moves on, Widom sampling is off (src/moves.cpp:415) and ComputeChemicalPotential divides
     // 0 by 0: the reference's log shows "nan" and "-nan" in these two columns
-    f << "nan" << "\t" << "-nan" << "\n";
+    if (have_mu) f << mu_ex << "\t" << mu << "\n";      // NVT: Widom/BAR values of the last set (ComputeChemicalPotential)
+    else f << "nan" << "\t" << "-nan" << "\n";
 }
 
 // MC::PrintStats, src/print.cpp:234-264
@@ -433,6 +435,7 @@ extern "C" int mcpm_simulate(const char* input_path, const char* out_dir, int fl
         mcpm_run_params rp;
         memset(&rp, 0, sizeof(rp));
         rp.first_set = set; rp.n_sets = last - set + 1; rp.steps_per_set = steps_per_set; rp.rng_mode = MCPM_RNG_PHILOX; rp.seed = seed;
+        rp.sample_rdf = cfg.sample_rdf;
         rp.check_energy = 2;   // re-anchor the running energies at every print interval (src/energy.cpp:35-42 in spirit)
         rc = run_all(rp);
         if (rc) return rc;
@@ -444,13 +447,39 @@ extern "C" int mcpm_simulate(const char* input_path, const char* out_dir, int fl
                     mcpm_get_positions(ctx[g], (int)k, &n, X[c].data(), Y[c].data(), Z[c].data());
                     if (c == 0) print_stats(cfg, desc[c], (size_t)last, &stats[g][k], log);
                     print_trajectory(outs[c], cfg, desc[c], (size_t)last, stats[g][k].dr, n, X[c].data(), Y[c].data(), Z[c].data());
-                    print_log(outs[c], cfg, desc[c], (size_t)last, &stats[g][k], q5);
+                    double mu_ex = 0., mu = 0.;
+                    const bool have_mu = desc[c].n_swap == 0 && last > n_equil;   // Widom sampling ran (src/moves.cpp:415, src/main.cpp:72)
+                    if (have_mu) mcpm_chemical_potential(ctx[g], (int)k, &mu_ex, &mu);
+                    print_log(outs[c], cfg, desc[c], (size_t)last, &stats[g][k], q5, have_mu, mu_ex, mu);
                 }
         }
         set = last + 1;
     }
     auto te = clock::now();
 
+    // MC::PrintRDF, src/print.cpp:127-162 (normalisation reproduced literally, including its use of ALL sets)
+    if (cfg.sample_rdf) {
+        const double NB = 100.;
+        for (int g = 0; g < G; g++)
+            for (size_t k = 0; k < owned[g].size(); k++) {
+                const int c = owned[g][k];
+                std::vector<double> hist(101, 0.0);
+                mcpm_get_rdf(ctx[g], (int)k, hist.data());
+                const double deltaR = desc[c].rcut / NB;
+                const int nParts = stats[g][k].n;
+                const double rho = nParts / box_volume(desc[c]);
+                const double constant = (4 * M_PI * rho / 3);
+                std::ofstream f(outs[c].box_dir + "/rdf_" + cfg.fluid + "-" + cfg.fluid + ".dat");
+                f << "nBins: " << 100 << std::endl;
+                f << "r(AA)\tg(r)" << std::endl;
+                for (int bin = 1; bin <= 100; bin++) {
+                    double gofr = hist[bin] / (1. * nParts * cfg.steps_per_set * cfg.n_sets);
+                    const double lowR = bin * deltaR, highR = lowR + deltaR;
+                    gofr /= constant * (ipow(highR, 3) - ipow(lowR, 3));
+                    f << (bin + 0.5) * deltaR << "\t" << gofr << std::endl;
+                }
+            }
+    }
     // final gather: per-state-point averages over replicas and production steps (the reference computes none)
     if (n_chains > 1) {
         std::ofstream iso(base + "/" + std::string(cfg.project) + "_isotherm.dat");

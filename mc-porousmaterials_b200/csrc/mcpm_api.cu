@@ -46,6 +46,7 @@ struct mcpm_ctx {
     unsigned int* d_counters = nullptr;
     double* d_out = nullptr;       // K1: 8 doubles; K3: 4 per chain
     double *d_pp = nullptr, *d_pw = nullptr;  // K3 per-particle outputs, one chain's worth
+    double* d_rdf = nullptr;       // [n_chains][MCPM_RDF_BINS]
     double* d_replay = nullptr; size_t replay_doubles = 0;
     unsigned char* d_trace = nullptr; size_t trace_bytes = 0;
     double* h_pin = nullptr;       // pinned staging, 4*n_chains+8 doubles
@@ -169,6 +170,8 @@ int mcpm_create(int device, int n_chains, int capacity, mcpm_ctx** out) {
     CU(cudaMalloc(&c->d_out, sizeof(double) * (4 * (size_t)n_chains + 8)));
     CU(cudaMalloc(&c->d_pp, sizeof(double) * c->cap));
     CU(cudaMalloc(&c->d_pw, sizeof(double) * c->cap));
+    CU(cudaMalloc(&c->d_rdf, sizeof(double) * MCPM_RDF_BINS * (size_t)n_chains));
+    CU(cudaMemsetAsync(c->d_rdf, 0, sizeof(double) * MCPM_RDF_BINS * (size_t)n_chains, c->stream));
     CU(cudaMallocHost(&c->h_pin, sizeof(double) * (4 * (size_t)n_chains + 8)));
     c->h_params.assign(n_chains, ChainParams());
     ChainState zero;
@@ -189,7 +192,7 @@ int mcpm_destroy(mcpm_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_params); cudaFree(c->d_state); cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_z);
     cudaFree(c->d_order); cudaFree(c->d_scratch); cudaFree(c->d_counters); cudaFree(c->d_out);
-    cudaFree(c->d_pp); cudaFree(c->d_pw); cudaFree(c->d_replay); cudaFree(c->d_trace);
+    cudaFree(c->d_pp); cudaFree(c->d_pw); cudaFree(c->d_rdf); cudaFree(c->d_replay); cudaFree(c->d_trace);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -432,13 +435,18 @@ int mcpm_remove_swap_last(mcpm_ctx* c, int chain, int index) {
 
 // ---- K2 ---------------------------------------------------------------------------------------
 static int pick_threads(const mcpm_ctx* c, int maxn) {
-    // Measured on B200 (scripts/latency_table.py): with at least ~2 chains per SM one warp per chain gives
-    // the highest aggregate rate (the per-step overhead — uniforms, wall term, reductions, decision — is paid
-    // once per warp); with fewer chains than SMs, spreading a large chain over 2-4 warps shortens its step.
-    if (c->n_chains >= 2 * c->num_sms) return 32;
-    if (maxn < 128) return 32;
-    if (maxn < 256 || c->n_chains >= c->num_sms) return 64;
-    return 128;
+    // Measured on B200 (scripts/latency_table.py, bench.py --config c1..c5 --threads T): aggregate throughput is best
+    // with ~8 warps resident per SM in total — one warp per chain when many chains share an SM (the per-step overhead:
+    // uniforms, wall term, reductions, decision, is paid once per warp), 256 threads when shared memory or the chain
+    // count leaves one chain per SM (C3: N = 5.4k, 157 KB of positions per CTA).
+    const size_t smem_per_cta = (size_t)(3 * c->cap + 232) * sizeof(double);
+    const int by_smem = std::max<int>(1, (int)((size_t)c->max_smem / smem_per_cta));
+    const int by_count = (c->n_chains + c->num_sms - 1) / c->num_sms;
+    const int resident = std::max(1, std::min(by_smem, by_count));
+    int t = 32;
+    while (t * 2 * resident <= 256) t *= 2;
+    while (t > 32 && t > maxn / 2) t /= 2;       // at least two partners per thread
+    return t;
 }
 
 int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
@@ -455,10 +463,12 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
         maxn = std::max(maxn, c->h_state[k].st.n);
     }
     const bool global_path = (size_t)c->cap > k2_smem_limit_cap(c->max_smem);   // positions stay in global memory / L2
-    if (threads == 0) threads = global_path ? 1024 : pick_threads(c, maxn);
+    if (threads == 0) threads = global_path ? 512 : pick_threads(c, maxn);
     bool all_fast = true;
     for (int k = 0; k < c->n_chains; k++) all_fast = all_fast && c->h_state[k].fast_image;
-    threads = k2_threads_supported(threads, global_path, all_fast);
+    bool sample = p->sample_rdf != 0;                       // in-kernel sampling: RDF on request, Widom whenever n_swap == 0
+    for (int k = 0; k < c->n_chains; k++) sample = sample || c->h_params[k].n_swap == 0;
+    threads = k2_threads_supported(threads, global_path, all_fast, sample);
     bool need_init = false;
     for (int k = 0; k < c->n_chains; k++) need_init |= !c->h_state[k].energy_valid;
     if (need_init) {  // exact bookkeeping starts from a full BoxEnergy evaluation (src/energy.cpp:20)
@@ -475,6 +485,7 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     memset(&a, 0, sizeof(a));
     a.first_set = p->first_set; a.n_sets = p->n_sets; a.steps_per_set = p->steps_per_set; a.seed = p->seed;
     a.check_energy = p->check_energy; a.cap = c->cap;
+    a.sample_rdf = p->sample_rdf; a.rdf = c->d_rdf;
     const unsigned long long nsteps = (unsigned long long)p->n_sets * (unsigned long long)p->steps_per_set;
     if (p->rng_mode == MCPM_RNG_REPLAY) {
         const size_t need = (size_t)c->n_chains * p->replay_stride;
@@ -497,7 +508,7 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
         a.trace = c->d_trace; a.trace_stride = nsteps;
     }
     CU(cudaEventRecord(c->ev0, c->stream));
-    CU(launch_k2(p->rng_mode, c->n_chains, threads, all_fast, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->max_smem, c->stream));
+    CU(launch_k2(p->rng_mode, c->n_chains, threads, all_fast, sample, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->max_smem, c->stream));
     CU(cudaEventRecord(c->ev1, c->stream));
     c->launches++;
     if (p->trace) CU(cudaMemcpyAsync(p->trace, c->d_trace, (size_t)c->n_chains * nsteps, cudaMemcpyDeviceToHost, c->stream));
@@ -526,6 +537,47 @@ int mcpm_reset_accumulators(mcpm_ctx* c) {
         st.sum_n = st.sum_n2 = st.sum_e = st.sum_e2 = 0.0; st.samples = 0;
         st.tot_disp = st.tot_disp_acc = st.tot_ins = st.tot_ins_acc = st.tot_del = st.tot_del_acc = st.tot_empty = 0;
         st.pair_evals = 0;
+    }
+    CU(cudaMemcpyAsync(c->d_state, c->h_state.data(), sizeof(ChainState) * c->n_chains, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(c->d_rdf, 0, sizeof(double) * MCPM_RDF_BINS * (size_t)c->n_chains, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return MCPM_OK;
+}
+
+int mcpm_get_rdf(mcpm_ctx* c, int chain, double* hist) {
+    int rc = check_chain(c, chain); if (rc) return rc;
+    if (!hist) return fail(MCPM_ERR_ARG, "null hist");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(hist, c->d_rdf + (size_t)chain * MCPM_RDF_BINS, sizeof(double) * MCPM_RDF_BINS, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return MCPM_OK;
+}
+
+// MC::ComputeChemicalPotential, src/moves.cpp:453-465
+int mcpm_chemical_potential(mcpm_ctx* c, int chain, double* mu_ex, double* mu) {
+    int rc = check_chain(c, chain); if (rc) return rc;
+    if (!c->has_system[chain]) return fail(MCPM_ERR_ARG, "chain %d has no system yet", chain);
+    const mcpm_system_desc& d = c->h_desc[chain];
+    const mcpm_chain_stats& st = c->h_state[chain].st;
+    const double kb = 1.380649e-23, na = 6.02214076e23, planck = 6.62607015e-34;
+    const double particleMass = d.molar_mass / na * 1e-3;
+    const double thermalWL = planck / sqrt(2.0 * M_PI * particleMass * kb * d.temperature) * 1e10;
+    const double volume = d.geometry == MCPM_GEOM_SLIT ? d.width[0] * d.width[1] * d.width[2] : ipow(d.width[2], 3);
+    const double widomParam = (st.widom_insert / st.widom_insertions) / (st.widom_delete / st.widom_deletions);
+    const double muIdeal = d.temperature * log(ipow(thermalWL, 3) * (st.n + 1) / volume);
+    const double muExcess = -d.temperature * log(widomParam);
+    if (mu_ex) *mu_ex = muExcess;
+    if (mu) *mu = muIdeal + muExcess;
+    return MCPM_OK;
+}
+
+int mcpm_set_running_energy(mcpm_ctx* c, const double* pair, const double* wall) {
+    if (!c || !pair || !wall) return fail(MCPM_ERR_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    for (int k = 0; k < c->n_chains; k++) {
+        mcpm_chain_stats& st = c->h_state[k].st;
+        st.pair = pair[k]; st.wall = wall[k]; st.energy = pair[k] + wall[k];
+        c->h_state[k].energy_valid = 1;
     }
     CU(cudaMemcpyAsync(c->d_state, c->h_state.data(), sizeof(ChainState) * c->n_chains, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));

@@ -163,9 +163,11 @@ __device__ __forceinline__ double u53(uint32_t lo, uint32_t hi) {
 }
 
 // Call index = 4*step + slot/2; ctr = (call_lo, call_hi, chain, 'MCPM'), key = (seed_lo, seed_hi).
-__device__ __forceinline__ void philox_call(unsigned long long seed, uint32_t chain, unsigned long long call, double& ua, double& ub) {
+// tag = 'MCPM' for the move's draws, 'MCPN' for the sampling (Widom) draws of the same step.
+__device__ __forceinline__ void philox_call(unsigned long long seed, uint32_t chain, unsigned long long call, double& ua, double& ub,
+                                            uint32_t tag = 0x4D43504Du) {
     uint32_t o0, o1, o2, o3;
-    philox4x32_10((uint32_t)call, (uint32_t)(call >> 32), chain, 0x4D43504Du, (uint32_t)seed, (uint32_t)(seed >> 32), o0, o1, o2, o3);
+    philox4x32_10((uint32_t)call, (uint32_t)(call >> 32), chain, tag, (uint32_t)seed, (uint32_t)(seed >> 32), o0, o1, o2, o3);
     ua = u53(o0, o1);
     ub = u53(o2, o3);
 }
@@ -195,6 +197,14 @@ struct PhiloxSource {
     }
     __device__ __forceinline__ void end_step(int) {}
     __device__ __forceinline__ unsigned long long cursor() const { return 0ull; }
+    // Sampling draws of a step (positions 8.. in the reference's sequential stream): lanes 0..3 evaluate the four
+    // calls of the step on the second stream; only production steps of NVT runs pay for this.
+    double ea, eb;
+    __device__ __forceinline__ void load_extra(unsigned long long seed, uint32_t chain, unsigned long long step, int lane) {
+        philox_call(seed, chain, 4ull * step + (unsigned long long)(lane & 3), ea, eb, 0x4D43504Eu);
+    }
+    template <int K>
+    __device__ __forceinline__ double extra() const { return __shfl_sync(MCPM_FULL_MASK, (K & 1) ? eb : ea, K >> 1); }
 };
 
 // Replay source: consumes a caller-supplied uniform stream exactly as the reference consumes
@@ -208,6 +218,9 @@ struct ReplaySource {
     __device__ __forceinline__ double at() const { return (pos + K < n) ? __ldg(u + pos + K) : 0.0; }
     __device__ __forceinline__ void end_step(int count) { pos += (unsigned long long)count; }
     __device__ __forceinline__ unsigned long long cursor() const { return pos; }
+    __device__ __forceinline__ void load_extra(unsigned long long, uint32_t, unsigned long long, int) {}
+    template <int K>
+    __device__ __forceinline__ double extra() const { return at<K>(); }   // the stream simply continues
 };
 
 // ------------------------------------------------------------------------------------------------

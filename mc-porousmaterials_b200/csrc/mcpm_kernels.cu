@@ -3,6 +3,8 @@
 //   K2 k2_chains            — persistent batched Metropolis chains, one CTA per chain
 //   K3 k3_box_energy        — MC::BoxEnergy, per-particle and box totals, O(N^2) tiled through smem
 //   fp64_peak_kernel        — DFMA microbenchmark for the roofline denominator
+#include <algorithm>
+
 #include "mcpm_device.cuh"
 #include "mcpm_kernels.h"
 
@@ -119,6 +121,29 @@ __device__ void cta_box_energy(const double* xs, const double* ys, const double*
     wall = v[1];
 }
 
+// MC::ComputeRDF same-species branch, src/sample.cpp:21-31: every pair i<j adds 2 to bin int(r/deltaR)+1 (if < NBINS).
+// Binning must agree with the reference at bin edges, so the distance is formed exactly as MC::NeighDistance does
+// (true division, round(), no FMA contraction, sqrt) rather than with the fast minimum image of the energy path.
+template <bool PBZ>
+__device__ void cta_rdf(const double* xs, const double* ys, const double* zs, int n, const ChainParams& P, double* hist, int tid, int T) {
+    const double deltaR = sqrt(P.rc2) / (1. * MCPM_RDF_BINS);
+    for (int i = 0; i < n - 1; i++) {
+        const double xi = xs[i], yi = ys[i], zi = zs[i];
+        for (int j = i + 1 + tid; j < n; j += T) {
+            double dx = xi - xs[j], dy = yi - ys[j], dz = zi - zs[j];
+            dx = __dsub_rn(dx, __dmul_rn(round(__ddiv_rn(dx, P.L[0])), P.L[0]));
+            dy = __dsub_rn(dy, __dmul_rn(round(__ddiv_rn(dy, P.L[1])), P.L[1]));
+            if (PBZ) dz = __dsub_rn(dz, __dmul_rn(round(__ddiv_rn(dz, P.L[2])), P.L[2]));
+            const double r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+            const int bin = (int)__ddiv_rn(r, deltaR) + 1;
+            if (bin < MCPM_RDF_BINS) atomicAdd(&hist[bin], 2.0);
+        }
+    }
+}
+
+// MC::BarWeight, src/moves.cpp:409, with barC = 1 (ResetStats, src/MC.cpp:88)
+__device__ __forceinline__ double bar_weight(double energy, double beta) { return 1. / cosh(0.5 * (energy - 1.) * beta); }
+
 // Per-set counters replicated in registers (cheap ints); flushed to the 64-bit totals in shared memory
 // by thread 0 at the end of every set.
 struct SetCounters {
@@ -132,14 +157,15 @@ struct SetCounters {
 // nothing but the partner loop's partial sums crosses threads.  (A variant that kept counters and
 // energies in shared memory for thread 0 only used 80 registers instead of 128 but was 10-15 % slower at
 // every occupancy measured on B200: the extra LDS/STS sit on the per-step critical path.)
-template <class Source, bool FAST, bool MULTI, bool PBZ>
+template <class Source, bool FAST, bool MULTI, bool PBZ, bool SAMPLE>
 __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, double* xs, double* ys, double* zs, double* partials,
-                           const RunArgs& a, unsigned char* trace, int cap, uint32_t chain) {
+                           const RunArgs& a, unsigned char* trace, int cap, uint32_t chain, double* hist) {
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
     const int tmask = T - 1;  // T is a power of two
     const bool lead = (tid == 0);
     const PairGeom g = make_geom<FAST>(P);
     mcpm_chain_stats& st = S.st;   // shared memory; written by thread 0 only
+    const bool widom_on = SAMPLE && (P.n_swap == 0);   // ComputeWidom acts only without swap moves, src/moves.cpp:415
 
     int n = st.n;
     double dr = st.dr, e_pair = st.pair, e_wall = st.wall;
@@ -155,11 +181,14 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
 
     for (int set = a.first_set; set < a.first_set + a.n_sets && !overflow; set++) {
         sc.reset();                      // MC::ResetStats, src/MC.cpp:81-98
+        if (lead) { st.widom_insert = st.widom_delete = 0.0; st.widom_insertions = st.widom_deletions = 1; }
         const bool production = set > P.n_equil;
         for (int s = 0; s < steps_per_set; s++) {
             rng.begin_step(a.seed, chain, step, lane);
             step++;
             int code;
+            double sx = 0., sy = 0., sz = 0., s_po = 0., s_wo = 0., mx = 0., my = 0., mz = 0.;   // this step's MoveParticle, for Widom's slot 0
+            bool s_acc = false;
             const double r = rng.template at<0>() * wsum;                         // src/main.cpp:67
             if (r <= thr_disp) {
                 // ---------------- MoveParticle, src/moves.cpp:118-186 ----------------
@@ -195,6 +224,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                     fwd.slot = i; fwd.x = xn; fwd.y = yn; fwd.z = zn;
                 }
                 code = acc ? 1 : 0;
+                if (SAMPLE) { sx = xo; sy = yo; sz = zo; s_po = po; s_wo = wo; mx = xn; my = yn; mz = zn; s_acc = acc; }
             } else if (r <= thr_vol) {
                 rng.end_step(1);
                 code = (4 << 1);  // volume moves are out of scope (n_vol is rejected by the host API)
@@ -257,6 +287,58 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                     code = (3 << 1);   // no barrier executed: fwd stays valid
                 }
             }
+            if (SAMPLE && production && widom_on) {
+                // ---------------- ComputeWidom, src/moves.cpp:410-449 (NVT branch) ----------------
+                rng.load_extra(a.seed, chain, step - 1, lane);
+                double energy;                                                   // draw 0 (species) is consumed but unused
+                if (rng.template extra<1>() < 0.5) {                             // ghost insertion
+                    const double gx = rng.template extra<2>() * Lx, gy = rng.template extra<3>() * Ly, gz = rng.template extra<4>() * Lz;
+                    rng.end_step(5);
+                    double v[1];
+                    v[0] = pair_sum1<FAST, PBZ>(xs, ys, zs, n, -1, g, gx, gy, gz, tid, T);
+                    double wg, wdummy;
+                    wall_two(P, gz, gz, wg, wdummy, lane);
+                    cta_allsum<1, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
+                    fwd.slot = -1;
+                    energy = eps4 * v[0] + wg;
+                    if (lead) { st.widom_insertions++; st.widom_insert += bar_weight(energy, beta) * exp(-0.5 * energy * beta); st.pair_evals += (unsigned long long)n; }
+                } else {                                                         // virtual deletion
+                    const int slot1 = (int)(rng.template extra<2>() * (double)n);   // 1-based slot in [0, n-1]: 0 is the scratch slot (Q14)
+                    rng.end_step(3);
+                    if (slot1 == 0) {
+                        // slot 0 holds the old position of this step's MoveParticle (src/moves.cpp:152).  Rejected move: the
+                        // particle sits there again and is skipped by position equality -> its old energy.  Accepted
+                        // move: a ghost at the old position that also sees the moved particle.
+                        double extra = 0.0;
+                        if (s_acc) pair_acc(extra, dist2<FAST, PBZ>(g, sx, sy, sz, mx, my, mz), g, 0, -1);
+                        energy = (s_po + eps4 * extra) + s_wo;
+                    } else {
+                        const int k = slot1 - 1;
+                        double xk, yk, zk;
+                        load_slot(xs, ys, zs, k, fwd, xk, yk, zk);
+                        double v[1];
+                        v[0] = pair_sum1<FAST, PBZ>(xs, ys, zs, n, k, g, xk, yk, zk, tid, T);
+                        double wk, wdummy;
+                        wall_two(P, zk, zk, wk, wdummy, lane);
+                        cta_allsum<1, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
+                        fwd.slot = -1;
+                        energy = eps4 * v[0] + wk;
+                        if (lead) st.pair_evals += (unsigned long long)n;
+                    }
+                    if (lead) {
+                        st.widom_deletions++;
+                        const double bw = bar_weight(energy, beta);
+                        if (exp(0.5 * energy * beta) < 1) st.widom_delete += bw * exp(0.5 * energy * beta);
+                        else st.widom_delete += bw * exp(-0.5 * energy * beta);   // the reference's boundary for deletion statistics
+                    }
+                }
+            }
+            if (SAMPLE && production && a.sample_rdf) {
+                __syncthreads();                                                 // this step's slot write is visible to everyone
+                fwd.slot = -1;
+                cta_rdf<PBZ>(xs, ys, zs, n, P, hist, tid, T);
+                __syncthreads();
+            }
             if (lead) {
                 if (trace) trace[(unsigned long long)(set - a.first_set) * (unsigned long long)a.steps_per_set + (unsigned long long)s] = (unsigned char)code;
                 if (production) {
@@ -300,7 +382,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
 //                 N = 20 000) are advanced in place in global memory; their 24 B x N working set stays L2-resident
 //                 (480 KB at N = 20k vs 126 MB of L2).  Plain (coherent) loads: a slot written by its owner thread
 //                 is visible to the CTA after the step's __syncthreads.
-template <int RNG_MODE, int MAXT, int MINB, bool GLOBAL, bool FAST>
+template <int RNG_MODE, int MAXT, int MINB, bool GLOBAL, bool FAST, bool SAMPLE>
 __global__ void __launch_bounds__(MAXT, MINB) k2_chains(const ChainParams* __restrict__ params, ChainState* __restrict__ states,
                                                   const int* __restrict__ order, double* X, double* Y, double* Z, RunArgs a) {
     extern __shared__ double smem[];
@@ -311,10 +393,12 @@ __global__ void __launch_bounds__(MAXT, MINB) k2_chains(const ChainParams* __res
     double* ys = GLOBAL ? Y + off : smem + cap;
     double* zs = GLOBAL ? Z + off : smem + 2 * cap;
     double* partials = GLOBAL ? smem : smem + 3 * cap;  // 2 parities x 32 warps x 2 values
+    double* hist = partials + 128;                      // MCPM_RDF_BINS doubles (+ padding)
     __shared__ ChainParams P;
     __shared__ ChainState S;
     const int tid = threadIdx.x, T = blockDim.x;
     if (tid == 0) { P = params[chain]; S = states[chain]; }
+    for (int k = threadIdx.x; k < MCPM_RDF_BINS + 4; k += blockDim.x) hist[k] = 0.0;
     __syncthreads();
     if (!GLOBAL) {
         // stage every slot (not only the n live ones): stale slots are observable through quirk Q12
@@ -326,7 +410,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k2_chains(const ChainParams* __res
     // FAST (all chains of the launch have their coordinates inside the box) is decided by the host per launch;
     // only the smallest CTA variant can run with a single warp, so MULTI is a compile-time fact elsewhere.
     const bool multi = (MAXT > 64) || T > 32, pbz = P.pbc[2] != 0;
-#define MCPM_GO(SRC, M, Z) chain_loop<SRC, FAST, M, Z>(P, S, rng, xs, ys, zs, partials, a, trace, cap, (uint32_t)chain)
+#define MCPM_GO(SRC, M, Z) chain_loop<SRC, FAST, M, Z, SAMPLE>(P, S, rng, xs, ys, zs, partials, a, trace, cap, (uint32_t)chain, hist)
 #define MCPM_DISPATCH(SRC)                                                                           \
     do {                                                                                             \
         if (MAXT > 64 || multi) { if (pbz) MCPM_GO(SRC, true, true); else MCPM_GO(SRC, true, false); } \
@@ -343,6 +427,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k2_chains(const ChainParams* __res
 #undef MCPM_GO
     __syncthreads();
     if (!GLOBAL) for (int j = tid; j < cap; j += T) { X[off + j] = xs[j]; Y[off + j] = ys[j]; Z[off + j] = zs[j]; }
+    if (a.sample_rdf && a.rdf) for (int k = tid; k < MCPM_RDF_BINS; k += T) a.rdf[(size_t)chain * MCPM_RDF_BINS + k] += hist[k];
     if (tid == 0) states[chain] = S;
 }
 
@@ -527,12 +612,12 @@ __global__ void philox_fill_kernel(unsigned long long seed, unsigned int chain, 
 // ================================================================================================
 // launchers
 // ================================================================================================
-static size_t k2_smem_bytes(int cap) { return (size_t)(3 * cap + 128) * sizeof(double); }
+static size_t k2_smem_bytes(int cap) { return (size_t)(3 * cap + 128 + 104) * sizeof(double); }
 
-size_t k2_smem_limit_cap(int max_smem_optin) { return ((size_t)max_smem_optin / sizeof(double) - 128 - 64) / 3; }
+size_t k2_smem_limit_cap(int max_smem_optin) { return ((size_t)max_smem_optin / sizeof(double) - 128 - 104 - 64) / 3; }
 
 template <int RNG_MODE>
-static cudaError_t launch_k2_rng(int n_chains, int threads, bool global, bool fast, size_t smem, const ChainParams* params,
+static cudaError_t launch_k2_rng(int n_chains, int threads, bool global, bool fast, bool sample, size_t smem, const ChainParams* params,
                                  ChainState* states, const int* order, double* X, double* Y, double* Z, const RunArgs& a,
                                  cudaStream_t stream) {
     auto go = [&](auto kern) -> cudaError_t {
@@ -541,31 +626,34 @@ static cudaError_t launch_k2_rng(int n_chains, int threads, bool global, bool fa
         kern<<<n_chains, threads, smem, stream>>>(params, states, order, X, Y, Z, a);
         return cudaSuccess;
     };
-    // register budgets by CTA size (ptxas: no spills at 128): <=64, <=256, <=512 threads -> 128 regs; 1024 -> 64.
-    // The general-minimum-image kernels (coordinates outside the box) exist for one shared-memory and one
-    // global-memory CTA shape; k2_threads_supported() clamps the thread count accordingly.
-    if (!fast) return global ? go(k2_chains<RNG_MODE, 1024, 1, true, false>) : go(k2_chains<RNG_MODE, 256, 2, false, false>);
-    if (global) return threads <= 512 ? go(k2_chains<RNG_MODE, 512, 1, true, true>) : go(k2_chains<RNG_MODE, 1024, 1, true, true>);
-    if (threads <= 64) return go(k2_chains<RNG_MODE, 64, 8, false, true>);
-    if (threads <= 256) return go(k2_chains<RNG_MODE, 256, 2, false, true>);
-    if (threads <= 512) return go(k2_chains<RNG_MODE, 512, 1, false, true>);
-    return go(k2_chains<RNG_MODE, 1024, 1, false, true>);
+    // The hot kernels (coordinates inside the box, no in-kernel sampling) exist for every CTA shape; register budgets
+    // by CTA size (ptxas: no spills at 128): <=64, <=256, <=512 threads -> 128 regs; 1024 -> 64.
+    // The general kernels (general minimum image for coordinates outside the box and/or Widom + RDF sampling after
+    // every production step) exist for one shared-memory and one global-memory CTA shape;
+    // k2_threads_supported() clamps the thread count accordingly.
+    if (!fast || sample) {
+        if (global) return fast ? go(k2_chains<RNG_MODE, 512, 1, true, true, true>) : go(k2_chains<RNG_MODE, 512, 1, true, false, true>);
+        return fast ? go(k2_chains<RNG_MODE, 256, 2, false, true, true>) : go(k2_chains<RNG_MODE, 256, 2, false, false, true>);
+    }
+    if (global) return threads <= 512 ? go(k2_chains<RNG_MODE, 512, 1, true, true, false>) : go(k2_chains<RNG_MODE, 1024, 1, true, true, false>);
+    if (threads <= 64) return go(k2_chains<RNG_MODE, 64, 8, false, true, false>);
+    if (threads <= 256) return go(k2_chains<RNG_MODE, 256, 2, false, true, false>);
+    if (threads <= 512) return go(k2_chains<RNG_MODE, 512, 1, false, true, false>);
+    return go(k2_chains<RNG_MODE, 1024, 1, false, true, false>);
 }
 
-int k2_threads_supported(int threads, bool global, bool fast) {
-    if (!fast && !global) return threads < 64 ? 64 : (threads > 256 ? 256 : threads);   // (256,2) kernel: multi-warp only
-    if (!fast && global) return threads < 64 ? 64 : threads;
-    if (global && threads < 64) return 64;
+int k2_threads_supported(int threads, bool global, bool fast, bool sample) {
+    if (!fast || sample) return global ? std::min(threads, 512) : std::min(threads, 256);
     return threads;
 }
 
-cudaError_t launch_k2(int rng_mode, int n_chains, int threads, bool fast, const ChainParams* params, ChainState* states, const int* order,
-                      double* X, double* Y, double* Z, const RunArgs& a, int max_smem_optin, cudaStream_t stream) {
+cudaError_t launch_k2(int rng_mode, int n_chains, int threads, bool fast, bool sample, const ChainParams* params, ChainState* states,
+                      const int* order, double* X, double* Y, double* Z, const RunArgs& a, int max_smem_optin, cudaStream_t stream) {
     const bool global = (size_t)a.cap > k2_smem_limit_cap(max_smem_optin);
-    const size_t smem = global ? 128 * sizeof(double) : k2_smem_bytes(a.cap);
+    const size_t smem = global ? (128 + 104) * sizeof(double) : k2_smem_bytes(a.cap);
     cudaError_t err = rng_mode == MCPM_RNG_PHILOX
-                          ? launch_k2_rng<MCPM_RNG_PHILOX>(n_chains, threads, global, fast, smem, params, states, order, X, Y, Z, a, stream)
-                          : launch_k2_rng<MCPM_RNG_REPLAY>(n_chains, threads, global, fast, smem, params, states, order, X, Y, Z, a, stream);
+                          ? launch_k2_rng<MCPM_RNG_PHILOX>(n_chains, threads, global, fast, sample, smem, params, states, order, X, Y, Z, a, stream)
+                          : launch_k2_rng<MCPM_RNG_REPLAY>(n_chains, threads, global, fast, sample, smem, params, states, order, X, Y, Z, a, stream);
     if (err != cudaSuccess) return err;
     return cudaGetLastError();
 }

@@ -41,4 +41,8 @@ struct RunArgs {
     unsigned long long trace_stride;
     int check_energy;
     int cap;
+    int sample_rdf;
+    double* rdf;                 // device, [n_chains][MCPM_RDF_BINS] accumulated histograms
 };
+
+#define MCPM_RDF_BINS 100        // NBINS, src/MC.h:11

@@ -55,7 +55,7 @@ class RunParams(C.Structure):
         ("rng_mode", C.c_int), ("seed", C.c_ulonglong),
         ("replay_u", _dp), ("replay_stride", C.c_size_t),
         ("trace", C.POINTER(C.c_ubyte)),
-        ("threads_per_chain", C.c_int), ("check_energy", C.c_int),
+        ("threads_per_chain", C.c_int), ("sample_rdf", C.c_int), ("check_energy", C.c_int),
     ]
 
 
@@ -72,6 +72,8 @@ class ChainStats(C.Structure):
         ("pair_evals", C.c_ulonglong), ("steps_done", C.c_ulonglong),
         ("sum_n", C.c_double), ("sum_n2", C.c_double), ("sum_e", C.c_double), ("sum_e2", C.c_double),
         ("samples", C.c_longlong), ("replay_consumed", C.c_ulonglong),
+        ("widom_insert", C.c_double), ("widom_delete", C.c_double),
+        ("widom_insertions", C.c_longlong), ("widom_deletions", C.c_longlong),
     ]
 
     def as_dict(self):
@@ -121,6 +123,9 @@ PROTOTYPES = {
     "mcpm_run": (C.c_int, [C.c_void_p, C.POINTER(RunParams), C.POINTER(ChainStats)]),
     "mcpm_get_stats": (C.c_int, [C.c_void_p, C.POINTER(ChainStats)]),
     "mcpm_reset_accumulators": (C.c_int, [C.c_void_p]),
+    "mcpm_get_rdf": (C.c_int, [C.c_void_p, C.c_int, _dp]),
+    "mcpm_chemical_potential": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp]),
+    "mcpm_set_running_energy": (C.c_int, [C.c_void_p, _dp, _dp]),
     "mcpm_set_dr": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "mcpm_set_step_counter": (C.c_int, [C.c_void_p, C.c_int, C.c_ulonglong]),
     "mcpm_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),

@@ -124,13 +124,14 @@ class Engine:
         check(self.L.mcpm_remove_swap_last(self.h, chain, index))
 
     # ---- K2
-    def run(self, first_set, n_sets, steps_per_set, seed=0, replay=None, trace=False, threads=0, check_energy=0):
+    def run(self, first_set, n_sets, steps_per_set, seed=0, replay=None, trace=False, threads=0, check_energy=0, sample_rdf=0):
         """Advance every chain n_sets*steps_per_set trial moves.  replay: float64[n_chains, stride] or None."""
         p = RunParams()
         p.first_set, p.n_sets, p.steps_per_set = first_set, n_sets, steps_per_set
         p.seed = seed
         p.threads_per_chain = threads
         p.check_energy = check_energy
+        p.sample_rdf = sample_rdf
         keep = []
         if replay is not None:
             r = np.ascontiguousarray(replay, dtype=np.float64)
@@ -157,6 +158,21 @@ class Engine:
 
     def reset_accumulators(self):
         check(self.L.mcpm_reset_accumulators(self.h))
+
+    def get_rdf(self, chain):
+        h = np.zeros(100)
+        check(self.L.mcpm_get_rdf(self.h, chain, _p(h)))
+        return h
+
+    def chemical_potential(self, chain):
+        a = C.c_double(0); b = C.c_double(0)
+        check(self.L.mcpm_chemical_potential(self.h, chain, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def set_running_energy(self, pair, wall):
+        pair = np.ascontiguousarray(pair, dtype=np.float64); wall = np.ascontiguousarray(wall, dtype=np.float64)
+        assert len(pair) == len(wall) == self.n_chains
+        check(self.L.mcpm_set_running_energy(self.h, _p(pair), _p(wall)))
 
     def set_dr(self, chain, dr):
         check(self.L.mcpm_set_dr(self.h, chain, dr))

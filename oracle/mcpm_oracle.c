@@ -57,6 +57,7 @@ struct orc_chain {
     uint64_t ph_seed, ph_step;
     uint32_t ph_chain;
     int ph_slot;
+    int sample_rdf;
 };
 
 /* ---------------------------------------------------------------- uniform sources ---------- */
@@ -107,8 +108,12 @@ void orc_philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint3
 /* The product's device stream (csrc/mcpm_rng.cuh): call = 4*step + slot/2;
  * ctr = (call_lo, call_hi, chain, 'MCPM'), key = (seed_lo, seed_hi); 53-bit mantissas; x0.9999. */
 double orc_philox_uniform(uint64_t seed, uint32_t chain_id, uint64_t step, int slot) {
+    /* slots 0..7: the move's stream (tag 'MCPM'); slots 8..15: the sampling stream of the same step (tag 'MCPN'),
+     * used by the Widom draws that follow the move in production steps */
+    uint32_t tag = 0x4D43504Du;
+    if (slot >= 8) { slot -= 8; tag = 0x4D43504Eu; }
     uint64_t call = 4ULL * step + (uint64_t)(slot >> 1);
-    uint32_t ctr[4] = {(uint32_t)call, (uint32_t)(call >> 32), chain_id, 0x4D43504Du};
+    uint32_t ctr[4] = {(uint32_t)call, (uint32_t)(call >> 32), chain_id, tag};
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t r[4];
     orc_philox4x32_10(ctr, key, r);
@@ -408,6 +413,11 @@ void orc_run_sets(orc_chain* c, int first_set, int n_sets, long long steps_per_s
             int code = orc_step(c, correct);
             if (trace) *trace++ = (unsigned char)code;
             if (set > c->sys.n_equil_sets) {
+                /* main.cpp:72-75: ComputeWidom(); ComputeRDF(); — the Widom draws follow the move's draws */
+                if (c->rng_mode == RNG_PHILOX) { c->ph_step--; c->ph_slot = 8; }
+                if (c->sys.n_swap == 0) orc_widom(c, NULL, NULL);
+                if (c->rng_mode == RNG_PHILOX) c->ph_step++;
+                if (c->sample_rdf) orc_rdf(c, NULL);
                 double n = (double)c->n, e = c->e_energy;
                 c->sum_n += n; c->sum_n2 += n * n; c->sum_e += e; c->sum_e2 += e * e;
                 c->samples++;
@@ -472,6 +482,11 @@ void orc_rdf(orc_chain* c, double* hist) {
     if (hist) memcpy(hist, c->rdf, sizeof(double) * ORC_NBINS);
 }
 void orc_rdf_reset(orc_chain* c) { memset(c->rdf, 0, sizeof(c->rdf)); }
+void orc_set_sample_rdf(orc_chain* c, int on) { c->sample_rdf = on; }
+void orc_get_rdf(const orc_chain* c, double* hist100) { memcpy(hist100, c->rdf, sizeof(double) * ORC_NBINS); }
+void orc_get_widom(const orc_chain* c, double out[2], long long iout[2]) {
+    out[0] = c->widom_insert; out[1] = c->widom_delete; iout[0] = c->widom_insertions; iout[1] = c->widom_deletions;
+}
 
 /* ---------------------------------------------------------------- lifecycle ---------------- */
 

@@ -90,6 +90,9 @@ void orc_widom(orc_chain* c, double out[2], long long iout[2]);
 void orc_chem_pot(orc_chain* c, double out[2]);                            /* moves.cpp:453-465 */
 void orc_rdf(orc_chain* c, double* hist100);
 void orc_rdf_reset(orc_chain* c);
+void orc_set_sample_rdf(orc_chain* c, int on);   /* orc_run_sets then calls ComputeRDF every production step */
+void orc_get_rdf(const orc_chain* c, double* hist100);
+void orc_get_widom(const orc_chain* c, double out[2], long long iout[2]);
 
 #ifdef __cplusplus
 }

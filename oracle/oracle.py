@@ -134,6 +134,9 @@ class COracle:
             L.orc_chem_pot.argtypes = [C.c_void_p, _dp]
             L.orc_rdf.argtypes = [C.c_void_p, _dp]
             L.orc_rdf_reset.argtypes = [C.c_void_p]
+            L.orc_set_sample_rdf.argtypes = [C.c_void_p, C.c_int]
+            L.orc_get_rdf.argtypes = [C.c_void_p, _dp]
+            L.orc_get_widom.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_longlong)]
             cls._lib = L
         return cls._lib
 
@@ -256,6 +259,17 @@ class COracle:
 
     def rdf_reset(self):
         self.L.orc_rdf_reset(self.h)
+
+    def set_sample_rdf(self, on=1):
+        self.L.orc_set_sample_rdf(self.h, on)
+
+    def get_rdf(self):
+        h = np.zeros(100); self.L.orc_get_rdf(self.h, h.ctypes.data_as(_dp)); return h
+
+    def get_widom(self):
+        out = np.zeros(2); i = np.zeros(2, dtype=np.int64)
+        self.L.orc_get_widom(self.h, out.ctypes.data_as(_dp), i.ctypes.data_as(C.POINTER(C.c_longlong)))
+        return out, i
 
 
 def philox4x32_10(ctr, key):

@@ -207,3 +207,62 @@ def test_bulk_global_path_translations_only(mcpm):
     n = 5000
     x, y, z = rng.random(n) * 70.0, rng.random(n) * 70.0, rng.random(n) * 70.0
     _replay_vs_oracle(mcpm, s, x, y, z, 10240, 1024, 300, 9)
+
+
+@pytest.mark.parametrize("threads", [32, 128])
+def test_nvt_widom_and_rdf_follow_oracle(mcpm, golden, threads):
+    """NVT (n_swap = 0): production steps run ComputeWidom and ComputeRDF after the move, as src/main.cpp:72-75 does.
+    Device Philox (move stream + sampling stream) vs the C oracle fed with the same streams."""
+    arrays, meta = golden
+    s = system_from_meta(meta["bulk"]["system"])
+    s.n_equil_sets = 1
+    x, y, z = arrays["bulk_x"], arrays["bulk_y"], arrays["bulk_z"]
+    seed, sets, sps = 4321, 3, 400
+    o = O.COracle(s, 1024)
+    o.set_positions(x, y, z)
+    o.box_energy()
+    o.philox(seed, 0, 0)
+    o.set_sample_rdf(1)
+    otr = o.run_sets(1, sets, sps, 0, True)
+    with mcpm.Engine(1, 1024) as e:
+        e.set_system(s)
+        e.set_positions(0, x, y, z)
+        stats, tr = e.run(1, sets, sps, seed=seed, trace=True, threads=threads, sample_rdf=1, check_energy=1)
+        hist = e.get_rdf(0)
+        mu_ex, mu = e.chemical_potential(0)
+        gx, gy, gz = e.get_positions(0)
+    assert first_divergence(tr[0], otr) == -1
+    ox, oy, oz = o.get_positions()
+    assert np.array_equal(gx, ox) and np.array_equal(gy, oy) and np.array_equal(gz, oz)
+    st = stats[0]
+    (wi, wd), (ni, nd) = o.get_widom()
+    assert (st.widom_insertions, st.widom_deletions) == (ni, nd) and ni + nd == sps + 2      # last set only; counts start at 1
+    assert st.widom_insert == pytest.approx(wi, rel=1e-10) and st.widom_delete == pytest.approx(wd, rel=1e-10)
+    omu = o.chem_pot()
+    assert mu_ex == pytest.approx(omu[0], rel=1e-9) and mu == pytest.approx(omu[1], rel=1e-9)
+    ohist = o.get_rdf()
+    assert hist.sum() == ohist.sum() > 0
+    assert np.array_equal(hist, ohist)                    # same binning as NeighDistance/deltaR, every production step
+    assert st.energy == pytest.approx(st.energy_check, rel=RTOL)
+
+
+def test_nvt_widom_replay_matches_reference_stream(mcpm, golden):
+    """Replay mode: the Widom draws continue the reference's sequential mt19937_64 stream (8 + 5 or 3 per step)."""
+    arrays, meta = golden
+    s = system_from_meta(meta["bulk"]["system"])
+    s.n_equil_sets = 0
+    x, y, z = arrays["bulk_x"], arrays["bulk_y"], arrays["bulk_z"]
+    u = O.mt_uniforms(99, 13 * 500)
+    o = O.COracle(s, 1024)
+    o.set_positions(x, y, z); o.box_energy(); o.replay(u)
+    otr = o.run_sets(1, 1, 500, 0, True)
+    with mcpm.Engine(1, 1024) as e:
+        e.set_system(s)
+        e.set_positions(0, x, y, z)
+        stats, tr = e.run(1, 1, 500, replay=u, trace=True, threads=64)
+    assert first_divergence(tr[0], otr) == -1
+    (wi, wd), (ni, nd) = o.get_widom()
+    st = stats[0]
+    assert st.replay_consumed == o.draws()
+    assert (st.widom_insertions, st.widom_deletions) == (ni, nd)
+    assert st.widom_insert == pytest.approx(wi, rel=1e-10) and st.widom_delete == pytest.approx(wd, rel=1e-10)

@@ -99,3 +99,22 @@ def test_isotherm_sweep_and_replicas(tmp_path):
     assert list(iso[:, 0]) == [-1700.0, -1500.0, -1300.0]
     assert iso[0, 1] < iso[1, 1] < iso[2, 1]                        # loading grows with chemical potential
     assert os.path.isdir(tmp_path / "ar_small_mu2_r3" / "pore")
+
+
+def test_nvt_run_writes_chemical_potential_and_rdf(tmp_path):
+    """NSwapAttempts 0 + SampleRDF: Widom/BAR mu columns in the log (production sets) and the rdf_<a>-<b>.dat file."""
+    inp = tmp_path / "nvt.in"
+    text = open(os.path.join(GOLDEN, "ar_small.in")).read().replace("PrintTrajectory\n", "")
+    text = text.replace("NSwapAttempts 1", "NSwapAttempts 0").replace("NumberOfParticles 60", "NumberOfParticles 80")
+    inp.write_text(text + "SampleRDF Ar Ar\n")
+    run_driver(tmp_path, str(inp), "--quiet")
+    log = open(tmp_path / "ar_small" / "pore" / "simulation_ar.log").read().splitlines()
+    eq = log[1].split("\t"); prod = log[-1].split("\t")
+    assert eq[0] == "2" and eq[9:] == ["nan", "-nan"]            # set 2 <= EquilibriumSets: no Widom sampling yet
+    assert prod[0] == "6" and int(prod[7]) == 80
+    mu_ex, mu = float(prod[9]), float(prod[10])
+    assert np.isfinite(mu_ex) and np.isfinite(mu) and -3000 < mu < 0
+    rdf = open(tmp_path / "ar_small" / "pore" / "rdf_ar-ar.dat").read().splitlines()
+    assert rdf[0] == "nBins: 100" and rdf[1] == "r(AA)\tg(r)" and len(rdf) == 102
+    g = np.array([[float(v) for v in line.split("\t")] for line in rdf[2:]])
+    assert g[0, 0] == pytest.approx(1.5 * 0.12) and np.all(g[:20, 1] == 0.0) and g[:, 1].max() > 0.5   # excluded core, first shell
