@@ -589,6 +589,154 @@ __global__ void __launch_bounds__(128) k3_box_energy(const ChainParams* __restri
 }
 
 // ================================================================================================
+// K3c — full box energy through a cell list (bulk-like systems whose box holds >= 3 cut-off lengths per periodic
+// axis, e.g. config C4: N = 20 000, L = 100 A, rcut = 12 A -> 8x8x8 cells, ~1050 candidate partners instead of
+// 20 000).  Same sums as K3 / MC::BoxEnergy: every in-range pair is visited twice, the pair total is halved; only
+// the order of the floating-point additions differs.  Four small kernels per call:
+//   k3c_bin      cell of every particle + per-cell counts
+//   k3c_scan     exclusive scan of the counts (<= 4096 cells: one CTA)
+//   k3c_scatter  positions copied into cell order (coalesced reads in the energy kernel)
+//   k3c_energy   one thread per particle, 27 neighbour cells
+// ================================================================================================
+#define K3C_MAXC 16   // cells per axis
+
+struct CellGrid { int nx, ny, nz; };
+
+__device__ __forceinline__ CellGrid cell_grid(const ChainParams& P) {
+    const double rc = sqrt(P.rc2);
+    CellGrid g;
+    g.nx = min(K3C_MAXC, (int)(P.L[0] / rc)); g.ny = min(K3C_MAXC, (int)(P.L[1] / rc)); g.nz = min(K3C_MAXC, (int)(P.L[2] / rc));
+    if (!P.pbc[2]) g.nz = max(1, g.nz);
+    return g;
+}
+__device__ __forceinline__ int cell_coord(double x, double L, int n) { return min(n - 1, max(0, (int)(x * ((double)n / L)))); }
+
+__global__ void k3c_bin(const ChainParams* __restrict__ params, const ChainState* __restrict__ states, const double* __restrict__ X,
+                        const double* __restrict__ Y, const double* __restrict__ Z, int cap, int chain0, int* __restrict__ cell_of,
+                        int* __restrict__ counts) {
+    const int chain = chain0 + blockIdx.y;
+    const ChainParams& P = params[chain];
+    const int n = states[chain].st.n;
+    const CellGrid g = cell_grid(P);
+    const size_t off = (size_t)chain * cap;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = (cell_coord(Z[off + i], P.L[2], g.nz) * g.ny + cell_coord(Y[off + i], P.L[1], g.ny)) * g.nx + cell_coord(X[off + i], P.L[0], g.nx);
+        cell_of[(size_t)blockIdx.y * cap + i] = c;
+        atomicAdd(&counts[(size_t)blockIdx.y * (K3C_MAXC * K3C_MAXC * K3C_MAXC) + c], 1);
+    }
+}
+
+__global__ void __launch_bounds__(1024) k3c_scan(const ChainParams* __restrict__ params, int chain0, int* __restrict__ counts, int* __restrict__ starts) {
+    __shared__ int part[1024];
+    const int chain = chain0 + blockIdx.x;
+    const CellGrid g = cell_grid(params[chain]);
+    const int nc = g.nx * g.ny * g.nz, tid = threadIdx.x;
+    int* cnt = counts + (size_t)blockIdx.x * (K3C_MAXC * K3C_MAXC * K3C_MAXC);
+    int* st = starts + (size_t)blockIdx.x * (K3C_MAXC * K3C_MAXC * K3C_MAXC + 1);
+    const int per = (nc + 1023) / 1024;
+    int local = 0;
+    for (int k = 0; k < per; k++) { const int c = tid * per + k; if (c < nc) local += cnt[c]; }
+    part[tid] = local;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) { int v = tid >= o ? part[tid - o] : 0; __syncthreads(); part[tid] += v; __syncthreads(); }
+    int run = part[tid] - local;
+    for (int k = 0; k < per; k++) { const int c = tid * per + k; if (c < nc) { st[c] = run; run += cnt[c]; cnt[c] = 0; } }
+    if (tid == 1023) st[nc] = part[1023];
+}
+
+__global__ void k3c_scatter(const ChainState* __restrict__ states, const double* __restrict__ X, const double* __restrict__ Y,
+                            const double* __restrict__ Z, int cap, int chain0, const int* __restrict__ cell_of, int* __restrict__ counts,
+                            const int* __restrict__ starts, double* __restrict__ sx, double* __restrict__ sy, double* __restrict__ sz,
+                            int* __restrict__ orig) {
+    const int chain = chain0 + blockIdx.y;
+    const int n = states[chain].st.n;
+    const size_t off = (size_t)chain * cap, so = (size_t)blockIdx.y * cap;
+    int* cnt = counts + (size_t)blockIdx.y * (K3C_MAXC * K3C_MAXC * K3C_MAXC);
+    const int* st = starts + (size_t)blockIdx.y * (K3C_MAXC * K3C_MAXC * K3C_MAXC + 1);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = cell_of[so + i];
+        const int slot = st[c] + atomicAdd(&cnt[c], 1);
+        sx[so + slot] = X[off + i]; sy[so + slot] = Y[off + i]; sz[so + slot] = Z[off + i];
+        orig[so + slot] = i;
+    }
+}
+
+template <bool PBZ>
+__global__ void __launch_bounds__(128) k3c_energy(const ChainParams* __restrict__ params, ChainState* __restrict__ states, int cap, int chain0,
+                                                  const int* __restrict__ starts, const double* __restrict__ sx, const double* __restrict__ sy,
+                                                  const double* __restrict__ sz, const int* __restrict__ orig, double* __restrict__ per_pair,
+                                                  double* __restrict__ per_wall, double* __restrict__ scratch, unsigned int* __restrict__ counters,
+                                                  double* __restrict__ out) {
+    __shared__ ChainParams P;
+    __shared__ double red[2][4];
+    __shared__ bool last;
+    const int chain = chain0 + blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) P = params[chain];
+    __syncthreads();
+    if ((P.pbc[2] != 0) != PBZ) return;                 // the other instantiation handles this chain
+    const PairGeom g = make_geom<true>(P);
+    const CellGrid cg = cell_grid(P);
+    const int n = states[chain].st.n;
+    const size_t so = (size_t)blockIdx.y * cap;
+    const int* st = starts + (size_t)blockIdx.y * (K3C_MAXC * K3C_MAXC * K3C_MAXC + 1);
+    double* sc = scratch + (size_t)blockIdx.y * 2 * gridDim.x;
+    const int p = blockIdx.x * blockDim.x + tid;
+    double pair_i = 0.0, wall_i = 0.0;
+    if (p < n) {
+        const double xi = sx[so + p], yi = sy[so + p], zi = sz[so + p];
+        const int cx = cell_coord(xi, P.L[0], cg.nx), cy = cell_coord(yi, P.L[1], cg.ny), cz = cell_coord(zi, P.L[2], cg.nz);
+        double s0 = 0.0, s1 = 0.0;
+        for (int dz = -1; dz <= 1; dz++) {
+            int z = cz + dz;
+            if (PBZ) z = (z + cg.nz) % cg.nz; else if (z < 0 || z >= cg.nz) continue;
+            for (int dy = -1; dy <= 1; dy++) {
+                const int y = (cy + dy + cg.ny) % cg.ny;
+                for (int dx = -1; dx <= 1; dx++) {
+                    const int x = (cx + dx + cg.nx) % cg.nx;
+                    const int c = (z * cg.ny + y) * cg.nx + x;
+                    int q = st[c];
+                    const int qe = st[c + 1];
+                    for (; q + 1 < qe; q += 2) {
+                        pair_acc(s0, dist2<true, PBZ>(g, xi, yi, zi, sx[so + q], sy[so + q], sz[so + q]), g, q, p);
+                        pair_acc(s1, dist2<true, PBZ>(g, xi, yi, zi, sx[so + q + 1], sy[so + q + 1], sz[so + q + 1]), g, q + 1, p);
+                    }
+                    if (q < qe) pair_acc(s0, dist2<true, PBZ>(g, xi, yi, zi, sx[so + q], sy[so + q], sz[so + q]), g, q, p);
+                }
+            }
+        }
+        pair_i = P.eps4 * (s0 + s1);
+        wall_i = wall_one(P, zi);
+        const int i = orig[so + p];
+        if (per_pair) per_pair[(size_t)blockIdx.y * cap + i] = pair_i;
+        if (per_wall) per_wall[(size_t)blockIdx.y * cap + i] = wall_i;
+    }
+    double sp = warp_allsum(pair_i), sw = warp_allsum(wall_i);
+    if (lane == 0) { red[0][warp] = sp; red[1][warp] = sw; }
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0, b = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { a += red[0][w]; b += red[1][w]; }
+        sc[2 * blockIdx.x] = a; sc[2 * blockIdx.x + 1] = b;
+        __threadfence();
+        last = (atomicAdd(&counters[blockIdx.y], 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && tid == 0) {
+        __threadfence();
+        double a = 0, b = 0;
+        for (unsigned t = 0; t < gridDim.x; t++) { a += ((volatile double*)sc)[2 * t]; b += ((volatile double*)sc)[2 * t + 1]; }
+        double* o = out + 4 * (size_t)blockIdx.y;
+        const double ph = 0.5 * a;
+        o[0] = ph; o[1] = 0.0; o[2] = b; o[3] = ph + b;
+        mcpm_chain_stats& stt = states[chain].st;
+        stt.pair = ph; stt.wall = b; stt.energy = ph + b;
+        stt.pair_check = ph; stt.wall_check = b; stt.energy_check = ph + b;
+        counters[blockIdx.y] = 0u;
+    }
+}
+
+// ================================================================================================
 __global__ void fp64_peak_kernel(double* out, int iters, double seed) {
     double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
     const double m = 0.9999999, c = 1e-9;
@@ -674,6 +822,24 @@ cudaError_t launch_k3(int tiles, int n_chains, int chain0, const ChainParams* pa
     // two instantiations (fast / general minimum image); each CTA exits at once if the chain is the other kind
     k3_box_energy<true><<<grid, 128, 0, stream>>>(params, states, X, Y, Z, cap, chain0, per_pair, per_wall, scratch, counters, out, 1);
     k3_box_energy<false><<<grid, 128, 0, stream>>>(params, states, X, Y, Z, cap, chain0, per_pair, per_wall, scratch, counters, out, 0);
+    return cudaGetLastError();
+}
+
+size_t k3c_cells_per_chain() { return (size_t)K3C_MAXC * K3C_MAXC * K3C_MAXC; }
+
+// Cell-list K3 for chains [chain0, chain0+n_chains): all of them must qualify (see mcpm_api.cu::cell_list_ok).
+cudaError_t launch_k3_cells(int maxn, int n_chains, int chain0, const ChainParams* params, ChainState* states, const double* X,
+                            const double* Y, const double* Z, int cap, int* cell_of, int* counts, int* starts, double* sx, double* sy,
+                            double* sz, int* orig, double* per_pair, double* per_wall, double* scratch, unsigned int* counters, double* out,
+                            cudaStream_t stream) {
+    const int blocks = (maxn + 255) / 256, tiles = (maxn + 127) / 128;
+    cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int) * k3c_cells_per_chain() * n_chains, stream);
+    if (e != cudaSuccess) return e;
+    k3c_bin<<<dim3(blocks, n_chains), 256, 0, stream>>>(params, states, X, Y, Z, cap, chain0, cell_of, counts);
+    k3c_scan<<<n_chains, 1024, 0, stream>>>(params, chain0, counts, starts);
+    k3c_scatter<<<dim3(blocks, n_chains), 256, 0, stream>>>(states, X, Y, Z, cap, chain0, cell_of, counts, starts, sx, sy, sz, orig);
+    k3c_energy<true><<<dim3(tiles, n_chains), 128, 0, stream>>>(params, states, cap, chain0, starts, sx, sy, sz, orig, per_pair, per_wall, scratch, counters, out);
+    k3c_energy<false><<<dim3(tiles, n_chains), 128, 0, stream>>>(params, states, cap, chain0, starts, sx, sy, sz, orig, per_pair, per_wall, scratch, counters, out);
     return cudaGetLastError();
 }
 

@@ -19,6 +19,12 @@ cudaError_t launch_k3(int tiles, int n_chains, int chain0, const ChainParams* pa
                       const double* Z, int cap, double* per_pair, double* per_wall, double* scratch, unsigned int* counters, double* out,
                       cudaStream_t stream);
 
+size_t k3c_cells_per_chain();
+cudaError_t launch_k3_cells(int maxn, int n_chains, int chain0, const ChainParams* params, ChainState* states, const double* X,
+                            const double* Y, const double* Z, int cap, int* cell_of, int* counts, int* starts, double* sx, double* sy,
+                            double* sz, int* orig, double* per_pair, double* per_wall, double* scratch, unsigned int* counters, double* out,
+                            cudaStream_t stream);
+
 cudaError_t launch_fp64_peak(double* out, int blocks, int threads, int iters, cudaStream_t stream);
 cudaError_t launch_philox_fill(unsigned long long seed, unsigned int chain, unsigned long long first_step, int n_steps, double* out,
                                cudaStream_t stream);

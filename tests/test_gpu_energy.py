@@ -152,3 +152,33 @@ def test_state_mutation_matches_reference_semantics(mcpm):
     ex, ey, ez = ex[:-1], ey[:-1], ez[:-1]
     ex[3], ey[3], ez[3] = 4.0, 5.0, 6.0
     assert np.array_equal(gx, ex) and np.array_equal(gy, ey) and np.array_equal(gz, ez)
+
+
+@pytest.mark.parametrize("system,n,seed", [
+    (O.argon_bulk(size=40.0, rcut=12.0), 9000, 31),                       # 3x3x3 cells: every neighbour cell distinct
+    (O.argon_bulk(size=100.0, rcut=12.0), 20000, 32),                     # config C4: 8x8x8 cells
+    (O.make_system(geometry=1, wall_kind=1, n_layers=3, n_disp=1, n_vol=0, n_swap=1, n_equil_sets=0,
+                   width=(50.0, 62.0, 30.0), temperature=120.0, eps_ff=119.8, sig_ff=3.405, rcut=12.0,
+                   molar_mass=39.948, mu=-1200.0, eps_sf=57.92, sig_sf=3.4025, rho_s=0.382, delta=3.35, dr=1.0), 8500, 33),
+])
+def test_k3_cell_list_matches_all_pairs_and_oracle(mcpm, system, n, seed):
+    """K3 through the cell list == K3 all-pairs == MC::BoxEnergy (oracle), per particle and in total."""
+    x, y, z = random_config(system, n, seed)
+    with mcpm.Engine(1, n + 32) as e:
+        e.set_system(system)
+        e.set_positions(0, x, y, z)
+        e.use_cell_list(True)
+        box_c, pp_c, pw_c = e.box_energy(0)
+        ms_cells = e.last_kernel_ms()
+        e.use_cell_list(False)
+        box_a, pp_a, pw_a = e.box_energy(0)
+        ms_all = e.last_kernel_ms()
+    assert close(box_c, box_a) and close(pp_c, pp_a) and close(pw_c, pw_a)
+    if n <= 9000:
+        c = O.COracle(system, n + 8)
+        c.set_positions(x, y, z)
+        obox, opp, opw = c.box_energy()
+        assert close(box_c, obox) and close(pp_c, opp) and close(pw_c, opw)
+    print(f"n={n}: cell-list K3 {ms_cells:.3f} ms, all-pairs K3 {ms_all:.3f} ms")
+    if n >= 20000:
+        assert ms_cells < ms_all
