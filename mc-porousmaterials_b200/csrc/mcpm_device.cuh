@@ -101,10 +101,16 @@ __device__ __forceinline__ void pair_acc(double& acc, double r2, const PairGeom&
 __device__ __forceinline__ void wall_two(const ChainParams& P, double z_a, double z_b, double& w_a, double& w_b, int lane) {
     double acc = 0.0;
     if (P.wall_kind == MCPM_WALL_SLIT_LJ && P.geometry == MCPM_GEOM_SLIT) {
-        if (lane < 16) {
-            double zc = ((lane & 8) ? z_b : z_a) - P.halfH;
-            if (lane & 1) zc = -zc;
-            for (int layer = (lane >> 1) & 3; layer < P.n_layers; layer += 4) {
+        double zc = ((lane & 8) ? z_b : z_a) - P.halfH;
+        if (lane & 1) zc = -zc;
+        const int layer0 = (lane >> 1) & 3;
+        if (P.n_layers <= 4) {   // the usual case (3 graphite layers): straight-line code, one term per lane, no loop
+            const double t = P.sig_sf * fast_rcp(P.halfH + layer0 * P.delta + zc);
+            const double t2 = t * t, t4 = t2 * t2;
+            const double term = 0.2 * (t4 * t4 * t2) - 0.5 * t4;
+            acc = (lane < 16 && layer0 < P.n_layers) ? term : 0.0;
+        } else if (lane < 16) {
+            for (int layer = layer0; layer < P.n_layers; layer += 4) {
                 double t = P.sig_sf * fast_rcp(P.halfH + layer * P.delta + zc);
                 double t2 = t * t, t4 = t2 * t2;
                 acc += 0.2 * (t4 * t4 * t2) - 0.5 * t4;
@@ -240,6 +246,37 @@ __device__ __forceinline__ double wrap_floor(double x, double L) {
     if (x >= -L && x < L + L) q = (x < 0.0) ? -1.0 : ((x >= L) ? 1.0 : 0.0);
     else q = floor(__ddiv_rn(x, L));
     return __dsub_rn(x, __dmul_rn(q, L));
+}
+
+// Common case of wrap_floor as pure selects; `odd` is raised when x lies outside [-L, 2L) and the caller must redo
+// the coordinate with wrap_floor (one rare, warp-uniform branch for all three coordinates).
+__device__ __forceinline__ double wrap_select(double x, double L, bool& odd) {
+    odd = odd || !(x >= -L && x < L + L);
+    const double q = (x < 0.0) ? -1.0 : ((x >= L) ? 1.0 : 0.0);
+    return __dsub_rn(x, __dmul_rn(q, L));
+}
+
+// Metropolis tests without a logarithm and (mostly) without an exponential.  The reference tests `u < f` with
+// f = exp(-dE/T), zz V exp(-E/T)/(N+1) or N exp(E/T)/(zz V).  Uniforms lie in (0, 0.9999) (quirk Q1; a 53-bit zero
+// has probability 1e-16), so ln f >= 0 always accepts and ln f < -37 (< ln of the smallest non-zero uniform) always
+// rejects; only in between is f evaluated, with the reference's own expression.  All inputs are identical in every
+// thread, so the branches are warp-uniform.
+__device__ __forceinline__ bool metropolis_translation(double u, double arg /* dE/T */) {
+    if (!(arg > 0.0)) return arg == arg;               // downhill: always (NaN: never, as u < NaN is false)
+    if (arg > 37.0) return u == 0.0 && exp(-arg) > 0.0;
+    return u < exp(-arg);
+}
+__device__ __forceinline__ bool metropolis_insertion(double u, double x /* -E/T */, double ln_zzV, double zzV, int n) {
+    const double t = ln_zzV + x;                        // ln f = t - ln(n+1), 0 <= ln(n+1) < 21
+    if (t >= 21.0) return true;
+    if (!(t >= -37.0)) return (t == t) && u == 0.0 && zzV * exp(x) / (double)(n + 1) > 0.0;
+    return u < zzV * exp(x) / (double)(n + 1);          // src/moves.cpp:306
+}
+__device__ __forceinline__ bool metropolis_deletion(double u, double y /* E/T */, double ln_zzV, double zzV, int n) {
+    const double t = y - ln_zzV;                        // ln f = t + ln(n), 0 <= ln(n) < 21
+    if (t >= 0.0) return true;
+    if (!(t >= -58.0)) return (t == t) && u == 0.0 && (double)n * exp(y) / zzV > 0.0;
+    return u < (double)n * exp(y) / zzV;                // src/moves.cpp:326
 }
 
 // ln(u) for the log-domain Metropolis test  ln u < -dE/T  <=>  u < exp(-dE/T).  u == 0 maps to the log of

@@ -172,7 +172,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
     unsigned long long step = st.steps_done;
     int overflow = 0;
     const double wsum = P.wsum, thr_disp = P.thr_disp, thr_vol = P.thr_vol;
-    const double beta = P.beta, eps4 = P.eps4, ln_zzV = P.ln_zzV;
+    const double beta = P.beta, eps4 = P.eps4, ln_zzV = P.ln_zzV, zzV = P.zzV;
     const double Lx = P.L[0], Ly = P.L[1], Lz = P.L[2];
     Fwd fwd; fwd.slot = -1; fwd.x = fwd.y = fwd.z = 0.0;
     int parity = 0;
@@ -196,14 +196,14 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                 const double u_i = rng.template at<3>(), u_x = rng.template at<4>(), u_y = rng.template at<5>(),
                              u_z = rng.template at<6>(), u_a = rng.template at<7>();
                 rng.end_step(8);
-                const double lnu = log_uniform(u_a);
                 const int i = (int)(u_i * (double)n);                             // int(u*n)+1 on 1-based slots; n==0 -> stale slot (Q12)
                 double xo, yo, zo;
                 load_slot(xs, ys, zs, i, fwd, xo, yo, zo);
-                double xn = wrap_floor(__dadd_rn(xo, __dmul_rn(u_x - 0.5, dr)), Lx);    // MC::PBC: x and y are always periodic
-                double yn = wrap_floor(__dadd_rn(yo, __dmul_rn(u_y - 0.5, dr)), Ly);
-                double zn = __dadd_rn(zo, __dmul_rn(u_z - 0.5, dr));
-                if (PBZ) zn = wrap_floor(zn, Lz);
+                const double xr = __dadd_rn(xo, __dmul_rn(u_x - 0.5, dr)), yr = __dadd_rn(yo, __dmul_rn(u_y - 0.5, dr));
+                const double zr = __dadd_rn(zo, __dmul_rn(u_z - 0.5, dr));
+                bool odd = false;                                                 // MC::PBC: x and y are always periodic
+                double xn = wrap_select(xr, Lx, odd), yn = wrap_select(yr, Ly, odd), zn = PBZ ? wrap_select(zr, Lz, odd) : zr;
+                if (odd) { xn = wrap_floor(xr, Lx); yn = wrap_floor(yr, Ly); if (PBZ) zn = wrap_floor(zr, Lz); }
                 double v[2];
                 pair_sum2<FAST, PBZ>(xs, ys, zs, n, i, g, xo, yo, zo, xn, yn, zn, tid, T, v[0], v[1]);
                 double wo, wn;
@@ -211,7 +211,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                 cta_allsum<2, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
                 const double po = eps4 * v[0], pn = eps4 * v[1];
                 const double dE = (pn + wn) - (po + wo);                          // newEnergy - oldEnergy, src/moves.cpp:169
-                const bool acc = lnu < -(dE * beta);                              // u < exp(-dE/T), src/moves.cpp:170-172
+                const bool acc = metropolis_translation(u_a, dE * beta);          // u < exp(-dE/T), src/moves.cpp:170-172
                 sc.n_disp++; sc.evals += 2ull * (unsigned long long)n;
                 fwd.slot = -1;
                 if (acc) {
@@ -235,8 +235,6 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                     if (n >= cap) { overflow = 1; break; }
                     const double u_x = rng.template at<3>(), u_y = rng.template at<4>(), u_z = rng.template at<5>(), u_a = rng.template at<6>();
                     rng.end_step(7);
-                    const double lnu = log_uniform(u_a);
-                    const double ln_np1 = log((double)(n + 1));
                     const double xi = u_x * Lx, yi = u_y * Ly, zi = u_z * Lz;     // InsertParticle, src/moves.cpp:46-54
                     // the trial position is written to the first free slot even if rejected (src/moves.cpp:302-303)
                     if ((n & tmask) == tid) { xs[n] = xi; ys[n] = yi; zs[n] = zi; }
@@ -247,8 +245,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                     cta_allsum<1, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
                     const double pi_ = eps4 * v[0];
                     const double e_in = pi_ + wi;
-                    // u < zz*V*exp(-E/T)/(N+1), src/moves.cpp:306-307, in the log domain
-                    const bool acc = lnu < (ln_zzV - e_in * beta) - ln_np1;
+                    const bool acc = metropolis_insertion(u_a, -(e_in * beta), ln_zzV, zzV, n);   // src/moves.cpp:306-307
                     sc.n_ins++; sc.evals += (unsigned long long)n;
                     fwd.slot = -1;
                     if (acc) { sc.acc_ins++; n++; e_pair += pi_; e_wall += wi; }
@@ -256,8 +253,6 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                 } else if (n > 0) {
                     const double u_o = rng.template at<3>(), u_a = rng.template at<4>();
                     rng.end_step(5);
-                    const double lnu = log_uniform(u_a);
-                    const double ln_n = log((double)n);
                     const int o = (int)(u_o * (double)n + 1.0) - 1;               // int(u*n+1) on 1-based slots
                     double xo, yo, zo, xl, yl, zl;
                     load_slot(xs, ys, zs, o, fwd, xo, yo, zo);
@@ -269,8 +264,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                     cta_allsum<1, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
                     const double po = eps4 * v[0];
                     const double e_out = po + wo;
-                    // u < N*exp(E/T)/(zz*V), src/moves.cpp:326-327, in the log domain
-                    const bool acc = lnu < (ln_n + e_out * beta) - ln_zzV;
+                    const bool acc = metropolis_deletion(u_a, e_out * beta, ln_zzV, zzV, n);      // src/moves.cpp:326-327
                     sc.n_del++; sc.evals += (unsigned long long)n;
                     fwd.slot = -1;
                     if (acc) {
