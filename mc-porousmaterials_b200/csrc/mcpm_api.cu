@@ -287,9 +287,15 @@ int mcpm_set_positions_all(mcpm_ctx* c, const int* n, const double* x, const dou
         if (n[k] < 0 || n[k] > c->cap) return fail(MCPM_ERR_CAPACITY, "chain %d: n=%d exceeds capacity %d", k, n[k], c->cap);
         if (!c->has_system[k]) return fail(MCPM_ERR_ARG, "set the system of chain %d first", k);
     }
-    CU(cudaMemcpyAsync(c->d_x, x, sizeof(double) * np, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->d_y, y, sizeof(double) * np, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->d_z, z, sizeof(double) * np, cudaMemcpyHostToDevice, c->stream));
+    // only the columns that can hold live particles (plus the free slot an insertion would use) cross the bus
+    int wcols = 1;
+    for (int k = 0; k < c->n_chains; k++) wcols = std::max(wcols, n[k] + 1);
+    wcols = std::min(c->cap, (wcols + 31) & ~31);
+    const size_t pitch = sizeof(double) * c->cap, wbytes = sizeof(double) * wcols;
+    (void)np;
+    CU(cudaMemcpy2DAsync(c->d_x, pitch, x, pitch, wbytes, c->n_chains, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpy2DAsync(c->d_y, pitch, y, pitch, wbytes, c->n_chains, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpy2DAsync(c->d_z, pitch, z, pitch, wbytes, c->n_chains, cudaMemcpyHostToDevice, c->stream));
     for (int k = 0; k < c->n_chains; k++) {
         ChainState& S = c->h_state[k];
         const size_t off = (size_t)k * c->cap;
@@ -305,9 +311,14 @@ int mcpm_get_positions_all(mcpm_ctx* c, int* n, double* x, double* y, double* z)
     if (!c || !n || !x || !y || !z) return fail(MCPM_ERR_ARG, "null argument");
     CU(cudaSetDevice(c->device));
     const size_t np = (size_t)c->n_chains * c->cap;
-    CU(cudaMemcpyAsync(x, c->d_x, sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(y, c->d_y, sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(z, c->d_z, sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream));
+    int wcols = 1;
+    for (int k = 0; k < c->n_chains; k++) wcols = std::max(wcols, c->h_state[k].st.n + 1);
+    wcols = std::min(c->cap, (wcols + 31) & ~31);
+    const size_t pitch = sizeof(double) * c->cap, wbytes = sizeof(double) * wcols;
+    (void)np;
+    CU(cudaMemcpy2DAsync(x, pitch, c->d_x, pitch, wbytes, c->n_chains, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpy2DAsync(y, pitch, c->d_y, pitch, wbytes, c->n_chains, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpy2DAsync(z, pitch, c->d_z, pitch, wbytes, c->n_chains, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     for (int k = 0; k < c->n_chains; k++) n[k] = c->h_state[k].st.n;
     return MCPM_OK;
@@ -471,7 +482,7 @@ static int pick_threads(const mcpm_ctx* c, int maxn) {
     // with ~8 warps resident per SM in total — one warp per chain when many chains share an SM (the per-step overhead:
     // uniforms, wall term, reductions, decision, is paid once per warp), 256 threads when shared memory or the chain
     // count leaves one chain per SM (C3: N = 5.4k, 157 KB of positions per CTA).
-    const size_t smem_per_cta = (size_t)(3 * c->cap + 232) * sizeof(double);
+    const size_t smem_per_cta = (size_t)(3 * c->cap) * sizeof(double) + 1024;
     const int by_smem = std::max<int>(1, (int)((size_t)c->max_smem / smem_per_cta));
     const int by_count = (c->n_chains + c->num_sms - 1) / c->num_sms;
     const int resident = std::max(1, std::min(by_smem, by_count));

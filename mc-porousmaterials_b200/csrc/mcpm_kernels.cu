@@ -386,13 +386,14 @@ __global__ void __launch_bounds__(MAXT, MINB) k2_chains(const ChainParams* __res
     double* xs = GLOBAL ? X + off : smem;
     double* ys = GLOBAL ? Y + off : smem + cap;
     double* zs = GLOBAL ? Z + off : smem + 2 * cap;
-    double* partials = GLOBAL ? smem : smem + 3 * cap;  // 2 parities x 32 warps x 2 values
-    double* hist = partials + 128;                      // MCPM_RDF_BINS doubles (+ padding)
+    // after the positions: [sampling kernels: RDF histogram, 104 doubles] [multi-warp CTAs: 2 parities x 32 warps x 2 partial sums]
+    double* hist = GLOBAL ? smem : smem + 3 * cap;
+    double* partials = hist + (SAMPLE ? 104 : 0);
     __shared__ ChainParams P;
     __shared__ ChainState S;
     const int tid = threadIdx.x, T = blockDim.x;
     if (tid == 0) { P = params[chain]; S = states[chain]; }
-    for (int k = threadIdx.x; k < MCPM_RDF_BINS + 4; k += blockDim.x) hist[k] = 0.0;
+    if (SAMPLE) for (int k = threadIdx.x; k < MCPM_RDF_BINS + 4; k += blockDim.x) hist[k] = 0.0;
     __syncthreads();
     if (!GLOBAL) {
         // stage every slot (not only the n live ones): stale slots are observable through quirk Q12
@@ -421,7 +422,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k2_chains(const ChainParams* __res
 #undef MCPM_GO
     __syncthreads();
     if (!GLOBAL) for (int j = tid; j < cap; j += T) { X[off + j] = xs[j]; Y[off + j] = ys[j]; Z[off + j] = zs[j]; }
-    if (a.sample_rdf && a.rdf) for (int k = tid; k < MCPM_RDF_BINS; k += T) a.rdf[(size_t)chain * MCPM_RDF_BINS + k] += hist[k];
+    if (SAMPLE && a.sample_rdf && a.rdf) for (int k = tid; k < MCPM_RDF_BINS; k += T) a.rdf[(size_t)chain * MCPM_RDF_BINS + k] += hist[k];
     if (tid == 0) states[chain] = S;
 }
 
@@ -754,7 +755,8 @@ __global__ void philox_fill_kernel(unsigned long long seed, unsigned int chain, 
 // ================================================================================================
 // launchers
 // ================================================================================================
-static size_t k2_smem_bytes(int cap) { return (size_t)(3 * cap + 128 + 104) * sizeof(double); }
+// positions + (multi-warp CTAs) 128 doubles of partial sums + (sampling kernels) the RDF histogram
+static size_t k2_smem_bytes(int cap, bool multi, bool sample) { return (size_t)(3 * cap + (multi ? 128 : 0) + (sample ? 104 : 0)) * sizeof(double); }
 
 size_t k2_smem_limit_cap(int max_smem_optin) { return ((size_t)max_smem_optin / sizeof(double) - 128 - 104 - 64) / 3; }
 
@@ -769,7 +771,9 @@ static cudaError_t launch_k2_rng(int n_chains, int threads, bool global, bool fa
         return cudaSuccess;
     };
     // The hot kernels (coordinates inside the box, no in-kernel sampling) exist for every CTA shape; register budgets
-    // by CTA size (ptxas: no spills at 128): <=64, <=256, <=512 threads -> 128 regs; 1024 -> 64.
+    // by CTA size: <=64, <=256, <=512 threads -> 128 regs; 1024 -> 64.  (ptxas fits the 32-thread kernel into 96
+    // registers without spills, but measured on B200 that costs more ILP than the extra occupancy returns: C2
+    // 7.2e8 vs 7.7e8 moves/s.)
     // The general kernels (general minimum image for coordinates outside the box and/or Widom + RDF sampling after
     // every production step) exist for one shared-memory and one global-memory CTA shape;
     // k2_threads_supported() clamps the thread count accordingly.
@@ -792,7 +796,8 @@ int k2_threads_supported(int threads, bool global, bool fast, bool sample) {
 cudaError_t launch_k2(int rng_mode, int n_chains, int threads, bool fast, bool sample, const ChainParams* params, ChainState* states,
                       const int* order, double* X, double* Y, double* Z, const RunArgs& a, int max_smem_optin, cudaStream_t stream) {
     const bool global = (size_t)a.cap > k2_smem_limit_cap(max_smem_optin);
-    const size_t smem = global ? (128 + 104) * sizeof(double) : k2_smem_bytes(a.cap);
+    const bool multi = threads > 32 || !fast || sample;   // only the smallest hot kernel runs single-warp CTAs
+    const size_t smem = k2_smem_bytes(global ? 0 : a.cap, multi, !fast || sample);
     cudaError_t err = rng_mode == MCPM_RNG_PHILOX
                           ? launch_k2_rng<MCPM_RNG_PHILOX>(n_chains, threads, global, fast, sample, smem, params, states, order, X, Y, Z, a, stream)
                           : launch_k2_rng<MCPM_RNG_REPLAY>(n_chains, threads, global, fast, sample, smem, params, states, order, X, Y, Z, a, stream);
