@@ -266,3 +266,29 @@ def test_nvt_widom_replay_matches_reference_stream(mcpm, golden):
     assert st.replay_consumed == o.draws()
     assert (st.widom_insertions, st.widom_deletions) == (ni, nd)
     assert st.widom_insert == pytest.approx(wi, rel=1e-10) and st.widom_delete == pytest.approx(wd, rel=1e-10)
+
+
+def test_results_do_not_depend_on_threads_per_chain(mcpm, golden):
+    """Race detector by construction: 60 000 steps of 4 chains at 32/64/256/512 threads per chain must give bit-identical
+    configurations, counters and accumulators (every thread decides redundantly from the same partial sums, and
+    the owner-writes / register-forwarding scheme has one barrier per step; compute-sanitizer is closed on this pool)."""
+    arrays, meta = golden
+    s = system_from_meta(meta["c1"]["system"])
+    s.n_equil_sets = 2
+    x, y, z = arrays["c1_x"], arrays["c1_y"], arrays["c1_z"]
+    ref = None
+    for threads in (32, 64, 256, 512):
+        with mcpm.Engine(4, 1024) as e:
+            e.set_system(s)
+            for c in range(4):
+                e.set_positions(c, x, y, z)
+            stats = e.run(1, 6, 10000, seed=2025, threads=threads)
+            pos = [e.get_positions(c) for c in range(4)]
+        sig = [(st.n, st.dr, st.tot_disp_acc, st.tot_ins_acc, st.tot_del_acc, st.sum_n, st.pair_evals) for st in stats]
+        if ref is None:
+            ref = (sig, pos)
+            continue
+        assert sig == ref[0], f"threads={threads}"
+        for a, b in zip(pos, ref[1]):
+            for u, v in zip(a, b):
+                assert np.array_equal(u, v), f"threads={threads}"
