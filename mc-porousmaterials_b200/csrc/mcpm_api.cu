@@ -51,6 +51,8 @@ struct mcpm_ctx {
     int *d_cell_of = nullptr, *d_cell_counts = nullptr, *d_cell_starts = nullptr, *d_orig = nullptr;
     double *d_sx = nullptr, *d_sy = nullptr, *d_sz = nullptr;
     int use_cells = 1;             // 0 disables the cell-list path (tests compare both)
+    int use_cache = 1;             // per-particle energy cache in K2 (mcpm_use_energy_cache)
+    double* d_ep = nullptr;        // [n_chains][cap], allocated on first use
     double* d_replay = nullptr; size_t replay_doubles = 0;
     unsigned char* d_trace = nullptr; size_t trace_bytes = 0;
     double* h_pin = nullptr;       // pinned staging, 4*n_chains+8 doubles
@@ -196,7 +198,7 @@ int mcpm_destroy(mcpm_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_params); cudaFree(c->d_state); cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_z);
     cudaFree(c->d_order); cudaFree(c->d_scratch); cudaFree(c->d_counters); cudaFree(c->d_out);
-    cudaFree(c->d_pp); cudaFree(c->d_pw); cudaFree(c->d_rdf);
+    cudaFree(c->d_pp); cudaFree(c->d_pw); cudaFree(c->d_rdf); cudaFree(c->d_ep);
     cudaFree(c->d_cell_of); cudaFree(c->d_cell_counts); cudaFree(c->d_cell_starts); cudaFree(c->d_orig);
     cudaFree(c->d_sx); cudaFree(c->d_sy); cudaFree(c->d_sz); cudaFree(c->d_replay); cudaFree(c->d_trace);
     if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -529,6 +531,8 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     a.first_set = p->first_set; a.n_sets = p->n_sets; a.steps_per_set = p->steps_per_set; a.seed = p->seed;
     a.check_energy = p->check_energy; a.cap = c->cap;
     a.sample_rdf = p->sample_rdf; a.rdf = c->d_rdf;
+    if (c->use_cache && !c->d_ep) CU(cudaMalloc(&c->d_ep, sizeof(double) * (size_t)c->n_chains * c->cap));
+    a.ep = c->use_cache ? c->d_ep : nullptr;
     const unsigned long long nsteps = (unsigned long long)p->n_sets * (unsigned long long)p->steps_per_set;
     if (p->rng_mode == MCPM_RNG_REPLAY) {
         const size_t need = (size_t)c->n_chains * p->replay_stride;
@@ -551,7 +555,7 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
         a.trace = c->d_trace; a.trace_stride = nsteps;
     }
     CU(cudaEventRecord(c->ev0, c->stream));
-    CU(launch_k2(p->rng_mode, c->n_chains, threads, all_fast, sample, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->max_smem, c->stream));
+    CU(launch_k2(p->rng_mode, c->n_chains, threads, all_fast, sample, c->use_cache != 0, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->max_smem, c->stream));
     CU(cudaEventRecord(c->ev1, c->stream));
     c->launches++;
     if (p->trace) CU(cudaMemcpyAsync(p->trace, c->d_trace, (size_t)c->n_chains * nsteps, cudaMemcpyDeviceToHost, c->stream));
@@ -624,6 +628,12 @@ int mcpm_set_running_energy(mcpm_ctx* c, const double* pair, const double* wall)
     }
     CU(cudaMemcpyAsync(c->d_state, c->h_state.data(), sizeof(ChainState) * c->n_chains, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return MCPM_OK;
+}
+
+int mcpm_use_energy_cache(mcpm_ctx* c, int enable) {
+    if (!c) return fail(MCPM_ERR_ARG, "null context");
+    c->use_cache = enable ? 1 : 0;
     return MCPM_OK;
 }
 

@@ -77,6 +77,9 @@ __device__ __forceinline__ double dist2(const PairGeom& g, double xi, double yi,
     return fma(dz, dz, fma(dy, dy, dx * dx));
 }
 
+// One partner's masked term (0 when out of range / self / coincident), for the energy-cache updates.
+__device__ __forceinline__ double pair_term(double r2, const PairGeom& g, int j, int self);
+
 // Adds partner j's contribution to acc, fully predicated (no branch, no select):
 //   r2 <= rc2   inclusive cutoff (quirk Q8)
 //   hi(r2) != 0 exactly coincident distinct particles, which the reference skips by position equality
@@ -91,6 +94,12 @@ __device__ __forceinline__ void pair_acc(double& acc, double r2, const PairGeom&
         "@p add.f64 %0, %0, %6;\n\t}"
         : "+d"(acc)
         : "d"(r2), "d"(g.rc2), "r"(__double2hiint(r2)), "r"(j), "r"(self), "d"(e));
+}
+
+__device__ __forceinline__ double pair_term(double r2, const PairGeom& g, int j, int self) {
+    double t = 0.0;
+    pair_acc(t, r2, g, j, self);
+    return t;
 }
 
 // ------------------------------------------------------------------------------------------------

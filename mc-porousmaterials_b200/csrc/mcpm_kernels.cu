@@ -103,7 +103,7 @@ __device__ __forceinline__ void cta_allsum(double (&v)[NV], double* partials, in
 
 // Full energy of the chain held in shared memory: per-particle sums as MC::BoxEnergy forms them
 // (src/energy.cpp:106-124; every pair is visited twice and the pair total halved).
-template <bool FAST, bool PBZ>
+template <bool FAST, bool PBZ, bool MULTI>
 __device__ void cta_box_energy(const double* xs, const double* ys, const double* zs, int n, const ChainParams& P, const PairGeom& g,
                                double* partials, int W, int warp, int lane, int tid, int T, double& pair_half, double& wall) {
     double v[2] = {0.0, 0.0};
@@ -115,7 +115,7 @@ __device__ void cta_box_energy(const double* xs, const double* ys, const double*
         v[1] += wall_one(P, zi);
     }
     __syncthreads();
-    cta_allsum<2, true>(v, partials, 0, W, warp, lane);
+    cta_allsum<2, MULTI>(v, partials, 0, W, warp, lane);   // single-warp CTAs have no partials area
     __syncthreads();
     pair_half = 0.5 * (P.eps4 * v[0]);
     wall = v[1];
@@ -144,6 +144,88 @@ __device__ void cta_rdf(const double* xs, const double* ys, const double* zs, in
 // MC::BarWeight, src/moves.cpp:409, with barC = 1 (ResetStats, src/MC.cpp:88)
 __device__ __forceinline__ double bar_weight(double energy, double beta) { return 1. / cosh(0.5 * (energy - 1.) * beta); }
 
+// ---- energy cache -------------------------------------------------------------------------------------------------
+// ep[j] = sum over partners k of s6(s6-1) for particle j (unscaled by 4*eps), kept in global memory (L2-resident, 8 B per
+// particle: it would cost a third more shared memory and with it occupancy).  With it a trial move needs the partner scan
+// only for the NEW position (translation, insertion) or not at all (deletion): the old energy is ep[i].  An ACCEPTED move
+// pays a second pass that applies the per-pair changes to every partner's entry.  At the reference's adapted ~20 %
+// translation acceptance this is ~0.95 N pair evaluations per step instead of 1.5 N.  The cache is rebuilt from scratch
+// at the start of every launch (N^2 evaluations), which also re-anchors the running energies.
+template <bool FAST, bool PBZ, bool MULTI>
+__device__ void cache_fill(const double* xs, const double* ys, const double* zs, double* ep, int n, const ChainParams& P, const PairGeom& g,
+                           double* partials, int W, int warp, int lane, int tid, int T, double& pair_half, double& wall) {
+    double v[2] = {0.0, 0.0};
+    for (int i = tid; i < n; i += T) {
+        const double xi = xs[i], yi = ys[i], zi = zs[i];
+        double s0 = 0.0, s1 = 0.0;
+        int j = 0;
+        for (; j + 1 < n; j += 2) {
+            pair_acc(s0, dist2<FAST, PBZ>(g, xi, yi, zi, xs[j], ys[j], zs[j]), g, j, i);
+            pair_acc(s1, dist2<FAST, PBZ>(g, xi, yi, zi, xs[j + 1], ys[j + 1], zs[j + 1]), g, j + 1, i);
+        }
+        if (j < n) pair_acc(s0, dist2<FAST, PBZ>(g, xi, yi, zi, xs[j], ys[j], zs[j]), g, j, i);
+        ep[i] = s0 + s1;
+        v[0] += s0 + s1;
+        v[1] += wall_one(P, zi);
+    }
+    __syncthreads();
+    cta_allsum<2, MULTI>(v, partials, 0, W, warp, lane);   // single-warp CTAs have no partials area
+    __syncthreads();
+    pair_half = 0.5 * (P.eps4 * v[0]);
+    wall = v[1];
+}
+
+// Second pass of an accepted move: every thread updates the cache entries of its own slots.
+//   has_a: particle at (xa,ya,za) disappears from every partner's sum;  has_b: one at (xb,yb,zb) appears.
+// Returns true if this thread saw a term so large (|s6(s6-1)| > 1e6, i.e. a hard overlap of ~5e8 K) that adding and later
+// removing it would leave a visible rounding residue in the cache: the caller then rebuilds the cache at once.
+template <bool FAST, bool PBZ>
+__device__ __forceinline__ bool cache_apply(const double* xs, const double* ys, const double* zs, double* ep, int n, int self, const PairGeom& g,
+                                            bool has_a, double xa, double ya, double za, bool has_b, double xb, double yb, double zb,
+                                            int tid, int T) {
+    bool big = false;
+    for (int j = tid; j < n; j += T) {
+        const double xj = xs[j], yj = ys[j], zj = zs[j];
+        double tb = 0.0, ta = 0.0;
+        if (has_b) tb = pair_term(dist2<FAST, PBZ>(g, xb, yb, zb, xj, yj, zj), g, j, self);
+        if (has_a) ta = pair_term(dist2<FAST, PBZ>(g, xa, ya, za, xj, yj, zj), g, j, self);
+        big = big || !(fabs(tb) <= 1e6) || !(fabs(ta) <= 1e6);
+        if (j != self) ep[j] += tb - ta;
+    }
+    return big;
+}
+
+// Barrier that also ORs a flag over the CTA (one warp: a vote).
+template <bool MULTI>
+__device__ __forceinline__ bool cta_sync_or(bool flag) {
+    if (MULTI) return __syncthreads_or(flag ? 1 : 0) != 0;
+    const bool r = __any_sync(MCPM_FULL_MASK, flag);
+    __syncwarp();
+    return r;
+}
+template <bool MULTI>
+__device__ __forceinline__ void cta_sync() { if (MULTI) __syncthreads(); else __syncwarp(); }
+
+// Order-independent checksum of the live configuration (all threads return the same value; contains barriers).
+template <bool MULTI>
+__device__ unsigned long long config_checksum(const double* xs, const double* ys, const double* zs, int n, unsigned long long* scratch,
+                                              int tid, int T, int lane, int warp, int W) {
+    unsigned long long h = 0ull;
+    for (int j = tid; j < n; j += T)
+        h += (unsigned long long)__double_as_longlong(xs[j]) * 0x9E3779B97F4A7C15ull + (unsigned long long)__double_as_longlong(ys[j]) * 0xC2B2AE3D27D4EB4Full +
+             (unsigned long long)__double_as_longlong(zs[j]) * 0x165667B19E3779F9ull + (unsigned long long)(j + 1) * 0xD6E8FEB86659FD93ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(MCPM_FULL_MASK, h, o);
+    if (!MULTI) return h + (unsigned long long)n;          // single-warp CTAs have no scratch area
+    __syncthreads();
+    if (lane == 0) scratch[warp] = h;
+    __syncthreads();
+    unsigned long long tot = (unsigned long long)n;
+    for (int w = 0; w < W; w++) tot += scratch[w];
+    __syncthreads();
+    return tot;
+}
+
 // Per-set counters replicated in registers (cheap ints); flushed to the 64-bit totals in shared memory
 // by thread 0 at the end of every set.
 struct SetCounters {
@@ -157,7 +239,7 @@ struct SetCounters {
 // nothing but the partner loop's partial sums crosses threads.  (A variant that kept counters and
 // energies in shared memory for thread 0 only used 80 registers instead of 128 but was 10-15 % slower at
 // every occupancy measured on B200: the extra LDS/STS sit on the per-step critical path.)
-template <class Source, bool FAST, bool MULTI, bool PBZ, bool SAMPLE>
+template <class Source, bool FAST, bool MULTI, bool PBZ, bool SAMPLE, bool CACHE>
 __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, double* xs, double* ys, double* zs, double* partials,
                            const RunArgs& a, unsigned char* trace, int cap, uint32_t chain, double* hist) {
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
@@ -178,6 +260,18 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
     int parity = 0;
     SetCounters sc;
     const int steps_per_set = (int)a.steps_per_set;
+    double* ep = CACHE ? a.ep + (size_t)chain * (size_t)cap : nullptr;
+    if (CACHE) {
+        // The cache left by the previous launch is reused if the configuration is still the one it was built for
+        // (checksum); otherwise it is rebuilt, which also re-anchors the running energies (what MC::BoxEnergy returns).
+        const unsigned long long sum = config_checksum<MULTI>(xs, ys, zs, n, (unsigned long long*)partials, tid, T, lane, warp, W);
+        if (!(S.cache_valid && S.cache_sum == sum)) {
+            double c_pair0, c_wall0;
+            cache_fill<FAST, PBZ, MULTI>(xs, ys, zs, ep, n, P, g, partials, W, warp, lane, tid, T, c_pair0, c_wall0);
+            e_pair = c_pair0; e_wall = c_wall0;
+            if (lead) st.pair_evals += (unsigned long long)n * (unsigned long long)n;
+        }
+    }
 
     for (int set = a.first_set; set < a.first_set + a.n_sets && !overflow; set++) {
         sc.reset();                      // MC::ResetStats, src/MC.cpp:81-98
@@ -205,14 +299,25 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                 double xn = wrap_select(xr, Lx, odd), yn = wrap_select(yr, Ly, odd), zn = PBZ ? wrap_select(zr, Lz, odd) : zr;
                 if (odd) { xn = wrap_floor(xr, Lx); yn = wrap_floor(yr, Ly); if (PBZ) zn = wrap_floor(zr, Lz); }
                 double v[2];
-                pair_sum2<FAST, PBZ>(xs, ys, zs, n, i, g, xo, yo, zo, xn, yn, zn, tid, T, v[0], v[1]);
                 double wo, wn;
-                wall_two(P, zo, zn, wo, wn, lane);
-                cta_allsum<2, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
+                if (CACHE) {
+                    const double ep_i = (n > 0) ? ep[i] : 0.0;                    // old pair sum from the cache (issued before the scan)
+                    v[1] = pair_sum1<FAST, PBZ>(xs, ys, zs, n, i, g, xn, yn, zn, tid, T);
+                    wall_two(P, zo, zn, wo, wn, lane);
+                    double w1[1] = {v[1]};
+                    cta_allsum<1, MULTI>(w1, partials, parity, W, warp, lane); parity ^= 1;
+                    v[0] = ep_i; v[1] = w1[0];
+                    sc.evals += (unsigned long long)n;
+                } else {
+                    pair_sum2<FAST, PBZ>(xs, ys, zs, n, i, g, xo, yo, zo, xn, yn, zn, tid, T, v[0], v[1]);
+                    wall_two(P, zo, zn, wo, wn, lane);
+                    cta_allsum<2, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
+                    sc.evals += 2ull * (unsigned long long)n;
+                }
                 const double po = eps4 * v[0], pn = eps4 * v[1];
                 const double dE = (pn + wn) - (po + wo);                          // newEnergy - oldEnergy, src/moves.cpp:169
                 const bool acc = metropolis_translation(u_a, dE * beta);          // u < exp(-dE/T), src/moves.cpp:170-172
-                sc.n_disp++; sc.evals += 2ull * (unsigned long long)n;
+                sc.n_disp++;
                 fwd.slot = -1;
                 if (acc) {
                     sc.acc_disp++;
@@ -220,8 +325,20 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                                    // reference's 0.5*dp, src/moves.cpp:178, is quirk Q16); n==0 moves a ghost (Q12)
                         e_pair += pn - po; e_wall += wn - wo;
                     }
+                    bool big = false;
+                    if (CACHE) {   // partners' entries follow the move; the moved particle's entry is the fresh sum
+                        big = cache_apply<FAST, PBZ>(xs, ys, zs, ep, n, i, g, true, xo, yo, zo, true, xn, yn, zn, tid, T);
+                        if ((i & tmask) == tid) ep[i] = v[1];
+                        sc.evals += 2ull * (unsigned long long)n;
+                    }
                     if ((i & tmask) == tid) { xs[i] = xn; ys[i] = yn; zs[i] = zn; }
                     fwd.slot = i; fwd.x = xn; fwd.y = yn; fwd.z = zn;
+                    if (CACHE && cta_sync_or<MULTI>(big)) {                        // entries visible before the next selection
+                        double cp, cw;                                             // a hard overlap went through the cache: rebuild it
+                        cache_fill<FAST, PBZ, MULTI>(xs, ys, zs, ep, n, P, g, partials, W, warp, lane, tid, T, cp, cw);
+                        e_pair = cp; e_wall = cw; fwd.slot = -1;
+                        sc.evals += (unsigned long long)n * (unsigned long long)n;
+                    }
                 }
                 code = acc ? 1 : 0;
                 if (SAMPLE) { sx = xo; sy = yo; sz = zo; s_po = po; s_wo = wo; mx = xn; my = yn; mz = zn; s_acc = acc; }
@@ -248,7 +365,21 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                     const bool acc = metropolis_insertion(u_a, -(e_in * beta), ln_zzV, zzV, n);   // src/moves.cpp:306-307
                     sc.n_ins++; sc.evals += (unsigned long long)n;
                     fwd.slot = -1;
-                    if (acc) { sc.acc_ins++; n++; e_pair += pi_; e_wall += wi; }
+                    if (acc) {
+                        bool big = false;
+                        if (CACHE) {
+                            big = cache_apply<FAST, PBZ>(xs, ys, zs, ep, n, -1, g, false, 0., 0., 0., true, xi, yi, zi, tid, T);
+                            if ((n & tmask) == tid) ep[n] = v[0];
+                            sc.evals += (unsigned long long)n;
+                        }
+                        sc.acc_ins++; n++; e_pair += pi_; e_wall += wi;
+                        if (CACHE && cta_sync_or<MULTI>(big)) {
+                            double cp, cw;
+                            cache_fill<FAST, PBZ, MULTI>(xs, ys, zs, ep, n, P, g, partials, W, warp, lane, tid, T, cp, cw);
+                            e_pair = cp; e_wall = cw; fwd.slot = -1;
+                            sc.evals += (unsigned long long)n * (unsigned long long)n;
+                        }
+                    }
                     code = (1 << 1) | (acc ? 1 : 0);
                 } else if (n > 0) {
                     const double u_o = rng.template at<3>(), u_a = rng.template at<4>();
@@ -258,21 +389,44 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                     load_slot(xs, ys, zs, o, fwd, xo, yo, zo);
                     load_slot(xs, ys, zs, n - 1, fwd, xl, yl, zl);                // the particle that would fill the hole
                     double v[1];
-                    v[0] = pair_sum1<FAST, PBZ>(xs, ys, zs, n, o, g, xo, yo, zo, tid, T);
                     double wo, wdummy;
-                    wall_two(P, zo, zo, wo, wdummy, lane);
-                    cta_allsum<1, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
+                    if (CACHE) {
+                        v[0] = ep[o];                                             // no partner scan at all
+                        wall_two(P, zo, zo, wo, wdummy, lane);
+                    } else {
+                        v[0] = pair_sum1<FAST, PBZ>(xs, ys, zs, n, o, g, xo, yo, zo, tid, T);
+                        wall_two(P, zo, zo, wo, wdummy, lane);
+                        cta_allsum<1, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
+                        fwd.slot = -1;
+                        sc.evals += (unsigned long long)n;
+                    }
                     const double po = eps4 * v[0];
                     const double e_out = po + wo;
                     const bool acc = metropolis_deletion(u_a, e_out * beta, ln_zzV, zzV, n);      // src/moves.cpp:326-327
-                    sc.n_del++; sc.evals += (unsigned long long)n;
-                    fwd.slot = -1;
+                    sc.n_del++;
                     if (acc) {
                         sc.acc_del++;
+                        bool big = false;
+                        if (CACHE) {   // the leaving particle drops out of every partner's sum; then the last entry fills the hole
+                            big = cache_apply<FAST, PBZ>(xs, ys, zs, ep, n, o, g, true, xo, yo, zo, false, 0., 0., 0., tid, T);
+                            sc.evals += (unsigned long long)n;
+                            big = cta_sync_or<MULTI>(big);
+                            if ((o & tmask) == tid) ep[o] = ep[n - 1];
+                            fwd.slot = -1;                                          // barrier passed: earlier slot writes are visible
+                        }
                         if ((o & tmask) == tid) { xs[o] = xl; ys[o] = yl; zs[o] = zl; }  // swap-with-last, src/moves.cpp:329
                         fwd.slot = o; fwd.x = xl; fwd.y = yl; fwd.z = zl;
                         n--;
                         e_pair -= po; e_wall -= wo;   // exact bookkeeping with the fresh energies (quirks Q3, Q16 fixed)
+                        if (CACHE) {
+                            cta_sync<MULTI>();                                      // the moved entry and slot are visible
+                            if (big) {
+                                double cp, cw;
+                                cache_fill<FAST, PBZ, MULTI>(xs, ys, zs, ep, n, P, g, partials, W, warp, lane, tid, T, cp, cw);
+                                e_pair = cp; e_wall = cw; fwd.slot = -1;
+                                sc.evals += (unsigned long long)n * (unsigned long long)n;
+                            }
+                        }
                     }
                     code = (2 << 1) | (acc ? 1 : 0);
                 } else {
@@ -359,7 +513,12 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
     __syncthreads();
 
     double c_pair = 0.0, c_wall = 0.0;
-    if (a.check_energy) cta_box_energy<FAST, PBZ>(xs, ys, zs, n, P, g, partials, W, warp, lane, tid, T, c_pair, c_wall);
+    if (a.check_energy) {
+        if (CACHE) cache_fill<FAST, PBZ, MULTI>(xs, ys, zs, ep, n, P, g, partials, W, warp, lane, tid, T, c_pair, c_wall);   // also refreshes the cache
+        else cta_box_energy<FAST, PBZ, MULTI>(xs, ys, zs, n, P, g, partials, W, warp, lane, tid, T, c_pair, c_wall);
+    }
+    unsigned long long end_sum = 0ull;
+    if (CACHE) end_sum = config_checksum<MULTI>(xs, ys, zs, n, (unsigned long long*)partials, tid, T, lane, warp, W);
 
     if (lead) {
         st.n = n; st.overflow = overflow; st.dr = dr; st.steps_done = step;
@@ -368,6 +527,8 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
         if (a.check_energy == 2) { st.pair = c_pair; st.wall = c_wall; st.energy = c_pair + c_wall; }   // adopt, like BoxEnergy does
         S.replay_pos = rng.cursor();
         st.replay_consumed = rng.cursor();
+        S.cache_valid = (CACHE && !overflow) ? 1 : 0;   // kernels that do not maintain the cache leave it stale
+        S.cache_sum = end_sum;
     }
 }
 
@@ -376,7 +537,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
 //                 N = 20 000) are advanced in place in global memory; their 24 B x N working set stays L2-resident
 //                 (480 KB at N = 20k vs 126 MB of L2).  Plain (coherent) loads: a slot written by its owner thread
 //                 is visible to the CTA after the step's __syncthreads.
-template <int RNG_MODE, int MAXT, int MINB, bool GLOBAL, bool FAST, bool SAMPLE>
+template <int RNG_MODE, int MAXT, int MINB, bool GLOBAL, bool FAST, bool SAMPLE, bool CACHE>
 __global__ void __launch_bounds__(MAXT, MINB) k2_chains(const ChainParams* __restrict__ params, ChainState* __restrict__ states,
                                                   const int* __restrict__ order, double* X, double* Y, double* Z, RunArgs a) {
     extern __shared__ double smem[];
@@ -405,7 +566,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k2_chains(const ChainParams* __res
     // FAST (all chains of the launch have their coordinates inside the box) is decided by the host per launch;
     // only the smallest CTA variant can run with a single warp, so MULTI is a compile-time fact elsewhere.
     const bool multi = (MAXT > 64) || T > 32, pbz = P.pbc[2] != 0;
-#define MCPM_GO(SRC, M, Z) chain_loop<SRC, FAST, M, Z, SAMPLE>(P, S, rng, xs, ys, zs, partials, a, trace, cap, (uint32_t)chain, hist)
+#define MCPM_GO(SRC, M, Z) chain_loop<SRC, FAST, M, Z, SAMPLE, CACHE>(P, S, rng, xs, ys, zs, partials, a, trace, cap, (uint32_t)chain, hist)
 #define MCPM_DISPATCH(SRC)                                                                           \
     do {                                                                                             \
         if (MAXT > 64 || multi) { if (pbz) MCPM_GO(SRC, true, true); else MCPM_GO(SRC, true, false); } \
@@ -761,46 +922,54 @@ static size_t k2_smem_bytes(int cap, bool multi, bool sample) { return (size_t)(
 size_t k2_smem_limit_cap(int max_smem_optin) { return ((size_t)max_smem_optin / sizeof(double) - 128 - 104 - 64) / 3; }
 
 template <int RNG_MODE>
-static cudaError_t launch_k2_rng(int n_chains, int threads, bool global, bool fast, bool sample, size_t smem, const ChainParams* params,
-                                 ChainState* states, const int* order, double* X, double* Y, double* Z, const RunArgs& a,
-                                 cudaStream_t stream) {
+static cudaError_t launch_k2_rng(int n_chains, int threads, bool global, bool fast, bool sample, bool cache, size_t smem,
+                                 const ChainParams* params, ChainState* states, const int* order, double* X, double* Y, double* Z,
+                                 const RunArgs& a, cudaStream_t stream) {
     auto go = [&](auto kern) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         kern<<<n_chains, threads, smem, stream>>>(params, states, order, X, Y, Z, a);
         return cudaSuccess;
     };
-    // The hot kernels (coordinates inside the box, no in-kernel sampling) exist for every CTA shape; register budgets
-    // by CTA size: <=64, <=256, <=512 threads -> 128 regs; 1024 -> 64.  (ptxas fits the 32-thread kernel into 96
-    // registers without spills, but measured on B200 that costs more ILP than the extra occupancy returns: C2
-    // 7.2e8 vs 7.7e8 moves/s.)
-    // The general kernels (general minimum image for coordinates outside the box and/or Widom + RDF sampling after
-    // every production step) exist for one shared-memory and one global-memory CTA shape;
-    // k2_threads_supported() clamps the thread count accordingly.
+    // template arguments: <rng, max threads, min CTAs/SM, GLOBAL, FAST, SAMPLE, CACHE>
+    // The hot kernels (shared-memory positions, coordinates inside the box, no in-kernel sampling) exist for CTAs of up
+    // to 64 / 256 / 512 threads (128 registers each; ptxas fits the 32-thread kernel into 96 registers without spills,
+    // but measured on B200 that costs more ILP than the extra occupancy returns: C2 7.2e8 vs 7.7e8 moves/s), each with
+    // and without the per-particle energy cache.  The general kernels (general minimum image for coordinates outside
+    // the box and/or Widom + RDF sampling after every production step) and the global-memory kernels exist for one CTA
+    // shape each; k2_threads_supported() clamps the thread count accordingly.
     if (!fast || sample) {
-        if (global) return fast ? go(k2_chains<RNG_MODE, 512, 1, true, true, true>) : go(k2_chains<RNG_MODE, 512, 1, true, false, true>);
-        return fast ? go(k2_chains<RNG_MODE, 256, 2, false, true, true>) : go(k2_chains<RNG_MODE, 256, 2, false, false, true>);
+        if (global) return fast ? go(k2_chains<RNG_MODE, 512, 1, true, true, true, false>) : go(k2_chains<RNG_MODE, 512, 1, true, false, true, false>);
+        return fast ? go(k2_chains<RNG_MODE, 256, 2, false, true, true, false>) : go(k2_chains<RNG_MODE, 256, 2, false, false, true, false>);
     }
-    if (global) return threads <= 512 ? go(k2_chains<RNG_MODE, 512, 1, true, true, false>) : go(k2_chains<RNG_MODE, 1024, 1, true, true, false>);
-    if (threads <= 64) return go(k2_chains<RNG_MODE, 64, 8, false, true, false>);
-    if (threads <= 256) return go(k2_chains<RNG_MODE, 256, 2, false, true, false>);
-    if (threads <= 512) return go(k2_chains<RNG_MODE, 512, 1, false, true, false>);
-    return go(k2_chains<RNG_MODE, 1024, 1, false, true, false>);
+    if (global) return go(k2_chains<RNG_MODE, 512, 1, true, true, false, false>);
+    if (cache) {
+        if (threads <= 64) return go(k2_chains<RNG_MODE, 64, 8, false, true, false, true>);
+        if (threads <= 256) return go(k2_chains<RNG_MODE, 256, 2, false, true, false, true>);
+        return go(k2_chains<RNG_MODE, 512, 1, false, true, false, true>);
+    }
+    if (threads <= 64) return go(k2_chains<RNG_MODE, 64, 8, false, true, false, false>);
+    if (threads <= 256) return go(k2_chains<RNG_MODE, 256, 2, false, true, false, false>);
+    return go(k2_chains<RNG_MODE, 512, 1, false, true, false, false>);
 }
 
 int k2_threads_supported(int threads, bool global, bool fast, bool sample) {
-    if (!fast || sample) return global ? std::min(threads, 512) : std::min(threads, 256);
-    return threads;
+    if ((!fast || sample) && !global) return std::min(threads, 256);
+    return std::min(threads, 512);
 }
 
-cudaError_t launch_k2(int rng_mode, int n_chains, int threads, bool fast, bool sample, const ChainParams* params, ChainState* states,
-                      const int* order, double* X, double* Y, double* Z, const RunArgs& a, int max_smem_optin, cudaStream_t stream) {
+bool k2_cache_supported(bool global, bool fast, bool sample) { return !global && fast && !sample; }
+
+cudaError_t launch_k2(int rng_mode, int n_chains, int threads, bool fast, bool sample, bool cache, const ChainParams* params,
+                      ChainState* states, const int* order, double* X, double* Y, double* Z, const RunArgs& a, int max_smem_optin,
+                      cudaStream_t stream) {
     const bool global = (size_t)a.cap > k2_smem_limit_cap(max_smem_optin);
     const bool multi = threads > 32 || !fast || sample;   // only the smallest hot kernel runs single-warp CTAs
     const size_t smem = k2_smem_bytes(global ? 0 : a.cap, multi, !fast || sample);
+    cache = cache && k2_cache_supported(global, fast, sample) && a.ep != nullptr;
     cudaError_t err = rng_mode == MCPM_RNG_PHILOX
-                          ? launch_k2_rng<MCPM_RNG_PHILOX>(n_chains, threads, global, fast, sample, smem, params, states, order, X, Y, Z, a, stream)
-                          : launch_k2_rng<MCPM_RNG_REPLAY>(n_chains, threads, global, fast, sample, smem, params, states, order, X, Y, Z, a, stream);
+                          ? launch_k2_rng<MCPM_RNG_PHILOX>(n_chains, threads, global, fast, sample, cache, smem, params, states, order, X, Y, Z, a, stream)
+                          : launch_k2_rng<MCPM_RNG_REPLAY>(n_chains, threads, global, fast, sample, cache, smem, params, states, order, X, Y, Z, a, stream);
     if (err != cudaSuccess) return err;
     return cudaGetLastError();
 }

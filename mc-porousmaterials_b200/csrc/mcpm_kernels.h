@@ -6,7 +6,7 @@
 
 namespace mcpm {
 
-cudaError_t launch_k2(int rng_mode, int n_chains, int threads, bool fast, bool sample, const ChainParams* params, ChainState* states, const int* order,
+cudaError_t launch_k2(int rng_mode, int n_chains, int threads, bool fast, bool sample, bool cache, const ChainParams* params, ChainState* states, const int* order,
                       double* X, double* Y, double* Z, const RunArgs& a, int max_smem_optin, cudaStream_t stream);
 size_t k2_smem_limit_cap(int max_smem_optin);
 int k2_threads_supported(int threads, bool global, bool fast, bool sample);

@@ -29,6 +29,9 @@ struct ChainState {
     int fast_image;                 // all positions lie in [0,L] on periodic axes
     int energy_valid;               // running box energies were initialised by a full K3 evaluation
     unsigned long long replay_pos;  // cursor into the replay stream (REPLAY mode)
+    unsigned long long cache_sum;   // checksum of the configuration the energy cache (RunArgs::ep) belongs to
+    int cache_valid;                // the cache was left consistent by the last K2 launch
+    int pad2;
 };
 
 struct RunArgs {
@@ -42,6 +45,7 @@ struct RunArgs {
     int check_energy;
     int cap;
     int sample_rdf;
+    double* ep;                  // device, [n_chains][cap]: per-particle pair sums (unscaled) of the energy cache, or null
     double* rdf;                 // device, [n_chains][MCPM_RDF_BINS] accumulated histograms
 };
 

@@ -22,9 +22,10 @@ def first_divergence(a, b):
     return int(d[0]) if len(d) else -1
 
 
+@pytest.mark.parametrize("cache", [True, False], ids=["cache", "nocache"])
 @pytest.mark.parametrize("threads", [32, 64, 128, 256, 512])
 @pytest.mark.parametrize("name", ["c1t", "lowt", "bulkt"])
-def test_replay_trace_matches_reference_golden(mcpm, golden, name, threads):
+def test_replay_trace_matches_reference_golden(mcpm, golden, name, threads, cache):
     arrays, meta = golden
     mkey, start = TRACE_CASES[name]
     m = meta[mkey]
@@ -33,6 +34,7 @@ def test_replay_trace_matches_reference_golden(mcpm, golden, name, threads):
     x, y, z = arrays[start + "_x"][:n0], arrays[start + "_y"][:n0], arrays[start + "_z"][:n0]
     u = O.mt_uniforms(m["seed"], 8 * sets * sps)
     with mcpm.Engine(1, 1024) as e:
+        e.use_energy_cache(cache)
         e.set_system(s)
         e.set_positions(0, x, y, z)
         per_set, traces = [], []
@@ -86,8 +88,9 @@ def test_device_philox_stream_is_the_documented_one(mcpm):
             assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("cache", [True, False], ids=["cache", "nocache"])
 @pytest.mark.parametrize("threads", [32, 128])
-def test_philox_chain_follows_oracle(mcpm, golden, threads):
+def test_philox_chain_follows_oracle(mcpm, golden, threads, cache):
     """Device Philox + Metropolis on the GPU == the C oracle fed with the same counter-based stream."""
     arrays, meta = golden
     s = system_from_meta(meta["c1"]["system"])
@@ -95,6 +98,7 @@ def test_philox_chain_follows_oracle(mcpm, golden, threads):
     x, y, z = arrays["c1_x"], arrays["c1_y"], arrays["c1_z"]
     seed, nchains, sets, sps = 987654321, 3, 2, 1500
     with mcpm.Engine(nchains, 1024) as e:
+        e.use_energy_cache(cache)
         e.set_system(s)
         for c in range(nchains):
             e.set_positions(c, x, y, z)
@@ -112,7 +116,10 @@ def test_philox_chain_follows_oracle(mcpm, golden, threads):
             assert st.n == ost["n"] and st.dr == ost["dr"]
             assert st.tot_disp == ost["tot_disp"] and st.tot_disp_acc == ost["tot_disp_acc"]
             assert st.tot_ins + st.tot_del == ost["tot_swap"]
-            assert st.pair_evals == ost["pair_evals"] - evals0
+            if not cache:      # with the energy cache fewer partner scans are needed (and the rebuild adds n*n)
+                assert st.pair_evals == ost["pair_evals"] - evals0
+            else:
+                assert st.pair_evals < ost["pair_evals"] - evals0 + len(x) ** 2
             assert st.samples == ost["samples"] == sps
             assert st.sum_n == ost["sum_n"] and st.sum_n2 == ost["sum_n2"]
             assert st.sum_e == pytest.approx(ost["sum_e"], rel=RTOL)
@@ -292,3 +299,63 @@ def test_results_do_not_depend_on_threads_per_chain(mcpm, golden):
         for a, b in zip(pos, ref[1]):
             for u, v in zip(a, b):
                 assert np.array_equal(u, v), f"threads={threads}"
+
+
+def test_energy_cache_survives_launches_and_uploads(mcpm, golden):
+    """The per-particle energy cache is kept across launches (checksum of the configuration), is rebuilt after the host
+    changes a configuration, and never changes the chain: split and unsplit runs, with and without re-uploading the
+    positions in between, give bit-identical results."""
+    arrays, meta = golden
+    s = system_from_meta(meta["c1"]["system"])
+    x, y, z = arrays["c1_x"], arrays["c1_y"], arrays["c1_z"]
+    results = []
+    for mode in ("one", "split", "reupload", "nocache"):
+        with mcpm.Engine(2, 1024) as e:
+            e.use_energy_cache(mode != "nocache")
+            e.set_system(s)
+            for c in range(2):
+                e.set_positions(c, x, y, z)
+            if mode in ("one", "nocache"):
+                st = e.run(50, 1, 6000, seed=77, threads=32, check_energy=1)
+            else:
+                e.run(50, 1, 2500, seed=77, threads=32)
+                if mode == "reupload":
+                    n, X, Y, Z = e.get_positions_all()
+                    st0 = e.stats()
+                    e.set_positions_all(n, X, Y, Z)                    # unchanged configuration: the cache is reused
+                    e.set_running_energy([q.pair for q in st0], [q.wall for q in st0])
+                e.run(50, 1, 3500, seed=77, threads=32)
+                st = e.run(50, 1, 0, seed=77, threads=32, check_energy=1)
+            results.append(([(q.n, q.tot_disp_acc, q.tot_ins_acc, q.tot_del_acc) for q in st], [e.get_positions(c) for c in range(2)],
+                            [(q.energy, q.energy_check) for q in st]))
+    for sig, pos, en in results[1:]:
+        assert sig == results[0][0]
+        for a, b in zip(pos, results[0][1]):
+            for u, v in zip(a, b):
+                assert np.array_equal(u, v)
+    for sig, pos, en in results:
+        for running, check in en:
+            assert running == pytest.approx(check, rel=RTOL)
+
+
+def test_energy_cache_with_hard_overlaps(mcpm):
+    """Random start (energies ~1e20 K): accepted moves push huge terms through the cache, which must be rebuilt on the
+    spot; the chain stays identical to the cache-free one and the running energy stays exact after relaxation."""
+    s = O.argon_slit(mu=-1300.0, rcut=12.0, n_equil_sets=0)
+    rng = np.random.default_rng(8)
+    n0 = 150
+    x, y, z = rng.random(n0) * 24, rng.random(n0) * 24, rng.random(n0) * 20
+    out = []
+    for cache in (True, False):
+        with mcpm.Engine(1, 512) as e:
+            e.use_energy_cache(cache)
+            e.set_system(s)
+            e.set_positions(0, x, y, z)
+            st, tr = e.run(1, 1, 20000, seed=5, threads=64, trace=True, check_energy=2)
+            st2 = e.run(2, 1, 5000, seed=5, threads=64, check_energy=1)
+            out.append((tr[0].copy(), e.get_positions(0), st2[0].energy, st2[0].energy_check))
+    assert first_divergence(out[0][0], out[1][0]) == -1
+    for a, b in zip(out[0][1], out[1][1]):
+        assert np.array_equal(a, b)
+    for _, _, running, check in out:
+        assert running == pytest.approx(check, rel=1e-9)
