@@ -55,7 +55,7 @@ def build_workload(config, replicas, steps_per_set):
         if config == "c1":
             pts = pts[-1:]                       # mu = -1134 K
             w["workload"] = "C1 Ar in graphite slit, single mu=-1134 K (H=20A, rcut=20A, T=87K, N~560, disp:swap=1:1)"
-            w["replicas"] = replicas or 2048
+            w["replicas"] = replicas or 1920
         else:
             w["workload"] = "C2 40-point Ar isotherm (mu_k=-1800+k*666/39 K, H=20A, rcut=20A, T=87K, disp:swap=1:1)"
             w["replicas"] = replicas or 128
@@ -280,8 +280,8 @@ def gpu_arm(args, world, rank, local, dist):
     barrier(dist, local)
     if rank == 0:
         sampler.start()
-    dev_ms, kern_ms, evals = [], [], []
-    prev_evals = 0
+    dev_ms, kern_ms, evals, evals_x = [], [], [], []
+    prev_evals = prev_x = 0
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         flush.zero_()                       # L2 flush between timed iterations (256 MiB write > 126 MB L2)
@@ -290,8 +290,9 @@ def gpu_arm(args, world, rank, local, dist):
         st = one_step(set_index); set_index += 1
         dev_ms.append(eng.timer_stop())
         kern_ms.append(eng.last_kernel_ms())
-        tot = sum(int(s.pair_evals) for s in st)
+        tot = sum(int(s.pair_evals_algorithmic) for s in st); totx = sum(int(s.pair_evals) for s in st)
         evals.append(tot - prev_evals); prev_evals = tot
+        evals_x.append(totx - prev_x); prev_x = totx
     barrier(dist, local)
     t_wall = time.perf_counter() - t_wall0
     launches = eng.launch_count() - launches0
@@ -299,6 +300,7 @@ def gpu_arm(args, world, rank, local, dist):
     moves_per_rank = float(n_chains) * S * args.steps
     value = world * moves_per_rank / t_dev
     evals_all = allsum(dist, local, float(sum(evals)))
+    evals_x_all = allsum(dist, local, float(sum(evals_x)))
     stats = eng.stats()
     mean_n = float(np.mean([s.sum_n / max(s.samples, 1) for s in stats])) if stats[0].samples else float(np.mean([s.n for s in stats]))
 
@@ -343,7 +345,9 @@ def gpu_arm(args, world, rank, local, dist):
             traffic = None
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
                 "traffic": traffic, "kernel": "k2_chains", "kernel_ms": k_ms,
-                "algorithmic": f"{w['flop_per_pair']} flop x {evals_per_launch:.4g} pair evals per launch",
+                "algorithmic": f"{w['flop_per_pair']} flop x {evals_per_launch:.4g} pair evaluations per launch = what the reference's moves evaluate for "
+                               f"the same steps (2N per translation, N per insertion/deletion, SURVEY.md 8d); the engine executed "
+                               f"{float(np.mean(evals_x)):.4g} of them (per-particle energy cache)",
                 "peak_source": "mcpm_fp64_peak DFMA microbenchmark, measured live (MEASURED_PEAKS.json has no fp64 figure)",
                 "pair_evals_per_s": evals_per_launch / (k_ms * 1e-3),
                 "smem_bytes_per_s": BYTES_PER_PAIR * evals_per_launch / (k_ms * 1e-3)}
@@ -356,7 +360,7 @@ def gpu_arm(args, world, rank, local, dist):
                    "capacity": cap, "mean_particles": mean_n, "threads_per_chain": args.threads or "auto",
                    "start": w["start"], "rng": "device Philox4x32-10",
                    "l2": "256 MiB device write between timed steps (L2 flush)"},
-        "pair_evals_per_s": evals_all / t_dev,
+        "pair_evals_per_s": evals_all / t_dev, "pair_evals_executed_per_s": evals_x_all / t_dev,
         "wall_s_timed_region": t_wall,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),

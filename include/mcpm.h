@@ -103,7 +103,9 @@ typedef struct mcpm_chain_stats {
     long long acceptance, rejection, n_displacements;
     long long accept_swap, reject_swap, n_swaps;
     long long tot_disp, tot_disp_acc, tot_ins, tot_ins_acc, tot_del, tot_del_acc, tot_empty;
-    unsigned long long pair_evals;  /* iterations of the partner loop src/potentials.cpp:65-71 */
+    unsigned long long pair_evals;  /* partner-loop iterations (src/potentials.cpp:65-71) the engine EXECUTED, cache rebuilds included */
+    unsigned long long pair_evals_algorithmic; /* what the reference's moves evaluate for the same steps: 2N per translation,
+                                                  N per insertion / deletion / Widom step (src/moves.cpp:153,165,304,324,421,429) */
     unsigned long long steps_done;  /* chain's global step counter (= Philox step index) */
     /* production accumulators (set > n_equil_sets), one sample per step */
     double sum_n, sum_n2, sum_e, sum_e2;

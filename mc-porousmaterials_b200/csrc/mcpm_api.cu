@@ -583,7 +583,7 @@ int mcpm_reset_accumulators(mcpm_ctx* c) {
         mcpm_chain_stats& st = c->h_state[k].st;
         st.sum_n = st.sum_n2 = st.sum_e = st.sum_e2 = 0.0; st.samples = 0;
         st.tot_disp = st.tot_disp_acc = st.tot_ins = st.tot_ins_acc = st.tot_del = st.tot_del_acc = st.tot_empty = 0;
-        st.pair_evals = 0;
+        st.pair_evals = 0; st.pair_evals_algorithmic = 0;
     }
     CU(cudaMemcpyAsync(c->d_state, c->h_state.data(), sizeof(ChainState) * c->n_chains, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemsetAsync(c->d_rdf, 0, sizeof(double) * MCPM_RDF_BINS * (size_t)c->n_chains, c->stream));

@@ -230,8 +230,9 @@ __device__ unsigned long long config_checksum(const double* xs, const double* ys
 // by thread 0 at the end of every set.
 struct SetCounters {
     int n_disp, acc_disp, n_ins, acc_ins, n_del, acc_del, n_empty;
-    unsigned long long evals;
-    __device__ __forceinline__ void reset() { n_disp = acc_disp = n_ins = acc_ins = n_del = acc_del = n_empty = 0; evals = 0ull; }
+    unsigned long long evals;   // executed partner-loop iterations
+    unsigned long long alg;     // what the reference evaluates: 2n per translation, n per swap
+    __device__ __forceinline__ void reset() { n_disp = acc_disp = n_ins = acc_ins = n_del = acc_del = n_empty = 0; evals = 0ull; alg = 0ull; }
 };
 
 // n, dr, the running energies, the per-set counters and the decision itself are REPLICATED in every
@@ -317,7 +318,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                 const double po = eps4 * v[0], pn = eps4 * v[1];
                 const double dE = (pn + wn) - (po + wo);                          // newEnergy - oldEnergy, src/moves.cpp:169
                 const bool acc = metropolis_translation(u_a, dE * beta);          // u < exp(-dE/T), src/moves.cpp:170-172
-                sc.n_disp++;
+                sc.n_disp++; sc.alg += 2ull * (unsigned long long)n;
                 fwd.slot = -1;
                 if (acc) {
                     sc.acc_disp++;
@@ -363,7 +364,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                     const double pi_ = eps4 * v[0];
                     const double e_in = pi_ + wi;
                     const bool acc = metropolis_insertion(u_a, -(e_in * beta), ln_zzV, zzV, n);   // src/moves.cpp:306-307
-                    sc.n_ins++; sc.evals += (unsigned long long)n;
+                    sc.n_ins++; sc.evals += (unsigned long long)n; sc.alg += (unsigned long long)n;
                     fwd.slot = -1;
                     if (acc) {
                         bool big = false;
@@ -403,7 +404,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                     const double po = eps4 * v[0];
                     const double e_out = po + wo;
                     const bool acc = metropolis_deletion(u_a, e_out * beta, ln_zzV, zzV, n);      // src/moves.cpp:326-327
-                    sc.n_del++;
+                    sc.n_del++; sc.alg += (unsigned long long)n;
                     if (acc) {
                         sc.acc_del++;
                         bool big = false;
@@ -449,7 +450,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                     cta_allsum<1, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
                     fwd.slot = -1;
                     energy = eps4 * v[0] + wg;
-                    if (lead) { st.widom_insertions++; st.widom_insert += bar_weight(energy, beta) * exp(-0.5 * energy * beta); st.pair_evals += (unsigned long long)n; }
+                    if (lead) { st.widom_insertions++; st.widom_insert += bar_weight(energy, beta) * exp(-0.5 * energy * beta); st.pair_evals += (unsigned long long)n; st.pair_evals_algorithmic += (unsigned long long)n; }
                 } else {                                                         // virtual deletion
                     const int slot1 = (int)(rng.template extra<2>() * (double)n);   // 1-based slot in [0, n-1]: 0 is the scratch slot (Q14)
                     rng.end_step(3);
@@ -474,6 +475,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                         if (lead) st.pair_evals += (unsigned long long)n;
                     }
                     if (lead) {
+                        st.pair_evals_algorithmic += (unsigned long long)n;
                         st.widom_deletions++;
                         const double bw = bar_weight(energy, beta);
                         if (exp(0.5 * energy * beta) < 1) st.widom_delete += bw * exp(0.5 * energy * beta);
@@ -507,7 +509,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
             st.accept_swap = sc.acc_ins + sc.acc_del; st.reject_swap = (sc.n_ins + sc.n_del) - (sc.acc_ins + sc.acc_del);
             st.n_swaps = 1 + sc.n_ins + sc.n_del;
             st.tot_disp += sc.n_disp; st.tot_disp_acc += sc.acc_disp; st.tot_ins += sc.n_ins; st.tot_ins_acc += sc.acc_ins;
-            st.tot_del += sc.n_del; st.tot_del_acc += sc.acc_del; st.tot_empty += sc.n_empty; st.pair_evals += sc.evals;
+            st.tot_del += sc.n_del; st.tot_del_acc += sc.acc_del; st.tot_empty += sc.n_empty; st.pair_evals += sc.evals; st.pair_evals_algorithmic += sc.alg;
         }
     }
     __syncthreads();

@@ -69,7 +69,7 @@ class ChainStats(C.Structure):
         ("tot_disp", C.c_longlong), ("tot_disp_acc", C.c_longlong), ("tot_ins", C.c_longlong),
         ("tot_ins_acc", C.c_longlong), ("tot_del", C.c_longlong), ("tot_del_acc", C.c_longlong),
         ("tot_empty", C.c_longlong),
-        ("pair_evals", C.c_ulonglong), ("steps_done", C.c_ulonglong),
+        ("pair_evals", C.c_ulonglong), ("pair_evals_algorithmic", C.c_ulonglong), ("steps_done", C.c_ulonglong),
         ("sum_n", C.c_double), ("sum_n2", C.c_double), ("sum_e", C.c_double), ("sum_e2", C.c_double),
         ("samples", C.c_longlong), ("replay_consumed", C.c_ulonglong),
         ("widom_insert", C.c_double), ("widom_delete", C.c_double),

@@ -116,6 +116,7 @@ def test_philox_chain_follows_oracle(mcpm, golden, threads, cache):
             assert st.n == ost["n"] and st.dr == ost["dr"]
             assert st.tot_disp == ost["tot_disp"] and st.tot_disp_acc == ost["tot_disp_acc"]
             assert st.tot_ins + st.tot_del == ost["tot_swap"]
+            assert st.pair_evals_algorithmic == ost["pair_evals"] - evals0    # what the reference's moves evaluate
             if not cache:      # with the energy cache fewer partner scans are needed (and the rebuild adds n*n)
                 assert st.pair_evals == ost["pair_evals"] - evals0
             else:
