@@ -52,6 +52,8 @@ struct mcpm_ctx {
     double *d_sx = nullptr, *d_sy = nullptr, *d_sz = nullptr;
     int use_cells = 1;             // 0 disables the cell-list path (tests compare both)
     int use_cache = 1;             // per-particle energy cache in K2 (mcpm_use_energy_cache)
+    int use_subwarp = 1;           // pack 2 or 4 small chains into one warp (mcpm_use_subwarp)
+    int2* d_ctas = nullptr;        // CTA descriptors of the sub-warp kernel, n_chains entries
     double* d_ep = nullptr;        // [n_chains][cap], allocated on first use
     double* d_replay = nullptr; size_t replay_doubles = 0;
     unsigned char* d_trace = nullptr; size_t trace_bytes = 0;
@@ -198,7 +200,7 @@ int mcpm_destroy(mcpm_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_params); cudaFree(c->d_state); cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_z);
     cudaFree(c->d_order); cudaFree(c->d_scratch); cudaFree(c->d_counters); cudaFree(c->d_out);
-    cudaFree(c->d_pp); cudaFree(c->d_pw); cudaFree(c->d_rdf); cudaFree(c->d_ep);
+    cudaFree(c->d_pp); cudaFree(c->d_pw); cudaFree(c->d_rdf); cudaFree(c->d_ep); cudaFree(c->d_ctas);
     cudaFree(c->d_cell_of); cudaFree(c->d_cell_counts); cudaFree(c->d_cell_starts); cudaFree(c->d_orig);
     cudaFree(c->d_sx); cudaFree(c->d_sy); cudaFree(c->d_sz); cudaFree(c->d_replay); cudaFree(c->d_trace);
     if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -554,10 +556,52 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
         CU(cudaMemsetAsync(c->d_trace, 0xff, std::max<size_t>(need, 1), c->stream));
         a.trace = c->d_trace; a.trace_stride = nsteps;
     }
+    // The sub-warp kernel (mcpm_subwarp.cu) takes over whenever one warp per chain was chosen: it needs the energy cache,
+    // coordinates inside the box, shared-memory positions, no in-kernel sampling and one geometry for the whole launch.
+    bool same_pbz = true;
+    for (int k = 1; k < c->n_chains; k++) same_pbz = same_pbz && c->h_params[k].pbc[2] == c->h_params[0].pbc[2];
+    const bool use_sub = threads == 32 && c->use_cache && all_fast && !sample && !global_path && same_pbz;
     CU(cudaEventRecord(c->ev0, c->stream));
-    CU(launch_k2(p->rng_mode, c->n_chains, threads, all_fast, sample, c->use_cache != 0, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->max_smem, c->stream));
+    if (use_sub) {
+        const int cap_cta = ((c->cap + 127) / 128) * 128;
+        if (!c->d_ctas) CU(cudaMalloc(&c->d_ctas, sizeof(int2) * c->n_chains));
+        auto chains_per_warp = [&](int n) {   // room for the fluctuations of N during the launch; outgrowing the slot pauses the chain
+            if (!c->use_subwarp) return 1;
+            const int need = n + std::max(32, n / 4) + 1;
+            return need <= cap_cta / 4 ? 4 : (need <= cap_cta / 2 ? 2 : 1);
+        };
+        std::vector<int2> ctas;
+        for (int i = 0; i < c->n_chains;) {     // `order` is sorted by loading: equal classes are contiguous
+            const int k = chains_per_warp(c->h_state[order[i]].st.n);
+            int cnt = 1;
+            while (cnt < k && i + cnt < c->n_chains && chains_per_warp(c->h_state[order[i + cnt]].st.n) == k) cnt++;
+            ctas.push_back(make_int2(i, k | (cnt << 8)));
+            i += cnt;
+        }
+        for (int k = 0; k < c->n_chains; k++) c->h_state[k].res.paused = 0;
+        CU(cudaMemcpyAsync(c->d_state, c->h_state.data(), sizeof(ChainState) * c->n_chains, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->d_ctas, ctas.data(), sizeof(int2) * ctas.size(), cudaMemcpyHostToDevice, c->stream));
+        CU(launch_k2_sub(p->rng_mode, c->h_params[0].pbc[2] != 0, (int)ctas.size(), c->d_params, c->d_state, c->d_order, c->d_ctas, c->d_x,
+                         c->d_y, c->d_z, a, cap_cta, c->stream));
+        c->launches++;
+        for (int round = 0; round < 4; round++) {   // chains that outgrew their slot continue alone in a warp with the full capacity
+            int rc1 = pull_states(c); if (rc1) return rc1;
+            std::vector<int> again;
+            for (int k = 0; k < c->n_chains; k++) if (c->h_state[k].res.paused) again.push_back(k);
+            if (again.empty()) break;
+            std::vector<int2> solo;
+            for (size_t i = 0; i < again.size(); i++) solo.push_back(make_int2((int)i, 1 | (1 << 8)));
+            CU(cudaMemcpyAsync(c->d_order, again.data(), sizeof(int) * again.size(), cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(c->d_ctas, solo.data(), sizeof(int2) * solo.size(), cudaMemcpyHostToDevice, c->stream));
+            CU(launch_k2_sub(p->rng_mode, c->h_params[0].pbc[2] != 0, (int)solo.size(), c->d_params, c->d_state, c->d_order, c->d_ctas, c->d_x,
+                             c->d_y, c->d_z, a, cap_cta, c->stream));
+            c->launches++;
+        }
+    } else {
+        CU(launch_k2(p->rng_mode, c->n_chains, threads, all_fast, sample, c->use_cache != 0, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->max_smem, c->stream));
+        c->launches++;
+    }
     CU(cudaEventRecord(c->ev1, c->stream));
-    c->launches++;
     if (p->trace) CU(cudaMemcpyAsync(p->trace, c->d_trace, (size_t)c->n_chains * nsteps, cudaMemcpyDeviceToHost, c->stream));
     int rc = pull_states(c); if (rc) return rc;
     CU(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
@@ -628,6 +672,12 @@ int mcpm_set_running_energy(mcpm_ctx* c, const double* pair, const double* wall)
     }
     CU(cudaMemcpyAsync(c->d_state, c->h_state.data(), sizeof(ChainState) * c->n_chains, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return MCPM_OK;
+}
+
+int mcpm_use_subwarp(mcpm_ctx* c, int enable) {
+    if (!c) return fail(MCPM_ERR_ARG, "null context");
+    c->use_subwarp = enable ? 1 : 0;
     return MCPM_OK;
 }
 

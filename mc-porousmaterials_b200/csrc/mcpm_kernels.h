@@ -19,6 +19,10 @@ cudaError_t launch_k3(int tiles, int n_chains, int chain0, const ChainParams* pa
                       const double* Z, int cap, double* per_pair, double* per_wall, double* scratch, unsigned int* counters, double* out,
                       cudaStream_t stream);
 
+size_t k2_sub_smem_bytes(int cap_cta);
+cudaError_t launch_k2_sub(int rng_mode, bool pbz, int n_ctas, const ChainParams* params, ChainState* states, const int* order, const int2* ctas,
+                          double* X, double* Y, double* Z, const RunArgs& a, int cap_cta, cudaStream_t stream);
+
 size_t k3c_cells_per_chain();
 cudaError_t launch_k3_cells(int maxn, int n_chains, int chain0, const ChainParams* params, ChainState* states, const double* X,
                             const double* Y, const double* Z, int cap, int* cell_of, int* counts, int* starts, double* sx, double* sy,

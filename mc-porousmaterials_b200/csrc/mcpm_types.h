@@ -23,6 +23,13 @@ struct ChainParams {
     int n_disp, n_vol, n_swap, n_equil;
 };
 
+// Where a chain that outgrew its sub-warp slot (mcpm_subwarp.cu) stopped, and the counters of the interrupted set.
+struct ChainResume {
+    int paused, set, step;
+    int n_disp, acc_disp, n_ins, acc_ins, n_del, acc_del, n_empty;
+    unsigned long long evals, alg;
+};
+
 // Mutable chain state; `st` is exactly what mcpm_run reports.
 struct ChainState {
     mcpm_chain_stats st;
@@ -32,6 +39,7 @@ struct ChainState {
     unsigned long long cache_sum;   // checksum of the configuration the energy cache (RunArgs::ep) belongs to
     int cache_valid;                // the cache was left consistent by the last K2 launch
     int pad2;
+    ChainResume res;
 };
 
 struct RunArgs {

@@ -111,6 +111,9 @@ class Engine:
         check(self.L.mcpm_box_energy_all(self.h, arr))
         return np.array([[e.pair, e.many_body, e.wall, e.energy] for e in arr])
 
+    def use_subwarp(self, enable=True):
+        check(self.L.mcpm_use_subwarp(self.h, 1 if enable else 0))
+
     def use_energy_cache(self, enable=True):
         check(self.L.mcpm_use_energy_cache(self.h, 1 if enable else 0))
 

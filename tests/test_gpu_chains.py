@@ -360,3 +360,70 @@ def test_energy_cache_with_hard_overlaps(mcpm):
         assert np.array_equal(a, b)
     for _, _, running, check in out:
         assert running == pytest.approx(check, rel=1e-9)
+
+
+@pytest.mark.parametrize("packed", [True, False], ids=["subwarp", "onewarp"])
+def test_subwarp_packing_mixed_loadings(mcpm, golden, packed):
+    """The throughput kernel packs 4 / 2 / 1 chains per warp by loading.  12 chains of very different size (3 ... 504
+    particles, different mu) against the C oracle fed with the same Philox streams: identical traces and configurations."""
+    arrays, meta = golden
+    base = meta["c1"]["system"]
+    x, y, z = arrays["c1_x"], arrays["c1_y"], arrays["c1_z"]
+    sizes = [504, 3, 40, 150, 10, 260, 90, 504, 33, 200, 5, 120]
+    mus = [-1134.0, -1900.0, -1700.0, -1500.0, -1800.0, -1350.0, -1600.0, -1134.0, -1750.0, -1400.0, -1850.0, -1550.0]
+    seed, sets, sps = 31337, 2, 1500
+    with mcpm.Engine(len(sizes), 704) as e:
+        e.use_subwarp(packed)
+        systems = []
+        for c, (n0, mu) in enumerate(zip(sizes, mus)):
+            d = dict(base); d["mu"] = mu; d["n_equil_sets"] = 1
+            s = system_from_meta(d)
+            systems.append(s)
+            e.set_system(s, c)
+            e.set_positions(c, x[:n0], y[:n0], z[:n0])
+        stats, tr = e.run(1, sets, sps, seed=seed, trace=True, threads=32, check_energy=1)
+        for c, (n0, s) in enumerate(zip(sizes, systems)):
+            o = O.COracle(s, 1024)
+            o.set_positions(x[:n0], y[:n0], z[:n0])
+            o.box_energy()
+            o.philox(seed, c, 0)
+            otr = o.run_sets(1, sets, sps, 0, True)
+            div = first_divergence(tr[c], otr)
+            assert div == -1, f"chain {c} (n0={n0}): first divergence at step {div}"
+            st, ost = stats[c], o.state()
+            assert st.n == ost["n"] and st.dr == ost["dr"]
+            assert (st.acceptance, st.rejection, st.n_displacements, st.accept_swap, st.reject_swap, st.n_swaps) == \
+                (ost["acceptance"], ost["rejection"], ost["n_displacements"], ost["accept_swap"], ost["reject_swap"], ost["n_swaps"])
+            assert st.samples == ost["samples"] and st.sum_n == ost["sum_n"]
+            assert st.sum_e == pytest.approx(ost["sum_e"], rel=RTOL)
+            assert st.energy == pytest.approx(st.energy_check, rel=RTOL, abs=1e-9)
+            gx, gy, gz = e.get_positions(c)
+            ox, oy, oz = o.get_positions()
+            assert np.array_equal(gx, ox) and np.array_equal(gy, oy) and np.array_equal(gz, oz)
+
+
+def test_subwarp_chain_outgrows_its_slot(mcpm, golden):
+    """A chain that starts small (packed 4 per warp) and fills up during the launch is paused when its slot is full and
+    finishes the call alone in a warp; the result is the chain the oracle produces."""
+    arrays, meta = golden
+    d = dict(meta["c1"]["system"]); d["n_equil_sets"] = 0          # mu = -1134 K: N grows towards ~550
+    s = system_from_meta(d)
+    x, y, z = arrays["c1_x"][:20], arrays["c1_y"][:20], arrays["c1_z"][:20]
+    seed, sps = 99, 60000
+    with mcpm.Engine(8, 704) as e:
+        e.set_system(s)
+        for c in range(8):
+            e.set_positions(c, x, y, z)
+        stats, tr = e.run(1, 1, sps, seed=seed, trace=True, threads=32, check_energy=1)
+        launches = e.launch_count()
+        o = O.COracle(s, 1024)
+        o.set_positions(x, y, z); o.box_energy(); o.philox(seed, 5, 0)
+        otr = o.run_sets(1, 1, sps, 0, True)
+        assert first_divergence(tr[5], otr) == -1
+        assert stats[5].n == o.state()["n"] > 176                  # it did outgrow the 4-per-warp slot (704/4 = 176)
+        assert stats[5].samples == sps and stats[5].sum_n == o.state()["sum_n"]
+        assert stats[5].steps_done == sps
+        gx, gy, gz = e.get_positions(5)
+        ox, oy, oz = o.get_positions()
+        assert np.array_equal(gx, ox) and np.array_equal(gy, oy) and np.array_equal(gz, oz)
+        assert launches >= 3                                        # K3 initialisation is 2 launches, then >= 2 K2 launches
