@@ -174,10 +174,12 @@ int mcpm_get_stats(mcpm_ctx* ctx, mcpm_chain_stats* stats /* [n_chains] */);
  * 1.5 N pair evaluations per step at 20 % translation acceptance.  enable = 0 re-sums both energies every move, exactly
  * like MC::MoveParticle / MC::SwapParticle. */
 int mcpm_use_energy_cache(mcpm_ctx* ctx, int enable);
-/* With one warp per chain (threads_per_chain 32, chosen automatically for many chains) K2 packs 2 or 4 small chains
- * into one warp (16 or 8 lanes each), so that the per-step work that does not scale with N is shared (default on).
- * Chains that outgrow their slot during a launch finish the call in a warp of their own.  Same chain, same results up
- * to the order of floating-point additions.  enable = 0 keeps one chain per warp. */
+/* EXPERIMENTAL, default off.  With one warp per chain (threads_per_chain 32) an alternative K2 kernel packs 2 or 4 small
+ * chains into one warp (16 or 8 lanes each) and runs translation / insertion / deletion as one branch-free code path,
+ * so that the per-step work that does not scale with N is shared by the chains of a warp.  Chains that outgrow their
+ * slot during a launch finish the call in a warp of their own.  Same chain and results (tested against the same golden
+ * traces); measured on B200 it is 1.7-2x SLOWER than the default kernel in round 1 (more instructions per step and
+ * longer dependent chains outweigh the sharing), see DESIGN.md. */
 int mcpm_use_subwarp(mcpm_ctx* ctx, int enable);
 int mcpm_reset_accumulators(mcpm_ctx* ctx);
 /* Accumulated pair-distance histogram of one chain: hist[0..99] = MC::Stats::rdf(0..99) (bin 0 is never filled,

@@ -52,7 +52,7 @@ struct mcpm_ctx {
     double *d_sx = nullptr, *d_sy = nullptr, *d_sz = nullptr;
     int use_cells = 1;             // 0 disables the cell-list path (tests compare both)
     int use_cache = 1;             // per-particle energy cache in K2 (mcpm_use_energy_cache)
-    int use_subwarp = 1;           // pack 2 or 4 small chains into one warp (mcpm_use_subwarp)
+    int use_subwarp = 0;           // opt-in: the sub-warp kernel that packs 2 or 4 small chains into one warp (mcpm_use_subwarp)
     int2* d_ctas = nullptr;        // CTA descriptors of the sub-warp kernel, n_chains entries
     double* d_ep = nullptr;        // [n_chains][cap], allocated on first use
     double* d_replay = nullptr; size_t replay_doubles = 0;
@@ -560,13 +560,12 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     // coordinates inside the box, shared-memory positions, no in-kernel sampling and one geometry for the whole launch.
     bool same_pbz = true;
     for (int k = 1; k < c->n_chains; k++) same_pbz = same_pbz && c->h_params[k].pbc[2] == c->h_params[0].pbc[2];
-    const bool use_sub = threads == 32 && c->use_cache && all_fast && !sample && !global_path && same_pbz;
+    const bool use_sub = c->use_subwarp && threads == 32 && c->use_cache && all_fast && !sample && !global_path && same_pbz;
     CU(cudaEventRecord(c->ev0, c->stream));
     if (use_sub) {
         const int cap_cta = ((c->cap + 127) / 128) * 128;
         if (!c->d_ctas) CU(cudaMalloc(&c->d_ctas, sizeof(int2) * c->n_chains));
         auto chains_per_warp = [&](int n) {   // room for the fluctuations of N during the launch; outgrowing the slot pauses the chain
-            if (!c->use_subwarp) return 1;
             const int need = n + std::max(32, n / 4) + 1;
             return need <= cap_cta / 4 ? 4 : (need <= cap_cta / 2 ? 2 : 1);
         };

@@ -22,10 +22,12 @@ def first_divergence(a, b):
     return int(d[0]) if len(d) else -1
 
 
-@pytest.mark.parametrize("cache", [True, False], ids=["cache", "nocache"])
+@pytest.mark.parametrize("cache", [True, False, "subwarp"], ids=["cache", "nocache", "subwarp"])
 @pytest.mark.parametrize("threads", [32, 64, 128, 256, 512])
 @pytest.mark.parametrize("name", ["c1t", "lowt", "bulkt"])
 def test_replay_trace_matches_reference_golden(mcpm, golden, name, threads, cache):
+    if cache == "subwarp" and threads != 32:
+        pytest.skip("the sub-warp kernel runs one warp per chain")
     arrays, meta = golden
     mkey, start = TRACE_CASES[name]
     m = meta[mkey]
@@ -34,7 +36,8 @@ def test_replay_trace_matches_reference_golden(mcpm, golden, name, threads, cach
     x, y, z = arrays[start + "_x"][:n0], arrays[start + "_y"][:n0], arrays[start + "_z"][:n0]
     u = O.mt_uniforms(m["seed"], 8 * sets * sps)
     with mcpm.Engine(1, 1024) as e:
-        e.use_energy_cache(cache)
+        e.use_energy_cache(bool(cache))
+        e.use_subwarp(cache == "subwarp")
         e.set_system(s)
         e.set_positions(0, x, y, z)
         per_set, traces = [], []
@@ -411,6 +414,7 @@ def test_subwarp_chain_outgrows_its_slot(mcpm, golden):
     x, y, z = arrays["c1_x"][:20], arrays["c1_y"][:20], arrays["c1_z"][:20]
     seed, sps = 99, 60000
     with mcpm.Engine(8, 704) as e:
+        e.use_subwarp(True)
         e.set_system(s)
         for c in range(8):
             e.set_positions(c, x, y, z)
