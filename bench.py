@@ -308,7 +308,8 @@ def gpu_arm(args, world, rank, local, dist):
     nbuf = np.zeros(n_chains, dtype=np.int32)
     n_host, _, _, _ = eng.get_positions_all(X, Y, Z)
     nbuf[:] = n_host
-    e_pair = np.array([s.pair for s in stats]); e_wall = np.array([s.wall for s in stats])   # the host owns the state
+    sv = eng.stats_view(stats)
+    e_pair = sv["pair"].copy(); e_wall = sv["wall"].copy()   # the host owns the state
     barrier(dist, local)
     e2e_s = 0.0
     for _ in range(args.steps):
@@ -319,7 +320,8 @@ def gpu_arm(args, world, rank, local, dist):
         st = one_step(set_index); set_index += 1              # K2
         n_host, _, _, _ = eng.get_positions_all(X, Y, Z)        # D2H: positions; statistics came back with run()
         nbuf[:] = n_host
-        e_pair = np.array([s.pair for s in st]); e_wall = np.array([s.wall for s in st])
+        sv = eng.stats_view(st)
+        e_pair = sv["pair"].copy(); e_wall = sv["wall"].copy()
         e2e_s += time.perf_counter() - t0
     barrier(dist, local)
     clocks = sampler.stop() if rank == 0 else None     # sampled over both timed regions (device-resident and end-to-end)

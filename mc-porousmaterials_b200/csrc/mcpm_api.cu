@@ -54,6 +54,8 @@ struct mcpm_ctx {
     int use_cache = 1;             // per-particle energy cache in K2 (mcpm_use_energy_cache)
     int use_subwarp = 0;           // opt-in: the sub-warp kernel that packs 2 or 4 small chains into one warp (mcpm_use_subwarp)
     int2* d_ctas = nullptr;        // CTA descriptors of the sub-warp kernel, n_chains entries
+    int* d_flags = nullptr;        // 2*n_chains ints: particle counts in, in-box flags out (bulk uploads)
+    int* h_flags = nullptr;        // pinned mirror
     double* d_ep = nullptr;        // [n_chains][cap], allocated on first use
     double* d_replay = nullptr; size_t replay_doubles = 0;
     unsigned char* d_trace = nullptr; size_t trace_bytes = 0;
@@ -200,7 +202,8 @@ int mcpm_destroy(mcpm_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_params); cudaFree(c->d_state); cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_z);
     cudaFree(c->d_order); cudaFree(c->d_scratch); cudaFree(c->d_counters); cudaFree(c->d_out);
-    cudaFree(c->d_pp); cudaFree(c->d_pw); cudaFree(c->d_rdf); cudaFree(c->d_ep); cudaFree(c->d_ctas);
+    cudaFree(c->d_pp); cudaFree(c->d_pw); cudaFree(c->d_rdf); cudaFree(c->d_ep); cudaFree(c->d_ctas); cudaFree(c->d_flags);
+    if (c->h_flags) cudaFreeHost(c->h_flags);
     cudaFree(c->d_cell_of); cudaFree(c->d_cell_counts); cudaFree(c->d_cell_starts); cudaFree(c->d_orig);
     cudaFree(c->d_sx); cudaFree(c->d_sy); cudaFree(c->d_sz); cudaFree(c->d_replay); cudaFree(c->d_trace);
     if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -300,11 +303,18 @@ int mcpm_set_positions_all(mcpm_ctx* c, const int* n, const double* x, const dou
     CU(cudaMemcpy2DAsync(c->d_x, pitch, x, pitch, wbytes, c->n_chains, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpy2DAsync(c->d_y, pitch, y, pitch, wbytes, c->n_chains, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpy2DAsync(c->d_z, pitch, z, pitch, wbytes, c->n_chains, cudaMemcpyHostToDevice, c->stream));
+    // in-box test of ~MBs of coordinates: on the device, where they just arrived (a host loop costs as much as the copy)
+    if (!c->d_flags) { CU(cudaMalloc(&c->d_flags, sizeof(int) * 2 * c->n_chains)); CU(cudaMallocHost(&c->h_flags, sizeof(int) * 2 * c->n_chains)); }
+    memcpy(c->h_flags, n, sizeof(int) * c->n_chains);
+    CU(cudaMemcpyAsync(c->d_flags, c->h_flags, sizeof(int) * c->n_chains, cudaMemcpyHostToDevice, c->stream));
+    CU(launch_in_box(c->n_chains, c->d_params, c->d_flags, c->d_x, c->d_y, c->d_z, c->cap, c->d_flags + c->n_chains, c->stream));
+    c->launches++;
+    CU(cudaMemcpyAsync(c->h_flags + c->n_chains, c->d_flags + c->n_chains, sizeof(int) * c->n_chains, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     for (int k = 0; k < c->n_chains; k++) {
         ChainState& S = c->h_state[k];
-        const size_t off = (size_t)k * c->cap;
         S.st.n = n[k]; S.st.overflow = 0; S.energy_valid = 0;
-        S.fast_image = in_box(c->h_params[k], n[k], x + off, y + off, z + off) ? 1 : 0;
+        S.fast_image = c->h_flags[c->n_chains + k];
     }
     CU(cudaMemcpyAsync(c->d_state, c->h_state.data(), sizeof(ChainState) * c->n_chains, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));

@@ -995,6 +995,29 @@ cudaError_t launch_k3(int tiles, int n_chains, int chain0, const ChainParams* pa
     return cudaGetLastError();
 }
 
+// fast_image flag of every chain after a bulk upload: all coordinates on periodic axes inside [0, L] (and finite)
+__global__ void in_box_kernel(const ChainParams* __restrict__ params, const int* __restrict__ n_of, const double* __restrict__ X,
+                              const double* __restrict__ Y, const double* __restrict__ Z, int cap, int* __restrict__ flags) {
+    const int chain = blockIdx.x;
+    const ChainParams& P = params[chain];
+    const int n = n_of[chain];
+    const size_t off = (size_t)chain * cap;
+    int bad = 0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const double x = X[off + j], y = Y[off + j], z = Z[off + j];
+        if (P.pbc[0] && !(x >= 0.0 && x <= P.L[0])) bad = 1;
+        if (P.pbc[1] && !(y >= 0.0 && y <= P.L[1])) bad = 1;
+        if (P.pbc[2] && !(z >= 0.0 && z <= P.L[2])) bad = 1;
+    }
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) flags[chain] = bad ? 0 : 1;
+}
+cudaError_t launch_in_box(int n_chains, const ChainParams* params, const int* n_of, const double* X, const double* Y, const double* Z, int cap,
+                          int* flags, cudaStream_t stream) {
+    in_box_kernel<<<n_chains, 128, 0, stream>>>(params, n_of, X, Y, Z, cap, flags);
+    return cudaGetLastError();
+}
+
 size_t k3c_cells_per_chain() { return (size_t)K3C_MAXC * K3C_MAXC * K3C_MAXC; }
 
 // Cell-list K3 for chains [chain0, chain0+n_chains): all of them must qualify (see mcpm_api.cu::cell_list_ok).

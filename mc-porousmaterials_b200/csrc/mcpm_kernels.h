@@ -23,6 +23,8 @@ size_t k2_sub_smem_bytes(int cap_cta);
 cudaError_t launch_k2_sub(int rng_mode, bool pbz, int n_ctas, const ChainParams* params, ChainState* states, const int* order, const int2* ctas,
                           double* X, double* Y, double* Z, const RunArgs& a, int cap_cta, cudaStream_t stream);
 
+cudaError_t launch_in_box(int n_chains, const ChainParams* params, const int* n_of, const double* X, const double* Y, const double* Z, int cap,
+                          int* flags, cudaStream_t stream);
 size_t k3c_cells_per_chain();
 cudaError_t launch_k3_cells(int maxn, int n_chains, int chain0, const ChainParams* params, ChainState* states, const double* X,
                             const double* Y, const double* Z, int cap, int* cell_of, int* counts, int* starts, double* sx, double* sy,

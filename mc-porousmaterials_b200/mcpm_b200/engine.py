@@ -165,6 +165,13 @@ class Engine:
         check(self.L.mcpm_get_stats(self.h, stats))
         return stats
 
+    @staticmethod
+    def stats_view(stats):
+        """Structured numpy view (no copy) of an array of ChainStats: stats_view(st)['pair'] etc."""
+        dt = np.dtype([(name, np.dtype(ct)) for name, ct in ChainStats._fields_], align=True)
+        assert dt.itemsize == C.sizeof(ChainStats)
+        return np.frombuffer(stats, dtype=dt)
+
     def reset_accumulators(self):
         check(self.L.mcpm_reset_accumulators(self.h))
 
