@@ -543,8 +543,16 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     a.first_set = p->first_set; a.n_sets = p->n_sets; a.steps_per_set = p->steps_per_set; a.seed = p->seed;
     a.check_energy = p->check_energy; a.cap = c->cap;
     a.sample_rdf = p->sample_rdf; a.rdf = c->d_rdf;
-    if (c->use_cache && !c->d_ep) CU(cudaMalloc(&c->d_ep, sizeof(double) * (size_t)c->n_chains * c->cap));
-    a.ep = c->use_cache ? c->d_ep : nullptr;
+    // The energy cache pays while accepted translations (each costs a second pass over the partners) are the minority:
+    // N + 2pN < 2N for p < 0.5.  Decide from the acceptance of the last set; the reference's dr adaptation aims at 0.2.
+    bool cache_now = c->use_cache != 0;
+    {
+        double acc = 0.0, att = 0.0;
+        for (int k = 0; k < c->n_chains; k++) { acc += (double)c->h_state[k].st.acceptance; att += (double)c->h_state[k].st.n_displacements - 1.0; }
+        if (att >= 100.0 * c->n_chains && acc / att > 0.4) cache_now = false;
+    }
+    if (cache_now && !c->d_ep) CU(cudaMalloc(&c->d_ep, sizeof(double) * (size_t)c->n_chains * c->cap));
+    a.ep = cache_now ? c->d_ep : nullptr;
     const unsigned long long nsteps = (unsigned long long)p->n_sets * (unsigned long long)p->steps_per_set;
     if (p->rng_mode == MCPM_RNG_REPLAY) {
         const size_t need = (size_t)c->n_chains * p->replay_stride;
@@ -570,7 +578,7 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     // coordinates inside the box, shared-memory positions, no in-kernel sampling and one geometry for the whole launch.
     bool same_pbz = true;
     for (int k = 1; k < c->n_chains; k++) same_pbz = same_pbz && c->h_params[k].pbc[2] == c->h_params[0].pbc[2];
-    const bool use_sub = c->use_subwarp && threads == 32 && c->use_cache && all_fast && !sample && !global_path && same_pbz;
+    const bool use_sub = c->use_subwarp && threads == 32 && cache_now && all_fast && !sample && !global_path && same_pbz;
     CU(cudaEventRecord(c->ev0, c->stream));
     if (use_sub) {
         const int cap_cta = ((c->cap + 127) / 128) * 128;
@@ -607,7 +615,7 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
             c->launches++;
         }
     } else {
-        CU(launch_k2(p->rng_mode, c->n_chains, threads, all_fast, sample, c->use_cache != 0, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->max_smem, c->stream));
+        CU(launch_k2(p->rng_mode, c->n_chains, threads, all_fast, sample, cache_now, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->max_smem, c->stream));
         c->launches++;
     }
     CU(cudaEventRecord(c->ev1, c->stream));

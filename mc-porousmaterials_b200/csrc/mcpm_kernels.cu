@@ -466,13 +466,18 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                         double xk, yk, zk;
                         load_slot(xs, ys, zs, k, fwd, xk, yk, zk);
                         double v[1];
-                        v[0] = pair_sum1<FAST, PBZ>(xs, ys, zs, n, k, g, xk, yk, zk, tid, T);
                         double wk, wdummy;
-                        wall_two(P, zk, zk, wk, wdummy, lane);
-                        cta_allsum<1, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
-                        fwd.slot = -1;
+                        if (CACHE) {
+                            v[0] = ep[k];                                         // a real particle's pair sum is in the cache
+                            wall_two(P, zk, zk, wk, wdummy, lane);
+                        } else {
+                            v[0] = pair_sum1<FAST, PBZ>(xs, ys, zs, n, k, g, xk, yk, zk, tid, T);
+                            wall_two(P, zk, zk, wk, wdummy, lane);
+                            cta_allsum<1, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
+                            fwd.slot = -1;
+                            if (lead) st.pair_evals += (unsigned long long)n;
+                        }
                         energy = eps4 * v[0] + wk;
-                        if (lead) st.pair_evals += (unsigned long long)n;
                     }
                     if (lead) {
                         st.pair_evals_algorithmic += (unsigned long long)n;
@@ -937,14 +942,15 @@ static cudaError_t launch_k2_rng(int n_chains, int threads, bool global, bool fa
     // The hot kernels (shared-memory positions, coordinates inside the box, no in-kernel sampling) exist for CTAs of up
     // to 64 / 256 / 512 threads (128 registers each; ptxas fits the 32-thread kernel into 96 registers without spills,
     // but measured on B200 that costs more ILP than the extra occupancy returns: C2 7.2e8 vs 7.7e8 moves/s), each with
-    // and without the per-particle energy cache.  The general kernels (general minimum image for coordinates outside
-    // the box and/or Widom + RDF sampling after every production step) and the global-memory kernels exist for one CTA
-    // shape each; k2_threads_supported() clamps the thread count accordingly.
-    if (!fast || sample) {
-        if (global) return fast ? go(k2_chains<RNG_MODE, 512, 1, true, true, true, false>) : go(k2_chains<RNG_MODE, 512, 1, true, false, true, false>);
-        return fast ? go(k2_chains<RNG_MODE, 256, 2, false, true, true, false>) : go(k2_chains<RNG_MODE, 256, 2, false, false, true, false>);
+    // and without the per-particle energy cache.  The sampling kernels (Widom + RDF after every production step), the
+    // global-memory kernels and the general-minimum-image kernels (coordinates outside the box, never cached) exist for
+    // one CTA shape each; k2_threads_supported() clamps the thread count accordingly.
+    if (!fast) return global ? go(k2_chains<RNG_MODE, 512, 1, true, false, true, false>) : go(k2_chains<RNG_MODE, 256, 2, false, false, true, false>);
+    if (sample) {
+        if (global) return cache ? go(k2_chains<RNG_MODE, 512, 1, true, true, true, true>) : go(k2_chains<RNG_MODE, 512, 1, true, true, true, false>);
+        return cache ? go(k2_chains<RNG_MODE, 256, 2, false, true, true, true>) : go(k2_chains<RNG_MODE, 256, 2, false, true, true, false>);
     }
-    if (global) return go(k2_chains<RNG_MODE, 512, 1, true, true, false, false>);
+    if (global) return cache ? go(k2_chains<RNG_MODE, 512, 1, true, true, false, true>) : go(k2_chains<RNG_MODE, 512, 1, true, true, false, false>);
     if (cache) {
         if (threads <= 64) return go(k2_chains<RNG_MODE, 64, 8, false, true, false, true>);
         if (threads <= 256) return go(k2_chains<RNG_MODE, 256, 2, false, true, false, true>);
@@ -960,7 +966,7 @@ int k2_threads_supported(int threads, bool global, bool fast, bool sample) {
     return std::min(threads, 512);
 }
 
-bool k2_cache_supported(bool global, bool fast, bool sample) { return !global && fast && !sample; }
+bool k2_cache_supported(bool global, bool fast, bool sample) { (void)global; (void)sample; return fast; }
 
 cudaError_t launch_k2(int rng_mode, int n_chains, int threads, bool fast, bool sample, bool cache, const ChainParams* params,
                       ChainState* states, const int* order, double* X, double* Y, double* Z, const RunArgs& a, int max_smem_optin,
