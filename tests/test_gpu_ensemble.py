@@ -66,3 +66,32 @@ def test_replicas_are_statistically_independent(mcpm):
         stats, tr = e.run(1, 1, 4000, seed=11, trace=True)
     sig = [tuple(t[:200]) for t in tr]
     assert len(set(sig)) == 32                         # no two chains share an accept/reject sequence
+
+
+def test_ideal_gas_known_answer(mcpm):
+    """Closed-form check that needs no oracle: with eps = 0 and no wall, GCMC samples a Poisson distribution of N with
+    mean zz*V (zz = exp(mu/T)/Lambda^3, src/moves.cpp:296-298), so <N> = Var(N) = zz*V.  (The reference's [0,0.9999)
+    uniforms bias insertion/deletion acceptance identically, the ratio and hence the mean are unaffected to ~1e-4.)"""
+    import math
+    T, L = 100.0, 30.0
+    lam = 6.62607015e-34 / math.sqrt(2.0 * math.pi * (39.948 / 6.02214076e23 * 1e-3) * 1.380649e-23 * T) * 1e10
+    target = 60.0
+    mu = T * math.log(target * lam ** 3 / L ** 3)
+    s = O.make_system(geometry=0, wall_kind=0, n_layers=0, n_disp=1, n_vol=0, n_swap=1, n_equil_sets=0,
+                      width=(L, L, L), temperature=T, eps_ff=0.0, sig_ff=3.4, rcut=10.0, molar_mass=39.948, mu=mu,
+                      eps_sf=0.0, sig_sf=0.0, rho_s=0.0, delta=0.0, dr=3.0)
+    rng = np.random.default_rng(0)
+    R = 128
+    with mcpm.Engine(R, 256) as e:
+        e.set_system(s)
+        for r in range(R):
+            e.set_positions(r, rng.random(60) * L, rng.random(60) * L, rng.random(60) * L)
+        e.run(1, 1, 20000, seed=3)
+        e.reset_accumulators()
+        stats = e.run(2, 1, 60000, seed=3)
+    mean = np.array([st.sum_n / st.samples for st in stats])
+    var = np.array([st.sum_n2 / st.samples - (st.sum_n / st.samples) ** 2 for st in stats])
+    sem = mean.std(ddof=1) / np.sqrt(R)
+    assert abs(mean.mean() - target) < 4.0 * sem + 0.01 * target * 1e-2, (mean.mean(), sem)
+    assert var.mean() == pytest.approx(target, rel=0.03)
+    assert all(st.energy == 0.0 for st in stats)
