@@ -181,6 +181,14 @@ int mcpm_use_energy_cache(mcpm_ctx* ctx, int enable);
  * traces); measured on B200 it is 1.7-2x SLOWER than the default kernel in round 1 (more instructions per step and
  * longer dependent chains outweigh the sharing), see DESIGN.md. */
 int mcpm_use_subwarp(mcpm_ctx* ctx, int enable);
+/* Speculative moves (the latency kernel for FEW chains, e.g. one chain per isotherm point): a CTA of 8 warps evaluates
+ * the next 8 steps of its chain concurrently against the same configuration, commits the first accepted one and
+ * re-evaluates the steps after it; rejected steps before it stand.  The chain is exactly the sequential one (same
+ * uniforms per step index, same decisions, same trace).  mode -1 (default): chosen automatically when the context has
+ * no more chains than the device has SMs, threads_per_chain is 0 and the energy cache is in use; 0: never; 1: whenever
+ * the launch qualifies (energy cache enabled, coordinates inside the box, no in-kernel sampling, shared-memory
+ * positions).  Replaces nothing in the reference: it is a schedule of src/main.cpp:66-71. */
+int mcpm_use_speculation(mcpm_ctx* ctx, int mode);
 int mcpm_reset_accumulators(mcpm_ctx* ctx);
 /* Accumulated pair-distance histogram of one chain: hist[0..99] = MC::Stats::rdf(0..99) (bin 0 is never filled,
  * each pair adds 2, src/sample.cpp:27-28).  mcpm_reset_accumulators clears it. */

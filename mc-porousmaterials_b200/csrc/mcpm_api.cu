@@ -52,6 +52,7 @@ struct mcpm_ctx {
     double *d_sx = nullptr, *d_sy = nullptr, *d_sz = nullptr;
     int use_cells = 1;             // 0 disables the cell-list path (tests compare both)
     int use_cache = 1;             // per-particle energy cache in K2 (mcpm_use_energy_cache)
+    int use_spec = -1;             // speculative-moves kernel (mcpm_spec.cu): -1 = automatic (fewer chains than SMs), 0 = never, 1 = whenever possible
     int use_subwarp = 0;           // opt-in: the sub-warp kernel that packs 2 or 4 small chains into one warp (mcpm_use_subwarp)
     int2* d_ctas = nullptr;        // CTA descriptors of the sub-warp kernel, n_chains entries
     int* d_flags = nullptr;        // 2*n_chains ints: particle counts in, in-box flags out (bulk uploads)
@@ -551,6 +552,14 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
         for (int k = 0; k < c->n_chains; k++) { acc += (double)c->h_state[k].st.acceptance; att += (double)c->h_state[k].st.n_displacements - 1.0; }
         if (att >= 100.0 * c->n_chains && acc / att > 0.4) cache_now = false;
     }
+    // The speculative-moves kernel (mcpm_spec.cu) trades throughput for latency: it is chosen when there are too few
+    // chains to fill the GPU anyway, the caller left the thread count open, and moves are mostly rejected.  It needs the
+    // energy cache, coordinates inside the box, shared-memory positions, no in-kernel sampling and one geometry.
+    bool same_pbz = true;
+    for (int k = 1; k < c->n_chains; k++) same_pbz = same_pbz && c->h_params[k].pbc[2] == c->h_params[0].pbc[2];
+    const bool spec_ok = c->use_cache && all_fast && !sample && !global_path && same_pbz && k2_spec_smem_bytes(c->cap) <= (size_t)c->max_smem;
+    const bool use_spec = spec_ok && (c->use_spec == 1 || (c->use_spec < 0 && cache_now && p->threads_per_chain == 0 && c->n_chains <= c->num_sms));
+    if (use_spec) cache_now = true;
     if (cache_now && !c->d_ep) CU(cudaMalloc(&c->d_ep, sizeof(double) * (size_t)c->n_chains * c->cap));
     a.ep = cache_now ? c->d_ep : nullptr;
     const unsigned long long nsteps = (unsigned long long)p->n_sets * (unsigned long long)p->steps_per_set;
@@ -576,11 +585,12 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     }
     // The sub-warp kernel (mcpm_subwarp.cu) takes over whenever one warp per chain was chosen: it needs the energy cache,
     // coordinates inside the box, shared-memory positions, no in-kernel sampling and one geometry for the whole launch.
-    bool same_pbz = true;
-    for (int k = 1; k < c->n_chains; k++) same_pbz = same_pbz && c->h_params[k].pbc[2] == c->h_params[0].pbc[2];
     const bool use_sub = c->use_subwarp && threads == 32 && cache_now && all_fast && !sample && !global_path && same_pbz;
     CU(cudaEventRecord(c->ev0, c->stream));
-    if (use_sub) {
+    if (use_spec) {
+        CU(launch_k2_spec(p->rng_mode, c->h_params[0].pbc[2] != 0, c->n_chains, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->stream));
+        c->launches++;
+    } else if (use_sub) {
         const int cap_cta = ((c->cap + 127) / 128) * 128;
         if (!c->d_ctas) CU(cudaMalloc(&c->d_ctas, sizeof(int2) * c->n_chains));
         auto chains_per_warp = [&](int n) {   // room for the fluctuations of N during the launch; outgrowing the slot pauses the chain
@@ -689,6 +699,13 @@ int mcpm_set_running_energy(mcpm_ctx* c, const double* pair, const double* wall)
     }
     CU(cudaMemcpyAsync(c->d_state, c->h_state.data(), sizeof(ChainState) * c->n_chains, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return MCPM_OK;
+}
+
+int mcpm_use_speculation(mcpm_ctx* c, int mode) {
+    if (!c) return fail(MCPM_ERR_ARG, "null context");
+    if (mode < -1 || mode > 1) return fail(MCPM_ERR_ARG, "speculation mode must be -1 (automatic), 0 (off) or 1 (on)");
+    c->use_spec = mode;
     return MCPM_OK;
 }
 

@@ -1,0 +1,312 @@
+// K2x — speculative moves: the LATENCY kernel for few chains (a 40-point isotherm with one chain per state point is
+// 40 sequential Markov chains: 148 SMs cannot be filled with chains, so each chain should finish its steps sooner).
+//
+// A Markov chain is sequential only through its ACCEPTED moves.  Most trial moves are rejected (the reference adapts the
+// step size to ~20 % translation acceptance; GCMC insertions/deletions in a dense pore succeed a few % of the time), and
+// a rejected move leaves the configuration untouched.  One CTA of KW warps therefore evaluates the next KW steps of ITS
+// chain concurrently, every warp one step against the SAME configuration, as if all earlier steps of the round were
+// rejected.  The first accepted step k* is committed, the steps after k* are discarded and evaluated again in the next
+// round with the same uniforms (the stream is counter-based: a step's draws depend only on its index), so the chain is
+// exactly the sequential one.  Expected progress per round is (1-(1-p)^KW)/p steps (5.5 at p = 0.11, KW = 8).
+// A warp scans all partners of its candidate alone (old energies come from the per-particle energy cache, so a
+// candidate costs at most one scan); the commit of the accepted move (second pass over the partners) uses the whole CTA.
+//
+// Restates the same reference code as chain_loop in mcpm_kernels.cu: step loop src/main.cpp:66-71, MoveParticle
+// src/moves.cpp:118-186, SwapParticle src/moves.cpp:284-341, ResetStats src/MC.cpp:81-98, AdjustMCMoves src/moves.cpp:68-78.
+#include <algorithm>
+
+#include "mcpm_chain.cuh"
+#include "mcpm_device.cuh"
+#include "mcpm_kernels.h"
+
+namespace mcpm {
+
+namespace {
+
+enum { CAND_TRANS = 0, CAND_INS = 1, CAND_DEL = 2, CAND_EMPTY = 3, CAND_VOL = 4, CAND_OVERFLOW = 5 };
+
+struct Cand {            // one warp's candidate step, published in shared memory
+    int type, acc, idx, pad;
+    double px, py, pz;   // trial position (translation, insertion)
+    double ox, oy, oz;   // position of the selected particle (translation, deletion)
+    double v;            // unscaled pair sum of the trial position
+    double po, pn, wo, wn;
+};
+
+// The 8 uniforms of global step `step` of this chain: lanes 0..3 hold the step's four Philox calls.
+struct StepPhilox {
+    double ua, ub;
+    __device__ __forceinline__ void load(unsigned long long seed, uint32_t chain, unsigned long long step, int lane) {
+        philox_call(seed, chain, 4ull * step + (unsigned long long)(lane & 3), ua, ub);
+    }
+    template <int K>
+    __device__ __forceinline__ double at() const { return __shfl_sync(MCPM_FULL_MASK, (K & 1) ? ub : ua, K >> 1); }
+};
+struct StepReplay {
+    const double* u;
+    unsigned long long pos, n;
+    template <int K>
+    __device__ __forceinline__ double at() const { return (pos + K < n) ? __ldg(u + pos + K) : 0.0; }
+};
+
+// Evaluates one step read-only.  Called by one full warp; every lane returns the same candidate.
+template <class Draws, bool PBZ>
+__device__ __forceinline__ Cand evaluate_candidate(const Draws& rng, const ChainParams& P, const PairGeom& g, const double* xs, const double* ys,
+                                                   const double* zs, const double* ep, int n, int cap, double dr, int lane) {
+    Cand c;
+    c.type = CAND_EMPTY; c.acc = 0; c.idx = 0; c.pad = 0;
+    c.px = c.py = c.pz = c.ox = c.oy = c.oz = c.v = c.po = c.pn = c.wo = c.wn = 0.0;
+    const double r = rng.template at<0>() * P.wsum;                                       // src/main.cpp:67
+    if (r <= P.thr_disp) {
+        const double u_i = rng.template at<3>(), u_x = rng.template at<4>(), u_y = rng.template at<5>(), u_z = rng.template at<6>(),
+                     u_a = rng.template at<7>();
+        const int i = (int)(u_i * (double)n);                                             // n == 0: the stale slot 0 (quirk Q12)
+        const double xo = xs[i], yo = ys[i], zo = zs[i];
+        const double ep_i = (n > 0) ? ep[i] : 0.0;
+        const double xr = __dadd_rn(xo, __dmul_rn(u_x - 0.5, dr)), yr = __dadd_rn(yo, __dmul_rn(u_y - 0.5, dr));
+        const double zr = __dadd_rn(zo, __dmul_rn(u_z - 0.5, dr));
+        bool odd = false;
+        double xn = wrap_select(xr, P.L[0], odd), yn = wrap_select(yr, P.L[1], odd), zn = PBZ ? wrap_select(zr, P.L[2], odd) : zr;
+        if (odd) { xn = wrap_floor(xr, P.L[0]); yn = wrap_floor(yr, P.L[1]); if (PBZ) zn = wrap_floor(zr, P.L[2]); }
+        double v = pair_sum1<true, PBZ>(xs, ys, zs, n, i, g, xn, yn, zn, lane, 32);
+        double wo, wn;
+        wall_two(P, zo, zn, wo, wn, lane);
+        v = warp_allsum(v);
+        const double po = P.eps4 * ep_i, pn = P.eps4 * v;
+        const double dE = (pn + wn) - (po + wo);                                          // src/moves.cpp:169
+        c.type = CAND_TRANS; c.acc = metropolis_translation(u_a, dE * P.beta) ? 1 : 0; c.idx = i;
+        c.px = xn; c.py = yn; c.pz = zn; c.ox = xo; c.oy = yo; c.oz = zo; c.v = v; c.po = po; c.pn = pn; c.wo = wo; c.wn = wn;
+    } else if (r <= P.thr_vol) {
+        c.type = CAND_VOL;
+    } else if (rng.template at<2>() < 0.5) {
+        if (n >= cap) { c.type = CAND_OVERFLOW; c.acc = 1; }
+        else {
+            const double u_x = rng.template at<3>(), u_y = rng.template at<4>(), u_z = rng.template at<5>(), u_a = rng.template at<6>();
+            const double xi = u_x * P.L[0], yi = u_y * P.L[1], zi = u_z * P.L[2];         // src/moves.cpp:46-54
+            double v = pair_sum1<true, PBZ>(xs, ys, zs, n, -1, g, xi, yi, zi, lane, 32);
+            double wi, wd;
+            wall_two(P, zi, zi, wi, wd, lane);
+            v = warp_allsum(v);
+            const double pi_ = P.eps4 * v;
+            c.type = CAND_INS; c.acc = metropolis_insertion(u_a, -((pi_ + wi) * P.beta), P.ln_zzV, P.zzV, n) ? 1 : 0; c.idx = n;   // src/moves.cpp:306
+            c.px = xi; c.py = yi; c.pz = zi; c.v = v; c.pn = pi_; c.wn = wi;
+        }
+    } else if (n > 0) {
+        const double u_o = rng.template at<3>(), u_a = rng.template at<4>();
+        const int o = (int)(u_o * (double)n + 1.0) - 1;
+        const double xo = xs[o], yo = ys[o], zo = zs[o];
+        double wo, wd;
+        wall_two(P, zo, zo, wo, wd, lane);
+        const double po = P.eps4 * ep[o];
+        c.type = CAND_DEL; c.acc = metropolis_deletion(u_a, (po + wo) * P.beta, P.ln_zzV, P.zzV, n) ? 1 : 0; c.idx = o;            // src/moves.cpp:326
+        c.ox = xo; c.oy = yo; c.oz = zo; c.po = po; c.wo = wo;
+    }
+    return c;
+}
+
+}  // namespace
+
+template <int RNG_MODE, bool PBZ, int KW>
+__global__ void __launch_bounds__(32 * KW, 1) k2_spec(const ChainParams* __restrict__ params, ChainState* __restrict__ states,
+                                                      const int* __restrict__ order, double* X, double* Y, double* Z, RunArgs a) {
+    extern __shared__ double smem[];
+    __shared__ ChainParams P;
+    __shared__ ChainState S;
+    __shared__ Cand cand[2][KW];                     // double-buffered by round parity: a round needs ONE barrier
+    __shared__ unsigned long long rpos[KW + 1];      // replay mode: stream position of every candidate of the round
+    const int chain = order[blockIdx.x];
+    const int cap = a.cap;
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    double* xs = smem;
+    double* ys = smem + cap;
+    double* zs = smem + 2 * cap;
+    double* partials = smem + 3 * cap;               // 128 doubles
+    if (tid == 0) { P = params[chain]; S = states[chain]; }
+    __syncthreads();
+    const size_t off = (size_t)chain * (size_t)cap;
+    for (int j = tid; j < cap; j += T) { xs[j] = X[off + j]; ys[j] = Y[off + j]; zs[j] = Z[off + j]; }
+    __syncthreads();
+
+    const bool lead = (tid == 0);
+    const PairGeom g = make_geom<true>(P);
+    mcpm_chain_stats& st = S.st;                     // shared memory; written by thread 0 only
+    double* ep = a.ep + off;
+    unsigned char* trace = a.trace ? a.trace + (unsigned long long)chain * a.trace_stride : nullptr;
+    const double* replay = (RNG_MODE == MCPM_RNG_REPLAY) ? a.replay_u + (unsigned long long)chain * a.replay_stride : nullptr;
+
+    int n = st.n;
+    double dr = st.dr, e_pair = st.pair, e_wall = st.wall;
+    unsigned long long step = st.steps_done, rcur = 0ull;
+    int overflow = 0, par = 0;
+    const int steps_per_set = (int)a.steps_per_set;
+
+    {   // energy cache: reuse the previous launch's if the configuration is unchanged, else rebuild (see chain_loop)
+        const unsigned long long sum = config_checksum<true>(xs, ys, zs, n, (unsigned long long*)partials, tid, T, lane, warp, KW);
+        if (!(S.cache_valid && S.cache_sum == sum)) {
+            double cp, cw;
+            cache_fill<true, PBZ, true>(xs, ys, zs, ep, n, P, g, partials, KW, warp, lane, tid, T, cp, cw);
+            e_pair = cp; e_wall = cw;
+            if (lead) st.pair_evals += (unsigned long long)n * (unsigned long long)n;
+        }
+    }
+
+    SetCounters sc;
+    for (int set = a.first_set; set < a.first_set + a.n_sets && !overflow; set++) {
+        sc.reset();                                  // MC::ResetStats, src/MC.cpp:81-98
+        if (lead) { st.widom_insert = st.widom_delete = 0.0; st.widom_insertions = st.widom_deletions = 1; }
+        const bool production = set > P.n_equil;
+        int s = 0;
+        while (s < steps_per_set && !overflow) {
+            // An empty box exposes the stale slot 0, which rejected insertion attempts overwrite (quirk Q12): serial rounds.
+            const int B = (n == 0) ? 1 : min(KW, steps_per_set - s);
+            if (RNG_MODE == MCPM_RNG_REPLAY) {       // where each candidate's draws start: 1 + 7/6/4/2 draws per step
+                if (tid == 0) {
+                    unsigned long long p = rcur;
+                    for (int w = 0; w < B; w++) {
+                        rpos[w] = p;
+                        const double u0 = (p < a.replay_stride) ? replay[p] : 0.0, u2 = (p + 2 < a.replay_stride) ? replay[p + 2] : 0.0;
+                        const double r = u0 * P.wsum;
+                        p += (r <= P.thr_disp) ? 8 : ((r <= P.thr_vol) ? 1 : ((u2 < 0.5) ? 7 : (n > 0 ? 5 : 3)));
+                    }
+                    rpos[B] = p;
+                }
+                __syncthreads();
+            }
+            // ---- every warp evaluates one candidate step against the current configuration ----
+            if (warp < B) {
+                Cand c;
+                if (RNG_MODE == MCPM_RNG_PHILOX) {
+                    StepPhilox rng; rng.load(a.seed, (uint32_t)chain, step + (unsigned long long)warp, lane);
+                    c = evaluate_candidate<StepPhilox, PBZ>(rng, P, g, xs, ys, zs, ep, n, cap, dr, lane);
+                } else {
+                    StepReplay rng; rng.u = replay; rng.pos = rpos[warp]; rng.n = a.replay_stride;
+                    c = evaluate_candidate<StepReplay, PBZ>(rng, P, g, xs, ys, zs, ep, n, cap, dr, lane);
+                }
+                if (lane == 0) cand[par][warp] = c;
+            }
+            __syncthreads();
+            const Cand* cd = cand[par];
+            par ^= 1;
+            // ---- the first accepted candidate wins; everything before it is a rejected step that stands ----
+            int kstar = -1;
+            for (int w = B - 1; w >= 0; w--) if (cd[w].acc) kstar = w;
+            const bool stop = (kstar >= 0 && cd[kstar].type == CAND_OVERFLOW);
+            const int kept = stop ? kstar : (kstar >= 0 ? kstar + 1 : B);
+            int last_ins = -1;
+            for (int w = 0; w < B; w++) {            // counters (replicated in every thread)
+                const int ty = cd[w].type;
+                if (ty == CAND_TRANS || ty == CAND_INS) sc.evals += (unsigned long long)n;   // executed, kept or not
+                if (w >= kept) continue;
+                const int ac = cd[w].acc;
+                if (ty == CAND_TRANS) { sc.n_disp++; sc.acc_disp += ac; sc.alg += 2ull * (unsigned long long)n; }
+                else if (ty == CAND_INS) { sc.n_ins++; sc.acc_ins += ac; sc.alg += (unsigned long long)n; last_ins = w; }
+                else if (ty == CAND_DEL) { sc.n_del++; sc.acc_del += ac; sc.alg += (unsigned long long)n; }
+                else if (ty == CAND_EMPTY) sc.n_empty++;
+            }
+            // the trial position of an insertion attempt stays in the first free slot even if rejected (src/moves.cpp:302-303)
+            if (last_ins >= 0 && tid == 0) { xs[n] = cd[last_ins].px; ys[n] = cd[last_ins].py; zs[n] = cd[last_ins].pz; }
+            const int n_before = n;
+            const double e_before = e_pair + e_wall;
+            // ---- commit the accepted move with the whole CTA ----
+            if (kstar >= 0 && !stop) {
+                const Cand c = cd[kstar];
+                bool big = false;
+                if (c.type == CAND_TRANS) {
+                    const int i = c.idx;
+                    big = cache_apply<true, PBZ>(xs, ys, zs, ep, n, i, g, true, c.ox, c.oy, c.oz, true, c.px, c.py, c.pz, tid, T);
+                    if (tid == 0) { ep[i] = c.v; xs[i] = c.px; ys[i] = c.py; zs[i] = c.pz; }   // readers of slot i mask it out (self)
+                    if (n > 0) { e_pair += c.pn - c.po; e_wall += c.wn - c.wo; }   // full pair change (Q16); n == 0 moves a ghost (Q12)
+                    sc.evals += 2ull * (unsigned long long)n;
+                } else if (c.type == CAND_INS) {
+                    big = cache_apply<true, PBZ>(xs, ys, zs, ep, n, -1, g, false, 0., 0., 0., true, c.px, c.py, c.pz, tid, T);
+                    if (tid == 0) ep[n] = c.v;
+                    e_pair += c.pn; e_wall += c.wn;
+                    sc.evals += (unsigned long long)n;
+                    n++;
+                } else {                                                            // CAND_DEL: swap-with-last, src/moves.cpp:329
+                    const int o = c.idx;
+                    const double xl = xs[n - 1], yl = ys[n - 1], zl = zs[n - 1];
+                    big = cache_apply<true, PBZ>(xs, ys, zs, ep, n, o, g, true, c.ox, c.oy, c.oz, false, 0., 0., 0., tid, T);
+                    sc.evals += (unsigned long long)n;
+                    __syncthreads();                                                // entry n-1 is final, everyone has read slot n-1
+                    if (tid == 0) { ep[o] = ep[n - 1]; xs[o] = xl; ys[o] = yl; zs[o] = zl; }
+                    e_pair -= c.po; e_wall -= c.wo;
+                    n--;
+                }
+                if (__syncthreads_or(big ? 1 : 0)) {   // a hard overlap went through the cache: rebuild it
+                    double cp, cw;
+                    cache_fill<true, PBZ, true>(xs, ys, zs, ep, n, P, g, partials, KW, warp, lane, tid, T, cp, cw);
+                    e_pair = cp; e_wall = cw;
+                    sc.evals += (unsigned long long)n * (unsigned long long)n;
+                }
+            }
+            // ---- trace and production accumulators of the kept steps, in step order ----
+            if (lead) {
+                for (int w = 0; w < kept; w++) {
+                    const int ty = cd[w].type, ac = cd[w].acc;
+                    if (trace) {
+                        const int code = ty == CAND_TRANS ? ac : (ty == CAND_INS ? (2 | ac) : (ty == CAND_DEL ? (4 | ac) : (ty == CAND_EMPTY ? 6 : 8)));
+                        trace[(unsigned long long)(set - a.first_set) * (unsigned long long)a.steps_per_set + (unsigned long long)(s + w)] = (unsigned char)code;
+                    }
+                    if (production) {
+                        const bool after = (w == kstar);                            // only the accepted step sees the new state
+                        const double dn = (double)(after ? n : n_before), e = after ? (e_pair + e_wall) : e_before;
+                        st.sum_n += dn; st.sum_n2 += dn * dn; st.sum_e += e; st.sum_e2 += e * e;
+                        st.samples++;
+                    }
+                }
+            }
+            if (RNG_MODE == MCPM_RNG_REPLAY) rcur = rpos[kept];
+            step += (unsigned long long)(kept + (stop ? 1 : 0));
+            s += kept;
+            if (stop) overflow = 1;
+            if (RNG_MODE == MCPM_RNG_REPLAY || n_before == 0 || n == 0) __syncthreads();   // rpos[] / slot 0 are reused at once
+        }
+        // MC::AdjustMCMoves displacement part, src/moves.cpp:68-78 (ResetStats starts nDisplacements at ONE)
+        if (!overflow && n > 0 && set <= P.n_equil) {
+            const double ratio = (double)sc.acc_disp * 1. / (1. * (double)(sc.n_disp + 1));
+            if (ratio < 0.2) dr /= 1.1;
+            else dr *= 1.1;
+        }
+        if (lead) {
+            st.acceptance = sc.acc_disp; st.rejection = sc.n_disp - sc.acc_disp; st.n_displacements = 1 + sc.n_disp;
+            st.accept_swap = sc.acc_ins + sc.acc_del; st.reject_swap = (sc.n_ins + sc.n_del) - (sc.acc_ins + sc.acc_del);
+            st.n_swaps = 1 + sc.n_ins + sc.n_del;
+            st.tot_disp += sc.n_disp; st.tot_disp_acc += sc.acc_disp; st.tot_ins += sc.n_ins; st.tot_ins_acc += sc.acc_ins;
+            st.tot_del += sc.n_del; st.tot_del_acc += sc.acc_del; st.tot_empty += sc.n_empty; st.pair_evals += sc.evals; st.pair_evals_algorithmic += sc.alg;
+        }
+    }
+    __syncthreads();
+
+    double c_pair = 0.0, c_wall = 0.0;
+    if (a.check_energy) cache_fill<true, PBZ, true>(xs, ys, zs, ep, n, P, g, partials, KW, warp, lane, tid, T, c_pair, c_wall);
+    const unsigned long long end_sum = config_checksum<true>(xs, ys, zs, n, (unsigned long long*)partials, tid, T, lane, warp, KW);
+    if (lead) {
+        st.n = n; st.overflow = overflow; st.dr = dr; st.steps_done = step;
+        st.pair = e_pair; st.wall = e_wall; st.energy = e_pair + e_wall;
+        if (a.check_energy) { st.pair_check = c_pair; st.wall_check = c_wall; st.energy_check = c_pair + c_wall; }
+        if (a.check_energy == 2) { st.pair = c_pair; st.wall = c_wall; st.energy = c_pair + c_wall; }
+        S.replay_pos = rcur; st.replay_consumed = rcur;
+        S.cache_valid = overflow ? 0 : 1; S.cache_sum = end_sum;
+    }
+    __syncthreads();
+    for (int j = tid; j < cap; j += T) { X[off + j] = xs[j]; Y[off + j] = ys[j]; Z[off + j] = zs[j]; }
+    if (tid == 0) states[chain] = S;
+}
+
+size_t k2_spec_smem_bytes(int cap) { return (size_t)(3 * cap + 128) * sizeof(double); }
+
+cudaError_t launch_k2_spec(int rng_mode, bool pbz, int n_chains, const ChainParams* params, ChainState* states, const int* order, double* X,
+                           double* Y, double* Z, const RunArgs& a, cudaStream_t stream) {
+    const size_t smem = k2_spec_smem_bytes(a.cap);
+    auto go = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<n_chains, 256, smem, stream>>>(params, states, order, X, Y, Z, a);
+        return cudaGetLastError();
+    };
+    if (rng_mode == MCPM_RNG_PHILOX) return pbz ? go(k2_spec<MCPM_RNG_PHILOX, true, 8>) : go(k2_spec<MCPM_RNG_PHILOX, false, 8>);
+    return pbz ? go(k2_spec<MCPM_RNG_REPLAY, true, 8>) : go(k2_spec<MCPM_RNG_REPLAY, false, 8>);
+}
+
+}  // namespace mcpm

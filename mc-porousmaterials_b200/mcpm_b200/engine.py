@@ -111,6 +111,10 @@ class Engine:
         check(self.L.mcpm_box_energy_all(self.h, arr))
         return np.array([[e.pair, e.many_body, e.wall, e.energy] for e in arr])
 
+    def use_speculation(self, mode=-1):
+        """-1 automatic (few chains), 0 never, 1 whenever the launch qualifies (mcpm_use_speculation)."""
+        check(self.L.mcpm_use_speculation(self.h, int(mode)))
+
     def use_subwarp(self, enable=True):
         check(self.L.mcpm_use_subwarp(self.h, 1 if enable else 0))
 

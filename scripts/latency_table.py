@@ -20,8 +20,11 @@ print("chains", nchains, "steps", S)
 for k in (0, 5, 12, 27, 39):
     x, y, z = g[f"x{k}"], g[f"y{k}"], g[f"z{k}"]
     row = []
-    for T in (32, 64, 128, 256, 512):
+    for T in (32, 64, 128, 256, 512, "spec"):
         with m.Engine(nchains, 768) as e:
+            e.use_speculation(1 if T == "spec" else 0)
+            if T == "spec":
+                T = 0
             e.set_system(workloads.argon_slit(mu=float(g["mu"][k]), n_equil_sets=0))
             for c in range(nchains):
                 e.set_positions(c, x, y, z)
@@ -30,5 +33,5 @@ for k in (0, 5, 12, 27, 39):
             st = e.run(2, 1, S, seed=1, threads=T)
             ms = e.last_kernel_ms()
             evals = sum(int(s.pair_evals) for s in st)
-            row.append("T=%d: %.2f us/step (%.3g evals/s)" % (T, 1e3 * ms / S, evals / (ms * 1e-3) if False else (evals - 0) / (ms * 1e-3)))
+            row.append("T=%s: %.2f us/step (%.3g evals/s)" % (T or "spec", 1e3 * ms / S, evals / (ms * 1e-3) if False else (evals - 0) / (ms * 1e-3)))
     print("point", k, "N=%d" % len(x), " | ".join(row))

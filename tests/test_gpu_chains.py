@@ -22,12 +22,14 @@ def first_divergence(a, b):
     return int(d[0]) if len(d) else -1
 
 
-@pytest.mark.parametrize("cache", [True, False, "subwarp"], ids=["cache", "nocache", "subwarp"])
+@pytest.mark.parametrize("cache", [True, False, "subwarp", "spec"], ids=["cache", "nocache", "subwarp", "spec"])
 @pytest.mark.parametrize("threads", [32, 64, 128, 256, 512])
 @pytest.mark.parametrize("name", ["c1t", "lowt", "bulkt"])
 def test_replay_trace_matches_reference_golden(mcpm, golden, name, threads, cache):
     if cache == "subwarp" and threads != 32:
         pytest.skip("the sub-warp kernel runs one warp per chain")
+    if cache == "spec" and threads != 32:
+        pytest.skip("the speculative kernel has one CTA shape")
     arrays, meta = golden
     mkey, start = TRACE_CASES[name]
     m = meta[mkey]
@@ -38,6 +40,7 @@ def test_replay_trace_matches_reference_golden(mcpm, golden, name, threads, cach
     with mcpm.Engine(1, 1024) as e:
         e.use_energy_cache(bool(cache))
         e.use_subwarp(cache == "subwarp")
+        e.use_speculation(1 if cache == "spec" else 0)
         e.set_system(s)
         e.set_positions(0, x, y, z)
         per_set, traces = [], []
@@ -91,17 +94,20 @@ def test_device_philox_stream_is_the_documented_one(mcpm):
             assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("cache", [True, False], ids=["cache", "nocache"])
+@pytest.mark.parametrize("cache", [True, False, "spec"], ids=["cache", "nocache", "spec"])
 @pytest.mark.parametrize("threads", [32, 128])
 def test_philox_chain_follows_oracle(mcpm, golden, threads, cache):
     """Device Philox + Metropolis on the GPU == the C oracle fed with the same counter-based stream."""
+    if cache == "spec" and threads != 32:
+        pytest.skip("the speculative kernel has one CTA shape")
     arrays, meta = golden
     s = system_from_meta(meta["c1"]["system"])
     s.n_equil_sets = 1
     x, y, z = arrays["c1_x"], arrays["c1_y"], arrays["c1_z"]
     seed, nchains, sets, sps = 987654321, 3, 2, 1500
     with mcpm.Engine(nchains, 1024) as e:
-        e.use_energy_cache(cache)
+        e.use_energy_cache(bool(cache))
+        e.use_speculation(1 if cache == "spec" else 0)
         e.set_system(s)
         for c in range(nchains):
             e.set_positions(c, x, y, z)
@@ -122,6 +128,8 @@ def test_philox_chain_follows_oracle(mcpm, golden, threads, cache):
             assert st.pair_evals_algorithmic == ost["pair_evals"] - evals0    # what the reference's moves evaluate
             if not cache:      # with the energy cache fewer partner scans are needed (and the rebuild adds n*n)
                 assert st.pair_evals == ost["pair_evals"] - evals0
+            elif cache == "spec":   # discarded candidates are executed evaluations too
+                assert st.pair_evals > 0
             else:
                 assert st.pair_evals < ost["pair_evals"] - evals0 + len(x) ** 2
             assert st.samples == ost["samples"] == sps
@@ -350,19 +358,84 @@ def test_energy_cache_with_hard_overlaps(mcpm):
     n0 = 150
     x, y, z = rng.random(n0) * 24, rng.random(n0) * 24, rng.random(n0) * 20
     out = []
-    for cache in (True, False):
+    for cache in (True, False, "spec"):
         with mcpm.Engine(1, 512) as e:
-            e.use_energy_cache(cache)
+            e.use_energy_cache(bool(cache))
+            e.use_speculation(1 if cache == "spec" else 0)
             e.set_system(s)
             e.set_positions(0, x, y, z)
             st, tr = e.run(1, 1, 20000, seed=5, threads=64, trace=True, check_energy=2)
             st2 = e.run(2, 1, 5000, seed=5, threads=64, check_energy=1)
             out.append((tr[0].copy(), e.get_positions(0), st2[0].energy, st2[0].energy_check))
-    assert first_divergence(out[0][0], out[1][0]) == -1
-    for a, b in zip(out[0][1], out[1][1]):
-        assert np.array_equal(a, b)
+    for other in out[1:]:
+        assert first_divergence(out[0][0], other[0]) == -1
+        for a, b in zip(out[0][1], other[1]):
+            assert np.array_equal(a, b)
     for _, _, running, check in out:
         assert running == pytest.approx(check, rel=1e-9)
+
+
+@pytest.mark.parametrize("start", ["dense", "empty", "bulk"])
+def test_speculative_moves_are_the_sequential_chain(mcpm, golden, start):
+    """The speculative kernel (8 candidate steps per round, first accepted one committed, later ones re-evaluated) must
+    reproduce the one-step-at-a-time kernel bit for bit: trace, configuration, counters, dr adaptation, accumulators.
+    'empty' starts from an empty pore (stale-slot moves, quirk Q12, force serial rounds) and fills it."""
+    arrays, meta = golden
+    s = system_from_meta(meta["c1"]["system"])
+    s.n_equil_sets = 2
+    if start == "bulk":          # periodic in z, GCMC
+        s = system_from_meta(meta["bulk_trace"]["system"])
+        s.n_equil_sets = 2
+        s.n_swap, s.mu = 1, -1100.0
+        x, y, z = arrays["bulk_x"], arrays["bulk_y"], arrays["bulk_z"]
+    elif start == "dense":
+        x, y, z = arrays["c1_x"], arrays["c1_y"], arrays["c1_z"]
+    else:
+        x = y = z = np.zeros(0)
+    nch, sets, sps = 3, 4, 5003
+    out = []
+    for spec in (0, 1):
+        with mcpm.Engine(nch, 1024) as e:
+            e.use_speculation(spec)
+            e.set_system(s)
+            for c in range(nch):
+                e.set_positions(c, x, y, z)
+            stats, tr = e.run(1, sets, sps, seed=424242, trace=True, threads=64 if not spec else 0, check_energy=1)
+            out.append((tr.copy(), [e.get_positions(c) for c in range(nch)], stats))
+    for c in range(nch):
+        assert first_divergence(out[0][0][c], out[1][0][c]) == -1
+        for a, b in zip(out[0][1][c], out[1][1][c]):
+            assert np.array_equal(a, b)
+        p, q = out[0][2][c], out[1][2][c]
+        for f in ("n", "dr", "acceptance", "rejection", "n_displacements", "accept_swap", "reject_swap", "n_swaps", "tot_disp", "tot_disp_acc",
+                  "tot_ins", "tot_ins_acc", "tot_del", "tot_del_acc", "tot_empty", "steps_done", "samples", "sum_n", "sum_n2", "pair_evals_algorithmic"):
+            assert getattr(p, f) == getattr(q, f), f
+        assert q.sum_e == pytest.approx(p.sum_e, rel=RTOL) and q.sum_e2 == pytest.approx(p.sum_e2, rel=RTOL)
+        assert q.energy == pytest.approx(q.energy_check, rel=RTOL, abs=1e-9)
+        assert q.energy == pytest.approx(p.energy, rel=RTOL, abs=1e-9)
+    if start == "empty":
+        assert out[1][2][0].tot_empty > 0 and out[1][2][0].n > 0
+
+
+def test_speculation_is_chosen_for_few_chains_only(mcpm, golden):
+    """Automatic mode: a context with no more chains than SMs runs the speculative kernel (its executed evaluation count
+    includes discarded candidates, so it differs from the standard kernel's), a caller-fixed thread count does not."""
+    arrays, meta = golden
+    s = system_from_meta(meta["c1"]["system"])
+    x, y, z = arrays["c1_x"], arrays["c1_y"], arrays["c1_z"]
+    evals = {}
+    for mode, threads in (("auto", 0), ("off", 0), ("fixed", 128)):
+        with mcpm.Engine(2, 1024) as e:
+            if mode == "off":
+                e.use_speculation(0)
+            e.set_system(s)
+            for c in range(2):
+                e.set_positions(c, x, y, z)
+            st = e.run(50, 1, 4000, seed=3, threads=threads)
+            evals[mode] = (st[0].pair_evals, st[0].pair_evals_algorithmic, st[0].n)
+    assert evals["auto"][1:] == evals["off"][1:] == evals["fixed"][1:]
+    assert evals["off"][0] == evals["fixed"][0]
+    assert evals["auto"][0] > evals["off"][0]
 
 
 @pytest.mark.parametrize("packed", [True, False], ids=["subwarp", "onewarp"])
