@@ -11,6 +11,13 @@
 // A warp scans all partners of its candidate alone (old energies come from the per-particle energy cache, so a
 // candidate costs at most one scan); the commit of the accepted move (second pass over the partners) uses the whole CTA.
 //
+// Critical path of a round: read 8 uniforms from a shared-memory ring -> scan -> Metropolis -> publish {type, accepted}
+// as ONE BYTE per candidate -> barrier -> every thread loads the 8 (16) bytes as one word and finds the first accepted
+// candidate with a bit scan -> commit.  Everything else lives in an extra BOOKKEEPING warp that evaluates no candidate:
+// its lane 0 keeps the per-set counters, the trace, the production accumulators and the stale-slot writes of rejected
+// insertions, and the whole warp refills the uniform ring (Philox4x32-10 for the steps 2*KW ahead) while the candidate
+// warps are already evaluating the next round.
+//
 // Restates the same reference code as chain_loop in mcpm_kernels.cu: step loop src/main.cpp:66-71, MoveParticle
 // src/moves.cpp:118-186, SwapParticle src/moves.cpp:284-341, ResetStats src/MC.cpp:81-98, AdjustMCMoves src/moves.cpp:68-78.
 #include <algorithm>
@@ -41,6 +48,11 @@ struct StepPhilox {
     }
     template <int K>
     __device__ __forceinline__ double at() const { return __shfl_sync(MCPM_FULL_MASK, (K & 1) ? ub : ua, K >> 1); }
+};
+struct StepRing {        // uniforms prepared by the bookkeeping warp
+    const double* u;
+    template <int K>
+    __device__ __forceinline__ double at() const { return u[K]; }
 };
 struct StepReplay {
     const double* u;
@@ -107,16 +119,20 @@ __device__ __forceinline__ Cand evaluate_candidate(const Draws& rng, const Chain
 }  // namespace
 
 template <int RNG_MODE, bool PBZ, int KW>
-__global__ void __launch_bounds__(32 * KW, 1) k2_spec(const ChainParams* __restrict__ params, ChainState* __restrict__ states,
-                                                      const int* __restrict__ order, double* X, double* Y, double* Z, RunArgs a) {
+__global__ void __launch_bounds__(32 * (KW + 1), 1) k2_spec(const ChainParams* __restrict__ params, ChainState* __restrict__ states,
+                                                            const int* __restrict__ order, double* X, double* Y, double* Z, RunArgs a) {
+    constexpr int RS = 2 * KW;                       // ring of prepared uniforms, in steps
     extern __shared__ double smem[];
     __shared__ ChainParams P;
     __shared__ ChainState S;
     __shared__ Cand cand[2][KW];                     // double-buffered by round parity: a round needs ONE barrier
+    __shared__ __align__(16) unsigned char code[2][16];   // type | accepted << 3 of every candidate of the round
+    __shared__ __align__(16) double ring[RS][8];
     __shared__ unsigned long long rpos[KW + 1];      // replay mode: stream position of every candidate of the round
+    __shared__ double sh_dr;
     const int chain = order[blockIdx.x];
     const int cap = a.cap;
-    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, W = KW + 1;
     double* xs = smem;
     double* ys = smem + cap;
     double* zs = smem + 2 * cap;
@@ -125,11 +141,10 @@ __global__ void __launch_bounds__(32 * KW, 1) k2_spec(const ChainParams* __restr
     __syncthreads();
     const size_t off = (size_t)chain * (size_t)cap;
     for (int j = tid; j < cap; j += T) { xs[j] = X[off + j]; ys[j] = Y[off + j]; zs[j] = Z[off + j]; }
-    __syncthreads();
 
-    const bool lead = (tid == 0);
+    const bool book = (tid == 32 * KW);              // lane 0 of the bookkeeping warp; the only writer of S.st
     const PairGeom g = make_geom<true>(P);
-    mcpm_chain_stats& st = S.st;                     // shared memory; written by thread 0 only
+    mcpm_chain_stats& st = S.st;
     double* ep = a.ep + off;
     unsigned char* trace = a.trace ? a.trace + (unsigned long long)chain * a.trace_stride : nullptr;
     const double* replay = (RNG_MODE == MCPM_RNG_REPLAY) ? a.replay_u + (unsigned long long)chain * a.replay_stride : nullptr;
@@ -139,21 +154,39 @@ __global__ void __launch_bounds__(32 * KW, 1) k2_spec(const ChainParams* __restr
     unsigned long long step = st.steps_done, rcur = 0ull;
     int overflow = 0, par = 0;
     const int steps_per_set = (int)a.steps_per_set;
+    unsigned long long filled = step;                // the ring holds the uniforms of steps [.., filled)
+    // Bookkeeping warp: prepare the uniforms of the steps below `upto` (at most RS ahead of the oldest step still needed).
+    auto refill = [&](unsigned long long upto) {
+        while (filled < upto) {
+            const unsigned long long stp = filled + (unsigned long long)(lane >> 2);
+            if (stp < upto) {
+                double ua, ub;
+                philox_call(a.seed, (uint32_t)chain, 4ull * stp + (unsigned long long)(lane & 3), ua, ub);
+                double* slot = &ring[(int)(stp & (unsigned long long)(RS - 1))][2 * (lane & 3)];
+                slot[0] = ua; slot[1] = ub;
+            }
+            filled = (filled + 8ull < upto) ? filled + 8ull : upto;
+        }
+    };
+    if (RNG_MODE == MCPM_RNG_PHILOX && warp == KW) refill(step + (unsigned long long)RS);
+    __syncthreads();
 
     {   // energy cache: reuse the previous launch's if the configuration is unchanged, else rebuild (see chain_loop)
-        const unsigned long long sum = config_checksum<true>(xs, ys, zs, n, (unsigned long long*)partials, tid, T, lane, warp, KW);
+        const unsigned long long sum = config_checksum<true>(xs, ys, zs, n, (unsigned long long*)partials, tid, T, lane, warp, W);
         if (!(S.cache_valid && S.cache_sum == sum)) {
             double cp, cw;
-            cache_fill<true, PBZ, true>(xs, ys, zs, ep, n, P, g, partials, KW, warp, lane, tid, T, cp, cw);
+            cache_fill<true, PBZ, true>(xs, ys, zs, ep, n, P, g, partials, W, warp, lane, tid, T, cp, cw);
             e_pair = cp; e_wall = cw;
-            if (lead) st.pair_evals += (unsigned long long)n * (unsigned long long)n;
+            if (book) st.pair_evals += (unsigned long long)n * (unsigned long long)n;
         }
     }
 
-    SetCounters sc;
+    SetCounters sc;                                  // meaningful in the bookkeeping thread only
+    double sum_n = st.sum_n, sum_n2 = st.sum_n2, sum_e = st.sum_e, sum_e2 = st.sum_e2;
+    unsigned long long samples = st.samples;
     for (int set = a.first_set; set < a.first_set + a.n_sets && !overflow; set++) {
         sc.reset();                                  // MC::ResetStats, src/MC.cpp:81-98
-        if (lead) { st.widom_insert = st.widom_delete = 0.0; st.widom_insertions = st.widom_deletions = 1; }
+        if (book) { st.widom_insert = st.widom_delete = 0.0; st.widom_insertions = st.widom_deletions = 1; }
         const bool production = set > P.n_equil;
         int s = 0;
         while (s < steps_per_set && !overflow) {
@@ -172,62 +205,58 @@ __global__ void __launch_bounds__(32 * KW, 1) k2_spec(const ChainParams* __restr
                 }
                 __syncthreads();
             }
-            // ---- every warp evaluates one candidate step against the current configuration ----
+            // ---- every candidate warp evaluates one step against the current configuration ----
             if (warp < B) {
                 Cand c;
                 if (RNG_MODE == MCPM_RNG_PHILOX) {
-                    StepPhilox rng; rng.load(a.seed, (uint32_t)chain, step + (unsigned long long)warp, lane);
-                    c = evaluate_candidate<StepPhilox, PBZ>(rng, P, g, xs, ys, zs, ep, n, cap, dr, lane);
+                    StepRing rng; rng.u = ring[(int)((step + (unsigned long long)warp) & (unsigned long long)(RS - 1))];
+                    c = evaluate_candidate<StepRing, PBZ>(rng, P, g, xs, ys, zs, ep, n, cap, dr, lane);
                 } else {
                     StepReplay rng; rng.u = replay; rng.pos = rpos[warp]; rng.n = a.replay_stride;
                     c = evaluate_candidate<StepReplay, PBZ>(rng, P, g, xs, ys, zs, ep, n, cap, dr, lane);
                 }
-                if (lane == 0) cand[par][warp] = c;
+                if (lane == 0) { cand[par][warp] = c; code[par][warp] = (unsigned char)(c.type | (c.acc << 3)); }
+            } else if (warp < KW && lane == 0) {
+                code[par][warp] = 0;
             }
             __syncthreads();
+            // ---- the first accepted candidate wins; everything before it is a rejected step that stands ----
+            const unsigned long long lo = *reinterpret_cast<const unsigned long long*>(&code[par][0]);
+            const unsigned long long hi = (KW > 8) ? *reinterpret_cast<const unsigned long long*>(&code[par][8]) : 0ull;
             const Cand* cd = cand[par];
             par ^= 1;
-            // ---- the first accepted candidate wins; everything before it is a rejected step that stands ----
-            int kstar = -1;
-            for (int w = B - 1; w >= 0; w--) if (cd[w].acc) kstar = w;
-            const bool stop = (kstar >= 0 && cd[kstar].type == CAND_OVERFLOW);
+            const unsigned long long alo = lo & 0x0808080808080808ull, ahi = hi & 0x0808080808080808ull;
+            const int kstar = alo ? ((__ffsll((long long)alo) - 1) >> 3) : (ahi ? 8 + ((__ffsll((long long)ahi) - 1) >> 3) : -1);
+            auto code_of = [&](int w) { return (int)(((w < 8) ? (lo >> (8 * w)) : (hi >> (8 * (w - 8)))) & 0xFull); };
+            const int tk = (kstar >= 0) ? (code_of(kstar) & 7) : -1;
+            const bool stop = (tk == CAND_OVERFLOW);
             const int kept = stop ? kstar : (kstar >= 0 ? kstar + 1 : B);
-            int last_ins = -1;
-            for (int w = 0; w < B; w++) {            // counters (replicated in every thread)
-                const int ty = cd[w].type;
-                if (ty == CAND_TRANS || ty == CAND_INS) sc.evals += (unsigned long long)n;   // executed, kept or not
-                if (w >= kept) continue;
-                const int ac = cd[w].acc;
-                if (ty == CAND_TRANS) { sc.n_disp++; sc.acc_disp += ac; sc.alg += 2ull * (unsigned long long)n; }
-                else if (ty == CAND_INS) { sc.n_ins++; sc.acc_ins += ac; sc.alg += (unsigned long long)n; last_ins = w; }
-                else if (ty == CAND_DEL) { sc.n_del++; sc.acc_del += ac; sc.alg += (unsigned long long)n; }
-                else if (ty == CAND_EMPTY) sc.n_empty++;
-            }
-            // the trial position of an insertion attempt stays in the first free slot even if rejected (src/moves.cpp:302-303)
-            if (last_ins >= 0 && tid == 0) { xs[n] = cd[last_ins].px; ys[n] = cd[last_ins].py; zs[n] = cd[last_ins].pz; }
             const int n_before = n;
             const double e_before = e_pair + e_wall;
+            unsigned long long commit_evals = 0ull;
             // ---- commit the accepted move with the whole CTA ----
             if (kstar >= 0 && !stop) {
-                const Cand c = cd[kstar];
+                const Cand& c = cd[kstar];
                 bool big = false;
-                if (c.type == CAND_TRANS) {
+                if (tk == CAND_TRANS) {
                     const int i = c.idx;
-                    big = cache_apply<true, PBZ>(xs, ys, zs, ep, n, i, g, true, c.ox, c.oy, c.oz, true, c.px, c.py, c.pz, tid, T);
-                    if (tid == 0) { ep[i] = c.v; xs[i] = c.px; ys[i] = c.py; zs[i] = c.pz; }   // readers of slot i mask it out (self)
+                    const double px = c.px, py = c.py, pz = c.pz;
+                    big = cache_apply<true, PBZ>(xs, ys, zs, ep, n, i, g, true, c.ox, c.oy, c.oz, true, px, py, pz, tid, T);
+                    if (tid == 0) { ep[i] = c.v; xs[i] = px; ys[i] = py; zs[i] = pz; }         // readers of slot i mask it out (self)
                     if (n > 0) { e_pair += c.pn - c.po; e_wall += c.wn - c.wo; }   // full pair change (Q16); n == 0 moves a ghost (Q12)
-                    sc.evals += 2ull * (unsigned long long)n;
-                } else if (c.type == CAND_INS) {
-                    big = cache_apply<true, PBZ>(xs, ys, zs, ep, n, -1, g, false, 0., 0., 0., true, c.px, c.py, c.pz, tid, T);
-                    if (tid == 0) ep[n] = c.v;
+                    commit_evals = 2ull * (unsigned long long)n;
+                } else if (tk == CAND_INS) {
+                    const double px = c.px, py = c.py, pz = c.pz;
+                    big = cache_apply<true, PBZ>(xs, ys, zs, ep, n, -1, g, false, 0., 0., 0., true, px, py, pz, tid, T);
+                    if (tid == 0) { ep[n] = c.v; xs[n] = px; ys[n] = py; zs[n] = pz; }
                     e_pair += c.pn; e_wall += c.wn;
-                    sc.evals += (unsigned long long)n;
+                    commit_evals = (unsigned long long)n;
                     n++;
                 } else {                                                            // CAND_DEL: swap-with-last, src/moves.cpp:329
                     const int o = c.idx;
                     const double xl = xs[n - 1], yl = ys[n - 1], zl = zs[n - 1];
                     big = cache_apply<true, PBZ>(xs, ys, zs, ep, n, o, g, true, c.ox, c.oy, c.oz, false, 0., 0., 0., tid, T);
-                    sc.evals += (unsigned long long)n;
+                    commit_evals = (unsigned long long)n;
                     __syncthreads();                                                // entry n-1 is final, everyone has read slot n-1
                     if (tid == 0) { ep[o] = ep[n - 1]; xs[o] = xl; ys[o] = yl; zs[o] = zl; }
                     e_pair -= c.po; e_wall -= c.wo;
@@ -235,55 +264,72 @@ __global__ void __launch_bounds__(32 * KW, 1) k2_spec(const ChainParams* __restr
                 }
                 if (__syncthreads_or(big ? 1 : 0)) {   // a hard overlap went through the cache: rebuild it
                     double cp, cw;
-                    cache_fill<true, PBZ, true>(xs, ys, zs, ep, n, P, g, partials, KW, warp, lane, tid, T, cp, cw);
+                    cache_fill<true, PBZ, true>(xs, ys, zs, ep, n, P, g, partials, W, warp, lane, tid, T, cp, cw);
                     e_pair = cp; e_wall = cw;
-                    sc.evals += (unsigned long long)n * (unsigned long long)n;
-                }
-            }
-            // ---- trace and production accumulators of the kept steps, in step order ----
-            if (lead) {
-                for (int w = 0; w < kept; w++) {
-                    const int ty = cd[w].type, ac = cd[w].acc;
-                    if (trace) {
-                        const int code = ty == CAND_TRANS ? ac : (ty == CAND_INS ? (2 | ac) : (ty == CAND_DEL ? (4 | ac) : (ty == CAND_EMPTY ? 6 : 8)));
-                        trace[(unsigned long long)(set - a.first_set) * (unsigned long long)a.steps_per_set + (unsigned long long)(s + w)] = (unsigned char)code;
-                    }
-                    if (production) {
-                        const bool after = (w == kstar);                            // only the accepted step sees the new state
-                        const double dn = (double)(after ? n : n_before), e = after ? (e_pair + e_wall) : e_before;
-                        st.sum_n += dn; st.sum_n2 += dn * dn; st.sum_e += e; st.sum_e2 += e * e;
-                        st.samples++;
-                    }
+                    commit_evals += (unsigned long long)n * (unsigned long long)n;
                 }
             }
             if (RNG_MODE == MCPM_RNG_REPLAY) rcur = rpos[kept];
             step += (unsigned long long)(kept + (stop ? 1 : 0));
+            // ---- off the critical path: uniforms of later rounds, counters, trace, accumulators ----
+            if (warp == KW) {
+                if (RNG_MODE == MCPM_RNG_PHILOX) refill(step + (unsigned long long)RS);
+                if (book) {
+                    sc.evals += commit_evals;
+                    int last_ins = -1;
+                    for (int w = 0; w < B; w++) {
+                        const int cw = code_of(w), ty = cw & 7, ac = cw >> 3;
+                        if (ty == CAND_TRANS || ty == CAND_INS) sc.evals += (unsigned long long)n_before;   // executed, kept or not
+                        if (w >= kept) continue;
+                        if (ty == CAND_TRANS) { sc.n_disp++; sc.acc_disp += ac; sc.alg += 2ull * (unsigned long long)n_before; }
+                        else if (ty == CAND_INS) { sc.n_ins++; sc.acc_ins += ac; sc.alg += (unsigned long long)n_before; last_ins = w; }
+                        else if (ty == CAND_DEL) { sc.n_del++; sc.acc_del += ac; sc.alg += (unsigned long long)n_before; }
+                        else if (ty == CAND_EMPTY) sc.n_empty++;
+                        if (trace) {
+                            const int tc = ty == CAND_TRANS ? ac : (ty == CAND_INS ? (2 | ac) : (ty == CAND_DEL ? (4 | ac) : (ty == CAND_EMPTY ? 6 : 8)));
+                            trace[(unsigned long long)(set - a.first_set) * (unsigned long long)a.steps_per_set + (unsigned long long)(s + w)] = (unsigned char)tc;
+                        }
+                        if (production) {
+                            const bool after = (w == kstar);                        // only the accepted step sees the new state
+                            const double dn = (double)(after ? n : n_before), e = after ? (e_pair + e_wall) : e_before;
+                            sum_n += dn; sum_n2 += dn * dn; sum_e += e; sum_e2 += e * e;
+                            samples++;
+                        }
+                    }
+                    // the trial position of a rejected insertion attempt stays in the first free slot (src/moves.cpp:302-303)
+                    if (last_ins >= 0 && last_ins != kstar) { xs[n_before] = cd[last_ins].px; ys[n_before] = cd[last_ins].py; zs[n_before] = cd[last_ins].pz; }
+                }
+            }
             s += kept;
             if (stop) overflow = 1;
             if (RNG_MODE == MCPM_RNG_REPLAY || n_before == 0 || n == 0) __syncthreads();   // rpos[] / slot 0 are reused at once
         }
         // MC::AdjustMCMoves displacement part, src/moves.cpp:68-78 (ResetStats starts nDisplacements at ONE)
-        if (!overflow && n > 0 && set <= P.n_equil) {
-            const double ratio = (double)sc.acc_disp * 1. / (1. * (double)(sc.n_disp + 1));
-            if (ratio < 0.2) dr /= 1.1;
-            else dr *= 1.1;
-        }
-        if (lead) {
+        if (book) {
+            if (!overflow && n > 0 && set <= P.n_equil) {
+                const double ratio = (double)sc.acc_disp * 1. / (1. * (double)(sc.n_disp + 1));
+                if (ratio < 0.2) dr /= 1.1;
+                else dr *= 1.1;
+            }
+            sh_dr = dr;
             st.acceptance = sc.acc_disp; st.rejection = sc.n_disp - sc.acc_disp; st.n_displacements = 1 + sc.n_disp;
             st.accept_swap = sc.acc_ins + sc.acc_del; st.reject_swap = (sc.n_ins + sc.n_del) - (sc.acc_ins + sc.acc_del);
             st.n_swaps = 1 + sc.n_ins + sc.n_del;
             st.tot_disp += sc.n_disp; st.tot_disp_acc += sc.acc_disp; st.tot_ins += sc.n_ins; st.tot_ins_acc += sc.acc_ins;
             st.tot_del += sc.n_del; st.tot_del_acc += sc.acc_del; st.tot_empty += sc.n_empty; st.pair_evals += sc.evals; st.pair_evals_algorithmic += sc.alg;
         }
+        __syncthreads();
+        dr = sh_dr;
     }
     __syncthreads();
 
     double c_pair = 0.0, c_wall = 0.0;
-    if (a.check_energy) cache_fill<true, PBZ, true>(xs, ys, zs, ep, n, P, g, partials, KW, warp, lane, tid, T, c_pair, c_wall);
-    const unsigned long long end_sum = config_checksum<true>(xs, ys, zs, n, (unsigned long long*)partials, tid, T, lane, warp, KW);
-    if (lead) {
+    if (a.check_energy) cache_fill<true, PBZ, true>(xs, ys, zs, ep, n, P, g, partials, W, warp, lane, tid, T, c_pair, c_wall);
+    const unsigned long long end_sum = config_checksum<true>(xs, ys, zs, n, (unsigned long long*)partials, tid, T, lane, warp, W);
+    if (book) {
         st.n = n; st.overflow = overflow; st.dr = dr; st.steps_done = step;
         st.pair = e_pair; st.wall = e_wall; st.energy = e_pair + e_wall;
+        st.sum_n = sum_n; st.sum_n2 = sum_n2; st.sum_e = sum_e; st.sum_e2 = sum_e2; st.samples = samples;
         if (a.check_energy) { st.pair_check = c_pair; st.wall_check = c_wall; st.energy_check = c_pair + c_wall; }
         if (a.check_energy == 2) { st.pair = c_pair; st.wall = c_wall; st.energy = c_pair + c_wall; }
         S.replay_pos = rcur; st.replay_consumed = rcur;
@@ -291,22 +337,28 @@ __global__ void __launch_bounds__(32 * KW, 1) k2_spec(const ChainParams* __restr
     }
     __syncthreads();
     for (int j = tid; j < cap; j += T) { X[off + j] = xs[j]; Y[off + j] = ys[j]; Z[off + j] = zs[j]; }
-    if (tid == 0) states[chain] = S;
+    if (book) states[chain] = S;
 }
 
 size_t k2_spec_smem_bytes(int cap) { return (size_t)(3 * cap + 128) * sizeof(double); }
 
-cudaError_t launch_k2_spec(int rng_mode, bool pbz, int n_chains, const ChainParams* params, ChainState* states, const int* order, double* X,
-                           double* Y, double* Z, const RunArgs& a, cudaStream_t stream) {
+cudaError_t launch_k2_spec(int rng_mode, bool pbz, int width, int n_chains, const ChainParams* params, ChainState* states, const int* order,
+                           double* X, double* Y, double* Z, const RunArgs& a, cudaStream_t stream) {
     const size_t smem = k2_spec_smem_bytes(a.cap);
-    auto go = [&](auto kern) -> cudaError_t {
+    auto go = [&](auto kern, int threads) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kern<<<n_chains, 256, smem, stream>>>(params, states, order, X, Y, Z, a);
+        kern<<<n_chains, threads, smem, stream>>>(params, states, order, X, Y, Z, a);
         return cudaGetLastError();
     };
-    if (rng_mode == MCPM_RNG_PHILOX) return pbz ? go(k2_spec<MCPM_RNG_PHILOX, true, 8>) : go(k2_spec<MCPM_RNG_PHILOX, false, 8>);
-    return pbz ? go(k2_spec<MCPM_RNG_REPLAY, true, 8>) : go(k2_spec<MCPM_RNG_REPLAY, false, 8>);
+#define MCPM_SPEC(R, Z, K) go(k2_spec<R, Z, K>, 32 * (K + 1))
+    if (width == 16) {
+        if (rng_mode == MCPM_RNG_PHILOX) return pbz ? MCPM_SPEC(MCPM_RNG_PHILOX, true, 16) : MCPM_SPEC(MCPM_RNG_PHILOX, false, 16);
+        return pbz ? MCPM_SPEC(MCPM_RNG_REPLAY, true, 16) : MCPM_SPEC(MCPM_RNG_REPLAY, false, 16);
+    }
+    if (rng_mode == MCPM_RNG_PHILOX) return pbz ? MCPM_SPEC(MCPM_RNG_PHILOX, true, 8) : MCPM_SPEC(MCPM_RNG_PHILOX, false, 8);
+    return pbz ? MCPM_SPEC(MCPM_RNG_REPLAY, true, 8) : MCPM_SPEC(MCPM_RNG_REPLAY, false, 8);
+#undef MCPM_SPEC
 }
 
 }  // namespace mcpm

@@ -20,10 +20,11 @@ print("chains", nchains, "steps", S)
 for k in (0, 5, 12, 27, 39):
     x, y, z = g[f"x{k}"], g[f"y{k}"], g[f"z{k}"]
     row = []
-    for T in (32, 64, 128, 256, 512, "spec"):
+    for T in (32, 128, 256, "spec8", "spec16"):
         with m.Engine(nchains, 768) as e:
-            e.use_speculation(1 if T == "spec" else 0)
-            if T == "spec":
+            label = T
+            e.use_speculation(int(T[4:]) if isinstance(T, str) else 0)
+            if isinstance(T, str):
                 T = 0
             e.set_system(workloads.argon_slit(mu=float(g["mu"][k]), n_equil_sets=0))
             for c in range(nchains):
@@ -33,5 +34,5 @@ for k in (0, 5, 12, 27, 39):
             st = e.run(2, 1, S, seed=1, threads=T)
             ms = e.last_kernel_ms()
             evals = sum(int(s.pair_evals) for s in st)
-            row.append("T=%s: %.2f us/step (%.3g evals/s)" % (T or "spec", 1e3 * ms / S, evals / (ms * 1e-3) if False else (evals - 0) / (ms * 1e-3)))
+            row.append("T=%s: %.2f us/step (%.3g evals/s)" % (label, 1e3 * ms / S, evals / (ms * 1e-3) if False else (evals - 0) / (ms * 1e-3)))
     print("point", k, "N=%d" % len(x), " | ".join(row))
