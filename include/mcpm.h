@@ -187,7 +187,7 @@ int mcpm_use_subwarp(mcpm_ctx* ctx, int enable);
  * uniforms per step index, same decisions, same trace).  mode -1 (default): chosen automatically when the context has
  * no more chains than the device has SMs, threads_per_chain is 0 and the energy cache is in use; 0: never; 1: whenever
  * the launch qualifies (energy cache enabled, coordinates inside the box, no in-kernel sampling, shared-memory
- * positions); 8 or 16: like 1 with that many candidate steps per round.  Replaces nothing in the reference: it is a schedule of src/main.cpp:66-71. */
+ * positions).  Replaces nothing in the reference: it is a schedule of src/main.cpp:66-71. */
 int mcpm_use_speculation(mcpm_ctx* ctx, int mode);
 int mcpm_reset_accumulators(mcpm_ctx* ctx);
 /* Accumulated pair-distance histogram of one chain: hist[0..99] = MC::Stats::rdf(0..99) (bin 0 is never filled,

@@ -52,7 +52,7 @@ struct mcpm_ctx {
     double *d_sx = nullptr, *d_sy = nullptr, *d_sz = nullptr;
     int use_cells = 1;             // 0 disables the cell-list path (tests compare both)
     int use_cache = 1;             // per-particle energy cache in K2 (mcpm_use_energy_cache)
-    int use_spec = -1;             // speculative-moves kernel (mcpm_spec.cu): -1 = automatic (fewer chains than SMs), 0 = never, 1/8/16 = whenever possible (candidates per round)
+    int use_spec = -1;             // speculative-moves kernel (mcpm_spec.cu): -1 = automatic (fewer chains than SMs), 0 = never, 1 = whenever possible
     int use_subwarp = 0;           // opt-in: the sub-warp kernel that packs 2 or 4 small chains into one warp (mcpm_use_subwarp)
     int2* d_ctas = nullptr;        // CTA descriptors of the sub-warp kernel, n_chains entries
     int* d_flags = nullptr;        // 2*n_chains ints: particle counts in, in-box flags out (bulk uploads)
@@ -588,7 +588,7 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     const bool use_sub = c->use_subwarp && threads == 32 && cache_now && all_fast && !sample && !global_path && same_pbz;
     CU(cudaEventRecord(c->ev0, c->stream));
     if (use_spec) {
-        CU(launch_k2_spec(p->rng_mode, c->h_params[0].pbc[2] != 0, c->use_spec == 16 ? 16 : 8, c->n_chains, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->stream));
+        CU(launch_k2_spec(p->rng_mode, c->h_params[0].pbc[2] != 0, c->n_chains, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->stream));
         c->launches++;
     } else if (use_sub) {
         const int cap_cta = ((c->cap + 127) / 128) * 128;
@@ -704,8 +704,7 @@ int mcpm_set_running_energy(mcpm_ctx* c, const double* pair, const double* wall)
 
 int mcpm_use_speculation(mcpm_ctx* c, int mode) {
     if (!c) return fail(MCPM_ERR_ARG, "null context");
-    if (mode != -1 && mode != 0 && mode != 1 && mode != 8 && mode != 16)
-        return fail(MCPM_ERR_ARG, "speculation mode must be -1 (automatic), 0 (off), 1 (on) or the number of candidate steps per round (8, 16)");
+    if (mode < -1 || mode > 1) return fail(MCPM_ERR_ARG, "speculation mode must be -1 (automatic), 0 (off) or 1 (on)");
     c->use_spec = mode;
     return MCPM_OK;
 }

@@ -55,6 +55,30 @@ __device__ __forceinline__ double pair_sum1(const double* xs, const double* ys, 
     return (s0 + s1) + (s2 + s3);
 }
 
+// Latency-oriented scan for a single warp (or a few) per position: U independent partner evaluations in flight per
+// thread and NO serial tail — slots past n are evaluated on a clamped index and mask themselves out (self := j), so a
+// chain of N <= U*T particles is one straight-line block of U interleaved dependency chains.
+template <bool FAST, bool PBZ, int U>
+__device__ __forceinline__ double pair_sum_wide(const double* xs, const double* ys, const double* zs, int n, int self, const PairGeom& g,
+                                                double xa, double ya, double za, int tid, int T) {
+    double acc[U];
+#pragma unroll
+    for (int k = 0; k < U; k++) acc[k] = 0.0;
+    for (int j0 = tid; j0 < n; j0 += U * T) {
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            const int j = j0 + k * T;
+            const int jc = min(j, n - 1);
+            pair_acc(acc[k], dist2<FAST, PBZ>(g, xa, ya, za, xs[jc], ys[jc], zs[jc]), g, j, (j < n) ? self : j);
+        }
+    }
+#pragma unroll
+    for (int w = 1; w < U; w *= 2)
+#pragma unroll
+        for (int k = 0; k + w < U; k += 2 * w) acc[k] += acc[k + w];
+    return acc[0];
+}
+
 // All-reduce of NV per-thread values over the CTA; every thread returns the same bits.
 template <int NV, bool MULTI>
 __device__ __forceinline__ void cta_allsum(double (&v)[NV], double* partials, int parity, int W, int warp, int lane) {

@@ -270,21 +270,38 @@ __device__ __forceinline__ double wrap_select(double x, double L, bool& odd) {
 // has probability 1e-16), so ln f >= 0 always accepts and ln f < -37 (< ln of the smallest non-zero uniform) always
 // rejects; only in between is f evaluated, with the reference's own expression.  All inputs are identical in every
 // thread, so the branches are warp-uniform.
+// In between, a single-precision screen decides all but ~1e-4 of the cases: f32 = exp(t) evaluated with ex2.approx
+// carries a relative error < 1e-5 for |t| <= 58 (CUDA documents 2 + floor(1.16|t|) ulp for __expf, plus the rounding of
+// t to float and one multiply/divide), so u outside f32 (1 +- 1e-4) has the same outcome as the exact test; only inside
+// that band is the reference's fp64 expression evaluated.  The decision is therefore always the reference's.
+#define MCPM_SCREEN 1e-4
+__device__ __forceinline__ int screen(double u, float f32) {   // +1 accept, -1 reject, 0 undecided
+    const double e = (double)f32;
+    if (u < e * (1.0 - MCPM_SCREEN)) return 1;
+    if (u > e * (1.0 + MCPM_SCREEN)) return -1;
+    return 0;
+}
 __device__ __forceinline__ bool metropolis_translation(double u, double arg /* dE/T */) {
     if (!(arg > 0.0)) return arg == arg;               // downhill: always (NaN: never, as u < NaN is false)
     if (arg > 37.0) return u == 0.0 && exp(-arg) > 0.0;
+    const int sc = screen(u, __expf(-(float)arg));
+    if (sc != 0) return sc > 0;
     return u < exp(-arg);
 }
 __device__ __forceinline__ bool metropolis_insertion(double u, double x /* -E/T */, double ln_zzV, double zzV, int n) {
     const double t = ln_zzV + x;                        // ln f = t - ln(n+1), 0 <= ln(n+1) < 21
     if (t >= 21.0) return true;
     if (!(t >= -37.0)) return (t == t) && u == 0.0 && zzV * exp(x) / (double)(n + 1) > 0.0;
+    const int sc = screen(u, __fdividef(__expf((float)t), (float)(n + 1)));
+    if (sc != 0) return sc > 0;
     return u < zzV * exp(x) / (double)(n + 1);          // src/moves.cpp:306
 }
 __device__ __forceinline__ bool metropolis_deletion(double u, double y /* E/T */, double ln_zzV, double zzV, int n) {
     const double t = y - ln_zzV;                        // ln f = t + ln(n), 0 <= ln(n) < 21
     if (t >= 0.0) return true;
     if (!(t >= -58.0)) return (t == t) && u == 0.0 && (double)n * exp(y) / zzV > 0.0;
+    const int sc = screen(u, (float)n * __expf((float)t));
+    if (sc != 0) return sc > 0;
     return u < (double)n * exp(y) / zzV;                // src/moves.cpp:326
 }
 

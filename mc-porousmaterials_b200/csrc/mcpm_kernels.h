@@ -23,9 +23,9 @@ size_t k2_sub_smem_bytes(int cap_cta);
 cudaError_t launch_k2_sub(int rng_mode, bool pbz, int n_ctas, const ChainParams* params, ChainState* states, const int* order, const int2* ctas,
                           double* X, double* Y, double* Z, const RunArgs& a, int cap_cta, cudaStream_t stream);
 
-// mcpm_spec.cu: speculative-moves kernel, one CTA of `width` (8 or 16) candidate warps + 1 bookkeeping warp per chain
+// mcpm_spec.cu: speculative-moves kernel, one CTA of 8 candidate warps + 2 helper warps per chain
 size_t k2_spec_smem_bytes(int cap);
-cudaError_t launch_k2_spec(int rng_mode, bool pbz, int width, int n_chains, const ChainParams* params, ChainState* states, const int* order,
+cudaError_t launch_k2_spec(int rng_mode, bool pbz, int n_chains, const ChainParams* params, ChainState* states, const int* order,
                            double* X, double* Y, double* Z, const RunArgs& a, cudaStream_t stream);
 
 cudaError_t launch_in_box(int n_chains, const ChainParams* params, const int* n_of, const double* X, const double* Y, const double* Z, int cap,

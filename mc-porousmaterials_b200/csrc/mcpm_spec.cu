@@ -12,11 +12,11 @@
 // candidate costs at most one scan); the commit of the accepted move (second pass over the partners) uses the whole CTA.
 //
 // Critical path of a round: read 8 uniforms from a shared-memory ring -> scan -> Metropolis -> publish {type, accepted}
-// as ONE BYTE per candidate -> barrier -> every thread loads the 8 (16) bytes as one word and finds the first accepted
-// candidate with a bit scan -> commit.  Everything else lives in an extra BOOKKEEPING warp that evaluates no candidate:
-// its lane 0 keeps the per-set counters, the trace, the production accumulators and the stale-slot writes of rejected
-// insertions, and the whole warp refills the uniform ring (Philox4x32-10 for the steps 2*KW ahead) while the candidate
-// warps are already evaluating the next round.
+// as ONE BYTE per candidate -> barrier -> every thread loads the 8 bytes as one word and finds the first accepted
+// candidate with a bit scan -> commit.  Everything else lives in two helper warps that evaluate no candidate and work
+// while the candidate warps are already in the next round: lane 0 of the BOOKKEEPING warp keeps the per-set counters
+// (popc over the code word: O(1) per round), the trace, the production accumulators and the stale-slot writes of
+// rejected insertions; the UNIFORMS warp refills the ring (Philox4x32-10 for the steps up to 2*KW ahead).
 //
 // Restates the same reference code as chain_loop in mcpm_kernels.cu: step loop src/main.cpp:66-71, MoveParticle
 // src/moves.cpp:118-186, SwapParticle src/moves.cpp:284-341, ResetStats src/MC.cpp:81-98, AdjustMCMoves src/moves.cpp:68-78.
@@ -30,7 +30,9 @@ namespace mcpm {
 
 namespace {
 
-enum { CAND_TRANS = 0, CAND_INS = 1, CAND_DEL = 2, CAND_EMPTY = 3, CAND_VOL = 4, CAND_OVERFLOW = 5 };
+// One-hot move types: the round's eight codes are read as one 64-bit word and counted with popc on bit planes.
+enum { CAND_TRANS = 0x01, CAND_INS = 0x02, CAND_DEL = 0x04, CAND_EMPTY = 0x08, CAND_VOL = 0x10, CAND_OVERFLOW = 0x20, CAND_ACCEPTED = 0x80 };
+#define MCPM_PLANE(b) (0x0101010101010101ull * (unsigned long long)(b))
 
 struct Cand {            // one warp's candidate step, published in shared memory
     int type, acc, idx, pad;
@@ -61,15 +63,33 @@ struct StepReplay {
     __device__ __forceinline__ double at() const { return (pos + K < n) ? __ldg(u + pos + K) : 0.0; }
 };
 
+#ifdef MCPM_SPEC_TIMING
+__device__ __forceinline__ long long spec_clock() {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory");
+    return t;
+}
+// clock read that cannot issue before x is available (the branch needs x)
+__device__ __forceinline__ long long spec_probe(double x) {
+    if (__double_as_longlong(x) == 0x7ff8dead00000001ll) asm volatile("trap;");
+    return spec_clock();
+}
+#define SPEC_PROBE(k, x) tp[k] = spec_probe(x)
+#else
+#define SPEC_PROBE(k, x)
+#endif
+
 // Evaluates one step read-only.  Called by one full warp; every lane returns the same candidate.
 template <class Draws, bool PBZ>
 __device__ __forceinline__ Cand evaluate_candidate(const Draws& rng, const ChainParams& P, const PairGeom& g, const double* xs, const double* ys,
-                                                   const double* zs, const double* ep, int n, int cap, double dr, int lane) {
+                                                   const double* zs, const double* ep, int n, int cap, double dr, int lane, long long* tp) {
     Cand c;
+    SPEC_PROBE(0, dr);
     c.type = CAND_EMPTY; c.acc = 0; c.idx = 0; c.pad = 0;
     c.px = c.py = c.pz = c.ox = c.oy = c.oz = c.v = c.po = c.pn = c.wo = c.wn = 0.0;
     const double r = rng.template at<0>() * P.wsum;                                       // src/main.cpp:67
     if (r <= P.thr_disp) {
+        SPEC_PROBE(1, r);
         const double u_i = rng.template at<3>(), u_x = rng.template at<4>(), u_y = rng.template at<5>(), u_z = rng.template at<6>(),
                      u_a = rng.template at<7>();
         const int i = (int)(u_i * (double)n);                                             // n == 0: the stale slot 0 (quirk Q12)
@@ -80,13 +100,19 @@ __device__ __forceinline__ Cand evaluate_candidate(const Draws& rng, const Chain
         bool odd = false;
         double xn = wrap_select(xr, P.L[0], odd), yn = wrap_select(yr, P.L[1], odd), zn = PBZ ? wrap_select(zr, P.L[2], odd) : zr;
         if (odd) { xn = wrap_floor(xr, P.L[0]); yn = wrap_floor(yr, P.L[1]); if (PBZ) zn = wrap_floor(zr, P.L[2]); }
-        double v = pair_sum1<true, PBZ>(xs, ys, zs, n, i, g, xn, yn, zn, lane, 32);
+        SPEC_PROBE(2, xn + yn + zn);
+        double v = (n <= 128) ? pair_sum_wide<true, PBZ, 4>(xs, ys, zs, n, i, g, xn, yn, zn, lane, 32)
+                              : pair_sum_wide<true, PBZ, 8>(xs, ys, zs, n, i, g, xn, yn, zn, lane, 32);
+        SPEC_PROBE(3, v);
         double wo, wn;
         wall_two(P, zo, zn, wo, wn, lane);
+        SPEC_PROBE(4, wo + wn);
         v = warp_allsum(v);
+        SPEC_PROBE(5, v);
         const double po = P.eps4 * ep_i, pn = P.eps4 * v;
         const double dE = (pn + wn) - (po + wo);                                          // src/moves.cpp:169
         c.type = CAND_TRANS; c.acc = metropolis_translation(u_a, dE * P.beta) ? 1 : 0; c.idx = i;
+        SPEC_PROBE(6, (double)c.acc);
         c.px = xn; c.py = yn; c.pz = zn; c.ox = xo; c.oy = yo; c.oz = zo; c.v = v; c.po = po; c.pn = pn; c.wo = wo; c.wn = wn;
     } else if (r <= P.thr_vol) {
         c.type = CAND_VOL;
@@ -95,7 +121,8 @@ __device__ __forceinline__ Cand evaluate_candidate(const Draws& rng, const Chain
         else {
             const double u_x = rng.template at<3>(), u_y = rng.template at<4>(), u_z = rng.template at<5>(), u_a = rng.template at<6>();
             const double xi = u_x * P.L[0], yi = u_y * P.L[1], zi = u_z * P.L[2];         // src/moves.cpp:46-54
-            double v = pair_sum1<true, PBZ>(xs, ys, zs, n, -1, g, xi, yi, zi, lane, 32);
+            double v = (n <= 128) ? pair_sum_wide<true, PBZ, 4>(xs, ys, zs, n, -1, g, xi, yi, zi, lane, 32)
+                                  : pair_sum_wide<true, PBZ, 8>(xs, ys, zs, n, -1, g, xi, yi, zi, lane, 32);
             double wi, wd;
             wall_two(P, zi, zi, wi, wd, lane);
             v = warp_allsum(v);
@@ -118,34 +145,37 @@ __device__ __forceinline__ Cand evaluate_candidate(const Draws& rng, const Chain
 
 }  // namespace
 
-template <int RNG_MODE, bool PBZ, int KW>
-__global__ void __launch_bounds__(32 * (KW + 1), 1) k2_spec(const ChainParams* __restrict__ params, ChainState* __restrict__ states,
-                                                            const int* __restrict__ order, double* X, double* Y, double* Z, RunArgs a) {
+template <int RNG_MODE, bool PBZ>
+__global__ void __launch_bounds__(32 * 10, 1) k2_spec(const ChainParams* __restrict__ params, ChainState* __restrict__ states,
+                                                      const int* __restrict__ order, double* X, double* Y, double* Z, RunArgs a) {
+    constexpr int KW = 8;                            // candidate warps = steps per round (one code byte each in a 64-bit word)
     constexpr int RS = 2 * KW;                       // ring of prepared uniforms, in steps
+    constexpr int W = KW + 2;                        // + bookkeeping warp (KW) + uniforms warp (KW + 1)
     extern __shared__ double smem[];
     __shared__ ChainParams P;
     __shared__ ChainState S;
     __shared__ Cand cand[2][KW];                     // double-buffered by round parity: a round needs ONE barrier
-    __shared__ __align__(16) unsigned char code[2][16];   // type | accepted << 3 of every candidate of the round
+    __shared__ __align__(8) unsigned char code[2][8];
     __shared__ __align__(16) double ring[RS][8];
     __shared__ unsigned long long rpos[KW + 1];      // replay mode: stream position of every candidate of the round
     __shared__ double sh_dr;
     const int chain = order[blockIdx.x];
     const int cap = a.cap;
-    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, W = KW + 1;
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
     double* xs = smem;
     double* ys = smem + cap;
     double* zs = smem + 2 * cap;
-    double* partials = smem + 3 * cap;               // 128 doubles
+    double* ep = smem + 3 * cap;                     // per-particle pair sums (the energy cache) live in shared memory here
+    double* partials = smem + 4 * cap;               // 128 doubles
     if (tid == 0) { P = params[chain]; S = states[chain]; }
     __syncthreads();
     const size_t off = (size_t)chain * (size_t)cap;
-    for (int j = tid; j < cap; j += T) { xs[j] = X[off + j]; ys[j] = Y[off + j]; zs[j] = Z[off + j]; }
+    double* ep_global = a.ep + off;
+    for (int j = tid; j < cap; j += T) { xs[j] = X[off + j]; ys[j] = Y[off + j]; zs[j] = Z[off + j]; ep[j] = ep_global[j]; }
 
     const bool book = (tid == 32 * KW);              // lane 0 of the bookkeeping warp; the only writer of S.st
     const PairGeom g = make_geom<true>(P);
     mcpm_chain_stats& st = S.st;
-    double* ep = a.ep + off;
     unsigned char* trace = a.trace ? a.trace + (unsigned long long)chain * a.trace_stride : nullptr;
     const double* replay = (RNG_MODE == MCPM_RNG_REPLAY) ? a.replay_u + (unsigned long long)chain * a.replay_stride : nullptr;
 
@@ -155,7 +185,7 @@ __global__ void __launch_bounds__(32 * (KW + 1), 1) k2_spec(const ChainParams* _
     int overflow = 0, par = 0;
     const int steps_per_set = (int)a.steps_per_set;
     unsigned long long filled = step;                // the ring holds the uniforms of steps [.., filled)
-    // Bookkeeping warp: prepare the uniforms of the steps below `upto` (at most RS ahead of the oldest step still needed).
+    // Uniforms warp: prepare the uniforms of the steps below `upto` (at most RS ahead of the oldest step still needed).
     auto refill = [&](unsigned long long upto) {
         while (filled < upto) {
             const unsigned long long stp = filled + (unsigned long long)(lane >> 2);
@@ -168,7 +198,7 @@ __global__ void __launch_bounds__(32 * (KW + 1), 1) k2_spec(const ChainParams* _
             filled = (filled + 8ull < upto) ? filled + 8ull : upto;
         }
     };
-    if (RNG_MODE == MCPM_RNG_PHILOX && warp == KW) refill(step + (unsigned long long)RS);
+    if (RNG_MODE == MCPM_RNG_PHILOX && warp == KW + 1) refill(step + (unsigned long long)RS);
     __syncthreads();
 
     {   // energy cache: reuse the previous launch's if the configuration is unchanged, else rebuild (see chain_loop)
@@ -184,6 +214,10 @@ __global__ void __launch_bounds__(32 * (KW + 1), 1) k2_spec(const ChainParams* _
     SetCounters sc;                                  // meaningful in the bookkeeping thread only
     double sum_n = st.sum_n, sum_n2 = st.sum_n2, sum_e = st.sum_e, sum_e2 = st.sum_e2;
     unsigned long long samples = st.samples;
+#ifdef MCPM_SPEC_TIMING
+    double tacc[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+    double tsub[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+#endif
     for (int set = a.first_set; set < a.first_set + a.n_sets && !overflow; set++) {
         sc.reset();                                  // MC::ResetStats, src/MC.cpp:81-98
         if (book) { st.widom_insert = st.widom_delete = 0.0; st.widom_insertions = st.widom_deletions = 1; }
@@ -192,6 +226,9 @@ __global__ void __launch_bounds__(32 * (KW + 1), 1) k2_spec(const ChainParams* _
         while (s < steps_per_set && !overflow) {
             // An empty box exposes the stale slot 0, which rejected insertion attempts overwrite (quirk Q12): serial rounds.
             const int B = (n == 0) ? 1 : min(KW, steps_per_set - s);
+#ifdef MCPM_SPEC_TIMING
+            const long long tq0 = spec_clock();
+#endif
             if (RNG_MODE == MCPM_RNG_REPLAY) {       // where each candidate's draws start: 1 + 7/6/4/2 draws per step
                 if (tid == 0) {
                     unsigned long long p = rcur;
@@ -208,34 +245,48 @@ __global__ void __launch_bounds__(32 * (KW + 1), 1) k2_spec(const ChainParams* _
             // ---- every candidate warp evaluates one step against the current configuration ----
             if (warp < B) {
                 Cand c;
+                long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                (void)tp;
                 if (RNG_MODE == MCPM_RNG_PHILOX) {
                     StepRing rng; rng.u = ring[(int)((step + (unsigned long long)warp) & (unsigned long long)(RS - 1))];
-                    c = evaluate_candidate<StepRing, PBZ>(rng, P, g, xs, ys, zs, ep, n, cap, dr, lane);
+                    c = evaluate_candidate<StepRing, PBZ>(rng, P, g, xs, ys, zs, ep, n, cap, dr, lane, tp);
                 } else {
                     StepReplay rng; rng.u = replay; rng.pos = rpos[warp]; rng.n = a.replay_stride;
-                    c = evaluate_candidate<StepReplay, PBZ>(rng, P, g, xs, ys, zs, ep, n, cap, dr, lane);
+                    c = evaluate_candidate<StepReplay, PBZ>(rng, P, g, xs, ys, zs, ep, n, cap, dr, lane, tp);
                 }
-                if (lane == 0) { cand[par][warp] = c; code[par][warp] = (unsigned char)(c.type | (c.acc << 3)); }
+                if (lane == 0) { cand[par][warp] = c; code[par][warp] = (unsigned char)(c.type | (c.acc ? CAND_ACCEPTED : 0)); }
+#ifdef MCPM_SPEC_TIMING
+                if (lane == 0 && c.type == CAND_TRANS) {
+                    const long long tend = spec_clock();
+                    for (int k = 0; k < 6; k++) tsub[k] += (double)(tp[k + 1] - tp[k]);
+                    tsub[6] += (double)(tend - tp[6]); tsub[7] += 1.0;
+                }
+#endif
             } else if (warp < KW && lane == 0) {
                 code[par][warp] = 0;
             }
+#ifdef MCPM_SPEC_TIMING
+            const long long tq1 = spec_clock();
+#endif
             __syncthreads();
+#ifdef MCPM_SPEC_TIMING
+            const long long tq2 = spec_clock();
+#endif
             // ---- the first accepted candidate wins; everything before it is a rejected step that stands ----
             const unsigned long long lo = *reinterpret_cast<const unsigned long long*>(&code[par][0]);
-            const unsigned long long hi = (KW > 8) ? *reinterpret_cast<const unsigned long long*>(&code[par][8]) : 0ull;
             const Cand* cd = cand[par];
             par ^= 1;
-            const unsigned long long alo = lo & 0x0808080808080808ull, ahi = hi & 0x0808080808080808ull;
-            const int kstar = alo ? ((__ffsll((long long)alo) - 1) >> 3) : (ahi ? 8 + ((__ffsll((long long)ahi) - 1) >> 3) : -1);
-            auto code_of = [&](int w) { return (int)(((w < 8) ? (lo >> (8 * w)) : (hi >> (8 * (w - 8)))) & 0xFull); };
-            const int tk = (kstar >= 0) ? (code_of(kstar) & 7) : -1;
+            const unsigned long long am = lo & MCPM_PLANE(CAND_ACCEPTED);
+            const int kstar = am ? ((__ffsll((long long)am) - 1) >> 3) : -1;
+            const int tk = (kstar >= 0) ? (int)((lo >> (8 * kstar)) & 0x7Full) : 0;
             const bool stop = (tk == CAND_OVERFLOW);
+            const bool committed = (kstar >= 0) && !stop;
             const int kept = stop ? kstar : (kstar >= 0 ? kstar + 1 : B);
             const int n_before = n;
             const double e_before = e_pair + e_wall;
             unsigned long long commit_evals = 0ull;
             // ---- commit the accepted move with the whole CTA ----
-            if (kstar >= 0 && !stop) {
+            if (committed) {
                 const Cand& c = cd[kstar];
                 bool big = false;
                 if (tk == CAND_TRANS) {
@@ -271,37 +322,47 @@ __global__ void __launch_bounds__(32 * (KW + 1), 1) k2_spec(const ChainParams* _
             }
             if (RNG_MODE == MCPM_RNG_REPLAY) rcur = rpos[kept];
             step += (unsigned long long)(kept + (stop ? 1 : 0));
-            // ---- off the critical path: uniforms of later rounds, counters, trace, accumulators ----
-            if (warp == KW) {
-                if (RNG_MODE == MCPM_RNG_PHILOX) refill(step + (unsigned long long)RS);
-                if (book) {
-                    sc.evals += commit_evals;
-                    int last_ins = -1;
-                    for (int w = 0; w < B; w++) {
-                        const int cw = code_of(w), ty = cw & 7, ac = cw >> 3;
-                        if (ty == CAND_TRANS || ty == CAND_INS) sc.evals += (unsigned long long)n_before;   // executed, kept or not
-                        if (w >= kept) continue;
-                        if (ty == CAND_TRANS) { sc.n_disp++; sc.acc_disp += ac; sc.alg += 2ull * (unsigned long long)n_before; }
-                        else if (ty == CAND_INS) { sc.n_ins++; sc.acc_ins += ac; sc.alg += (unsigned long long)n_before; last_ins = w; }
-                        else if (ty == CAND_DEL) { sc.n_del++; sc.acc_del += ac; sc.alg += (unsigned long long)n_before; }
-                        else if (ty == CAND_EMPTY) sc.n_empty++;
-                        if (trace) {
-                            const int tc = ty == CAND_TRANS ? ac : (ty == CAND_INS ? (2 | ac) : (ty == CAND_DEL ? (4 | ac) : (ty == CAND_EMPTY ? 6 : 8)));
-                            trace[(unsigned long long)(set - a.first_set) * (unsigned long long)a.steps_per_set + (unsigned long long)(s + w)] = (unsigned char)tc;
-                        }
-                        if (production) {
-                            const bool after = (w == kstar);                        // only the accepted step sees the new state
-                            const double dn = (double)(after ? n : n_before), e = after ? (e_pair + e_wall) : e_before;
-                            sum_n += dn; sum_n2 += dn * dn; sum_e += e; sum_e2 += e * e;
-                            samples++;
-                        }
+#ifdef MCPM_SPEC_TIMING
+            const long long tq3 = spec_clock();
+#endif
+            // ---- off the critical path: uniforms of later rounds; counters, trace, accumulators ----
+            if (RNG_MODE == MCPM_RNG_PHILOX && warp == KW + 1) refill(step + (unsigned long long)RS);
+            if (book) {
+                const unsigned long long kl = (kept >= 8) ? lo : (lo & ((1ull << (8 * kept)) - 1ull));   // the kept steps' codes
+                const int nd = __popcll(kl & MCPM_PLANE(CAND_TRANS)), ni = __popcll(kl & MCPM_PLANE(CAND_INS)), nx = __popcll(kl & MCPM_PLANE(CAND_DEL));
+                sc.n_disp += nd; sc.n_ins += ni; sc.n_del += nx; sc.n_empty += __popcll(kl & MCPM_PLANE(CAND_EMPTY));
+                if (committed) { sc.acc_disp += (tk == CAND_TRANS); sc.acc_ins += (tk == CAND_INS); sc.acc_del += (tk == CAND_DEL); }
+                sc.evals += commit_evals + (unsigned long long)__popcll(lo & MCPM_PLANE(CAND_TRANS | CAND_INS)) * (unsigned long long)n_before;   // executed, kept or not
+                sc.alg += (unsigned long long)(2 * nd + ni + nx) * (unsigned long long)n_before;
+                if (trace) {
+                    for (int w = 0; w < kept; w++) {
+                        const int cw = (int)((lo >> (8 * w)) & 0xFFull), ac = cw >> 7, ty = cw & 0x7F;
+                        const int tc = ty == CAND_TRANS ? ac : (ty == CAND_INS ? (2 | ac) : (ty == CAND_DEL ? (4 | ac) : (ty == CAND_EMPTY ? 6 : 8)));
+                        trace[(unsigned long long)(set - a.first_set) * (unsigned long long)a.steps_per_set + (unsigned long long)(s + w)] = (unsigned char)tc;
                     }
-                    // the trial position of a rejected insertion attempt stays in the first free slot (src/moves.cpp:302-303)
-                    if (last_ins >= 0 && last_ins != kstar) { xs[n_before] = cd[last_ins].px; ys[n_before] = cd[last_ins].py; zs[n_before] = cd[last_ins].pz; }
+                }
+                if (production) {   // rejected steps see the old state, the accepted one (the last kept) the new state
+                    const double m = (double)(kept - (committed ? 1 : 0)), dn = (double)n_before;
+                    sum_n += m * dn; sum_n2 += m * (dn * dn); sum_e = fma(m, e_before, sum_e); sum_e2 = fma(m, e_before * e_before, sum_e2);
+                    if (committed) { const double da = (double)n, e = e_pair + e_wall; sum_n += da; sum_n2 += da * da; sum_e += e; sum_e2 += e * e; }
+                    samples += (unsigned long long)kept;
+                }
+                // the trial position of a rejected insertion attempt stays in the first free slot (src/moves.cpp:302-303)
+                const unsigned long long im = kl & MCPM_PLANE(CAND_INS);
+                if (im) {
+                    const int last_ins = (63 - __clzll((long long)im)) >> 3;
+                    if (last_ins != kstar) { xs[n_before] = cd[last_ins].px; ys[n_before] = cd[last_ins].py; zs[n_before] = cd[last_ins].pz; }
                 }
             }
             s += kept;
             if (stop) overflow = 1;
+#ifdef MCPM_SPEC_TIMING
+            if (lane == 0) {
+                const long long tq4 = spec_clock();
+                tacc[0] += (double)(tq1 - tq0); tacc[1] += (double)(tq2 - tq1); tacc[2] += (double)(tq3 - tq2); tacc[3] += (double)(tq4 - tq3);
+                tacc[4] += 1.0; tacc[5] += committed ? 1.0 : 0.0; tacc[6] += (double)kept;
+            }
+#endif
             if (RNG_MODE == MCPM_RNG_REPLAY || n_before == 0 || n == 0) __syncthreads();   // rpos[] / slot 0 are reused at once
         }
         // MC::AdjustMCMoves displacement part, src/moves.cpp:68-78 (ResetStats starts nDisplacements at ONE)
@@ -336,29 +397,27 @@ __global__ void __launch_bounds__(32 * (KW + 1), 1) k2_spec(const ChainParams* _
         S.cache_valid = overflow ? 0 : 1; S.cache_sum = end_sum;
     }
     __syncthreads();
-    for (int j = tid; j < cap; j += T) { X[off + j] = xs[j]; Y[off + j] = ys[j]; Z[off + j] = zs[j]; }
+    for (int j = tid; j < cap; j += T) { X[off + j] = xs[j]; Y[off + j] = ys[j]; Z[off + j] = zs[j]; ep_global[j] = ep[j]; }
     if (book) states[chain] = S;
+#ifdef MCPM_SPEC_TIMING
+    if (lane == 0 && a.rdf) for (int k = 0; k < 8; k++) a.rdf[(size_t)chain * MCPM_RDF_BINS + warp * 8 + k] = tacc[k];   // debug build only
+    if (tid == 32 && a.rdf) for (int k = 0; k < 8; k++) a.rdf[(size_t)chain * MCPM_RDF_BINS + 80 + k] = tsub[k];
+#endif
 }
 
-size_t k2_spec_smem_bytes(int cap) { return (size_t)(3 * cap + 128) * sizeof(double); }
+size_t k2_spec_smem_bytes(int cap) { return (size_t)(4 * cap + 128) * sizeof(double); }
 
-cudaError_t launch_k2_spec(int rng_mode, bool pbz, int width, int n_chains, const ChainParams* params, ChainState* states, const int* order,
+cudaError_t launch_k2_spec(int rng_mode, bool pbz, int n_chains, const ChainParams* params, ChainState* states, const int* order,
                            double* X, double* Y, double* Z, const RunArgs& a, cudaStream_t stream) {
     const size_t smem = k2_spec_smem_bytes(a.cap);
-    auto go = [&](auto kern, int threads) -> cudaError_t {
+    auto go = [&](auto kern) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kern<<<n_chains, threads, smem, stream>>>(params, states, order, X, Y, Z, a);
+        kern<<<n_chains, 320, smem, stream>>>(params, states, order, X, Y, Z, a);
         return cudaGetLastError();
     };
-#define MCPM_SPEC(R, Z, K) go(k2_spec<R, Z, K>, 32 * (K + 1))
-    if (width == 16) {
-        if (rng_mode == MCPM_RNG_PHILOX) return pbz ? MCPM_SPEC(MCPM_RNG_PHILOX, true, 16) : MCPM_SPEC(MCPM_RNG_PHILOX, false, 16);
-        return pbz ? MCPM_SPEC(MCPM_RNG_REPLAY, true, 16) : MCPM_SPEC(MCPM_RNG_REPLAY, false, 16);
-    }
-    if (rng_mode == MCPM_RNG_PHILOX) return pbz ? MCPM_SPEC(MCPM_RNG_PHILOX, true, 8) : MCPM_SPEC(MCPM_RNG_PHILOX, false, 8);
-    return pbz ? MCPM_SPEC(MCPM_RNG_REPLAY, true, 8) : MCPM_SPEC(MCPM_RNG_REPLAY, false, 8);
-#undef MCPM_SPEC
+    if (rng_mode == MCPM_RNG_PHILOX) return pbz ? go(k2_spec<MCPM_RNG_PHILOX, true>) : go(k2_spec<MCPM_RNG_PHILOX, false>);
+    return pbz ? go(k2_spec<MCPM_RNG_REPLAY, true>) : go(k2_spec<MCPM_RNG_REPLAY, false>);
 }
 
 }  // namespace mcpm

@@ -20,10 +20,10 @@ print("chains", nchains, "steps", S)
 for k in (0, 5, 12, 27, 39):
     x, y, z = g[f"x{k}"], g[f"y{k}"], g[f"z{k}"]
     row = []
-    for T in (32, 128, 256, "spec8", "spec16"):
+    for T in (32, 128, 256, "spec"):
         with m.Engine(nchains, 768) as e:
             label = T
-            e.use_speculation(int(T[4:]) if isinstance(T, str) else 0)
+            e.use_speculation(1 if isinstance(T, str) else 0)
             if isinstance(T, str):
                 T = 0
             e.set_system(workloads.argon_slit(mu=float(g["mu"][k]), n_equil_sets=0))
