@@ -339,14 +339,15 @@ def gpu_arm(args, world, rank, local, dist):
     evals_per_launch = float(np.mean(evals))
     achieved = w["flop_per_pair"] * evals_per_launch / (k_ms * 1e-3) * 1e-12
     traffic = None
+    kernel_name = eng.last_kernel_name()
     summ = os.path.join(ROOT, "profiles", "k2_ncu_summary.json")
-    if os.path.exists(summ):
+    if os.path.exists(summ) and kernel_name == "k2_chains" and args.config == "c2" and not args.replicas:   # the capture is of the default workload
         try:
             traffic = json.load(open(summ)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-                "traffic": traffic, "kernel": "k2_chains", "kernel_ms": k_ms,
+                "traffic": traffic, "kernel": kernel_name, "kernel_ms": k_ms,
                 "algorithmic": f"{w['flop_per_pair']} flop x {evals_per_launch:.4g} pair evaluations per launch = what the reference's moves evaluate for "
                                f"the same steps (2N per translation, N per insertion/deletion, SURVEY.md 8d); the engine executed "
                                f"{float(np.mean(evals_x)):.4g} of them (per-particle energy cache)",

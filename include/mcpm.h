@@ -206,11 +206,18 @@ int mcpm_set_step_counter(mcpm_ctx* ctx, int chain, unsigned long long step);
 /* ---- measurement support ------------------------------------------------------------------ */
 /* Device time (CUDA events on the context's stream) and launch count of the last compute call. */
 int mcpm_last_kernel_ms(const mcpm_ctx* ctx, float* ms);
+/* Which K2 kernel the last mcpm_run launched: "k2_chains", "k2_spec" or "k2_sub" ("" before the first run). */
+const char* mcpm_last_kernel_name(const mcpm_ctx* ctx);
 int mcpm_launch_count(const mcpm_ctx* ctx, unsigned long long* launches);
 /* CUDA-event stopwatch on the context's stream: start records an event, stop records a second one,
  * waits for it and returns the device time between the two in milliseconds. */
 int mcpm_timer_start(mcpm_ctx* ctx);
 int mcpm_timer_stop(mcpm_ctx* ctx, float* ms);
+/* The device Metropolis tests on caller-supplied inputs, for tests: kind 0 translation u < exp(-x) with x = dE/T
+ * (src/moves.cpp:170); 1 insertion u < zzV exp(x)/(n+1) with x = -E/T (src/moves.cpp:306); 2 deletion
+ * u < n exp(x)/zzV with x = E/T (src/moves.cpp:326).  out[k] = 1 if accepted.  The device evaluates them with bounds
+ * and a single-precision screen first; the outcome must always be that of the fp64 expression. */
+int mcpm_metropolis_probe(mcpm_ctx* ctx, int kind, int count, const double* u, const double* x, const int* n, double zzV, int* out);
 /* FP64 FMA microbenchmark on `device`: the roofline denominator for these kernels (TFLOP/s). */
 int mcpm_fp64_peak(int device, double* tflops, double* ms);
 /* The device Philox stream, for tests: uniform of (seed, chain, step, slot). */

@@ -52,6 +52,7 @@ struct mcpm_ctx {
     double *d_sx = nullptr, *d_sy = nullptr, *d_sz = nullptr;
     int use_cells = 1;             // 0 disables the cell-list path (tests compare both)
     int use_cache = 1;             // per-particle energy cache in K2 (mcpm_use_energy_cache)
+    const char* last_kernel = "";
     int use_spec = -1;             // speculative-moves kernel (mcpm_spec.cu): -1 = automatic (fewer chains than SMs), 0 = never, 1 = whenever possible
     int use_subwarp = 0;           // opt-in: the sub-warp kernel that packs 2 or 4 small chains into one warp (mcpm_use_subwarp)
     int2* d_ctas = nullptr;        // CTA descriptors of the sub-warp kernel, n_chains entries
@@ -587,6 +588,7 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     // coordinates inside the box, shared-memory positions, no in-kernel sampling and one geometry for the whole launch.
     const bool use_sub = c->use_subwarp && threads == 32 && cache_now && all_fast && !sample && !global_path && same_pbz;
     CU(cudaEventRecord(c->ev0, c->stream));
+    c->last_kernel = use_spec ? "k2_spec" : (use_sub ? "k2_sub" : "k2_chains");
     if (use_spec) {
         CU(launch_k2_spec(p->rng_mode, c->h_params[0].pbc[2] != 0, c->n_chains, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->stream));
         c->launches++;
@@ -745,6 +747,8 @@ int mcpm_set_step_counter(mcpm_ctx* c, int chain, unsigned long long step) {
 }
 
 // ---- measurement support ------------------------------------------------------------------------
+const char* mcpm_last_kernel_name(const mcpm_ctx* c) { return c ? c->last_kernel : ""; }
+
 int mcpm_last_kernel_ms(const mcpm_ctx* c, float* ms) {
     if (!c || !ms) return fail(MCPM_ERR_ARG, "null argument");
     *ms = c->last_ms;
@@ -799,6 +803,24 @@ int mcpm_fp64_peak(int device, double* tflops, double* ms_out) {
     const double flops = 2.0 * 8.0 * (double)iters * (double)threads * (double)blocks;
     *tflops = flops / (best * 1e-3) * 1e-12;
     if (ms_out) *ms_out = best;
+    return MCPM_OK;
+}
+
+int mcpm_metropolis_probe(mcpm_ctx* c, int kind, int count, const double* u, const double* x, const int* n, double zzV, int* out) {
+    if (!c || !u || !x || !out || count <= 0 || kind < 0 || kind > 2 || (kind > 0 && !n)) return fail(MCPM_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(c->device));
+    double *du = nullptr, *dx = nullptr; int *dn = nullptr, *dout = nullptr;
+    CU(cudaMalloc(&du, sizeof(double) * count)); CU(cudaMalloc(&dx, sizeof(double) * count));
+    CU(cudaMalloc(&dn, sizeof(int) * count)); CU(cudaMalloc(&dout, sizeof(int) * count));
+    CU(cudaMemcpyAsync(du, u, sizeof(double) * count, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(dx, x, sizeof(double) * count, cudaMemcpyHostToDevice, c->stream));
+    if (n) CU(cudaMemcpyAsync(dn, n, sizeof(int) * count, cudaMemcpyHostToDevice, c->stream));
+    else CU(cudaMemsetAsync(dn, 0, sizeof(int) * count, c->stream));
+    CU(launch_metropolis_probe(kind, count, du, dx, dn, log(zzV), zzV, dout, c->stream));
+    c->launches++;
+    CU(cudaMemcpyAsync(out, dout, sizeof(int) * count, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(du); cudaFree(dx); cudaFree(dn); cudaFree(dout);
     return MCPM_OK;
 }
 

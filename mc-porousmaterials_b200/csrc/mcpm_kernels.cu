@@ -717,6 +717,19 @@ __global__ void philox_fill_kernel(unsigned long long seed, unsigned int chain, 
     }
 }
 
+// The device Metropolis tests (mcpm_device.cuh) on caller-supplied inputs, for the parity tests of the screen:
+// kind 0: translation (x = dE/T), 1: insertion (x = -E/T), 2: deletion (x = E/T).
+__global__ void metropolis_probe_kernel(int kind, int count, const double* __restrict__ u, const double* __restrict__ x, const int* __restrict__ n,
+                                        double ln_zzV, double zzV, int* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    bool r;
+    if (kind == 0) r = metropolis_translation(u[k], x[k]);
+    else if (kind == 1) r = metropolis_insertion(u[k], x[k], ln_zzV, zzV, n[k]);
+    else r = metropolis_deletion(u[k], x[k], ln_zzV, zzV, n[k]);
+    out[k] = r ? 1 : 0;
+}
+
 // ================================================================================================
 // launchers
 // ================================================================================================
@@ -841,6 +854,12 @@ cudaError_t launch_k3_cells(int maxn, int n_chains, int chain0, const ChainParam
 
 cudaError_t launch_fp64_peak(double* out, int blocks, int threads, int iters, cudaStream_t stream) {
     fp64_peak_kernel<<<blocks, threads, 0, stream>>>(out, iters, 1.0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_metropolis_probe(int kind, int count, const double* u, const double* x, const int* n, double ln_zzV, double zzV, int* out,
+                                    cudaStream_t stream) {
+    metropolis_probe_kernel<<<(count + 127) / 128, 128, 0, stream>>>(kind, count, u, x, n, ln_zzV, zzV, out);
     return cudaGetLastError();
 }
 

@@ -37,6 +37,8 @@ cudaError_t launch_k3_cells(int maxn, int n_chains, int chain0, const ChainParam
                             cudaStream_t stream);
 
 cudaError_t launch_fp64_peak(double* out, int blocks, int threads, int iters, cudaStream_t stream);
+cudaError_t launch_metropolis_probe(int kind, int count, const double* u, const double* x, const int* n, double ln_zzV, double zzV, int* out,
+                                    cudaStream_t stream);
 cudaError_t launch_philox_fill(unsigned long long seed, unsigned int chain, unsigned long long first_step, int n_steps, double* out,
                                cudaStream_t stream);
 

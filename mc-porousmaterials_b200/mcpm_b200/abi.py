@@ -133,6 +133,8 @@ PROTOTYPES = {
     "mcpm_set_dr": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "mcpm_set_step_counter": (C.c_int, [C.c_void_p, C.c_int, C.c_ulonglong]),
     "mcpm_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "mcpm_last_kernel_name": (C.c_char_p, [C.c_void_p]),
+    "mcpm_metropolis_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
     "mcpm_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong)]),
     "mcpm_timer_start": (C.c_int, [C.c_void_p]),
     "mcpm_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),

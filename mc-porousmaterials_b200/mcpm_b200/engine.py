@@ -201,6 +201,17 @@ class Engine:
         check(self.L.mcpm_set_step_counter(self.h, chain, step))
 
     # ---- measurement
+    def metropolis_probe(self, kind, u, x, n=None, zzV=1.0):
+        """Device Metropolis decisions for arrays of uniforms u and arguments x (see mcpm_metropolis_probe)."""
+        u = np.ascontiguousarray(u, dtype=np.float64); x = np.ascontiguousarray(x, dtype=np.float64)
+        nn = np.ascontiguousarray(n if n is not None else np.zeros(len(u)), dtype=np.int32)
+        out = np.zeros(len(u), dtype=np.int32)
+        check(self.L.mcpm_metropolis_probe(self.h, int(kind), len(u), u.ctypes.data, x.ctypes.data, nn.ctypes.data, float(zzV), out.ctypes.data))
+        return out.astype(bool)
+
+    def last_kernel_name(self) -> str:
+        return self.L.mcpm_last_kernel_name(self.h).decode()
+
     def last_kernel_ms(self) -> float:
         ms = C.c_float(0)
         check(self.L.mcpm_last_kernel_ms(self.h, C.byref(ms)))

@@ -504,3 +504,39 @@ def test_subwarp_chain_outgrows_its_slot(mcpm, golden):
         ox, oy, oz = o.get_positions()
         assert np.array_equal(gx, ox) and np.array_equal(gy, oy) and np.array_equal(gz, oz)
         assert launches >= 3                                        # K3 initialisation is 2 launches, then >= 2 K2 launches
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2], ids=["translation", "insertion", "deletion"])
+def test_metropolis_screen_never_changes_a_decision(mcpm, kind):
+    """The device decides u < f with bounds and a single-precision screen before it evaluates the reference's fp64
+    expression (src/moves.cpp:170,306,326).  Stress the screen: uniforms placed at f (1 + d) for |d| from 1e-12 to 1e-2 on
+    both sides, over the whole range of arguments, plus random pairs; every decision must equal the fp64 one (the two
+    libm's exp may differ in the last ulp, hence |d| >= 1e-12)."""
+    rng = np.random.default_rng(100 + kind)
+    m = 20000
+    zzV = 37.5
+    n = rng.integers(1, 700, size=m).astype(np.int32)
+    if kind == 0:
+        x = np.concatenate([rng.random(m) * 40.0, -rng.random(100)])           # dE/T, some downhill
+        nn = np.concatenate([n, n[:100]])
+        f = np.exp(-x)
+    elif kind == 1:
+        x = rng.random(m) * 70.0 - 45.0                                        # -E/T
+        nn = n
+        f = zzV * np.exp(x) / (nn + 1.0)
+    else:
+        x = rng.random(m) * 70.0 - 60.0                                        # E/T
+        nn = n
+        f = nn * np.exp(x) / zzV
+    d = rng.choice([1e-12, 1e-9, 1e-7, 3e-6, 1e-5, 5e-5, 9e-5, 1.1e-4, 3e-4, 1e-3, 1e-2], size=len(x)) * rng.choice([-1.0, 1.0], size=len(x))
+    u_min = 0.9999 * 2.0 ** -53        # the smallest non-zero uniform of the 53-bit generators (quirk Q1 scaling included)
+    u_edge = np.clip(f * (1.0 + d), u_min, 0.9999)
+    u_rand = np.maximum(rng.random(len(x)) * 0.9999, u_min)
+    with mcpm.Engine(1, 32) as e:
+        for u in (u_edge, u_rand):
+            got = e.metropolis_probe(kind, u, x, nn, zzV)
+            want = u < f
+            sure = np.abs(u - f) > 1e-13 * f                                   # away from the last-ulp ambiguity of exp itself
+            bad = np.nonzero(sure & (got != want))[0]
+            assert len(bad) == 0, f"{len(bad)} wrong decisions, first: u={u[bad[0]]!r} x={x[bad[0]]!r} n={nn[bad[0]]} f={f[bad[0]]!r}"
+            assert sure.mean() > 0.5
