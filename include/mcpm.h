@@ -189,6 +189,14 @@ int mcpm_use_subwarp(mcpm_ctx* ctx, int enable);
  * the launch qualifies (energy cache enabled, coordinates inside the box, no in-kernel sampling, shared-memory
  * positions).  Replaces nothing in the reference: it is a schedule of src/main.cpp:66-71. */
 int mcpm_use_speculation(mcpm_ctx* ctx, int mode);
+/* EXPERIMENTAL, default off (measured 25 % slower than the default kernel on config C2 in round 1: the selection and
+ * decision of the two candidates stay serial, only the scan gains parallelism, and 168 registers cost a resident chain
+ * per SM).  With one warp per chain (the choice for many small chains) a round evaluates TWO consecutive steps
+ * against the same configuration in one interleaved instruction stream (one partner loop for both trial positions, one
+ * wall evaluation, one reduction); the second is used only if the first is rejected, else it is evaluated again next
+ * round with the same uniforms.  Same chain as one step at a time; more instruction-level parallelism per warp.
+ * Applies when the energy cache is in use, coordinates lie inside the box and nothing is sampled in-kernel. */
+int mcpm_use_dual_candidates(mcpm_ctx* ctx, int enable);
 int mcpm_reset_accumulators(mcpm_ctx* ctx);
 /* Accumulated pair-distance histogram of one chain: hist[0..99] = MC::Stats::rdf(0..99) (bin 0 is never filled,
  * each pair adds 2, src/sample.cpp:27-28).  mcpm_reset_accumulators clears it. */

@@ -53,6 +53,7 @@ struct mcpm_ctx {
     int use_cells = 1;             // 0 disables the cell-list path (tests compare both)
     int use_cache = 1;             // per-particle energy cache in K2 (mcpm_use_energy_cache)
     const char* last_kernel = "";
+    int use_dual = 0;              // opt-in: one-warp chains evaluate two candidate steps per round (mcpm_dual.cu); measured slower in round 1
     int use_spec = -1;             // speculative-moves kernel (mcpm_spec.cu): -1 = automatic (fewer chains than SMs), 0 = never, 1 = whenever possible
     int use_subwarp = 0;           // opt-in: the sub-warp kernel that packs 2 or 4 small chains into one warp (mcpm_use_subwarp)
     int2* d_ctas = nullptr;        // CTA descriptors of the sub-warp kernel, n_chains entries
@@ -588,8 +589,12 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     // coordinates inside the box, shared-memory positions, no in-kernel sampling and one geometry for the whole launch.
     const bool use_sub = c->use_subwarp && threads == 32 && cache_now && all_fast && !sample && !global_path && same_pbz;
     CU(cudaEventRecord(c->ev0, c->stream));
-    c->last_kernel = use_spec ? "k2_spec" : (use_sub ? "k2_sub" : "k2_chains");
-    if (use_spec) {
+    const bool use_dual = c->use_dual && !use_spec && !use_sub && threads == 32 && cache_now && all_fast && !sample && !global_path && same_pbz;
+    c->last_kernel = use_spec ? "k2_spec" : (use_sub ? "k2_sub" : (use_dual ? "k2_dual" : "k2_chains"));
+    if (use_dual) {
+        CU(launch_k2_dual(p->rng_mode, c->h_params[0].pbc[2] != 0, c->n_chains, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->stream));
+        c->launches++;
+    } else if (use_spec) {
         CU(launch_k2_spec(p->rng_mode, c->h_params[0].pbc[2] != 0, c->n_chains, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->stream));
         c->launches++;
     } else if (use_sub) {
@@ -701,6 +706,12 @@ int mcpm_set_running_energy(mcpm_ctx* c, const double* pair, const double* wall)
     }
     CU(cudaMemcpyAsync(c->d_state, c->h_state.data(), sizeof(ChainState) * c->n_chains, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return MCPM_OK;
+}
+
+int mcpm_use_dual_candidates(mcpm_ctx* c, int enable) {
+    if (!c) return fail(MCPM_ERR_ARG, "null context");
+    c->use_dual = enable ? 1 : 0;
     return MCPM_OK;
 }
 

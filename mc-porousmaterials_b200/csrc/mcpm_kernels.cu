@@ -57,6 +57,9 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
     Fwd fwd; fwd.slot = -1; fwd.x = fwd.y = fwd.z = 0.0;
     int parity = 0;
     SetCounters sc;
+    double sum_n = 0.0, sum_n2 = 0.0, sum_e = 0.0, sum_e2 = 0.0;   // production accumulators (non-sampling kernels), written back at the end
+    unsigned long long samples = 0ull;
+    if (!SAMPLE) { sum_n = st.sum_n; sum_n2 = st.sum_n2; sum_e = st.sum_e; sum_e2 = st.sum_e2; samples = st.samples; }
     const int steps_per_set = (int)a.steps_per_set;
     double* ep = CACHE ? a.ep + (size_t)chain * (size_t)cap : nullptr;
     if (CACHE) {
@@ -291,10 +294,13 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                 cta_rdf<PBZ>(xs, ys, zs, n, P, hist, tid, T);
                 __syncthreads();
             }
-            if (lead) {
-                if (trace) trace[(unsigned long long)(set - a.first_set) * (unsigned long long)a.steps_per_set + (unsigned long long)s] = (unsigned char)code;
-                if (production) {
-                    const double dn = (double)n, e = e_pair + e_wall;
+            if (lead && trace) trace[(unsigned long long)(set - a.first_set) * (unsigned long long)a.steps_per_set + (unsigned long long)s] = (unsigned char)code;
+            if (production) {
+                const double dn = (double)n, e = e_pair + e_wall;
+                if (!SAMPLE) {   // replicated in registers like the energies: no divergent read-modify-write of shared memory per step
+                    sum_n += dn; sum_n2 += dn * dn; sum_e += e; sum_e2 += e * e;
+                    samples++;
+                } else if (lead) {   // the sampling kernels are short of registers (Widom state): thread 0 keeps the sums in shared memory
                     st.sum_n += dn; st.sum_n2 += dn * dn; st.sum_e += e; st.sum_e2 += e * e;
                     st.samples++;
                 }
@@ -327,6 +333,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
     if (lead) {
         st.n = n; st.overflow = overflow; st.dr = dr; st.steps_done = step;
         st.pair = e_pair; st.wall = e_wall; st.energy = e_pair + e_wall;
+        if (!SAMPLE) { st.sum_n = sum_n; st.sum_n2 = sum_n2; st.sum_e = sum_e; st.sum_e2 = sum_e2; st.samples = samples; }
         if (a.check_energy) { st.pair_check = c_pair; st.wall_check = c_wall; st.energy_check = c_pair + c_wall; }
         if (a.check_energy == 2) { st.pair = c_pair; st.wall = c_wall; st.energy = c_pair + c_wall; }   // adopt, like BoxEnergy does
         S.replay_pos = rng.cursor();

@@ -28,6 +28,11 @@ size_t k2_spec_smem_bytes(int cap);
 cudaError_t launch_k2_spec(int rng_mode, bool pbz, int n_chains, const ChainParams* params, ChainState* states, const int* order,
                            double* X, double* Y, double* Z, const RunArgs& a, cudaStream_t stream);
 
+// mcpm_dual.cu: one warp per chain, two candidate steps per round
+size_t k2_dual_smem_bytes(int cap);
+cudaError_t launch_k2_dual(int rng_mode, bool pbz, int n_chains, const ChainParams* params, ChainState* states, const int* order, double* X,
+                           double* Y, double* Z, const RunArgs& a, cudaStream_t stream);
+
 cudaError_t launch_in_box(int n_chains, const ChainParams* params, const int* n_of, const double* X, const double* Y, const double* Z, int cap,
                           int* flags, cudaStream_t stream);
 size_t k3c_cells_per_chain();

@@ -115,6 +115,9 @@ class Engine:
         """-1 automatic (few chains), 0 never, 1 whenever the launch qualifies (mcpm_use_speculation)."""
         check(self.L.mcpm_use_speculation(self.h, int(mode)))
 
+    def use_dual_candidates(self, enable=True):
+        check(self.L.mcpm_use_dual_candidates(self.h, 1 if enable else 0))
+
     def use_subwarp(self, enable=True):
         check(self.L.mcpm_use_subwarp(self.h, 1 if enable else 0))
 

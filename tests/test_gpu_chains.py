@@ -22,14 +22,17 @@ def first_divergence(a, b):
     return int(d[0]) if len(d) else -1
 
 
-@pytest.mark.parametrize("cache", [True, False, "subwarp", "spec"], ids=["cache", "nocache", "subwarp", "spec"])
+@pytest.mark.parametrize("cache", [True, False, "subwarp", "spec", "dual"], ids=["cache", "nocache", "subwarp", "spec", "dual"])
 @pytest.mark.parametrize("threads", [32, 64, 128, 256, 512])
 @pytest.mark.parametrize("name", ["c1t", "lowt", "bulkt"])
 def test_replay_trace_matches_reference_golden(mcpm, golden, name, threads, cache):
+    """'dual' = the opt-in dual-candidate kernel (k2_dual, one warp per chain, two steps per round)."""
     if cache == "subwarp" and threads != 32:
         pytest.skip("the sub-warp kernel runs one warp per chain")
     if cache == "spec" and threads != 32:
         pytest.skip("the speculative kernel has one CTA shape")
+    if cache == "dual" and threads != 32:
+        pytest.skip("the dual-candidate kernel only replaces the one-warp variant")
     arrays, meta = golden
     mkey, start = TRACE_CASES[name]
     m = meta[mkey]
@@ -41,6 +44,7 @@ def test_replay_trace_matches_reference_golden(mcpm, golden, name, threads, cach
         e.use_energy_cache(bool(cache))
         e.use_subwarp(cache == "subwarp")
         e.use_speculation(1 if cache == "spec" else 0)
+        e.use_dual_candidates(cache == "dual")
         e.set_system(s)
         e.set_positions(0, x, y, z)
         per_set, traces = [], []
@@ -94,12 +98,12 @@ def test_device_philox_stream_is_the_documented_one(mcpm):
             assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("cache", [True, False, "spec"], ids=["cache", "nocache", "spec"])
+@pytest.mark.parametrize("cache", [True, False, "spec", "dual"], ids=["cache", "nocache", "spec", "dual"])
 @pytest.mark.parametrize("threads", [32, 128])
 def test_philox_chain_follows_oracle(mcpm, golden, threads, cache):
     """Device Philox + Metropolis on the GPU == the C oracle fed with the same counter-based stream."""
-    if cache == "spec" and threads != 32:
-        pytest.skip("the speculative kernel has one CTA shape")
+    if cache in ("spec", "dual") and threads != 32:
+        pytest.skip("one CTA shape")
     arrays, meta = golden
     s = system_from_meta(meta["c1"]["system"])
     s.n_equil_sets = 1
@@ -108,10 +112,12 @@ def test_philox_chain_follows_oracle(mcpm, golden, threads, cache):
     with mcpm.Engine(nchains, 1024) as e:
         e.use_energy_cache(bool(cache))
         e.use_speculation(1 if cache == "spec" else 0)
+        e.use_dual_candidates(cache == "dual")
         e.set_system(s)
         for c in range(nchains):
             e.set_positions(c, x, y, z)
         stats, tr = e.run(1, sets, sps, seed=seed, trace=True, threads=threads, check_energy=1)
+        assert e.last_kernel_name() == {True: "k2_chains", False: "k2_chains", "spec": "k2_spec", "dual": "k2_dual"}[cache]
         for c in range(nchains):
             o = O.COracle(s, 1024)
             o.set_positions(x, y, z)
@@ -128,7 +134,7 @@ def test_philox_chain_follows_oracle(mcpm, golden, threads, cache):
             assert st.pair_evals_algorithmic == ost["pair_evals"] - evals0    # what the reference's moves evaluate
             if not cache:      # with the energy cache fewer partner scans are needed (and the rebuild adds n*n)
                 assert st.pair_evals == ost["pair_evals"] - evals0
-            elif cache == "spec":   # discarded candidates are executed evaluations too
+            elif cache in ("spec", "dual"):   # discarded candidates are executed evaluations too
                 assert st.pair_evals > 0
             else:
                 assert st.pair_evals < ost["pair_evals"] - evals0 + len(x) ** 2
@@ -303,7 +309,7 @@ def test_results_do_not_depend_on_threads_per_chain(mcpm, golden):
                 e.set_positions(c, x, y, z)
             stats = e.run(1, 6, 10000, seed=2025, threads=threads)
             pos = [e.get_positions(c) for c in range(4)]
-        sig = [(st.n, st.dr, st.tot_disp_acc, st.tot_ins_acc, st.tot_del_acc, st.sum_n, st.pair_evals) for st in stats]
+        sig = [(st.n, st.dr, st.tot_disp_acc, st.tot_ins_acc, st.tot_del_acc, st.sum_n, st.pair_evals_algorithmic) for st in stats]
         if ref is None:
             ref = (sig, pos)
             continue
@@ -377,7 +383,8 @@ def test_energy_cache_with_hard_overlaps(mcpm):
 
 @pytest.mark.parametrize("start", ["dense", "empty", "bulk"])
 def test_speculative_moves_are_the_sequential_chain(mcpm, golden, start):
-    """The speculative kernel (8 candidate steps per round, first accepted one committed, later ones re-evaluated) must
+    """The speculative kernel (8 candidate steps per round, first accepted one committed, later ones re-evaluated) and the
+    dual-candidate kernel (2 per round inside one warp) must
     reproduce the one-step-at-a-time kernel bit for bit: trace, configuration, counters, dr adaptation, accumulators.
     'empty' starts from an empty pore (stale-slot moves, quirk Q12, force serial rounds) and fills it."""
     arrays, meta = golden
@@ -394,19 +401,21 @@ def test_speculative_moves_are_the_sequential_chain(mcpm, golden, start):
         x = y = z = np.zeros(0)
     nch, sets, sps = 3, 4, 5003
     out = []
-    for spec in (0, 1):
+    for kernel, spec, threads in (("k2_chains", 0, 64), ("k2_spec", 1, 0), ("k2_dual", 0, 32)):
         with mcpm.Engine(nch, 1024) as e:
             e.use_speculation(spec)
+            e.use_dual_candidates(kernel == "k2_dual")
             e.set_system(s)
             for c in range(nch):
                 e.set_positions(c, x, y, z)
-            stats, tr = e.run(1, sets, sps, seed=424242, trace=True, threads=64 if not spec else 0, check_energy=1)
+            stats, tr = e.run(1, sets, sps, seed=424242, trace=True, threads=threads, check_energy=1)
+            assert e.last_kernel_name() == kernel
             out.append((tr.copy(), [e.get_positions(c) for c in range(nch)], stats))
-    for c in range(nch):
-        assert first_divergence(out[0][0][c], out[1][0][c]) == -1
-        for a, b in zip(out[0][1][c], out[1][1][c]):
+    for c, other in [(c, other) for c in range(nch) for other in (1, 2)]:
+        assert first_divergence(out[0][0][c], out[other][0][c]) == -1
+        for a, b in zip(out[0][1][c], out[other][1][c]):
             assert np.array_equal(a, b)
-        p, q = out[0][2][c], out[1][2][c]
+        p, q = out[0][2][c], out[other][2][c]
         for f in ("n", "dr", "acceptance", "rejection", "n_displacements", "accept_swap", "reject_swap", "n_swaps", "tot_disp", "tot_disp_acc",
                   "tot_ins", "tot_ins_acc", "tot_del", "tot_del_acc", "tot_empty", "steps_done", "samples", "sum_n", "sum_n2", "pair_evals_algorithmic"):
             assert getattr(p, f) == getattr(q, f), f
