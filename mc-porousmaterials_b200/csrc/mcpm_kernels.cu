@@ -384,8 +384,13 @@ __global__ void __launch_bounds__(MAXT, MINB) k2_chains(const ChainParams* __res
         else { if (pbz) MCPM_GO(SRC, false, true); else MCPM_GO(SRC, false, false); }                  \
     } while (0)
     if (RNG_MODE == MCPM_RNG_PHILOX) {
-        PhiloxSource rng; rng.init(a.seed, (uint32_t)chain, S.st.steps_done, tid & 31);
-        MCPM_DISPATCH(PhiloxSource);
+        if (MAXT <= 64 && !GLOBAL && !multi) {   // one warp per chain: uniforms through shared memory (the partials area is free)
+            PhiloxSmemSource rng; rng.init(a.seed, (uint32_t)chain, S.st.steps_done, tid & 31, partials);
+            if (pbz) MCPM_GO(PhiloxSmemSource, false, true); else MCPM_GO(PhiloxSmemSource, false, false);
+        } else {
+            PhiloxSource rng; rng.init(a.seed, (uint32_t)chain, S.st.steps_done, tid & 31);
+            MCPM_DISPATCH(PhiloxSource);
+        }
     } else {
         ReplaySource rng; rng.init(a.replay_u + (unsigned long long)chain * a.replay_stride, 0ull, a.replay_stride);
         MCPM_DISPATCH(ReplaySource);
@@ -740,8 +745,8 @@ __global__ void metropolis_probe_kernel(int kind, int count, const double* __res
 // ================================================================================================
 // launchers
 // ================================================================================================
-// positions + (multi-warp CTAs) 128 doubles of partial sums + (sampling kernels) the RDF histogram
-static size_t k2_smem_bytes(int cap, bool multi, bool sample) { return (size_t)(3 * cap + (multi ? 128 : 0) + (sample ? 104 : 0)) * sizeof(double); }
+// positions + (multi-warp CTAs) 128 doubles of partial sums or (one warp) 64 doubles of uniforms + (sampling kernels) the RDF histogram
+static size_t k2_smem_bytes(int cap, bool multi, bool sample) { return (size_t)(3 * cap + (multi ? 128 : 64) + (sample ? 104 : 0)) * sizeof(double); }
 
 size_t k2_smem_limit_cap(int max_smem_optin) { return ((size_t)max_smem_optin / sizeof(double) - 128 - 104 - 64) / 3; }
 
