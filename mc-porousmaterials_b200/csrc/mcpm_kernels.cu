@@ -55,6 +55,14 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
     const double beta = P.beta, eps4 = P.eps4, ln_zzV = P.ln_zzV, zzV = P.zzV;
     const double Lx = P.L[0], Ly = P.L[1], Lz = P.L[2];
     Fwd fwd; fwd.slot = -1; fwd.x = fwd.y = fwd.z = 0.0;
+    // One-warp chains on the energy cache synchronise after every accepted move (the cache entries must be visible), so a
+    // slot is never read before its last write is visible: no register forwarding, and the hole-filling particle of a
+    // deletion is read only when the deletion is accepted.
+    constexpr bool NOFWD = CACHE && !MULTI && !SAMPLE;
+    auto load_sel = [&](const double* px, const double* py, const double* pz, int i, const Fwd& f, double& x, double& y, double& z) {
+        if (NOFWD) { x = px[i]; y = py[i]; z = pz[i]; }
+        else load_slot(px, py, pz, i, f, x, y, z);
+    };
     int parity = 0;
     SetCounters sc;
     double sum_n = 0.0, sum_n2 = 0.0, sum_e = 0.0, sum_e2 = 0.0;   // production accumulators (non-sampling kernels), written back at the end
@@ -93,7 +101,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                 rng.end_step(8);
                 const int i = (int)(u_i * (double)n);                             // int(u*n)+1 on 1-based slots; n==0 -> stale slot (Q12)
                 double xo, yo, zo;
-                load_slot(xs, ys, zs, i, fwd, xo, yo, zo);
+                load_sel(xs, ys, zs, i, fwd, xo, yo, zo);
                 const double xr = __dadd_rn(xo, __dmul_rn(u_x - 0.5, dr)), yr = __dadd_rn(yo, __dmul_rn(u_y - 0.5, dr));
                 const double zr = __dadd_rn(zo, __dmul_rn(u_z - 0.5, dr));
                 bool odd = false;                                                 // MC::PBC: x and y are always periodic
@@ -186,9 +194,9 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                     const double u_o = rng.template at<3>(), u_a = rng.template at<4>();
                     rng.end_step(5);
                     const int o = (int)(u_o * (double)n + 1.0) - 1;               // int(u*n+1) on 1-based slots
-                    double xo, yo, zo, xl, yl, zl;
-                    load_slot(xs, ys, zs, o, fwd, xo, yo, zo);
-                    load_slot(xs, ys, zs, n - 1, fwd, xl, yl, zl);                // the particle that would fill the hole
+                    double xo, yo, zo, xl = 0., yl = 0., zl = 0.;
+                    load_sel(xs, ys, zs, o, fwd, xo, yo, zo);
+                    if (!NOFWD) load_slot(xs, ys, zs, n - 1, fwd, xl, yl, zl);    // the particle that would fill the hole
                     double v[1];
                     double wo, wdummy;
                     if (CACHE) {
@@ -215,6 +223,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                             if ((o & tmask) == tid) ep[o] = ep[n - 1];
                             fwd.slot = -1;                                          // barrier passed: earlier slot writes are visible
                         }
+                        if (NOFWD && (o & tmask) == tid) { xl = xs[n - 1]; yl = ys[n - 1]; zl = zs[n - 1]; }   // read only when needed, by the writer
                         if ((o & tmask) == tid) { xs[o] = xl; ys[o] = yl; zs[o] = zl; }  // swap-with-last, src/moves.cpp:329
                         fwd.slot = o; fwd.x = xl; fwd.y = yl; fwd.z = zl;
                         n--;
