@@ -120,6 +120,9 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        deadline = time.time() + 1.5            # a timed region shorter than nvidia-smi's start-up: wait for its first row (GPU still busy
+        while not self.rows and time.time() < deadline and self.proc.poll() is None:   # or just released: clocks do not drop within ms)
+            time.sleep(0.02)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)

@@ -185,7 +185,7 @@ int mcpm_use_subwarp(mcpm_ctx* ctx, int enable);
  * the next 8 steps of its chain concurrently against the same configuration, commits the first accepted one and
  * re-evaluates the steps after it; rejected steps before it stand.  The chain is exactly the sequential one (same
  * uniforms per step index, same decisions, same trace).  mode -1 (default): chosen automatically when the context has
- * no more chains than the device has SMs, threads_per_chain is 0 and the energy cache is in use; 0: never; 1: whenever
+ * no more chains than the device has SMs, none larger than 2048 particles, threads_per_chain is 0 and the energy cache is in use; 0: never; 1: whenever
  * the launch qualifies (energy cache enabled, coordinates inside the box, no in-kernel sampling, shared-memory
  * positions).  Replaces nothing in the reference: it is a schedule of src/main.cpp:66-71. */
 int mcpm_use_speculation(mcpm_ctx* ctx, int mode);

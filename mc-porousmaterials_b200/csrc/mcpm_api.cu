@@ -560,7 +560,10 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     bool same_pbz = true;
     for (int k = 1; k < c->n_chains; k++) same_pbz = same_pbz && c->h_params[k].pbc[2] == c->h_params[0].pbc[2];
     const bool spec_ok = c->use_cache && all_fast && !sample && !global_path && same_pbz && k2_spec_smem_bytes(c->cap) <= (size_t)c->max_smem;
-    const bool use_spec = spec_ok && (c->use_spec >= 1 || (c->use_spec < 0 && cache_now && p->threads_per_chain == 0 && c->n_chains <= c->num_sms));
+    // Automatic choice: chains that cannot fill the GPU anyway, and small enough that a candidate's scan by one warp is latency-
+    // rather than FP64-throughput-bound (measured: 2.6-3x faster at N <= 600, break-even near N ~ 5000 where the discarded
+    // candidates' evaluations cost as much as the latency they hide).
+    const bool use_spec = spec_ok && (c->use_spec >= 1 || (c->use_spec < 0 && cache_now && p->threads_per_chain == 0 && c->n_chains <= c->num_sms && maxn <= 2048));
     if (use_spec) cache_now = true;
     if (cache_now && !c->d_ep) CU(cudaMalloc(&c->d_ep, sizeof(double) * (size_t)c->n_chains * c->cap));
     a.ep = cache_now ? c->d_ep : nullptr;
