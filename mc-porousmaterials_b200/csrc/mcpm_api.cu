@@ -53,6 +53,8 @@ struct mcpm_ctx {
     int use_cells = 1;             // 0 disables the cell-list path (tests compare both)
     int use_cache = 1;             // per-particle energy cache in K2 (mcpm_use_energy_cache)
     const char* last_kernel = "";
+    int *d_kc_items = nullptr, *d_kc_cell_of = nullptr, *d_kc_slot_of = nullptr;   // K2c cell lists (mcpm_cells.cu)
+    size_t kc_items_ints = 0;
     int use_dual = 0;              // opt-in: one-warp chains evaluate two candidate steps per round (mcpm_dual.cu); measured slower in round 1
     int use_spec = -1;             // speculative-moves kernel (mcpm_spec.cu): -1 = automatic (fewer chains than SMs), 0 = never, 1 = whenever possible
     int use_subwarp = 0;           // opt-in: the sub-warp kernel that packs 2 or 4 small chains into one warp (mcpm_use_subwarp)
@@ -205,7 +207,7 @@ int mcpm_destroy(mcpm_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_params); cudaFree(c->d_state); cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_z);
     cudaFree(c->d_order); cudaFree(c->d_scratch); cudaFree(c->d_counters); cudaFree(c->d_out);
-    cudaFree(c->d_pp); cudaFree(c->d_pw); cudaFree(c->d_rdf); cudaFree(c->d_ep); cudaFree(c->d_ctas); cudaFree(c->d_flags);
+    cudaFree(c->d_pp); cudaFree(c->d_pw); cudaFree(c->d_rdf); cudaFree(c->d_ep); cudaFree(c->d_kc_items); cudaFree(c->d_kc_cell_of); cudaFree(c->d_kc_slot_of); cudaFree(c->d_ctas); cudaFree(c->d_flags);
     if (c->h_flags) cudaFreeHost(c->h_flags);
     cudaFree(c->d_cell_of); cudaFree(c->d_cell_counts); cudaFree(c->d_cell_starts); cudaFree(c->d_orig);
     cudaFree(c->d_sx); cudaFree(c->d_sy); cudaFree(c->d_sz); cudaFree(c->d_replay); cudaFree(c->d_trace);
@@ -554,12 +556,48 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
         for (int k = 0; k < c->n_chains; k++) { acc += (double)c->h_state[k].st.acceptance; att += (double)c->h_state[k].st.n_displacements - 1.0; }
         if (att >= 100.0 * c->n_chains && acc / att > 0.4) cache_now = false;
     }
+    // K2 through a cell list (mcpm_cells.cu): large chains whose box holds >= 3 cut-off lengths per periodic axis (config C4).
+    // ~27 cells x occupancy candidate partners per energy evaluation instead of N; measured break-even is a few thousand particles.
+    bool use_k2c = c->use_cells && all_fast && !p->sample_rdf && p->threads_per_chain == 0 && maxn >= 4096;
+    int kc_stride = 1, kc_ccap = 64;
+    size_t kc_smem = 0;
+    if (use_k2c) {
+        double occ = 0.0;
+        for (int k = 0; k < c->n_chains && use_k2c; k++) {
+            const ChainParams& P = c->h_params[k];
+            const double rc = sqrt(P.rc2);
+            int dims[3];
+            for (int ax = 0; ax < 3; ax++) {
+                dims[ax] = std::min(16, (int)(P.L[ax] / rc));
+                if (P.pbc[ax] && dims[ax] < 3) use_k2c = false;
+                dims[ax] = std::max(1, dims[ax]);
+            }
+            const int ncell = dims[0] * dims[1] * dims[2];
+            kc_stride = std::max(kc_stride, ncell);
+            occ = std::max(occ, (double)c->h_state[k].st.n / ncell);
+        }
+        kc_ccap = std::max(64, (((int)(3.0 * occ) + 32 + 31) / 32) * 32);       // room for density fluctuations and growth; a full cell stops the chain
+        kc_smem = use_k2c ? k2_cells_smem_items_bytes(c->cap, kc_stride, kc_ccap, c->max_smem) : 0;
+        if (use_k2c) {
+            const size_t need = kc_smem ? 1 : (size_t)c->n_chains * kc_stride * kc_ccap;   // lists in shared memory need no global copy
+            if (need > c->kc_items_ints) {
+                cudaFree(c->d_kc_items); c->d_kc_items = nullptr; c->kc_items_ints = 0;
+                CU(cudaMalloc(&c->d_kc_items, sizeof(int) * need));
+                c->kc_items_ints = need;
+            }
+            if (!c->d_kc_cell_of) {
+                CU(cudaMalloc(&c->d_kc_cell_of, sizeof(int) * (size_t)c->n_chains * c->cap));
+                CU(cudaMalloc(&c->d_kc_slot_of, sizeof(int) * (size_t)c->n_chains * c->cap));
+            }
+        }
+    }
+    if (use_k2c) cache_now = false;
     // The speculative-moves kernel (mcpm_spec.cu) trades throughput for latency: it is chosen when there are too few
     // chains to fill the GPU anyway, the caller left the thread count open, and moves are mostly rejected.  It needs the
     // energy cache, coordinates inside the box, shared-memory positions, no in-kernel sampling and one geometry.
     bool same_pbz = true;
     for (int k = 1; k < c->n_chains; k++) same_pbz = same_pbz && c->h_params[k].pbc[2] == c->h_params[0].pbc[2];
-    const bool spec_ok = c->use_cache && all_fast && !sample && !global_path && same_pbz && k2_spec_smem_bytes(c->cap) <= (size_t)c->max_smem;
+    const bool spec_ok = !use_k2c && c->use_cache && all_fast && !sample && !global_path && same_pbz && k2_spec_smem_bytes(c->cap) <= (size_t)c->max_smem;
     // Automatic choice: chains that cannot fill the GPU anyway, and small enough that a candidate's scan by one warp is latency-
     // rather than FP64-throughput-bound (measured: 2.6-3x faster at N <= 600, break-even near N ~ 5000 where the discarded
     // candidates' evaluations cost as much as the latency they hide).
@@ -592,9 +630,15 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     // coordinates inside the box, shared-memory positions, no in-kernel sampling and one geometry for the whole launch.
     const bool use_sub = c->use_subwarp && threads == 32 && cache_now && all_fast && !sample && !global_path && same_pbz;
     CU(cudaEventRecord(c->ev0, c->stream));
-    const bool use_dual = c->use_dual && !use_spec && !use_sub && threads == 32 && cache_now && all_fast && !sample && !global_path && same_pbz;
-    c->last_kernel = use_spec ? "k2_spec" : (use_sub ? "k2_sub" : (use_dual ? "k2_dual" : "k2_chains"));
-    if (use_dual) {
+    const bool use_dual = c->use_dual && !use_k2c && !use_spec && !use_sub && threads == 32 && cache_now && all_fast && !sample && !global_path && same_pbz;
+    c->last_kernel = use_k2c ? "k2_cells" : use_spec ? "k2_spec" : (use_sub ? "k2_sub" : (use_dual ? "k2_dual" : "k2_chains"));
+    if (use_k2c) {
+        bool widom = false;
+        for (int k = 0; k < c->n_chains; k++) widom = widom || c->h_params[k].n_swap == 0;
+        CU(launch_k2_cells(p->rng_mode, widom, c->n_chains, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->d_kc_items,
+                           c->d_kc_cell_of, c->d_kc_slot_of, kc_stride, kc_ccap, kc_smem, c->stream));
+        c->launches++;
+    } else if (use_dual) {
         CU(launch_k2_dual(p->rng_mode, c->h_params[0].pbc[2] != 0, c->n_chains, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->stream));
         c->launches++;
     } else if (use_spec) {
@@ -642,11 +686,28 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     if (p->trace) CU(cudaMemcpyAsync(p->trace, c->d_trace, (size_t)c->n_chains * nsteps, cudaMemcpyDeviceToHost, c->stream));
     int rc = pull_states(c); if (rc) return rc;
     CU(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    if (use_k2c && p->check_energy) {   // the cell-list kernel leaves the end-of-launch energy check to K3 (itself through a cell list)
+        bool stopped = false;
+        for (int k = 0; k < c->n_chains; k++) stopped = stopped || c->h_state[k].st.overflow;
+        if (!stopped) {
+            std::vector<double> run(3 * (size_t)c->n_chains);
+            for (int k = 0; k < c->n_chains; k++) { run[3 * k] = c->h_state[k].st.pair; run[3 * k + 1] = c->h_state[k].st.wall; run[3 * k + 2] = c->h_state[k].st.energy; }
+            const float ms = c->last_ms;
+            rc = box_energy_range(c, 0, c->n_chains, nullptr, nullptr); if (rc) return rc;     // fills *_check and overwrites the running values
+            c->last_ms = ms;
+            if (p->check_energy != 2)
+                for (int k = 0; k < c->n_chains; k++) { c->h_state[k].st.pair = run[3 * k]; c->h_state[k].st.wall = run[3 * k + 1]; c->h_state[k].st.energy = run[3 * k + 2]; }
+            CU(cudaMemcpyAsync(c->d_state, c->h_state.data(), sizeof(ChainState) * c->n_chains, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+        }
+    }
     int overflowed = -1;
     for (int k = 0; k < c->n_chains; k++) {
         if (stats) stats[k] = c->h_state[k].st;
         if (c->h_state[k].st.overflow && overflowed < 0) overflowed = k;
     }
+    if (overflowed >= 0 && c->h_state[overflowed].st.overflow == 2)
+        return fail(MCPM_ERR_CAPACITY, "chain %d: a cell of its cell list ran out of slots (the density grew by more than 3x during the run) and the chain stopped", overflowed);
     if (overflowed >= 0) return fail(MCPM_ERR_CAPACITY, "chain %d reached its capacity of %d particles and stopped", overflowed, c->cap);
     return MCPM_OK;
 }

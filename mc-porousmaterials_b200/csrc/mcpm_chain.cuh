@@ -224,6 +224,20 @@ __device__ unsigned long long config_checksum(const double* xs, const double* ys
     return tot;
 }
 
+// ---- cell grid shared by the cell-list kernels (K3c in mcpm_kernels.cu, K2c in mcpm_cells.cu) ------------------------
+#define K3C_MAXC 16   // cells per axis
+
+struct CellGrid { int nx, ny, nz; };
+
+__device__ __forceinline__ CellGrid cell_grid(const ChainParams& P) {
+    const double rc = sqrt(P.rc2);
+    CellGrid g;
+    g.nx = min(K3C_MAXC, (int)(P.L[0] / rc)); g.ny = min(K3C_MAXC, (int)(P.L[1] / rc)); g.nz = min(K3C_MAXC, (int)(P.L[2] / rc));
+    if (!P.pbc[2]) g.nz = max(1, g.nz);
+    return g;
+}
+__device__ __forceinline__ int cell_coord(double x, double L, int n) { return min(n - 1, max(0, (int)(x * ((double)n / L)))); }
+
 // Per-set counters replicated in registers (cheap ints); flushed to the 64-bit totals in shared memory
 // by thread 0 at the end of every set.
 struct SetCounters {

@@ -579,19 +579,6 @@ __global__ void __launch_bounds__(128) k3_box_energy(const ChainParams* __restri
 //   k3c_scatter  positions copied into cell order (coalesced reads in the energy kernel)
 //   k3c_energy   one thread per particle, 27 neighbour cells
 // ================================================================================================
-#define K3C_MAXC 16   // cells per axis
-
-struct CellGrid { int nx, ny, nz; };
-
-__device__ __forceinline__ CellGrid cell_grid(const ChainParams& P) {
-    const double rc = sqrt(P.rc2);
-    CellGrid g;
-    g.nx = min(K3C_MAXC, (int)(P.L[0] / rc)); g.ny = min(K3C_MAXC, (int)(P.L[1] / rc)); g.nz = min(K3C_MAXC, (int)(P.L[2] / rc));
-    if (!P.pbc[2]) g.nz = max(1, g.nz);
-    return g;
-}
-__device__ __forceinline__ int cell_coord(double x, double L, int n) { return min(n - 1, max(0, (int)(x * ((double)n / L)))); }
-
 __global__ void k3c_bin(const ChainParams* __restrict__ params, const ChainState* __restrict__ states, const double* __restrict__ X,
                         const double* __restrict__ Y, const double* __restrict__ Z, int cap, int chain0, int* __restrict__ cell_of,
                         int* __restrict__ counts) {

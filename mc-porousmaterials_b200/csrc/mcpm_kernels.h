@@ -33,6 +33,12 @@ size_t k2_dual_smem_bytes(int cap);
 cudaError_t launch_k2_dual(int rng_mode, bool pbz, int n_chains, const ChainParams* params, ChainState* states, const int* order, double* X,
                            double* Y, double* Z, const RunArgs& a, cudaStream_t stream);
 
+// mcpm_cells.cu: K2 through a cell list (large bulk-like chains), 256 threads per chain, positions in global memory
+cudaError_t launch_k2_cells(int rng_mode, bool sample, int n_chains, const ChainParams* params, ChainState* states, const int* order, double* X,
+                            double* Y, double* Z, const RunArgs& a, int* items, int* cell_of, int* slot_of, int cells_stride, int ccap,
+                            size_t smem_items, cudaStream_t stream);
+size_t k2_cells_smem_items_bytes(int cap, int cells_stride, int ccap, int max_smem_optin);
+
 cudaError_t launch_in_box(int n_chains, const ChainParams* params, const int* n_of, const double* X, const double* Y, const double* Z, int cap,
                           int* flags, cudaStream_t stream);
 size_t k3c_cells_per_chain();

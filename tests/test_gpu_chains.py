@@ -181,8 +181,8 @@ def test_capacity_overflow_is_reported(mcpm):
         assert e.stats()[0].overflow == 1
 
 
-def _replay_vs_oracle(mcpm, system, x, y, z, capacity, threads, nsteps, seed):
-    u = O.mt_uniforms(seed, 8 * nsteps)
+def _replay_vs_oracle(mcpm, system, x, y, z, capacity, threads, nsteps, seed, expect_kernel=None, draws_per_step=8):
+    u = O.mt_uniforms(seed, draws_per_step * nsteps)
     o = O.COracle(system, capacity)
     o.set_positions(x, y, z)
     o.box_energy()
@@ -192,6 +192,8 @@ def _replay_vs_oracle(mcpm, system, x, y, z, capacity, threads, nsteps, seed):
         e.set_system(system)
         e.set_positions(0, x, y, z)
         stats, tr = e.run(1, 1, nsteps, replay=u, trace=True, threads=threads, check_energy=1)
+        if expect_kernel:
+            assert e.last_kernel_name() == expect_kernel
         gx, gy, gz = e.get_positions(0)
     div = first_divergence(tr[0], otr)
     assert div == -1, f"first divergence at step {div}"
@@ -232,6 +234,58 @@ def test_bulk_global_path_translations_only(mcpm):
     n = 5000
     x, y, z = rng.random(n) * 70.0, rng.random(n) * 70.0, rng.random(n) * 70.0
     _replay_vs_oracle(mcpm, s, x, y, z, 10240, 1024, 300, 9)
+
+
+def _jittered_lattice(m, size, seed):
+    rng = np.random.default_rng(seed)
+    site = np.arange(m) * (size / m)
+    gx, gy, gz = np.meshgrid(site, site, site, indexing="ij")
+    p = np.column_stack([gx.ravel(), gy.ravel(), gz.ravel()]) + (rng.random((m ** 3, 3)) - 0.5) * 0.5 + 0.4
+    return p[:, 0].copy(), p[:, 1].copy(), p[:, 2].copy()
+
+
+@pytest.mark.parametrize("ensemble", ["nvt", "nvt_production", "gcmc"])
+def test_cell_list_chain_follows_oracle(mcpm, ensemble):
+    """K2 through a cell list (k2_cells: bulk box with 5 cut-off lengths per axis, N = 5000, positions in global memory) against
+    the all-pairs C oracle under the reference's mt19937_64 stream: same trace, bit-identical positions, energies to 1e-10.
+    'nvt_production' also runs ComputeWidom every step (13 draws per step), 'gcmc' exercises the list updates of
+    insertions and deletions (swap-with-last renames an entry)."""
+    s = O.argon_bulk(size=70.0, rcut=12.0)
+    x, y, z = _jittered_lattice(17, 70.0, 12)       # 4913 particles, no overlaps
+    if ensemble == "gcmc":
+        s.n_swap, s.mu = 2, -900.0
+    if ensemble == "nvt_production":
+        s.n_equil_sets = 0
+    _replay_vs_oracle(mcpm, s, x, y, z, 10240, 0, 400, 9, expect_kernel="k2_cells", draws_per_step=13)
+
+
+def test_cell_list_widom_and_accumulators(mcpm):
+    """Philox mode through the cell list: Widom/BAR sums, production accumulators and counters equal the oracle's."""
+    s = O.argon_bulk(size=70.0, rcut=12.0)
+    s.n_equil_sets = 1
+    x, y, z = _jittered_lattice(17, 70.0, 13)
+    seed, sets, sps = 77, 2, 300
+    o = O.COracle(s, 8192)
+    o.set_positions(x, y, z); o.box_energy(); o.philox(seed, 0, 0)
+    otr = o.run_sets(1, sets, sps, 0, True)
+    with mcpm.Engine(1, 10240) as e:
+        e.set_system(s)
+        e.set_positions(0, x, y, z)
+        stats, tr = e.run(1, sets, sps, seed=seed, trace=True, check_energy=1)
+        assert e.last_kernel_name() == "k2_cells"
+        gx_, gy_, gz_ = e.get_positions(0)
+    assert first_divergence(tr[0], otr) == -1
+    ox, oy, oz = o.get_positions()
+    assert np.array_equal(gx_, ox) and np.array_equal(gy_, oy) and np.array_equal(gz_, oz)
+    st, ost = stats[0], o.state()
+    (wi, wd), (ni, nd) = o.get_widom()
+    assert (st.widom_insertions, st.widom_deletions) == (ni, nd)
+    assert st.widom_insert == pytest.approx(wi, rel=1e-9) and st.widom_delete == pytest.approx(wd, rel=1e-9)
+    assert st.samples == ost["samples"] and st.sum_n == ost["sum_n"]
+    assert st.sum_e == pytest.approx(ost["sum_e"], rel=RTOL)
+    assert st.tot_disp_acc == ost["tot_disp_acc"] and st.dr == ost["dr"]
+    assert st.energy == pytest.approx(st.energy_check, rel=RTOL)
+    assert st.pair_evals < st.pair_evals_algorithmic / 3          # ~27 cells of 125 instead of all N partners
 
 
 @pytest.mark.parametrize("threads", [32, 128])
