@@ -73,7 +73,7 @@ def build_workload(config, replicas, steps_per_set):
         site = np.arange(28) * (100.0 / 28)
         gx, gy, gz = np.meshgrid(site, site, site, indexing="ij")
         p = np.column_stack([gx.ravel(), gy.ravel(), gz.ravel()])[:20000] + (rng.random((20000, 3)) - 0.5) * 0.4 + 0.3
-        w["workload"] = "C4 dense NVT LJ argon, bulk L=100A, rcut=12A, T=120K, N=20000, translations only (O(N) scan, global-memory path)"
+        w["workload"] = "C4 dense NVT LJ argon, bulk L=100A, rcut=12A, T=120K, N=20000, translations + Widom sampling (K2 through a cell list: 27 cells of ~39 particles per scan instead of the reference's N)"
         w["points"] = [(workloads.argon_bulk(n_equil_sets=0), p[:, 0].copy(), p[:, 1].copy(), p[:, 2].copy(), 0.5)]
         w["replicas"] = replicas or 148
         w["steps_per_set"] = steps_per_set or 500
@@ -353,7 +353,7 @@ def gpu_arm(args, world, rank, local, dist):
                 "traffic": traffic, "kernel": kernel_name, "kernel_ms": k_ms,
                 "algorithmic": f"{w['flop_per_pair']} flop x {evals_per_launch:.4g} pair evaluations per launch = what the reference's moves evaluate for "
                                f"the same steps (2N per translation, N per insertion/deletion, SURVEY.md 8d); the engine executed "
-                               f"{float(np.mean(evals_x)):.4g} of them (per-particle energy cache)",
+                               f"{float(np.mean(evals_x)):.4g} of them ({'cell list' if kernel_name == 'k2_cells' else 'per-particle energy cache'})",
                 "peak_source": "mcpm_fp64_peak DFMA microbenchmark, measured live (MEASURED_PEAKS.json has no fp64 figure)",
                 "pair_evals_per_s": evals_per_launch / (k_ms * 1e-3),
                 "smem_bytes_per_s": BYTES_PER_PAIR * evals_per_launch / (k_ms * 1e-3)}

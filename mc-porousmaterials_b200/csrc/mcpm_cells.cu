@@ -121,6 +121,12 @@ __device__ __forceinline__ void cell_scan(const CellList& cl, const double* xs, 
     nev += (double)ne;
 }
 
+// Bulk boxes have neither walls nor an out-of-pore guard (src/energy.cpp:53-77): skip the lane-parallel wall evaluation.
+__device__ __forceinline__ void wall_any(const ChainParams& P, double z_a, double z_b, double& w_a, double& w_b, int lane) {
+    if (P.geometry == MCPM_GEOM_SLIT) wall_two(P, z_a, z_b, w_a, w_b, lane);
+    else { w_a = 0.0; w_b = 0.0; }
+}
+
 // All-reduce of three per-thread values over the 8 warps; every thread returns the same bits.
 __device__ __forceinline__ void cta_allsum3(double (&v)[3], double* partials, int parity, int warp, int lane) {
 #pragma unroll
@@ -136,9 +142,31 @@ __device__ __forceinline__ void cta_allsum3(double (&v)[3], double* partials, in
     }
 }
 
+// ComputeWidom's exponentials (src/moves.cpp:425-447) are not needed by the chain itself: thread 0 only queues the sampled
+// energy and warp 0 turns 32 queued samples into BAR terms at once, one per lane.
+struct WidomQueue {
+    double energy[32];
+    int kind[32];      // 0 insertion, 1 deletion
+    int count;
+};
+__device__ __forceinline__ void widom_flush(WidomQueue& wq, mcpm_chain_stats& st, double beta, int lane) {   // warp 0, all lanes
+    const int m = wq.count;
+    double ins = 0.0, del = 0.0;
+    if (lane < m) {
+        const double energy = wq.energy[lane];
+        const double bw = bar_weight(energy, beta);
+        if (wq.kind[lane] == 0) ins = bw * exp(-0.5 * energy * beta);
+        else if (exp(0.5 * energy * beta) < 1) del = bw * exp(0.5 * energy * beta);
+        else del = bw * exp(-0.5 * energy * beta);   // the reference's boundary for deletion statistics
+    }
+    ins = warp_allsum(ins); del = warp_allsum(del);
+    if (lane == 0) { st.widom_insert += ins; st.widom_delete += del; wq.count = 0; }
+    __syncwarp();
+}
+
 template <class Source, bool PBZ, bool SAMPLE, class CellList>
 __device__ void chain_loop_cells(const ChainParams& P, ChainState& S, Source& rng, double* xs, double* ys, double* zs, double* partials,
-                                 const CellList& cl, const RunArgs& a, unsigned char* trace, int cap, uint32_t chain) {
+                                 WidomQueue& wq, const CellList& cl, const RunArgs& a, unsigned char* trace, int cap, uint32_t chain) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool lead = (tid == 0);
     const PairGeom g = make_geom<true>(P);
@@ -188,7 +216,7 @@ __device__ void chain_loop_cells(const ChainParams& P, ChainState& S, Source& rn
                     cell_scan<PBZ, false>(cl, xs, ys, zs, g, cn, xn, yn, zn, 0., 0., 0., i, warp, lane, v[1], dummy, v[2]);
                 }
                 double wo, wn;
-                wall_two(P, zo, zn, wo, wn, lane);
+                wall_any(P, zo, zn, wo, wn, lane);
                 cta_allsum3(v, partials, parity, warp, lane); parity ^= 1;
                 sc.evals += (unsigned long long)v[2];
                 const double po = eps4 * v[0], pn = eps4 * v[1];
@@ -223,7 +251,7 @@ __device__ void chain_loop_cells(const ChainParams& P, ChainState& S, Source& rn
                     double v[3] = {0.0, 0.0, 0.0}, dummy = 0.0;
                     cell_scan<PBZ, false>(cl, xs, ys, zs, g, ci, xi, yi, zi, 0., 0., 0., -1, warp, lane, v[0], dummy, v[2]);
                     double wi, wdummy;
-                    wall_two(P, zi, zi, wi, wdummy, lane);
+                    wall_any(P, zi, zi, wi, wdummy, lane);
                     cta_allsum3(v, partials, parity, warp, lane); parity ^= 1;
                     sc.evals += (unsigned long long)v[2];
                     const double pi_ = eps4 * v[0];
@@ -245,7 +273,7 @@ __device__ void chain_loop_cells(const ChainParams& P, ChainState& S, Source& rn
                     double v[3] = {0.0, 0.0, 0.0}, dummy = 0.0;
                     cell_scan<PBZ, false>(cl, xs, ys, zs, g, co, xo, yo, zo, 0., 0., 0., o, warp, lane, v[0], dummy, v[2]);
                     double wo, wdummy;
-                    wall_two(P, zo, zo, wo, wdummy, lane);
+                    wall_any(P, zo, zo, wo, wdummy, lane);
                     cta_allsum3(v, partials, parity, warp, lane); parity ^= 1;
                     sc.evals += (unsigned long long)v[2];
                     const double po = eps4 * v[0];
@@ -278,10 +306,10 @@ __device__ void chain_loop_cells(const ChainParams& P, ChainState& S, Source& rn
                     double v[3] = {0.0, 0.0, 0.0}, dummy = 0.0;
                     cell_scan<PBZ, false>(cl, xs, ys, zs, g, cell_index(cl, P, gx, gy, gz), gx, gy, gz, 0., 0., 0., -1, warp, lane, v[0], dummy, v[2]);
                     double wg, wdummy;
-                    wall_two(P, gz, gz, wg, wdummy, lane);
+                    wall_any(P, gz, gz, wg, wdummy, lane);
                     cta_allsum3(v, partials, parity, warp, lane); parity ^= 1;
                     energy = eps4 * v[0] + wg;
-                    if (lead) { st.widom_insertions++; st.widom_insert += bar_weight(energy, beta) * exp(-0.5 * energy * beta); st.pair_evals += (unsigned long long)v[2]; st.pair_evals_algorithmic += (unsigned long long)n; }
+                    if (lead) { st.widom_insertions++; wq.energy[wq.count] = energy; wq.kind[wq.count] = 0; wq.count++; st.pair_evals += (unsigned long long)v[2]; st.pair_evals_algorithmic += (unsigned long long)n; }
                 } else {                                                         // virtual deletion
                     const int slot1 = (int)(rng.template extra<2>() * (double)n);   // 1-based slot in [0, n-1]: 0 is the scratch slot (Q14)
                     rng.end_step(3);
@@ -296,7 +324,7 @@ __device__ void chain_loop_cells(const ChainParams& P, ChainState& S, Source& rn
                         double v[3] = {0.0, 0.0, 0.0}, dummy = 0.0;
                         cell_scan<PBZ, false>(cl, xs, ys, zs, g, cell_index(cl, P, xk, yk, zk), xk, yk, zk, 0., 0., 0., k, warp, lane, v[0], dummy, v[2]);
                         double wk, wdummy;
-                        wall_two(P, zk, zk, wk, wdummy, lane);
+                        wall_any(P, zk, zk, wk, wdummy, lane);
                         cta_allsum3(v, partials, parity, warp, lane); parity ^= 1;
                         if (lead) st.pair_evals += (unsigned long long)v[2];
                         energy = eps4 * v[0] + wk;
@@ -304,10 +332,12 @@ __device__ void chain_loop_cells(const ChainParams& P, ChainState& S, Source& rn
                     if (lead) {
                         st.pair_evals_algorithmic += (unsigned long long)n;
                         st.widom_deletions++;
-                        const double bw = bar_weight(energy, beta);
-                        if (exp(0.5 * energy * beta) < 1) st.widom_delete += bw * exp(0.5 * energy * beta);
-                        else st.widom_delete += bw * exp(-0.5 * energy * beta);   // the reference's boundary for deletion statistics
+                        wq.energy[wq.count] = energy; wq.kind[wq.count] = 1; wq.count++;
                     }
+                }
+                if (warp == 0) {                     // (the queue belongs to warp 0: no barrier needed)
+                    __syncwarp();
+                    if (wq.count == 32) widom_flush(wq, st, beta, lane);
                 }
             }
             if (lead) {
@@ -319,6 +349,7 @@ __device__ void chain_loop_cells(const ChainParams& P, ChainState& S, Source& rn
                 }
             }
         }
+        if (SAMPLE && warp == 0) { __syncwarp(); if (wq.count > 0) widom_flush(wq, st, beta, lane); }   // the sums are per set (ResetStats)
         // MC::AdjustMCMoves displacement part, src/moves.cpp:68-78 (ResetStats starts nDisplacements at ONE)
         if (!overflow && n > 0 && set <= P.n_equil) {
             const double ratio = (double)sc.acc_disp * 1. / (1. * (double)(sc.n_disp + 1));
@@ -357,6 +388,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) k2_cells(const ChainParams* __r
     __shared__ ChainState S;
     __shared__ int cnt[KC_MAXCELLS];
     __shared__ double partials[128];
+    __shared__ WidomQueue wq;
     __shared__ int build_overflow;
     const int chain = order[blockIdx.x];
     const int cap = a.cap;
@@ -365,7 +397,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) k2_cells(const ChainParams* __r
     double* ys = Y + off;
     double* zs = Z + off;
     const int tid = threadIdx.x, T = blockDim.x;
-    if (tid == 0) { P = params[chain]; S = states[chain]; build_overflow = 0; }
+    if (tid == 0) { P = params[chain]; S = states[chain]; build_overflow = 0; wq.count = 0; }
     __syncthreads();
     const CellGrid cg = cell_grid(P);
     CellListT<ItemT> cl;
@@ -405,12 +437,12 @@ __global__ void __launch_bounds__(KC_THREADS, 1) k2_cells(const ChainParams* __r
     const bool pbz = P.pbc[2] != 0;
     if (RNG_MODE == MCPM_RNG_PHILOX) {
         PhiloxSource rng; rng.init(a.seed, (uint32_t)chain, S.st.steps_done, tid & 31);
-        if (pbz) chain_loop_cells<PhiloxSource, true, SAMPLE>(P, S, rng, xs, ys, zs, partials, cl, a, trace, cap, (uint32_t)chain);
-        else chain_loop_cells<PhiloxSource, false, SAMPLE>(P, S, rng, xs, ys, zs, partials, cl, a, trace, cap, (uint32_t)chain);
+        if (pbz) chain_loop_cells<PhiloxSource, true, SAMPLE>(P, S, rng, xs, ys, zs, partials, wq, cl, a, trace, cap, (uint32_t)chain);
+        else chain_loop_cells<PhiloxSource, false, SAMPLE>(P, S, rng, xs, ys, zs, partials, wq, cl, a, trace, cap, (uint32_t)chain);
     } else {
         ReplaySource rng; rng.init(a.replay_u + (unsigned long long)chain * a.replay_stride, 0ull, a.replay_stride);
-        if (pbz) chain_loop_cells<ReplaySource, true, SAMPLE>(P, S, rng, xs, ys, zs, partials, cl, a, trace, cap, (uint32_t)chain);
-        else chain_loop_cells<ReplaySource, false, SAMPLE>(P, S, rng, xs, ys, zs, partials, cl, a, trace, cap, (uint32_t)chain);
+        if (pbz) chain_loop_cells<ReplaySource, true, SAMPLE>(P, S, rng, xs, ys, zs, partials, wq, cl, a, trace, cap, (uint32_t)chain);
+        else chain_loop_cells<ReplaySource, false, SAMPLE>(P, S, rng, xs, ys, zs, partials, wq, cl, a, trace, cap, (uint32_t)chain);
     }
     __syncthreads();
     if (tid == 0) states[chain] = S;
