@@ -154,8 +154,11 @@ int mcpm_particle_energy(mcpm_ctx* ctx, int chain, int index, const double* tria
  * BoxEnergy leaves them in the particle records.  Also resets the chain's running energies. */
 int mcpm_box_energy(mcpm_ctx* ctx, int chain, mcpm_box_energy_t* out, double* per_pair, double* per_wall);
 int mcpm_box_energy_all(mcpm_ctx* ctx, mcpm_box_energy_t* out /* [n_chains] */);
-/* K3 switches to a cell list (27 neighbour cells instead of all N partners) for large bulk-like chains whose box holds
- * >= 3 cut-off lengths per periodic axis (config C4).  enable = 0 forces the all-pairs kernel (default: 1). */
+/* K3 (chains of >= 8192 particles) and K2 / mcpm_run (largest chain >= 4096 particles, threads_per_chain 0, no in-kernel RDF)
+ * switch to a cell list — 27 neighbour cells instead of all N partners per energy evaluation — for bulk-like chains whose box
+ * holds >= 3 cut-off lengths per periodic axis and whose coordinates lie inside the box (config C4).  Same sums up to the
+ * order of the additions.  A K2 chain whose local density more than triples during a run stops with MCPM_ERR_CAPACITY (a
+ * cell ran out of slots).  enable = 0 forces the all-pairs kernels (default: 1). */
 int mcpm_use_cell_list(mcpm_ctx* ctx, int enable);
 
 /* ---- state mutation for a host-driven loop (src/moves.cpp:163,184 / :302-311 / :329-332) --- */
