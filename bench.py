@@ -340,9 +340,13 @@ def gpu_arm(args, world, rank, local, dist):
     peak_tflops, _ = m.fp64_peak_tflops(local)
     k_ms = float(np.mean(kern_ms))
     evals_per_launch = float(np.mean(evals))
-    achieved = w["flop_per_pair"] * evals_per_launch / (k_ms * 1e-3) * 1e-12
-    traffic = None
     kernel_name = eng.last_kernel_name()
+    executed_per_launch = float(np.mean(evals_x))
+    # The roofline counts the reference's (algorithmic) pair evaluations, except through the cell list: there the engine evaluates
+    # ~1/19 of them (a different algorithm), and a utilisation figure must count what the FP64 pipe actually executed.
+    roof_evals = executed_per_launch if kernel_name == "k2_cells" else evals_per_launch
+    achieved = w["flop_per_pair"] * roof_evals / (k_ms * 1e-3) * 1e-12
+    traffic = None
     summ = os.path.join(ROOT, "profiles", "k2_ncu_summary.json")
     if os.path.exists(summ) and kernel_name == "k2_chains" and args.config == "c2" and not args.replicas:   # the capture is of the default workload
         try:
@@ -351,9 +355,11 @@ def gpu_arm(args, world, rank, local, dist):
             traffic = None
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
                 "traffic": traffic, "kernel": kernel_name, "kernel_ms": k_ms,
-                "algorithmic": f"{w['flop_per_pair']} flop x {evals_per_launch:.4g} pair evaluations per launch = what the reference's moves evaluate for "
-                               f"the same steps (2N per translation, N per insertion/deletion, SURVEY.md 8d); the engine executed "
-                               f"{float(np.mean(evals_x)):.4g} of them ({'cell list' if kernel_name == 'k2_cells' else 'per-particle energy cache'})",
+                "algorithmic": (f"{w['flop_per_pair']} flop x {evals_per_launch:.4g} pair evaluations per launch = what the reference's moves evaluate for "
+                                f"the same steps (2N per translation, N per insertion/deletion, SURVEY.md 8d); the engine executed "
+                                f"{executed_per_launch:.4g} of them (per-particle energy cache)") if kernel_name != "k2_cells" else
+                               (f"{w['flop_per_pair']} flop x {executed_per_launch:.4g} EXECUTED pair evaluations per launch (cell list: 27 cells around the "
+                                f"position); the reference's moves evaluate {evals_per_launch:.4g} for the same steps (2N per translation, SURVEY.md 8d)"),
                 "peak_source": "mcpm_fp64_peak DFMA microbenchmark, measured live (MEASURED_PEAKS.json has no fp64 figure)",
                 "pair_evals_per_s": evals_per_launch / (k_ms * 1e-3),
                 "smem_bytes_per_s": BYTES_PER_PAIR * evals_per_launch / (k_ms * 1e-3)}
