@@ -252,6 +252,8 @@ def gpu_arm(args, world, rank, local, dist):
     if args.config == "c5":
         cap = args.capacity or 1024
     eng = m.Engine(n_chains, cap, device=local)
+    if args.speculation is not None:
+        eng.use_speculation(args.speculation)
     cap = eng.capacity
     seed = 20240611 + 7919 * rank           # every rank: its own replicas of the workload
     n0 = np.zeros(n_chains, dtype=np.int32)
@@ -409,6 +411,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"], help="BASELINE.json config (default: the isotherm)")
     ap.add_argument("--capacity", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--speculation", type=int, default=None, help="mcpm_use_speculation mode (experiments)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

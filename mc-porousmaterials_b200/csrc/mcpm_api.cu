@@ -601,7 +601,8 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     // Automatic choice: chains that cannot fill the GPU anyway, and small enough that a candidate's scan by one warp is latency-
     // rather than FP64-throughput-bound (measured: 2.6-3x faster at N <= 600, break-even near N ~ 5000 where the discarded
     // candidates' evaluations cost as much as the latency they hide).
-    const bool use_spec = spec_ok && (c->use_spec >= 1 || (c->use_spec < 0 && cache_now && p->threads_per_chain == 0 && c->n_chains <= c->num_sms && maxn <= 2048));
+    const bool use_pair = c->use_spec == 2 && !use_k2c && threads == 32 && cache_now && all_fast && !sample && !global_path && same_pbz;
+    const bool use_spec = !use_pair && spec_ok && (c->use_spec == 1 || (c->use_spec < 0 && cache_now && p->threads_per_chain == 0 && c->n_chains <= c->num_sms && maxn <= 2048));
     if (use_spec) cache_now = true;
     if (cache_now && !c->d_ep) CU(cudaMalloc(&c->d_ep, sizeof(double) * (size_t)c->n_chains * c->cap));
     a.ep = cache_now ? c->d_ep : nullptr;
@@ -631,7 +632,7 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     const bool use_sub = c->use_subwarp && threads == 32 && cache_now && all_fast && !sample && !global_path && same_pbz;
     CU(cudaEventRecord(c->ev0, c->stream));
     const bool use_dual = c->use_dual && !use_k2c && !use_spec && !use_sub && threads == 32 && cache_now && all_fast && !sample && !global_path && same_pbz;
-    c->last_kernel = use_k2c ? "k2_cells" : use_spec ? "k2_spec" : (use_sub ? "k2_sub" : (use_dual ? "k2_dual" : "k2_chains"));
+    c->last_kernel = use_k2c ? "k2_cells" : use_pair ? "k2_pair" : use_spec ? "k2_spec" : (use_sub ? "k2_sub" : (use_dual ? "k2_dual" : "k2_chains"));
     if (use_k2c) {
         bool widom = false;
         for (int k = 0; k < c->n_chains; k++) widom = widom || c->h_params[k].n_swap == 0;
@@ -641,8 +642,11 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     } else if (use_dual) {
         CU(launch_k2_dual(p->rng_mode, c->h_params[0].pbc[2] != 0, c->n_chains, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->stream));
         c->launches++;
+    } else if (use_pair) {
+        CU(launch_k2_spec(p->rng_mode, c->h_params[0].pbc[2] != 0, true, c->n_chains, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->stream));
+        c->launches++;
     } else if (use_spec) {
-        CU(launch_k2_spec(p->rng_mode, c->h_params[0].pbc[2] != 0, c->n_chains, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->stream));
+        CU(launch_k2_spec(p->rng_mode, c->h_params[0].pbc[2] != 0, false, c->n_chains, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->stream));
         c->launches++;
     } else if (use_sub) {
         const int cap_cta = ((c->cap + 127) / 128) * 128;
@@ -781,7 +785,7 @@ int mcpm_use_dual_candidates(mcpm_ctx* c, int enable) {
 
 int mcpm_use_speculation(mcpm_ctx* c, int mode) {
     if (!c) return fail(MCPM_ERR_ARG, "null context");
-    if (mode < -1 || mode > 1) return fail(MCPM_ERR_ARG, "speculation mode must be -1 (automatic), 0 (off) or 1 (on)");
+    if (mode < -1 || mode > 2) return fail(MCPM_ERR_ARG, "speculation mode must be -1 (automatic), 0 (off), 1 (on) or 2 (two-warp variant for one-warp chains)");
     c->use_spec = mode;
     return MCPM_OK;
 }

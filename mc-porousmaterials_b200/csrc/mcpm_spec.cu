@@ -80,7 +80,7 @@ __device__ __forceinline__ long long spec_probe(double x) {
 #endif
 
 // Evaluates one step read-only.  Called by one full warp; every lane returns the same candidate.
-template <class Draws, bool PBZ>
+template <class Draws, bool PBZ, bool WIDE>
 __device__ __forceinline__ Cand evaluate_candidate(const Draws& rng, const ChainParams& P, const PairGeom& g, const double* xs, const double* ys,
                                                    const double* zs, const double* ep, int n, int cap, double dr, int lane, long long* tp) {
     Cand c;
@@ -101,7 +101,8 @@ __device__ __forceinline__ Cand evaluate_candidate(const Draws& rng, const Chain
         double xn = wrap_select(xr, P.L[0], odd), yn = wrap_select(yr, P.L[1], odd), zn = PBZ ? wrap_select(zr, P.L[2], odd) : zr;
         if (odd) { xn = wrap_floor(xr, P.L[0]); yn = wrap_floor(yr, P.L[1]); if (PBZ) zn = wrap_floor(zr, P.L[2]); }
         SPEC_PROBE(2, xn + yn + zn);
-        double v = (n <= 128) ? pair_sum_wide<true, PBZ, 4>(xs, ys, zs, n, i, g, xn, yn, zn, lane, 32)
+        double v = !WIDE ? pair_sum1<true, PBZ>(xs, ys, zs, n, i, g, xn, yn, zn, lane, 32)
+                 : (n <= 128) ? pair_sum_wide<true, PBZ, 4>(xs, ys, zs, n, i, g, xn, yn, zn, lane, 32)
                               : pair_sum_wide<true, PBZ, 8>(xs, ys, zs, n, i, g, xn, yn, zn, lane, 32);
         SPEC_PROBE(3, v);
         double wo, wn;
@@ -121,7 +122,8 @@ __device__ __forceinline__ Cand evaluate_candidate(const Draws& rng, const Chain
         else {
             const double u_x = rng.template at<3>(), u_y = rng.template at<4>(), u_z = rng.template at<5>(), u_a = rng.template at<6>();
             const double xi = u_x * P.L[0], yi = u_y * P.L[1], zi = u_z * P.L[2];         // src/moves.cpp:46-54
-            double v = (n <= 128) ? pair_sum_wide<true, PBZ, 4>(xs, ys, zs, n, -1, g, xi, yi, zi, lane, 32)
+            double v = !WIDE ? pair_sum1<true, PBZ>(xs, ys, zs, n, -1, g, xi, yi, zi, lane, 32)
+                     : (n <= 128) ? pair_sum_wide<true, PBZ, 4>(xs, ys, zs, n, -1, g, xi, yi, zi, lane, 32)
                                   : pair_sum_wide<true, PBZ, 8>(xs, ys, zs, n, -1, g, xi, yi, zi, lane, 32);
             double wi, wd;
             wall_two(P, zi, zi, wi, wd, lane);
@@ -145,12 +147,21 @@ __device__ __forceinline__ Cand evaluate_candidate(const Draws& rng, const Chain
 
 }  // namespace
 
-template <int RNG_MODE, bool PBZ>
-__global__ void __launch_bounds__(32 * 10, 1) k2_spec(const ChainParams* __restrict__ params, ChainState* __restrict__ states,
-                                                      const int* __restrict__ order, double* X, double* Y, double* Z, RunArgs a) {
-    constexpr int KW = 8;                            // candidate warps = steps per round (one code byte each in a 64-bit word)
-    constexpr int RS = 2 * KW;                       // ring of prepared uniforms, in steps
-    constexpr int W = KW + 2;                        // + bookkeeping warp (KW) + uniforms warp (KW + 1)
+// LEAN = false: the latency kernel described above (8 candidate warps + 2 helper warps, energy cache in shared memory, one chain
+//   per SM).
+// LEAN = true : the THROUGHPUT variant for many small chains: KW = 2 candidate warps and nothing else per chain, so that as many
+//   chains stay resident per SM as with one warp per chain (same shared memory: the energy cache stays in global memory) but
+//   twice the warps are there to hide each other's latencies, and a round advances the chain by 2 - p steps.  Thread 0 keeps
+//   the books, the last warp refills the uniform ring 8 steps at a time.
+template <int RNG_MODE, bool PBZ, int KW, bool LEAN>
+__global__ void __launch_bounds__(32 * (LEAN ? KW : KW + 2), LEAN ? 11 : 1) k2_spec(const ChainParams* __restrict__ params,
+                                                                                   ChainState* __restrict__ states,
+                                                                                   const int* __restrict__ order, double* X, double* Y, double* Z,
+                                                                                   RunArgs a) {
+    static_assert(KW >= 2 && KW <= 8, "one code byte per candidate in a 64-bit word");
+    constexpr int RS = 16;                           // ring of prepared uniforms, in steps (>= 2*KW + 8 for the lazy refill)
+    constexpr int W = LEAN ? KW : KW + 2;            // + bookkeeping warp (KW) + uniforms warp (KW + 1)
+    constexpr int BOOK_WARP = LEAN ? 0 : KW, RING_WARP = LEAN ? KW - 1 : KW + 1;
     extern __shared__ double smem[];
     __shared__ ChainParams P;
     __shared__ ChainState S;
@@ -165,15 +176,16 @@ __global__ void __launch_bounds__(32 * 10, 1) k2_spec(const ChainParams* __restr
     double* xs = smem;
     double* ys = smem + cap;
     double* zs = smem + 2 * cap;
-    double* ep = smem + 3 * cap;                     // per-particle pair sums (the energy cache) live in shared memory here
-    double* partials = smem + 4 * cap;               // 128 doubles
-    if (tid == 0) { P = params[chain]; S = states[chain]; }
-    __syncthreads();
     const size_t off = (size_t)chain * (size_t)cap;
     double* ep_global = a.ep + off;
-    for (int j = tid; j < cap; j += T) { xs[j] = X[off + j]; ys[j] = Y[off + j]; zs[j] = Z[off + j]; ep[j] = ep_global[j]; }
+    double* ep = LEAN ? ep_global : smem + 3 * cap;  // per-particle pair sums (the energy cache): shared memory, or global when LEAN
+    double* partials = smem + (LEAN ? 3 : 4) * cap;  // 128 doubles (LEAN: 16)
+    if (tid == 0) { P = params[chain]; S = states[chain]; }
+    if (tid < 16) code[tid >> 3][tid & 7] = 0;       // bytes of candidates that do not exist (KW < 8) stay zero
+    __syncthreads();
+    for (int j = tid; j < cap; j += T) { xs[j] = X[off + j]; ys[j] = Y[off + j]; zs[j] = Z[off + j]; if (!LEAN) ep[j] = ep_global[j]; }
 
-    const bool book = (tid == 32 * KW);              // lane 0 of the bookkeeping warp; the only writer of S.st
+    const bool book = (tid == 32 * BOOK_WARP);       // lane 0 of the bookkeeping warp; the only writer of S.st
     const PairGeom g = make_geom<true>(P);
     mcpm_chain_stats& st = S.st;
     unsigned char* trace = a.trace ? a.trace + (unsigned long long)chain * a.trace_stride : nullptr;
@@ -198,7 +210,7 @@ __global__ void __launch_bounds__(32 * 10, 1) k2_spec(const ChainParams* __restr
             filled = (filled + 8ull < upto) ? filled + 8ull : upto;
         }
     };
-    if (RNG_MODE == MCPM_RNG_PHILOX && warp == KW + 1) refill(step + (unsigned long long)RS);
+    if (RNG_MODE == MCPM_RNG_PHILOX && warp == RING_WARP) refill(step + (unsigned long long)RS);
     __syncthreads();
 
     {   // energy cache: reuse the previous launch's if the configuration is unchanged, else rebuild (see chain_loop)
@@ -249,10 +261,10 @@ __global__ void __launch_bounds__(32 * 10, 1) k2_spec(const ChainParams* __restr
                 (void)tp;
                 if (RNG_MODE == MCPM_RNG_PHILOX) {
                     StepRing rng; rng.u = ring[(int)((step + (unsigned long long)warp) & (unsigned long long)(RS - 1))];
-                    c = evaluate_candidate<StepRing, PBZ>(rng, P, g, xs, ys, zs, ep, n, cap, dr, lane, tp);
+                    c = evaluate_candidate<StepRing, PBZ, !LEAN>(rng, P, g, xs, ys, zs, ep, n, cap, dr, lane, tp);
                 } else {
                     StepReplay rng; rng.u = replay; rng.pos = rpos[warp]; rng.n = a.replay_stride;
-                    c = evaluate_candidate<StepReplay, PBZ>(rng, P, g, xs, ys, zs, ep, n, cap, dr, lane, tp);
+                    c = evaluate_candidate<StepReplay, PBZ, !LEAN>(rng, P, g, xs, ys, zs, ep, n, cap, dr, lane, tp);
                 }
                 if (lane == 0) { cand[par][warp] = c; code[par][warp] = (unsigned char)(c.type | (c.acc ? CAND_ACCEPTED : 0)); }
 #ifdef MCPM_SPEC_TIMING
@@ -326,7 +338,10 @@ __global__ void __launch_bounds__(32 * 10, 1) k2_spec(const ChainParams* __restr
             const long long tq3 = spec_clock();
 #endif
             // ---- off the critical path: uniforms of later rounds; counters, trace, accumulators ----
-            if (RNG_MODE == MCPM_RNG_PHILOX && warp == KW + 1) refill(step + (unsigned long long)RS);
+            if (RNG_MODE == MCPM_RNG_PHILOX && warp == RING_WARP) {
+                if (!LEAN) refill(step + (unsigned long long)RS);
+                else if (filled < step + 2ull * KW) refill(filled + 8ull);          // lazily, one full Philox pass (8 steps) at a time
+            }
             if (book) {
                 const unsigned long long kl = (kept >= 8) ? lo : (lo & ((1ull << (8 * kept)) - 1ull));   // the kept steps' codes
                 const int nd = __popcll(kl & MCPM_PLANE(CAND_TRANS)), ni = __popcll(kl & MCPM_PLANE(CAND_INS)), nx = __popcll(kl & MCPM_PLANE(CAND_DEL));
@@ -397,7 +412,7 @@ __global__ void __launch_bounds__(32 * 10, 1) k2_spec(const ChainParams* __restr
         S.cache_valid = overflow ? 0 : 1; S.cache_sum = end_sum;
     }
     __syncthreads();
-    for (int j = tid; j < cap; j += T) { X[off + j] = xs[j]; Y[off + j] = ys[j]; Z[off + j] = zs[j]; ep_global[j] = ep[j]; }
+    for (int j = tid; j < cap; j += T) { X[off + j] = xs[j]; Y[off + j] = ys[j]; Z[off + j] = zs[j]; if (!LEAN) ep_global[j] = ep[j]; }
     if (book) states[chain] = S;
 #ifdef MCPM_SPEC_TIMING
     if (lane == 0 && a.rdf) for (int k = 0; k < 8; k++) a.rdf[(size_t)chain * MCPM_RDF_BINS + warp * 8 + k] = tacc[k];   // debug build only
@@ -406,18 +421,24 @@ __global__ void __launch_bounds__(32 * 10, 1) k2_spec(const ChainParams* __restr
 }
 
 size_t k2_spec_smem_bytes(int cap) { return (size_t)(4 * cap + 128) * sizeof(double); }
+size_t k2_pair_smem_bytes(int cap) { return (size_t)(3 * cap + 16) * sizeof(double); }
 
-cudaError_t launch_k2_spec(int rng_mode, bool pbz, int n_chains, const ChainParams* params, ChainState* states, const int* order,
+cudaError_t launch_k2_spec(int rng_mode, bool pbz, bool lean, int n_chains, const ChainParams* params, ChainState* states, const int* order,
                            double* X, double* Y, double* Z, const RunArgs& a, cudaStream_t stream) {
-    const size_t smem = k2_spec_smem_bytes(a.cap);
-    auto go = [&](auto kern) -> cudaError_t {
+    const size_t smem = lean ? k2_pair_smem_bytes(a.cap) : k2_spec_smem_bytes(a.cap);
+    auto go = [&](auto kern, int threads) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kern<<<n_chains, 320, smem, stream>>>(params, states, order, X, Y, Z, a);
+        kern<<<n_chains, threads, smem, stream>>>(params, states, order, X, Y, Z, a);
         return cudaGetLastError();
     };
-    if (rng_mode == MCPM_RNG_PHILOX) return pbz ? go(k2_spec<MCPM_RNG_PHILOX, true>) : go(k2_spec<MCPM_RNG_PHILOX, false>);
-    return pbz ? go(k2_spec<MCPM_RNG_REPLAY, true>) : go(k2_spec<MCPM_RNG_REPLAY, false>);
+    const bool ph = rng_mode == MCPM_RNG_PHILOX;
+    if (lean) {
+        if (ph) return pbz ? go(k2_spec<MCPM_RNG_PHILOX, true, 2, true>, 64) : go(k2_spec<MCPM_RNG_PHILOX, false, 2, true>, 64);
+        return pbz ? go(k2_spec<MCPM_RNG_REPLAY, true, 2, true>, 64) : go(k2_spec<MCPM_RNG_REPLAY, false, 2, true>, 64);
+    }
+    if (ph) return pbz ? go(k2_spec<MCPM_RNG_PHILOX, true, 8, false>, 320) : go(k2_spec<MCPM_RNG_PHILOX, false, 8, false>, 320);
+    return pbz ? go(k2_spec<MCPM_RNG_REPLAY, true, 8, false>, 320) : go(k2_spec<MCPM_RNG_REPLAY, false, 8, false>, 320);
 }
 
 }  // namespace mcpm

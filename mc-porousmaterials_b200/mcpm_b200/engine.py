@@ -112,7 +112,7 @@ class Engine:
         return np.array([[e.pair, e.many_body, e.wall, e.energy] for e in arr])
 
     def use_speculation(self, mode=-1):
-        """-1 automatic (few chains), 0 never, 1 whenever the launch qualifies (mcpm_use_speculation)."""
+        """-1 automatic (few chains), 0 never, 1 whenever the launch qualifies, 2 two-warp variant for one-warp chains (mcpm_use_speculation)."""
         check(self.L.mcpm_use_speculation(self.h, int(mode)))
 
     def use_dual_candidates(self, enable=True):

@@ -22,7 +22,7 @@ def first_divergence(a, b):
     return int(d[0]) if len(d) else -1
 
 
-@pytest.mark.parametrize("cache", [True, False, "subwarp", "spec", "dual"], ids=["cache", "nocache", "subwarp", "spec", "dual"])
+@pytest.mark.parametrize("cache", [True, False, "subwarp", "spec", "dual", "pair"], ids=["cache", "nocache", "subwarp", "spec", "dual", "pair"])
 @pytest.mark.parametrize("threads", [32, 64, 128, 256, 512])
 @pytest.mark.parametrize("name", ["c1t", "lowt", "bulkt"])
 def test_replay_trace_matches_reference_golden(mcpm, golden, name, threads, cache):
@@ -31,8 +31,8 @@ def test_replay_trace_matches_reference_golden(mcpm, golden, name, threads, cach
         pytest.skip("the sub-warp kernel runs one warp per chain")
     if cache == "spec" and threads != 32:
         pytest.skip("the speculative kernel has one CTA shape")
-    if cache == "dual" and threads != 32:
-        pytest.skip("the dual-candidate kernel only replaces the one-warp variant")
+    if cache in ("dual", "pair") and threads != 32:
+        pytest.skip("the dual-candidate and two-warp kernels only replace the one-warp variant")
     arrays, meta = golden
     mkey, start = TRACE_CASES[name]
     m = meta[mkey]
@@ -43,7 +43,7 @@ def test_replay_trace_matches_reference_golden(mcpm, golden, name, threads, cach
     with mcpm.Engine(1, 1024) as e:
         e.use_energy_cache(bool(cache))
         e.use_subwarp(cache == "subwarp")
-        e.use_speculation(1 if cache == "spec" else 0)
+        e.use_speculation({"spec": 1, "pair": 2}.get(cache, 0))
         e.use_dual_candidates(cache == "dual")
         e.set_system(s)
         e.set_positions(0, x, y, z)
@@ -98,11 +98,11 @@ def test_device_philox_stream_is_the_documented_one(mcpm):
             assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("cache", [True, False, "spec", "dual"], ids=["cache", "nocache", "spec", "dual"])
+@pytest.mark.parametrize("cache", [True, False, "spec", "dual", "pair"], ids=["cache", "nocache", "spec", "dual", "pair"])
 @pytest.mark.parametrize("threads", [32, 128])
 def test_philox_chain_follows_oracle(mcpm, golden, threads, cache):
     """Device Philox + Metropolis on the GPU == the C oracle fed with the same counter-based stream."""
-    if cache in ("spec", "dual") and threads != 32:
+    if cache in ("spec", "dual", "pair") and threads != 32:
         pytest.skip("one CTA shape")
     arrays, meta = golden
     s = system_from_meta(meta["c1"]["system"])
@@ -111,13 +111,13 @@ def test_philox_chain_follows_oracle(mcpm, golden, threads, cache):
     seed, nchains, sets, sps = 987654321, 3, 2, 1500
     with mcpm.Engine(nchains, 1024) as e:
         e.use_energy_cache(bool(cache))
-        e.use_speculation(1 if cache == "spec" else 0)
+        e.use_speculation({"spec": 1, "pair": 2}.get(cache, 0))
         e.use_dual_candidates(cache == "dual")
         e.set_system(s)
         for c in range(nchains):
             e.set_positions(c, x, y, z)
         stats, tr = e.run(1, sets, sps, seed=seed, trace=True, threads=threads, check_energy=1)
-        assert e.last_kernel_name() == {True: "k2_chains", False: "k2_chains", "spec": "k2_spec", "dual": "k2_dual"}[cache]
+        assert e.last_kernel_name() == {True: "k2_chains", False: "k2_chains", "spec": "k2_spec", "dual": "k2_dual", "pair": "k2_pair"}[cache]
         for c in range(nchains):
             o = O.COracle(s, 1024)
             o.set_positions(x, y, z)
@@ -134,7 +134,7 @@ def test_philox_chain_follows_oracle(mcpm, golden, threads, cache):
             assert st.pair_evals_algorithmic == ost["pair_evals"] - evals0    # what the reference's moves evaluate
             if not cache:      # with the energy cache fewer partner scans are needed (and the rebuild adds n*n)
                 assert st.pair_evals == ost["pair_evals"] - evals0
-            elif cache in ("spec", "dual"):   # discarded candidates are executed evaluations too
+            elif cache in ("spec", "dual", "pair"):   # discarded candidates are executed evaluations too
                 assert st.pair_evals > 0
             else:
                 assert st.pair_evals < ost["pair_evals"] - evals0 + len(x) ** 2
@@ -455,7 +455,7 @@ def test_speculative_moves_are_the_sequential_chain(mcpm, golden, start):
         x = y = z = np.zeros(0)
     nch, sets, sps = 3, 4, 5003
     out = []
-    for kernel, spec, threads in (("k2_chains", 0, 64), ("k2_spec", 1, 0), ("k2_dual", 0, 32)):
+    for kernel, spec, threads in (("k2_chains", 0, 64), ("k2_spec", 1, 0), ("k2_dual", 0, 32), ("k2_pair", 2, 32)):
         with mcpm.Engine(nch, 1024) as e:
             e.use_speculation(spec)
             e.use_dual_candidates(kernel == "k2_dual")
@@ -465,7 +465,7 @@ def test_speculative_moves_are_the_sequential_chain(mcpm, golden, start):
             stats, tr = e.run(1, sets, sps, seed=424242, trace=True, threads=threads, check_energy=1)
             assert e.last_kernel_name() == kernel
             out.append((tr.copy(), [e.get_positions(c) for c in range(nch)], stats))
-    for c, other in [(c, other) for c in range(nch) for other in (1, 2)]:
+    for c, other in [(c, other) for c in range(nch) for other in (1, 2, 3)]:
         assert first_divergence(out[0][0][c], out[other][0][c]) == -1
         for a, b in zip(out[0][1][c], out[other][1][c]):
             assert np.array_equal(a, b)
