@@ -601,7 +601,12 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     // Automatic choice: chains that cannot fill the GPU anyway, and small enough that a candidate's scan by one warp is latency-
     // rather than FP64-throughput-bound (measured: 2.6-3x faster at N <= 600, break-even near N ~ 5000 where the discarded
     // candidates' evaluations cost as much as the latency they hide).
-    const bool use_pair = c->use_spec == 2 && !use_k2c && threads == 32 && cache_now && all_fast && !sample && !global_path && same_pbz;
+    // Two-warp speculative chains: when one warp per chain was chosen but at most 8 chains share an SM (one wave, e.g. config C5),
+    // a second warp per chain evaluating the following step uses issue slots that would otherwise idle (+12 % measured on C5);
+    // with more chains per SM it costs residency (128 registers -> 8 chains per SM) and loses.
+    const int per_sm = (c->n_chains + c->num_sms - 1) / c->num_sms;
+    const bool pair_wanted = c->use_spec == 2 || (c->use_spec < 0 && p->threads_per_chain == 0 && per_sm <= 8 && c->n_chains > c->num_sms);
+    const bool use_pair = pair_wanted && !use_k2c && k2_pair_smem_bytes(c->cap) <= (size_t)c->max_smem && threads == 32 && cache_now && all_fast && !sample && !global_path && same_pbz;
     const bool use_spec = !use_pair && spec_ok && (c->use_spec == 1 || (c->use_spec < 0 && cache_now && p->threads_per_chain == 0 && c->n_chains <= c->num_sms && maxn <= 2048));
     if (use_spec) cache_now = true;
     if (cache_now && !c->d_ep) CU(cudaMalloc(&c->d_ep, sizeof(double) * (size_t)c->n_chains * c->cap));

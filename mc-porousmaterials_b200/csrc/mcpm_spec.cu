@@ -154,7 +154,7 @@ __device__ __forceinline__ Cand evaluate_candidate(const Draws& rng, const Chain
 //   twice the warps are there to hide each other's latencies, and a round advances the chain by 2 - p steps.  Thread 0 keeps
 //   the books, the last warp refills the uniform ring 8 steps at a time.
 template <int RNG_MODE, bool PBZ, int KW, bool LEAN>
-__global__ void __launch_bounds__(32 * (LEAN ? KW : KW + 2), LEAN ? 11 : 1) k2_spec(const ChainParams* __restrict__ params,
+__global__ void __launch_bounds__(32 * (LEAN ? KW : KW + 2), LEAN ? 8 : 1) k2_spec(const ChainParams* __restrict__ params,
                                                                                    ChainState* __restrict__ states,
                                                                                    const int* __restrict__ order, double* X, double* Y, double* Z,
                                                                                    RunArgs a) {
