@@ -190,9 +190,10 @@ int mcpm_use_subwarp(mcpm_ctx* ctx, int enable);
  * uniforms per step index, same decisions, same trace).  mode -1 (default): chosen automatically when the context has
  * no more chains than the device has SMs, none larger than 2048 particles, threads_per_chain is 0 and the energy cache is in use; 0: never; 1: whenever
  * the launch qualifies (energy cache enabled, coordinates inside the box, no in-kernel sampling, shared-memory
- * positions); 2: the two-warp variant for one-warp chains whenever the launch qualifies — two candidate warps and nothing else
- * per chain, 8 chains per SM.  Chosen automatically (mode -1) when one warp per chain was picked and at most 8 chains share an
- * SM (+12 % on config C5); with more chains per SM it costs residency and is 30 % slower than one warp per chain (config C2).
+ * positions); 2 / 4: the LEAN variants whenever the launch qualifies — two / four candidate warps and nothing else per chain,
+ * energy cache in global memory, 8 / 4 chains per SM.  Chosen automatically (mode -1) when more chains than SMs but at most
+ * 8 (two warps) or 4 (four warps) share an SM (+12 % on config C5); with more chains per SM they cost residency and are 30 %
+ * slower than one warp per chain (config C2).
  * Replaces nothing in the reference: it is a schedule of src/main.cpp:66-71. */
 int mcpm_use_speculation(mcpm_ctx* ctx, int mode);
 /* EXPERIMENTAL, default off (measured 25 % slower than the default kernel on config C2 in round 1: the selection and

@@ -605,8 +605,11 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     // a second warp per chain evaluating the following step uses issue slots that would otherwise idle (+12 % measured on C5);
     // with more chains per SM it costs residency (128 registers -> 8 chains per SM) and loses.
     const int per_sm = (c->n_chains + c->num_sms - 1) / c->num_sms;
-    const bool pair_wanted = c->use_spec == 2 || (c->use_spec < 0 && p->threads_per_chain == 0 && per_sm <= 8 && c->n_chains > c->num_sms);
-    const bool use_pair = pair_wanted && !use_k2c && k2_pair_smem_bytes(c->cap) <= (size_t)c->max_smem && threads == 32 && cache_now && all_fast && !sample && !global_path && same_pbz;
+    // (2-4 chains per SM: four candidate warps per chain.)  The thread count picked for the one-step kernel does not matter here.
+    const bool lean_auto = c->use_spec < 0 && p->threads_per_chain == 0 && per_sm <= 8 && c->n_chains > c->num_sms && maxn <= 2048;
+    const bool pair_wanted = c->use_spec == 2 || c->use_spec == 4 || lean_auto;
+    const int lean_width = c->use_spec == 4 ? 4 : (c->use_spec == 2 ? 2 : (per_sm <= 4 ? 4 : 2));
+    const bool use_pair = pair_wanted && !use_k2c && k2_pair_smem_bytes(c->cap) <= (size_t)c->max_smem && (threads == 32 || lean_auto || c->use_spec == 4) && cache_now && all_fast && !sample && !global_path && same_pbz;
     const bool use_spec = !use_pair && spec_ok && (c->use_spec == 1 || (c->use_spec < 0 && cache_now && p->threads_per_chain == 0 && c->n_chains <= c->num_sms && maxn <= 2048));
     if (use_spec) cache_now = true;
     if (cache_now && !c->d_ep) CU(cudaMalloc(&c->d_ep, sizeof(double) * (size_t)c->n_chains * c->cap));
@@ -637,7 +640,7 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     const bool use_sub = c->use_subwarp && threads == 32 && cache_now && all_fast && !sample && !global_path && same_pbz;
     CU(cudaEventRecord(c->ev0, c->stream));
     const bool use_dual = c->use_dual && !use_k2c && !use_spec && !use_sub && threads == 32 && cache_now && all_fast && !sample && !global_path && same_pbz;
-    c->last_kernel = use_k2c ? "k2_cells" : use_pair ? "k2_pair" : use_spec ? "k2_spec" : (use_sub ? "k2_sub" : (use_dual ? "k2_dual" : "k2_chains"));
+    c->last_kernel = use_k2c ? "k2_cells" : use_pair ? (lean_width == 4 ? "k2_quad" : "k2_pair") : use_spec ? "k2_spec" : (use_sub ? "k2_sub" : (use_dual ? "k2_dual" : "k2_chains"));
     if (use_k2c) {
         bool widom = false;
         for (int k = 0; k < c->n_chains; k++) widom = widom || c->h_params[k].n_swap == 0;
@@ -648,10 +651,10 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
         CU(launch_k2_dual(p->rng_mode, c->h_params[0].pbc[2] != 0, c->n_chains, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->stream));
         c->launches++;
     } else if (use_pair) {
-        CU(launch_k2_spec(p->rng_mode, c->h_params[0].pbc[2] != 0, true, c->n_chains, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->stream));
+        CU(launch_k2_spec(p->rng_mode, c->h_params[0].pbc[2] != 0, lean_width, c->n_chains, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->stream));
         c->launches++;
     } else if (use_spec) {
-        CU(launch_k2_spec(p->rng_mode, c->h_params[0].pbc[2] != 0, false, c->n_chains, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->stream));
+        CU(launch_k2_spec(p->rng_mode, c->h_params[0].pbc[2] != 0, 0, c->n_chains, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->stream));
         c->launches++;
     } else if (use_sub) {
         const int cap_cta = ((c->cap + 127) / 128) * 128;
@@ -790,7 +793,7 @@ int mcpm_use_dual_candidates(mcpm_ctx* c, int enable) {
 
 int mcpm_use_speculation(mcpm_ctx* c, int mode) {
     if (!c) return fail(MCPM_ERR_ARG, "null context");
-    if (mode < -1 || mode > 2) return fail(MCPM_ERR_ARG, "speculation mode must be -1 (automatic), 0 (off), 1 (on) or 2 (two-warp variant for one-warp chains)");
+    if (mode < -1 || (mode > 2 && mode != 4)) return fail(MCPM_ERR_ARG, "speculation mode must be -1 (automatic), 0 (off), 1 (on), 2 or 4 (lean variants with 2 / 4 candidate warps per chain)");
     c->use_spec = mode;
     return MCPM_OK;
 }

@@ -26,7 +26,7 @@ cudaError_t launch_k2_sub(int rng_mode, bool pbz, int n_ctas, const ChainParams*
 // mcpm_spec.cu: speculative-moves kernel, one CTA of 8 candidate warps + 2 helper warps per chain
 size_t k2_spec_smem_bytes(int cap);
 size_t k2_pair_smem_bytes(int cap);
-cudaError_t launch_k2_spec(int rng_mode, bool pbz, bool lean, int n_chains, const ChainParams* params, ChainState* states, const int* order,
+cudaError_t launch_k2_spec(int rng_mode, bool pbz, int lean, int n_chains, const ChainParams* params, ChainState* states, const int* order,
                            double* X, double* Y, double* Z, const RunArgs& a, cudaStream_t stream);
 
 // mcpm_dual.cu: one warp per chain, two candidate steps per round

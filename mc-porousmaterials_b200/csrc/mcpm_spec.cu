@@ -154,7 +154,7 @@ __device__ __forceinline__ Cand evaluate_candidate(const Draws& rng, const Chain
 //   twice the warps are there to hide each other's latencies, and a round advances the chain by 2 - p steps.  Thread 0 keeps
 //   the books, the last warp refills the uniform ring 8 steps at a time.
 template <int RNG_MODE, bool PBZ, int KW, bool LEAN>
-__global__ void __launch_bounds__(32 * (LEAN ? KW : KW + 2), LEAN ? 8 : 1) k2_spec(const ChainParams* __restrict__ params,
+__global__ void __launch_bounds__(32 * (LEAN ? KW : KW + 2), LEAN ? 16 / KW : 1) k2_spec(const ChainParams* __restrict__ params,
                                                                                    ChainState* __restrict__ states,
                                                                                    const int* __restrict__ order, double* X, double* Y, double* Z,
                                                                                    RunArgs a) {
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(32 * (LEAN ? KW : KW + 2), LEAN ? 8 : 1) k2_sp
 size_t k2_spec_smem_bytes(int cap) { return (size_t)(4 * cap + 128) * sizeof(double); }
 size_t k2_pair_smem_bytes(int cap) { return (size_t)(3 * cap + 16) * sizeof(double); }
 
-cudaError_t launch_k2_spec(int rng_mode, bool pbz, bool lean, int n_chains, const ChainParams* params, ChainState* states, const int* order,
+cudaError_t launch_k2_spec(int rng_mode, bool pbz, int lean /* 0, or candidate warps of the lean variant: 2 or 4 */, int n_chains, const ChainParams* params, ChainState* states, const int* order,
                            double* X, double* Y, double* Z, const RunArgs& a, cudaStream_t stream) {
     const size_t smem = lean ? k2_pair_smem_bytes(a.cap) : k2_spec_smem_bytes(a.cap);
     auto go = [&](auto kern, int threads) -> cudaError_t {
@@ -433,6 +433,10 @@ cudaError_t launch_k2_spec(int rng_mode, bool pbz, bool lean, int n_chains, cons
         return cudaGetLastError();
     };
     const bool ph = rng_mode == MCPM_RNG_PHILOX;
+    if (lean == 4) {
+        if (ph) return pbz ? go(k2_spec<MCPM_RNG_PHILOX, true, 4, true>, 128) : go(k2_spec<MCPM_RNG_PHILOX, false, 4, true>, 128);
+        return pbz ? go(k2_spec<MCPM_RNG_REPLAY, true, 4, true>, 128) : go(k2_spec<MCPM_RNG_REPLAY, false, 4, true>, 128);
+    }
     if (lean) {
         if (ph) return pbz ? go(k2_spec<MCPM_RNG_PHILOX, true, 2, true>, 64) : go(k2_spec<MCPM_RNG_PHILOX, false, 2, true>, 64);
         return pbz ? go(k2_spec<MCPM_RNG_REPLAY, true, 2, true>, 64) : go(k2_spec<MCPM_RNG_REPLAY, false, 2, true>, 64);

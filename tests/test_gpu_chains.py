@@ -455,7 +455,7 @@ def test_speculative_moves_are_the_sequential_chain(mcpm, golden, start):
         x = y = z = np.zeros(0)
     nch, sets, sps = 3, 4, 5003
     out = []
-    for kernel, spec, threads in (("k2_chains", 0, 64), ("k2_spec", 1, 0), ("k2_dual", 0, 32), ("k2_pair", 2, 32)):
+    for kernel, spec, threads in (("k2_chains", 0, 64), ("k2_spec", 1, 0), ("k2_dual", 0, 32), ("k2_pair", 2, 32), ("k2_quad", 4, 0)):
         with mcpm.Engine(nch, 1024) as e:
             e.use_speculation(spec)
             e.use_dual_candidates(kernel == "k2_dual")
@@ -465,7 +465,7 @@ def test_speculative_moves_are_the_sequential_chain(mcpm, golden, start):
             stats, tr = e.run(1, sets, sps, seed=424242, trace=True, threads=threads, check_energy=1)
             assert e.last_kernel_name() == kernel
             out.append((tr.copy(), [e.get_positions(c) for c in range(nch)], stats))
-    for c, other in [(c, other) for c in range(nch) for other in (1, 2, 3)]:
+    for c, other in [(c, other) for c in range(nch) for other in (1, 2, 3, 4)]:
         assert first_divergence(out[0][0][c], out[other][0][c]) == -1
         for a, b in zip(out[0][1][c], out[other][1][c]):
             assert np.array_equal(a, b)
@@ -603,3 +603,28 @@ def test_metropolis_screen_never_changes_a_decision(mcpm, kind):
             bad = np.nonzero(sure & (got != want))[0]
             assert len(bad) == 0, f"{len(bad)} wrong decisions, first: u={u[bad[0]]!r} x={x[bad[0]]!r} n={nn[bad[0]]} f={f[bad[0]]!r}"
             assert sure.mean() > 0.5
+
+
+@pytest.mark.parametrize("nch,kernel", [(300, "k2_quad"), (1000, "k2_pair"), (1500, "k2_chains")])
+def test_lean_speculation_is_chosen_by_chains_per_sm(mcpm, golden, nch, kernel):
+    """Automatic mode between 'fewer chains than SMs' (k2_spec) and 'more than 8 chains per SM' (one warp per chain): four or two
+    candidate warps per chain.  Same chains as the one-step kernel."""
+    arrays, meta = golden
+    s = system_from_meta(meta["c1"]["system"])
+    x, y, z = arrays["c1_x"][:200], arrays["c1_y"][:200], arrays["c1_z"][:200]
+    out = []
+    for mode in (-1, 0):
+        with mcpm.Engine(nch, 256) as e:
+            e.use_speculation(mode)
+            e.set_system(s)
+            for c in range(nch):
+                e.set_positions(c, x, y, z)
+            st = e.run(50, 1, 700, seed=11, check_energy=1)
+            if mode == -1:
+                assert e.last_kernel_name() == kernel          # 148 SMs: 3, 7 and 11 chains per SM
+            out.append([(q.n, q.tot_disp_acc, q.tot_ins_acc, q.tot_del_acc, q.sum_n) for q in st[:5]] + [e.get_positions(3)])
+            for q in st[:5]:
+                assert q.energy == pytest.approx(q.energy_check, rel=RTOL)
+    assert out[0][:5] == out[1][:5]
+    for a, b in zip(out[0][5], out[1][5]):
+        assert np.array_equal(a, b)
