@@ -9,6 +9,7 @@ for c in c2 c1 c5 c3 c4; do
   python bench.py --config $c --steps 5 --warmup 3 2> $OUT/bench_$c.err | tail -1 > $OUT/bench_$c.json; echo "bench $c rc=$?"
 done
 python bench.py --replicas 1 --steps 5 --warmup 3 --no-cpu 2> $OUT/bench_c2_r1.err | tail -1 > $OUT/bench_c2_r1.json
+python bench.py --replicas 8 --steps 5 --warmup 3 --no-cpu 2> $OUT/bench_c2_r8.err | tail -1 > $OUT/bench_c2_r8.json
 python bench.py --impl reference --steps 2 --warmup 1 2> $OUT/bench_ref.err | tail -1 > $OUT/bench_ref.json
 python scripts/latency_table.py 40 > $OUT/latency_40.txt 2>&1
 # ncu: only after the same commands exited 0 above
