@@ -55,7 +55,7 @@ def build_workload(config, replicas, steps_per_set):
         if config == "c1":
             pts = pts[-1:]                       # mu = -1134 K
             w["workload"] = "C1 Ar in graphite slit, single mu=-1134 K (H=20A, rcut=20A, T=87K, N~560, disp:swap=1:1)"
-            w["replicas"] = replicas or 1920
+            w["replicas"] = replicas or 1776       # identical chains: one per resident slot (12 chains x 148 SMs); 1920 would run a second, nearly empty wave
         else:
             w["workload"] = "C2 40-point Ar isotherm (mu_k=-1800+k*666/39 K, H=20A, rcut=20A, T=87K, disp:swap=1:1)"
             w["replicas"] = replicas or 128
