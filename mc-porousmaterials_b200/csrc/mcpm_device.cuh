@@ -138,6 +138,46 @@ __device__ __forceinline__ void wall_two(const ChainParams& P, double z_a, doubl
     }
 }
 
+// wall_two fused with the warp all-reduce of one scan partial `v` (one-warp chains): the two shuffle trees are independent, so
+// their stages are issued together and the wall's reduction hides behind the longer one of v.  (butterfly in ascending order: every
+// lane still ends with the same bits.)
+__device__ __forceinline__ void wall_two_and_sum(const ChainParams& P, double z_a, double z_b, double& w_a, double& w_b, double& v, int lane) {
+    double acc = 0.0;
+    const bool slit_lj = (P.wall_kind == MCPM_WALL_SLIT_LJ && P.geometry == MCPM_GEOM_SLIT);
+    if (slit_lj) {
+        double zc = ((lane & 8) ? z_b : z_a) - P.halfH;
+        if (lane & 1) zc = -zc;
+        const int layer0 = (lane >> 1) & 3;
+        if (P.n_layers <= 4) {
+            const double t = P.sig_sf * fast_rcp(P.halfH + layer0 * P.delta + zc);
+            const double t2 = t * t, t4 = t2 * t2;
+            const double term = 0.2 * (t4 * t4 * t2) - 0.5 * t4;
+            acc = (lane < 16 && layer0 < P.n_layers) ? term : 0.0;
+        } else if (lane < 16) {
+            for (int layer = layer0; layer < P.n_layers; layer += 4) {
+                double t = P.sig_sf * fast_rcp(P.halfH + layer * P.delta + zc);
+                double t2 = t * t, t4 = t2 * t2;
+                acc += 0.2 * (t4 * t4 * t2) - 0.5 * t4;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 1; o <= 4; o <<= 1) {
+        const double pv = __shfl_xor_sync(MCPM_FULL_MASK, v, o), pa = __shfl_xor_sync(MCPM_FULL_MASK, acc, o);
+        v += pv; acc += pa;
+    }
+    const double a0 = __shfl_sync(MCPM_FULL_MASK, acc, 0), a8 = __shfl_sync(MCPM_FULL_MASK, acc, 8);
+    v += __shfl_xor_sync(MCPM_FULL_MASK, v, 8);
+    v += __shfl_xor_sync(MCPM_FULL_MASK, v, 16);
+    w_a = a0 * P.wall_pref;
+    w_b = a8 * P.wall_pref;
+    if (P.geometry == MCPM_GEOM_SLIT) {  // out-of-pore guard: finite INT_MAX, wall still added (quirk Q6)
+        double za = z_a - P.halfH, zb = z_b - P.halfH;
+        if (za * za > P.sqr_pore_r) w_a = MCPM_INT_MAX_D + w_a;
+        if (zb * zb > P.sqr_pore_r) w_b = MCPM_INT_MAX_D + w_b;
+    }
+}
+
 // Serial single-thread version (K3 computes one wall term per particle per thread).
 __device__ __forceinline__ double wall_one(const ChainParams& P, double z) {
     double boxE = 0.0;

@@ -112,9 +112,14 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                 if (CACHE) {
                     const double ep_i = (n > 0) ? ep[i] : 0.0;                    // old pair sum from the cache (issued before the scan)
                     v[1] = pair_sum1<FAST, PBZ>(xs, ys, zs, n, i, g, xn, yn, zn, tid, T);
-                    wall_two(P, zo, zn, wo, wn, lane);
                     double w1[1] = {v[1]};
-                    cta_allsum<1, MULTI>(w1, partials, parity, W, warp, lane); parity ^= 1;
+                    if (MULTI) {
+                        wall_two(P, zo, zn, wo, wn, lane);
+                        cta_allsum<1, MULTI>(w1, partials, parity, W, warp, lane); parity ^= 1;
+                    } else {
+                        wall_two_and_sum(P, zo, zn, wo, wn, w1[0], lane);     // one warp: wall and scan reductions interleaved
+                        __syncwarp();
+                    }
                     v[0] = ep_i; v[1] = w1[0];
                     sc.evals += (unsigned long long)n;
                 } else {
@@ -167,8 +172,13 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                     double v[1];
                     v[0] = pair_sum1<FAST, PBZ>(xs, ys, zs, n, -1, g, xi, yi, zi, tid, T);
                     double wi, wdummy;
-                    wall_two(P, zi, zi, wi, wdummy, lane);
-                    cta_allsum<1, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
+                    if (MULTI) {
+                        wall_two(P, zi, zi, wi, wdummy, lane);
+                        cta_allsum<1, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
+                    } else {
+                        wall_two_and_sum(P, zi, zi, wi, wdummy, v[0], lane);
+                        __syncwarp();
+                    }
                     const double pi_ = eps4 * v[0];
                     const double e_in = pi_ + wi;
                     const bool acc = metropolis_insertion(u_a, -(e_in * beta), ln_zzV, zzV, n);   // src/moves.cpp:306-307
