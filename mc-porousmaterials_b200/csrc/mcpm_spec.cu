@@ -106,9 +106,8 @@ __device__ __forceinline__ Cand evaluate_candidate(const Draws& rng, const Chain
                               : pair_sum_wide<true, PBZ, 8>(xs, ys, zs, n, i, g, xn, yn, zn, lane, 32);
         SPEC_PROBE(3, v);
         double wo, wn;
-        wall_two(P, zo, zn, wo, wn, lane);
+        wall_two_and_sum(P, zo, zn, wo, wn, v, lane);      // wall and scan reductions interleaved
         SPEC_PROBE(4, wo + wn);
-        v = warp_allsum(v);
         SPEC_PROBE(5, v);
         const double po = P.eps4 * ep_i, pn = P.eps4 * v;
         const double dE = (pn + wn) - (po + wo);                                          // src/moves.cpp:169
@@ -126,8 +125,7 @@ __device__ __forceinline__ Cand evaluate_candidate(const Draws& rng, const Chain
                      : (n <= 128) ? pair_sum_wide<true, PBZ, 4>(xs, ys, zs, n, -1, g, xi, yi, zi, lane, 32)
                                   : pair_sum_wide<true, PBZ, 8>(xs, ys, zs, n, -1, g, xi, yi, zi, lane, 32);
             double wi, wd;
-            wall_two(P, zi, zi, wi, wd, lane);
-            v = warp_allsum(v);
+            wall_two_and_sum(P, zi, zi, wi, wd, v, lane);
             const double pi_ = P.eps4 * v;
             c.type = CAND_INS; c.acc = metropolis_insertion(u_a, -((pi_ + wi) * P.beta), P.ln_zzV, P.zzV, n) ? 1 : 0; c.idx = n;   // src/moves.cpp:306
             c.px = xi; c.py = yi; c.pz = zi; c.v = v; c.pn = pi_; c.wn = wi;
