@@ -48,6 +48,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
     const bool widom_on = SAMPLE && (P.n_swap == 0);   // ComputeWidom acts only without swap moves, src/moves.cpp:415
 
     int n = st.n;
+    double nd = (double)n;            // n as a double, kept in step (the conversion would sit on every step's critical path)
     double dr = st.dr, e_pair = st.pair, e_wall = st.wall;
     unsigned long long step = st.steps_done;
     int overflow = 0;
@@ -99,7 +100,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                 const double u_i = rng.template at<3>(), u_x = rng.template at<4>(), u_y = rng.template at<5>(),
                              u_z = rng.template at<6>(), u_a = rng.template at<7>();
                 rng.end_step(8);
-                const int i = (int)(u_i * (double)n);                             // int(u*n)+1 on 1-based slots; n==0 -> stale slot (Q12)
+                const int i = (int)(u_i * nd);                             // int(u*n)+1 on 1-based slots; n==0 -> stale slot (Q12)
                 double xo, yo, zo;
                 load_sel(xs, ys, zs, i, fwd, xo, yo, zo);
                 const double xr = __dadd_rn(xo, __dmul_rn(u_x - 0.5, dr)), yr = __dadd_rn(yo, __dmul_rn(u_y - 0.5, dr));
@@ -191,7 +192,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                             if ((n & tmask) == tid) ep[n] = v[0];
                             sc.evals += (unsigned long long)n;
                         }
-                        sc.acc_ins++; n++; e_pair += pi_; e_wall += wi;
+                        sc.acc_ins++; n++; nd += 1.0; e_pair += pi_; e_wall += wi;
                         if (CACHE && cta_sync_or<MULTI>(big)) {
                             double cp, cw;
                             cache_fill<FAST, PBZ, MULTI>(xs, ys, zs, ep, n, P, g, partials, W, warp, lane, tid, T, cp, cw);
@@ -203,7 +204,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                 } else if (n > 0) {
                     const double u_o = rng.template at<3>(), u_a = rng.template at<4>();
                     rng.end_step(5);
-                    const int o = (int)(u_o * (double)n + 1.0) - 1;               // int(u*n+1) on 1-based slots
+                    const int o = (int)(u_o * nd + 1.0) - 1;               // int(u*n+1) on 1-based slots
                     double xo, yo, zo, xl = 0., yl = 0., zl = 0.;
                     load_sel(xs, ys, zs, o, fwd, xo, yo, zo);
                     if (!NOFWD) load_slot(xs, ys, zs, n - 1, fwd, xl, yl, zl);    // the particle that would fill the hole
@@ -236,7 +237,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                         if (NOFWD && (o & tmask) == tid) { xl = xs[n - 1]; yl = ys[n - 1]; zl = zs[n - 1]; }   // read only when needed, by the writer
                         if ((o & tmask) == tid) { xs[o] = xl; ys[o] = yl; zs[o] = zl; }  // swap-with-last, src/moves.cpp:329
                         fwd.slot = o; fwd.x = xl; fwd.y = yl; fwd.z = zl;
-                        n--;
+                        n--; nd -= 1.0;
                         e_pair -= po; e_wall -= wo;   // exact bookkeeping with the fresh energies (quirks Q3, Q16 fixed)
                         if (CACHE) {
                             cta_sync<MULTI>();                                      // the moved entry and slot are visible
@@ -315,7 +316,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
             }
             if (lead && trace) trace[(unsigned long long)(set - a.first_set) * (unsigned long long)a.steps_per_set + (unsigned long long)s] = (unsigned char)code;
             if (production) {
-                const double dn = (double)n, e = e_pair + e_wall;
+                const double dn = nd, e = e_pair + e_wall;
                 if (!SAMPLE) {   // replicated in registers like the energies: no divergent read-modify-write of shared memory per step
                     sum_n += dn; sum_n2 += dn * dn; sum_e += e; sum_e2 += e * e;
                     samples++;
