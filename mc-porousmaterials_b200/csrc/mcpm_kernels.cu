@@ -37,6 +37,18 @@ namespace mcpm {
 // nothing but the partner loop's partial sums crosses threads.  (A variant that kept counters and
 // energies in shared memory for thread 0 only used 80 registers instead of 128 but was 10-15 % slower at
 // every occupancy measured on B200: the extra LDS/STS sit on the per-step critical path.)
+#ifdef MCPM_K2_TIMING   // phase timing of a translation step (scripts/k2_timing.py); the probes serialise the phases they separate
+__device__ __forceinline__ long long k2_probe(double x) {   // clock read that cannot issue before x is available
+    if (__double_as_longlong(x) == 0x7ff8dead00000001ll) asm volatile("trap;");
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory");
+    return t;
+}
+#define K2_PROBE(k, x) tp[k] = k2_probe(x)
+#else
+#define K2_PROBE(k, x)
+#endif
+
 template <class Source, bool FAST, bool MULTI, bool PBZ, bool SAMPLE, bool CACHE>
 __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, double* xs, double* ys, double* zs, double* partials,
                            const RunArgs& a, unsigned char* trace, int cap, uint32_t chain, double* hist) {
@@ -88,6 +100,10 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
         if (lead) { st.widom_insert = st.widom_delete = 0.0; st.widom_insertions = st.widom_deletions = 1; }
         const bool production = set > P.n_equil;
         for (int s = 0; s < steps_per_set; s++) {
+#ifdef MCPM_K2_TIMING
+            long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            K2_PROBE(0, e_pair);
+#endif
             rng.begin_step(a.seed, chain, step, lane);
             step++;
             int code;
@@ -110,9 +126,11 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                 if (odd) { xn = wrap_floor(xr, Lx); yn = wrap_floor(yr, Ly); if (PBZ) zn = wrap_floor(zr, Lz); }
                 double v[2];
                 double wo, wn;
+                K2_PROBE(1, xn + yn + zn);
                 if (CACHE) {
                     const double ep_i = (n > 0) ? ep[i] : 0.0;                    // old pair sum from the cache (issued before the scan)
                     v[1] = pair_sum1<FAST, PBZ>(xs, ys, zs, n, i, g, xn, yn, zn, tid, T);
+                    K2_PROBE(2, v[1]);
                     double w1[1] = {v[1]};
                     if (MULTI) {
                         wall_two(P, zo, zn, wo, wn, lane);
@@ -129,9 +147,11 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                     cta_allsum<2, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
                     sc.evals += 2ull * (unsigned long long)n;
                 }
+                K2_PROBE(3, v[1] + wn + wo);
                 const double po = eps4 * v[0], pn = eps4 * v[1];
                 const double dE = (pn + wn) - (po + wo);                          // newEnergy - oldEnergy, src/moves.cpp:169
                 const bool acc = metropolis_translation(u_a, dE * beta);          // u < exp(-dE/T), src/moves.cpp:170-172
+                K2_PROBE(4, acc ? 1.0 : 2.0);
                 sc.n_disp++; sc.alg += 2ull * (unsigned long long)n;
                 fwd.slot = -1;
                 if (acc) {
@@ -314,6 +334,14 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                 cta_rdf<PBZ>(xs, ys, zs, n, P, hist, tid, T);
                 __syncthreads();
             }
+#ifdef MCPM_K2_TIMING
+            if (lane == 0 && warp == 0 && tp[4] != 0 && a.rdf) {
+                const long long tend = k2_probe(e_pair + e_wall);
+                double* o = a.rdf + (size_t)chain * MCPM_RDF_BINS;
+                o[0] += (double)(tp[1] - tp[0]); o[1] += (double)(tp[2] - tp[1]); o[2] += (double)(tp[3] - tp[2]); o[3] += (double)(tp[4] - tp[3]);
+                o[4] += (double)(tend - tp[4]); o[5] += 1.0;
+            }
+#endif
             if (lead && trace) trace[(unsigned long long)(set - a.first_set) * (unsigned long long)a.steps_per_set + (unsigned long long)s] = (unsigned char)code;
             if (production) {
                 const double dn = nd, e = e_pair + e_wall;
