@@ -335,8 +335,10 @@ __device__ __forceinline__ double wrap_floor(double x, double L) {
 // the coordinate with wrap_floor (one rare, warp-uniform branch for all three coordinates).
 __device__ __forceinline__ double wrap_select(double x, double L, bool& odd) {
     odd = odd || !(x >= -L && x < L + L);
-    const double q = (x < 0.0) ? -1.0 : ((x >= L) ? 1.0 : 0.0);
-    return __dsub_rn(x, __dmul_rn(q, L));
+    // x - 0*L == x exactly, so the in-box case (by far the most frequent) is a plain select: the add/subtract of L is evaluated
+    // beside the two comparisons instead of behind a compare -> select q -> multiply -> subtract chain
+    const double up = __dadd_rn(x, L), down = __dsub_rn(x, L);   // == x - (-1)*L and x - 1*L (the products are exact)
+    return (x < 0.0) ? up : ((x >= L) ? down : x);
 }
 
 // Metropolis tests without a logarithm and (mostly) without an exponential.  The reference tests `u < f` with
