@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MCPM_VERSION 100
+#define MCPM_VERSION 200
 
 enum {
     MCPM_OK = 0,
@@ -90,6 +90,9 @@ typedef struct mcpm_run_params {
                                   histogram out to rcut, accumulated per chain; read it with mcpm_get_rdf */
     int check_energy;          /* 1: recompute the full box energy on the device at the end (drift check, reported in
                                   *_check); 2: also adopt it as the running energy, as MC::BoxEnergy does */
+    int no_sampling;           /* !=0: moves only — no ComputeWidom / ComputeRDF after the steps even where the reference's
+                                  step loop would sample (src/main.cpp:72-75).  MC::MinimizeEnergy (src/energy.cpp:13-34) is
+                                  such a loop: it calls MoveParticle and nothing else. */
 } mcpm_run_params;
 
 /* Per-chain result of mcpm_run.  Per-set counters follow MC::Stats after the LAST set of the call
@@ -115,6 +118,8 @@ typedef struct mcpm_chain_stats {
      * n_swap == 0, in production sets; ResetStats restarts the counts at ONE and the sums at 0 every set) */
     double widom_insert, widom_delete;
     long long widom_insertions, widom_deletions;
+    double dr_used;            /* translation amplitude in effect DURING the last set (the reference prints its statistics
+                                  before AdjustMCMoves changes it, src/main.cpp:77-83); `dr` above is the value after it */
 } mcpm_chain_stats;
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -177,13 +182,6 @@ int mcpm_get_stats(mcpm_ctx* ctx, mcpm_chain_stats* stats /* [n_chains] */);
  * 1.5 N pair evaluations per step at 20 % translation acceptance.  enable = 0 re-sums both energies every move, exactly
  * like MC::MoveParticle / MC::SwapParticle. */
 int mcpm_use_energy_cache(mcpm_ctx* ctx, int enable);
-/* EXPERIMENTAL, default off.  With one warp per chain (threads_per_chain 32) an alternative K2 kernel packs 2 or 4 small
- * chains into one warp (16 or 8 lanes each) and runs translation / insertion / deletion as one branch-free code path,
- * so that the per-step work that does not scale with N is shared by the chains of a warp.  Chains that outgrow their
- * slot during a launch finish the call in a warp of their own.  Same chain and results (tested against the same golden
- * traces); measured on B200 it is 1.7-2x SLOWER than the default kernel in round 1 (more instructions per step and
- * longer dependent chains outweigh the sharing), see DESIGN.md. */
-int mcpm_use_subwarp(mcpm_ctx* ctx, int enable);
 /* Speculative moves (the latency kernel for FEW chains, e.g. one chain per isotherm point): a CTA of 8 warps evaluates
  * the next 8 steps of its chain concurrently against the same configuration, commits the first accepted one and
  * re-evaluates the steps after it; rejected steps before it stand.  The chain is exactly the sequential one (same
@@ -196,14 +194,6 @@ int mcpm_use_subwarp(mcpm_ctx* ctx, int enable);
  * slower than one warp per chain (config C2).
  * Replaces nothing in the reference: it is a schedule of src/main.cpp:66-71. */
 int mcpm_use_speculation(mcpm_ctx* ctx, int mode);
-/* EXPERIMENTAL, default off (measured 25 % slower than the default kernel on config C2 in round 1: the selection and
- * decision of the two candidates stay serial, only the scan gains parallelism, and 168 registers cost a resident chain
- * per SM).  With one warp per chain (the choice for many small chains) a round evaluates TWO consecutive steps
- * against the same configuration in one interleaved instruction stream (one partner loop for both trial positions, one
- * wall evaluation, one reduction); the second is used only if the first is rejected, else it is evaluated again next
- * round with the same uniforms.  Same chain as one step at a time; more instruction-level parallelism per warp.
- * Applies when the energy cache is in use, coordinates lie inside the box and nothing is sampled in-kernel. */
-int mcpm_use_dual_candidates(mcpm_ctx* ctx, int enable);
 int mcpm_reset_accumulators(mcpm_ctx* ctx);
 /* Accumulated pair-distance histogram of one chain: hist[0..99] = MC::Stats::rdf(0..99) (bin 0 is never filled,
  * each pair adds 2, src/sample.cpp:27-28).  mcpm_reset_accumulators clears it. */
@@ -214,6 +204,10 @@ int mcpm_chemical_potential(mcpm_ctx* ctx, int chain, double* mu_ex, double* mu)
  * positions whose energies the caller already knows (e.g. from the previous mcpm_run's statistics): skips the
  * full K3 evaluation that mcpm_run would otherwise do to initialise its exact bookkeeping. */
 int mcpm_set_running_energy(mcpm_ctx* ctx, const double* pair /* [n_chains] */, const double* wall /* [n_chains] */);
+/* Philox stream of every chain: the device stream is keyed by (seed, stream id, step).  Default: the chain's index inside
+ * the context.  A caller that shards one set of chains over several contexts / GPUs passes each chain's GLOBAL id here,
+ * so that no two chains of the job share a stream whatever the sharding (and results do not depend on it). */
+int mcpm_set_stream_ids(mcpm_ctx* ctx, const unsigned int* ids /* [n_chains] */);
 /* Override a chain's translation amplitude / global step counter (restart, tests). */
 int mcpm_set_dr(mcpm_ctx* ctx, int chain, double dr);
 int mcpm_set_step_counter(mcpm_ctx* ctx, int chain, unsigned long long step);
@@ -221,7 +215,7 @@ int mcpm_set_step_counter(mcpm_ctx* ctx, int chain, unsigned long long step);
 /* ---- measurement support ------------------------------------------------------------------ */
 /* Device time (CUDA events on the context's stream) and launch count of the last compute call. */
 int mcpm_last_kernel_ms(const mcpm_ctx* ctx, float* ms);
-/* Which K2 kernel the last mcpm_run launched: "k2_chains", "k2_spec" or "k2_sub" ("" before the first run). */
+/* Which K2 kernel the last mcpm_run launched: "k2_chains", "k2_spec", "k2_pair", "k2_quad" or "k2_cells" ("" before the first run). */
 const char* mcpm_last_kernel_name(const mcpm_ctx* ctx);
 int mcpm_launch_count(const mcpm_ctx* ctx, unsigned long long* launches);
 /* CUDA-event stopwatch on the context's stream: start records an event, stop records a second one,

@@ -16,9 +16,9 @@
 // Needs: energy cache, coordinates inside the box (fast image), shared-memory positions, no in-kernel sampling.
 #include <algorithm>
 
-#include "mcpm_chain.cuh"
-#include "mcpm_device.cuh"
-#include "mcpm_kernels.h"
+#include "../mcpm_chain.cuh"
+#include "../mcpm_device.cuh"
+#include "../mcpm_kernels.h"
 
 namespace mcpm {
 
@@ -331,6 +331,7 @@ __device__ void chain_loop_dual(const ChainParams& P, ChainState& S, Draws& rng,
             __syncwarp();              // a stale-slot write of this round is visible to the next selection (n == 0, quirk Q12)
             if (overflow) break;
         }
+        if (lead) st.dr_used = dr;          // the amplitude this set ran with (statistics are printed before the adjustment, src/main.cpp:77-83)
         // MC::AdjustMCMoves displacement part, src/moves.cpp:68-78 (ResetStats starts nDisplacements at ONE)
         if (!overflow && n > 0 && set <= P.n_equil) {
             const double ratio = (double)sc.acc_disp * 1. / (1. * (double)(sc.n_disp + 1));
@@ -384,7 +385,7 @@ __global__ void __launch_bounds__(32, 12) k2_dual(const ChainParams* __restrict_
     __syncwarp();
     unsigned char* trace = a.trace ? a.trace + (unsigned long long)chain * a.trace_stride : nullptr;
     if (RNG_MODE == MCPM_RNG_PHILOX) {
-        DualPhilox rng; rng.init(a.seed, (uint32_t)chain, S.st.steps_done, lane);
+        DualPhilox rng; rng.init(a.seed, S.stream_id, S.st.steps_done, lane);
         chain_loop_dual<DualPhilox, PBZ>(P, S, rng, xs, ys, zs, a, trace, cap, (uint32_t)chain);
     } else {
         DualReplay rng; rng.init(a.replay_u + (unsigned long long)chain * a.replay_stride, a.replay_stride);

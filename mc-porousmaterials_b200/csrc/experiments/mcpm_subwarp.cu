@@ -13,8 +13,8 @@
 // and are tested against the same golden traces of the compiled reference.
 #include <algorithm>
 
-#include "mcpm_device.cuh"
-#include "mcpm_kernels.h"
+#include "../mcpm_device.cuh"
+#include "../mcpm_kernels.h"
 
 namespace mcpm {
 
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(32, 16) k2_sub(const ChainParams* __restrict__
                                         if (set != set0) { /* counters of the previous set were flushed below */ } }
         const bool production = set > P.n_equil;
         for (int s = (set == set0 ? s0 : 0); s < steps_per_set; s++) {
-            if (RNG_MODE == MCPM_RNG_PHILOX) prng.begin_step(a.seed, (uint32_t)chain, step, l, G);
+            if (RNG_MODE == MCPM_RNG_PHILOX) prng.begin_step(a.seed, S.stream_id, step, l, G);
             // ---- what kind of step is this (src/main.cpp:67-70, src/moves.cpp:299,320) ----
             const double r = DRAW(0) * wsum;
             const bool is_t = alive && (r <= thr_disp);
@@ -329,6 +329,7 @@ __global__ void __launch_bounds__(32, 16) k2_sub(const ChainParams* __restrict__
             }
         }
         // MC::AdjustMCMoves displacement part, src/moves.cpp:68-78 (ResetStats starts nDisplacements at ONE)
+        if (lead && alive) st.dr_used = dr;
         if (alive && n > 0 && set <= P.n_equil) {
             const double ratio = (double)c_adisp * 1. / (1. * (double)(c_ndisp + 1));
             if (ratio < 0.2) dr /= 1.1;

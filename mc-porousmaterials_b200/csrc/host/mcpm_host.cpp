@@ -27,9 +27,9 @@
 
 #include "../../../include/mcpm.h"
 
-namespace {
+namespace mcpm { void set_last_error(const char* msg); }   // mcpm_api.cu: what mcpm_last_error() returns
 
-thread_local std::string g_host_err;
+namespace {
 
 // Tools::LowerCase, src/tools.h:19-30: lower-case, strip one trailing ';'.
 std::string lower(std::string s) {
@@ -66,10 +66,24 @@ struct RefRandom {
 
 }  // namespace
 
+static int read_input_file(const char* path, mcpm_sim_config* cfg);
+
 extern "C" int mcpm_read_input_file(const char* path, mcpm_sim_config* cfg) {
-    if (!path || !cfg) return MCPM_ERR_ARG;
+    if (!path || !cfg) { mcpm::set_last_error("null argument"); return MCPM_ERR_ARG; }
+    try {
+        return read_input_file(path, cfg);
+    } catch (const std::exception& e) {     // std::stod / stoi on a malformed or missing value: never across the C boundary
+        mcpm::set_last_error((std::string("input file ") + path + ": malformed value (" + e.what() + ")").c_str());
+        return MCPM_ERR_ARG;
+    } catch (...) {
+        mcpm::set_last_error("input file: unknown error");
+        return MCPM_ERR_ARG;
+    }
+}
+
+static int read_input_file(const char* path, mcpm_sim_config* cfg) {
     std::ifstream in(path);
-    if (!in.is_open()) return MCPM_ERR_IO;   // the reference prints "Error opening file" and exits, src/read.cpp:46-49
+    if (!in.is_open()) { mcpm::set_last_error((std::string("cannot open ") + path).c_str()); return MCPM_ERR_IO; }   // the reference prints "Error opening file" and exits, src/read.cpp:46-49
     memset(cfg, 0, sizeof(*cfg));
     cfg->pressure = -1.;
     cfg->replicas = 1;
@@ -275,7 +289,13 @@ void print_stats(const mcpm_sim_config& c, const mcpm_system_desc& d, size_t set
     os << std::endl;   // like the reference, the stream stays fixed/7 for everything printed afterwards
 }
 
-int host_fail(int code, const std::string& msg) { g_host_err = msg; std::cerr << "mcpm_simulate: " << msg << std::endl; return code; }
+int host_fail(int code, const std::string& msg) { mcpm::set_last_error(msg.c_str()); std::cerr << "mcpm_simulate: " << msg << std::endl; return code; }
+
+// Contexts of a run: destroyed on every way out of mcpm_simulate.
+struct ContextSet {
+    std::vector<mcpm_ctx*> ctx;
+    ~ContextSet() { for (auto* c : ctx) if (c) mcpm_destroy(c); }
+};
 
 // One device's share of the chains: the set loop of src/main.cpp:63-84 for chains [lo, hi).
 struct Shard {
@@ -287,7 +307,21 @@ struct Shard {
 
 }  // namespace
 
+static int simulate(const char* input_path, const char* out_dir, int flags);
+
 extern "C" int mcpm_simulate(const char* input_path, const char* out_dir, int flags) {
+    try {
+        return simulate(input_path, out_dir, flags);
+    } catch (const std::filesystem::filesystem_error& e) {   // unwritable output directory
+        return host_fail(MCPM_ERR_IO, e.what());
+    } catch (const std::exception& e) {                      // nothing may cross the C boundary
+        return host_fail(MCPM_ERR_ARG, e.what());
+    } catch (...) {
+        return host_fail(MCPM_ERR_ARG, "unknown error");
+    }
+}
+
+static int simulate(const char* input_path, const char* out_dir, int flags) {
     using clock = std::chrono::system_clock;
     const bool q5 = flags & 1, quiet = flags & 2;
     std::ostream& os = std::cout;
@@ -300,8 +334,10 @@ extern "C" int mcpm_simulate(const char* input_path, const char* out_dir, int fl
     mcpm_sim_config cfg;
     int rc = mcpm_read_input_file(input_path, &cfg);
     if (rc == MCPM_ERR_IO) { std::cout << "Error opening file: " << (input_path ? input_path : "") << std::endl; return rc; }
-    if (rc) return host_fail(rc, "could not parse the input file");
+    if (rc) return host_fail(rc, std::string("could not parse the input file: ") + mcpm_last_error());
     if (cfg.n_boxes != 1 || cfg.n_species != 1) return host_fail(MCPM_ERR_UNSUPPORTED, "exactly one box and one species are supported");
+    if (cfg.continue_after_crash)   // the reference restarts from ReadTrajectory/ReadLogFile (src/read.cpp:173-281): out of scope, say so
+        return host_fail(MCPM_ERR_UNSUPPORTED, "ContinueAfterCrash (restart from trajectory/log files) is not supported");
     mcpm_system_desc& sys = cfg.system;
     if (sys.geometry != MCPM_GEOM_SLIT && sys.geometry != MCPM_GEOM_BULK) return host_fail(MCPM_ERR_UNSUPPORTED, "only slit and bulk geometries are supported");
     if (sys.n_vol != 0) return host_fail(MCPM_ERR_UNSUPPORTED, "volume moves are out of scope");
@@ -309,6 +345,7 @@ extern "C" int mcpm_simulate(const char* input_path, const char* out_dir, int fl
     if (sys.geometry == MCPM_GEOM_BULK && sys.width[2] < 2 * sys.rcut) {   // src/print.cpp:96-103
         std::cout << "Error: Box size must be larger than twice the cut-off radius." << std::endl;
         std::cout << "Box: " << cfg.box << std::endl << std::endl;
+        mcpm::set_last_error("box size must be larger than twice the cut-off radius");
         return MCPM_ERR_ARG;
     }
     const int n_sets = (int)cfg.n_sets, n_equil = (int)cfg.n_equil_sets, print_every = std::max(1, (int)cfg.print_every);
@@ -338,7 +375,9 @@ extern "C" int mcpm_simulate(const char* input_path, const char* out_dir, int fl
     const int G = std::min({std::max(1, cfg.devices), ndev, n_chains});
     std::vector<std::vector<int>> owned(G);
     for (int c = 0; c < n_chains; c++) owned[c % G].push_back(c);
-    std::vector<mcpm_ctx*> ctx(G, nullptr);
+    ContextSet guard;
+    guard.ctx.assign(G, nullptr);
+    std::vector<mcpm_ctx*>& ctx = guard.ctx;
     for (int g = 0; g < G; g++) {
         rc = mcpm_create(g, (int)owned[g].size(), capacity, &ctx[g]);
         if (rc) return host_fail(rc, mcpm_last_error());
@@ -346,6 +385,11 @@ extern "C" int mcpm_simulate(const char* input_path, const char* out_dir, int fl
             rc = mcpm_set_system(ctx[g], (int)k, &desc[owned[g][k]]);
             if (rc) return host_fail(rc, mcpm_last_error());
         }
+        // the Philox stream of a chain is keyed by its GLOBAL id: no two chains of the job share uniforms, and the
+        // results do not depend on how many devices the chains are sharded over
+        std::vector<unsigned int> ids(owned[g].begin(), owned[g].end());
+        rc = mcpm_set_stream_ids(ctx[g], ids.data());
+        if (rc) return host_fail(rc, mcpm_last_error());
     }
 
     // MC::InitialConfig, src/moves.cpp:56-67: three draws per particle from the reference's Random()
@@ -383,40 +427,53 @@ extern "C" int mcpm_simulate(const char* input_path, const char* out_dir, int fl
         for (int g = 0; g < G; g++) if (rcs[g]) return host_fail(rcs[g], errs[g]);
         return MCPM_OK;
     };
+    // global chain 0 lives on device 0, local index 0 (c mod G, c div G)
+    auto stats_of = [&](int c) -> const mcpm_chain_stats& { return stats[c % G][c / G]; };
 
     // MC::MinimizeEnergy, src/energy.cpp:13-34: BoxEnergy; 200*N MoveParticle calls at temperature T; BoxEnergy
     log << "Starting minimization..." << std::endl;
     auto t0 = clock::now();
     if (cfg.n_particles > 0) {
-        std::vector<mcpm_box_energy_t> be(n_chains);
-        for (int g = 0; g < G; g++) { rc = mcpm_box_energy_all(ctx[g], be.data()); if (rc) return host_fail(rc, mcpm_last_error()); }
+        std::vector<mcpm_box_energy_t> be0(owned[0].size());
+        for (int g = 0; g < G; g++) {
+            std::vector<mcpm_box_energy_t> be(owned[g].size());
+            rc = mcpm_box_energy_all(ctx[g], be.data());
+            if (rc) return host_fail(rc, mcpm_last_error());
+            if (g == 0) be0 = be;
+        }
         log << "Minimizing initial configuration of box \"" << cfg.box << "\"..." << std::endl;
-        log << "\tEnergy/part. of box \"" << cfg.box << "\" before minimization: " << be[0].energy / cfg.n_particles << " K" << std::endl;
+        log << "\tEnergy/part. of box \"" << cfg.box << "\" before minimization: " << be0[0].energy / cfg.n_particles << " K" << std::endl;
         for (int g = 0; g < G; g++)
             for (size_t k = 0; k < owned[g].size(); k++) {
                 mcpm_system_desc m = desc[owned[g][k]];
                 m.n_swap = 0; m.n_disp = 1; m.n_equil_sets = 0;       // translations only, no dr adaptation (AdjustMCMoves is commented out there)
-                mcpm_set_system(ctx[g], (int)k, &m);
-                mcpm_set_positions(ctx[g], (int)k, cfg.n_particles, X[owned[g][k]].data(), Y[owned[g][k]].data(), Z[owned[g][k]].data());
+                rc = mcpm_set_system(ctx[g], (int)k, &m);
+                if (rc) return host_fail(rc, mcpm_last_error());
             }
         mcpm_run_params mp;
         memset(&mp, 0, sizeof(mp));
         mp.first_set = 1; mp.n_sets = 1; mp.steps_per_set = 200LL * cfg.n_particles; mp.rng_mode = MCPM_RNG_PHILOX;
         mp.seed = seed ^ 0x6d696e696d697a65ull; mp.check_energy = 1;
+        mp.no_sampling = 1;                                           // MinimizeEnergy calls MoveParticle only: no ComputeWidom after the moves
         rc = run_all(mp);
         if (rc) return rc;
         log << "\tEnergy/part. of box \"" << cfg.box << "\" after minimization (" << cfg.n_particles * 200 << " moves): ";
-        log << stats[0][0].energy_check / std::max(1, stats[0][0].n) << " K" << std::endl;
+        log << stats_of(0).energy_check / std::max(1, stats_of(0).n) << " K" << std::endl;
         for (int g = 0; g < G; g++) {
             for (size_t k = 0; k < owned[g].size(); k++) {
                 const int c = owned[g][k];
-                int n = 0;
-                mcpm_get_positions(ctx[g], (int)k, &n, X[c].data(), Y[c].data(), Z[c].data());
-                mcpm_set_system(ctx[g], (int)k, &desc[c]);            // restore the real move weights (dr back to 0.1*H)
-                mcpm_set_positions(ctx[g], (int)k, n, X[c].data(), Y[c].data(), Z[c].data());
-                mcpm_set_step_counter(ctx[g], (int)k, 0);
+                rc = mcpm_set_system(ctx[g], (int)k, &desc[c]);       // the real move weights; same energetics, so positions and energies stay
+                if (!rc) rc = mcpm_set_dr(ctx[g], (int)k, sys.dr);    // (the minimisation never adapts dr)
+                if (!rc) rc = mcpm_set_step_counter(ctx[g], (int)k, 0);
+                if (rc) return host_fail(rc, mcpm_last_error());
             }
-            mcpm_reset_accumulators(ctx[g]);
+            rc = mcpm_reset_accumulators(ctx[g]);
+            if (rc) return host_fail(rc, mcpm_last_error());
+        }
+        for (int c = 0; c < n_chains; c++) {
+            int n = 0;
+            rc = mcpm_get_positions(ctx[c % G], c / G, &n, X[c].data(), Y[c].data(), Z[c].data());
+            if (rc) return host_fail(rc, mcpm_last_error());
         }
     }
     auto t1 = clock::now();
@@ -440,18 +497,21 @@ extern "C" int mcpm_simulate(const char* input_path, const char* out_dir, int fl
         rc = run_all(rp);
         if (rc) return rc;
         if (last % print_every == 0) {
-            for (int g = 0; g < G; g++)
-                for (size_t k = 0; k < owned[g].size(); k++) {
-                    const int c = owned[g][k];
-                    int n = 0;
-                    mcpm_get_positions(ctx[g], (int)k, &n, X[c].data(), Y[c].data(), Z[c].data());
-                    if (c == 0) print_stats(cfg, desc[c], (size_t)last, &stats[g][k], log);
-                    print_trajectory(outs[c], cfg, desc[c], (size_t)last, stats[g][k].dr, n, X[c].data(), Y[c].data(), Z[c].data());
-                    double mu_ex = 0., mu = 0.;
-                    const bool have_mu = desc[c].n_swap == 0 && last > n_equil;   // Widom sampling ran (src/moves.cpp:415, src/main.cpp:72)
-                    if (have_mu) mcpm_chemical_potential(ctx[g], (int)k, &mu_ex, &mu);
-                    print_log(outs[c], cfg, desc[c], (size_t)last, &stats[g][k], q5, have_mu, mu_ex, mu);
-                }
+            for (int c = 0; c < n_chains; c++) {
+                const int g = c % G, k = c / G;
+                int n = 0;
+                rc = mcpm_get_positions(ctx[g], k, &n, X[c].data(), Y[c].data(), Z[c].data());
+                if (rc) return host_fail(rc, mcpm_last_error());
+                // the reference prints BEFORE AdjustMCMoves (src/main.cpp:77-83): report the amplitude the set ran with
+                mcpm_chain_stats shown = stats[g][k];
+                shown.dr = shown.dr_used;
+                if (c == 0) print_stats(cfg, desc[c], (size_t)last, &shown, log);
+                print_trajectory(outs[c], cfg, desc[c], (size_t)last, shown.dr, n, X[c].data(), Y[c].data(), Z[c].data());
+                double mu_ex = 0., mu = 0.;
+                const bool have_mu = desc[c].n_swap == 0 && last > n_equil;   // Widom sampling ran (src/moves.cpp:415, src/main.cpp:72)
+                if (have_mu) { rc = mcpm_chemical_potential(ctx[g], k, &mu_ex, &mu); if (rc) return host_fail(rc, mcpm_last_error()); }
+                print_log(outs[c], cfg, desc[c], (size_t)last, &stats[g][k], q5, have_mu, mu_ex, mu);
+            }
         }
         set = last + 1;
     }
@@ -460,25 +520,25 @@ extern "C" int mcpm_simulate(const char* input_path, const char* out_dir, int fl
     // MC::PrintRDF, src/print.cpp:127-162 (normalisation reproduced literally, including its use of ALL sets)
     if (cfg.sample_rdf) {
         const double NB = 100.;
-        for (int g = 0; g < G; g++)
-            for (size_t k = 0; k < owned[g].size(); k++) {
-                const int c = owned[g][k];
-                std::vector<double> hist(101, 0.0);
-                mcpm_get_rdf(ctx[g], (int)k, hist.data());
-                const double deltaR = desc[c].rcut / NB;
-                const int nParts = stats[g][k].n;
-                const double rho = nParts / box_volume(desc[c]);
-                const double constant = (4 * M_PI * rho / 3);
-                std::ofstream f(outs[c].box_dir + "/rdf_" + cfg.fluid + "-" + cfg.fluid + ".dat");
-                f << "nBins: " << 100 << std::endl;
-                f << "r(AA)\tg(r)" << std::endl;
-                for (int bin = 1; bin <= 100; bin++) {
-                    double gofr = hist[bin] / (1. * nParts * cfg.steps_per_set * cfg.n_sets);
-                    const double lowR = bin * deltaR, highR = lowR + deltaR;
-                    gofr /= constant * (ipow(highR, 3) - ipow(lowR, 3));
-                    f << (bin + 0.5) * deltaR << "\t" << gofr << std::endl;
-                }
+        for (int c = 0; c < n_chains; c++) {
+            const int g = c % G, k = c / G;
+            std::vector<double> hist(101, 0.0);
+            rc = mcpm_get_rdf(ctx[g], k, hist.data());
+            if (rc) return host_fail(rc, mcpm_last_error());
+            const double deltaR = desc[c].rcut / NB;
+            const int nParts = stats[g][k].n;
+            const double rho = nParts / box_volume(desc[c]);
+            const double constant = (4 * M_PI * rho / 3);
+            std::ofstream f(outs[c].box_dir + "/rdf_" + cfg.fluid + "-" + cfg.fluid + ".dat");
+            f << "nBins: " << 100 << std::endl;
+            f << "r(AA)\tg(r)" << std::endl;
+            for (int bin = 1; bin <= 100; bin++) {
+                double gofr = hist[bin] / (1. * nParts * cfg.steps_per_set * cfg.n_sets);
+                const double lowR = bin * deltaR, highR = lowR + deltaR;
+                gofr /= constant * (ipow(highR, 3) - ipow(lowR, 3));
+                f << (bin + 0.5) * deltaR << "\t" << gofr << std::endl;
             }
+        }
     }
     // final gather: per-state-point averages over replicas and production steps (the reference computes none)
     if (n_chains > 1) {
@@ -487,15 +547,13 @@ extern "C" int mcpm_simulate(const char* input_path, const char* out_dir, int fl
         for (int p = 0; p < points; p++) {
             double sn = 0, sn2 = 0, se = 0; long long ns = 0;
             for (int r = 0; r < replicas; r++) {
-                const int c = p * replicas + r, g = c % G, k = c / G;
-                const mcpm_chain_stats& st = stats[g][k];
+                const mcpm_chain_stats& st = stats_of(p * replicas + r);
                 sn += st.sum_n; sn2 += st.sum_n2; se += st.sum_e; ns += st.samples;
             }
             const double mean = ns ? sn / ns : 0, var = ns ? std::max(0.0, sn2 / ns - mean * mean) : 0;
             iso << desc[p * replicas].mu << "\t" << mean << "\t" << std::sqrt(var) << "\t" << (ns ? se / ns : 0) << "\t" << replicas << "\t" << ns << "\n";
         }
     }
-    for (int g = 0; g < G; g++) mcpm_destroy(ctx[g]);
     std::time_t endTime = clock::to_time_t(te);
     log << std::endl << "Simulation finished" << std::endl;
     log << "Elapsed time of simulation: " << std::chrono::duration<double>(te - ts).count() << " s" << std::endl;

@@ -13,10 +13,16 @@
 
 #include "mcpm_kernels.h"
 #include "mcpm_types.h"
+#ifdef MCPM_EXPERIMENTS
+#include "experiments/mcpm_experiments.h"
+#endif
 
 using namespace mcpm;
 
 static thread_local std::string g_err;
+
+// The host driver (host/mcpm_host.cpp) reports its failures through the same per-thread message mcpm_last_error() returns.
+namespace mcpm { void set_last_error(const char* msg) { g_err = msg ? msg : ""; } }
 
 static int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -193,6 +199,7 @@ int mcpm_create(int device, int n_chains, int capacity, mcpm_ctx** out) {
     memset(&zero, 0, sizeof(zero));
     zero.fast_image = 1;
     c->h_state.assign(n_chains, zero);
+    for (int k = 0; k < n_chains; k++) c->h_state[k].stream_id = (unsigned int)k;
     c->h_desc.assign(n_chains, mcpm_system_desc());
     c->has_system.assign(n_chains, 0);
     CU(cudaMemcpyAsync(c->d_state, c->h_state.data(), sizeof(ChainState) * n_chains, cudaMemcpyHostToDevice, c->stream));
@@ -228,6 +235,26 @@ int mcpm_n_chains(const mcpm_ctx* c, int* n_chains, int* capacity) {
     return MCPM_OK;
 }
 
+// Do two digested systems give the same energies for the same configuration?  (mu, T, move weights and n_equil do not enter.)
+static bool same_energetics(const ChainParams& a, const ChainParams& b) {
+    for (int k = 0; k < 3; k++) if (a.L[k] != b.L[k] || a.pbc[k] != b.pbc[k]) return false;
+    return a.sig2 == b.sig2 && a.eps4 == b.eps4 && a.rc2 == b.rc2 && a.wall_pref == b.wall_pref && a.sig_sf == b.sig_sf && a.delta == b.delta &&
+           a.geometry == b.geometry && a.wall_kind == b.wall_kind && a.n_layers == b.n_layers;
+}
+
+// fast_image of every chain from the positions on the device (all coordinates on periodic axes inside [0, L]).
+static int refresh_fast_image(mcpm_ctx* c) {
+    if (!c->d_flags) { CU(cudaMalloc(&c->d_flags, sizeof(int) * 2 * c->n_chains)); CU(cudaMallocHost(&c->h_flags, sizeof(int) * 2 * c->n_chains)); }
+    for (int k = 0; k < c->n_chains; k++) c->h_flags[k] = c->h_state[k].st.n;
+    CU(cudaMemcpyAsync(c->d_flags, c->h_flags, sizeof(int) * c->n_chains, cudaMemcpyHostToDevice, c->stream));
+    CU(launch_in_box(c->n_chains, c->d_params, c->d_flags, c->d_x, c->d_y, c->d_z, c->cap, c->d_flags + c->n_chains, c->stream));
+    c->launches++;
+    CU(cudaMemcpyAsync(c->h_flags + c->n_chains, c->d_flags + c->n_chains, sizeof(int) * c->n_chains, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < c->n_chains; k++) c->h_state[k].fast_image = c->h_flags[c->n_chains + k];
+    return MCPM_OK;
+}
+
 int mcpm_set_system(mcpm_ctx* c, int chain, const mcpm_system_desc* desc) {
     if (!c || !desc) return fail(MCPM_ERR_ARG, "null argument");
     if (chain != -1) { int rc = check_chain(c, chain); if (rc) return rc; }
@@ -237,11 +264,23 @@ int mcpm_set_system(mcpm_ctx* c, int chain, const mcpm_system_desc* desc) {
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
     const int lo = chain == -1 ? 0 : chain, hi = chain == -1 ? c->n_chains : chain + 1;
+    bool recheck = false;
     for (int k = lo; k < hi; k++) {
+        ChainState& S = c->h_state[k];
+        // A chain that already holds a configuration keeps its running energies and energy cache only if the new system
+        // gives the same energies (e.g. a mu- or T-only update in a sweep); otherwise both are stale, and a smaller box may
+        // have left coordinates outside [0, L], which the fast minimum image must not see.
+        if (c->has_system[k] && !same_energetics(c->h_params[k], P)) {
+            S.energy_valid = 0; S.cache_valid = 0; S.cache_sum = 0ull;
+            if (S.st.n > 0) recheck = true;
+        }
+        // dr: taken from the description the first time and whenever the description's own dr changes; an unchanged
+        // desc->dr keeps the amplitude the chain has adapted to (AdjustMCMoves), e.g. across mu updates of a sweep.
+        if (!c->has_system[k] || c->h_desc[k].dr != desc->dr) S.st.dr = desc->dr;
         c->h_params[k] = P; c->h_desc[k] = *desc; c->has_system[k] = 1;
-        c->h_state[k].st.dr = desc->dr;
     }
     CU(cudaMemcpyAsync(c->d_params + lo, c->h_params.data() + lo, sizeof(ChainParams) * (hi - lo), cudaMemcpyHostToDevice, c->stream));
+    if (recheck) { rc = refresh_fast_image(c); if (rc) return rc; }
     CU(cudaMemcpyAsync(c->d_state + lo, c->h_state.data() + lo, sizeof(ChainState) * (hi - lo), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return MCPM_OK;
@@ -530,6 +569,7 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     for (int k = 0; k < c->n_chains; k++) all_fast = all_fast && c->h_state[k].fast_image;
     bool sample = p->sample_rdf != 0;                       // in-kernel sampling: RDF on request, Widom whenever n_swap == 0
     for (int k = 0; k < c->n_chains; k++) sample = sample || c->h_params[k].n_swap == 0;
+    if (p->no_sampling) sample = false;                     // moves only (MC::MinimizeEnergy): the hot kernels apply
     threads = k2_threads_supported(threads, global_path, all_fast, sample);
     bool need_init = false;
     for (int k = 0; k < c->n_chains; k++) need_init |= !c->h_state[k].energy_valid;
@@ -547,7 +587,7 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     memset(&a, 0, sizeof(a));
     a.first_set = p->first_set; a.n_sets = p->n_sets; a.steps_per_set = p->steps_per_set; a.seed = p->seed;
     a.check_energy = p->check_energy; a.cap = c->cap;
-    a.sample_rdf = p->sample_rdf; a.rdf = c->d_rdf;
+    a.sample_rdf = p->no_sampling ? 0 : p->sample_rdf; a.rdf = c->d_rdf; a.no_sampling = p->no_sampling ? 1 : 0;
     // The energy cache pays while accepted translations (each costs a second pass over the partners) are the minority:
     // N + 2pN < 2N for p < 0.5.  Decide from the acceptance of the last set; the reference's dr adaptation aims at 0.2.
     bool cache_now = c->use_cache != 0;
@@ -558,7 +598,7 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     }
     // K2 through a cell list (mcpm_cells.cu): large chains whose box holds >= 3 cut-off lengths per periodic axis (config C4).
     // ~27 cells x occupancy candidate partners per energy evaluation instead of N; measured break-even is a few thousand particles.
-    bool use_k2c = c->use_cells && all_fast && !p->sample_rdf && p->threads_per_chain == 0 && maxn >= 4096;
+    bool use_k2c = c->use_cells && all_fast && !a.sample_rdf && p->threads_per_chain == 0 && maxn >= 4096;
     int kc_stride = 1, kc_ccap = 64;
     size_t kc_smem = 0;
     if (use_k2c) {
@@ -637,25 +677,36 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     }
     // The sub-warp kernel (mcpm_subwarp.cu) takes over whenever one warp per chain was chosen: it needs the energy cache,
     // coordinates inside the box, shared-memory positions, no in-kernel sampling and one geometry for the whole launch.
+#ifdef MCPM_EXPERIMENTS
     const bool use_sub = c->use_subwarp && threads == 32 && cache_now && all_fast && !sample && !global_path && same_pbz;
+#else
+    const bool use_sub = false;
+#endif
     CU(cudaEventRecord(c->ev0, c->stream));
+#ifdef MCPM_EXPERIMENTS
     const bool use_dual = c->use_dual && !use_k2c && !use_spec && !use_sub && threads == 32 && cache_now && all_fast && !sample && !global_path && same_pbz;
+#else
+    const bool use_dual = false;
+#endif
     c->last_kernel = use_k2c ? "k2_cells" : use_pair ? (lean_width == 4 ? "k2_quad" : "k2_pair") : use_spec ? "k2_spec" : (use_sub ? "k2_sub" : (use_dual ? "k2_dual" : "k2_chains"));
     if (use_k2c) {
         bool widom = false;
-        for (int k = 0; k < c->n_chains; k++) widom = widom || c->h_params[k].n_swap == 0;
+        for (int k = 0; k < c->n_chains; k++) widom = widom || (c->h_params[k].n_swap == 0 && !p->no_sampling);
         CU(launch_k2_cells(p->rng_mode, widom, c->n_chains, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->d_kc_items,
                            c->d_kc_cell_of, c->d_kc_slot_of, kc_stride, kc_ccap, kc_smem, c->stream));
         c->launches++;
+#ifdef MCPM_EXPERIMENTS
     } else if (use_dual) {
         CU(launch_k2_dual(p->rng_mode, c->h_params[0].pbc[2] != 0, c->n_chains, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->stream));
         c->launches++;
+#endif
     } else if (use_pair) {
         CU(launch_k2_spec(p->rng_mode, c->h_params[0].pbc[2] != 0, lean_width, c->n_chains, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->stream));
         c->launches++;
     } else if (use_spec) {
         CU(launch_k2_spec(p->rng_mode, c->h_params[0].pbc[2] != 0, 0, c->n_chains, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->stream));
         c->launches++;
+#ifdef MCPM_EXPERIMENTS
     } else if (use_sub) {
         const int cap_cta = ((c->cap + 127) / 128) * 128;
         if (!c->d_ctas) CU(cudaMalloc(&c->d_ctas, sizeof(int2) * c->n_chains));
@@ -690,6 +741,7 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
                              c->d_y, c->d_z, a, cap_cta, c->stream));
             c->launches++;
         }
+#endif
     } else {
         CU(launch_k2(p->rng_mode, c->n_chains, threads, all_fast, sample, cache_now, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->max_smem, c->stream));
         c->launches++;
@@ -785,11 +837,13 @@ int mcpm_set_running_energy(mcpm_ctx* c, const double* pair, const double* wall)
     return MCPM_OK;
 }
 
+#ifdef MCPM_EXPERIMENTS
 int mcpm_use_dual_candidates(mcpm_ctx* c, int enable) {
     if (!c) return fail(MCPM_ERR_ARG, "null context");
     c->use_dual = enable ? 1 : 0;
     return MCPM_OK;
 }
+#endif
 
 int mcpm_use_speculation(mcpm_ctx* c, int mode) {
     if (!c) return fail(MCPM_ERR_ARG, "null context");
@@ -798,11 +852,13 @@ int mcpm_use_speculation(mcpm_ctx* c, int mode) {
     return MCPM_OK;
 }
 
+#ifdef MCPM_EXPERIMENTS
 int mcpm_use_subwarp(mcpm_ctx* c, int enable) {
     if (!c) return fail(MCPM_ERR_ARG, "null context");
     c->use_subwarp = enable ? 1 : 0;
     return MCPM_OK;
 }
+#endif
 
 int mcpm_use_energy_cache(mcpm_ctx* c, int enable) {
     if (!c) return fail(MCPM_ERR_ARG, "null context");
@@ -813,6 +869,15 @@ int mcpm_use_energy_cache(mcpm_ctx* c, int enable) {
 int mcpm_use_cell_list(mcpm_ctx* c, int enable) {
     if (!c) return fail(MCPM_ERR_ARG, "null context");
     c->use_cells = enable ? 1 : 0;
+    return MCPM_OK;
+}
+
+int mcpm_set_stream_ids(mcpm_ctx* c, const unsigned int* ids) {
+    if (!c || !ids) return fail(MCPM_ERR_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    for (int k = 0; k < c->n_chains; k++) c->h_state[k].stream_id = ids[k];
+    CU(cudaMemcpyAsync(c->d_state, c->h_state.data(), sizeof(ChainState) * c->n_chains, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return MCPM_OK;
 }
 

@@ -171,7 +171,7 @@ __device__ void chain_loop_cells(const ChainParams& P, ChainState& S, Source& rn
     const bool lead = (tid == 0);
     const PairGeom g = make_geom<true>(P);
     mcpm_chain_stats& st = S.st;   // shared memory; written by thread 0 only
-    const bool widom_on = SAMPLE && (P.n_swap == 0);   // ComputeWidom acts only without swap moves, src/moves.cpp:415
+    const bool widom_on = SAMPLE && (P.n_swap == 0) && !a.no_sampling;   // ComputeWidom acts only without swap moves, src/moves.cpp:415
 
     int n = st.n;
     double dr = st.dr, e_pair = st.pair, e_wall = st.wall;
@@ -189,7 +189,7 @@ __device__ void chain_loop_cells(const ChainParams& P, ChainState& S, Source& rn
         if (lead) { st.widom_insert = st.widom_delete = 0.0; st.widom_insertions = st.widom_deletions = 1; }
         const bool production = set > P.n_equil;
         for (int s = 0; s < steps_per_set; s++) {
-            rng.begin_step(a.seed, chain, step, lane);
+            rng.begin_step(a.seed, S.stream_id, step, lane);
             step++;
             int code;
             double sx = 0., sy = 0., sz = 0., s_po = 0., s_wo = 0., mx = 0., my = 0., mz = 0.;   // this step's MoveParticle, for Widom's slot 0
@@ -298,7 +298,7 @@ __device__ void chain_loop_cells(const ChainParams& P, ChainState& S, Source& rn
             }
             if (SAMPLE && production && widom_on) {
                 // ---------------- ComputeWidom, src/moves.cpp:410-449 (NVT branch) ----------------
-                rng.load_extra(a.seed, chain, step - 1, lane);
+                rng.load_extra(a.seed, S.stream_id, step - 1, lane);
                 double energy;                                                   // draw 0 (species) is consumed but unused
                 if (rng.template extra<1>() < 0.5) {                             // ghost insertion
                     const double gx = rng.template extra<2>() * Lx, gy = rng.template extra<3>() * Ly, gz = rng.template extra<4>() * Lz;
@@ -350,6 +350,7 @@ __device__ void chain_loop_cells(const ChainParams& P, ChainState& S, Source& rn
             }
         }
         if (SAMPLE && warp == 0) { __syncwarp(); if (wq.count > 0) widom_flush(wq, st, beta, lane); }   // the sums are per set (ResetStats)
+        if (lead) st.dr_used = dr;          // the amplitude this set ran with (statistics are printed before the adjustment, src/main.cpp:77-83)
         // MC::AdjustMCMoves displacement part, src/moves.cpp:68-78 (ResetStats starts nDisplacements at ONE)
         if (!overflow && n > 0 && set <= P.n_equil) {
             const double ratio = (double)sc.acc_disp * 1. / (1. * (double)(sc.n_disp + 1));
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) k2_cells(const ChainParams* __r
     unsigned char* trace = a.trace ? a.trace + (unsigned long long)chain * a.trace_stride : nullptr;
     const bool pbz = P.pbc[2] != 0;
     if (RNG_MODE == MCPM_RNG_PHILOX) {
-        PhiloxSource rng; rng.init(a.seed, (uint32_t)chain, S.st.steps_done, tid & 31);
+        PhiloxSource rng; rng.init(a.seed, S.stream_id, S.st.steps_done, tid & 31);
         if (pbz) chain_loop_cells<PhiloxSource, true, SAMPLE>(P, S, rng, xs, ys, zs, partials, wq, cl, a, trace, cap, (uint32_t)chain);
         else chain_loop_cells<PhiloxSource, false, SAMPLE>(P, S, rng, xs, ys, zs, partials, wq, cl, a, trace, cap, (uint32_t)chain);
     } else {

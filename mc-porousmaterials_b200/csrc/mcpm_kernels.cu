@@ -52,12 +52,13 @@ __device__ __forceinline__ long long k2_probe(double x) {   // clock read that c
 template <class Source, bool FAST, bool MULTI, bool PBZ, bool SAMPLE, bool CACHE>
 __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, double* xs, double* ys, double* zs, double* partials,
                            const RunArgs& a, unsigned char* trace, int cap, uint32_t chain, double* hist) {
+    const uint32_t sid = S.stream_id;   // Philox streams are keyed by the chain's global id, not its index inside this context
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
     const int tmask = T - 1;  // T is a power of two
     const bool lead = (tid == 0);
     const PairGeom g = make_geom<FAST>(P);
     mcpm_chain_stats& st = S.st;   // shared memory; written by thread 0 only
-    const bool widom_on = SAMPLE && (P.n_swap == 0);   // ComputeWidom acts only without swap moves, src/moves.cpp:415
+    const bool widom_on = SAMPLE && (P.n_swap == 0) && !a.no_sampling;   // ComputeWidom acts only without swap moves, src/moves.cpp:415
 
     int n = st.n;
     double nd = (double)n;            // n as a double, kept in step (the conversion would sit on every step's critical path)
@@ -104,7 +105,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
             long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             K2_PROBE(0, e_pair);
 #endif
-            rng.begin_step(a.seed, chain, step, lane);
+            rng.begin_step(a.seed, sid, step, lane);
             step++;
             int code;
             double sx = 0., sy = 0., sz = 0., s_po = 0., s_wo = 0., mx = 0., my = 0., mz = 0.;   // this step's MoveParticle, for Widom's slot 0
@@ -278,7 +279,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
             }
             if (SAMPLE && production && widom_on) {
                 // ---------------- ComputeWidom, src/moves.cpp:410-449 (NVT branch) ----------------
-                rng.load_extra(a.seed, chain, step - 1, lane);
+                rng.load_extra(a.seed, sid, step - 1, lane);
                 double energy;                                                   // draw 0 (species) is consumed but unused
                 if (rng.template extra<1>() < 0.5) {                             // ghost insertion
                     const double gx = rng.template extra<2>() * Lx, gy = rng.template extra<3>() * Ly, gz = rng.template extra<4>() * Lz;
@@ -354,6 +355,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                 }
             }
         }
+        if (lead) st.dr_used = dr;          // the amplitude this set ran with (statistics are printed before the adjustment, src/main.cpp:77-83)
         // MC::AdjustMCMoves displacement part, src/moves.cpp:68-78 (ResetStats starts nDisplacements at ONE)
         if (!overflow && n > 0 && set <= P.n_equil) {
             const double ratio = (double)sc.acc_disp * 1. / (1. * (double)(sc.n_disp + 1));
@@ -433,10 +435,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k2_chains(const ChainParams* __res
     } while (0)
     if (RNG_MODE == MCPM_RNG_PHILOX) {
         if (MAXT <= 64 && !GLOBAL && !multi) {   // one warp per chain: uniforms through shared memory (the partials area is free)
-            PhiloxSmemSource rng; rng.init(a.seed, (uint32_t)chain, S.st.steps_done, tid & 31, partials);
+            PhiloxSmemSource rng; rng.init(a.seed, S.stream_id, S.st.steps_done, tid & 31, partials);
             if (pbz) MCPM_GO(PhiloxSmemSource, false, true); else MCPM_GO(PhiloxSmemSource, false, false);
         } else {
-            PhiloxSource rng; rng.init(a.seed, (uint32_t)chain, S.st.steps_done, tid & 31);
+            PhiloxSource rng; rng.init(a.seed, S.stream_id, S.st.steps_done, tid & 31);
             MCPM_DISPATCH(PhiloxSource);
         }
     } else {

@@ -6,6 +6,8 @@
 
 namespace mcpm {
 
+void set_last_error(const char* msg);   // mcpm_api.cu: the per-thread message behind mcpm_last_error()
+
 cudaError_t launch_k2(int rng_mode, int n_chains, int threads, bool fast, bool sample, bool cache, const ChainParams* params, ChainState* states, const int* order,
                       double* X, double* Y, double* Z, const RunArgs& a, int max_smem_optin, cudaStream_t stream);
 size_t k2_smem_limit_cap(int max_smem_optin);

@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(32 * (LEAN ? KW : KW + 2), LEAN ? 16 / KW : 1)
             const unsigned long long stp = filled + (unsigned long long)(lane >> 2);
             if (stp < upto) {
                 double ua, ub;
-                philox_call(a.seed, (uint32_t)chain, 4ull * stp + (unsigned long long)(lane & 3), ua, ub);
+                philox_call(a.seed, S.stream_id, 4ull * stp + (unsigned long long)(lane & 3), ua, ub);
                 double* slot = &ring[(int)(stp & (unsigned long long)(RS - 1))][2 * (lane & 3)];
                 slot[0] = ua; slot[1] = ub;
             }
@@ -380,6 +380,7 @@ __global__ void __launch_bounds__(32 * (LEAN ? KW : KW + 2), LEAN ? 16 / KW : 1)
         }
         // MC::AdjustMCMoves displacement part, src/moves.cpp:68-78 (ResetStats starts nDisplacements at ONE)
         if (book) {
+            st.dr_used = dr;                        // the amplitude this set ran with (src/main.cpp:77-83 prints before adjusting)
             if (!overflow && n > 0 && set <= P.n_equil) {
                 const double ratio = (double)sc.acc_disp * 1. / (1. * (double)(sc.n_disp + 1));
                 if (ratio < 0.2) dr /= 1.1;

@@ -38,7 +38,7 @@ struct ChainState {
     unsigned long long replay_pos;  // cursor into the replay stream (REPLAY mode)
     unsigned long long cache_sum;   // checksum of the configuration the energy cache (RunArgs::ep) belongs to
     int cache_valid;                // the cache was left consistent by the last K2 launch
-    int pad2;
+    unsigned int stream_id;         // Philox stream of this chain: its GLOBAL id (default: index inside the context; mcpm_set_stream_ids)
     ChainResume res;
 };
 
@@ -53,6 +53,7 @@ struct RunArgs {
     int check_energy;
     int cap;
     int sample_rdf;
+    int no_sampling;             // moves only: the sampling kernels skip ComputeWidom / ComputeRDF (mcpm_run_params::no_sampling)
     double* ep;                  // device, [n_chains][cap]: per-particle pair sums (unscaled) of the energy cache, or null
     double* rdf;                 // device, [n_chains][MCPM_RDF_BINS] accumulated histograms
 };

@@ -4,10 +4,10 @@ The product is the CUDA library + C++ host driver under ../csrc; this package on
 tests and bench.py can drive the C ABI (include/mcpm.h) from Python.  It contains no numerics and no
 fallback: if libmcpm.so is missing, or there is no CUDA device, calls raise.
 """
-from .abi import (McpmError, SimConfig, SystemDesc, ChainStats, RunParams, ParticleEnergy, BoxEnergy, lib, lib_path,
+from .abi import (has_experiments, McpmError, SimConfig, SystemDesc, ChainStats, RunParams, ParticleEnergy, BoxEnergy, lib, lib_path,
                   RNG_PHILOX, RNG_REPLAY, GEOM_BULK, GEOM_SLIT, WALL_NONE, WALL_SLIT_LJ)
 from .engine import Engine, fp64_peak_tflops, device_count
 
-__all__ = ["McpmError", "SimConfig", "SystemDesc", "ChainStats", "RunParams", "ParticleEnergy", "BoxEnergy", "lib", "lib_path",
+__all__ = ["has_experiments", "McpmError", "SimConfig", "SystemDesc", "ChainStats", "RunParams", "ParticleEnergy", "BoxEnergy", "lib", "lib_path",
            "Engine", "fp64_peak_tflops", "device_count", "RNG_PHILOX", "RNG_REPLAY", "GEOM_BULK", "GEOM_SLIT",
            "WALL_NONE", "WALL_SLIT_LJ"]

@@ -55,7 +55,7 @@ class RunParams(C.Structure):
         ("rng_mode", C.c_int), ("seed", C.c_ulonglong),
         ("replay_u", _dp), ("replay_stride", C.c_size_t),
         ("trace", C.POINTER(C.c_ubyte)),
-        ("threads_per_chain", C.c_int), ("sample_rdf", C.c_int), ("check_energy", C.c_int),
+        ("threads_per_chain", C.c_int), ("sample_rdf", C.c_int), ("check_energy", C.c_int), ("no_sampling", C.c_int),
     ]
 
 
@@ -74,6 +74,7 @@ class ChainStats(C.Structure):
         ("samples", C.c_longlong), ("replay_consumed", C.c_ulonglong),
         ("widom_insert", C.c_double), ("widom_delete", C.c_double),
         ("widom_insertions", C.c_longlong), ("widom_deletions", C.c_longlong),
+        ("dr_used", C.c_double),
     ]
 
     def as_dict(self):
@@ -95,7 +96,13 @@ class SimConfig(C.Structure):
 
 
 def lib_path() -> str:
-    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "libmcpm.so")
+    """libmcpm.so, or — only when MCPM_EXPERIMENTS=1 is set and it was built (make EXPERIMENTS=1) — libmcpm_exp.so,
+    the same library plus the experimental kernels of csrc/experiments/."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exp = os.path.join(here, "libmcpm_exp.so")
+    if os.environ.get("MCPM_EXPERIMENTS") == "1" and os.path.exists(exp):
+        return exp
+    return os.path.join(here, "libmcpm.so")
 
 
 _LIB = None
@@ -117,9 +124,7 @@ PROTOTYPES = {
     "mcpm_particle_energy": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, C.POINTER(ParticleEnergy), C.POINTER(ParticleEnergy)]),
     "mcpm_box_energy": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(BoxEnergy), _dp, _dp]),
     "mcpm_box_energy_all": (C.c_int, [C.c_void_p, C.POINTER(BoxEnergy)]),
-    "mcpm_use_subwarp": (C.c_int, [C.c_void_p, C.c_int]),
     "mcpm_use_speculation": (C.c_int, [C.c_void_p, C.c_int]),
-    "mcpm_use_dual_candidates": (C.c_int, [C.c_void_p, C.c_int]),
     "mcpm_use_energy_cache": (C.c_int, [C.c_void_p, C.c_int]),
     "mcpm_use_cell_list": (C.c_int, [C.c_void_p, C.c_int]),
     "mcpm_apply_move": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp]),
@@ -131,6 +136,7 @@ PROTOTYPES = {
     "mcpm_get_rdf": (C.c_int, [C.c_void_p, C.c_int, _dp]),
     "mcpm_chemical_potential": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp]),
     "mcpm_set_running_energy": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "mcpm_set_stream_ids": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint)]),
     "mcpm_set_dr": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "mcpm_set_step_counter": (C.c_int, [C.c_void_p, C.c_int, C.c_ulonglong]),
     "mcpm_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
@@ -143,6 +149,12 @@ PROTOTYPES = {
     "mcpm_read_input_file": (C.c_int, [C.c_char_p, C.POINTER(SimConfig)]),
     "mcpm_simulate": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int]),
     "mcpm_philox_uniforms": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_uint, C.c_ulonglong, C.c_int, _dp]),
+}
+
+
+EXPERIMENTAL = {
+    "mcpm_use_subwarp": (C.c_int, [C.c_void_p, C.c_int]),
+    "mcpm_use_dual_candidates": (C.c_int, [C.c_void_p, C.c_int]),
 }
 
 
@@ -159,8 +171,17 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
+        for name, (res, args) in EXPERIMENTAL.items():      # csrc/experiments/mcpm_experiments.h, libmcpm_exp.so only
+            if hasattr(L, name):
+                fn = getattr(L, name)
+                fn.restype = res
+                fn.argtypes = args
         _LIB = L
     return _LIB
+
+
+def has_experiments() -> bool:
+    return all(hasattr(lib(), name) for name in EXPERIMENTAL)
 
 
 def check(rc):

@@ -116,10 +116,19 @@ class Engine:
         check(self.L.mcpm_use_speculation(self.h, int(mode)))
 
     def use_dual_candidates(self, enable=True):
-        check(self.L.mcpm_use_dual_candidates(self.h, 1 if enable else 0))
+        """Experimental kernel (libmcpm_exp.so only); disabling it is a no-op on the product library."""
+        if enable or abi.has_experiments():
+            check(self.L.mcpm_use_dual_candidates(self.h, 1 if enable else 0))
 
     def use_subwarp(self, enable=True):
-        check(self.L.mcpm_use_subwarp(self.h, 1 if enable else 0))
+        """Experimental kernel (libmcpm_exp.so only); disabling it is a no-op on the product library."""
+        if enable or abi.has_experiments():
+            check(self.L.mcpm_use_subwarp(self.h, 1 if enable else 0))
+
+    def set_stream_ids(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        assert len(ids) == self.n_chains
+        check(self.L.mcpm_set_stream_ids(self.h, ids.ctypes.data_as(C.POINTER(C.c_uint))))
 
     def use_energy_cache(self, enable=True):
         check(self.L.mcpm_use_energy_cache(self.h, 1 if enable else 0))
@@ -140,7 +149,7 @@ class Engine:
         check(self.L.mcpm_remove_swap_last(self.h, chain, index))
 
     # ---- K2
-    def run(self, first_set, n_sets, steps_per_set, seed=0, replay=None, trace=False, threads=0, check_energy=0, sample_rdf=0):
+    def run(self, first_set, n_sets, steps_per_set, seed=0, replay=None, trace=False, threads=0, check_energy=0, sample_rdf=0, no_sampling=0):
         """Advance every chain n_sets*steps_per_set trial moves.  replay: float64[n_chains, stride] or None."""
         p = RunParams()
         p.first_set, p.n_sets, p.steps_per_set = first_set, n_sets, steps_per_set
@@ -148,6 +157,7 @@ class Engine:
         p.threads_per_chain = threads
         p.check_energy = check_energy
         p.sample_rdf = sample_rdf
+        p.no_sampling = no_sampling
         keep = []
         if replay is not None:
             r = np.ascontiguousarray(replay, dtype=np.float64)

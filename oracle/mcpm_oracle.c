@@ -481,6 +481,7 @@ void orc_rdf(orc_chain* c, double* hist) {
         }
     if (hist) memcpy(hist, c->rdf, sizeof(double) * ORC_NBINS);
 }
+void orc_set_dr(orc_chain* c, double dr) { c->dr = dr; }
 void orc_rdf_reset(orc_chain* c) { memset(c->rdf, 0, sizeof(c->rdf)); }
 void orc_set_sample_rdf(orc_chain* c, int on) { c->sample_rdf = on; }
 void orc_get_rdf(const orc_chain* c, double* hist100) { memcpy(hist100, c->rdf, sizeof(double) * ORC_NBINS); }

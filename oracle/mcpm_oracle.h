@@ -71,6 +71,7 @@ void orc_initial_config(orc_chain* c, int n);                              /* mo
  * move 0 = translation, 1 = insertion attempt, 2 = deletion attempt, 3 = deletion branch on empty box. */
 int orc_step(orc_chain* c, int correct_energy);
 long long orc_run(orc_chain* c, long long nsteps, int correct_energy, unsigned char* trace);
+void orc_set_dr(orc_chain* c, double dr);                                  /* Simulation::dr, restart / tests */
 void orc_reset_stats(orc_chain* c);                                        /* MC.cpp:81-98 */
 void orc_adjust(orc_chain* c, int set);                                    /* moves.cpp:68-78 */
 /* Sets first_set..first_set+n_sets-1: ResetStats; steps; sampling when set > n_equil_sets; adjust.

@@ -127,6 +127,7 @@ class COracle:
             L.orc_run.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]
             L.orc_run.restype = C.c_longlong
             L.orc_reset_stats.argtypes = [C.c_void_p]
+            L.orc_set_dr.argtypes = [C.c_void_p, C.c_double]
             L.orc_adjust.argtypes = [C.c_void_p, C.c_int]
             L.orc_run_sets.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_void_p]
             L.orc_get_state.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_longlong)]
@@ -224,6 +225,9 @@ class COracle:
 
     def reset_stats(self):
         self.L.orc_reset_stats(self.h)
+
+    def set_dr(self, dr):
+        self.L.orc_set_dr(self.h, dr)
 
     def adjust(self, set_index):
         self.L.orc_adjust(self.h, set_index)

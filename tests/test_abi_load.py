@@ -36,7 +36,7 @@ def test_struct_layouts_match_oracle(mcpm):
 
 def test_version_and_error_paths(mcpm):
     L = mcpm.lib()
-    assert L.mcpm_version() == 100
+    assert L.mcpm_version() == 200
     h = ctypes.c_void_p()
     assert L.mcpm_create(0, 0, 16, ctypes.byref(h)) != 0          # bad argument, no device needed
     assert b"positive" in L.mcpm_last_error()

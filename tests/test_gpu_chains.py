@@ -27,6 +27,8 @@ def first_divergence(a, b):
 @pytest.mark.parametrize("name", ["c1t", "lowt", "bulkt"])
 def test_replay_trace_matches_reference_golden(mcpm, golden, name, threads, cache):
     """'dual' = the opt-in dual-candidate kernel (k2_dual, one warp per chain, two steps per round)."""
+    if cache in ("subwarp", "dual") and not mcpm.has_experiments():
+        pytest.skip("experimental kernels: build with `make EXPERIMENTS=1` and run with MCPM_EXPERIMENTS=1")
     if cache == "subwarp" and threads != 32:
         pytest.skip("the sub-warp kernel runs one warp per chain")
     if cache == "spec" and threads != 32:
@@ -102,6 +104,8 @@ def test_device_philox_stream_is_the_documented_one(mcpm):
 @pytest.mark.parametrize("threads", [32, 128])
 def test_philox_chain_follows_oracle(mcpm, golden, threads, cache):
     """Device Philox + Metropolis on the GPU == the C oracle fed with the same counter-based stream."""
+    if cache == "dual" and not mcpm.has_experiments():
+        pytest.skip("experimental kernel: build with `make EXPERIMENTS=1` and run with MCPM_EXPERIMENTS=1")
     if cache in ("spec", "dual", "pair") and threads != 32:
         pytest.skip("one CTA shape")
     arrays, meta = golden
@@ -455,7 +459,10 @@ def test_speculative_moves_are_the_sequential_chain(mcpm, golden, start):
         x = y = z = np.zeros(0)
     nch, sets, sps = 3, 4, 5003
     out = []
-    for kernel, spec, threads in (("k2_chains", 0, 64), ("k2_spec", 1, 0), ("k2_dual", 0, 32), ("k2_pair", 2, 32), ("k2_quad", 4, 0)):
+    kernels = [("k2_chains", 0, 64), ("k2_spec", 1, 0), ("k2_pair", 2, 32), ("k2_quad", 4, 0)]
+    if mcpm.has_experiments():
+        kernels.append(("k2_dual", 0, 32))
+    for kernel, spec, threads in kernels:
         with mcpm.Engine(nch, 1024) as e:
             e.use_speculation(spec)
             e.use_dual_candidates(kernel == "k2_dual")
@@ -465,7 +472,7 @@ def test_speculative_moves_are_the_sequential_chain(mcpm, golden, start):
             stats, tr = e.run(1, sets, sps, seed=424242, trace=True, threads=threads, check_energy=1)
             assert e.last_kernel_name() == kernel
             out.append((tr.copy(), [e.get_positions(c) for c in range(nch)], stats))
-    for c, other in [(c, other) for c in range(nch) for other in (1, 2, 3, 4)]:
+    for c, other in [(c, other) for c in range(nch) for other in range(1, len(out))]:
         assert first_divergence(out[0][0][c], out[other][0][c]) == -1
         for a, b in zip(out[0][1][c], out[other][1][c]):
             assert np.array_equal(a, b)
@@ -503,6 +510,8 @@ def test_speculation_is_chosen_for_few_chains_only(mcpm, golden):
 
 @pytest.mark.parametrize("packed", [True, False], ids=["subwarp", "onewarp"])
 def test_subwarp_packing_mixed_loadings(mcpm, golden, packed):
+    if packed and not mcpm.has_experiments():
+        pytest.skip("experimental kernel: build with `make EXPERIMENTS=1` and run with MCPM_EXPERIMENTS=1")
     """The throughput kernel packs 4 / 2 / 1 chains per warp by loading.  12 chains of very different size (3 ... 504
     particles, different mu) against the C oracle fed with the same Philox streams: identical traces and configurations."""
     arrays, meta = golden
@@ -544,6 +553,8 @@ def test_subwarp_packing_mixed_loadings(mcpm, golden, packed):
 def test_subwarp_chain_outgrows_its_slot(mcpm, golden):
     """A chain that starts small (packed 4 per warp) and fills up during the launch is paused when its slot is full and
     finishes the call alone in a warp; the result is the chain the oracle produces."""
+    if not mcpm.has_experiments():
+        pytest.skip("experimental kernel: build with `make EXPERIMENTS=1` and run with MCPM_EXPERIMENTS=1")
     arrays, meta = golden
     d = dict(meta["c1"]["system"]); d["n_equil_sets"] = 0          # mu = -1134 K: N grows towards ~550
     s = system_from_meta(d)

@@ -118,3 +118,39 @@ def test_nvt_run_writes_chemical_potential_and_rdf(tmp_path):
     assert rdf[0] == "nBins: 100" and rdf[1] == "r(AA)\tg(r)" and len(rdf) == 102
     g = np.array([[float(v) for v in line.split("\t")] for line in rdf[2:]])
     assert g[0, 0] == pytest.approx(1.5 * 0.12) and np.all(g[:20, 1] == 0.0) and g[:, 1].max() > 0.5   # excluded core, first shell
+
+
+def _sweep_input(tmp_path, devices):
+    text = open(os.path.join(GOLDEN, "ar_small.in")).read().replace("PrintTrajectory\n", "")
+    text = text.replace("ProductionSets 6", "ProductionSets 8").replace("StepsPerSet 400", "StepsPerSet 1000")
+    d = tmp_path / f"dev{devices}"
+    d.mkdir()
+    inp = d / "sweep.in"
+    inp.write_text(text + f"ChemicalPotentialSweep -1700 -1300 3\nReplicas 4\nDevices {devices}\n")
+    return d, inp
+
+
+def test_replicas_of_one_state_point_are_different_chains(tmp_path):
+    """Every chain of a run has its own Philox stream (keyed by the global chain id): replicas of one state point must not
+    coincide — with identical streams their per-replica logs would be equal line for line."""
+    d, inp = _sweep_input(tmp_path, 1)
+    run_driver(d, str(inp), "--quiet")
+    logs = [open(d / f"ar_small_mu1_r{r}" / "pore" / "simulation_ar.log").read() for r in range(4)]
+    assert len(set(logs)) == 4
+
+
+def test_sharding_over_two_devices_does_not_change_the_results(tmp_path, mcpm):
+    """`Devices 2` shards the 12 chains c -> device c mod 2 (one context and host thread per device).  Initial configurations are
+    seeded by the global chain id and so are the Philox streams, so the isotherm file and every per-chain log must equal the
+    1-device run byte for byte."""
+    if mcpm.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    d1, i1 = _sweep_input(tmp_path, 1)
+    d2, i2 = _sweep_input(tmp_path, 2)
+    run_driver(d1, str(i1), "--quiet")
+    run_driver(d2, str(i2), "--quiet")
+    assert open(d1 / "ar_small_isotherm.dat").read() == open(d2 / "ar_small_isotherm.dat").read()
+    for p in range(3):
+        for r in range(4):
+            rel = os.path.join(f"ar_small_mu{p}_r{r}", "pore", "simulation_ar.log")
+            assert open(d1 / rel).read() == open(d2 / rel).read(), rel

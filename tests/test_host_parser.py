@@ -68,3 +68,26 @@ def test_parser_quirks(mcpm, tmp_path):
     rc, cfg = parse(mcpm, str(p))
     assert rc == 0 and (cfg.replicas, cfg.sweep_points, cfg.devices, cfg.capacity) == (8, 40, 8, 768)
     assert (cfg.sweep_mu0, cfg.sweep_mu1) == (-1800.0, -1134.0)
+
+
+def test_malformed_values_return_a_status(mcpm, tmp_path):
+    """mcpm.h promises status codes, never an exception across the C boundary: a value std::stod / stoi cannot parse must
+    come back as MCPM_ERR_ARG with a message (through ctypes an escaping C++ exception is std::terminate)."""
+    text = open(os.path.join(GOLDEN, "ar_cfg1.in")).read()
+    for bad in ("ProductionSets\n", "Seed abc\n", "ar ar Sigma x3.4\n", "NSwapAttempts\n"):
+        p = tmp_path / "bad.in"
+        p.write_text(text + bad)
+        rc, _ = parse(mcpm, str(p))
+        assert rc == 1, bad
+        assert b"malformed" in mcpm.lib().mcpm_last_error()
+        assert mcpm.lib().mcpm_simulate(str(p).encode(), str(tmp_path).encode(), 2) == 1
+    rc, _ = parse(mcpm, str(tmp_path / "nope.in"))
+    assert rc == 5 and b"cannot open" in mcpm.lib().mcpm_last_error()
+
+
+def test_unsupported_inputs_are_refused_before_any_device_work(mcpm, tmp_path):
+    text = open(os.path.join(GOLDEN, "ar_cfg1.in")).read()
+    p = tmp_path / "restart.in"
+    p.write_text(text + "ContinueAfterCrash\n")
+    assert mcpm.lib().mcpm_simulate(str(p).encode(), str(tmp_path).encode(), 2) == 4          # MCPM_ERR_UNSUPPORTED
+    assert b"ContinueAfterCrash" in mcpm.lib().mcpm_last_error()
