@@ -5,20 +5,27 @@
     python bench.py --impl reference [--gpus N] ...              # the reference's CPU path, host cores
 
 A "step" is one SET of the reference's step loop (src/main.cpp:63-84): --steps-per-set trial moves
-(translation / insertion / deletion, 1:1 disp:swap) for EVERY chain.  The workload per GPU is the
+(translation / insertion / deletion, 1:1 disp:swap) for EVERY chain.  The headline workload per GPU is the
 40-point isotherm (mu_k = -1800 + k*666/39 K, C1 system otherwise) with --replicas independent replica
 chains per state point, started from the oracle-equilibrated configurations in
-tests/golden/isotherm_c2_start.npz.  State points / replicas shard over ranks with no collective on the
-data path (weak scaling: every rank runs its own full set of chains with its own Philox seed).
+tests/golden/isotherm_c2_start.npz.  Chains shard over ranks with no collective on the data path (weak
+scaling: every rank runs its own full set of chains; Philox streams are keyed by the global chain id).
 
 Prints ONE JSON line (rank 0).  `value` = trial moves/s with the chain state resident in HBM, timed on
 the device with CUDA events on the engine's stream (max over ranks); `e2e` = the same through the
 C ABI with HOST buffers (pinned): upload all positions, run the set, download positions + statistics,
 every step.  `roofline` is against the FP64 FMA pipe (measured live with a DFMA microbenchmark —
 MEASURED_PEAKS.json carries no fp64 figure); `cpu_baseline` times the compiled reference on the host
-cores on a bounded sample of the same workload.
+cores on a bounded sample of the same workload.  Further sub-records of the same line:
+
+  literal_isotherm   the workload north_star names literally: ONE chain per state point, 40 chains in total, sharded
+                     chain -> rank (chain mod N) over the ranks present — STRONG scaling, emitted at every --gpus N;
+  configs            (N = 1) short runs of the other BASELINE configs C1, C3, C4, C5: value, e2e, roofline fraction, kernel;
+  k3, k1             (N = 1) full-energy kernel pair evaluations/s at N = 500 / 5 000 / 20 000 and the latency of one
+                     EnergyOfParticle call through the C ABI.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -36,6 +43,8 @@ FLOP_PER_PAIR_SLIT = 22      # algorithmic fp64 flop per in-cu
 BYTES_PER_PAIR = 24          # x,y,z fp64 of partner j
 METRIC = "gcmc_trial_moves_per_s"
 UNIT = "moves/s"
+L2_NOTE = "GPU arm: 256 MiB device write between timed steps (L2 flush); CPU arm: not applicable"
+MIN_WARMUP = 3               # timing rule of the bench contract, applied to both arms and reported as run
 
 
 def load_start():
@@ -69,12 +78,9 @@ def build_workload(config, replicas, steps_per_set):
         w["steps_per_set"] = steps_per_set or 2000
         w["start"] = "tests/golden/c3_start.npz"
     elif config == "c4":
-        rng = np.random.default_rng(2024)
-        site = np.arange(28) * (100.0 / 28)
-        gx, gy, gz = np.meshgrid(site, site, site, indexing="ij")
-        p = np.column_stack([gx.ravel(), gy.ravel(), gz.ravel()])[:20000] + (rng.random((20000, 3)) - 0.5) * 0.4 + 0.3
+        cx, cy, cz = workloads.c4_lattice()
         w["workload"] = "C4 dense NVT LJ argon, bulk L=100A, rcut=12A, T=120K, N=20000, translations + Widom sampling (K2 through a cell list: 27 cells of ~39 particles per scan instead of the reference's N)"
-        w["points"] = [(workloads.argon_bulk(n_equil_sets=0), p[:, 0].copy(), p[:, 1].copy(), p[:, 2].copy(), 0.5)]
+        w["points"] = [(workloads.argon_bulk(n_equil_sets=0), cx, cy, cz, 0.5)]
         w["replicas"] = replicas or 148
         w["steps_per_set"] = steps_per_set or 500
         w["flop_per_pair"] = 25
@@ -83,8 +89,7 @@ def build_workload(config, replicas, steps_per_set):
         rng = np.random.default_rng(12345)
         pts = []
         for d in workloads.replica_sweep():
-            n0 = 100
-            pts.append((d, rng.random(n0) * d.width[0], rng.random(n0) * d.width[1], 3.0 + rng.random(n0) * (d.width[2] - 6.0), 0.1 * d.width[2]))
+            pts.append((d, *workloads.c5_start(d, rng), 0.1 * d.width[2]))
         w["workload"] = "C5 1024 replica chains per GPU: H in 8..39A x T in 77..139K, Rcut 17 (L=34A), mu(T)=T ln(8.44e-5 Lambda^3), N0=100"
         w["points"] = pts
         w["replicas"] = replicas or 1
@@ -94,6 +99,11 @@ def build_workload(config, replicas, steps_per_set):
         raise SystemExit(f"unknown config {config}")
     w["steps_per_set"] = w["steps_per_set"] or 10000
     return w
+
+
+def config_record(w):
+    """The `config` object — identical in both arms (what differs between them goes into `arm`)."""
+    return {"workload": w["workload"], "state_points": len(w["points"]), "start": w["start"], "l2": L2_NOTE}
 
 
 class ClockSampler:
@@ -182,6 +192,7 @@ def barrier(dist, local):
     torch.cuda.synchronize(local)
 
 
+# ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_points(w, max_points=40):
     """A bounded sample of the workload's state points for the CPU arm (all of them for C1-C4)."""
     pts = w["points"]
@@ -229,7 +240,9 @@ def reference_arm(args, world, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * cpu_seconds / cores / len(t_all), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["workload"] + ", reference CPU path", "steps_per_point": steps, "start": w["start"]},
+        "config": config_record(w),
+        "arm": {"what": "the reference's own CPU path (oracle/_ref/libmcref.so when built, else the C port), one single-threaded process per host core",
+                "state_points_sampled": res["points"], "steps_per_point_per_step": steps},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": res["kind"], "sample": sample,
                          "per_core": total_steps / cpu_seconds, "makespan_rate": res["moves_per_s_makespan"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -238,149 +251,277 @@ def reference_arm(args, world, rank):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ GPU arm
+class Job:
+    """One context of chains on one GPU + pinned host mirrors of their positions."""
+
+    def __init__(self, m, torch, chains, steps_per_set, device, cap, stream_ids, args, equil_steps=0, seed=20240611, speculation=None):
+        self.m, self.torch, self.device, self.S, self.seed, self.threads = m, torch, device, steps_per_set, seed, args.threads
+        n_chains = len(chains)
+        self.n_chains = n_chains
+        self.eng = m.Engine(n_chains, cap, device=device)
+        if speculation is not None:
+            self.eng.use_speculation(speculation)
+        self.cap = cap = self.eng.capacity
+        self.n0 = np.zeros(n_chains, dtype=np.int32)
+        hx = torch.zeros((n_chains, cap), dtype=torch.float64).pin_memory()
+        hy = torch.zeros_like(hx).pin_memory(); hz = torch.zeros_like(hx).pin_memory()
+        self._pins = (hx, hy, hz)
+        self.X, self.Y, self.Z = hx.numpy(), hy.numpy(), hz.numpy()
+        for c, (sysd, x, y, z, dr) in enumerate(chains):
+            self.eng.set_system(sysd, c)
+            self.eng.set_dr(c, dr)
+            self.n0[c] = len(x)
+            self.X[c, :len(x)] = x; self.Y[c, :len(x)] = y; self.Z[c, :len(x)] = z
+        self.eng.set_stream_ids(stream_ids)
+        self.eng.set_positions_all(self.n0, self.X, self.Y, self.Z)
+        self.set_index = 1
+        if equil_steps:
+            self.eng.run(1, 1, equil_steps, seed=seed + 1, threads=self.threads, check_energy=2)
+            self.eng.reset_accumulators()
+
+    def close(self):
+        self.eng.close()
+
+    def one_step(self):
+        st = self.eng.run(self.set_index, 1, self.S, seed=self.seed, threads=self.threads, check_energy=0)
+        self.set_index += 1
+        return st
+
+    def time_resident(self, steps, warmup, flush, dist):
+        """W untimed + K timed steps, chain state resident in HBM; CUDA events on the engine's stream."""
+        eng, torch, local = self.eng, self.torch, self.device
+        for _ in range(warmup):
+            self.one_step()
+        eng.reset_accumulators()
+        launches0 = eng.launch_count()
+        barrier(dist, local)
+        dev_ms, kern_ms, evals, evals_x = [], [], [], []
+        prev_evals = prev_x = 0
+        t_wall0 = time.perf_counter()
+        for _ in range(steps):
+            flush.zero_()                       # L2 flush between timed iterations (256 MiB write > 126 MB L2)
+            torch.cuda.synchronize(local)
+            eng.timer_start()
+            st = self.one_step()
+            dev_ms.append(eng.timer_stop())
+            kern_ms.append(eng.last_kernel_ms())
+            sv = eng.stats_view(st)
+            tot = int(sv["pair_evals_algorithmic"].sum()); totx = int(sv["pair_evals"].sum())
+            evals.append(tot - prev_evals); prev_evals = tot
+            evals_x.append(totx - prev_x); prev_x = totx
+        barrier(dist, local)
+        stats = eng.stats()
+        sv = eng.stats_view(stats)
+        mean_n = float(np.mean(sv["sum_n"] / np.maximum(sv["samples"], 1))) if stats[0].samples else float(np.mean(sv["n"]))
+        return {"dev_s": sum(dev_ms) * 1e-3, "kern_ms": float(np.mean(kern_ms)), "evals": float(np.mean(evals)), "evals_x": float(np.mean(evals_x)),
+                "evals_sum": float(sum(evals)), "evals_x_sum": float(sum(evals_x)), "launches": eng.launch_count() - launches0,
+                "wall_s": time.perf_counter() - t_wall0, "mean_n": mean_n, "kernel": eng.last_kernel_name(), "stats": stats}
+
+    def time_e2e(self, steps, dist):
+        """The same steps through the C ABI with HOST buffers: H2D of every chain's positions and running energies, K2, D2H of
+        positions and statistics — every step, inside the timed region."""
+        eng, torch, local, m = self.eng, self.torch, self.device, self.m
+        nbuf = np.zeros(self.n_chains, dtype=np.int32)
+        n_host, _, _, _ = eng.get_positions_all(self.X, self.Y, self.Z)
+        nbuf[:] = n_host
+        sv = eng.stats_view(eng.stats())
+        e_pair = sv["pair"].copy(); e_wall = sv["wall"].copy()   # the host owns the state
+        barrier(dist, local)
+        e2e_s = 0.0
+        for _ in range(steps):
+            torch.cuda.synchronize(local)
+            t0 = time.perf_counter()
+            eng.set_positions_all(nbuf, self.X, self.Y, self.Z)       # H2D: every chain's positions, pinned host memory
+            eng.set_running_energy(e_pair, e_wall)                    # ... and their running energies (else K3 re-evaluates them)
+            st = self.one_step()                                      # K2
+            n_host, _, _, _ = eng.get_positions_all(self.X, self.Y, self.Z)   # D2H: positions; statistics came back with run()
+            nbuf[:] = n_host
+            sv = eng.stats_view(st)
+            e_pair = sv["pair"].copy(); e_wall = sv["wall"].copy()
+            e2e_s += time.perf_counter() - t0
+        barrier(dist, local)
+        wcols = min(self.cap, (int(max(nbuf)) + 1 + 31) // 32 * 32)       # columns actually copied (mcpm_set/get_positions_all)
+        stat_bytes = ctypes.sizeof(m.ChainStats)
+        h2d = 3 * self.n_chains * wcols * 8 + self.n_chains * (4 + 16 + stat_bytes)
+        d2h = 3 * self.n_chains * wcols * 8 + self.n_chains * stat_bytes
+        return e2e_s, h2d, d2h
+
+
+def expand(w):
+    """Replica-major chain list of a workload."""
+    pts, R = w["points"], w["replicas"]
+    return [pts[c % len(pts)] for c in range(len(pts) * R)]
+
+
+def roofline_record(w, r, peak_tflops, traffic=None, traffic_source=None):
+    k_ms, evals, evals_x, kernel = r["kern_ms"], r["evals"], r["evals_x"], r["kernel"]
+    # The roofline counts the reference's (algorithmic) pair evaluations, except through the cell list: there the engine evaluates
+    # ~1/19 of them (a different algorithm), and a utilisation figure must count what the FP64 pipe actually executed.
+    roof_evals = evals_x if kernel == "k2_cells" else evals
+    achieved = w["flop_per_pair"] * roof_evals / (k_ms * 1e-3) * 1e-12
+    return {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
+            "frac_executed": w["flop_per_pair"] * evals_x / (k_ms * 1e-3) * 1e-12 / peak_tflops,
+            "traffic": traffic, "traffic_source": traffic_source, "kernel": kernel, "kernel_ms": k_ms,
+            "algorithmic": (f"{w['flop_per_pair']} flop x {evals:.4g} pair evaluations per launch = what the reference's moves evaluate for "
+                            f"the same steps (2N per translation, N per insertion/deletion, SURVEY.md 8d); the engine executed "
+                            f"{evals_x:.4g} of them (per-particle energy cache)") if kernel != "k2_cells" else
+                           (f"{w['flop_per_pair']} flop x {evals_x:.4g} EXECUTED pair evaluations per launch (cell list: 27 cells around the "
+                            f"position); the reference's moves evaluate {evals:.4g} for the same steps (2N per translation, SURVEY.md 8d)"),
+            "peak_source": "mcpm_fp64_peak DFMA microbenchmark, measured live (MEASURED_PEAKS.json has no fp64 figure)",
+            "pair_evals_per_s": evals / (k_ms * 1e-3),
+            "smem_bytes_per_s": BYTES_PER_PAIR * evals / (k_ms * 1e-3)}
+
+
+def literal_isotherm(m, torch, args, world, rank, local, dist, flush):
+    """North_star's literal target: the 40-point isotherm with ONE chain per state point, points sharded chain -> rank
+    (chain mod N).  Strong scaling: the total work is fixed, each rank runs 40/N chains, and since every chain
+    already has an SM (or a whole CTA of candidate warps) to itself the time is bounded by the slowest chain's step latency."""
+    from mcpm_b200 import workloads
+    w = build_workload("c2", 1, args.steps_per_set)
+    pts = w["points"]
+    mine = [c for c in range(len(pts)) if c % world == rank]
+    nmax = max(len(p[1]) for p in pts)
+    job = Job(m, torch, [pts[c] for c in mine], w["steps_per_set"], local, workloads.bench_capacity(nmax), mine, args)
+    r = job.time_resident(args.steps, args.warmup, flush, dist)
+    e2e_s, h2d, d2h = job.time_e2e(args.steps, dist)
+    job.close()
+    t_dev = allmax(dist, local, r["dev_s"])
+    e2e_s = allmax(dist, local, e2e_s)
+    moves = float(len(pts)) * w["steps_per_set"] * args.steps
+    slowest = max((st.n, c) for st, c in zip(r["stats"], mine))
+    return {"what": "40 chains in total (one per state point), chain c on rank c mod N, strong scaling", "chains_total": len(pts),
+            "chains_this_rank": len(mine), "value": moves / t_dev, "unit": UNIT, "scaling": "strong", "ms_per_step": 1e3 * t_dev / args.steps,
+            "us_per_trial_move_per_chain": 1e6 * t_dev / (args.steps * w["steps_per_set"]),
+            "e2e": {"value": moves / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "kernel": r["kernel"], "gpu_launches": int(r["launches"]),
+            "bound": f"step latency of the largest chain on rank 0 (N = {slowest[0]} particles, state point {slowest[1]}): a Markov chain is "
+                     "sequential, so more GPUs only remove neighbours that never competed for its SM"}
+
+
+def k3_k1_records(m, torch, local):
+    """Full-energy kernel (MC::BoxEnergy, N(N-1) pair evaluations as the reference counts them) at N = 500 / 5 000 / 20 000, and the
+    latency of one MC::EnergyOfParticle call (K1) through the C ABI — the reference does ~8e7 pair evaluations/s per core."""
+    from mcpm_b200 import workloads
+    out = {"k3": [], "k1": []}
+    pts = load_start()
+    g3 = np.load(os.path.join(ROOT, "tests", "golden", "c3_start.npz"))
+    cx, cy, cz = workloads.c4_lattice()
+    cases = [("C1 N~560", workloads.argon_slit(n_equil_sets=0), pts[-1][1], pts[-1][2], pts[-1][3], 1024, True),
+             ("C3 N~5.4k", workloads.methane_slit(n_equil_sets=0), g3["x"], g3["y"], g3["z"], 148, True),
+             ("C4 N=20000 all pairs", workloads.argon_bulk(n_equil_sets=0), cx, cy, cz, 16, False),
+             ("C4 N=20000 cell list", workloads.argon_bulk(n_equil_sets=0), cx, cy, cz, 16, True)]
+    for name, sysd, x, y, z, chains, cells in cases:
+        n = len(x)
+        with m.Engine(chains, n + 32, device=local) as e:
+            e.use_cell_list(cells)
+            e.set_system(sysd)
+            for c in range(chains):
+                e.set_positions(c, x, y, z)
+            ms = []
+            for it in range(6):
+                e.box_energy_all()
+                if it >= 2:
+                    ms.append(e.last_kernel_ms())
+            t = float(np.mean(ms)) * 1e-3
+            out["k3"].append({"case": name, "n": n, "chains": chains, "kernel_ms": t * 1e3, "pair_evals_algorithmic_per_s": chains * n * (n - 1.0) / t,
+                              "kernel": "k3c_energy (cell list)" if (cells and n >= 8192) else "k3_box_energy"})
+            if chains >= 148:
+                rng = np.random.default_rng(1)
+                idx = rng.integers(0, n, size=200)
+                trial = np.column_stack([rng.random(200) * sysd.width[0], rng.random(200) * sysd.width[1], 3.0 + rng.random(200) * (sysd.width[2] - 6.0)])
+                for i in range(20):
+                    e.particle_energy(0, int(idx[i]), trial[i])
+                kms = []
+                t0 = time.perf_counter()
+                for i in range(200):
+                    e.particle_energy(0, int(idx[i]), trial[i])
+                    kms.append(e.last_kernel_ms())
+                dt = time.perf_counter() - t0
+                out["k1"].append({"case": name, "n": n, "us_per_call_through_abi": 1e6 * dt / 200, "us_kernel": 1e3 * float(np.mean(kms)),
+                                  "pair_evals_per_call": 2 * n, "what": "mcpm_particle_energy: stored + displaced position in one launch, 64-byte read-back"})
+    return out
+
+
 def gpu_arm(args, world, rank, local, dist):
     import torch
     import mcpm_b200 as m
     from mcpm_b200 import workloads
 
-    w = build_workload(args.config, args.replicas, args.steps_per_set)
-    pts = w["points"]
-    P, R, S = len(pts), w["replicas"], w["steps_per_set"]
-    n_chains = P * R
-    nmax = max(len(p[1]) for p in pts)
-    cap = args.capacity or int(-(-int(nmax * 1.15 + 40) // 32) * 32)   # headroom for fluctuations of N; overflow is an error
-    if args.config == "c5":
-        cap = args.capacity or 1024
-    eng = m.Engine(n_chains, cap, device=local)
-    if args.speculation is not None:
-        eng.use_speculation(args.speculation)
-    cap = eng.capacity
-    seed = 20240611 + 7919 * rank           # every rank: its own replicas of the workload
-    n0 = np.zeros(n_chains, dtype=np.int32)
-    hx = torch.zeros((n_chains, cap), dtype=torch.float64).pin_memory()
-    hy = torch.zeros_like(hx).pin_memory(); hz = torch.zeros_like(hx).pin_memory()
-    X, Y, Z = hx.numpy(), hy.numpy(), hz.numpy()
-    for c in range(n_chains):
-        sysd, x, y, z, dr = pts[c % P]
-        eng.set_system(sysd, c)
-        eng.set_dr(c, dr)
-        n0[c] = len(x)
-        X[c, :len(x)] = x; Y[c, :len(x)] = y; Z[c, :len(x)] = z
-    eng.set_positions_all(n0, X, Y, Z)
-    if w["equil_steps"]:
-        eng.run(1, 1, w["equil_steps"], seed=seed + 1, threads=args.threads, check_energy=2)
-        eng.reset_accumulators()
     flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=f"cuda:{local}")
+    w = build_workload(args.config, args.replicas, args.steps_per_set)
+    chains = expand(w)
+    P, R, S = len(w["points"]), w["replicas"], w["steps_per_set"]
+    n_chains = len(chains)
+    nmax = max(len(p[1]) for p in w["points"])
+    cap = args.capacity or (1024 if args.config == "c5" else workloads.bench_capacity(nmax))   # headroom for fluctuations of N; overflow is an error
+    ids = np.arange(n_chains, dtype=np.uint32) + np.uint32(rank * n_chains)      # every rank: its own replicas of the workload
+    job = Job(m, torch, chains, S, local, cap, ids, args, equil_steps=w["equil_steps"], speculation=args.speculation)
 
-    def one_step(set_index):
-        return eng.run(set_index, 1, S, seed=seed, threads=args.threads, check_energy=0)
-
-    # ---- device-resident timing -------------------------------------------------------------------
-    set_index = 1
-    for _ in range(args.warmup):
-        one_step(set_index); set_index += 1
-    eng.reset_accumulators()
-    launches0 = eng.launch_count()
     sampler = ClockSampler(local)
-    barrier(dist, local)
     if rank == 0:
         sampler.start()
-    dev_ms, kern_ms, evals, evals_x = [], [], [], []
-    prev_evals = prev_x = 0
-    t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.zero_()                       # L2 flush between timed iterations (256 MiB write > 126 MB L2)
-        torch.cuda.synchronize(local)
-        eng.timer_start()
-        st = one_step(set_index); set_index += 1
-        dev_ms.append(eng.timer_stop())
-        kern_ms.append(eng.last_kernel_ms())
-        tot = sum(int(s.pair_evals_algorithmic) for s in st); totx = sum(int(s.pair_evals) for s in st)
-        evals.append(tot - prev_evals); prev_evals = tot
-        evals_x.append(totx - prev_x); prev_x = totx
-    barrier(dist, local)
-    t_wall = time.perf_counter() - t_wall0
-    launches = eng.launch_count() - launches0
-    t_dev = allmax(dist, local, sum(dev_ms) * 1e-3)
+    r = job.time_resident(args.steps, args.warmup, flush, dist)
+    e2e_s, h2d, d2h = job.time_e2e(args.steps, dist)
+    clocks = sampler.stop() if rank == 0 else None     # sampled over both timed regions (device-resident and end-to-end)
+    cap = job.cap
+    job.close()
+    t_dev = allmax(dist, local, r["dev_s"])
+    e2e_s = allmax(dist, local, e2e_s)
     moves_per_rank = float(n_chains) * S * args.steps
     value = world * moves_per_rank / t_dev
-    evals_all = allsum(dist, local, float(sum(evals)))
-    evals_x_all = allsum(dist, local, float(sum(evals_x)))
-    stats = eng.stats()
-    mean_n = float(np.mean([s.sum_n / max(s.samples, 1) for s in stats])) if stats[0].samples else float(np.mean([s.n for s in stats]))
+    evals_all = allsum(dist, local, r["evals_sum"])
+    evals_x_all = allsum(dist, local, r["evals_x_sum"])
 
-    # ---- end to end through the C ABI with host buffers ---------------------------------------------
-    nbuf = np.zeros(n_chains, dtype=np.int32)
-    n_host, _, _, _ = eng.get_positions_all(X, Y, Z)
-    nbuf[:] = n_host
-    sv = eng.stats_view(stats)
-    e_pair = sv["pair"].copy(); e_wall = sv["wall"].copy()   # the host owns the state
-    barrier(dist, local)
-    e2e_s = 0.0
-    for _ in range(args.steps):
-        torch.cuda.synchronize(local)
-        t0 = time.perf_counter()
-        eng.set_positions_all(nbuf, X, Y, Z)                    # H2D: every chain's positions, pinned host memory
-        eng.set_running_energy(e_pair, e_wall)                  # ... and their running energies (else K3 re-evaluates them)
-        st = one_step(set_index); set_index += 1              # K2
-        n_host, _, _, _ = eng.get_positions_all(X, Y, Z)        # D2H: positions; statistics came back with run()
-        nbuf[:] = n_host
-        sv = eng.stats_view(st)
-        e_pair = sv["pair"].copy(); e_wall = sv["wall"].copy()
-        e2e_s += time.perf_counter() - t0
-    barrier(dist, local)
-    clocks = sampler.stop() if rank == 0 else None     # sampled over both timed regions (device-resident and end-to-end)
-    e2e_s = allmax(dist, local, e2e_s)
-    e2e_value = world * moves_per_rank / e2e_s
-    wcols = min(cap, (int(max(nbuf)) + 1 + 31) // 32 * 32)       # columns actually copied (mcpm_set/get_positions_all)
-    h2d = 3 * n_chains * wcols * 8 + n_chains * (4 + 16 + 352)
-    d2h = 3 * n_chains * wcols * 8 + n_chains * 352
-
+    literal = literal_isotherm(m, torch, args, world, rank, local, dist, flush) if args.config == "c2" and not args.no_literal else None
     if rank != 0:
         return
-    # ---- roofline (FP64 pipe) -------------------------------------------------------------------
     peak_tflops, _ = m.fp64_peak_tflops(local)
-    k_ms = float(np.mean(kern_ms))
-    evals_per_launch = float(np.mean(evals))
-    kernel_name = eng.last_kernel_name()
-    executed_per_launch = float(np.mean(evals_x))
-    # The roofline counts the reference's (algorithmic) pair evaluations, except through the cell list: there the engine evaluates
-    # ~1/19 of them (a different algorithm), and a utilisation figure must count what the FP64 pipe actually executed.
-    roof_evals = executed_per_launch if kernel_name == "k2_cells" else evals_per_launch
-    achieved = w["flop_per_pair"] * roof_evals / (k_ms * 1e-3) * 1e-12
-    traffic = None
+    traffic = traffic_source = None
     summ = os.path.join(ROOT, "profiles", "k2_ncu_summary.json")
-    if os.path.exists(summ) and kernel_name == "k2_chains" and args.config == "c2" and not args.replicas:   # the capture is of the default workload
+    if os.path.exists(summ) and r["kernel"] == "k2_chains" and args.config == "c2" and not args.replicas:   # the capture is of the default workload
         try:
             traffic = json.load(open(summ)).get("dram_bytes_per_launch")
+            traffic_source = "profiles/k2_ncu_summary.json: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this command, NOT measured in this run"
         except Exception:
             traffic = None
-    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-                "traffic": traffic, "kernel": kernel_name, "kernel_ms": k_ms,
-                "algorithmic": (f"{w['flop_per_pair']} flop x {evals_per_launch:.4g} pair evaluations per launch = what the reference's moves evaluate for "
-                                f"the same steps (2N per translation, N per insertion/deletion, SURVEY.md 8d); the engine executed "
-                                f"{executed_per_launch:.4g} of them (per-particle energy cache)") if kernel_name != "k2_cells" else
-                               (f"{w['flop_per_pair']} flop x {executed_per_launch:.4g} EXECUTED pair evaluations per launch (cell list: 27 cells around the "
-                                f"position); the reference's moves evaluate {evals_per_launch:.4g} for the same steps (2N per translation, SURVEY.md 8d)"),
-                "peak_source": "mcpm_fp64_peak DFMA microbenchmark, measured live (MEASURED_PEAKS.json has no fp64 figure)",
-                "pair_evals_per_s": evals_per_launch / (k_ms * 1e-3),
-                "smem_bytes_per_s": BYTES_PER_PAIR * evals_per_launch / (k_ms * 1e-3)}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["workload"],
-                   "state_points": P, "replicas_per_point_per_gpu": R, "chains_per_gpu": n_chains, "steps_per_set": S,
-                   "capacity": cap, "mean_particles": mean_n, "threads_per_chain": args.threads or "auto",
-                   "start": w["start"], "rng": "device Philox4x32-10",
-                   "l2": "256 MiB device write between timed steps (L2 flush)"},
+        "config": config_record(w),
+        "arm": {"what": "B200 engine (libmcpm.so), device Philox4x32-10", "replicas_per_point_per_gpu": R, "chains_per_gpu": n_chains,
+                "steps_per_set": S, "capacity": cap, "mean_particles": r["mean_n"], "threads_per_chain": args.threads or "auto"},
         "pair_evals_per_s": evals_all / t_dev, "pair_evals_executed_per_s": evals_x_all / t_dev,
-        "wall_s_timed_region": t_wall,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": int(launches),
+        "wall_s_timed_region": r["wall_s"],
+        "e2e": {"value": world * moves_per_rank / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(r["launches"]),
         "clocks": clocks,
-        "roofline": roofline,
+        "roofline": roofline_record(w, r, peak_tflops, traffic, traffic_source),
     }
+    if literal is not None:
+        line["literal_isotherm"] = literal
+    if world == 1 and args.config == "c2" and not args.no_configs:
+        recs = []
+        for cfg in ("c1", "c3", "c4", "c5"):
+            wc = build_workload(cfg, 0, 0)
+            nm = max(len(p[1]) for p in wc["points"])
+            chains_c = expand(wc)
+            jc = Job(m, torch, chains_c, wc["steps_per_set"], local, 1024 if cfg == "c5" else workloads.bench_capacity(nm),
+                     np.arange(len(chains_c), dtype=np.uint32), args, equil_steps=wc["equil_steps"])
+            k = min(args.steps, 3)
+            rc = jc.time_resident(k, MIN_WARMUP, flush, None)
+            es, hb, db = jc.time_e2e(k, None)
+            jc.close()
+            mv = float(len(chains_c)) * wc["steps_per_set"] * k
+            rf = roofline_record(wc, rc, peak_tflops)
+            recs.append({"config": cfg, "workload": wc["workload"], "chains": len(chains_c), "steps_per_set": wc["steps_per_set"], "steps": k,
+                         "mean_particles": rc["mean_n"], "value": mv / rc["dev_s"], "unit": UNIT,
+                         "e2e": {"value": mv / es, "unit": UNIT, "h2d_bytes_per_step": hb, "d2h_bytes_per_step": db},
+                         "kernel": rc["kernel"], "roofline_frac": rf["frac"], "roofline_frac_executed": rf["frac_executed"],
+                         "pair_evals_per_s": rf["pair_evals_per_s"]})
+        line["configs"] = recs
+        line.update(k3_k1_records(m, torch, local))
     if world == 1 and not args.no_cpu:
         from oracle import cpu_baseline
         pool = cpu_baseline.CpuPool()
@@ -411,9 +552,13 @@ def main():
     ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"], help="BASELINE.json config (default: the isotherm)")
     ap.add_argument("--capacity", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short C1/C3/C4/C5 runs and the K3/K1 records")
+    ap.add_argument("--no-literal", action="store_true", help="skip the literal 40-chain isotherm sub-record")
     ap.add_argument("--speculation", type=int, default=None, help="mcpm_use_speculation mode (experiments)")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.warmup < MIN_WARMUP:
+        print(f"bench.py: --warmup {args.warmup} raised to {MIN_WARMUP} (timing rule: at least 3 warm-up steps; both arms)", file=sys.stderr)
+        args.warmup = MIN_WARMUP
     if args.impl == "reference":
         world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
         reference_arm(args, world, rank)

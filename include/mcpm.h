@@ -182,6 +182,10 @@ int mcpm_get_stats(mcpm_ctx* ctx, mcpm_chain_stats* stats /* [n_chains] */);
  * 1.5 N pair evaluations per step at 20 % translation acceptance.  enable = 0 re-sums both energies every move, exactly
  * like MC::MoveParticle / MC::SwapParticle. */
 int mcpm_use_energy_cache(mcpm_ctx* ctx, int enable);
+/* The cache itself, for drift checks: pair[j] = the pairPotE (K) the engine currently carries for particle j of `chain`
+ * (what MC::EnergyOfParticle would store, src/energy.cpp:102-104); *valid = 0 if no K2 launch has left a consistent cache
+ * for the chain's present configuration (then pair[] is not written).  Compare with mcpm_box_energy's per_pair. */
+int mcpm_get_energy_cache(mcpm_ctx* ctx, int chain, double* pair /* n */, int* valid);
 /* Speculative moves (the latency kernel for FEW chains, e.g. one chain per isotherm point): a CTA of 8 warps evaluates
  * the next 8 steps of its chain concurrently against the same configuration, commits the first accepted one and
  * re-evaluates the steps after it; rejected steps before it stand.  The chain is exactly the sequential one (same

@@ -75,6 +75,7 @@ struct mcpm_ctx {
     std::vector<ChainState> h_state;
     std::vector<mcpm_system_desc> h_desc;
     std::vector<char> has_system;
+    std::vector<char> cache_fresh;   // the device cache belongs to the configuration now on the device (no host write since the last K2 launch)
     float last_ms = 0.f;
     unsigned long long launches = 0;
 };
@@ -202,6 +203,7 @@ int mcpm_create(int device, int n_chains, int capacity, mcpm_ctx** out) {
     for (int k = 0; k < n_chains; k++) c->h_state[k].stream_id = (unsigned int)k;
     c->h_desc.assign(n_chains, mcpm_system_desc());
     c->has_system.assign(n_chains, 0);
+    c->cache_fresh.assign(n_chains, 0);
     CU(cudaMemcpyAsync(c->d_state, c->h_state.data(), sizeof(ChainState) * n_chains, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     *out = c;
@@ -272,6 +274,7 @@ int mcpm_set_system(mcpm_ctx* c, int chain, const mcpm_system_desc* desc) {
         // have left coordinates outside [0, L], which the fast minimum image must not see.
         if (c->has_system[k] && !same_energetics(c->h_params[k], P)) {
             S.energy_valid = 0; S.cache_valid = 0; S.cache_sum = 0ull;
+            c->cache_fresh[k] = 0;
             if (S.st.n > 0) recheck = true;
         }
         // dr: taken from the description the first time and whenever the description's own dr changes; an unchanged
@@ -307,6 +310,7 @@ int mcpm_set_positions(mcpm_ctx* c, int chain, int n, const double* x, const dou
         CU(cudaMemcpyAsync(c->d_z + off, z, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
     }
     ChainState& S = c->h_state[chain];
+    c->cache_fresh[chain] = 0;
     S.st.n = n; S.st.overflow = 0;
     S.st.pair = S.st.wall = S.st.energy = 0.0; S.energy_valid = 0;
     S.fast_image = in_box(c->h_params[chain], n, x, y, z) ? 1 : 0;
@@ -358,6 +362,7 @@ int mcpm_set_positions_all(mcpm_ctx* c, const int* n, const double* x, const dou
     for (int k = 0; k < c->n_chains; k++) {
         ChainState& S = c->h_state[k];
         S.st.n = n[k]; S.st.overflow = 0; S.energy_valid = 0;
+        c->cache_fresh[k] = 0;
         S.fast_image = c->h_flags[c->n_chains + k];
     }
     CU(cudaMemcpyAsync(c->d_state, c->h_state.data(), sizeof(ChainState) * c->n_chains, cudaMemcpyHostToDevice, c->stream));
@@ -493,6 +498,7 @@ static int write_slot(mcpm_ctx* c, int chain, int slot, const double xyz[3]) {
     const ChainParams& P = c->h_params[chain];
     for (int k = 0; k < 3; k++) if (P.pbc[k] && !(xyz[k] >= 0.0 && xyz[k] <= P.L[k])) c->h_state[chain].fast_image = 0;
     c->h_state[chain].energy_valid = 0;
+    c->cache_fresh[chain] = 0;
     return MCPM_OK;
 }
 int mcpm_apply_move(mcpm_ctx* c, int chain, int index, const double xyz[3]) {
@@ -529,6 +535,7 @@ int mcpm_remove_swap_last(mcpm_ctx* c, int chain, int index) {
     }
     c->h_state[chain].st.n = n - 1;
     c->h_state[chain].energy_valid = 0;
+    c->cache_fresh[chain] = 0;
     rc = push_state(c, chain); if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));
     return MCPM_OK;
@@ -749,6 +756,7 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     CU(cudaEventRecord(c->ev1, c->stream));
     if (p->trace) CU(cudaMemcpyAsync(p->trace, c->d_trace, (size_t)c->n_chains * nsteps, cudaMemcpyDeviceToHost, c->stream));
     int rc = pull_states(c); if (rc) return rc;
+    for (int k = 0; k < c->n_chains; k++) c->cache_fresh[k] = (a.ep != nullptr && c->h_state[k].cache_valid) ? 1 : 0;
     CU(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
     if (use_k2c && p->check_energy) {   // the cell-list kernel leaves the end-of-launch energy check to K3 (itself through a cell list)
         bool stopped = false;
@@ -863,6 +871,21 @@ int mcpm_use_subwarp(mcpm_ctx* c, int enable) {
 int mcpm_use_energy_cache(mcpm_ctx* c, int enable) {
     if (!c) return fail(MCPM_ERR_ARG, "null context");
     c->use_cache = enable ? 1 : 0;
+    return MCPM_OK;
+}
+
+int mcpm_get_energy_cache(mcpm_ctx* c, int chain, double* pair, int* valid) {
+    int rc = check_chain(c, chain); if (rc) return rc;
+    if (!pair || !valid) return fail(MCPM_ERR_ARG, "null argument");
+    const ChainState& S = c->h_state[chain];
+    *valid = (c->d_ep && S.cache_valid && c->cache_fresh[chain]) ? 1 : 0;
+    if (!*valid) return MCPM_OK;
+    CU(cudaSetDevice(c->device));
+    const int n = S.st.n;
+    if (n > 0) CU(cudaMemcpyAsync(pair, c->d_ep + (size_t)chain * c->cap, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const double eps4 = c->h_params[chain].eps4;          // the cache holds sums of s6(s6-1); 4*eps is applied once per sum
+    for (int j = 0; j < n; j++) pair[j] *= eps4;
     return MCPM_OK;
 }
 

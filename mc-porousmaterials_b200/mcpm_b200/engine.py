@@ -133,6 +133,13 @@ class Engine:
     def use_energy_cache(self, enable=True):
         check(self.L.mcpm_use_energy_cache(self.h, 1 if enable else 0))
 
+    def energy_cache(self, chain):
+        """Per-particle pair energies (K) carried by the K2 energy cache, or None if no valid cache exists."""
+        n = self.stats()[chain].n
+        out = np.zeros(max(n, 1)); valid = C.c_int(0)
+        check(self.L.mcpm_get_energy_cache(self.h, chain, _p(out), C.byref(valid)))
+        return out[:n].copy() if valid.value else None
+
     def use_cell_list(self, enable=True):
         check(self.L.mcpm_use_cell_list(self.h, 1 if enable else 0))
 

@@ -1,7 +1,9 @@
-"""The BASELINE.json workloads as system descriptions.  No numerics here."""
+"""The BASELINE.json workloads as system descriptions and synthetic start configurations.  No numerics here."""
 from __future__ import annotations
 
 import math
+
+import numpy as np
 
 from .abi import GEOM_BULK, GEOM_SLIT, WALL_NONE, WALL_SLIT_LJ, SystemDesc
 
@@ -62,3 +64,23 @@ def replica_sweep(n_h: int = 32, n_t: int = 32):
             mu = T * math.log(8.44e-5 * thermal_wavelength(39.948, T) ** 3)
             out.append(argon_slit(mu=mu, H=H, rcut=17.0, T=T))
     return out
+
+
+def c4_lattice(n: int = 20000, size: float = 100.0, m: int = 28, seed: int = 2024):
+    """C4 start: simple-cubic lattice of m^3 sites (spacing size/m), first n sites occupied, uniform
+    jitter +-0.2 A per axis (numpy default_rng(seed)), shifted by 0.3 A so that every coordinate lies inside the box."""
+    rng = np.random.default_rng(seed)
+    site = np.arange(m) * (size / m)
+    gx, gy, gz = np.meshgrid(site, site, site, indexing="ij")
+    p = np.column_stack([gx.ravel(), gy.ravel(), gz.ravel()])[:n] + (rng.random((n, 3)) - 0.5) * 0.4 + 0.3
+    return p[:, 0].copy(), p[:, 1].copy(), p[:, 2].copy()
+
+
+def c5_start(desc: SystemDesc, rng, n0: int = 100):
+    """C5 start: n0 random particles, at least 3 A away from either wall."""
+    return rng.random(n0) * desc.width[0], rng.random(n0) * desc.width[1], 3.0 + rng.random(n0) * (desc.width[2] - 6.0)
+
+
+def bench_capacity(nmax: int) -> int:
+    """Particle slots per chain used by bench.py: 15 % + 40 headroom over the largest start loading, rounded up to 32."""
+    return int(-(-int(nmax * 1.15 + 40) // 32) * 32)

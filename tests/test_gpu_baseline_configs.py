@@ -1,0 +1,257 @@
+"""GPU: parity on the BASELINE configurations AS THEY ARE RUN by bench.py (sizes, boxes, move weights, kernels), against the
+C oracle (pinned to the compiled reference, tests/test_oracle_vs_reference.py) and against loadings of the compiled reference
+itself (tests/golden/isotherm_reference.json, made by tests/golden/make_isotherm_reference.py).
+
+  C3  tests/golden/c3_start.npz (N ~ 5.4k, Rcut 92 => L = 184 A, disp:swap = 1:3): K1, K3, 400-step replay trace
+  C4  N = 20 000, L = 100 A, rcut = 12 A (8x8x8 cells): K3 vs the oracle, k2_cells replay trace with Widom sampling
+  C5  corners of the H x T sweep (H = 8 / 39 A, T = 77 / 139 K) through k2_chains, k2_pair, k2_quad, k2_spec
+  C1  10^6-step traces per kernel family vs the oracle + drift of the per-particle energy cache
+  C2  <N> at 8 of the 40 chemical potentials vs chains of the compiled reference, 2 sigma
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, O, system_from_meta
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def close(a, b, rtol=RTOL):
+    return np.allclose(a, b, rtol=rtol, atol=0)
+
+
+def first_divergence(a, b):
+    d = np.nonzero(a != b)[0]
+    return int(d[0]) if len(d) else -1
+
+
+def follow_oracle_replay(mcpm, system, x, y, z, capacity, nsteps, seed, draws_per_step, kernel, threads=0, spec=None):
+    u = O.mt_uniforms(seed, draws_per_step * nsteps)
+    o = O.COracle(system, capacity)
+    o.set_positions(x, y, z); o.box_energy(); o.replay(u)
+    otr = o.run_sets(1, 1, nsteps, 0, True)
+    with mcpm.Engine(1, capacity) as e:
+        if spec is not None:
+            e.use_speculation(spec)
+        e.set_system(system)
+        e.set_positions(0, x, y, z)
+        stats, tr = e.run(1, 1, nsteps, replay=u, trace=True, threads=threads, check_energy=1)
+        assert e.last_kernel_name() == kernel
+        g = e.get_positions(0)
+    div = first_divergence(tr[0], otr)
+    assert div == -1, f"first divergence at step {div}"
+    for a, b in zip(g, o.get_positions()):
+        assert np.array_equal(a, b)
+    st, ost = stats[0], o.state()
+    assert st.n == ost["n"] and st.replay_consumed == o.draws()
+    assert st.energy == pytest.approx(st.energy_check, rel=RTOL)
+    assert st.energy == pytest.approx(ost["exact_energy"], rel=RTOL)
+    return st, o
+
+
+# ---------------------------------------------------------------------------------------------- C3
+@pytest.fixture(scope="module")
+def c3():
+    g = np.load(os.path.join(GOLDEN, "c3_start.npz"))
+    return O.methane_slit(rcut=92.0, n_equil_sets=0), g["x"], g["y"], g["z"], float(g["dr"])
+
+
+def test_c3_energies_on_the_bench_fixture(mcpm, c3):
+    """K3 (per particle and totals) and K1 (stored, displaced and ghost positions) on the configuration bench.py --config c3
+    starts from: N ~ 5.4k, L = 184 A."""
+    from mcpm_b200 import workloads
+    s, x, y, z, dr = c3
+    n = len(x)
+    assert 5000 < n < 6000 and list(s.width) == [184.0, 184.0, 20.0] and (s.n_disp, s.n_swap) == (1, 3)
+    o = O.COracle(s, n + 8)
+    o.set_positions(x, y, z)
+    obox, opp, opw = o.box_energy()
+    rng = np.random.default_rng(3)
+    with mcpm.Engine(1, workloads.bench_capacity(n)) as e:
+        e.set_system(s)
+        e.set_positions(0, x, y, z)
+        box, pp, pw = e.box_energy(0)
+        assert close(box, obox) and close(pp, opp) and close(pw, opw)
+        for i in rng.integers(0, n, size=6):
+            t = [rng.random() * 184.0, rng.random() * 184.0, 2.5 + rng.random() * 15.0]
+            cur, moved = e.particle_energy(0, int(i), t)
+            assert close(cur, o.particle_energy(int(i))) and close(moved, o.moved_energy(int(i), *t))
+            _, ghost = e.particle_energy(0, -1, t)
+            assert close(ghost, o.trial_energy(*t))
+
+
+def test_c3_replay_trace_with_c3_move_weights(mcpm, c3):
+    """400 steps of the reference's mt19937_64 stream at disp:swap = 1:3 from the bench fixture, default kernel choice
+    (one chain of 5.4k particles: 256 threads, positions in shared memory)."""
+    from mcpm_b200 import workloads
+    s, x, y, z, dr = c3
+    s.dr = dr
+    st, _ = follow_oracle_replay(mcpm, s, x, y, z, workloads.bench_capacity(len(x)), 400, 31, 8, "k2_chains")
+    assert st.tot_ins + st.tot_del > 200 and st.tot_disp > 50
+
+
+# ---------------------------------------------------------------------------------------------- C4
+@pytest.fixture(scope="module")
+def c4():
+    from mcpm_b200 import workloads
+    x, y, z = workloads.c4_lattice()
+    return O.argon_bulk(size=100.0, rcut=12.0, n_equil_sets=0), x, y, z
+
+
+def test_c4_box_energy_against_the_oracle_at_full_size(mcpm, c4):
+    """N = 20 000: the cell-list K3 and the all-pairs K3 against MC::BoxEnergy's 4e8 evaluations in the C oracle (~5 s)."""
+    s, x, y, z = c4
+    o = O.COracle(s, 20008)
+    o.set_positions(x, y, z)
+    obox, opp, opw = o.box_energy()
+    with mcpm.Engine(1, 20032) as e:
+        e.set_system(s)
+        e.set_positions(0, x, y, z)
+        for cells in (True, False):
+            e.use_cell_list(cells)
+            box, pp, pw = e.box_energy(0)
+            assert close(box, obox) and close(pp, opp) and close(pw, opw), cells
+
+
+@pytest.mark.parametrize("production", [True, False], ids=["widom", "moves"])
+def test_c4_cell_list_chain_on_the_real_box(mcpm, c4, production):
+    """k2_cells on C4's own 8x8x8 grid (L = 100 A, rcut = 12 A, N = 20 000), NVT with ComputeWidom after every production step
+    (13 draws per step) — what bench.py --config c4 times — against the all-pairs oracle under the reference's stream."""
+    from mcpm_b200 import workloads
+    s, x, y, z = c4
+    s = O.argon_bulk(size=100.0, rcut=12.0, n_equil_sets=0 if production else 5)
+    s.dr = 0.5
+    st, o = follow_oracle_replay(mcpm, s, x, y, z, workloads.bench_capacity(20000), 320, 41, 13, "k2_cells")
+    (wi, wd), (ni, nd) = o.get_widom()
+    assert (st.widom_insertions, st.widom_deletions) == (ni, nd)
+    assert ni + nd == (322 if production else 2)
+    assert st.widom_insert == pytest.approx(wi, rel=1e-9) and st.widom_delete == pytest.approx(wd, rel=1e-9)
+    assert st.tot_disp_acc > 30
+
+
+# ---------------------------------------------------------------------------------------------- C5
+@pytest.mark.parametrize("kernel,spec,threads", [("k2_chains", 0, 32), ("k2_pair", 2, 32), ("k2_quad", 4, 0), ("k2_spec", 1, 0)])
+@pytest.mark.parametrize("ih,it", [(0, 0), (0, 31), (31, 0), (31, 31)], ids=["H8_T77", "H8_T139", "H39_T77", "H39_T139"])
+def test_c5_corners_follow_the_oracle(mcpm, ih, it, kernel, spec, threads):
+    """Corners of the pore-width x temperature sweep.  H = 8 A: the two walls' terms overlap and most insertion attempts land
+    where the wall energy is huge; T = 139 K: high acceptance.  Started like bench.py --config c5 (100 random particles), so
+    the first sets also push hard overlaps through the energy cache.  Device Philox vs the oracle on the same stream."""
+    from mcpm_b200 import workloads
+    d = workloads.replica_sweep()[ih * 32 + it]
+    assert (d.width[2], d.temperature) == (8.0 + ih, 77.0 + 2.0 * it)
+    s = O.make_system(**{name: (list(getattr(d, name)) if name == "width" else getattr(d, name)) for name, _ in d._fields_ if name != "reserved"})
+    s.n_equil_sets = 2
+    x, y, z = workloads.c5_start(d, np.random.default_rng(500 + ih + it))
+    seed, chain_id, sets, sps = 12345, ih * 32 + it, 3, 4000
+    o = O.COracle(s, 1024)
+    o.set_positions(x, y, z); o.box_energy(); o.philox(seed, chain_id, 0)
+    otr = o.run_sets(1, sets, sps, 0, True)
+    with mcpm.Engine(1, 1024) as e:
+        e.use_speculation(spec)
+        e.set_system(s)
+        e.set_positions(0, x, y, z)
+        e.set_stream_ids([chain_id])
+        stats, tr = e.run(1, sets, sps, seed=seed, trace=True, threads=threads, check_energy=1)
+        assert e.last_kernel_name() == kernel
+        g = e.get_positions(0)
+    div = first_divergence(tr[0], otr)
+    assert div == -1, f"first divergence at step {div}"
+    for a, b in zip(g, o.get_positions()):
+        assert np.array_equal(a, b)
+    st, ost = stats[0], o.state()
+    assert (st.n, st.dr, st.tot_disp_acc, st.samples, st.sum_n) == (ost["n"], ost["dr"], ost["tot_disp_acc"], ost["samples"], ost["sum_n"])
+    assert st.energy == pytest.approx(st.energy_check, rel=1e-9)
+    assert st.energy == pytest.approx(ost["exact_energy"], rel=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------- C1, long traces
+@pytest.fixture(scope="module")
+def long_oracle(golden):
+    """ONE oracle chain of 10^6 steps (C1 system, equilibrated golden configuration, Philox stream): every kernel family is
+    compared with it."""
+    arrays, meta = golden
+    s = system_from_meta(meta["c1"]["system"])
+    s.n_equil_sets = 10
+    x, y, z = arrays["c1_x"], arrays["c1_y"], arrays["c1_z"]
+    o = O.COracle(s, 1024)
+    o.set_positions(x, y, z); o.box_energy(); o.philox(2024, 0, 0)
+    otr = o.run_sets(1, 100, 10000, 0, True)
+    return s, (x, y, z), otr, o.get_positions(), o.state()
+
+
+@pytest.mark.parametrize("kernel,spec,threads", [("k2_chains", 0, 32), ("k2_chains", 0, 128), ("k2_spec", 1, 0), ("k2_pair", 2, 32), ("k2_quad", 4, 0)])
+def test_million_step_trace_and_cache_drift(mcpm, long_oracle, kernel, spec, threads):
+    """10^6 steps (100 sets x 10 000, dr adapting during the first 10) in 4 launches with NO end-of-launch rebuild: the
+    accept/reject trace must equal the oracle's (first divergence reported), positions bit-identical, and the per-particle
+    energy cache — updated incrementally ~2e5 times, never rebuilt — must still equal a fresh MC::BoxEnergy per particle."""
+    s, (x, y, z), otr, opos, ost = long_oracle
+    with mcpm.Engine(1, 1024) as e:
+        e.use_speculation(spec)
+        e.set_system(s)
+        e.set_positions(0, x, y, z)
+        trs = []
+        for k in range(4):
+            st, tr = e.run(1 + 25 * k, 25, 10000, seed=2024, trace=True, threads=threads, check_energy=0)
+            trs.append(tr[0])
+        assert e.last_kernel_name() == kernel
+        ep = e.energy_cache(0)
+        running = e.stats()[0]
+        g = e.get_positions(0)
+        box, pp, _ = e.box_energy(0)
+    tr = np.concatenate(trs)
+    div = first_divergence(tr, otr)
+    assert div == -1, f"{kernel}: first divergence from the oracle at step {div} of 1e6"
+    for a, b in zip(g, opos):
+        assert np.array_equal(a, b)
+    assert running.n == ost["n"] and running.dr == ost["dr"] and running.sum_n == ost["sum_n"]
+    assert ep is not None and len(ep) == running.n
+    scale = np.maximum(np.abs(pp), np.mean(np.abs(pp)))
+    drift = np.max(np.abs(ep - pp) / scale)
+    print(f"{kernel} T={threads}: max |ep - recomputed| / |ep| after 1e6 steps = {drift:.3e}; running energy off by "
+          f"{abs(running.energy - box[3]) / abs(box[3]):.3e}")
+    assert drift <= 1e-10
+    assert running.energy == pytest.approx(box[3], rel=RTOL)
+    assert running.energy == pytest.approx(ost["exact_energy"], rel=RTOL)
+
+
+# ---------------------------------------------------------------------------------------------- C2, ensemble
+def test_isotherm_loadings_match_the_compiled_reference_within_2_sigma(mcpm):
+    """<N>(mu) at 8 of C2's 40 state points: 64 device-Philox replicas per point (20 equilibration + 80 production sets x
+    10 000 steps, C2's own protocol) against 8 chains x 10^6 steps of the COMPILED reference (fixture).  Criterion: north_star's
+    2 sigma on every point, sigma = combined standard error of the two independent estimates, plus a chi^2 bound."""
+    ref = json.load(open(os.path.join(GOLDEN, "isotherm_reference.json")))
+    g = np.load(os.path.join(GOLDEN, "isotherm_c2_start.npz"))
+    pts = ref["points"]
+    R = 64
+    with mcpm.Engine(len(pts) * R, 704) as e:
+        for p, pt in enumerate(pts):
+            k = pt["k"]
+            s = O.argon_slit(mu=pt["mu"], n_equil_sets=20, dr=pt["dr"])
+            for r in range(R):
+                c = p * R + r
+                e.set_system(s, c)
+                e.set_positions(c, g[f"x{k}"], g[f"y{k}"], g[f"z{k}"])
+        e.run(1, 20, 10000, seed=777)
+        stats = e.run(21, 80, 10000, seed=777, check_energy=1)
+        assert e.last_kernel_name() == "k2_chains"
+    chi2 = 0.0
+    rows = []
+    for p, pt in enumerate(pts):
+        st = stats[p * R:(p + 1) * R]
+        assert all(q.samples == 800000 for q in st)
+        assert all(abs(q.energy - q.energy_check) <= 1e-9 * max(1.0, abs(q.energy_check)) for q in st)
+        means = np.array([q.sum_n / q.samples for q in st])
+        m, sem = means.mean(), means.std(ddof=1) / np.sqrt(R)
+        sigma = float(np.hypot(sem, pt["sem"]))
+        zscore = (m - pt["mean_n"]) / sigma
+        rows.append((pt["k"], pt["mu"], m, sem, pt["mean_n"], pt["sem"], zscore))
+        chi2 += zscore ** 2
+    for r in rows:
+        print("k=%2d mu=%8.1f  GPU <N> = %8.3f +- %.3f   reference <N> = %8.3f +- %.3f   z = %+.2f" % r)
+    for r in rows:
+        assert abs(r[6]) <= 2.0, r
+    assert chi2 / len(rows) < 2.0
