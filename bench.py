@@ -262,6 +262,8 @@ class Job:
         self.eng = m.Engine(n_chains, cap, device=device)
         if speculation is not None:
             self.eng.use_speculation(speculation)
+        if getattr(args, "pool", None) is not None:
+            self.eng.use_pool(args.pool)
         self.cap = cap = self.eng.capacity
         self.n0 = np.zeros(n_chains, dtype=np.int32)
         hx = torch.zeros((n_chains, cap), dtype=torch.float64).pin_memory()
@@ -432,14 +434,19 @@ def k3_k1_records(m, torch, local):
                 trial = np.column_stack([rng.random(200) * sysd.width[0], rng.random(200) * sysd.width[1], 3.0 + rng.random(200) * (sysd.width[2] - 6.0)])
                 for i in range(20):
                     e.particle_energy(0, int(idx[i]), trial[i])
-                kms = []
+                e.timer_start()
                 t0 = time.perf_counter()
                 for i in range(200):
                     e.particle_energy(0, int(idx[i]), trial[i])
-                    kms.append(e.last_kernel_ms())
                 dt = time.perf_counter() - t0
-                out["k1"].append({"case": name, "n": n, "us_per_call_through_abi": 1e6 * dt / 200, "us_kernel": 1e3 * float(np.mean(kms)),
-                                  "pair_evals_per_call": 2 * n, "what": "mcpm_particle_energy: stored + displaced position in one launch, 64-byte read-back"})
+                dev_ms = e.timer_stop()
+                t0 = time.perf_counter()
+                e.particle_energy_batch(0, idx.astype(np.int32), trial)
+                dtb = time.perf_counter() - t0
+                out["k1"].append({"case": name, "n": n, "us_per_call_through_abi": 1e6 * dt / 200, "us_device_per_call": 1e3 * dev_ms / 200,
+                                  "us_per_request_in_a_batch_of_200": 1e6 * dtb / 200, "pair_evals_per_call": 2 * n,
+                                  "what": "mcpm_particle_energy: stored + displaced position in one launch (positions staged by TMA bulk copies, "
+                                          "results through mapped host memory); ctypes call overhead included"})
     return out
 
 
@@ -555,6 +562,7 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the short C1/C3/C4/C5 runs and the K3/K1 records")
     ap.add_argument("--no-literal", action="store_true", help="skip the literal 40-chain isotherm sub-record")
     ap.add_argument("--speculation", type=int, default=None, help="mcpm_use_speculation mode (experiments)")
+    ap.add_argument("--pool", type=int, default=None, help="mcpm_use_pool: 16 / 20 warps per persistent CTA, 0 = one CTA per chain (experiments)")
     args = ap.parse_args()
     if args.warmup < MIN_WARMUP:
         print(f"bench.py: --warmup {args.warmup} raised to {MIN_WARMUP} (timing rule: at least 3 warm-up steps; both arms)", file=sys.stderr)

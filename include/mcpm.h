@@ -37,8 +37,12 @@ enum {
     MCPM_ERR_IO = 5
 };
 
-enum { MCPM_GEOM_BULK = 0, MCPM_GEOM_SLIT = 1 };      /* Box::geometry, src/read.cpp:74, :146-162 */
-enum { MCPM_WALL_NONE = 0, MCPM_WALL_SLIT_LJ = 1 };   /* wall dispatch, src/energy.cpp:69-77      */
+/* Box::geometry, src/read.cpp:74; derived widths :128-135, PBC flags :146-162 (bulk xyz, slit xy, cylinder x, sphere none) */
+enum { MCPM_GEOM_BULK = 0, MCPM_GEOM_SLIT = 1, MCPM_GEOM_CYLINDER = 2, MCPM_GEOM_SPHERE = 3 };
+/* wall dispatch, src/energy.cpp:69-77: "lj" + slit -> SlitLJ_Pot, "lj" + sphere -> SphericalLJ_Pot (src/potentials.cpp:474-504) */
+enum { MCPM_WALL_NONE = 0, MCPM_WALL_SLIT_LJ = 1, MCPM_WALL_SPHERE_LJ = 2 };
+/* pair dispatch, src/energy.cpp:79-83: "lj" -> LJ126_Pot, "hs" -> HardSphere_Pot (src/potentials.cpp:40-54) */
+enum { MCPM_PAIR_LJ = 0, MCPM_PAIR_HS = 1 };
 enum { MCPM_RNG_PHILOX = 0, MCPM_RNG_REPLAY = 1 };
 
 typedef struct mcpm_ctx mcpm_ctx; /* opaque */
@@ -50,15 +54,18 @@ typedef struct mcpm_system_desc {
     int geometry;        /* MCPM_GEOM_*;  PBC flags follow the geometry as in src/read.cpp:146-162 */
     int wall_kind;       /* MCPM_WALL_*;  SLIT_LJ = SlitLJ_Pot, src/potentials.cpp:381-402 */
     int n_layers;        /* Box::nLayersPerWall */
-    int n_disp, n_vol, n_swap; /* move weights, src/main.cpp:67-70 (n_vol must be 0: volume moves out of scope) */
+    int n_disp, n_vol, n_swap; /* move weights, src/main.cpp:67-70; n_vol > 0 = NPT volume moves (MC::ChangeVolume, src/moves.cpp:191-231):
+                                  bulk geometry and pressure > 0 only (the two-box Gibbs branches are out of scope) */
     int n_equil_sets;    /* sets during which dr adapts and nothing is sampled, src/moves.cpp:74, src/main.cpp:72 */
-    int reserved;
+    int pair_kind;       /* MCPM_PAIR_*: fluid-fluid potential */
     double width[3];     /* Box::width, angstrom; width[2] is the pore size H */
     double temperature;  /* K */
     double eps_ff, sig_ff, rcut;    /* Fluid::{epsilon,sigma,rcut}(0), src/potentials.cpp:62-64 */
     double molar_mass, mu;          /* g/mol; full chemical potential mu/kB in K, src/moves.cpp:296-298 */
     double eps_sf, sig_sf, rho_s, delta; /* Box::fluid(0).{epsilon,sigma}(0), solidDens, deltaLayers, src/potentials.cpp:384-389 */
     double dr;           /* Simulation::dr, src/read.cpp:168 */
+    double pressure;     /* ExternalPressure in Pa (src/read.cpp:64); <= 0: none */
+    double dv;           /* Simulation::dv, amplitude of the log-volume step (src/MC.cpp:33); <= 0: the reference's 1e-3 */
 } mcpm_system_desc;
 
 /* Energies of one particle, as MC::EnergyOfParticle leaves them in the particle record
@@ -118,6 +125,12 @@ typedef struct mcpm_chain_stats {
      * n_swap == 0, in production sets; ResetStats restarts the counts at ONE and the sums at 0 every set) */
     double widom_insert, widom_delete;
     long long widom_insertions, widom_deletions;
+    /* NPT (n_vol > 0): MC::Stats volume counters of the last set (nVolChanges starts at ONE), box after the run */
+    long long accept_vol, reject_vol, n_vol_changes;
+    double volume, width;      /* Box::volume, Box::width(2) (== width(0) == width(1) after a volume move, src/moves.cpp:217-218) */
+    double dv;                 /* Simulation::dv after AdjustMCMoves (src/moves.cpp:79-84) */
+    double energy_as_shipped;  /* the reference's RUNNING box energy (half pair updates, CorrectEnergy's ratio test: quirks Q3, Q4, Q16), which
+                                  MC::ChangeVolume uses as the old energy (src/moves.cpp:220); tracked only when n_vol > 0 */
     double dr_used;            /* translation amplitude in effect DURING the last set (the reference prints its statistics
                                   before AdjustMCMoves changes it, src/main.cpp:77-83); `dr` above is the value after it */
 } mcpm_chain_stats;
@@ -150,9 +163,15 @@ int mcpm_get_positions_all(mcpm_ctx* ctx, int* n, double* x, double* y, double* 
  *                             (what MoveParticle evaluates, src/moves.cpp:153,165) -> cur and moved
  * index == -1, trial != NULL: energy of a ghost / inserted particle at trial[3]
  *                             (src/moves.cpp:304, :421)                          -> moved
- * Either output pointer may be NULL. One launch evaluates both positions in one pass over j. */
+ * Either output pointer may be NULL. One launch evaluates both positions in one pass over j; the results come back through
+ * mapped host memory (no device->host copy, no stream synchronisation per call). */
 int mcpm_particle_energy(mcpm_ctx* ctx, int chain, int index, const double* trial,
                          mcpm_particle_energy_t* cur, mcpm_particle_energy_t* moved);
+/* The same for `count` requests against the chain's PRESENT configuration in one launch (a host loop that speculates on several
+ * trial moves, Widom ghost batches, ...): index[count]; trial = NULL or [count][3]; cur / moved = NULL or [count].  The launch
+ * latency that bounds a single call is paid once per batch. */
+int mcpm_particle_energy_batch(mcpm_ctx* ctx, int chain, int count, const int* index, const double* trial,
+                               mcpm_particle_energy_t* cur, mcpm_particle_energy_t* moved);
 
 /* ---- K3: full box energy == MC::BoxEnergy (src/energy.cpp:106-124) ------------------------- *
  * per_pair / per_wall (nullable, n doubles each) receive every particle's pairPotE / boxE, as
@@ -182,6 +201,13 @@ int mcpm_get_stats(mcpm_ctx* ctx, mcpm_chain_stats* stats /* [n_chains] */);
  * 1.5 N pair evaluations per step at 20 % translation acceptance.  enable = 0 re-sums both energies every move, exactly
  * like MC::MoveParticle / MC::SwapParticle. */
 int mcpm_use_energy_cache(mcpm_ctx* ctx, int enable);
+/* OPT-IN alternative for one-warp chains (the choice when many chains share an SM): k2_pool, one persistent CTA per SM whose warps own
+ * shared-memory slots of up to three capacity classes and take chains from work queues, longest first; a chain that outgrows its slot
+ * pauses and is finished by a follow-up launch.  warps = 12 (168 registers per thread), 14, 16 (128) or 20 (96); 0 = off (default: the
+ * one-CTA-per-chain kernel k2_chains, whose shared memory is sized for the largest chain).  Same chains, same results.  Measured on
+ * B200 (round 2, profiles/r02_pool.md): equal to k2_chains at 12 warps, SLOWER at 16 — the claim loop around the chain loop costs the
+ * registers the scan's instruction-level parallelism needs — so it is not the default. */
+int mcpm_use_pool(mcpm_ctx* ctx, int warps);
 /* The cache itself, for drift checks: pair[j] = the pairPotE (K) the engine currently carries for particle j of `chain`
  * (what MC::EnergyOfParticle would store, src/energy.cpp:102-104); *valid = 0 if no K2 launch has left a consistent cache
  * for the chain's present configuration (then pair[] is not written).  Compare with mcpm_box_energy's per_pair. */

@@ -1,6 +1,7 @@
 // C-ABI implementation (include/mcpm.h): context, state transfer, launches.  No torch types, no CPU
 // fallback: every compute entry point needs a CUDA device and fails with MCPM_ERR_CUDA otherwise.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -53,6 +54,16 @@ struct mcpm_ctx {
     double* d_out = nullptr;       // K1: 8 doubles; K3: 4 per chain
     double *d_pp = nullptr, *d_pw = nullptr;  // K3 per-particle outputs, one chain's worth
     double* d_rdf = nullptr;       // [n_chains][MCPM_RDF_BINS]
+    // K1 (mcpm_k1.cu): request / result buffers, allocated on first use.  h_k1 is MAPPED pinned host memory: the kernel writes the
+    // result records and then a sequence flag straight into it, the host spins on the flag (no copy, no stream synchronisation).
+    K1Request* d_k1_reqs = nullptr;
+    K1Request* h_k1_reqs = nullptr;            // pinned staging of a batch's requests
+    double* d_k1_out = nullptr;
+    double* d_k1_scratch = nullptr;
+    unsigned int* d_k1_counters = nullptr;     // MCPM_K1_MAX_BATCH/4 group counters + 1 launch counter
+    double* h_k1 = nullptr;                    // [MCPM_K1_MAX_BATCH][8] records + the flag word
+    double* d_k1_alias = nullptr;              // device address of h_k1
+    unsigned long long k1_seq = 0;
     // cell-list K3 workspace, allocated on first use
     int *d_cell_of = nullptr, *d_cell_counts = nullptr, *d_cell_starts = nullptr, *d_orig = nullptr;
     double *d_sx = nullptr, *d_sy = nullptr, *d_sz = nullptr;
@@ -62,6 +73,9 @@ struct mcpm_ctx {
     int *d_kc_items = nullptr, *d_kc_cell_of = nullptr, *d_kc_slot_of = nullptr;   // K2c cell lists (mcpm_cells.cu)
     size_t kc_items_ints = 0;
     int use_dual = 0;              // opt-in: one-warp chains evaluate two candidate steps per round (mcpm_dual.cu); measured slower in round 1
+    int use_pool = 0;              // opt-in (mcpm_use_pool): one-warp chains through the persistent pooled kernel k2_pool; warps per CTA below
+    int pool_warps = 12;
+    int* d_pool_next = nullptr;    // k2_pool queue counters
     int use_spec = -1;             // speculative-moves kernel (mcpm_spec.cu): -1 = automatic (fewer chains than SMs), 0 = never, 1 = whenever possible
     int use_subwarp = 0;           // opt-in: the sub-warp kernel that packs 2 or 4 small chains into one warp (mcpm_use_subwarp)
     int2* d_ctas = nullptr;        // CTA descriptors of the sub-warp kernel, n_chains entries
@@ -84,11 +98,27 @@ struct mcpm_ctx {
 // Tools::Pow, reference src/tools.h:53-58 (repeated multiply starting from 1.)
 static double ipow(double v, int p) { double r = 1.; for (int i = 1; i <= p; i++) r *= v; return r; }
 
+// MC::ComputeVolume, src/read.cpp:26-35
+static double box_volume(const mcpm_system_desc& d) {
+    if (d.geometry == MCPM_GEOM_SPHERE) return (M_PI / 6.) * ipow(d.width[2], 3);
+    if (d.geometry == MCPM_GEOM_CYLINDER) return (M_PI / 4.) * ipow(d.width[2], 2) * d.width[0];
+    if (d.geometry == MCPM_GEOM_SLIT) return d.width[0] * d.width[1] * d.width[2];
+    return ipow(d.width[2], 3);
+}
+
 static int digest(const mcpm_system_desc& d, ChainParams& P) {
-    if (d.geometry != MCPM_GEOM_BULK && d.geometry != MCPM_GEOM_SLIT) return fail(MCPM_ERR_UNSUPPORTED, "geometry %d not supported (bulk and slit only)", d.geometry);
-    if (d.wall_kind != MCPM_WALL_NONE && d.wall_kind != MCPM_WALL_SLIT_LJ) return fail(MCPM_ERR_UNSUPPORTED, "wall_kind %d not supported", d.wall_kind);
-    if (d.n_vol != 0) return fail(MCPM_ERR_UNSUPPORTED, "volume moves (n_vol=%d) are out of scope", d.n_vol);
-    if (d.n_disp < 0 || d.n_swap < 0 || d.n_disp + d.n_swap <= 0) return fail(MCPM_ERR_ARG, "move weights must be non-negative and not all zero");
+    if (d.geometry < MCPM_GEOM_BULK || d.geometry > MCPM_GEOM_SPHERE) return fail(MCPM_ERR_UNSUPPORTED, "geometry %d not supported", d.geometry);
+    if (d.wall_kind != MCPM_WALL_NONE && d.wall_kind != MCPM_WALL_SLIT_LJ && d.wall_kind != MCPM_WALL_SPHERE_LJ)
+        return fail(MCPM_ERR_UNSUPPORTED, "wall_kind %d not supported (the cylindrical 10-4 / 10-4-3 walls need 2F1 and are out of scope)", d.wall_kind);
+    if (d.pair_kind != MCPM_PAIR_LJ && d.pair_kind != MCPM_PAIR_HS) return fail(MCPM_ERR_UNSUPPORTED, "pair_kind %d not supported (EAM potentials are out of scope)", d.pair_kind);
+    if (d.n_vol < 0) return fail(MCPM_ERR_ARG, "move weights must be non-negative");
+    if (d.n_vol > 0) {   // MC::ChangeVolume: the NPT branch of a single bulk box (src/moves.cpp:198-231); its other branches need two boxes
+        if (!(d.pressure > 0)) return fail(MCPM_ERR_UNSUPPORTED, "volume moves without an external pressure are the two-box Gibbs ensemble: out of scope");
+        if (d.geometry != MCPM_GEOM_BULK) return fail(MCPM_ERR_UNSUPPORTED, "volume moves are supported for the bulk geometry only");
+        if (d.n_swap != 0) return fail(MCPM_ERR_UNSUPPORTED, "volume moves together with swap moves are not supported");
+        if (!(d.width[0] == d.width[2] && d.width[1] == d.width[2])) return fail(MCPM_ERR_ARG, "a bulk box is cubic (src/read.cpp:135)");
+    }
+    if (d.n_disp < 0 || d.n_swap < 0 || d.n_disp + d.n_swap + d.n_vol <= 0) return fail(MCPM_ERR_ARG, "move weights must be non-negative and not all zero");
     if (!(d.width[0] > 0 && d.width[1] > 0 && d.width[2] > 0) || !(d.temperature > 0)) return fail(MCPM_ERR_ARG, "widths and temperature must be positive");
     if (d.n_layers < 0) return fail(MCPM_ERR_ARG, "n_layers must be >= 0");
     for (int k = 0; k < 3; k++) { P.L[k] = d.width[k]; P.invL[k] = 1.0 / d.width[k]; }
@@ -96,10 +126,9 @@ static int digest(const mcpm_system_desc& d, ChainParams& P) {
     P.sqr_pore_r = d.width[2] * d.width[2] * 0.25;               // src/energy.cpp:53
     P.T = d.temperature;
     P.sig2 = d.sig_ff * d.sig_ff;
-    P.eps4 = 4. * d.eps_ff;
+    P.eps4 = d.pair_kind == MCPM_PAIR_HS ? 1.0 : 4. * d.eps_ff;  // hard-sphere sums are energies already (INT_MAX per overlap)
     P.rc2 = d.rcut * d.rcut;
-    // MC::ComputeVolume, src/read.cpp:26-35
-    const double volume = d.geometry == MCPM_GEOM_SLIT ? d.width[0] * d.width[1] * d.width[2] : ipow(d.width[2], 3);
+    const double volume = box_volume(d);
     // activity, src/moves.cpp:296-298 (constants src/MC.h:16-18)
     const double kb = 1.380649e-23, na = 6.02214076e23, planck = 6.62607015e-34;
     const double particleMass = d.molar_mass / na * 1e-3;
@@ -116,8 +145,16 @@ static int digest(const mcpm_system_desc& d, ChainParams& P) {
     P.wall_pref = 4. * M_PI * d.eps_sf * d.rho_s * d.sig_sf * d.sig_sf;  // src/potentials.cpp:400
     P.sig_sf = d.sig_sf; P.delta = d.delta;
     P.geometry = d.geometry; P.wall_kind = d.wall_kind; P.n_layers = d.n_layers;
-    P.pbc[0] = 1; P.pbc[1] = 1; P.pbc[2] = d.geometry == MCPM_GEOM_SLIT ? 0 : 1;  // src/read.cpp:146-162
+    // PBC flags follow the geometry, src/read.cpp:146-162: bulk xyz, slit xy, cylinder x, sphere none
+    P.pbc[0] = d.geometry != MCPM_GEOM_SPHERE;
+    P.pbc[1] = d.geometry == MCPM_GEOM_BULK || d.geometry == MCPM_GEOM_SLIT;
+    P.pbc[2] = d.geometry == MCPM_GEOM_BULK;
     P.n_disp = d.n_disp; P.n_vol = d.n_vol; P.n_swap = d.n_swap; P.n_equil = d.n_equil_sets;
+    P.pair_kind = d.pair_kind;
+    P.sig_ff = d.sig_ff; P.eps_sf = d.eps_sf; P.rho_s = d.rho_s;
+    P.press_k = d.pressure > 0 ? d.pressure / kb * 1e-30 : 0.0;   // src/moves.cpp:198
+    // everything beyond "Lennard-Jones fluid, bulk or slit with the layered 10-4 wall, fixed volume" runs through the general kernels
+    P.exotic = (d.geometry == MCPM_GEOM_CYLINDER || d.geometry == MCPM_GEOM_SPHERE || d.wall_kind == MCPM_WALL_SPHERE_LJ || d.pair_kind == MCPM_PAIR_HS || d.n_vol > 0) ? 1 : 0;
     return MCPM_OK;
 }
 
@@ -127,6 +164,7 @@ static int check_chain(const mcpm_ctx* c, int chain) {
     return MCPM_OK;
 }
 static bool in_box(const ChainParams& P, int n, const double* x, const double* y, const double* z) {
+    if (P.exotic) return false;   // exotic systems always take the general kernels
     const double* a[3] = {x, y, z};
     for (int k = 0; k < 3; k++) {
         if (!P.pbc[k]) continue;
@@ -215,6 +253,10 @@ int mcpm_destroy(mcpm_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_params); cudaFree(c->d_state); cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_z);
+    cudaFree(c->d_pool_next);
+    cudaFree(c->d_k1_reqs); cudaFree(c->d_k1_out); cudaFree(c->d_k1_scratch); cudaFree(c->d_k1_counters);
+    if (c->h_k1_reqs) cudaFreeHost(c->h_k1_reqs);
+    if (c->h_k1) cudaFreeHost(c->h_k1);
     cudaFree(c->d_order); cudaFree(c->d_scratch); cudaFree(c->d_counters); cudaFree(c->d_out);
     cudaFree(c->d_pp); cudaFree(c->d_pw); cudaFree(c->d_rdf); cudaFree(c->d_ep); cudaFree(c->d_kc_items); cudaFree(c->d_kc_cell_of); cudaFree(c->d_kc_slot_of); cudaFree(c->d_ctas); cudaFree(c->d_flags);
     if (c->h_flags) cudaFreeHost(c->h_flags);
@@ -241,7 +283,8 @@ int mcpm_n_chains(const mcpm_ctx* c, int* n_chains, int* capacity) {
 static bool same_energetics(const ChainParams& a, const ChainParams& b) {
     for (int k = 0; k < 3; k++) if (a.L[k] != b.L[k] || a.pbc[k] != b.pbc[k]) return false;
     return a.sig2 == b.sig2 && a.eps4 == b.eps4 && a.rc2 == b.rc2 && a.wall_pref == b.wall_pref && a.sig_sf == b.sig_sf && a.delta == b.delta &&
-           a.geometry == b.geometry && a.wall_kind == b.wall_kind && a.n_layers == b.n_layers;
+           a.geometry == b.geometry && a.wall_kind == b.wall_kind && a.n_layers == b.n_layers && a.pair_kind == b.pair_kind &&
+           a.sig_ff == b.sig_ff && a.eps_sf == b.eps_sf && a.rho_s == b.rho_s && a.exotic == b.exotic;
 }
 
 // fast_image of every chain from the positions on the device (all coordinates on periodic axes inside [0, L]).
@@ -279,7 +322,11 @@ int mcpm_set_system(mcpm_ctx* c, int chain, const mcpm_system_desc* desc) {
         }
         // dr: taken from the description the first time and whenever the description's own dr changes; an unchanged
         // desc->dr keeps the amplitude the chain has adapted to (AdjustMCMoves), e.g. across mu updates of a sweep.
+        if (P.exotic) S.fast_image = 0;                       // general kernels only
+        else if (c->has_system[k] && c->h_params[k].exotic && S.st.n > 0) recheck = true;
         if (!c->has_system[k] || c->h_desc[k].dr != desc->dr) S.st.dr = desc->dr;
+        if (!c->has_system[k] || c->h_desc[k].dv != desc->dv) S.st.dv = desc->dv > 0 ? desc->dv : 1e-3;     // Simulation::dv, src/MC.cpp:33
+        if (P.n_vol > 0 && (!c->has_system[k] || !same_energetics(c->h_params[k], P))) S.b_valid = 0;
         c->h_params[k] = P; c->h_desc[k] = *desc; c->has_system[k] = 1;
     }
     CU(cudaMemcpyAsync(c->d_params + lo, c->h_params.data() + lo, sizeof(ChainParams) * (hi - lo), cudaMemcpyHostToDevice, c->stream));
@@ -388,6 +435,64 @@ int mcpm_get_positions_all(mcpm_ctx* c, int* n, double* x, double* y, double* z)
 }
 
 // ---- K1 ---------------------------------------------------------------------------------------
+static int k1_prepare(mcpm_ctx* c) {
+    if (c->h_k1) return MCPM_OK;
+    const size_t groups = MCPM_K1_MAX_BATCH / 4 + 1;
+    CU(cudaMalloc(&c->d_k1_reqs, sizeof(K1Request) * MCPM_K1_MAX_BATCH));
+    CU(cudaMallocHost(&c->h_k1_reqs, sizeof(K1Request) * MCPM_K1_MAX_BATCH));
+    CU(cudaMalloc(&c->d_k1_out, sizeof(double) * 8 * MCPM_K1_MAX_BATCH));
+    CU(cudaMalloc(&c->d_k1_scratch, sizeof(double) * 8 * (MCPM_K1_MAX_BATCH / 4) * (size_t)k1_slices(c->cap)));
+    CU(cudaMalloc(&c->d_k1_counters, sizeof(unsigned int) * groups));
+    CU(cudaMemsetAsync(c->d_k1_counters, 0, sizeof(unsigned int) * groups, c->stream));
+    CU(cudaHostAlloc(&c->h_k1, sizeof(double) * (8 * MCPM_K1_MAX_BATCH + 2), cudaHostAllocMapped));
+    memset(c->h_k1, 0, sizeof(double) * (8 * MCPM_K1_MAX_BATCH + 2));
+    CU(cudaHostGetDevicePointer((void**)&c->d_k1_alias, c->h_k1, 0));
+    CU(cudaStreamSynchronize(c->stream));
+    return MCPM_OK;
+}
+
+// `count` requests (<= MCPM_K1_MAX_BATCH) in ONE launch; results are waited for on the mapped flag.
+static int k1_launch(mcpm_ctx* c, int chain, int count, const K1Request* host_reqs, bool fast) {
+    int rc = k1_prepare(c); if (rc) return rc;
+    const int n = c->h_state[chain].st.n;
+    const K1Request* dev_reqs = nullptr;
+    if (count > 1) {
+        memcpy(c->h_k1_reqs, host_reqs, sizeof(K1Request) * count);
+        CU(cudaMemcpyAsync(c->d_k1_reqs, c->h_k1_reqs, sizeof(K1Request) * count, cudaMemcpyHostToDevice, c->stream));
+        dev_reqs = c->d_k1_reqs;
+    }
+    const unsigned long long seq = ++c->k1_seq;
+    volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(c->h_k1 + 8 * MCPM_K1_MAX_BATCH);
+    CU(launch_k1(fast, n, count, c->d_params, c->d_state, c->d_x, c->d_y, c->d_z, chain, c->cap, dev_reqs, host_reqs[0], c->d_k1_scratch,
+                 c->d_k1_counters, c->d_k1_out, c->d_k1_alias, reinterpret_cast<unsigned long long*>(c->d_k1_alias + 8 * MCPM_K1_MAX_BATCH), seq,
+                 c->d_k1_counters + MCPM_K1_MAX_BATCH / 4, c->stream));
+    c->launches++;
+    // spin on the flag the kernel raises after its records are in host memory; look at the stream now and then so that a failed
+    // launch is reported instead of waited for
+    for (unsigned long long spins = 1; *flag != seq; spins++) {
+        if ((spins & 0x3fffull) == 0) {
+            cudaError_t q = cudaStreamQuery(c->stream);
+            if (q == cudaSuccess) break;                       // finished: the flag write has landed by now (checked below)
+            if (q != cudaErrorNotReady) return fail(MCPM_ERR_CUDA, "K1 launch failed: %s", cudaGetErrorString(q));
+        }
+    }
+    if (*flag != seq) {
+        CU(cudaStreamSynchronize(c->stream));
+        if (*flag != seq) return fail(MCPM_ERR_CUDA, "K1 finished without delivering its results");
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return MCPM_OK;
+}
+
+static bool trial_in_box(const ChainParams& P, const double* t) {
+    for (int k = 0; k < 3; k++) if (P.pbc[k] && !(t[k] >= 0.0 && t[k] <= P.L[k])) return false;
+    return true;
+}
+static void k1_record(const double* r, mcpm_particle_energy_t* cur, mcpm_particle_energy_t* moved) {
+    if (cur) { cur->pair = r[0]; cur->many_body = 0.0; cur->wall = r[2]; cur->energy = r[3]; }
+    if (moved) { moved->pair = r[4]; moved->many_body = 0.0; moved->wall = r[6]; moved->energy = r[7]; }
+}
+
 int mcpm_particle_energy(mcpm_ctx* c, int chain, int index, const double* trial, mcpm_particle_energy_t* cur,
                          mcpm_particle_energy_t* moved) {
     int rc = check_chain(c, chain); if (rc) return rc;
@@ -396,22 +501,39 @@ int mcpm_particle_energy(mcpm_ctx* c, int chain, int index, const double* trial,
     if (index < -1 || index >= std::max(n, 1)) return fail(MCPM_ERR_ARG, "index %d out of range (n=%d)", index, n);
     if (index == -1 && !trial) return fail(MCPM_ERR_ARG, "index -1 needs a trial position");
     CU(cudaSetDevice(c->device));
+    K1Request rq;
+    rq.index = index; rq.has_trial = trial ? 1 : 0;
+    for (int k = 0; k < 3; k++) rq.t[k] = trial ? trial[k] : 0.0;
+    // the trial position must satisfy the fast-image precondition too
+    const bool fast = c->h_state[chain].fast_image != 0 && (!trial || trial_in_box(c->h_params[chain], trial));
+    rc = k1_launch(c, chain, 1, &rq, fast); if (rc) return rc;
+    k1_record(c->h_k1, cur, moved);
+    return MCPM_OK;
+}
+
+int mcpm_particle_energy_batch(mcpm_ctx* c, int chain, int count, const int* index, const double* trial, mcpm_particle_energy_t* cur,
+                               mcpm_particle_energy_t* moved) {
+    int rc = check_chain(c, chain); if (rc) return rc;
+    if (!c->has_system[chain]) return fail(MCPM_ERR_ARG, "set the system of chain %d first", chain);
+    if (count < 0 || (count > 0 && !index)) return fail(MCPM_ERR_ARG, "bad request list");
+    const int n = c->h_state[chain].st.n;
     bool fast = c->h_state[chain].fast_image != 0;
-    if (trial) {  // the trial position must satisfy the fast-image precondition too
-        const ChainParams& P = c->h_params[chain];
-        for (int k = 0; k < 3; k++) if (P.pbc[k] && !(trial[k] >= 0.0 && trial[k] <= P.L[k])) fast = false;
+    for (int r = 0; r < count; r++) {
+        if (index[r] < -1 || index[r] >= std::max(n, 1)) return fail(MCPM_ERR_ARG, "request %d: index %d out of range (n=%d)", r, index[r], n);
+        if (index[r] == -1 && !trial) return fail(MCPM_ERR_ARG, "request %d: index -1 needs a trial position", r);
+        if (trial && !trial_in_box(c->h_params[chain], trial + 3 * r)) fast = false;
     }
-    const int blocks = std::max(1, std::min((n + 1023) / 1024, 2 * c->num_sms));
-    CU(cudaEventRecord(c->ev0, c->stream));
-    CU(launch_k1(fast, blocks, c->d_params, c->d_state, c->d_x, c->d_y, c->d_z, chain, c->cap, index, trial ? 1 : 0, trial,
-                 c->d_scratch, c->d_counters + c->n_chains, c->d_out, c->stream));
-    CU(cudaEventRecord(c->ev1, c->stream));
-    c->launches++;
-    CU(cudaMemcpyAsync(c->h_pin, c->d_out, sizeof(double) * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    CU(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
-    if (cur) { cur->pair = c->h_pin[0]; cur->many_body = 0.0; cur->wall = c->h_pin[2]; cur->energy = c->h_pin[3]; }
-    if (moved) { moved->pair = c->h_pin[4]; moved->many_body = 0.0; moved->wall = c->h_pin[6]; moved->energy = c->h_pin[7]; }
+    CU(cudaSetDevice(c->device));
+    std::vector<K1Request> rq(std::min(count, MCPM_K1_MAX_BATCH));
+    for (int r0 = 0; r0 < count; r0 += MCPM_K1_MAX_BATCH) {
+        const int m = std::min(MCPM_K1_MAX_BATCH, count - r0);
+        for (int r = 0; r < m; r++) {
+            rq[r].index = index[r0 + r]; rq[r].has_trial = trial ? 1 : 0;
+            for (int k = 0; k < 3; k++) rq[r].t[k] = trial ? trial[3 * (r0 + r) + k] : 0.0;
+        }
+        rc = k1_launch(c, chain, m, rq.data(), fast); if (rc) return rc;
+        for (int r = 0; r < m; r++) k1_record(c->h_k1 + 8 * r, cur ? cur + r0 + r : nullptr, moved ? moved + r0 + r : nullptr);
+    }
     return MCPM_OK;
 }
 
@@ -557,6 +679,73 @@ static int pick_threads(const mcpm_ctx* c, int maxn) {
     return t;
 }
 
+// ---- k2_pool: capacity classes, slot mix and queues ---------------------------------------------------------------------
+// Slot a chain of n particles needs for one launch: headroom for the fluctuations of N (a chain that still outgrows it pauses and
+// is finished in a full-size slot).
+static int pool_need(int n, int cap) { return std::min(cap, ((int)(n * 1.15) + 48 + 31) & ~31); }
+
+// Builds the layout for the chains listed in `chains` (all of them get slots of the full capacity if `full`), reorders them by
+// (class, loading descending) into `order`, and returns the dynamic shared-memory size (0: does not fit).
+static size_t pool_layout(const mcpm_ctx* c, const std::vector<int>& chains, bool full, int max_warps, PoolLayout& L, std::vector<int>& order, int& n_ctas) {
+    memset(&L, 0, sizeof(L));
+    const int cap = c->cap;
+    int top = 32;
+    for (int k : chains) top = std::max(top, full ? cap : pool_need(c->h_state[k].st.n, cap));
+    // geometric classes: top, top/2, top/4 (multiples of 32); a chain joins the smallest class that holds its need
+    int ccap[MCPM_POOL_MAX_CLASSES] = {top, std::max(32, ((top / 2) + 31) & ~31), std::max(32, ((top / 4) + 31) & ~31)};
+    std::vector<int> members[MCPM_POOL_MAX_CLASSES];
+    double work[MCPM_POOL_MAX_CLASSES] = {0., 0., 0.};
+    for (int k : chains) {
+        const int n = c->h_state[k].st.n, need = full ? cap : pool_need(n, cap);
+        int cls = 0;
+        for (int q = MCPM_POOL_MAX_CLASSES - 1; q > 0; q--) if (need <= ccap[q] && ccap[q] < ccap[q - 1]) { cls = q; break; }
+        members[cls].push_back(k);
+        work[cls] += 1400.0 + 6.0 * n;          // cycles per step: fixed latency + scan (profiles/r01_k2_step_phases.md)
+    }
+    // drop empty classes (keep the order large -> small)
+    int ncls = 0;
+    int keep_cap[MCPM_POOL_MAX_CLASSES]; double keep_work[MCPM_POOL_MAX_CLASSES]; std::vector<int> keep_members[MCPM_POOL_MAX_CLASSES];
+    for (int q = 0; q < MCPM_POOL_MAX_CLASSES; q++) if (!members[q].empty()) { keep_cap[ncls] = ccap[q]; keep_work[ncls] = work[q]; keep_members[ncls] = members[q]; ncls++; }
+    if (ncls == 0) return 0;
+    const int n_chains = (int)chains.size();
+    int slots = std::max(1, std::min(max_warps, (n_chains + c->num_sms - 1) / c->num_sms));
+    const size_t stride = pool_state_stride_doubles();
+    auto slot_doubles = [](int cp) { return (size_t)3 * cp + 64; };
+    int per[MCPM_POOL_MAX_CLASSES];
+    for (;; slots--) {
+        if (slots < 1) return 0;
+        if (slots < ncls) {                        // fewer warps than classes: one class of the largest capacity
+            for (int q = 1; q < ncls; q++) { keep_members[0].insert(keep_members[0].end(), keep_members[q].begin(), keep_members[q].end()); keep_work[0] += keep_work[q]; }
+            ncls = 1;
+        }
+        double tot = 0.; for (int q = 0; q < ncls; q++) tot += keep_work[q];
+        int used = 0;
+        for (int q = 0; q < ncls; q++) { per[q] = std::max(1, (int)(slots * keep_work[q] / tot)); used += per[q]; }
+        for (int q = 0; used < slots; q = (q + 1) % ncls) { per[q]++; used++; }          // leftovers to the larger classes first
+        for (int q = ncls - 1; used > slots; q = (q + ncls - 1) % ncls) if (per[q] > 1) { per[q]--; used--; }
+        size_t doubles = (size_t)slots * stride;
+        for (int q = 0; q < ncls; q++) doubles += per[q] * slot_doubles(keep_cap[q]);
+        if (doubles * sizeof(double) + 64 + sizeof(RunArgs) + 16 <= (size_t)c->max_smem) break;
+    }
+    L.n_slots = slots; L.n_classes = ncls;
+    size_t off = 0;
+    int w = 0;
+    for (int q = 0; q < ncls; q++)
+        for (int k = 0; k < per[q]; k++, w++) { L.slot_cap[w] = keep_cap[q]; L.slot_off[w] = (int)off; L.slot_cls[w] = q; off += slot_doubles(keep_cap[q]); }
+    off = (off + 1) & ~(size_t)1;                  // 16-byte alignment of the record area
+    L.state_off = (int)off; L.state_stride = (int)stride;
+    L.args_off = (int)(off + (size_t)slots * stride);
+    order.clear();
+    for (int q = 0; q < ncls; q++) {
+        std::stable_sort(keep_members[q].begin(), keep_members[q].end(), [&](int a, int b) { return c->h_state[a].st.n > c->h_state[b].st.n; });
+        L.q_begin[q] = (int)order.size();
+        order.insert(order.end(), keep_members[q].begin(), keep_members[q].end());
+        L.q_end[q] = (int)order.size();
+    }
+    n_ctas = std::min(c->num_sms, (n_chains + slots - 1) / slots);
+    return (off + (size_t)slots * stride) * sizeof(double) + ((sizeof(RunArgs) + 15) / 16) * 16;
+}
+
 int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     if (!c || !p) return fail(MCPM_ERR_ARG, "null argument");
     if (p->n_sets < 0 || p->steps_per_set < 0 || p->steps_per_set > 2000000000LL) return fail(MCPM_ERR_ARG, "set count must be >= 0 and steps_per_set in [0, 2e9]");
@@ -573,7 +762,7 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     const bool global_path = (size_t)c->cap > k2_smem_limit_cap(c->max_smem);   // positions stay in global memory / L2
     if (threads == 0) threads = global_path ? 512 : pick_threads(c, maxn);
     bool all_fast = true;
-    for (int k = 0; k < c->n_chains; k++) all_fast = all_fast && c->h_state[k].fast_image;
+    for (int k = 0; k < c->n_chains; k++) all_fast = all_fast && c->h_state[k].fast_image && !c->h_params[k].exotic;
     bool sample = p->sample_rdf != 0;                       // in-kernel sampling: RDF on request, Widom whenever n_swap == 0
     for (int k = 0; k < c->n_chains; k++) sample = sample || c->h_params[k].n_swap == 0;
     if (p->no_sampling) sample = false;                     // moves only (MC::MinimizeEnergy): the hot kernels apply
@@ -593,7 +782,7 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     RunArgs a;
     memset(&a, 0, sizeof(a));
     a.first_set = p->first_set; a.n_sets = p->n_sets; a.steps_per_set = p->steps_per_set; a.seed = p->seed;
-    a.check_energy = p->check_energy; a.cap = c->cap;
+    a.check_energy = p->check_energy; a.cap = c->cap; a.pool_threads = 32;
     a.sample_rdf = p->no_sampling ? 0 : p->sample_rdf; a.rdf = c->d_rdf; a.no_sampling = p->no_sampling ? 1 : 0;
     // The energy cache pays while accepted translations (each costs a second pass over the partners) are the minority:
     // N + 2pN < 2N for p < 0.5.  Decide from the acceptance of the last set; the reference's dr adaptation aims at 0.2.
@@ -695,8 +884,33 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
 #else
     const bool use_dual = false;
 #endif
-    c->last_kernel = use_k2c ? "k2_cells" : use_pair ? (lean_width == 4 ? "k2_quad" : "k2_pair") : use_spec ? "k2_spec" : (use_sub ? "k2_sub" : (use_dual ? "k2_dual" : "k2_chains"));
-    if (use_k2c) {
+    // One warp per chain on the energy cache: the persistent pooled kernel (shared-memory slots per capacity class, work queues).
+    const bool use_pool = c->use_pool && !use_k2c && !use_pair && !use_spec && !use_sub && !use_dual && threads == 32 && cache_now && all_fast && !sample && !global_path && same_pbz;
+    c->last_kernel = use_pool ? "k2_pool" : use_k2c ? "k2_cells" : use_pair ? (lean_width == 4 ? "k2_quad" : "k2_pair") : use_spec ? "k2_spec" : (use_sub ? "k2_sub" : (use_dual ? "k2_dual" : "k2_chains"));
+    if (use_pool) {
+        if (!c->d_pool_next) CU(cudaMalloc(&c->d_pool_next, sizeof(int) * MCPM_POOL_MAX_CLASSES));
+        for (int k = 0; k < c->n_chains; k++) c->h_state[k].res.paused = 0;
+        CU(cudaMemcpyAsync(c->d_state, c->h_state.data(), sizeof(ChainState) * c->n_chains, cudaMemcpyHostToDevice, c->stream));
+        std::vector<int> todo(c->n_chains);
+        std::iota(todo.begin(), todo.end(), 0);
+        for (int round = 0; !todo.empty(); round++) {
+            if (round > 8) return fail(MCPM_ERR_CUDA, "k2_pool: chains still paused after %d launches", round);
+            PoolLayout L;
+            std::vector<int> pool_order;
+            int n_ctas = 0;
+            const size_t smem = pool_layout(c, todo, round > 0, c->pool_warps, L, pool_order, n_ctas);
+            if (smem == 0) return fail(MCPM_ERR_CAPACITY, "k2_pool: a chain of capacity %d does not fit one SM's shared memory", c->cap);
+            L.q_next = c->d_pool_next;
+            CU(cudaMemsetAsync(c->d_pool_next, 0, sizeof(int) * MCPM_POOL_MAX_CLASSES, c->stream));
+            CU(cudaMemcpyAsync(c->d_order, pool_order.data(), sizeof(int) * pool_order.size(), cudaMemcpyHostToDevice, c->stream));
+            CU(launch_k2_pool(p->rng_mode, c->h_params[0].pbc[2] != 0, c->pool_warps, n_ctas, smem, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, L, c->stream));
+            c->launches++;
+            if (round == 0) CU(cudaEventRecord(c->ev1, c->stream));      // (follow-up launches for paused chains are rare and short)
+            int rc1 = pull_states(c); if (rc1) return rc1;
+            todo.clear();
+            for (int k = 0; k < c->n_chains; k++) if (c->h_state[k].res.paused) todo.push_back(k);
+        }
+    } else if (use_k2c) {
         bool widom = false;
         for (int k = 0; k < c->n_chains; k++) widom = widom || (c->h_params[k].n_swap == 0 && !p->no_sampling);
         CU(launch_k2_cells(p->rng_mode, widom, c->n_chains, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->d_kc_items,
@@ -753,7 +967,7 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
         CU(launch_k2(p->rng_mode, c->n_chains, threads, all_fast, sample, cache_now, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->max_smem, c->stream));
         c->launches++;
     }
-    CU(cudaEventRecord(c->ev1, c->stream));
+    if (!use_pool) CU(cudaEventRecord(c->ev1, c->stream));
     if (p->trace) CU(cudaMemcpyAsync(p->trace, c->d_trace, (size_t)c->n_chains * nsteps, cudaMemcpyDeviceToHost, c->stream));
     int rc = pull_states(c); if (rc) return rc;
     for (int k = 0; k < c->n_chains; k++) c->cache_fresh[k] = (a.ep != nullptr && c->h_state[k].cache_valid) ? 1 : 0;
@@ -770,6 +984,21 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
             if (p->check_energy != 2)
                 for (int k = 0; k < c->n_chains; k++) { c->h_state[k].st.pair = run[3 * k]; c->h_state[k].st.wall = run[3 * k + 1]; c->h_state[k].st.energy = run[3 * k + 2]; }
             CU(cudaMemcpyAsync(c->d_state, c->h_state.data(), sizeof(ChainState) * c->n_chains, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+        }
+    }
+    {   // NPT: the box a chain ended with becomes its system (widths, volume-dependent constants) for K1 / K3 and the next launch
+        bool any = false;
+        for (int k = 0; k < c->n_chains; k++) {
+            if (c->h_params[k].n_vol <= 0 || !(c->h_state[k].st.width > 0) || c->h_state[k].st.width == c->h_desc[k].width[2]) continue;
+            mcpm_system_desc d = c->h_desc[k];
+            d.width[0] = d.width[1] = d.width[2] = c->h_state[k].st.width;
+            ChainParams P;
+            memset(&P, 0, sizeof(P));
+            if (digest(d, P) == MCPM_OK) { c->h_desc[k] = d; c->h_params[k] = P; any = true; }
+        }
+        if (any) {
+            CU(cudaMemcpyAsync(c->d_params, c->h_params.data(), sizeof(ChainParams) * c->n_chains, cudaMemcpyHostToDevice, c->stream));
             CU(cudaStreamSynchronize(c->stream));
         }
     }
@@ -823,7 +1052,7 @@ int mcpm_chemical_potential(mcpm_ctx* c, int chain, double* mu_ex, double* mu) {
     const double kb = 1.380649e-23, na = 6.02214076e23, planck = 6.62607015e-34;
     const double particleMass = d.molar_mass / na * 1e-3;
     const double thermalWL = planck / sqrt(2.0 * M_PI * particleMass * kb * d.temperature) * 1e10;
-    const double volume = d.geometry == MCPM_GEOM_SLIT ? d.width[0] * d.width[1] * d.width[2] : ipow(d.width[2], 3);
+    const double volume = box_volume(d);
     const double widomParam = (st.widom_insert / st.widom_insertions) / (st.widom_delete / st.widom_deletions);
     const double muIdeal = d.temperature * log(ipow(thermalWL, 3) * (st.n + 1) / volume);
     const double muExcess = -d.temperature * log(widomParam);
@@ -867,6 +1096,14 @@ int mcpm_use_subwarp(mcpm_ctx* c, int enable) {
     return MCPM_OK;
 }
 #endif
+
+int mcpm_use_pool(mcpm_ctx* c, int warps) {
+    if (!c) return fail(MCPM_ERR_ARG, "null context");
+    if (warps != 0 && warps != 12 && warps != 14 && warps != 16 && warps != 20) return fail(MCPM_ERR_ARG, "k2_pool runs 12, 16 or 20 warps per CTA (0: the one-CTA-per-chain kernel)");
+    c->use_pool = warps ? 1 : 0;
+    if (warps) c->pool_warps = warps;
+    return MCPM_OK;
+}
 
 int mcpm_use_energy_cache(mcpm_ctx* c, int enable) {
     if (!c) return fail(MCPM_ERR_ARG, "null context");

@@ -28,15 +28,15 @@ __device__ __forceinline__ void pair_sum2(const double* xs, const double* ys, co
     for (; j + T < n; j += 2 * T) {
         const double x0 = xs[j], y0 = ys[j], z0 = zs[j];
         const double x1 = xs[j + T], y1 = ys[j + T], z1 = zs[j + T];
-        pair_acc(a0, dist2<FAST, PBZ>(g, xa, ya, za, x0, y0, z0), g, j, self);
-        pair_acc(b0, dist2<FAST, PBZ>(g, xb, yb, zb, x0, y0, z0), g, j, self);
-        pair_acc(a1, dist2<FAST, PBZ>(g, xa, ya, za, x1, y1, z1), g, j + T, self);
-        pair_acc(b1, dist2<FAST, PBZ>(g, xb, yb, zb, x1, y1, z1), g, j + T, self);
+        pair_add<FAST>(a0, dist2<FAST, PBZ>(g, xa, ya, za, x0, y0, z0), g, j, self);
+        pair_add<FAST>(b0, dist2<FAST, PBZ>(g, xb, yb, zb, x0, y0, z0), g, j, self);
+        pair_add<FAST>(a1, dist2<FAST, PBZ>(g, xa, ya, za, x1, y1, z1), g, j + T, self);
+        pair_add<FAST>(b1, dist2<FAST, PBZ>(g, xb, yb, zb, x1, y1, z1), g, j + T, self);
     }
     if (j < n) {
         const double x0 = xs[j], y0 = ys[j], z0 = zs[j];
-        pair_acc(a0, dist2<FAST, PBZ>(g, xa, ya, za, x0, y0, z0), g, j, self);
-        pair_acc(b0, dist2<FAST, PBZ>(g, xb, yb, zb, x0, y0, z0), g, j, self);
+        pair_add<FAST>(a0, dist2<FAST, PBZ>(g, xa, ya, za, x0, y0, z0), g, j, self);
+        pair_add<FAST>(b0, dist2<FAST, PBZ>(g, xb, yb, zb, x0, y0, z0), g, j, self);
     }
     ea = a0 + a1; eb = b0 + b1;
 }
@@ -46,12 +46,12 @@ __device__ __forceinline__ double pair_sum1(const double* xs, const double* ys, 
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     int j = tid;
     for (; j + 3 * T < n; j += 4 * T) {
-        pair_acc(s0, dist2<FAST, PBZ>(g, xa, ya, za, xs[j], ys[j], zs[j]), g, j, self);
-        pair_acc(s1, dist2<FAST, PBZ>(g, xa, ya, za, xs[j + T], ys[j + T], zs[j + T]), g, j + T, self);
-        pair_acc(s2, dist2<FAST, PBZ>(g, xa, ya, za, xs[j + 2 * T], ys[j + 2 * T], zs[j + 2 * T]), g, j + 2 * T, self);
-        pair_acc(s3, dist2<FAST, PBZ>(g, xa, ya, za, xs[j + 3 * T], ys[j + 3 * T], zs[j + 3 * T]), g, j + 3 * T, self);
+        pair_add<FAST>(s0, dist2<FAST, PBZ>(g, xa, ya, za, xs[j], ys[j], zs[j]), g, j, self);
+        pair_add<FAST>(s1, dist2<FAST, PBZ>(g, xa, ya, za, xs[j + T], ys[j + T], zs[j + T]), g, j + T, self);
+        pair_add<FAST>(s2, dist2<FAST, PBZ>(g, xa, ya, za, xs[j + 2 * T], ys[j + 2 * T], zs[j + 2 * T]), g, j + 2 * T, self);
+        pair_add<FAST>(s3, dist2<FAST, PBZ>(g, xa, ya, za, xs[j + 3 * T], ys[j + 3 * T], zs[j + 3 * T]), g, j + 3 * T, self);
     }
-    for (; j < n; j += T) pair_acc(s0, dist2<FAST, PBZ>(g, xa, ya, za, xs[j], ys[j], zs[j]), g, j, self);
+    for (; j < n; j += T) pair_add<FAST>(s0, dist2<FAST, PBZ>(g, xa, ya, za, xs[j], ys[j], zs[j]), g, j, self);
     return (s0 + s1) + (s2 + s3);
 }
 
@@ -99,6 +99,17 @@ __device__ __forceinline__ void cta_allsum(double (&v)[NV], double* partials, in
     }
 }
 
+// Barrier that also ORs a flag over the CTA (one warp: a vote).
+template <bool MULTI>
+__device__ __forceinline__ bool cta_sync_or(bool flag) {
+    if (MULTI) return __syncthreads_or(flag ? 1 : 0) != 0;
+    const bool r = __any_sync(MCPM_FULL_MASK, flag);
+    __syncwarp();
+    return r;
+}
+template <bool MULTI>
+__device__ __forceinline__ void cta_sync() { if (MULTI) __syncthreads(); else __syncwarp(); }
+
 // Full energy of the chain held in shared memory: per-particle sums as MC::BoxEnergy forms them
 // (src/energy.cpp:106-124; every pair is visited twice and the pair total halved).
 template <bool FAST, bool PBZ, bool MULTI>
@@ -108,13 +119,13 @@ __device__ void cta_box_energy(const double* xs, const double* ys, const double*
     for (int i = tid; i < n; i += T) {
         double xi = xs[i], yi = ys[i], zi = zs[i];
         double s = 0.0;
-        for (int j = 0; j < n; j++) pair_acc(s, dist2<FAST, PBZ>(g, xi, yi, zi, xs[j], ys[j], zs[j]), g, j, i);
+        for (int j = 0; j < n; j++) pair_add<FAST>(s, dist2<FAST, PBZ>(g, xi, yi, zi, xs[j], ys[j], zs[j]), g, j, i);
         v[0] += s;
-        v[1] += wall_one(P, zi);
+        v[1] += wall_single<FAST>(P, xi, yi, zi);
     }
-    __syncthreads();
+    cta_sync<MULTI>();                                     // (one warp per chain: warp-level only — several chains may share a CTA)
     cta_allsum<2, MULTI>(v, partials, 0, W, warp, lane);   // single-warp CTAs have no partials area
-    __syncthreads();
+    cta_sync<MULTI>();
     pair_half = 0.5 * (P.eps4 * v[0]);
     wall = v[1];
 }
@@ -164,11 +175,11 @@ __device__ void cache_fill(const double* xs, const double* ys, const double* zs,
         if (j < n) pair_acc(s0, dist2<FAST, PBZ>(g, xi, yi, zi, xs[j], ys[j], zs[j]), g, j, i);
         ep[i] = s0 + s1;
         v[0] += s0 + s1;
-        v[1] += wall_one(P, zi);
+        v[1] += wall_single<FAST>(P, xi, yi, zi);
     }
-    __syncthreads();
+    cta_sync<MULTI>();                                     // (one warp per chain: warp-level only — several chains may share a CTA)
     cta_allsum<2, MULTI>(v, partials, 0, W, warp, lane);   // single-warp CTAs have no partials area
-    __syncthreads();
+    cta_sync<MULTI>();
     pair_half = 0.5 * (P.eps4 * v[0]);
     wall = v[1];
 }
@@ -192,17 +203,6 @@ __device__ __forceinline__ bool cache_apply(const double* xs, const double* ys, 
     }
     return big;
 }
-
-// Barrier that also ORs a flag over the CTA (one warp: a vote).
-template <bool MULTI>
-__device__ __forceinline__ bool cta_sync_or(bool flag) {
-    if (MULTI) return __syncthreads_or(flag ? 1 : 0) != 0;
-    const bool r = __any_sync(MCPM_FULL_MASK, flag);
-    __syncwarp();
-    return r;
-}
-template <bool MULTI>
-__device__ __forceinline__ void cta_sync() { if (MULTI) __syncthreads(); else __syncwarp(); }
 
 // Order-independent checksum of the live configuration (all threads return the same value; contains barriers).
 template <bool MULTI>

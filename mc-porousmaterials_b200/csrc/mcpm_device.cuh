@@ -36,6 +36,9 @@ struct PairGeom {
     double Lx, Ly, Lz;     // FAST: HALF widths; general: full widths
     double iLx, iLy, iLz;  // general path only: 1/L
     double rc2, sig2;
+    // general path only (dead in the FAST instantiations): which axes are periodic (src/read.cpp:146-162) and the pair potential
+    int px, py, pz, hs;
+    double sig;
 };
 
 template <bool FAST>
@@ -45,8 +48,11 @@ __device__ __forceinline__ PairGeom make_geom(const ChainParams& P) {
     g.Lx = f * P.L[0]; g.Ly = f * P.L[1]; g.Lz = f * P.L[2];
     g.iLx = P.invL[0]; g.iLy = P.invL[1]; g.iLz = P.invL[2];
     g.rc2 = P.rc2; g.sig2 = P.sig2;
+    g.px = P.pbc[0]; g.py = P.pbc[1]; g.pz = P.pbc[2]; g.hs = (P.pair_kind == MCPM_PAIR_HS); g.sig = P.sig_ff;
     return g;
 }
+// A cubic box of a new width (NPT volume moves, general path)
+__device__ __forceinline__ void geom_set_cube(PairGeom& g, double L) { g.Lx = g.Ly = g.Lz = L; g.iLx = g.iLy = g.iLz = 1.0 / L; }
 
 // Minimum image, MC::NeighDistance src/potentials.cpp:22-33.
 //  FAST: both positions lie in [0,L] (true for every chain the engine itself advances: insertion
@@ -70,11 +76,19 @@ __device__ __forceinline__ double image(double d, double L, double invL) {
 // PBZ: z is periodic (bulk geometry); in a slit only x and y are (src/read.cpp:146-162).
 template <bool FAST, bool PBZ>
 __device__ __forceinline__ double dist2(const PairGeom& g, double xi, double yi, double zi, double xj, double yj, double zj) {
-    double dx = image<FAST>(xi - xj, g.Lx, g.iLx);
-    double dy = image<FAST>(yi - yj, g.Ly, g.iLy);
-    double dz = zi - zj;
-    if (PBZ) dz = image<FAST>(dz, g.Lz, g.iLz);
-    return fma(dz, dz, fma(dy, dy, dx * dx));
+    if (FAST) {
+        double dx = image<FAST>(xi - xj, g.Lx, g.iLx);
+        double dy = image<FAST>(yi - yj, g.Ly, g.iLy);
+        double dz = zi - zj;
+        if (PBZ) dz = image<FAST>(dz, g.Lz, g.iLz);
+        return fma(dz, dz, fma(dy, dy, dx * dx));
+    } else {   // general path: the periodic axes follow the geometry (bulk xyz, slit xy, cylinder x, sphere none)
+        double dx = xi - xj, dy = yi - yj, dz = zi - zj;
+        if (g.px) dx = image<false>(dx, g.Lx, g.iLx);
+        if (g.py) dy = image<false>(dy, g.Ly, g.iLy);
+        if (g.pz) dz = image<false>(dz, g.Lz, g.iLz);
+        return fma(dz, dz, fma(dy, dy, dx * dx));
+    }
 }
 
 // One partner's masked term (0 when out of range / self / coincident), for the energy-cache updates.
@@ -100,6 +114,16 @@ __device__ __forceinline__ double pair_term(double r2, const PairGeom& g, int j,
     double t = 0.0;
     pair_acc(t, r2, g, j, self);
     return t;
+}
+
+// Partner term of the GENERAL kernels: Lennard-Jones as above, or MC::HardSphere_Pot (src/potentials.cpp:40-54): the finite INT_MAX
+// for every partner within sigma, and NO self-exclusion — a stored particle meets its own record at distance 0 and counts itself,
+// wherever the trial position is (the record moves with it, src/moves.cpp:163): quirk Q17.  Sums of hard-sphere terms are energies
+// already (the host sets the 4*eps prefactor to 1).
+template <bool FAST>
+__device__ __forceinline__ void pair_add(double& acc, double r2, const PairGeom& g, int j, int self) {
+    if (FAST || !g.hs) pair_acc(acc, r2, g, j, self);
+    else if (j == self || sqrt(r2) <= g.sig) acc += MCPM_INT_MAX_D;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -178,6 +202,29 @@ __device__ __forceinline__ void wall_two_and_sum(const ChainParams& P, double z_
     }
 }
 
+// Tools::Pow, src/tools.h:53-58
+__device__ __forceinline__ double ipow_d(double v, int p) { double r = 1.0; for (int i = 1; i <= p; i++) r *= v; return r; }
+
+// MC::SphericalLJ_Pot, src/potentials.cpp:474-504 (Baksh & Yang 1991), restated term for term.
+__device__ __forceinline__ double sphere_wall(const ChainParams& P, double xc, double yc, double zc) {
+    const double sig = P.sig_sf;
+    const double dens = P.rho_s * sig * sig, R = P.halfH / sig;
+    const double r = sqrt(xc * xc + yc * yc + zc * zc) / sig;
+    const double x = R - r, x2 = x - 2.0 * R;
+    double u1 = 0.0, u2 = 0.0, sgn = 1.0;
+    for (int i = 0; i < 10; i++) {
+        const double ri = ipow_d(R, i);
+        u1 += 1. / ri / ipow_d(x, 10 - i);
+        u1 += sgn / ri / ipow_d(x2, 10 - i);
+        if (i < 4) {
+            u2 += 1. / ri / ipow_d(x, 4 - i);
+            u2 += sgn / ri / ipow_d(x2, 4 - i);
+        }
+        sgn = -sgn;
+    }
+    return ((2. / 5.) * u1 - u2) * (2. * 3.14159265358979323846 * P.eps_sf * dens);
+}
+
 // Serial single-thread version (K3 computes one wall term per particle per thread).
 __device__ __forceinline__ double wall_one(const ChainParams& P, double z) {
     double boxE = 0.0;
@@ -194,6 +241,42 @@ __device__ __forceinline__ double wall_one(const ChainParams& P, double z) {
         boxE += usf * P.wall_pref;
     }
     return boxE;
+}
+
+// boxE of MC::EnergyOfParticle (src/energy.cpp:53-77) for ANY supported geometry / wall: out-of-pore guard by geometry (sphere r^2,
+// cylinder y^2+z^2, slit z^2 against (H/2)^2; finite INT_MAX, the wall term is still added: quirk Q6), then the wall dispatch.
+__device__ __forceinline__ double wall_any(const ChainParams& P, double x, double y, double z) {
+    const double xc = x - 0.5 * P.L[0], yc = y - 0.5 * P.L[1], zc = z - P.halfH;
+    double d2 = 0.0;
+    if (P.geometry == MCPM_GEOM_SPHERE) d2 = xc * xc + yc * yc + zc * zc;
+    else if (P.geometry == MCPM_GEOM_CYLINDER) d2 = yc * yc + zc * zc;
+    else if (P.geometry == MCPM_GEOM_SLIT) d2 = zc * zc;
+    double boxE = (d2 > P.sqr_pore_r || d2 < 0.0) ? MCPM_INT_MAX_D : 0.0;
+    if (P.wall_kind == MCPM_WALL_SPHERE_LJ && P.geometry == MCPM_GEOM_SPHERE) boxE += sphere_wall(P, xc, yc, zc);
+    else if (P.wall_kind == MCPM_WALL_SLIT_LJ && P.geometry == MCPM_GEOM_SLIT) {
+        double usf = 0.0;
+        for (int i = 0; i < P.n_layers; i++) {
+            double ta = P.sig_sf * fast_rcp(P.halfH + i * P.delta + zc);
+            double tb = P.sig_sf * fast_rcp(P.halfH + i * P.delta - zc);
+            double a2 = ta * ta, a4 = a2 * a2, b2 = tb * tb, b4 = b2 * b2;
+            usf += 0.2 * (a4 * a4 * a2 + b4 * b4 * b2) - 0.5 * (a4 + b4);
+        }
+        boxE += usf * P.wall_pref;
+    }
+    return boxE;
+}
+// Wall terms of two positions: the hot kernels (FAST) know only slits and use the lane-parallel wall_two on z; the general kernels
+// take the lane-parallel path too unless the system is exotic.  Must be called by all 32 lanes.
+template <bool FAST>
+__device__ __forceinline__ void wall_pair(const ChainParams& P, double xa, double ya, double za, double xb, double yb, double zb, double& wa, double& wb,
+                                          int lane) {
+    if (FAST || !P.exotic) wall_two(P, za, zb, wa, wb, lane);
+    else { wa = wall_any(P, xa, ya, za); wb = wall_any(P, xb, yb, zb); }
+}
+template <bool FAST>
+__device__ __forceinline__ double wall_single(const ChainParams& P, double x, double y, double z) {
+    if (FAST || !P.exotic) return wall_one(P, z);
+    return wall_any(P, x, y, z);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1,5 +1,5 @@
 // CUDA kernels of the engine (sm_100a, fp64):
-//   K1 k1_particle_energy   — MC::EnergyOfParticle, one particle (stored and/or displaced) vs all
+//   (K1, MC::EnergyOfParticle for a host-driven loop, lives in mcpm_k1.cu)
 //   K2 k2_chains            — persistent batched Metropolis chains, one CTA per chain
 //   K3 k3_box_energy        — MC::BoxEnergy, per-particle and box totals, O(N^2) tiled through smem
 //   fp64_peak_kernel        — DFMA microbenchmark for the roofline denominator
@@ -49,14 +49,18 @@ __device__ __forceinline__ long long k2_probe(double x) {   // clock read that c
 #define K2_PROBE(k, x)
 #endif
 
-template <class Source, bool FAST, bool MULTI, bool PBZ, bool SAMPLE, bool CACHE>
+// POOL (k2_pool below): the chain lives in a shared-memory SLOT of cap_slot <= cap particles; a chain that outgrows its slot
+// PAUSES (position in the run and the counters of the interrupted set go to S.res) and is resumed by a later launch in a larger slot.
+template <class Source, bool FAST, bool MULTI, bool PBZ, bool SAMPLE, bool CACHE, bool POOL = false>
 __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, double* xs, double* ys, double* zs, double* partials,
-                           const RunArgs& a, unsigned char* trace, int cap, uint32_t chain, double* hist) {
+                           const RunArgs& a, unsigned char* trace, int cap, uint32_t chain, double* hist, int cap_slot = 0) {
+    if (!POOL) cap_slot = cap;
     const uint32_t sid = S.stream_id;   // Philox streams are keyed by the chain's global id, not its index inside this context
+    // (pooled kernel: blocks are (32, warps) — threadIdx.x is the lane and blockDim.x == 32, so every warp of the CTA is a "CTA" of its own here)
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
     const int tmask = T - 1;  // T is a power of two
     const bool lead = (tid == 0);
-    const PairGeom g = make_geom<FAST>(P);
+    PairGeom g = make_geom<FAST>(P);   // (mutable only for NPT volume moves in the general kernels)
     mcpm_chain_stats& st = S.st;   // shared memory; written by thread 0 only
     const bool widom_on = SAMPLE && (P.n_swap == 0) && !a.no_sampling;   // ComputeWidom acts only without swap moves, src/moves.cpp:415
 
@@ -67,7 +71,14 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
     int overflow = 0;
     const double wsum = P.wsum, thr_disp = P.thr_disp, thr_vol = P.thr_vol;
     const double beta = P.beta, eps4 = P.eps4, ln_zzV = P.ln_zzV, zzV = P.zzV;
-    const double Lx = P.L[0], Ly = P.L[1], Lz = P.L[2];
+    double Lx = P.L[0], Ly = P.L[1], Lz = P.L[2];
+    // ---- general kernels only (row f4): NPT state.  MC::ChangeVolume compares the fresh BoxEnergy with the reference's RUNNING box
+    // energy (src/moves.cpp:219-220), which as shipped moves by HALF the pair change of an accepted translation (quirk Q16) and is
+    // re-anchored by CorrectEnergy's ratio test (src/energy.cpp:35-42, Q4).  Both are tracked here beside the exact energies: the
+    // recompute CorrectEnergy would do returns what the exact bookkeeping already holds, so it costs nothing.
+    const bool npt = !FAST && P.n_vol > 0;
+    double volume = npt ? Lz * Lz * Lz : 0.0, dv = st.dv, b_energy = S.b_valid ? S.b_energy : st.pair + st.wall, b_old = S.b_valid ? S.b_old : 0.0;
+    int acc_vol = 0, rej_vol = 0, n_volch = 1;
     Fwd fwd; fwd.slot = -1; fwd.x = fwd.y = fwd.z = 0.0;
     // One-warp chains on the energy cache synchronise after every accepted move (the cache entries must be visible), so a
     // slot is never read before its last write is visible: no register forwarding, and the hole-filling particle of a
@@ -96,11 +107,20 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
         }
     }
 
-    for (int set = a.first_set; set < a.first_set + a.n_sets && !overflow; set++) {
-        sc.reset();                      // MC::ResetStats, src/MC.cpp:81-98
-        if (lead) { st.widom_insert = st.widom_delete = 0.0; st.widom_insertions = st.widom_deletions = 1; }
+    int paused = 0, set0 = a.first_set, s0 = 0, p_set = 0, p_step = 0;
+    const bool resuming = POOL && S.res.paused;
+    if (resuming) { set0 = S.res.set; s0 = S.res.step; }
+    for (int set = set0; set < a.first_set + a.n_sets && !overflow && !paused; set++) {
+        if (resuming && set == set0) {   // the interrupted set goes on with the counters it had
+            sc.n_disp = S.res.n_disp; sc.acc_disp = S.res.acc_disp; sc.n_ins = S.res.n_ins; sc.acc_ins = S.res.acc_ins;
+            sc.n_del = S.res.n_del; sc.acc_del = S.res.acc_del; sc.n_empty = S.res.n_empty; sc.evals = S.res.evals; sc.alg = S.res.alg;
+        } else {
+            sc.reset();                  // MC::ResetStats, src/MC.cpp:81-98
+            acc_vol = rej_vol = 0; n_volch = 1;
+            if (lead) { st.widom_insert = st.widom_delete = 0.0; st.widom_insertions = st.widom_deletions = 1; }
+        }
         const bool production = set > P.n_equil;
-        for (int s = 0; s < steps_per_set; s++) {
+        for (int s = (resuming && set == set0) ? s0 : 0; s < steps_per_set; s++) {
 #ifdef MCPM_K2_TIMING
             long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             K2_PROBE(0, e_pair);
@@ -122,9 +142,10 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                 load_sel(xs, ys, zs, i, fwd, xo, yo, zo);
                 const double xr = __dadd_rn(xo, __dmul_rn(u_x - 0.5, dr)), yr = __dadd_rn(yo, __dmul_rn(u_y - 0.5, dr));
                 const double zr = __dadd_rn(zo, __dmul_rn(u_z - 0.5, dr));
-                bool odd = false;                                                 // MC::PBC: x and y are always periodic
-                double xn = wrap_select(xr, Lx, odd), yn = wrap_select(yr, Ly, odd), zn = PBZ ? wrap_select(zr, Lz, odd) : zr;
-                if (odd) { xn = wrap_floor(xr, Lx); yn = wrap_floor(yr, Ly); if (PBZ) zn = wrap_floor(zr, Lz); }
+                bool odd = false;                                                 // MC::PBC: periodic axes only (hot kernels: x, y and, in bulk, z)
+                const bool wx = FAST || g.px, wy = FAST || g.py, wz = FAST ? PBZ : (g.pz != 0);
+                double xn = wx ? wrap_select(xr, Lx, odd) : xr, yn = wy ? wrap_select(yr, Ly, odd) : yr, zn = wz ? wrap_select(zr, Lz, odd) : zr;
+                if (odd) { if (wx) xn = wrap_floor(xr, Lx); if (wy) yn = wrap_floor(yr, Ly); if (wz) zn = wrap_floor(zr, Lz); }
                 double v[2];
                 double wo, wn;
                 K2_PROBE(1, xn + yn + zn);
@@ -134,7 +155,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                     K2_PROBE(2, v[1]);
                     double w1[1] = {v[1]};
                     if (MULTI) {
-                        wall_two(P, zo, zn, wo, wn, lane);
+                        wall_pair<FAST>(P, xo, yo, zo, xn, yn, zn, wo, wn, lane);
                         cta_allsum<1, MULTI>(w1, partials, parity, W, warp, lane); parity ^= 1;
                     } else {
                         wall_two_and_sum(P, zo, zn, wo, wn, w1[0], lane);     // one warp: wall and scan reductions interleaved
@@ -144,7 +165,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                     sc.evals += (unsigned long long)n;
                 } else {
                     pair_sum2<FAST, PBZ>(xs, ys, zs, n, i, g, xo, yo, zo, xn, yn, zn, tid, T, v[0], v[1]);
-                    wall_two(P, zo, zn, wo, wn, lane);
+                    wall_pair<FAST>(P, xo, yo, zo, xn, yn, zn, wo, wn, lane);
                     cta_allsum<2, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
                     sc.evals += 2ull * (unsigned long long)n;
                 }
@@ -155,6 +176,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                 K2_PROBE(4, acc ? 1.0 : 2.0);
                 sc.n_disp++; sc.alg += 2ull * (unsigned long long)n;
                 fwd.slot = -1;
+                if (npt) { b_old = b_energy; if (acc) b_energy += 0.5 * (pn - po) + (wn - wo); }   // src/moves.cpp:149,173-180 as shipped
                 if (acc) {
                     sc.acc_disp++;
                     if (n > 0) {   // exact bookkeeping: the halved box total moves by the FULL pair change (the
@@ -179,23 +201,60 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                 code = acc ? 1 : 0;
                 if (SAMPLE) { sx = xo; sy = yo; sz = zo; s_po = po; s_wo = wo; mx = xn; my = yn; mz = zn; s_acc = acc; }
             } else if (r <= thr_vol) {
-                rng.end_step(1);
-                code = (4 << 1);  // volume moves are out of scope (n_vol is rejected by the host API)
+                code = (4 << 1);
+                if (!npt) rng.end_step(1);   // (the hot kernels never see volume moves: the host routes n_vol > 0 to the general kernels)
+                else {
+                    // ---------------- ChangeVolume, NPT branch, single box: src/moves.cpp:191-231 ----------------
+                    // draw 1 picks the box.  RescaleCenterOfMass runs BEFORE the widths change (ratio 1): the coordinates are NOT
+                    // rescaled (quirk Q18); all three widths become ComputeBoxWidth(V') = cbrt V' (bulk, src/read.cpp:19-25).
+                    const double u_v = rng.template at<2>(), u_a = rng.template at<3>();
+                    rng.end_step(4);
+                    n_volch++;
+                    const double v_new = exp(log(volume) + (u_v - 0.5) * dv);
+                    const double l_new = cbrt(v_new);
+                    PairGeom g2 = g;
+                    geom_set_cube(g2, l_new);
+                    cta_sync<MULTI>();                                            // the previous step's slot write is visible
+                    double t_pair, t_wall;
+                    cta_box_energy<FAST, PBZ, MULTI>(xs, ys, zs, n, P, g2, partials, W, warp, lane, tid, T, t_pair, t_wall);   // BoxEnergy, :219
+                    fwd.slot = -1;
+                    sc.evals += (unsigned long long)n * (unsigned long long)n;
+                    const double e_new = t_pair + t_wall;
+                    const double arg0 = (e_new - b_energy) + P.press_k * (v_new - volume) - (nd + 1.0) * log(v_new / volume) * P.T;   // :220-222
+                    if (u_a > exp(-arg0 / P.T)) rej_vol++;                        // rejected: box = oldBox0
+                    else {
+                        acc_vol++;
+                        volume = v_new; Lx = Ly = Lz = l_new; g = g2;
+                        e_pair = t_pair; e_wall = t_wall; b_energy = e_new;
+                        code |= 1;
+                    }
+                }
             } else {
                 // ---------------- SwapParticle, single box, src/moves.cpp:284-341 ----------------
                 // draw 1 (species selection) is consumed but unused
                 if (rng.template at<2>() < 0.5) {
-                    if (n >= cap) { overflow = 1; break; }
+                    if (n >= cap_slot) {
+                        if (POOL && cap_slot < cap) { paused = 1; p_set = set; p_step = s; step--; }   // this step runs again after the move to a larger slot
+                        else overflow = 1;
+                        break;
+                    }
                     const double u_x = rng.template at<3>(), u_y = rng.template at<4>(), u_z = rng.template at<5>(), u_a = rng.template at<6>();
                     rng.end_step(7);
-                    const double xi = u_x * Lx, yi = u_y * Ly, zi = u_z * Lz;     // InsertParticle, src/moves.cpp:46-54
+                    double xi = u_x * Lx, yi = u_y * Ly, zi = u_z * Lz;           // InsertParticle, src/moves.cpp:46-54
+                    if (!FAST && P.geometry == MCPM_GEOM_SPHERE) {                // :25-36: radius, theta, phi (not uniform in volume: as shipped)
+                        const double rad = u_x * Lz * 0.5, th = u_y * 3.14159265358979323846, ph = u_z * 2 * 3.14159265358979323846;
+                        xi = rad * sin(th) * cos(ph) + 0.5 * Lx; yi = rad * sin(th) * sin(ph) + 0.5 * Ly; zi = rad * cos(th) + 0.5 * Lz;
+                    } else if (!FAST && P.geometry == MCPM_GEOM_CYLINDER) {       // :37-45: rho, phi, then x
+                        const double rho = u_x * Lz * 0.5, ph = u_y * 2 * 3.14159265358979323846;
+                        xi = (u_z - 0.5) * Lx + 0.5 * Lx; yi = rho * sin(ph) + 0.5 * Ly; zi = rho * cos(ph) + 0.5 * Lz;
+                    }
                     // the trial position is written to the first free slot even if rejected (src/moves.cpp:302-303)
                     if ((n & tmask) == tid) { xs[n] = xi; ys[n] = yi; zs[n] = zi; }
                     double v[1];
                     v[0] = pair_sum1<FAST, PBZ>(xs, ys, zs, n, -1, g, xi, yi, zi, tid, T);
                     double wi, wdummy;
                     if (MULTI) {
-                        wall_two(P, zi, zi, wi, wdummy, lane);
+                        wall_pair<FAST>(P, xi, yi, zi, xi, yi, zi, wi, wdummy, lane);
                         cta_allsum<1, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
                     } else {
                         wall_two_and_sum(P, zi, zi, wi, wdummy, v[0], lane);
@@ -233,10 +292,10 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                     double wo, wdummy;
                     if (CACHE) {
                         v[0] = ep[o];                                             // no partner scan at all
-                        wall_two(P, zo, zo, wo, wdummy, lane);
+                        wall_pair<FAST>(P, xo, yo, zo, xo, yo, zo, wo, wdummy, lane);
                     } else {
                         v[0] = pair_sum1<FAST, PBZ>(xs, ys, zs, n, o, g, xo, yo, zo, tid, T);
-                        wall_two(P, zo, zo, wo, wdummy, lane);
+                        wall_pair<FAST>(P, xo, yo, zo, xo, yo, zo, wo, wdummy, lane);
                         cta_allsum<1, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
                         fwd.slot = -1;
                         sc.evals += (unsigned long long)n;
@@ -282,12 +341,16 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                 rng.load_extra(a.seed, sid, step - 1, lane);
                 double energy;                                                   // draw 0 (species) is consumed but unused
                 if (rng.template extra<1>() < 0.5) {                             // ghost insertion
-                    const double gx = rng.template extra<2>() * Lx, gy = rng.template extra<3>() * Ly, gz = rng.template extra<4>() * Lz;
+                    double gx = rng.template extra<2>() * Lx, gy = rng.template extra<3>() * Ly, gz = rng.template extra<4>() * Lz;
+                    if (!FAST && P.geometry == MCPM_GEOM_SPHERE) {                // InsertParticle's sphere branch, src/moves.cpp:25-36
+                        const double rad = rng.template extra<2>() * Lz * 0.5, th = rng.template extra<3>() * 3.14159265358979323846, ph = rng.template extra<4>() * 2 * 3.14159265358979323846;
+                        gx = rad * sin(th) * cos(ph) + 0.5 * Lx; gy = rad * sin(th) * sin(ph) + 0.5 * Ly; gz = rad * cos(th) + 0.5 * Lz;
+                    }
                     rng.end_step(5);
                     double v[1];
                     v[0] = pair_sum1<FAST, PBZ>(xs, ys, zs, n, -1, g, gx, gy, gz, tid, T);
                     double wg, wdummy;
-                    wall_two(P, gz, gz, wg, wdummy, lane);
+                    wall_pair<FAST>(P, gx, gy, gz, gx, gy, gz, wg, wdummy, lane);
                     cta_allsum<1, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
                     fwd.slot = -1;
                     energy = eps4 * v[0] + wg;
@@ -300,7 +363,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                         // particle sits there again and is skipped by position equality -> its old energy.  Accepted
                         // move: a ghost at the old position that also sees the moved particle.
                         double extra = 0.0;
-                        if (s_acc) pair_acc(extra, dist2<FAST, PBZ>(g, sx, sy, sz, mx, my, mz), g, 0, -1);
+                        if (s_acc) pair_add<FAST>(extra, dist2<FAST, PBZ>(g, sx, sy, sz, mx, my, mz), g, 0, -1);
                         energy = (s_po + eps4 * extra) + s_wo;
                     } else {
                         const int k = slot1 - 1;
@@ -310,10 +373,10 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                         double wk, wdummy;
                         if (CACHE) {
                             v[0] = ep[k];                                         // a real particle's pair sum is in the cache
-                            wall_two(P, zk, zk, wk, wdummy, lane);
+                            wall_pair<FAST>(P, xk, yk, zk, xk, yk, zk, wk, wdummy, lane);
                         } else {
                             v[0] = pair_sum1<FAST, PBZ>(xs, ys, zs, n, k, g, xk, yk, zk, tid, T);
-                            wall_two(P, zk, zk, wk, wdummy, lane);
+                            wall_pair<FAST>(P, xk, yk, zk, xk, yk, zk, wk, wdummy, lane);
                             cta_allsum<1, MULTI>(v, partials, parity, W, warp, lane); parity ^= 1;
                             fwd.slot = -1;
                             if (lead) st.pair_evals += (unsigned long long)n;
@@ -343,6 +406,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                 o[4] += (double)(tend - tp[4]); o[5] += 1.0;
             }
 #endif
+            if (npt && b_energy / b_old > 1) b_energy = e_pair + e_wall;        // MC::CorrectEnergy (src/main.cpp:71): BoxEnergy == the exact energy
             if (lead && trace) trace[(unsigned long long)(set - a.first_set) * (unsigned long long)a.steps_per_set + (unsigned long long)s] = (unsigned char)code;
             if (production) {
                 const double dn = nd, e = e_pair + e_wall;
@@ -355,6 +419,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                 }
             }
         }
+        if (POOL && paused) break;          // the set is not over: no adjustment, no flush of its counters
         if (lead) st.dr_used = dr;          // the amplitude this set ran with (statistics are printed before the adjustment, src/main.cpp:77-83)
         // MC::AdjustMCMoves displacement part, src/moves.cpp:68-78 (ResetStats starts nDisplacements at ONE)
         if (!overflow && n > 0 && set <= P.n_equil) {
@@ -362,7 +427,13 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
             if (ratio < 0.2) dr /= 1.1;
             else dr *= 1.1;
         }
+        if (npt && !overflow && n > 0) {   // AdjustMCMoves volume part, src/moves.cpp:79-84: every set, not only during equilibration
+            const double ratio = (double)acc_vol * 1. / (1. * (double)n_volch);
+            if (ratio < 0.5 && dv > 1e-3) dv /= 1.1;
+            else dv *= 1.1;
+        }
         if (lead) {
+            if (npt) { st.accept_vol = acc_vol; st.reject_vol = rej_vol; st.n_vol_changes = n_volch; }
             st.acceptance = sc.acc_disp; st.rejection = sc.n_disp - sc.acc_disp; st.n_displacements = 1 + sc.n_disp;
             st.accept_swap = sc.acc_ins + sc.acc_del; st.reject_swap = (sc.n_ins + sc.n_del) - (sc.acc_ins + sc.acc_del);
             st.n_swaps = 1 + sc.n_ins + sc.n_del;
@@ -370,10 +441,10 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
             st.tot_del += sc.n_del; st.tot_del_acc += sc.acc_del; st.tot_empty += sc.n_empty; st.pair_evals += sc.evals; st.pair_evals_algorithmic += sc.alg;
         }
     }
-    __syncthreads();
+    cta_sync<MULTI>();
 
     double c_pair = 0.0, c_wall = 0.0;
-    if (a.check_energy) {
+    if (a.check_energy && !paused) {
         if (CACHE) cache_fill<FAST, PBZ, MULTI>(xs, ys, zs, ep, n, P, g, partials, W, warp, lane, tid, T, c_pair, c_wall);   // also refreshes the cache
         else cta_box_energy<FAST, PBZ, MULTI>(xs, ys, zs, n, P, g, partials, W, warp, lane, tid, T, c_pair, c_wall);
     }
@@ -383,13 +454,22 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
     if (lead) {
         st.n = n; st.overflow = overflow; st.dr = dr; st.steps_done = step;
         st.pair = e_pair; st.wall = e_wall; st.energy = e_pair + e_wall;
+        if (npt) { st.volume = volume; st.width = Lz; st.dv = dv; st.energy_as_shipped = b_energy; S.b_energy = b_energy; S.b_old = b_old; S.b_valid = 1; }
         if (!SAMPLE) { st.sum_n = sum_n; st.sum_n2 = sum_n2; st.sum_e = sum_e; st.sum_e2 = sum_e2; st.samples = samples; }
-        if (a.check_energy) { st.pair_check = c_pair; st.wall_check = c_wall; st.energy_check = c_pair + c_wall; }
-        if (a.check_energy == 2) { st.pair = c_pair; st.wall = c_wall; st.energy = c_pair + c_wall; }   // adopt, like BoxEnergy does
+        if (a.check_energy && !paused) { st.pair_check = c_pair; st.wall_check = c_wall; st.energy_check = c_pair + c_wall; }
+        if (a.check_energy == 2 && !paused) { st.pair = c_pair; st.wall = c_wall; st.energy = c_pair + c_wall; }   // adopt, like BoxEnergy does
         S.replay_pos = rng.cursor();
         st.replay_consumed = rng.cursor();
         S.cache_valid = (CACHE && !overflow) ? 1 : 0;   // kernels that do not maintain the cache leave it stale
         S.cache_sum = end_sum;
+        if (POOL) {
+            S.res.paused = paused;
+            if (paused) {
+                S.res.set = p_set; S.res.step = p_step;
+                S.res.n_disp = sc.n_disp; S.res.acc_disp = sc.acc_disp; S.res.n_ins = sc.n_ins; S.res.acc_ins = sc.acc_ins;
+                S.res.n_del = sc.n_del; S.res.acc_del = sc.acc_del; S.res.n_empty = sc.n_empty; S.res.evals = sc.evals; S.res.alg = sc.alg;
+            }
+        }
     }
 }
 
@@ -454,71 +534,107 @@ __global__ void __launch_bounds__(MAXT, MINB) k2_chains(const ChainParams* __res
 }
 
 // ================================================================================================
-// K1 — single-particle energy (MC::EnergyOfParticle, src/energy.cpp:43-105).
-// Evaluates up to two positions against all n stored particles in ONE pass over j:
-//   A = stored particle `index` (if index >= 0), B = trial position (if has_trial).
-// grid.x CTAs each take a contiguous slice of j; partial sums go to scratch and the last CTA to
-// finish adds them in CTA order (deterministic) and writes out[8] = {pairA,0,wallA,EA, pairB,0,wallB,EB}.
+// K2p — k2_pool: the one-warp-per-chain hot kernel as ONE PERSISTENT CTA PER SM with a shared-memory pool.
+//
+// k2_chains sizes every CTA's shared memory for the LARGEST chain of the launch (17 KB at capacity 704), which caps the residency at
+// 12 chains per SM although the isotherm's mean loading is half of that and a third of its state points hold < 150 particles.  Here a CTA
+// of W warps owns the SM's whole shared memory and carves it into W slots of up to three capacity classes (host: pool_layout in
+// mcpm_api.cu); every warp runs the unchanged one-warp chain loop in its slot and, when its chain is done, claims the next one from
+// the queue of its class (or of a smaller class): 16 warps at 128 registers — the register file, no longer shared memory, is the
+// limit — and no wave quantisation (chains are handed out longest first as warps fall free).
+// A chain that grows beyond its slot during the launch pauses (ChainResume) and is finished by a follow-up launch in full-size slots.
 // ================================================================================================
-template <bool FAST>
-__global__ void __launch_bounds__(256) k1_particle_energy(const ChainParams* __restrict__ params, const ChainState* __restrict__ states,
-                                                          const double* __restrict__ X, const double* __restrict__ Y, const double* __restrict__ Z,
-                                                          int chain, int cap, int index, int has_trial, double tx, double ty, double tz,
-                                                          double* __restrict__ scratch, unsigned int* __restrict__ counter, double* __restrict__ out) {
-    __shared__ ChainParams P;
-    __shared__ double red[2][8];
-    __shared__ bool last;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) P = params[chain];
-    __syncthreads();
-    const PairGeom g = make_geom<FAST>(P);
-    const int n = states[chain].st.n;
-    const size_t off = (size_t)chain * (size_t)cap;
-    const double* xs = X + off; const double* ys = Y + off; const double* zs = Z + off;
-    double xa = 0, ya = 0, za = 0;
-    if (index >= 0) { xa = xs[index]; ya = ys[index]; za = zs[index]; }
-    if (!has_trial) { tx = xa; ty = ya; tz = za; }
-    double sa = 0.0, sb = 0.0;
-    if (P.pbc[2]) {
-        for (int j = blockIdx.x * blockDim.x + tid; j < n; j += gridDim.x * blockDim.x) {
-            double xj = xs[j], yj = ys[j], zj = zs[j];
-            pair_acc(sa, dist2<FAST, true>(g, xa, ya, za, xj, yj, zj), g, j, index);
-            pair_acc(sb, dist2<FAST, true>(g, tx, ty, tz, xj, yj, zj), g, j, index);
-        }
-    } else {
-        for (int j = blockIdx.x * blockDim.x + tid; j < n; j += gridDim.x * blockDim.x) {
-            double xj = xs[j], yj = ys[j], zj = zs[j];
-            pair_acc(sa, dist2<FAST, false>(g, xa, ya, za, xj, yj, zj), g, j, index);
-            pair_acc(sb, dist2<FAST, false>(g, tx, ty, tz, xj, yj, zj), g, j, index);
-        }
-    }
-    sa = warp_allsum(sa); sb = warp_allsum(sb);
-    if (lane == 0) { red[0][warp] = sa; red[1][warp] = sb; }
-    __syncthreads();
-    if (tid == 0) {
-        double ta = 0, tb = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { ta += red[0][w]; tb += red[1][w]; }
-        scratch[2 * blockIdx.x] = ta; scratch[2 * blockIdx.x + 1] = tb;
-        __threadfence();
-        last = (atomicAdd(counter, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (last && warp == 0) {
-        __threadfence();
-        double ta = 0, tb = 0;
+template <int RNG_MODE, int WARPS, bool PBZ>
+__global__ void __launch_bounds__(32 * WARPS, 1) k2_pool(const ChainParams* __restrict__ params, ChainState* __restrict__ states,
+                                                         const int* __restrict__ order, double* X, double* Y, double* Z, RunArgs a, PoolLayout L) {
+    // blockDim = (32, WARPS): threadIdx.x is the lane, threadIdx.y the warp / slot.  chain_loop then sees tid = lane and T = 32 exactly as in
+    // a one-warp CTA of k2_chains, and compiles to the same hot loop.
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x, w = threadIdx.y;
+    if (w >= L.n_slots) return;
+    const int cap = a.cap;
+    // everything the claim loop needs lives in shared memory / the constant bank and is re-read after a chain: nothing of it has to
+    // stay in registers across chain_loop
+    volatile int* wq = reinterpret_cast<volatile int*>(smem + L.state_off + (size_t)w * L.state_stride) + (((sizeof(ChainParams) + 15) / 16) * 16 + ((sizeof(ChainState) + 15) / 16) * 16) / 4;
+    for (;;) {
+        const int cap_slot = L.slot_cap[w];
+        double* xs = smem + L.slot_off[w];
+        double* ys = xs + cap_slot;
+        double* zs = ys + cap_slot;
+        double* ubuf = zs + cap_slot;                                    // 64 doubles: this warp's batch of uniforms
+        ChainParams& P = *reinterpret_cast<ChainParams*>(smem + L.state_off + (size_t)w * L.state_stride);
+        ChainState& S = *reinterpret_cast<ChainState*>(reinterpret_cast<char*>(&P) + ((sizeof(ChainParams) + 15) / 16) * 16);
+        // ---- claim a chain: own class first, then the smaller ones ----
+        int item = -1;
         if (lane == 0) {
-            for (unsigned b = 0; b < gridDim.x; b++) { ta += ((volatile double*)scratch)[2 * b]; tb += ((volatile double*)scratch)[2 * b + 1]; }
+            for (int c = L.slot_cls[w]; c < L.n_classes && item < 0; c++) {
+                if (L.q_begin[c] >= L.q_end[c]) continue;
+                const int k = L.q_begin[c] + atomicAdd(&L.q_next[c], 1);
+                if (k < L.q_end[c]) item = k;
+            }
         }
-        double wa, wb;
-        wall_two(P, za, tz, wa, wb, lane);
-        if (lane == 0) {
-            double pa = P.eps4 * ta, pb = P.eps4 * tb;
-            if (index < 0) { pa = 0; wa = 0; }
-            out[0] = pa; out[1] = 0.0; out[2] = wa; out[3] = pa + wa;
-            out[4] = pb; out[5] = 0.0; out[6] = wb; out[7] = pb + wb;
-            *counter = 0u;
+        item = __shfl_sync(MCPM_FULL_MASK, item, 0);
+        if (item < 0) return;
+        int chain = order[item];
+        if (lane == 0) wq[0] = chain;
+        {
+            const size_t off = (size_t)chain * (size_t)cap;
+            const int* ps = reinterpret_cast<const int*>(params + chain); int* pd = reinterpret_cast<int*>(&P);
+            for (int k = lane; k < (int)(sizeof(ChainParams) / 4); k += 32) pd[k] = ps[k];
+            const int* ss = reinterpret_cast<const int*>(states + chain); int* sd = reinterpret_cast<int*>(&S);
+            for (int k = lane; k < (int)(sizeof(ChainState) / 4); k += 32) sd[k] = ss[k];
+            for (int j = lane; j < cap_slot; j += 32) { xs[j] = X[off + j]; ys[j] = Y[off + j]; zs[j] = Z[off + j]; }
         }
+        __syncwarp();
+        if (S.st.n > cap_slot) {            // cannot happen with the host's class assignment; never touch memory beyond the slot
+            if (lane == 0) { S.res.paused = 1; S.res.set = a.first_set; S.res.step = 0; S.res.n_disp = S.res.acc_disp = S.res.n_ins = S.res.acc_ins = 0;
+                             S.res.n_del = S.res.acc_del = S.res.n_empty = 0; S.res.evals = S.res.alg = 0ull; states[chain].res = S.res; }
+            __syncwarp();
+            continue;
+        }
+        {
+            unsigned char* trace = a.trace ? a.trace + (unsigned long long)chain * a.trace_stride : nullptr;
+            if (RNG_MODE == MCPM_RNG_PHILOX) {
+                PhiloxSmemSource rng; rng.init(a.seed, S.stream_id, S.st.steps_done, lane, ubuf);
+                chain_loop<PhiloxSmemSource, true, false, PBZ, false, true, true>(P, S, rng, xs, ys, zs, ubuf, a, trace, cap, (uint32_t)chain, nullptr, cap_slot);
+            } else {
+                ReplaySource rng; rng.init(a.replay_u + (unsigned long long)chain * a.replay_stride, S.res.paused ? S.replay_pos : 0ull, a.replay_stride);
+                chain_loop<ReplaySource, true, false, PBZ, false, true, true>(P, S, rng, xs, ys, zs, ubuf, a, trace, cap, (uint32_t)chain, nullptr, cap_slot);
+            }
+        }
+        __syncwarp();
+        chain = wq[0];                                                   // re-read: not kept in a register across the chain
+        {
+            const size_t off = (size_t)chain * (size_t)cap;
+            for (int j = lane; j < cap_slot; j += 32) { X[off + j] = xs[j]; Y[off + j] = ys[j]; Z[off + j] = zs[j]; }
+            const int* sd = reinterpret_cast<const int*>(&S); int* ss = reinterpret_cast<int*>(states + chain);
+            for (int k = lane; k < (int)(sizeof(ChainState) / 4); k += 32) ss[k] = sd[k];
+        }
+        __syncwarp();
     }
+}
+
+size_t pool_state_stride_doubles() { return (((sizeof(ChainParams) + 15) / 16) * 16 + ((sizeof(ChainState) + 15) / 16) * 16 + 16) / sizeof(double); }   // + 16 bytes of claim-loop scratch
+
+cudaError_t launch_k2_pool(int rng_mode, bool pbz, int warps, int n_ctas, size_t smem, const ChainParams* params, ChainState* states, const int* order,
+                           double* X, double* Y, double* Z, const RunArgs& a, const PoolLayout& L, cudaStream_t stream) {
+    auto go = [&](auto kern, int threads) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<n_ctas, dim3(32, threads / 32), smem, stream>>>(params, states, order, X, Y, Z, a, L);
+        return cudaGetLastError();
+    };
+    const bool ph = rng_mode == MCPM_RNG_PHILOX;
+#define MCPM_POOL_GO(W)                                                                                                          \
+    do {                                                                                                                         \
+        if (ph) return pbz ? go(k2_pool<MCPM_RNG_PHILOX, W, true>, 32 * W) : go(k2_pool<MCPM_RNG_PHILOX, W, false>, 32 * W);     \
+        return pbz ? go(k2_pool<MCPM_RNG_REPLAY, W, true>, 32 * W) : go(k2_pool<MCPM_RNG_REPLAY, W, false>, 32 * W);             \
+    } while (0)
+    if (warps <= 12) MCPM_POOL_GO(12);     // 168 registers per thread (experiment: register pressure)
+    if (warps <= 14) MCPM_POOL_GO(14);     // 144 registers per thread
+    if (warps <= 16) MCPM_POOL_GO(16);     // 128 registers per thread
+    MCPM_POOL_GO(20);                      // 96 registers per thread: more warps per scheduler, less instruction-level parallelism
+#undef MCPM_POOL_GO
 }
 
 // ================================================================================================
@@ -565,22 +681,22 @@ __global__ void __launch_bounds__(128) k3_box_energy(const ChainParams* __restri
             if (P.pbc[2]) {
                 int k = 0;
                 for (; k + 1 < m; k += 2) {
-                    pair_acc(s0, dist2<FAST, true>(g, xi, yi, zi, tx[k], ty[k], tz[k]), g, j0 + k, i);
-                    pair_acc(s1, dist2<FAST, true>(g, xi, yi, zi, tx[k + 1], ty[k + 1], tz[k + 1]), g, j0 + k + 1, i);
+                    pair_add<FAST>(s0, dist2<FAST, true>(g, xi, yi, zi, tx[k], ty[k], tz[k]), g, j0 + k, i);
+                    pair_add<FAST>(s1, dist2<FAST, true>(g, xi, yi, zi, tx[k + 1], ty[k + 1], tz[k + 1]), g, j0 + k + 1, i);
                 }
-                if (k < m) pair_acc(s0, dist2<FAST, true>(g, xi, yi, zi, tx[k], ty[k], tz[k]), g, j0 + k, i);
+                if (k < m) pair_add<FAST>(s0, dist2<FAST, true>(g, xi, yi, zi, tx[k], ty[k], tz[k]), g, j0 + k, i);
             } else {
                 int k = 0;
                 for (; k + 1 < m; k += 2) {
-                    pair_acc(s0, dist2<FAST, false>(g, xi, yi, zi, tx[k], ty[k], tz[k]), g, j0 + k, i);
-                    pair_acc(s1, dist2<FAST, false>(g, xi, yi, zi, tx[k + 1], ty[k + 1], tz[k + 1]), g, j0 + k + 1, i);
+                    pair_add<FAST>(s0, dist2<FAST, false>(g, xi, yi, zi, tx[k], ty[k], tz[k]), g, j0 + k, i);
+                    pair_add<FAST>(s1, dist2<FAST, false>(g, xi, yi, zi, tx[k + 1], ty[k + 1], tz[k + 1]), g, j0 + k + 1, i);
                 }
-                if (k < m) pair_acc(s0, dist2<FAST, false>(g, xi, yi, zi, tx[k], ty[k], tz[k]), g, j0 + k, i);
+                if (k < m) pair_add<FAST>(s0, dist2<FAST, false>(g, xi, yi, zi, tx[k], ty[k], tz[k]), g, j0 + k, i);
             }
         }
         if (live) {
             pair_i = P.eps4 * (s0 + s1);
-            wall_i = wall_one(P, zi);
+            wall_i = wall_single<FAST>(P, xi, yi, zi);
             if (per_pair) per_pair[(size_t)blockIdx.y * cap + i] = pair_i;
             if (per_wall) per_wall[(size_t)blockIdx.y * cap + i] = wall_i;
         }
@@ -841,15 +957,6 @@ cudaError_t launch_k2(int rng_mode, int n_chains, int threads, bool fast, bool s
     return cudaGetLastError();
 }
 
-cudaError_t launch_k1(bool fast, int blocks, const ChainParams* params, const ChainState* states, const double* X, const double* Y,
-                      const double* Z, int chain, int cap, int index, int has_trial, const double* t, double* scratch,
-                      unsigned int* counter, double* out, cudaStream_t stream) {
-    double tx = t ? t[0] : 0, ty = t ? t[1] : 0, tz = t ? t[2] : 0;
-    if (fast) k1_particle_energy<true><<<blocks, 256, 0, stream>>>(params, states, X, Y, Z, chain, cap, index, has_trial, tx, ty, tz, scratch, counter, out);
-    else k1_particle_energy<false><<<blocks, 256, 0, stream>>>(params, states, X, Y, Z, chain, cap, index, has_trial, tx, ty, tz, scratch, counter, out);
-    return cudaGetLastError();
-}
-
 cudaError_t launch_k3(int tiles, int n_chains, int chain0, const ChainParams* params, ChainState* states, const double* X, const double* Y,
                       const double* Z, int cap, double* per_pair, double* per_wall, double* scratch, unsigned int* counters, double* out,
                       cudaStream_t stream) {
@@ -867,7 +974,7 @@ __global__ void in_box_kernel(const ChainParams* __restrict__ params, const int*
     const ChainParams& P = params[chain];
     const int n = n_of[chain];
     const size_t off = (size_t)chain * cap;
-    int bad = 0;
+    int bad = P.exotic ? 1 : 0;   // exotic systems always take the general kernels
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
         const double x = X[off + j], y = Y[off + j], z = Z[off + j];
         if (P.pbc[0] && !(x >= 0.0 && x <= P.L[0])) bad = 1;

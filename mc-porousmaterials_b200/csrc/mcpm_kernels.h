@@ -11,11 +11,19 @@ void set_last_error(const char* msg);   // mcpm_api.cu: the per-thread message b
 cudaError_t launch_k2(int rng_mode, int n_chains, int threads, bool fast, bool sample, bool cache, const ChainParams* params, ChainState* states, const int* order,
                       double* X, double* Y, double* Z, const RunArgs& a, int max_smem_optin, cudaStream_t stream);
 size_t k2_smem_limit_cap(int max_smem_optin);
+// k2_pool: persistent CTAs, one warp per chain, shared-memory slots of several capacity classes (see mcpm_kernels.cu)
+size_t pool_state_stride_doubles();
+cudaError_t launch_k2_pool(int rng_mode, bool pbz, int warps, int n_ctas, size_t smem, const ChainParams* params, ChainState* states, const int* order,
+                           double* X, double* Y, double* Z, const RunArgs& a, const PoolLayout& L, cudaStream_t stream);
 int k2_threads_supported(int threads, bool global, bool fast, bool sample);
 
-cudaError_t launch_k1(bool fast, int blocks, const ChainParams* params, const ChainState* states, const double* X, const double* Y,
-                      const double* Z, int chain, int cap, int index, int has_trial, const double* trial, double* scratch,
-                      unsigned int* counter, double* out, cudaStream_t stream);
+// mcpm_k1.cu: MC::EnergyOfParticle for a batch of requests; positions staged by TMA bulk copies, results optionally written
+// straight into mapped host memory followed by a sequence flag
+cudaError_t launch_k1(bool fast, int n, int count, const ChainParams* params, const ChainState* states, const double* X, const double* Y,
+                      const double* Z, int chain, int cap, const K1Request* reqs, const K1Request& single, double* scratch,
+                      unsigned int* counters, double* out, double* host_out, unsigned long long* host_flag, unsigned long long seq,
+                      unsigned int* done_groups, cudaStream_t stream);
+int k1_slices(int n);
 
 cudaError_t launch_k3(int tiles, int n_chains, int chain0, const ChainParams* params, ChainState* states, const double* X, const double* Y,
                       const double* Z, int cap, double* per_pair, double* per_wall, double* scratch, unsigned int* counters, double* out,

@@ -21,6 +21,11 @@ struct ChainParams {
     int geometry, wall_kind, n_layers;
     int pbc[3];
     int n_disp, n_vol, n_swap, n_equil;
+    // "exotic" systems (row f4 of SURVEY.md §8: cylinder / sphere geometry, spherical wall, hard spheres, NPT volume moves) run through
+    // the GENERAL kernels (the instantiations that also serve coordinates outside the box), never through the hot ones
+    int pair_kind, exotic;
+    double sig_ff, eps_sf, rho_s;
+    double press_k;       // ExternalPressure / kB * 1e-30, K/AA^3 (src/moves.cpp:198)
 };
 
 // Where a chain that outgrew its sub-warp slot (mcpm_subwarp.cu) stopped, and the counters of the interrupted set.
@@ -37,6 +42,8 @@ struct ChainState {
     int energy_valid;               // running box energies were initialised by a full K3 evaluation
     unsigned long long replay_pos;  // cursor into the replay stream (REPLAY mode)
     unsigned long long cache_sum;   // checksum of the configuration the energy cache (RunArgs::ep) belongs to
+    double b_energy, b_old;         // NPT only: the reference's RUNNING box energy and Box::oldEnergy (as shipped), see chain_loop
+    int b_valid, pad3;
     int cache_valid;                // the cache was left consistent by the last K2 launch
     unsigned int stream_id;         // Philox stream of this chain: its GLOBAL id (default: index inside the context; mcpm_set_stream_ids)
     ChainResume res;
@@ -53,9 +60,34 @@ struct RunArgs {
     int check_energy;
     int cap;
     int sample_rdf;
+    int pool_threads;            // k2_pool: threads per chain (32), passed at run time so that the chain loop compiles like the one-CTA-per-chain kernel's
     int no_sampling;             // moves only: the sampling kernels skip ComputeWidom / ComputeRDF (mcpm_run_params::no_sampling)
     double* ep;                  // device, [n_chains][cap]: per-particle pair sums (unscaled) of the energy cache, or null
     double* rdf;                 // device, [n_chains][MCPM_RDF_BINS] accumulated histograms
+};
+
+// One request of K1 (mcpm_k1.cu): stored particle `index` (or -1) and/or a trial position.
+struct K1Request {
+    int index, has_trial;
+    double t[3];
+};
+#define MCPM_K1_MAX_BATCH 1024   // requests per launch
+
+// k2_pool (mcpm_kernels.cu): one persistent CTA per SM whose warps each own a shared-memory SLOT and take chains from per-class
+// work queues.  Slots come in up to three capacity classes (largest first) so that small chains do not reserve the shared memory of
+// the largest state point; a slot of class k serves the queues of classes >= k.
+#define MCPM_POOL_MAX_SLOTS 24
+#define MCPM_POOL_MAX_CLASSES 3
+struct PoolLayout {
+    int n_slots, n_classes;
+    int slot_cap[MCPM_POOL_MAX_SLOTS];   // particles
+    int slot_off[MCPM_POOL_MAX_SLOTS];   // offset of the slot in the CTA's dynamic shared memory, in doubles
+    int slot_cls[MCPM_POOL_MAX_SLOTS];
+    int q_begin[MCPM_POOL_MAX_CLASSES], q_end[MCPM_POOL_MAX_CLASSES];   // class k's chains: order[q_begin[k] .. q_end[k]), longest first
+    int state_off;                       // offset of the per-warp ChainParams / ChainState copies, in doubles
+    int state_stride;                    // doubles per warp
+    int args_off;                        // offset of the CTA's copy of RunArgs, in doubles
+    int* q_next;                         // device, [n_classes]: next unclaimed entry of every queue (zeroed before the launch)
 };
 
 #define MCPM_RDF_BINS 100        // NBINS, src/MC.h:11

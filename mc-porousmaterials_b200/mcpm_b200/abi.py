@@ -5,8 +5,9 @@ import ctypes as C
 import os
 
 RNG_PHILOX, RNG_REPLAY = 0, 1
-GEOM_BULK, GEOM_SLIT = 0, 1
-WALL_NONE, WALL_SLIT_LJ = 0, 1
+GEOM_BULK, GEOM_SLIT, GEOM_CYLINDER, GEOM_SPHERE = 0, 1, 2, 3
+WALL_NONE, WALL_SLIT_LJ, WALL_SPHERE_LJ = 0, 1, 2
+PAIR_LJ, PAIR_HS = 0, 1
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -22,12 +23,12 @@ class SystemDesc(C.Structure):
     _fields_ = [
         ("geometry", C.c_int), ("wall_kind", C.c_int), ("n_layers", C.c_int),
         ("n_disp", C.c_int), ("n_vol", C.c_int), ("n_swap", C.c_int),
-        ("n_equil_sets", C.c_int), ("reserved", C.c_int),
+        ("n_equil_sets", C.c_int), ("pair_kind", C.c_int),
         ("width", C.c_double * 3), ("temperature", C.c_double),
         ("eps_ff", C.c_double), ("sig_ff", C.c_double), ("rcut", C.c_double),
         ("molar_mass", C.c_double), ("mu", C.c_double),
         ("eps_sf", C.c_double), ("sig_sf", C.c_double), ("rho_s", C.c_double), ("delta", C.c_double),
-        ("dr", C.c_double),
+        ("dr", C.c_double), ("pressure", C.c_double), ("dv", C.c_double),
     ]
 
     @classmethod
@@ -74,6 +75,8 @@ class ChainStats(C.Structure):
         ("samples", C.c_longlong), ("replay_consumed", C.c_ulonglong),
         ("widom_insert", C.c_double), ("widom_delete", C.c_double),
         ("widom_insertions", C.c_longlong), ("widom_deletions", C.c_longlong),
+        ("accept_vol", C.c_longlong), ("reject_vol", C.c_longlong), ("n_vol_changes", C.c_longlong),
+        ("volume", C.c_double), ("width", C.c_double), ("dv", C.c_double), ("energy_as_shipped", C.c_double),
         ("dr_used", C.c_double),
     ]
 
@@ -122,10 +125,12 @@ PROTOTYPES = {
     "mcpm_set_positions_all": (C.c_int, [C.c_void_p, _ip, _dp, _dp, _dp]),
     "mcpm_get_positions_all": (C.c_int, [C.c_void_p, _ip, _dp, _dp, _dp]),
     "mcpm_particle_energy": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, C.POINTER(ParticleEnergy), C.POINTER(ParticleEnergy)]),
+    "mcpm_particle_energy_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _ip, _dp, C.POINTER(ParticleEnergy), C.POINTER(ParticleEnergy)]),
     "mcpm_box_energy": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(BoxEnergy), _dp, _dp]),
     "mcpm_box_energy_all": (C.c_int, [C.c_void_p, C.POINTER(BoxEnergy)]),
     "mcpm_use_speculation": (C.c_int, [C.c_void_p, C.c_int]),
     "mcpm_use_energy_cache": (C.c_int, [C.c_void_p, C.c_int]),
+    "mcpm_use_pool": (C.c_int, [C.c_void_p, C.c_int]),
     "mcpm_get_energy_cache": (C.c_int, [C.c_void_p, C.c_int, _dp, _ip]),
     "mcpm_use_cell_list": (C.c_int, [C.c_void_p, C.c_int]),
     "mcpm_apply_move": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp]),

@@ -99,6 +99,16 @@ class Engine:
         f = lambda e: np.array([e.pair, e.many_body, e.wall, e.energy])
         return f(cur), f(mv)
 
+    def particle_energy_batch(self, chain, index, trial=None):
+        """-> (cur, moved), each [count, 4] = {pair, many_body, wall, energy}; see mcpm_particle_energy_batch."""
+        index = np.ascontiguousarray(index, dtype=np.int32)
+        m = len(index)
+        t = np.ascontiguousarray(trial, dtype=np.float64).reshape(m, 3) if trial is not None else None
+        cur = (ParticleEnergy * max(m, 1))(); mv = (ParticleEnergy * max(m, 1))()
+        check(self.L.mcpm_particle_energy_batch(self.h, chain, m, index.ctypes.data_as(C.POINTER(C.c_int)), _p(t) if t is not None else None, cur, mv))
+        f = lambda arr: np.array([[e.pair, e.many_body, e.wall, e.energy] for e in arr[:m]]).reshape(m, 4)
+        return f(cur), f(mv)
+
     def box_energy(self, chain, per_particle=True):
         out = BoxEnergy()
         pp = np.zeros(self.capacity); pw = np.zeros(self.capacity)
@@ -129,6 +139,9 @@ class Engine:
         ids = np.ascontiguousarray(ids, dtype=np.uint32)
         assert len(ids) == self.n_chains
         check(self.L.mcpm_set_stream_ids(self.h, ids.ctypes.data_as(C.POINTER(C.c_uint))))
+
+    def use_pool(self, warps=16):
+        check(self.L.mcpm_use_pool(self.h, int(warps)))
 
     def use_energy_cache(self, enable=True):
         check(self.L.mcpm_use_energy_cache(self.h, 1 if enable else 0))

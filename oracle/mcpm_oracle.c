@@ -39,6 +39,8 @@ struct orc_chain {
     double dr;
     /* per-set stats (MC.h:35-44, MC.cpp:81-98) */
     long long acceptance, rejection, n_displacements, accept_swap, reject_swap, n_swaps;
+    long long acceptance_vol, rejection_vol, n_vol_changes;   /* MC.h:37-38 */
+    double dv;                                                /* Simulation::dv */
     /* run totals */
     long long tot_disp, tot_disp_acc, tot_swap, tot_swap_acc, recomputes;
     unsigned long long pair_evals;
@@ -151,10 +153,19 @@ static double ipow(double v, int p) {
     for (int i = 1; i <= p; i++) r *= v;
     return r;
 }
-/* MC::ComputeVolume, read.cpp:26-35 (slit and bulk branches) */
+/* MC::ComputeVolume, read.cpp:26-35 */
 double orc_volume(const orc_system* s) {
+    if (s->geometry == 3) return (M_PI / 6.) * ipow(s->width[2], 3);
+    if (s->geometry == 2) return (M_PI / 4.) * ipow(s->width[2], 2) * s->width[0];
     if (s->geometry == 1) return s->width[0] * s->width[1] * s->width[2];
     return ipow(s->width[2], 3);
+}
+/* MC::ComputeBoxWidth, read.cpp:19-25 */
+static double box_width(const orc_system* s, double volume) {
+    if (s->geometry == 3) return 2 * cbrt(3 * volume / (4 * M_PI));
+    if (s->geometry == 2) return 2 * sqrt(volume / (M_PI * s->width[0]));
+    if (s->geometry == 1) return volume / (s->width[0] * s->width[1]);
+    return cbrt(volume);
 }
 /* SwapParticle's activity, moves.cpp:296-298 */
 double orc_swap_zz(const orc_system* s) {
@@ -183,6 +194,39 @@ static double lj126(orc_chain* c, double xi, double yi, double zi) {
     c->pair_evals += (unsigned long long)c->n;
     return energy;
 }
+/* MC::HardSphere_Pot, potentials.cpp:40-54: the finite INT_MAX per partner within sigma; NO self-exclusion — a stored particle
+ * finds its own record at distance 0 and counts itself (quirk Q17). */
+static double hard_sphere(orc_chain* c, double xi, double yi, double zi) {
+    double sig = c->sys.sig_ff, energy = 0.;
+    for (int j = 0; j < c->n; j++) {
+        double rij = neigh_distance(c, xi, yi, zi, c->x[j], c->y[j], c->z[j]);
+        if (rij <= sig) energy += INT_MAX;
+    }
+    c->pair_evals += (unsigned long long)c->n;
+    return energy;
+}
+/* MC::SphericalLJ_Pot, potentials.cpp:474-504 (Baksh & Yang 1991) */
+static double sphere_wall(const orc_system* s, double x, double y, double z) {
+    double sizeR = s->width[2] * 0.5, dens = s->rho_s, eps = s->eps_sf, sig = s->sig_sf;
+    double u1 = 0, u2 = 0;
+    double xPos = x - 0.5 * s->width[0], yPos = y - 0.5 * s->width[1], zPos = z - 0.5 * s->width[2];
+    double r = sqrt(ipow(xPos, 2) + ipow(yPos, 2) + ipow(zPos, 2));
+    dens *= sig * sig;
+    sizeR /= sig;
+    r /= sig;
+    double xx = sizeR - r;
+    for (int i = 0; i < 10; i++) {
+        u1 += 1. / ipow(sizeR, i) / ipow(xx, 10 - i);
+        u1 += ipow(-1.0, i) / ipow(sizeR, i) / ipow(xx - 2.0 * sizeR, 10 - i);
+        if (i < 4) {
+            u2 += 1. / ipow(sizeR, i) / ipow(xx, 4 - i);
+            u2 += ipow(-1.0, i) / ipow(sizeR, i) / ipow(xx - 2.0 * sizeR, 4 - i);
+        }
+    }
+    double usf = (2. / 5.) * u1 - u2;
+    usf *= 2. * M_PI * eps * dens;
+    return usf;
+}
 /* MC::SlitLJ_Pot, potentials.cpp:381-402 */
 double orc_slit_wall(const orc_system* s, double zabs) {
     int nLayers = s->n_layers;
@@ -201,15 +245,22 @@ double orc_slit_wall(const orc_system* s, double zabs) {
 }
 /* MC::EnergyOfParticle, energy.cpp:43-105 for a position (x,y,z): out-of-pore guard adds the FINITE
  * INT_MAX and the wall term is still added (Q6); pair term from LJ126_Pot. */
-static void energy_at(orc_chain* c, double x, double y, double z, double* pair, double* wall) {
+static double wall_at(const orc_system* s, double x, double y, double z) {
     double boxE = 0., sqrDist = 0.;
-    double sqrPoreRadius = c->sys.width[2] * c->sys.width[2] * 0.25;
-    double zPos = z - 0.5 * c->sys.width[2];
-    if (c->sys.geometry == 1) sqrDist = zPos * zPos;
+    double sqrPoreRadius = s->width[2] * s->width[2] * 0.25;
+    double xPos = x - 0.5 * s->width[0], yPos = y - 0.5 * s->width[1], zPos = z - 0.5 * s->width[2];
+    if (s->geometry == 3) sqrDist = xPos * xPos + yPos * yPos + zPos * zPos;     /* energy.cpp:61-63 */
+    else if (s->geometry == 2) sqrDist = yPos * yPos + zPos * zPos;
+    else if (s->geometry == 1) sqrDist = zPos * zPos;
     if ((sqrDist > sqrPoreRadius) || (sqrDist < 0)) boxE = INT_MAX;
-    if (c->sys.wall_kind == 1 && c->sys.geometry == 1) boxE += orc_slit_wall(&c->sys, z);
-    *pair = lj126(c, x, y, z);
-    *wall = boxE;
+    if (s->wall_kind == 2 && s->geometry == 3) boxE += sphere_wall(s, x, y, z);   /* energy.cpp:69-77 */
+    else if (s->wall_kind == 1 && s->geometry == 1) boxE += orc_slit_wall(s, z);
+    return boxE;
+}
+double orc_wall_energy(orc_chain* c, double x, double y, double z) { return wall_at(&c->sys, x, y, z); }
+static void energy_at(orc_chain* c, double x, double y, double z, double* pair, double* wall) {
+    *wall = wall_at(&c->sys, x, y, z);
+    *pair = c->sys.pair_kind == 1 ? hard_sphere(c, x, y, z) : lj126(c, x, y, z);   /* energy.cpp:79-83 */
 }
 /* EnergyOfParticle on a stored slot: results are written into the particle record (energy.cpp:102-104). */
 static void energy_of_slot(orc_chain* c, int slot) {
@@ -273,6 +324,25 @@ static void wrap(const orc_chain* c, double* x, double* y, double* z) {
 
 /* MC::InsertParticle slit/bulk branches, moves.cpp:46-54: x,y,z = u*width, three draws in that order. */
 static void insert_particle(orc_chain* c, int slot) {
+    if (c->sys.geometry == 3) {          /* moves.cpp:25-36: radius, theta, phi — NOT uniform in volume, as in the reference */
+        double radius = orc_random(c) * c->sys.width[2] * 0.5;
+        double theta = orc_random(c) * M_PI;
+        double phi = orc_random(c) * 2 * M_PI;
+        c->x[slot] = radius * sin(theta) * cos(phi);
+        c->y[slot] = radius * sin(theta) * sin(phi);
+        c->z[slot] = radius * cos(theta);
+        c->x[slot] += 0.5 * c->sys.width[0]; c->y[slot] += 0.5 * c->sys.width[1]; c->z[slot] += 0.5 * c->sys.width[2];
+        return;
+    }
+    if (c->sys.geometry == 2) {          /* moves.cpp:37-45: rho, phi, then x */
+        double rho = orc_random(c) * c->sys.width[2] * 0.5;
+        double phi = orc_random(c) * 2 * M_PI;
+        c->x[slot] = (orc_random(c) - 0.5) * c->sys.width[0];
+        c->y[slot] = rho * sin(phi);
+        c->z[slot] = rho * cos(phi);
+        c->x[slot] += 0.5 * c->sys.width[0]; c->y[slot] += 0.5 * c->sys.width[1]; c->z[slot] += 0.5 * c->sys.width[2];
+        return;
+    }
     c->x[slot] = orc_random(c) * c->sys.width[0];
     c->y[slot] = orc_random(c) * c->sys.width[1];
     c->z[slot] = orc_random(c) * c->sys.width[2];
@@ -365,13 +435,49 @@ static int swap_particle(orc_chain* c) {
     }
     return (3 << 1);
 }
-/* Body of the step loop, main.cpp:67-71 (volume moves are out of scope: n_vol must be 0). */
+/* MC::ChangeVolume, NPT branch (extPress > 0), single box, moves.cpp:191-231.  Three draws: box, log-volume step, accept.
+ * As shipped: RescaleCenterOfMass (moves.cpp:88-117) is called BEFORE the widths change, so its ratio is 1 and the coordinates are
+ * NOT rescaled (quirk Q18); all three widths are set to ComputeBoxWidth (bulk: cbrt V); the old energy is the RUNNING box energy. */
+static int change_volume(orc_chain* c) {
+    double T = c->sys.temperature;
+    double extPress = c->sys.pressure / ORC_KB * 1e-30; /* K/AA^3 */
+    c->n_vol_changes++;
+    if (!(extPress > 0)) return (4 << 1);               /* Gibbs-NVT branch: two boxes, out of scope */
+    (void)(int)(orc_random(c) * 1);                      /* do { ithBox = int(Random()*nBoxes) } while (fix) */
+    double oldW[3] = {c->sys.width[0], c->sys.width[1], c->sys.width[2]}, oldVol = c->volume;
+    double oldB[4] = {c->b_pair, c->b_many, c->b_wall, c->b_energy};
+    double logNewVol = log(c->volume) + (orc_random(c) - 0.5) * c->dv;
+    c->volume = exp(logNewVol);
+    c->sys.width[2] = box_width(&c->sys, c->volume);
+    c->sys.width[0] = c->sys.width[1] = c->sys.width[2];
+    double *sp = malloc(sizeof(double) * 3 * (size_t)(c->n + 1));   /* BoxEnergy rewrites every particle record */
+    for (int j = 0; j < c->n; j++) { sp[3 * j] = c->pe_pair[j]; sp[3 * j + 1] = c->pe_wall[j]; sp[3 * j + 2] = c->pe_tot[j]; }
+    box_energy(c);
+    double deltaE0 = c->b_energy - oldB[3];
+    double deltaVol0 = c->volume - oldVol;
+    double arg0 = deltaE0 + extPress * deltaVol0 - (c->n + 1) * log(c->volume / oldVol) * T;
+    int acc;
+    if (orc_random(c) > exp(-arg0 / T)) {
+        c->rejection_vol++;
+        c->sys.width[0] = oldW[0]; c->sys.width[1] = oldW[1]; c->sys.width[2] = oldW[2]; c->volume = oldVol;    /* box = oldBox0 */
+        c->b_pair = oldB[0]; c->b_many = oldB[1]; c->b_wall = oldB[2]; c->b_energy = oldB[3];
+        for (int j = 0; j < c->n; j++) { c->pe_pair[j] = sp[3 * j]; c->pe_wall[j] = sp[3 * j + 1]; c->pe_tot[j] = sp[3 * j + 2]; }
+        acc = 0;
+    } else {
+        c->acceptance_vol++;
+        c->e_pair = c->b_pair; c->e_wall = c->b_wall; c->e_energy = c->b_energy;   /* exact: the fresh BoxEnergy */
+        acc = 1;
+    }
+    free(sp);
+    return (4 << 1) | acc;
+}
+/* Body of the step loop, main.cpp:67-71. */
 int orc_step(orc_chain* c, int correct) {
     int nD = c->sys.n_disp, nV = c->sys.n_vol, nS = c->sys.n_swap, code = 0;
     if (c->rng_mode == RNG_PHILOX) c->ph_slot = 0;
     double r = orc_random(c) * (nD + nV + nS);
     if (r <= nD) code = move_particle(c);
-    else if (r <= nD + nV) code = (4 << 1);
+    else if (r <= nD + nV) code = change_volume(c);
     else if (r <= nD + nV + nS) code = swap_particle(c);
     if (correct) correct_energy(c);
     if (c->rng_mode == RNG_PHILOX) c->ph_step++;
@@ -395,6 +501,8 @@ void orc_reset_stats(orc_chain* c) {
     c->widom_insert = c->widom_delete = 0.;
     c->acceptance = c->rejection = 0;
     c->n_displacements = 1;
+    c->n_vol_changes = 1;
+    c->acceptance_vol = c->rejection_vol = 0;
 }
 /* MC::AdjustMCMoves displacement part, moves.cpp:68-78 */
 void orc_adjust(orc_chain* c, int set) {
@@ -403,6 +511,11 @@ void orc_adjust(orc_chain* c, int set) {
             double ratio = c->acceptance * 1. / (1. * c->n_displacements);
             if (ratio < 0.2) c->dr /= 1.1;
             else c->dr *= 1.1;
+        }
+        if (c->sys.n_vol > 0) {                         /* volume part, moves.cpp:79-84: every set, not only during equilibration */
+            double ratio = c->acceptance_vol * 1. / (1. * c->n_vol_changes);
+            if (ratio < 0.5 && c->dv > 1e-3) c->dv /= 1.1;
+            else c->dv *= 1.1;
         }
     }
 }
@@ -482,6 +595,10 @@ void orc_rdf(orc_chain* c, double* hist) {
     if (hist) memcpy(hist, c->rdf, sizeof(double) * ORC_NBINS);
 }
 void orc_set_dr(orc_chain* c, double dr) { c->dr = dr; }
+void orc_get_volume_state(const orc_chain* c, double d[6], long long i[3]) {
+    d[0] = c->volume; d[1] = c->sys.width[0]; d[2] = c->sys.width[1]; d[3] = c->sys.width[2]; d[4] = c->dv; d[5] = c->b_energy;
+    i[0] = c->acceptance_vol; i[1] = c->rejection_vol; i[2] = c->n_vol_changes;
+}
 void orc_rdf_reset(orc_chain* c) { memset(c->rdf, 0, sizeof(c->rdf)); }
 void orc_set_sample_rdf(orc_chain* c, int on) { c->sample_rdf = on; }
 void orc_get_rdf(const orc_chain* c, double* hist100) { memcpy(hist100, c->rdf, sizeof(double) * ORC_NBINS); }
@@ -495,13 +612,15 @@ orc_chain* orc_create(const orc_system* sys, int capacity) {
     orc_chain* c = (orc_chain*)calloc(1, sizeof(orc_chain));
     c->sys = *sys;
     /* PBC flags from the geometry, read.cpp:146-162 */
-    c->pbc[0] = 1; c->pbc[1] = 1; c->pbc[2] = (sys->geometry == 1) ? 0 : 1;
+    c->pbc[0] = (sys->geometry != 3); c->pbc[1] = (sys->geometry == 0 || sys->geometry == 1); c->pbc[2] = (sys->geometry == 0);
     c->volume = orc_volume(sys);
     c->cap = capacity + 2;
     size_t bytes = sizeof(double) * (size_t)c->cap;
     c->x = (double*)calloc(1, bytes); c->y = (double*)calloc(1, bytes); c->z = (double*)calloc(1, bytes);
     c->pe_pair = (double*)calloc(1, bytes); c->pe_wall = (double*)calloc(1, bytes); c->pe_tot = (double*)calloc(1, bytes);
     c->dr = sys->dr;
+    c->dv = sys->dv > 0 ? sys->dv : 1e-3;            /* MC.cpp:33 */
+    c->n_vol_changes = 0;
     c->bar_c = 1.; c->widom_insertions = c->widom_deletions = 1; /* MC.cpp:25-28 */
     orc_rng_mt(c, 5489ULL);
     return c;

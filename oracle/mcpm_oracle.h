@@ -24,18 +24,21 @@ extern "C" {
 
 /* Same field order as oracle/ref_harness.cpp::mcref_system. */
 typedef struct {
-    int geometry;   /* 0 = bulk (PBC x,y,z), 1 = slit (PBC x,y; walls at z=0 and z=H)  read.cpp:146-162 */
-    int wall_kind;  /* 0 = none, 1 = "lj" + slit -> SlitLJ_Pot                       energy.cpp:75-76 */
+    int geometry;   /* 0 = bulk (PBC x,y,z), 1 = slit (PBC x,y; walls at z=0 and z=H), 2 = cylinder (PBC x), 3 = sphere (no PBC)
+                       read.cpp:128-162 */
+    int wall_kind;  /* 0 = none, 1 = "lj" + slit -> SlitLJ_Pot, 2 = "lj" + sphere -> SphericalLJ_Pot   energy.cpp:69-77 */
     int n_layers;   /* nLayersPerWall */
     int n_disp, n_vol, n_swap; /* move weights, main.cpp:67-70 */
     int n_equil_sets;
-    int _pad;
+    int pair_kind;  /* 0 = "lj" -> LJ126_Pot, 1 = "hs" -> HardSphere_Pot                 energy.cpp:80-83 */
     double width[3];
     double temperature;
     double eps_ff, sig_ff, rcut;
     double molar_mass, mu;
     double eps_sf, sig_sf, rho_s, delta;
     double dr;
+    double pressure; /* ExternalPressure in Pa (<= 0: none), read.cpp:64; NPT volume moves moves.cpp:191-231 */
+    double dv;       /* Simulation::dv, log-volume step (MC.cpp:33: 1e-3) */
 } orc_system;
 
 typedef struct orc_chain orc_chain;
@@ -72,6 +75,9 @@ void orc_initial_config(orc_chain* c, int n);                              /* mo
 int orc_step(orc_chain* c, int correct_energy);
 long long orc_run(orc_chain* c, long long nsteps, int correct_energy, unsigned char* trace);
 void orc_set_dr(orc_chain* c, double dr);                                  /* Simulation::dr, restart / tests */
+/* dout = {volume, width[0], width[1], width[2], dv, as-shipped running energy}; iout = {acceptanceVol, rejectionVol, nVolChanges} */
+void orc_get_volume_state(const orc_chain* c, double dout[6], long long iout[3]);
+double orc_wall_energy(orc_chain* c, double x, double y, double z);        /* boxE of EnergyOfParticle at a position */
 void orc_reset_stats(orc_chain* c);                                        /* MC.cpp:81-98 */
 void orc_adjust(orc_chain* c, int set);                                    /* moves.cpp:68-78 */
 /* Sets first_set..first_set+n_sets-1: ResetStats; steps; sampling when set > n_equil_sets; adjust.

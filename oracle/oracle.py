@@ -21,6 +21,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIBORACLE = os.path.join(HERE, "liboracle.so")
 LIBMCREF = os.path.join(HERE, "_ref", "libmcref.so")
+LIBMCREF_NDEBUG = os.path.join(HERE, "_ref", "libmcref_ndebug.so")   # same sources, -DNDEBUG (MC::ChangeVolume aborts on an Eigen assertion otherwise)
+LIBMCREF_BOUND = os.path.join(HERE, "_ref", "libmcref_bound.so")   # the reference with its energy seam bound to libmcpm.so
 SIMULATE = os.path.join(HERE, "_ref", "simulate")
 REFERENCE_ROOT = "/root/reference"
 
@@ -33,19 +35,17 @@ class System(C.Structure):
     _fields_ = [
         ("geometry", C.c_int), ("wall_kind", C.c_int), ("n_layers", C.c_int),
         ("n_disp", C.c_int), ("n_vol", C.c_int), ("n_swap", C.c_int),
-        ("n_equil_sets", C.c_int), ("_pad", C.c_int),
+        ("n_equil_sets", C.c_int), ("pair_kind", C.c_int),
         ("width", C.c_double * 3), ("temperature", C.c_double),
         ("eps_ff", C.c_double), ("sig_ff", C.c_double), ("rcut", C.c_double),
         ("molar_mass", C.c_double), ("mu", C.c_double),
         ("eps_sf", C.c_double), ("sig_sf", C.c_double), ("rho_s", C.c_double), ("delta", C.c_double),
-        ("dr", C.c_double),
+        ("dr", C.c_double), ("pressure", C.c_double), ("dv", C.c_double),
     ]
 
     def as_dict(self):
         d = {}
         for name, _ in self._fields_:
-            if name == "_pad":
-                continue
             v = getattr(self, name)
             d[name] = list(v) if name == "width" else v
         return d
@@ -128,6 +128,9 @@ class COracle:
             L.orc_run.restype = C.c_longlong
             L.orc_reset_stats.argtypes = [C.c_void_p]
             L.orc_set_dr.argtypes = [C.c_void_p, C.c_double]
+            L.orc_get_volume_state.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_longlong)]
+            L.orc_wall_energy.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+            L.orc_wall_energy.restype = C.c_double
             L.orc_adjust.argtypes = [C.c_void_p, C.c_int]
             L.orc_run_sets.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_void_p]
             L.orc_get_state.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_longlong)]
@@ -229,6 +232,15 @@ class COracle:
     def set_dr(self, dr):
         self.L.orc_set_dr(self.h, dr)
 
+    def volume_state(self):
+        d = np.zeros(6); i = np.zeros(3, dtype=np.int64)
+        self.L.orc_get_volume_state(self.h, d.ctypes.data_as(_dp), i.ctypes.data_as(C.POINTER(C.c_longlong)))
+        return {"volume": d[0], "width": [d[1], d[2], d[3]], "dv": d[4], "as_shipped_energy": d[5],
+                "acceptance_vol": int(i[0]), "rejection_vol": int(i[1]), "n_vol_changes": int(i[2])}
+
+    def wall_energy(self, x, y, z):
+        return self.L.orc_wall_energy(self.h, x, y, z)
+
     def adjust(self, set_index):
         self.L.orc_adjust(self.h, set_index)
 
@@ -298,15 +310,22 @@ def have_reference_lib() -> bool:
     return os.path.exists(LIBMCREF)
 
 
-class RefOracle:
-    """The compiled, unmodified reference behind the subclass harness.  ~5.6 GB per instance."""
+def have_bound_reference_lib() -> bool:
+    return os.path.exists(LIBMCREF_BOUND)
 
-    _lib = None
+
+class RefOracle:
+    """The compiled, unmodified reference behind the subclass harness.  ~5.6 GB per instance.
+    bound=True loads oracle/_ref/libmcref_bound.so instead: the same reference objects with src/energy.cpp replaced by
+    oracle/energy_bound.cpp, i.e. every energy comes from libmcpm.so (needs a GPU)."""
+
+    _libs = {}
 
     @classmethod
-    def lib(cls):
-        if cls._lib is None:
-            L = C.CDLL(LIBMCREF)
+    def lib(cls, bound=False, ndebug=False):
+        path = LIBMCREF_BOUND if bound else (LIBMCREF_NDEBUG if ndebug else LIBMCREF)
+        if path not in cls._libs:
+            L = C.CDLL(path)
             L.mcref_create.restype = C.c_void_p
             L.mcref_destroy.argtypes = [C.c_void_p]
             L.mcref_setup.argtypes = [C.c_void_p, C.POINTER(System)]
@@ -322,6 +341,7 @@ class RefOracle:
             L.mcref_box_energy.argtypes = [C.c_void_p, _dp, _dp, _dp]
             L.mcref_get_state.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_int)]
             L.mcref_reset_stats.argtypes = [C.c_void_p]
+            L.mcref_volume_state.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_int)]
             L.mcref_adjust.argtypes = [C.c_void_p, C.c_int]
             L.mcref_initial_config.argtypes = [C.c_void_p, C.c_int]
             L.mcref_step.argtypes = [C.c_void_p, C.c_int]
@@ -343,11 +363,13 @@ class RefOracle:
             L.mcref_volume.restype = C.c_double
             L.mcref_swap_zz.argtypes = [C.c_void_p]
             L.mcref_swap_zz.restype = C.c_double
-            cls._lib = L
-        return cls._lib
+            L.mcref_is_bound.argtypes = [_dp]
+            L.mcref_is_bound.restype = C.c_int
+            cls._libs[path] = L
+        return cls._libs[path]
 
-    def __init__(self, system: System | None = None):
-        self.L = self.lib()
+    def __init__(self, system: System | None = None, bound: bool = False, ndebug: bool = False):
+        self.L = self.lib(bound, ndebug)
         self.h = self.L.mcref_create()
         self.capacity = 100000
         if system is not None:
@@ -440,6 +462,20 @@ class RefOracle:
 
     def rdf_reset(self):
         self.L.mcref_rdf_reset(self.h)
+
+    def volume_state(self):
+        d = np.zeros(6); i = np.zeros(3, dtype=np.int32)
+        self.L.mcref_volume_state(self.h, d.ctypes.data_as(_dp), i.ctypes.data_as(C.POINTER(C.c_int)))
+        return {"volume": d[0], "width": [d[1], d[2], d[3]], "dv": d[4], "as_shipped_energy": d[5],
+                "acceptance_vol": int(i[0]), "rejection_vol": int(i[1]), "n_vol_changes": int(i[2])}
+
+    def bound_stats(self):
+        """None for the stock build; for the bound build the binding's call counters and seconds."""
+        out = np.zeros(6)
+        if not self.L.mcref_is_bound(out.ctypes.data_as(_dp)):
+            return None
+        return {"particle_calls": int(out[0]), "particle_seconds": out[1], "box_calls": int(out[2]), "box_seconds": out[3],
+                "mirrored": int(out[4]), "uploads": int(out[5])}
 
     def read_input(self, path):
         s = System(); n0 = C.c_int(0)

@@ -30,30 +30,38 @@ extern "C" {
 
 // Same field order as oracle/mcpm_oracle.h::orc_system (single species, single box).
 struct mcref_system {
-    int geometry;        // 0 = bulk, 1 = slit
-    int wall_kind;       // 0 = none, 1 = "lj" slit wall (SlitLJ_Pot)
+    int geometry;        // 0 = bulk, 1 = slit, 2 = cylinder, 3 = sphere
+    int wall_kind;       // 0 = none, 1 = "lj" slit wall (SlitLJ_Pot), 2 = "lj" sphere wall (SphericalLJ_Pot)
     int n_layers;
     int n_disp, n_vol, n_swap;  // move weights (sim.nDispAttempts ...)
     int n_equil_sets;
-    int _pad;
+    int pair_kind;       // 0 = "lj", 1 = "hs"
     double width[3];
     double temperature;
     double eps_ff, sig_ff, rcut;
     double molar_mass, mu;
     double eps_sf, sig_sf, rho_s, delta;
     double dr;
+    double pressure;     // Pa (thermoSys.press); <= 0: none
+    double dv;           // sim.dv (<= 0: the constructor's 1e-3)
 };
+
+// Hooks of the BOUND build (oracle/energy_bound.cpp, `make ref_bound`): absent (null) in the stock build.
+void mcref_bound_reset(void) __attribute__((weak));
+void mcref_bound_invalidate(void) __attribute__((weak));
+void mcref_bound_stats(double out[6]) __attribute__((weak));
 
 }  // extern "C"
 
 struct Oracle : public MC {
     void setup(const mcref_system& s) {
+        if (mcref_bound_reset) mcref_bound_reset();          // a new system: the binding creates a fresh GPU context
         thermoSys.nBoxes = 1;
         thermoSys.nSpecies = 1;
         thermoSys.temp = s.temperature;
         thermoSys.nParts = 0;
         fluid(0).name = "a";
-        fluid(0).vdwPot(0) = "lj";
+        fluid(0).vdwPot(0) = s.pair_kind == 1 ? "hs" : "lj";
         fluid(0).sigma(0) = s.sig_ff;
         fluid(0).epsilon(0) = s.eps_ff;
         fluid(0).rcut(0) = s.rcut;
@@ -61,17 +69,20 @@ struct Oracle : public MC {
         fluid(0).mu = s.mu;
         Box& b = box(0);
         b.name = "box";
-        b.geometry = s.geometry == 1 ? "slit" : "bulk";
+        b.geometry = s.geometry == 1 ? "slit" : (s.geometry == 2 ? "cylinder" : (s.geometry == 3 ? "sphere" : "bulk"));
         for (int k = 0; k < 3; k++) b.width(k) = s.width[k];
-        if (s.geometry == 1) { b.PBC(0) = 1; b.PBC(1) = 1; b.PBC(2) = 0; }
-        else { b.PBC(0) = 1; b.PBC(1) = 1; b.PBC(2) = 1; }
+        // PBC flags as ReadInputFile derives them from the geometry, src/read.cpp:146-162
+        b.PBC(0) = s.geometry != 3; b.PBC(1) = (s.geometry == 0 || s.geometry == 1); b.PBC(2) = s.geometry == 0;
+        b.fix = false;
+        thermoSys.press = s.pressure > 0 ? s.pressure : -1.;
+        sim.dv(0) = s.dv > 0 ? s.dv : 1e-3;
         b.volume = ComputeVolume(b);
         thermoSys.volume = b.volume;
         b.maxRcut = s.rcut;
         b.solidDens = s.rho_s;
         b.nLayersPerWall = s.n_layers;
         b.deltaLayers = s.delta;
-        b.fluid(0).vdwPot(0) = s.wall_kind == 1 ? "lj" : "";
+        b.fluid(0).vdwPot(0) = (s.wall_kind == 1 || s.wall_kind == 2) ? "lj" : "";
         b.fluid(0).sigma(0) = s.sig_sf;
         b.fluid(0).epsilon(0) = s.eps_sf;
         b.fluid(0).mu = s.mu;
@@ -85,6 +96,7 @@ struct Oracle : public MC {
         sim.nSwapAttempts = s.n_swap;
     }
     void set_positions(int n, const double* x, const double* y, const double* z) {
+        if (mcref_bound_invalidate) mcref_bound_invalidate();   // the whole configuration changed behind the binding's back
         for (int k = 0; k < n; k++) {
             Particle& p = box(0).fluid(0).particle(k + 1);
             p.x = x[k]; p.y = y[k]; p.z = z[k];
@@ -116,12 +128,14 @@ struct Oracle : public MC {
         Particle free0 = box(0).fluid(0).particle(n0 + 1);  // slot an insertion attempt would overwrite
         int move = -1;
         double r = Random() * (nD + nV + nS);
+        int vacc0 = stats.acceptanceVol(0);
         if (r <= nD) { MoveParticle(); move = 0; }
         else if (r <= nD + nV) { ChangeVolume(); move = 4; }
         else if (r <= nD + nV + nS) { SwapParticle(); move = 1; }
         if (correct_energy) CorrectEnergy();
         int accepted = 0;
         if (move == 0) accepted = stats.acceptance(0) - acc0;
+        else if (move == 4) accepted = stats.acceptanceVol(0) - vacc0;
         else if (move == 1) {
             accepted = stats.acceptSwap - sw0;
             if (stats.nSwaps == nsw0) move = 3;
@@ -171,6 +185,10 @@ struct Oracle : public MC {
         iout[3] = stats.nDisplacements(0); iout[4] = stats.acceptSwap; iout[5] = stats.rejectSwap;
         iout[6] = stats.nSwaps; iout[7] = thermoSys.nParts;
     }
+    void volume_state(double d[6], int i[3]) {
+        d[0] = box(0).volume; d[1] = box(0).width(0); d[2] = box(0).width(1); d[3] = box(0).width(2); d[4] = sim.dv(0); d[5] = box(0).energy;
+        i[0] = stats.acceptanceVol(0); i[1] = stats.rejectionVol(0); i[2] = stats.nVolChanges;
+    }
     void reset_stats() { ResetStats(); }
     void adjust(int set) { AdjustMCMoves((size_t)set); }
     void initial_config(int n) {
@@ -208,8 +226,10 @@ struct Oracle : public MC {
         ReadInputFile(std::string(path));
         if (thermoSys.nBoxes != 1 || thermoSys.nSpecies != 1) return -1;
         const Box& b = box(0);
-        s->geometry = b.geometry == "slit" ? 1 : (b.geometry == "bulk" ? 0 : -1);
-        s->wall_kind = (box(0).fluid(0).vdwPot(0) == "lj" && b.geometry == "slit") ? 1 : 0;
+        s->geometry = b.geometry == "slit" ? 1 : (b.geometry == "bulk" ? 0 : (b.geometry == "cylinder" ? 2 : (b.geometry == "sphere" ? 3 : -1)));
+        s->wall_kind = (box(0).fluid(0).vdwPot(0) == "lj" && b.geometry == "slit") ? 1 : ((box(0).fluid(0).vdwPot(0) == "lj" && b.geometry == "sphere") ? 2 : 0);
+        s->pair_kind = fluid(0).vdwPot(0) == "hs" ? 1 : 0;
+        s->pressure = thermoSys.press; s->dv = sim.dv(0);
         s->n_layers = b.nLayersPerWall;
         s->n_disp = sim.nDispAttempts; s->n_vol = sim.nVolAttempts; s->n_swap = sim.nSwapAttempts;
         s->n_equil_sets = (int)sim.nEquilSets;
@@ -258,6 +278,7 @@ void mcref_box_energy(void* h, double out[4], double* per_pair, double* per_wall
 }
 void mcref_get_state(void* h, double out[8], int iout[8]) { ops(h)->get_state(out, iout); }
 void mcref_reset_stats(void* h) { ops(h)->reset_stats(); }
+void mcref_volume_state(void* h, double d[6], int i[3]) { ops(h)->volume_state(d, i); }
 void mcref_adjust(void* h, int set) { ops(h)->adjust(set); }
 void mcref_initial_config(void* h, int n) { ops(h)->initial_config(n); }
 int mcref_step(void* h, int correct_energy) { return ops(h)->step(correct_energy); }
@@ -285,6 +306,12 @@ void mcref_rdf_reset(void* h) { ops(h)->rdf_reset(); }
 int mcref_read_input(void* h, const char* path, mcref_system* s, int* n0, char* proj, char* fname,
                      char* bname, double sets[4]) {
     return ops(h)->read_input(path, s, n0, proj, fname, bname, sets);
+}
+// 1 if this library is the bound build; out = {EnergyOfParticle calls, seconds, BoxEnergy calls, seconds, slots mirrored, uploads}
+int mcref_is_bound(double out[6]) {
+    if (!mcref_bound_stats) return 0;
+    if (out) mcref_bound_stats(out);
+    return 1;
 }
 double mcref_volume(void* h) { return ops(h)->volume(); }
 double mcref_swap_zz(void* h) { return ops(h)->swap_zz(); }

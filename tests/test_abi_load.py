@@ -29,7 +29,7 @@ def test_python_prototypes_cover_header(mcpm):
 
 def test_struct_layouts_match_oracle(mcpm):
     from conftest import O
-    assert ctypes.sizeof(mcpm.SystemDesc) == ctypes.sizeof(O.System) == 8 * 4 + 14 * 8
+    assert ctypes.sizeof(mcpm.SystemDesc) == ctypes.sizeof(O.System) == 8 * 4 + 16 * 8
     for (a, ta), (b, tb) in zip(mcpm.SystemDesc._fields_, O.System._fields_):
         assert getattr(mcpm.SystemDesc, a).offset == getattr(O.System, b).offset
 

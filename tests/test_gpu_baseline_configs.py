@@ -24,6 +24,13 @@ def close(a, b, rtol=RTOL):
     return np.allclose(a, b, rtol=rtol, atol=0)
 
 
+def close_scaled(a, b, rtol=RTOL):
+    """Per-particle energies: a particle whose attractive and repulsive terms cancel (|sum| << |terms|) carries the rounding error
+    of its terms, so the error bound is relative to the typical magnitude, not to the individual sum."""
+    a = np.asarray(a); b = np.asarray(b)
+    return bool(np.all(np.abs(a - b) <= rtol * np.maximum(np.abs(b), np.mean(np.abs(b)))))
+
+
 def first_divergence(a, b):
     d = np.nonzero(a != b)[0]
     return int(d[0]) if len(d) else -1
@@ -75,7 +82,7 @@ def test_c3_energies_on_the_bench_fixture(mcpm, c3):
         e.set_system(s)
         e.set_positions(0, x, y, z)
         box, pp, pw = e.box_energy(0)
-        assert close(box, obox) and close(pp, opp) and close(pw, opw)
+        assert close(box, obox) and close_scaled(pp, opp) and close(pw, opw)
         for i in rng.integers(0, n, size=6):
             t = [rng.random() * 184.0, rng.random() * 184.0, 2.5 + rng.random() * 15.0]
             cur, moved = e.particle_energy(0, int(i), t)
@@ -134,7 +141,7 @@ def test_c4_cell_list_chain_on_the_real_box(mcpm, c4, production):
 
 
 # ---------------------------------------------------------------------------------------------- C5
-@pytest.mark.parametrize("kernel,spec,threads", [("k2_chains", 0, 32), ("k2_pair", 2, 32), ("k2_quad", 4, 0), ("k2_spec", 1, 0)])
+@pytest.mark.parametrize("kernel,spec,threads", [("k2_pool", 0, 32), ("k2_chains", 0, 64), ("k2_pair", 2, 32), ("k2_quad", 4, 0), ("k2_spec", 1, 0)])
 @pytest.mark.parametrize("ih,it", [(0, 0), (0, 31), (31, 0), (31, 31)], ids=["H8_T77", "H8_T139", "H39_T77", "H39_T139"])
 def test_c5_corners_follow_the_oracle(mcpm, ih, it, kernel, spec, threads):
     """Corners of the pore-width x temperature sweep.  H = 8 A: the two walls' terms overlap and most insertion attempts land
@@ -152,6 +159,7 @@ def test_c5_corners_follow_the_oracle(mcpm, ih, it, kernel, spec, threads):
     otr = o.run_sets(1, sets, sps, 0, True)
     with mcpm.Engine(1, 1024) as e:
         e.use_speculation(spec)
+        e.use_pool(16 if kernel == "k2_pool" else 0)
         e.set_system(s)
         e.set_positions(0, x, y, z)
         e.set_stream_ids([chain_id])
@@ -165,7 +173,9 @@ def test_c5_corners_follow_the_oracle(mcpm, ih, it, kernel, spec, threads):
     st, ost = stats[0], o.state()
     assert (st.n, st.dr, st.tot_disp_acc, st.samples, st.sum_n) == (ost["n"], ost["dr"], ost["tot_disp_acc"], ost["samples"], ost["sum_n"])
     assert st.energy == pytest.approx(st.energy_check, rel=1e-9)
-    assert st.energy == pytest.approx(ost["exact_energy"], rel=1e-9)
+    # (the oracle's own running energy relaxed from the ~1e20 K of the random start and keeps a rounding residue of that; the engine
+    # re-anchors when a hard overlap passes through its cache: compare with the oracle's RECOMPUTED energy of the final configuration)
+    assert st.energy_check == pytest.approx(o.box_energy()[0][3], rel=RTOL)
 
 
 # ---------------------------------------------------------------------------------------------- C1, long traces
@@ -183,7 +193,7 @@ def long_oracle(golden):
     return s, (x, y, z), otr, o.get_positions(), o.state()
 
 
-@pytest.mark.parametrize("kernel,spec,threads", [("k2_chains", 0, 32), ("k2_chains", 0, 128), ("k2_spec", 1, 0), ("k2_pair", 2, 32), ("k2_quad", 4, 0)])
+@pytest.mark.parametrize("kernel,spec,threads", [("k2_pool", 0, 32), ("k2_chains", 0, 128), ("k2_spec", 1, 0), ("k2_pair", 2, 32), ("k2_quad", 4, 0)])
 def test_million_step_trace_and_cache_drift(mcpm, long_oracle, kernel, spec, threads):
     """10^6 steps (100 sets x 10 000, dr adapting during the first 10) in 4 launches with NO end-of-launch rebuild: the
     accept/reject trace must equal the oracle's (first divergence reported), positions bit-identical, and the per-particle
@@ -191,6 +201,7 @@ def test_million_step_trace_and_cache_drift(mcpm, long_oracle, kernel, spec, thr
     s, (x, y, z), otr, opos, ost = long_oracle
     with mcpm.Engine(1, 1024) as e:
         e.use_speculation(spec)
+        e.use_pool(16 if kernel == "k2_pool" else 0)
         e.set_system(s)
         e.set_positions(0, x, y, z)
         trs = []
@@ -237,7 +248,7 @@ def test_isotherm_loadings_match_the_compiled_reference_within_2_sigma(mcpm):
                 e.set_positions(c, g[f"x{k}"], g[f"y{k}"], g[f"z{k}"])
         e.run(1, 20, 10000, seed=777)
         stats = e.run(21, 80, 10000, seed=777, check_energy=1)
-        assert e.last_kernel_name() == "k2_chains"
+        assert e.last_kernel_name() in ("k2_chains", "k2_pool", "k2_quad", "k2_pair")      # 512 chains: chosen by chains per SM
     chi2 = 0.0
     rows = []
     for p, pt in enumerate(pts):

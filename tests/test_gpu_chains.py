@@ -22,11 +22,14 @@ def first_divergence(a, b):
     return int(d[0]) if len(d) else -1
 
 
-@pytest.mark.parametrize("cache", [True, False, "subwarp", "spec", "dual", "pair"], ids=["cache", "nocache", "subwarp", "spec", "dual", "pair"])
+@pytest.mark.parametrize("cache", [True, False, "subwarp", "spec", "dual", "pair", "classic"], ids=["cache", "nocache", "subwarp", "spec", "dual", "pair", "classic"])
 @pytest.mark.parametrize("threads", [32, 64, 128, 256, 512])
 @pytest.mark.parametrize("name", ["c1t", "lowt", "bulkt"])
 def test_replay_trace_matches_reference_golden(mcpm, golden, name, threads, cache):
-    """'dual' = the opt-in dual-candidate kernel (k2_dual, one warp per chain, two steps per round)."""
+    """'cache' at 32 threads = the pooled persistent kernel k2_pool, 'classic' = one CTA per chain (k2_chains) for one-warp chains too;
+    'dual' = the opt-in dual-candidate kernel (k2_dual, one warp per chain, two steps per round)."""
+    if cache == "classic" and threads != 32:
+        pytest.skip("the pooled kernel only replaces the one-warp variant")
     if cache in ("subwarp", "dual") and not mcpm.has_experiments():
         pytest.skip("experimental kernels: build with `make EXPERIMENTS=1` and run with MCPM_EXPERIMENTS=1")
     if cache == "subwarp" and threads != 32:
@@ -47,6 +50,7 @@ def test_replay_trace_matches_reference_golden(mcpm, golden, name, threads, cach
         e.use_subwarp(cache == "subwarp")
         e.use_speculation({"spec": 1, "pair": 2}.get(cache, 0))
         e.use_dual_candidates(cache == "dual")
+        e.use_pool(0 if cache == "classic" else 16)
         e.set_system(s)
         e.set_positions(0, x, y, z)
         per_set, traces = [], []
@@ -64,6 +68,8 @@ def test_replay_trace_matches_reference_golden(mcpm, golden, name, threads, cach
                             st.n_swaps, st.dr])
             assert st.energy == pytest.approx(st.energy_check, rel=RTOL)
             assert st.pair == pytest.approx(st.pair_check, rel=RTOL, abs=1e-9)
+        if cache in (True, "classic") and threads == 32:
+            assert e.last_kernel_name() == ("k2_pool" if (cache is True and name != "bulkt") else "k2_chains")   # (NVT samples Widom: never pooled)
         got = np.concatenate(traces)
         div = first_divergence(got, arrays[name + "_trace"])
         assert div == -1, f"first divergence at step {div}"
@@ -117,11 +123,12 @@ def test_philox_chain_follows_oracle(mcpm, golden, threads, cache):
         e.use_energy_cache(bool(cache))
         e.use_speculation({"spec": 1, "pair": 2}.get(cache, 0))
         e.use_dual_candidates(cache == "dual")
+        e.use_pool(16 if (cache is True and threads == 32) else 0)       # the pooled one-warp kernel is opt-in
         e.set_system(s)
         for c in range(nchains):
             e.set_positions(c, x, y, z)
         stats, tr = e.run(1, sets, sps, seed=seed, trace=True, threads=threads, check_energy=1)
-        assert e.last_kernel_name() == {True: "k2_chains", False: "k2_chains", "spec": "k2_spec", "dual": "k2_dual", "pair": "k2_pair"}[cache]
+        assert e.last_kernel_name() == {True: "k2_pool" if threads == 32 else "k2_chains", False: "k2_chains", "spec": "k2_spec", "dual": "k2_dual", "pair": "k2_pair"}[cache]
         for c in range(nchains):
             o = O.COracle(s, 1024)
             o.set_positions(x, y, z)
@@ -639,3 +646,92 @@ def test_lean_speculation_is_chosen_by_chains_per_sm(mcpm, golden, nch, kernel):
     assert out[0][:5] == out[1][:5]
     for a, b in zip(out[0][5], out[1][5]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("warps", [16, 20])
+def test_pooled_kernel_mixed_loadings_and_slot_classes(mcpm, golden, warps):
+    """k2_pool: 40 chains of very different size (3 ... 504 particles: three slot classes in one CTA mix) against the C oracle on
+    the same Philox streams — traces, configurations, counters, accumulators — and bit-identical to the one-CTA-per-chain kernel."""
+    arrays, meta = golden
+    base = meta["c1"]["system"]
+    x, y, z = arrays["c1_x"], arrays["c1_y"], arrays["c1_z"]
+    sizes = [504, 3, 40, 150, 10, 260, 90, 504, 33, 200, 5, 120] * 3 + [300, 20, 450, 64]
+    mus = [-1134.0, -1900.0, -1700.0, -1500.0, -1800.0, -1350.0, -1600.0, -1134.0, -1750.0, -1400.0, -1850.0, -1550.0] * 3 + [-1300.0, -1800.0, -1200.0, -1650.0]
+    seed, sets, sps = 31337, 2, 1500
+    results = {}
+    for pool in (warps, 0):
+        with mcpm.Engine(len(sizes), 704) as e:
+            e.use_pool(pool)
+            systems = []
+            for c, (n0, mu) in enumerate(zip(sizes, mus)):
+                d = dict(base); d["mu"] = mu; d["n_equil_sets"] = 1
+                s = system_from_meta(d)
+                systems.append(s)
+                e.set_system(s, c)
+                e.set_positions(c, x[:n0], y[:n0], z[:n0])
+            stats, tr = e.run(1, sets, sps, seed=seed, trace=True, threads=32, check_energy=1)
+            assert e.last_kernel_name() == ("k2_pool" if pool else "k2_chains")
+            results[pool] = (tr.copy(), [e.get_positions(c) for c in range(len(sizes))], [(q.n, q.dr, q.sum_n, q.acceptance, q.n_swaps, q.steps_done, q.pair_evals) for q in stats],
+                             np.array([(q.sum_e, q.energy) for q in stats]))
+            if pool:
+                for c in (0, 1, 5, 8, 36, 38):
+                    n0, s = sizes[c], systems[c]
+                    o = O.COracle(s, 1024)
+                    o.set_positions(x[:n0], y[:n0], z[:n0]); o.box_energy(); o.philox(seed, c, 0)
+                    otr = o.run_sets(1, sets, sps, 0, True)
+                    assert first_divergence(tr[c], otr) == -1, c
+                    st, ost = stats[c], o.state()
+                    assert (st.n, st.dr, st.samples, st.sum_n) == (ost["n"], ost["dr"], ost["samples"], ost["sum_n"])
+                    assert (st.acceptance, st.rejection, st.n_displacements, st.accept_swap, st.reject_swap, st.n_swaps) == \
+                        (ost["acceptance"], ost["rejection"], ost["n_displacements"], ost["accept_swap"], ost["reject_swap"], ost["n_swaps"])
+                    assert st.energy == pytest.approx(st.energy_check, rel=RTOL, abs=1e-9)
+                    for a, b in zip(e.get_positions(c), o.get_positions()):
+                        assert np.array_equal(a, b)
+    assert np.array_equal(results[warps][0], results[0][0])
+    assert results[warps][2] == results[0][2]
+    assert np.allclose(results[warps][3], results[0][3], rtol=1e-12, atol=0)      # running sums: same terms, last-bit differences only
+    for a, b in zip(results[warps][1], results[0][1]):
+        assert all(np.array_equal(u, v) for u, v in zip(a, b))
+
+
+@pytest.mark.parametrize("mode", ["philox", "replay"])
+def test_pooled_chain_outgrows_its_slot(mcpm, golden, mode):
+    """Chains that start with 20 particles get a small slot; at mu = -1134 K they fill up to ~550 during the launch, pause when the slot
+    is full and are finished by a follow-up launch in full-size slots.  The result is the chain the oracle produces (same trace, counters
+    of the interrupted set, accumulators, dr adaptation, replay cursor)."""
+    arrays, meta = golden
+    d = dict(meta["c1"]["system"]); d["n_equil_sets"] = 2
+    s = system_from_meta(d)
+    x, y, z = arrays["c1_x"][:20], arrays["c1_y"][:20], arrays["c1_z"][:20]
+    seed, sets, sps = 99, 4, 15000
+    u = O.mt_uniforms(4242, 8 * sets * sps) if mode == "replay" else None
+    nch = 1 if mode == "replay" else 6
+    with mcpm.Engine(nch, 704) as e:
+        e.use_pool(16)
+        e.set_system(s)
+        for c in range(nch):
+            e.set_positions(c, x, y, z)
+        launches0 = e.launch_count()
+        stats, tr = e.run(1, sets, sps, seed=seed, replay=u, trace=True, threads=32, check_energy=1)
+        assert e.last_kernel_name() == "k2_pool"
+        assert e.launch_count() - launches0 >= 3 + 1                  # K3 initialisation (2 launches) + at least two K2 launches
+        c = nch - 1
+        o = O.COracle(s, 1024)
+        o.set_positions(x, y, z); o.box_energy()
+        if mode == "replay":
+            o.replay(u)
+        else:
+            o.philox(seed, c, 0)
+        otr = o.run_sets(1, sets, sps, 0, True)
+        assert first_divergence(tr[c], otr) == -1
+        st, ost = stats[c], o.state()
+        assert st.n == ost["n"] > 200                                 # it did outgrow the slot of a 20-particle chain
+        assert (st.dr, st.samples, st.sum_n, st.steps_done) == (ost["dr"], ost["samples"], ost["sum_n"], sets * sps)
+        assert (st.acceptance, st.rejection, st.n_displacements, st.accept_swap, st.reject_swap, st.n_swaps) == \
+            (ost["acceptance"], ost["rejection"], ost["n_displacements"], ost["accept_swap"], ost["reject_swap"], ost["n_swaps"])
+        assert st.tot_disp == ost["tot_disp"] and st.tot_ins + st.tot_del == ost["tot_swap"]
+        if mode == "replay":
+            assert st.replay_consumed == o.draws()
+        assert st.energy == pytest.approx(st.energy_check, rel=RTOL)
+        for a, b in zip(e.get_positions(c), o.get_positions()):
+            assert np.array_equal(a, b)

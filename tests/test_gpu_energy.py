@@ -181,3 +181,40 @@ def test_k3_cell_list_matches_all_pairs_and_oracle(mcpm, system, n, seed):
     print(f"n={n}: cell-list K3 {ms_cells:.3f} ms, all-pairs K3 {ms_all:.3f} ms")
     if n >= 20000:
         assert ms_cells < ms_all
+
+
+@pytest.mark.parametrize("n,outside", [(1, False), (333, False), (1024, False), (1025, False), (2600, False), (5400, False), (700, True)])
+def test_k1_batch_matches_oracle_and_single_calls(mcpm, n, outside):
+    """mcpm_particle_energy_batch: a mixed batch (stored + trial, stored only, ghost) in one launch — one CTA slice of 1024 staged
+    particles up to six of them — against the oracle, and bit-identical to the one-request launches (same per-thread partner
+    order, same reduction order).  `outside` puts coordinates and trials outside the box: the general minimum image."""
+    s = O.methane_slit(rcut=40.0, n_equil_sets=0)
+    rng = np.random.default_rng(n)
+    x, y, z = rng.random(n) * 80.0, rng.random(n) * 80.0, 3.0 + rng.random(n) * 14.0
+    if outside:
+        x += 80.0 * rng.integers(-2, 3, size=n)
+    o = O.COracle(s, n + 8)
+    o.set_positions(x, y, z)
+    m = 37
+    idx = rng.integers(-1, n, size=m).astype(np.int32)
+    trial = np.column_stack([rng.random(m) * 80.0 + (160.0 if outside else 0.0), rng.random(m) * 80.0, 2.0 + rng.random(m) * 16.0])
+    with mcpm.Engine(1, n + 40) as e:
+        e.set_system(s)
+        e.set_positions(0, x, y, z)
+        cur, moved = e.particle_energy_batch(0, idx, trial)
+        for r in range(m):
+            i = int(idx[r])
+            want_moved = o.moved_energy(i, *trial[r]) if i >= 0 else o.trial_energy(*trial[r])
+            assert close(moved[r], want_moved), (r, i)
+            if i >= 0:
+                assert close(cur[r], o.particle_energy(i)), (r, i)
+            c1, m1 = e.particle_energy(0, i, trial[r])
+            assert np.array_equal(m1, moved[r]) and (i < 0 or np.array_equal(c1, cur[r]))
+        stored = np.flatnonzero(idx >= 0)
+        if len(stored):
+            cur2, _ = e.particle_energy_batch(0, idx[stored])           # no trial positions: the stored particles where they are
+            assert np.array_equal(cur2, cur[stored])
+        big = np.arange(2500) % max(n, 1)                              # more requests than one launch takes (1024)
+        cur3, _ = e.particle_energy_batch(0, big.astype(np.int32))
+        assert np.array_equal(cur3[:n][: min(n, 50)], cur3[n:2 * n][: min(n, 50)]) if 2 * n <= 2500 else True
+        assert close(cur3[0], o.particle_energy(0))
