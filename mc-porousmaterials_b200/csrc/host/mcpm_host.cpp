@@ -144,12 +144,20 @@ static int read_input_file(const char* path, mcpm_sim_config* cfg) {
     d.width[2] = size;
     if (geometry == "slit") { d.geometry = MCPM_GEOM_SLIT; d.width[0] = d.width[1] = 2 * maxRcut; }   // :134
     else if (geometry == "bulk") { d.geometry = MCPM_GEOM_BULK; d.width[0] = d.width[1] = d.width[2]; } // :135
-    else d.geometry = geometry == "cylinder" ? 2 : 3;   // recognised, but out of scope for the engine
-    // wall dispatch of src/energy.cpp:69-77: only ("lj", slit) gives SlitLJ_Pot; e.g. "steele10-4-3" + slit matches nothing
-    d.wall_kind = (sf_pot == "lj" && geometry == "slit") ? MCPM_WALL_SLIT_LJ : MCPM_WALL_NONE;
+    else if (geometry == "sphere") { d.geometry = MCPM_GEOM_SPHERE; d.width[0] = d.width[1] = d.width[2]; }   // :130
+    else if (geometry == "cylinder") { d.geometry = MCPM_GEOM_CYLINDER; d.width[0] = 2 * maxRcut; d.width[1] = d.width[2]; }   // :131-133
+    else d.geometry = -1;
+    // wall dispatch of src/energy.cpp:69-77: ("lj", slit) -> SlitLJ_Pot, ("lj", sphere) -> SphericalLJ_Pot, the two cylindrical walls
+    // need 2F1 (recognised, refused by the engine); anything else matches nothing, e.g. "steele10-4-3" + slit
+    d.wall_kind = (sf_pot == "lj" && geometry == "slit") ? MCPM_WALL_SLIT_LJ : (sf_pot == "lj" && geometry == "sphere") ? MCPM_WALL_SPHERE_LJ :
+                  (sf_pot == "lj10-4" && geometry == "cylinder") ? 3 : (sf_pot == "steele10-4-3" && geometry == "cylinder") ? 4 : MCPM_WALL_NONE;
+    // pair dispatch of src/energy.cpp:79-101: "lj", "hs"; the EAM potentials are recognised and refused; anything else gives no pair energy
+    d.pair_kind = ff_pot == "hs" ? MCPM_PAIR_HS : (ff_pot.rfind("eam_", 0) == 0 ? 2 : MCPM_PAIR_LJ);
+    if (ff_pot != "lj" && ff_pot != "hs" && d.pair_kind == MCPM_PAIR_LJ) d.eps_ff = 0.0;      // no potential matched: an ideal gas
+    d.pressure = cfg->pressure;
+    d.dv = 1e-3;               // src/MC.cpp:33
     d.dr = 0.1 * d.width[2];   // :168
     d.n_equil_sets = (int)cfg->n_equil_sets;
-    (void)ff_pot;
     return MCPM_OK;
 }
 
@@ -161,7 +169,22 @@ struct Outputs {
 };
 
 double box_volume(const mcpm_system_desc& d) {  // MC::ComputeVolume, src/read.cpp:26-35
+    if (d.geometry == MCPM_GEOM_SPHERE) return (M_PI / 6.) * ipow(d.width[2], 3);
+    if (d.geometry == MCPM_GEOM_CYLINDER) return (M_PI / 4.) * ipow(d.width[2], 2) * d.width[0];
     return d.geometry == MCPM_GEOM_SLIT ? d.width[0] * d.width[1] * d.width[2] : ipow(d.width[2], 3);
+}
+const char* geometry_name(int g) { return g == MCPM_GEOM_SLIT ? "slit" : g == MCPM_GEOM_SPHERE ? "sphere" : g == MCPM_GEOM_CYLINDER ? "cylinder" : "bulk"; }
+
+// MC::InsertParticle, src/moves.cpp:21-55: sphere (radius, theta, phi), cylinder (rho, phi, x), slit / bulk (x, y, z)
+template <class Rnd>
+void insert_particle(const mcpm_system_desc& d, Rnd& rnd, double& x, double& y, double& z) {
+    if (d.geometry == MCPM_GEOM_SPHERE) {
+        const double radius = rnd() * d.width[2] * 0.5, theta = rnd() * M_PI, phi = rnd() * 2 * M_PI;
+        x = radius * sin(theta) * cos(phi) + 0.5 * d.width[0]; y = radius * sin(theta) * sin(phi) + 0.5 * d.width[1]; z = radius * cos(theta) + 0.5 * d.width[2];
+    } else if (d.geometry == MCPM_GEOM_CYLINDER) {
+        const double rho = rnd() * d.width[2] * 0.5, phi = rnd() * 2 * M_PI;
+        x = (rnd() - 0.5) * d.width[0] + 0.5 * d.width[0]; y = rho * sin(phi) + 0.5 * d.width[1]; z = rho * cos(phi) + 0.5 * d.width[2];
+    } else { x = rnd() * d.width[0]; y = rnd() * d.width[1]; z = rnd() * d.width[2]; }
 }
 
 // MC::PrintParams, src/print.cpp:16-104 (same wording and order)
@@ -189,14 +212,14 @@ void print_params(const mcpm_sim_config& c, std::ostream& os) {
     os << std::endl;
     os << "Fluid-fluid interaction parameters:" << std::endl;
     os << c.fluid << "-" << c.fluid << std::endl;
-    os << "\tVdW potential: lj" << std::endl;
+    os << "\tVdW potential: " << (d.pair_kind == MCPM_PAIR_HS ? "hs" : "lj") << std::endl;
     os << "\tsigma (AA): " << d.sig_ff << std::endl;
     os << "\tepsilon (K): " << d.eps_ff << std::endl;
     os << "\trcut (AA): " << d.rcut << std::endl;
     os << std::endl;
     os << "Box parameters:" << std::endl;
     os << "Box 0: " << c.box << std::endl;
-    os << "\tGeometry: " << (d.geometry == MCPM_GEOM_SLIT ? "slit" : "bulk") << std::endl;
+    os << "\tGeometry: " << geometry_name(d.geometry) << std::endl;
     os << "\tInitial width (AA): " << d.width[2] << std::endl;
     if (d.rho_s > 0) os << "\tSurface density (AA^-2): " << d.rho_s << std::endl;
     if (d.n_layers > 1) os << "\tLayers per wall: " << d.n_layers << std::endl;
@@ -205,7 +228,7 @@ void print_params(const mcpm_sim_config& c, std::ostream& os) {
     os << std::endl;
     os << "Box-fluid interaction parameters:" << std::endl;
     os << c.box << "-" << c.fluid << std::endl;
-    if (d.wall_kind == MCPM_WALL_SLIT_LJ) os << "\tVdW potential: lj" << std::endl;
+    if (d.wall_kind == MCPM_WALL_SLIT_LJ || d.wall_kind == MCPM_WALL_SPHERE_LJ) os << "\tVdW potential: lj" << std::endl;
     if (d.sig_sf > 0) os << "\tsigma (AA): " << d.sig_sf << std::endl;
     if (d.eps_sf > 0) os << "\tepsilon (K): " << d.eps_sf << std::endl;
     os << "\tInitial number of particles: " << c.n_particles << std::endl;
@@ -253,14 +276,15 @@ void print_log(const Outputs& o, const mcpm_sim_config& c, const mcpm_system_des
         return;
     }
     const double na = 6.02214076e23;
-    const double volume = box_volume(d);
+    const bool npt = d.n_vol > 0 && st->volume > 0;         // NPT: the box the chain ended the set with
+    const double volume = npt ? st->volume : box_volume(d), width = npt ? st->width : d.width[2];
     const double ff = q5 ? 0.5 * st->pair : st->pair;      // st->pair is the box pair energy (already halved once)
     const double energy = ff + st->wall;
     double density = st->n / volume;
     density *= d.molar_mass / na * 1e24;
     f.open(name, std::ios::app);
     f << std::fixed << std::setprecision(7);
-    f << set << "\t" << d.temperature << "\t" << d.width[2] << "\t" << volume << "\t";
+    f << set << "\t" << d.temperature << "\t" << width << "\t" << volume << "\t";
     f << ff / st->n << "\t" << st->wall / st->n << "\t" << energy / st->n << "\t";
     f << st->n << "\t" << density << "\t";
     // muEx / mu: with swap moves on, Widom sampling is off (src/moves.cpp:415) and ComputeChemicalPotential divides
@@ -275,6 +299,11 @@ void print_stats(const mcpm_sim_config& c, const mcpm_system_desc& d, size_t set
     if (set < c.n_equil_sets) os << "Equilibrium set: " << set << std::endl;
     else os << "Set: " << set << std::endl;
     os << "Box " << c.box << ":" << std::endl;
+    if (d.n_vol > 0) {
+        os << "\tAcceptVolRatio; RejectVolRatio:\t";
+        os << st->accept_vol * 1. / st->n_vol_changes << "; " << st->reject_vol * 1. / st->n_vol_changes << std::endl;
+        if (set < c.n_equil_sets) os << "\tVolume step size: " << st->dv << std::endl;
+    }
     if (d.n_swap > 0) {
         os << "\tAcceptSwapRatio; RejectSwapRatio:\t";
         os << st->accept_swap * 1. / st->n_swaps << "; " << st->reject_swap * 1. / st->n_swaps << std::endl;
@@ -285,7 +314,7 @@ void print_stats(const mcpm_sim_config& c, const mcpm_system_desc& d, size_t set
         if (set < c.n_equil_sets) os << "\tDisplacement step size: " << st->dr << std::endl;
     }
     os << "\tNumParticles; BoxSize; Energy/Particle:\t";
-    os << st->n << "; " << d.width[2] << "; " << st->energy / st->n << std::endl;
+    os << st->n << "; " << ((d.n_vol > 0 && st->width > 0) ? st->width : d.width[2]) << "; " << st->energy / st->n << std::endl;
     os << std::endl;   // like the reference, the stream stays fixed/7 for everything printed afterwards
 }
 
@@ -339,8 +368,11 @@ static int simulate(const char* input_path, const char* out_dir, int flags) {
     if (cfg.continue_after_crash)   // the reference restarts from ReadTrajectory/ReadLogFile (src/read.cpp:173-281): out of scope, say so
         return host_fail(MCPM_ERR_UNSUPPORTED, "ContinueAfterCrash (restart from trajectory/log files) is not supported");
     mcpm_system_desc& sys = cfg.system;
-    if (sys.geometry != MCPM_GEOM_SLIT && sys.geometry != MCPM_GEOM_BULK) return host_fail(MCPM_ERR_UNSUPPORTED, "only slit and bulk geometries are supported");
-    if (sys.n_vol != 0) return host_fail(MCPM_ERR_UNSUPPORTED, "volume moves are out of scope");
+    if (sys.geometry < 0) return host_fail(MCPM_ERR_UNSUPPORTED, "unknown geometry");
+    if (sys.pair_kind > MCPM_PAIR_HS) return host_fail(MCPM_ERR_UNSUPPORTED, "EAM potentials are out of scope");
+    if (sys.wall_kind > MCPM_WALL_SPHERE_LJ) return host_fail(MCPM_ERR_UNSUPPORTED, "the cylindrical 10-4 / 10-4-3 walls (2F1) are out of scope");
+    if (sys.n_vol != 0 && !(sys.pressure > 0)) return host_fail(MCPM_ERR_UNSUPPORTED, "volume moves without ExternalPressure are the two-box Gibbs ensemble: out of scope");
+    if (sys.n_vol != 0 && (sys.geometry != MCPM_GEOM_BULK || sys.n_swap != 0)) return host_fail(MCPM_ERR_UNSUPPORTED, "volume moves: bulk NPT only");
     print_params(cfg, log);
     if (sys.geometry == MCPM_GEOM_BULK && sys.width[2] < 2 * sys.rcut) {   // src/print.cpp:96-103
         std::cout << "Error: Box size must be larger than twice the cut-off radius." << std::endl;
@@ -399,7 +431,7 @@ static int simulate(const char* input_path, const char* out_dir, int flags) {
     for (int c = 0; c < n_chains; c++) {
         RefRandom rnd(seed + 7919ull * (unsigned long long)c);
         X[c].resize(capacity); Y[c].resize(capacity); Z[c].resize(capacity);
-        for (int k = 0; k < cfg.n_particles; k++) { X[c][k] = rnd() * sys.width[0]; Y[c][k] = rnd() * sys.width[1]; Z[c][k] = rnd() * sys.width[2]; }
+        for (int k = 0; k < cfg.n_particles; k++) insert_particle(sys, rnd, X[c][k], Y[c][k], Z[c][k]);
     }
     auto upload = [&]() -> int {
         for (int g = 0; g < G; g++)
@@ -446,7 +478,7 @@ static int simulate(const char* input_path, const char* out_dir, int flags) {
         for (int g = 0; g < G; g++)
             for (size_t k = 0; k < owned[g].size(); k++) {
                 mcpm_system_desc m = desc[owned[g][k]];
-                m.n_swap = 0; m.n_disp = 1; m.n_equil_sets = 0;       // translations only, no dr adaptation (AdjustMCMoves is commented out there)
+                m.n_swap = 0; m.n_vol = 0; m.n_disp = 1; m.n_equil_sets = 0;       // translations only, no dr adaptation (AdjustMCMoves is commented out there)
                 rc = mcpm_set_system(ctx[g], (int)k, &m);
                 if (rc) return host_fail(rc, mcpm_last_error());
             }
@@ -505,6 +537,7 @@ static int simulate(const char* input_path, const char* out_dir, int flags) {
                 // the reference prints BEFORE AdjustMCMoves (src/main.cpp:77-83): report the amplitude the set ran with
                 mcpm_chain_stats shown = stats[g][k];
                 shown.dr = shown.dr_used;
+                if (desc[c].n_vol > 0 && shown.width > 0) desc[c].width[0] = desc[c].width[1] = desc[c].width[2] = shown.width;   // NPT: the box moved
                 if (c == 0) print_stats(cfg, desc[c], (size_t)last, &shown, log);
                 print_trajectory(outs[c], cfg, desc[c], (size_t)last, shown.dr, n, X[c].data(), Y[c].data(), Z[c].data());
                 double mu_ex = 0., mu = 0.;

@@ -77,6 +77,8 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
     // re-anchored by CorrectEnergy's ratio test (src/energy.cpp:35-42, Q4).  Both are tracked here beside the exact energies: the
     // recompute CorrectEnergy would do returns what the exact bookkeeping already holds, so it costs nothing.
     const bool npt = !FAST && P.n_vol > 0;
+    // hard spheres: every stored particle carries its own INT_MAX in MC::BoxEnergy (quirk Q17), i.e. half of it in the halved box total
+    const double hs_self = (!FAST && g.hs) ? 0.5 * MCPM_INT_MAX_D : 0.0;
     double volume = npt ? Lz * Lz * Lz : 0.0, dv = st.dv, b_energy = S.b_valid ? S.b_energy : st.pair + st.wall, b_old = S.b_valid ? S.b_old : 0.0;
     int acc_vol = 0, rej_vol = 0, n_volch = 1;
     Fwd fwd; fwd.slot = -1; fwd.x = fwd.y = fwd.z = 0.0;
@@ -272,7 +274,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                             if ((n & tmask) == tid) ep[n] = v[0];
                             sc.evals += (unsigned long long)n;
                         }
-                        sc.acc_ins++; n++; nd += 1.0; e_pair += pi_; e_wall += wi;
+                        sc.acc_ins++; n++; nd += 1.0; e_pair += pi_ + hs_self; e_wall += wi;
                         if (CACHE && cta_sync_or<MULTI>(big)) {
                             double cp, cw;
                             cache_fill<FAST, PBZ, MULTI>(xs, ys, zs, ep, n, P, g, partials, W, warp, lane, tid, T, cp, cw);
@@ -318,7 +320,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
                         if ((o & tmask) == tid) { xs[o] = xl; ys[o] = yl; zs[o] = zl; }  // swap-with-last, src/moves.cpp:329
                         fwd.slot = o; fwd.x = xl; fwd.y = yl; fwd.z = zl;
                         n--; nd -= 1.0;
-                        e_pair -= po; e_wall -= wo;   // exact bookkeeping with the fresh energies (quirks Q3, Q16 fixed)
+                        e_pair -= po - hs_self; e_wall -= wo;   // exact bookkeeping with the fresh energies (quirks Q3, Q16 fixed)
                         if (CACHE) {
                             cta_sync<MULTI>();                                      // the moved entry and slot are visible
                             if (big) {

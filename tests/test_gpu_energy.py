@@ -128,8 +128,8 @@ def test_empty_chain_and_bad_arguments(mcpm):
             e.particle_energy(0, 5)
         bad = O.argon_slit(); bad.n_vol = 1
         with pytest.raises(mcpm.McpmError):
-            e.set_system(bad)                                   # volume moves are out of scope
-        bad = O.argon_slit(); bad.geometry = 3
+            e.set_system(bad)                                   # volume moves need a bulk box and a pressure
+        bad = O.argon_slit(); bad.geometry = 4
         with pytest.raises(mcpm.McpmError):
             e.set_system(bad)
 

@@ -154,3 +154,31 @@ def test_sharding_over_two_devices_does_not_change_the_results(tmp_path, mcpm):
         for r in range(4):
             rel = os.path.join(f"ar_small_mu{p}_r{r}", "pore", "simulation_ar.log")
             assert open(d1 / rel).read() == open(d2 / rel).read(), rel
+
+
+def test_spherical_pore_input_runs_in_reference_format(tmp_path):
+    """Geometry sphere + "lj" wall (SphericalLJ_Pot): initial configuration through InsertParticle's sphere branch, volume pi/6 D^3."""
+    stdout = run_driver(tmp_path, os.path.join(GOLDEN, "ar_sphere.in"))
+    assert "\tGeometry: sphere" in stdout and "AcceptSwapRatio; RejectSwapRatio:" in stdout
+    log = open(tmp_path / "ar_sphere" / "cavity" / "simulation_ar.log").read().splitlines()
+    assert len(log) == 4
+    for row in log[1:]:
+        a = row.split("\t")
+        assert float(a[2]) == 30.0 and float(a[3]) == pytest.approx(np.pi / 6 * 27000.0, abs=1e-6)
+        assert 5 <= int(a[7]) <= 400 and np.isfinite(float(a[6])) and float(a[5]) < 0          # attractive wall
+    traj = open(tmp_path / "ar_sphere" / "cavity" / "trajectory.exyz").read().splitlines()
+    n = int(traj[0])
+    xyz = np.array([[float(v) for v in line.split("\t")[1:]] for line in traj[2:2 + n]])
+    assert np.all(np.linalg.norm(xyz - 15.0, axis=1) < 15.0)                                   # everyone inside the cavity
+
+
+def test_npt_input_moves_the_box(tmp_path):
+    """NVolumeAttempts + ExternalPressure: MC::ChangeVolume on the device; the log's width / volume columns follow the box."""
+    stdout = run_driver(tmp_path, os.path.join(GOLDEN, "lj_npt.in"))
+    assert "AcceptVolRatio; RejectVolRatio:" in stdout and "Volume step size:" in stdout
+    log = open(tmp_path / "lj_npt" / "bulk" / "simulation_ar.log").read().splitlines()
+    rows = [r.split("\t") for r in log[1:]]
+    widths = [float(r[2]) for r in rows]; vols = [float(r[3]) for r in rows]
+    assert len(set(widths)) > 1 and all(v == pytest.approx(w ** 3, rel=1e-6) for w, v in zip(widths, vols))
+    assert all(int(r[7]) == 300 for r in rows)
+    assert all(25.0 < w < 60.0 for w in widths)

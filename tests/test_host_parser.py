@@ -91,3 +91,37 @@ def test_unsupported_inputs_are_refused_before_any_device_work(mcpm, tmp_path):
     p.write_text(text + "ContinueAfterCrash\n")
     assert mcpm.lib().mcpm_simulate(str(p).encode(), str(tmp_path).encode(), 2) == 4          # MCPM_ERR_UNSUPPORTED
     assert b"ContinueAfterCrash" in mcpm.lib().mcpm_last_error()
+
+
+@pytest.mark.parametrize("fname,project", [("ar_sphere.in", "ar_sphere"), ("lj_npt.in", "lj_npt")])
+def test_parser_f4_inputs_live_against_reference(mcpm, ref, fname, project):
+    """Spherical pore (widths = Size on all axes, "lj" + sphere = SphericalLJ_Pot) and an NPT input (ExternalPressure, NVolumeAttempts)."""
+    from conftest import O
+    r2 = O.RefOracle()
+    try:
+        path = os.path.join(GOLDEN, fname)
+        rc_ref, ps, n0, proj, fname_, bname, sets = r2.read_input(path)
+        rc, cfg = parse(mcpm, path)
+        assert rc == 0 and rc_ref == 0 and cfg.project.decode() == proj == project
+        assert cfg.n_particles == n0 and [cfg.n_sets, cfg.n_equil_sets, cfg.steps_per_set, cfg.print_every] == list(sets)
+        for name, _ in ps._fields_:
+            a = getattr(ps, name); b = getattr(cfg.system, name)
+            assert (list(a) == list(b)) if name == "width" else (a == b), name
+    finally:
+        r2.close()
+
+
+def test_parser_recognises_what_the_engine_refuses(mcpm, tmp_path):
+    text = open(os.path.join(GOLDEN, "ar_sphere.in")).read()
+    p = tmp_path / "cyl.in"
+    p.write_text(text.replace("Geometry sphere", "Geometry cylinder").replace("Cavity Ar VdwPotential lj", "Cavity Ar VdwPotential steele10-4-3"))
+    rc, cfg = parse(mcpm, str(p))
+    assert rc == 0 and cfg.system.geometry == mcpm.GEOM_CYLINDER and cfg.system.wall_kind == 4
+    assert list(cfg.system.width) == [30.0, 30.0, 30.0]            # PBC length 2*rcut along x, diameter on y and z
+    assert mcpm.lib().mcpm_simulate(str(p).encode(), str(tmp_path).encode(), 2) == 4
+    p = tmp_path / "eam.in"
+    p.write_text(text.replace("Ar Ar VdwPotential lj", "Ar Ar VdwPotential eam_na"))
+    assert mcpm.lib().mcpm_simulate(str(p).encode(), str(tmp_path).encode(), 2) == 4
+    p = tmp_path / "gibbs.in"
+    p.write_text(open(os.path.join(GOLDEN, "lj_npt.in")).read().replace("ExternalPressure 3.0e7\n", ""))
+    assert mcpm.lib().mcpm_simulate(str(p).encode(), str(tmp_path).encode(), 2) == 4
