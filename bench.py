@@ -450,6 +450,11 @@ def k3_k1_records(m, torch, local):
     return out
 
 
+def dbg(*a):
+    if os.environ.get("BENCH_DEBUG"):
+        print("[bench]", *a, file=sys.stderr, flush=True)
+
+
 def gpu_arm(args, world, rank, local, dist):
     import torch
     import mcpm_b200 as m
@@ -480,7 +485,9 @@ def gpu_arm(args, world, rank, local, dist):
     evals_all = allsum(dist, local, r["evals_sum"])
     evals_x_all = allsum(dist, local, r["evals_x_sum"])
 
+    dbg(rank, "main workload timed", value)
     literal = literal_isotherm(m, torch, args, world, rank, local, dist, flush) if args.config == "c2" and not args.no_literal else None
+    dbg(rank, "literal isotherm timed")
     if rank != 0:
         return
     peak_tflops, _ = m.fp64_peak_tflops(local)
@@ -543,6 +550,7 @@ def gpu_arm(args, world, rank, local, dist):
             "per_core": res["moves_per_s_per_core"], "makespan_rate": res["moves_per_s_makespan"],
             "without_correctenergy_recompute": fair["moves_per_s"],
         }
+    dbg(rank, "printing")
     print(json.dumps(line), flush=True)
 
 

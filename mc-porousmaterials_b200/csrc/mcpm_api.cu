@@ -761,6 +761,7 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     }
     const bool global_path = (size_t)c->cap > k2_smem_limit_cap(c->max_smem);   // positions stay in global memory / L2
     if (threads == 0) threads = global_path ? 512 : pick_threads(c, maxn);
+    if (p->threads_per_chain == 0 && p->sample_rdf && !p->no_sampling) threads = std::max(threads, 256);   // ComputeRDF is O(N^2) per production step: all the threads the sampling kernel takes (2x measured)
     bool all_fast = true;
     for (int k = 0; k < c->n_chains; k++) all_fast = all_fast && c->h_state[k].fast_image && !c->h_params[k].exotic;
     bool sample = p->sample_rdf != 0;                       // in-kernel sampling: RDF on request, Widom whenever n_swap == 0

@@ -133,20 +133,55 @@ __device__ void cta_box_energy(const double* xs, const double* ys, const double*
 // MC::ComputeRDF same-species branch, src/sample.cpp:21-31: every pair i<j adds 2 to bin int(r/deltaR)+1 (if < NBINS).
 // Binning must agree with the reference at bin edges, so the distance is formed exactly as MC::NeighDistance does
 // (true division, round(), no FMA contraction, sqrt) rather than with the fast minimum image of the energy path.
-template <bool PBZ>
-__device__ void cta_rdf(const double* xs, const double* ys, const double* zs, int n, const ChainParams& P, double* hist, int tid, int T) {
-    const double deltaR = sqrt(P.rc2) / (1. * MCPM_RDF_BINS);
-    for (int i = 0; i < n - 1; i++) {
-        const double xi = xs[i], yi = ys[i], zi = zs[i];
-        for (int j = i + 1 + tid; j < n; j += T) {
-            double dx = xi - xs[j], dy = yi - ys[j], dz = zi - zs[j];
-            dx = __dsub_rn(dx, __dmul_rn(round(__ddiv_rn(dx, P.L[0])), P.L[0]));
-            dy = __dsub_rn(dy, __dmul_rn(round(__ddiv_rn(dy, P.L[1])), P.L[1]));
-            if (PBZ) dz = __dsub_rn(dz, __dmul_rn(round(__ddiv_rn(dz, P.L[2])), P.L[2]));
-            const double r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
-            const int bin = (int)__ddiv_rn(r, deltaR) + 1;
-            if (bin < MCPM_RDF_BINS) atomicAdd(&hist[bin], 2.0);
+//   * pairs are tiled so that every thread has work in every trip: row i (n-1-i partners) is walked together with row n-2-i (i+1
+//     partners) — n items per combined row, strided over the CTA;
+//   * every warp counts into its OWN 32-bit histogram in shared memory (native shared-memory integer atomics, no contention between
+//     warps; a pair's contribution of 2 is an exact count), and the counts are folded into the fp64 histogram once per step.
+// Called by the whole CTA between two barriers.  whist: W x 128 unsigned ints, zero on entry and on exit.
+//   * exactness without the divisions: with both coordinates inside the box (FAST) |d| <= L, and round(fl(d/L)) is +-1 exactly when
+//     |d| >= L/2 (fl is monotone and L/2 is exact), so the image is chosen by comparison and subtracted with the reference's single
+//     rounding; pairs with r^2 > rcut^2 can never reach a bin below NBINS and are dropped before the square root; the bin
+//     int(fl(r/deltaR)) is taken from a reciprocal multiply unless the product lies within 1e-9 of an integer, where the true
+//     division decides.  Bins equal the reference's bit for bit (tests compare whole histograms).
+template <bool FAST, bool PBZ>
+__device__ void cta_rdf(const double* xs, const double* ys, const double* zs, int n, const ChainParams& P, double* hist, unsigned int* whist, int tid, int T,
+                        int warp, int W) {
+    const double deltaR = sqrt(P.rc2) / (1. * MCPM_RDF_BINS), inv_delta = 1.0 / deltaR;
+    const double Lx = P.L[0], Ly = P.L[1], Lz = P.L[2], hx = 0.5 * Lx, hy = 0.5 * Ly, hz = 0.5 * Lz, rc2 = P.rc2;
+    unsigned int* mine = whist + warp * 128;
+    const int rows = (n - 1 + 1) / 2;                      // combined rows r = 0 .. ceil((n-1)/2) - 1
+    for (int r = 0; r < rows; r++) {
+        const int i2 = n - 2 - r;                          // partner row; equals r for the middle row of an odd count of rows
+        const int len1 = n - 1 - r, len = len1 + ((i2 != r) ? r + 1 : 0);   // row i2 has n-1-i2 = r+1 partners
+        for (int k = tid; k < len; k += T) {
+            const int i = (k < len1) ? r : i2;
+            const int j = (k < len1) ? r + 1 + k : i2 + 1 + (k - len1);
+            double dx = xs[i] - xs[j], dy = ys[i] - ys[j], dz = zs[i] - zs[j];
+            if (FAST) {
+                dx = (dx >= hx) ? __dsub_rn(dx, Lx) : ((dx <= -hx) ? __dadd_rn(dx, Lx) : dx);
+                dy = (dy >= hy) ? __dsub_rn(dy, Ly) : ((dy <= -hy) ? __dadd_rn(dy, Ly) : dy);
+                if (PBZ) dz = (dz >= hz) ? __dsub_rn(dz, Lz) : ((dz <= -hz) ? __dadd_rn(dz, Lz) : dz);
+            } else {
+                if (P.pbc[0]) dx = __dsub_rn(dx, __dmul_rn(round(__ddiv_rn(dx, Lx)), Lx));
+                if (P.pbc[1]) dy = __dsub_rn(dy, __dmul_rn(round(__ddiv_rn(dy, Ly)), Ly));
+                if (P.pbc[2]) dz = __dsub_rn(dz, __dmul_rn(round(__ddiv_rn(dz, Lz)), Lz));
+            }
+            const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if (r2 > rc2) continue;                        // bin >= NBINS: never counted
+            const double rr = sqrt(r2);
+            const double q = rr * inv_delta;
+            int bin = (int)q;
+            const double frac = q - (double)bin;
+            if (frac < 1e-9 || frac > 1.0 - 1e-9) bin = (int)__ddiv_rn(rr, deltaR);   // at a bin edge the reference's own expression decides
+            bin += 1;
+            if (bin < MCPM_RDF_BINS) atomicAdd(&mine[bin], 1u);
         }
+    }
+    __syncthreads();
+    for (int k = tid; k < MCPM_RDF_BINS; k += T) {
+        unsigned int c = 0;
+        for (int w = 0; w < W; w++) { c += whist[w * 128 + k]; whist[w * 128 + k] = 0u; }
+        hist[k] += 2.0 * (double)c;
     }
 }
 

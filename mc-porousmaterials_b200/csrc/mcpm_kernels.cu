@@ -397,7 +397,7 @@ __device__ void chain_loop(const ChainParams& P, ChainState& S, Source& rng, dou
             if (SAMPLE && production && a.sample_rdf) {
                 __syncthreads();                                                 // this step's slot write is visible to everyone
                 fwd.slot = -1;
-                cta_rdf<PBZ>(xs, ys, zs, n, P, hist, tid, T);
+                cta_rdf<FAST, PBZ>(xs, ys, zs, n, P, hist, reinterpret_cast<unsigned int*>(hist + 104), tid, T, warp, W);
                 __syncthreads();
             }
 #ifdef MCPM_K2_TIMING
@@ -490,14 +490,15 @@ __global__ void __launch_bounds__(MAXT, MINB) k2_chains(const ChainParams* __res
     double* xs = GLOBAL ? X + off : smem;
     double* ys = GLOBAL ? Y + off : smem + cap;
     double* zs = GLOBAL ? Z + off : smem + 2 * cap;
-    // after the positions: [sampling kernels: RDF histogram, 104 doubles] [multi-warp CTAs: 2 parities x 32 warps x 2 partial sums]
+    // after the positions: [sampling kernels: RDF histogram, 104 doubles + 16 per-warp count histograms of 128 unsigned ints]
+    // [multi-warp CTAs: 2 parities x 32 warps x 2 partial sums]
     double* hist = GLOBAL ? smem : smem + 3 * cap;
-    double* partials = hist + (SAMPLE ? 104 : 0);
+    double* partials = hist + (SAMPLE ? MCPM_RDF_SMEM_DOUBLES : 0);
     __shared__ ChainParams P;
     __shared__ ChainState S;
     const int tid = threadIdx.x, T = blockDim.x;
     if (tid == 0) { P = params[chain]; S = states[chain]; }
-    if (SAMPLE) for (int k = threadIdx.x; k < MCPM_RDF_BINS + 4; k += blockDim.x) hist[k] = 0.0;
+    if (SAMPLE) for (int k = threadIdx.x; k < MCPM_RDF_SMEM_DOUBLES; k += blockDim.x) hist[k] = 0.0;   // (also zeroes the per-warp counts)
     __syncthreads();
     if (!GLOBAL) {
         // stage every slot (not only the n live ones): stale slots are observable through quirk Q12
@@ -901,9 +902,9 @@ __global__ void metropolis_probe_kernel(int kind, int count, const double* __res
 // launchers
 // ================================================================================================
 // positions + (multi-warp CTAs) 128 doubles of partial sums or (one warp) 64 doubles of uniforms + (sampling kernels) the RDF histogram
-static size_t k2_smem_bytes(int cap, bool multi, bool sample) { return (size_t)(3 * cap + (multi ? 128 : 64) + (sample ? 104 : 0)) * sizeof(double); }
+static size_t k2_smem_bytes(int cap, bool multi, bool sample) { return (size_t)(3 * cap + (multi ? 128 : 64) + (sample ? MCPM_RDF_SMEM_DOUBLES : 0)) * sizeof(double); }
 
-size_t k2_smem_limit_cap(int max_smem_optin) { return ((size_t)max_smem_optin / sizeof(double) - 128 - 104 - 64) / 3; }
+size_t k2_smem_limit_cap(int max_smem_optin) { return ((size_t)max_smem_optin / sizeof(double) - 128 - MCPM_RDF_SMEM_DOUBLES - 64) / 3; }
 
 template <int RNG_MODE>
 static cudaError_t launch_k2_rng(int n_chains, int threads, bool global, bool fast, bool sample, bool cache, size_t smem,

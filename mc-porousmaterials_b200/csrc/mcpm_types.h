@@ -91,3 +91,4 @@ struct PoolLayout {
 };
 
 #define MCPM_RDF_BINS 100        // NBINS, src/MC.h:11
+#define MCPM_RDF_SMEM_DOUBLES (104 + 16 * 128 / 2)   // fp64 histogram + 16 warps x 128 unsigned counts (sampling kernels)
