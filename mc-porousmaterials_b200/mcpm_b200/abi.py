@@ -102,6 +102,8 @@ def lib_path() -> str:
     """libmcpm.so, or — only when MCPM_EXPERIMENTS=1 is set and it was built (make EXPERIMENTS=1) — libmcpm_exp.so,
     the same library plus the experimental kernels of csrc/experiments/."""
     here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if os.environ.get("MCPM_LIB"):              # kernel experiments: a variant build of the same library (scripts/variants.sh)
+        return os.path.abspath(os.environ["MCPM_LIB"])
     exp = os.path.join(here, "libmcpm_exp.so")
     if os.environ.get("MCPM_EXPERIMENTS") == "1" and os.path.exists(exp):
         return exp
