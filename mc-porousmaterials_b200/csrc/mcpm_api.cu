@@ -813,7 +813,11 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
             kc_stride = std::max(kc_stride, ncell);
             occ = std::max(occ, (double)c->h_state[k].st.n / ncell);
         }
-        kc_ccap = std::max(64, (((int)(3.0 * occ) + 32 + 31) / 32) * 32);       // room for density fluctuations and growth; a full cell stops the chain
+        bool any_swap = false;
+        for (int k = 0; k < c->n_chains; k++) any_swap = any_swap || c->h_params[k].n_swap > 0;
+        // room for density fluctuations (NVT: twice the mean occupancy, > 8 sigma in a dense fluid) and, with swap moves, for growth;
+        // a full cell stops the chain
+        kc_ccap = any_swap ? std::max(64, (((int)(3.0 * occ) + 32 + 31) / 32) * 32) : std::max(64, (((int)(2.0 * occ) + 15) / 16) * 16);
         kc_smem = use_k2c ? k2_cells_smem_items_bytes(c->cap, kc_stride, kc_ccap, c->max_smem) : 0;
         if (use_k2c) {
             const size_t need = kc_smem ? 1 : (size_t)c->n_chains * kc_stride * kc_ccap;   // lists in shared memory need no global copy

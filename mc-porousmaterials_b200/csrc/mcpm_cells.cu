@@ -379,6 +379,7 @@ __device__ void chain_loop_cells(const ChainParams& P, ChainState& S, Source& rn
 }  // namespace
 
 // SMEM_ITEMS: the index lists (16-bit entries) live in dynamic shared memory; else 32-bit entries in global memory.
+// (round 2: __launch_bounds__(KC_THREADS, 2) — two chains per SM at 128 registers — spills 450 bytes and was measured 22-37 % slower)
 template <int RNG_MODE, bool SAMPLE, bool SMEM_ITEMS>
 __global__ void __launch_bounds__(KC_THREADS, 1) k2_cells(const ChainParams* __restrict__ params, ChainState* __restrict__ states,
                                                           const int* __restrict__ order, double* X, double* Y, double* Z, RunArgs a, int* items,
