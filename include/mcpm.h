@@ -39,8 +39,9 @@ enum {
 
 /* Box::geometry, src/read.cpp:74; derived widths :128-135, PBC flags :146-162 (bulk xyz, slit xy, cylinder x, sphere none) */
 enum { MCPM_GEOM_BULK = 0, MCPM_GEOM_SLIT = 1, MCPM_GEOM_CYLINDER = 2, MCPM_GEOM_SPHERE = 3 };
-/* wall dispatch, src/energy.cpp:69-77: "lj" + slit -> SlitLJ_Pot, "lj" + sphere -> SphericalLJ_Pot (src/potentials.cpp:474-504) */
-enum { MCPM_WALL_NONE = 0, MCPM_WALL_SLIT_LJ = 1, MCPM_WALL_SPHERE_LJ = 2 };
+/* wall dispatch, src/energy.cpp:69-77: "lj" + slit -> SlitLJ_Pot, "lj" + sphere -> SphericalLJ_Pot (src/potentials.cpp:474-504),
+ * "lj10-4" + cylinder -> CylindricalLJ10_4 (:412-444), "steele10-4-3" + cylinder -> CylindricalSteele10_4_3 (:445-469) */
+enum { MCPM_WALL_NONE = 0, MCPM_WALL_SLIT_LJ = 1, MCPM_WALL_SPHERE_LJ = 2, MCPM_WALL_CYL_LJ104 = 3, MCPM_WALL_CYL_STEELE = 4 };
 /* pair dispatch, src/energy.cpp:79-83: "lj" -> LJ126_Pot, "hs" -> HardSphere_Pot (src/potentials.cpp:40-54) */
 enum { MCPM_PAIR_LJ = 0, MCPM_PAIR_HS = 1 };
 enum { MCPM_RNG_PHILOX = 0, MCPM_RNG_REPLAY = 1 };

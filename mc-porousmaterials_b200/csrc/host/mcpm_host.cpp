@@ -147,10 +147,10 @@ static int read_input_file(const char* path, mcpm_sim_config* cfg) {
     else if (geometry == "sphere") { d.geometry = MCPM_GEOM_SPHERE; d.width[0] = d.width[1] = d.width[2]; }   // :130
     else if (geometry == "cylinder") { d.geometry = MCPM_GEOM_CYLINDER; d.width[0] = 2 * maxRcut; d.width[1] = d.width[2]; }   // :131-133
     else d.geometry = -1;
-    // wall dispatch of src/energy.cpp:69-77: ("lj", slit) -> SlitLJ_Pot, ("lj", sphere) -> SphericalLJ_Pot, the two cylindrical walls
-    // need 2F1 (recognised, refused by the engine); anything else matches nothing, e.g. "steele10-4-3" + slit
+    // wall dispatch of src/energy.cpp:69-77: ("lj", slit) -> SlitLJ_Pot, ("lj", sphere) -> SphericalLJ_Pot, ("lj10-4" | "steele10-4-3", cylinder)
+    // -> the two cylindrical walls; anything else matches nothing, e.g. "steele10-4-3" + slit
     d.wall_kind = (sf_pot == "lj" && geometry == "slit") ? MCPM_WALL_SLIT_LJ : (sf_pot == "lj" && geometry == "sphere") ? MCPM_WALL_SPHERE_LJ :
-                  (sf_pot == "lj10-4" && geometry == "cylinder") ? 3 : (sf_pot == "steele10-4-3" && geometry == "cylinder") ? 4 : MCPM_WALL_NONE;
+                  (sf_pot == "lj10-4" && geometry == "cylinder") ? MCPM_WALL_CYL_LJ104 : (sf_pot == "steele10-4-3" && geometry == "cylinder") ? MCPM_WALL_CYL_STEELE : MCPM_WALL_NONE;
     // pair dispatch of src/energy.cpp:79-101: "lj", "hs"; the EAM potentials are recognised and refused; anything else gives no pair energy
     d.pair_kind = ff_pot == "hs" ? MCPM_PAIR_HS : (ff_pot.rfind("eam_", 0) == 0 ? 2 : MCPM_PAIR_LJ);
     if (ff_pot != "lj" && ff_pot != "hs" && d.pair_kind == MCPM_PAIR_LJ) d.eps_ff = 0.0;      // no potential matched: an ideal gas
@@ -229,6 +229,8 @@ void print_params(const mcpm_sim_config& c, std::ostream& os) {
     os << "Box-fluid interaction parameters:" << std::endl;
     os << c.box << "-" << c.fluid << std::endl;
     if (d.wall_kind == MCPM_WALL_SLIT_LJ || d.wall_kind == MCPM_WALL_SPHERE_LJ) os << "\tVdW potential: lj" << std::endl;
+    else if (d.wall_kind == MCPM_WALL_CYL_LJ104) os << "\tVdW potential: lj10-4" << std::endl;
+    else if (d.wall_kind == MCPM_WALL_CYL_STEELE) os << "\tVdW potential: steele10-4-3" << std::endl;
     if (d.sig_sf > 0) os << "\tsigma (AA): " << d.sig_sf << std::endl;
     if (d.eps_sf > 0) os << "\tepsilon (K): " << d.eps_sf << std::endl;
     os << "\tInitial number of particles: " << c.n_particles << std::endl;
@@ -370,7 +372,6 @@ static int simulate(const char* input_path, const char* out_dir, int flags) {
     mcpm_system_desc& sys = cfg.system;
     if (sys.geometry < 0) return host_fail(MCPM_ERR_UNSUPPORTED, "unknown geometry");
     if (sys.pair_kind > MCPM_PAIR_HS) return host_fail(MCPM_ERR_UNSUPPORTED, "EAM potentials are out of scope");
-    if (sys.wall_kind > MCPM_WALL_SPHERE_LJ) return host_fail(MCPM_ERR_UNSUPPORTED, "the cylindrical 10-4 / 10-4-3 walls (2F1) are out of scope");
     if (sys.n_vol != 0 && !(sys.pressure > 0)) return host_fail(MCPM_ERR_UNSUPPORTED, "volume moves without ExternalPressure are the two-box Gibbs ensemble: out of scope");
     if (sys.n_vol != 0 && (sys.geometry != MCPM_GEOM_BULK || sys.n_swap != 0)) return host_fail(MCPM_ERR_UNSUPPORTED, "volume moves: bulk NPT only");
     print_params(cfg, log);

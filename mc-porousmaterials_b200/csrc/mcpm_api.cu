@@ -108,8 +108,7 @@ static double box_volume(const mcpm_system_desc& d) {
 
 static int digest(const mcpm_system_desc& d, ChainParams& P) {
     if (d.geometry < MCPM_GEOM_BULK || d.geometry > MCPM_GEOM_SPHERE) return fail(MCPM_ERR_UNSUPPORTED, "geometry %d not supported", d.geometry);
-    if (d.wall_kind != MCPM_WALL_NONE && d.wall_kind != MCPM_WALL_SLIT_LJ && d.wall_kind != MCPM_WALL_SPHERE_LJ)
-        return fail(MCPM_ERR_UNSUPPORTED, "wall_kind %d not supported (the cylindrical 10-4 / 10-4-3 walls need 2F1 and are out of scope)", d.wall_kind);
+    if (d.wall_kind < MCPM_WALL_NONE || d.wall_kind > MCPM_WALL_CYL_STEELE) return fail(MCPM_ERR_UNSUPPORTED, "wall_kind %d not supported", d.wall_kind);
     if (d.pair_kind != MCPM_PAIR_LJ && d.pair_kind != MCPM_PAIR_HS) return fail(MCPM_ERR_UNSUPPORTED, "pair_kind %d not supported (EAM potentials are out of scope)", d.pair_kind);
     if (d.n_vol < 0) return fail(MCPM_ERR_ARG, "move weights must be non-negative");
     if (d.n_vol > 0) {   // MC::ChangeVolume: the NPT branch of a single bulk box (src/moves.cpp:198-231); its other branches need two boxes
@@ -154,7 +153,7 @@ static int digest(const mcpm_system_desc& d, ChainParams& P) {
     P.sig_ff = d.sig_ff; P.eps_sf = d.eps_sf; P.rho_s = d.rho_s;
     P.press_k = d.pressure > 0 ? d.pressure / kb * 1e-30 : 0.0;   // src/moves.cpp:198
     // everything beyond "Lennard-Jones fluid, bulk or slit with the layered 10-4 wall, fixed volume" runs through the general kernels
-    P.exotic = (d.geometry == MCPM_GEOM_CYLINDER || d.geometry == MCPM_GEOM_SPHERE || d.wall_kind == MCPM_WALL_SPHERE_LJ || d.pair_kind == MCPM_PAIR_HS || d.n_vol > 0) ? 1 : 0;
+    P.exotic = (d.geometry == MCPM_GEOM_CYLINDER || d.geometry == MCPM_GEOM_SPHERE || d.wall_kind >= MCPM_WALL_SPHERE_LJ || d.pair_kind == MCPM_PAIR_HS || d.n_vol > 0) ? 1 : 0;
     return MCPM_OK;
 }
 

@@ -225,6 +225,79 @@ __device__ __forceinline__ double sphere_wall(const ChainParams& P, double xc, d
     return ((2. / 5.) * u1 - u2) * (2. * 3.14159265358979323846 * P.eps_sf * dens);
 }
 
+// ---- cylindrical walls.  The reference evaluates 2F1(a,b;1;z) with the vendored Numerical-Recipes hypgeo (series / ODE integration,
+// src/NumRecipes/hypgeo.h:46; for z > 1, outside the pore, integrated through the upper half plane, real part returned).  Here in closed
+// form: F(1/2,1/2) = 2K/pi, F(-1/2,1/2) = 2E/pi, F(-1/2,-1/2) = (2/pi)(2E - (1-z)K) with the complete elliptic integrals by the
+// arithmetic-geometric mean (z > 1: real parts of their continuation from above), then Gauss' contiguous relation (DLMF 15.5.11) lowers
+// one parameter at a time down to -9/2.  Agreement with the compiled reference inside the pore 2e-12 (tests/test_oracle_f4.py).
+__device__ __forceinline__ void ellip_ke01(double m, double& K, double& E) {   // 0 <= m < 1
+    double a = 1.0, b = sqrt(1.0 - m), c = sqrt(m), sum = 0.5 * c * c, pw = 1.0;
+    for (int n = 0; n < 12; n++) {
+        const double an = 0.5 * (a + b), bn = sqrt(a * b);
+        c = 0.5 * (a - b); a = an; b = bn;
+        sum += pw * c * c; pw *= 2.0;
+    }
+    K = 3.14159265358979323846 / (2.0 * a);
+    E = K * (1.0 - sum);
+}
+__device__ __forceinline__ void ellip_ke(double m, double& K, double& E) {
+    if (m < 1.0) { ellip_ke01(m, K, E); return; }
+    double k, e;
+    const double s = sqrt(m);
+    ellip_ke01(1.0 / m, k, e);
+    K = k / s;
+    E = s * e - (m - 1.0) / s * k;
+}
+// 2F1(-9/2,-9/2;1;z), 2F1(-3/2,-3/2;1;z), 2F1(-3/2,-1/2;1;z) from one pass over the table T[i][j] = 2F1(1/2-i, 1/2-j; 1; z), kept column by column
+__device__ __forceinline__ void hyp_wall(double z, double& f_m45_m45, double& f_m15_m15, double& f_m15_m05) {
+    double K, E;
+    ellip_ke(z, K, E);
+    const double p = 2.0 / 3.14159265358979323846;
+    double row0[6], row1[6];   // T[i][0], T[i][1]: the first two entries of every later column by symmetry
+    double col[6];
+    for (int j = 0; j < 6; j++) {
+        const double bb = 0.5 - j;
+        if (j == 0) { col[0] = p * K; col[1] = p * E; }
+        else if (j == 1) { col[0] = p * E; col[1] = p * (2 * E - (1 - z) * K); }
+        else { col[0] = row0[j]; col[1] = row1[j]; }
+        for (int i = 2; i < 6; i++) {
+            const double aa = 0.5 - (i - 1);
+            col[i] = -((2 * aa - 1 + (bb - aa) * z) * col[i - 1] + aa * (z - 1) * col[i - 2]) / (1 - aa);
+        }
+        if (j == 0) { for (int i = 0; i < 6; i++) row0[i] = col[i]; }
+        if (j == 1) { for (int i = 0; i < 6; i++) row1[i] = col[i]; f_m15_m05 = col[2]; }
+        if (j == 2) f_m15_m15 = col[2];
+        if (j == 5) f_m45_m45 = col[5];
+    }
+}
+// MC::CylindricalLJ10_4, src/potentials.cpp:412-444
+__device__ __forceinline__ double cyl_lj104(const ChainParams& P, double yc, double zc) {
+    const double sig = P.sig_sf, dens = P.rho_s * sig * sig, R = P.halfH / sig, delta = P.delta / sig;
+    const double rho = sqrt(yc * yc + zc * zc) / sig, x = R - rho;
+    double u1 = 0.0, u2 = 0.0;
+    for (int i = 0; i < P.n_layers; i++) {
+        const double Ri = R + i * delta, arg = ipow_d(1 - x / Ri, 2);
+        double f45, f15, f05;
+        hyp_wall(arg, f45, f15, f05);
+        u1 += 63. / 32. * 1. / (ipow_d(x, 10) * ipow_d(2.0 - x / Ri, 10)) * f45;
+        u2 += 3. / (ipow_d(x, 4) * ipow_d(2.0 - x / Ri, 4)) * f15;
+    }
+    return (u1 - u2) * 3.14159265358979323846 * 3.14159265358979323846 * dens * P.eps_sf;
+}
+// MC::CylindricalSteele10_4_3, src/potentials.cpp:445-469 (alpha = 0.61; the Gamma-function prefactors are constants)
+__device__ __forceinline__ double cyl_steele(const ChainParams& P, double yc, double zc) {
+    const double sig = P.sig_sf, R = P.halfH, Ra = R + 0.61 * P.delta;
+    const double rho = sqrt(yc * yc + zc * zc);
+    const double q = ipow_d(rho / R, 2), qa = ipow_d(rho / Ra, 2);
+    double f45, f15, f05, g45, g15, g05;
+    hyp_wall(q, f45, f15, f05);
+    hyp_wall(qa, g45, g15, g05);
+    const double psi6 = 3.0925052683774523 * ipow_d(sig / R, 10) / ipow_d(1 - q, 10) * f45;
+    const double psi3 = 4.712388980384691 * ipow_d(sig / R, 4) / ipow_d(1 - q, 4) * f15;
+    const double phi3 = 1.5707963267948966 * ipow_d(sig / Ra, 3) / ipow_d(1 - qa, 3) * g05;
+    return 2 * 3.14159265358979323846 * P.rho_s * P.delta * sig * sig * P.eps_sf * (psi6 - psi3 - sig / P.delta * phi3);
+}
+
 // Serial single-thread version (K3 computes one wall term per particle per thread).
 __device__ __forceinline__ double wall_one(const ChainParams& P, double z) {
     double boxE = 0.0;
@@ -253,6 +326,8 @@ __device__ __forceinline__ double wall_any(const ChainParams& P, double x, doubl
     else if (P.geometry == MCPM_GEOM_SLIT) d2 = zc * zc;
     double boxE = (d2 > P.sqr_pore_r || d2 < 0.0) ? MCPM_INT_MAX_D : 0.0;
     if (P.wall_kind == MCPM_WALL_SPHERE_LJ && P.geometry == MCPM_GEOM_SPHERE) boxE += sphere_wall(P, xc, yc, zc);
+    else if (P.wall_kind == MCPM_WALL_CYL_LJ104 && P.geometry == MCPM_GEOM_CYLINDER) boxE += cyl_lj104(P, yc, zc);
+    else if (P.wall_kind == MCPM_WALL_CYL_STEELE && P.geometry == MCPM_GEOM_CYLINDER) boxE += cyl_steele(P, yc, zc);
     else if (P.wall_kind == MCPM_WALL_SLIT_LJ && P.geometry == MCPM_GEOM_SLIT) {
         double usf = 0.0;
         for (int i = 0; i < P.n_layers; i++) {

@@ -6,7 +6,7 @@ import os
 
 RNG_PHILOX, RNG_REPLAY = 0, 1
 GEOM_BULK, GEOM_SLIT, GEOM_CYLINDER, GEOM_SPHERE = 0, 1, 2, 3
-WALL_NONE, WALL_SLIT_LJ, WALL_SPHERE_LJ = 0, 1, 2
+WALL_NONE, WALL_SLIT_LJ, WALL_SPHERE_LJ, WALL_CYL_LJ104, WALL_CYL_STEELE = 0, 1, 2, 3, 4
 PAIR_LJ, PAIR_HS = 0, 1
 
 _dp = C.POINTER(C.c_double)

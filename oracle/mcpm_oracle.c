@@ -227,6 +227,84 @@ static double sphere_wall(const orc_system* s, double x, double y, double z) {
     usf *= 2. * M_PI * eps * dens;
     return usf;
 }
+/* ---- Gauss hypergeometric functions 2F1(a,b;1;z) with half-integer a, b for the cylindrical walls.  The reference evaluates them with
+ * the vendored Numerical-Recipes hypgeo (NumRecipes/hypgeo.h:46: power series for |z| <= 1/2, else Bulirsch-Stoer integration of the
+ * hypergeometric ODE from z0 = 1/2 — or, for z > 1, i.e. OUTSIDE the pore, from z0 = i/2 through the upper half plane, returning the real
+ * part).  Restated here in closed form: F(1/2,1/2) = 2K/pi, F(-1/2,1/2) = 2E/pi, F(-1/2,-1/2) = (2/pi)(2E - (1-z)K) with the complete
+ * elliptic integrals K(z), E(z) (arithmetic-geometric mean; for z > 1 the real parts of their continuation from above,
+ * Re K = K(1/z)/sqrt z, Re E = sqrt z E(1/z) - (z-1)/sqrt z K(1/z)), and Gauss' contiguous relation (DLMF 15.5.11)
+ *   (1-a) F(a-1,b) = -(2a - 1 + (b-a) z) F(a,b) - a (z-1) F(a+1,b)
+ * lowers a parameter by one at a time down to -9/2 (stable: 1e-15 against the series on 0 <= z < 1). */
+static void ellip_ke01(double m, double* K, double* E) {          /* 0 <= m < 1 */
+    double a = 1.0, b = sqrt(1.0 - m), c = sqrt(m), sum = 0.5 * c * c, pw = 1.0;
+    for (int n = 0; n < 12; n++) {
+        double an = 0.5 * (a + b), bn = sqrt(a * b);
+        c = 0.5 * (a - b); a = an; b = bn;
+        sum += pw * c * c; pw *= 2.0;
+    }
+    *K = M_PI / (2.0 * a);
+    *E = *K * (1.0 - sum);
+}
+static void ellip_ke(double m, double* K, double* E) {
+    if (m < 1.0) { ellip_ke01(m, K, E); return; }
+    double k, e, s = sqrt(m);
+    ellip_ke01(1.0 / m, &k, &e);
+    *K = k / s;
+    *E = s * e - (m - 1.0) / s * k;
+}
+/* T[i][j] = 2F1(1/2 - i, 1/2 - j; 1; z), i, j = 0..5 */
+static void hyp_table(double z, double T[6][6]) {
+    double K, E, p = 2.0 / M_PI;
+    ellip_ke(z, &K, &E);
+    T[0][0] = p * K; T[1][0] = T[0][1] = p * E; T[1][1] = p * (2 * E - (1 - z) * K);
+    for (int j = 0; j < 6; j++) {
+        double bb = 0.5 - j;
+        if (j >= 2) { T[0][j] = T[j][0]; T[1][j] = T[j][1]; }        /* symmetry in (a, b) */
+        for (int i = 2; i < 6; i++) {
+            double aa = 0.5 - (i - 1);                               /* lower a = aa to aa - 1 */
+            T[i][j] = -((2 * aa - 1 + (bb - aa) * z) * T[i - 1][j] + aa * (z - 1) * T[i - 2][j]) / (1 - aa);
+        }
+    }
+}
+static double hyp_m45_m45(double z) { double T[6][6]; hyp_table(z, T); return T[5][5]; }
+static void hyp_three_halves(double z, double* f_m15_m15, double* f_m15_m05) { double T[6][6]; hyp_table(z, T); *f_m15_m15 = T[2][2]; *f_m15_m05 = T[2][1]; }
+/* MC::CylindricalLJ10_4, potentials.cpp:412-444 (Tjatjopoulos et al. 1988, summed over layers as the reference does) */
+static double cyl_lj104(const orc_system* s, double y, double z) {
+    int nLayers = s->n_layers;
+    double delta = s->delta, sizeR = s->width[2] * 0.5, dens = s->rho_s, eps = s->eps_sf, sig = s->sig_sf, u1 = 0, u2 = 0;
+    double yPos = y - 0.5 * s->width[1], zPos = z - 0.5 * s->width[2];
+    double rho = sqrt(ipow(yPos, 2) + ipow(zPos, 2));
+    dens *= sig * sig; sizeR /= sig; delta /= sig; rho /= sig;
+    double x = sizeR - rho;
+    for (int i = 0; i < nLayers; i++) {
+        double Ri = sizeR + i * delta, arg = ipow(1 - x / Ri, 2), T[6][6];
+        hyp_table(arg, T);
+        u1 += 63. / 32. * 1. / (ipow(x, 10) * ipow(2.0 - x / Ri, 10)) * T[5][5];
+        u2 += 3. / (ipow(x, 4) * ipow(2.0 - x / Ri, 4)) * T[2][2];
+    }
+    return (u1 - u2) * M_PI * M_PI * dens * eps;
+}
+/* MC::CylindricalSteele10_4_3, potentials.cpp:445-469 (Siderius & Gelb 2011); alpha = 0.61 */
+static double cyl_steele(const orc_system* s, double y, double z) {
+    double delta = s->delta, sizeR = s->width[2] * 0.5, dens = s->rho_s, eps = s->eps_sf, sig = s->sig_sf, alpha = 0.61;
+    double yPos = y - 0.5 * s->width[1], zPos = z - 0.5 * s->width[2];
+    double rho = sqrt(ipow(yPos, 2) + ipow(zPos, 2));
+    double q = ipow(rho / sizeR, 2), Ra = sizeR + alpha * delta, qa = ipow(rho / Ra, 2), T[6][6], Ta[6][6];
+    hyp_table(q, T);
+    hyp_table(qa, Ta);
+    double f15 = T[2][2], g05 = Ta[2][1];
+    /* 4 sqrt(pi) Gamma(5.5)/Gamma(6), 4 sqrt(pi) Gamma(2.5)/Gamma(3), (4 sqrt(pi)/3) Gamma(2.5)/Gamma(3) */
+    double psi6 = 3.0925052683774523 * ipow(sig / sizeR, 10) / ipow(1 - q, 10) * T[5][5];
+    double psi3 = 4.712388980384691 * ipow(sig / sizeR, 4) / ipow(1 - q, 4) * f15;
+    double phi3 = 1.5707963267948966 * ipow(sig / Ra, 3) / ipow(1 - qa, 3) * g05;
+    return 2 * M_PI * dens * delta * sig * sig * eps * (psi6 - psi3 - sig / delta * phi3);
+}
+double orc_hyp2f1(int which, double z) {   /* test hook: 0: (-9/2,-9/2;1), 1: (-3/2,-3/2;1), 2: (-3/2,-1/2;1) */
+    double a, b;
+    if (which == 0) return hyp_m45_m45(z);
+    hyp_three_halves(z, &a, &b);
+    return which == 1 ? a : b;
+}
 /* MC::SlitLJ_Pot, potentials.cpp:381-402 */
 double orc_slit_wall(const orc_system* s, double zabs) {
     int nLayers = s->n_layers;
@@ -254,6 +332,8 @@ static double wall_at(const orc_system* s, double x, double y, double z) {
     else if (s->geometry == 1) sqrDist = zPos * zPos;
     if ((sqrDist > sqrPoreRadius) || (sqrDist < 0)) boxE = INT_MAX;
     if (s->wall_kind == 2 && s->geometry == 3) boxE += sphere_wall(s, x, y, z);   /* energy.cpp:69-77 */
+    else if (s->wall_kind == 3 && s->geometry == 2) boxE += cyl_lj104(s, y, z);
+    else if (s->wall_kind == 4 && s->geometry == 2) boxE += cyl_steele(s, y, z);
     else if (s->wall_kind == 1 && s->geometry == 1) boxE += orc_slit_wall(s, z);
     return boxE;
 }

@@ -26,7 +26,8 @@ extern "C" {
 typedef struct {
     int geometry;   /* 0 = bulk (PBC x,y,z), 1 = slit (PBC x,y; walls at z=0 and z=H), 2 = cylinder (PBC x), 3 = sphere (no PBC)
                        read.cpp:128-162 */
-    int wall_kind;  /* 0 = none, 1 = "lj" + slit -> SlitLJ_Pot, 2 = "lj" + sphere -> SphericalLJ_Pot   energy.cpp:69-77 */
+    int wall_kind;  /* 0 = none, 1 = "lj" + slit -> SlitLJ_Pot, 2 = "lj" + sphere -> SphericalLJ_Pot, 3 = "lj10-4" + cylinder ->
+                       CylindricalLJ10_4, 4 = "steele10-4-3" + cylinder -> CylindricalSteele10_4_3              energy.cpp:69-77 */
     int n_layers;   /* nLayersPerWall */
     int n_disp, n_vol, n_swap; /* move weights, main.cpp:67-70 */
     int n_equil_sets;
@@ -77,6 +78,7 @@ long long orc_run(orc_chain* c, long long nsteps, int correct_energy, unsigned c
 void orc_set_dr(orc_chain* c, double dr);                                  /* Simulation::dr, restart / tests */
 /* dout = {volume, width[0], width[1], width[2], dv, as-shipped running energy}; iout = {acceptanceVol, rejectionVol, nVolChanges} */
 void orc_get_volume_state(const orc_chain* c, double dout[6], long long iout[3]);
+double orc_hyp2f1(int which, double z);                                  /* 2F1 closed forms of the cylindrical walls (test hook) */
 double orc_wall_energy(orc_chain* c, double x, double y, double z);        /* boxE of EnergyOfParticle at a position */
 void orc_reset_stats(orc_chain* c);                                        /* MC.cpp:81-98 */
 void orc_adjust(orc_chain* c, int set);                                    /* moves.cpp:68-78 */

@@ -131,6 +131,8 @@ class COracle:
             L.orc_get_volume_state.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_longlong)]
             L.orc_wall_energy.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
             L.orc_wall_energy.restype = C.c_double
+            L.orc_hyp2f1.argtypes = [C.c_int, C.c_double]
+            L.orc_hyp2f1.restype = C.c_double
             L.orc_adjust.argtypes = [C.c_void_p, C.c_int]
             L.orc_run_sets.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_void_p]
             L.orc_get_state.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_longlong)]

@@ -31,7 +31,7 @@ extern "C" {
 // Same field order as oracle/mcpm_oracle.h::orc_system (single species, single box).
 struct mcref_system {
     int geometry;        // 0 = bulk, 1 = slit, 2 = cylinder, 3 = sphere
-    int wall_kind;       // 0 = none, 1 = "lj" slit wall (SlitLJ_Pot), 2 = "lj" sphere wall (SphericalLJ_Pot)
+    int wall_kind;       // 0 = none, 1 = "lj" slit wall (SlitLJ_Pot), 2 = "lj" sphere wall (SphericalLJ_Pot), 3 = "lj10-4" / 4 = "steele10-4-3" cylinder walls
     int n_layers;
     int n_disp, n_vol, n_swap;  // move weights (sim.nDispAttempts ...)
     int n_equil_sets;
@@ -82,7 +82,7 @@ struct Oracle : public MC {
         b.solidDens = s.rho_s;
         b.nLayersPerWall = s.n_layers;
         b.deltaLayers = s.delta;
-        b.fluid(0).vdwPot(0) = (s.wall_kind == 1 || s.wall_kind == 2) ? "lj" : "";
+        b.fluid(0).vdwPot(0) = (s.wall_kind == 1 || s.wall_kind == 2) ? "lj" : (s.wall_kind == 3 ? "lj10-4" : (s.wall_kind == 4 ? "steele10-4-3" : ""));
         b.fluid(0).sigma(0) = s.sig_sf;
         b.fluid(0).epsilon(0) = s.eps_sf;
         b.fluid(0).mu = s.mu;
@@ -227,7 +227,9 @@ struct Oracle : public MC {
         if (thermoSys.nBoxes != 1 || thermoSys.nSpecies != 1) return -1;
         const Box& b = box(0);
         s->geometry = b.geometry == "slit" ? 1 : (b.geometry == "bulk" ? 0 : (b.geometry == "cylinder" ? 2 : (b.geometry == "sphere" ? 3 : -1)));
-        s->wall_kind = (box(0).fluid(0).vdwPot(0) == "lj" && b.geometry == "slit") ? 1 : ((box(0).fluid(0).vdwPot(0) == "lj" && b.geometry == "sphere") ? 2 : 0);
+        const std::string& wp = box(0).fluid(0).vdwPot(0);
+        s->wall_kind = (wp == "lj" && b.geometry == "slit") ? 1 : (wp == "lj" && b.geometry == "sphere") ? 2 : (wp == "lj10-4" && b.geometry == "cylinder") ? 3 :
+                       (wp == "steele10-4-3" && b.geometry == "cylinder") ? 4 : 0;
         s->pair_kind = fluid(0).vdwPot(0) == "hs" ? 1 : 0;
         s->pressure = thermoSys.press; s->dv = sim.dv(0);
         s->n_layers = b.nLayersPerWall;

@@ -15,7 +15,12 @@ RTOL = 1e-10
 
 @pytest.fixture(scope="module")
 def f4():
-    return np.load(os.path.join(GOLDEN, "reference_f4.npz")), json.load(open(os.path.join(GOLDEN, "reference_f4.json")))
+    """reference_f4 (sphere, hard spheres, NPT) and reference_cyl (cylindrical walls) merged."""
+    arrays = dict(np.load(os.path.join(GOLDEN, "reference_f4.npz")))
+    arrays.update(dict(np.load(os.path.join(GOLDEN, "reference_cyl.npz"))))
+    meta = json.load(open(os.path.join(GOLDEN, "reference_f4.json")))
+    meta.update(json.load(open(os.path.join(GOLDEN, "reference_cyl.json"))))
+    return arrays, meta
 
 
 def close(a, b, rtol=RTOL):
@@ -23,7 +28,7 @@ def close(a, b, rtol=RTOL):
     return bool(np.all(np.abs(a - b) <= rtol * np.maximum(np.abs(b), np.mean(np.abs(b)) + 1e-300)))
 
 
-@pytest.mark.parametrize("name", ["sph", "hs", "hsov"])
+@pytest.mark.parametrize("name", ["sph", "hs", "hsov", "cyl3", "cyl4"])
 def test_k1_k3_energies(mcpm, f4, name):
     arrays, meta = f4
     s = O.make_system(**meta[name]["system"])
@@ -44,7 +49,7 @@ def test_k1_k3_energies(mcpm, f4, name):
 
 def test_unsupported_systems_are_refused(mcpm):
     with mcpm.Engine(1, 64) as e:
-        for change in ({"n_vol": 1}, {"n_vol": 1, "pressure": 1e7, "geometry": 1}, {"n_vol": 1, "pressure": 1e7, "n_swap": 1}, {"wall_kind": 3},
+        for change in ({"n_vol": 1}, {"n_vol": 1, "pressure": 1e7, "geometry": 1}, {"n_vol": 1, "pressure": 1e7, "n_swap": 1}, {"wall_kind": 5},
                        {"pair_kind": 2}, {"geometry": 4}):
             s = O.argon_bulk(size=30.0, rcut=12.0)
             s.n_swap = 0
@@ -56,7 +61,8 @@ def test_unsupported_systems_are_refused(mcpm):
 
 
 @pytest.mark.parametrize("threads", [0, 64, 256])
-@pytest.mark.parametrize("name,mkey,start", [("spht", "sph_trace", "sph"), ("hst", "hs_trace", "hs"), ("hsgt", "hsg_trace", "hs"), ("nptt", "npt_trace", None)])
+@pytest.mark.parametrize("name,mkey,start", [("spht", "sph_trace", "sph"), ("hst", "hs_trace", "hs"), ("hsgt", "hsg_trace", "hs"), ("nptt", "npt_trace", None),
+                                              ("cyl3t", "cyl3_trace", "cyl3"), ("cyl4t", "cyl4_trace", "cyl4")])
 def test_replay_traces_match_the_reference(mcpm, f4, golden, name, mkey, start, threads):
     """The reference's own mt19937_64 stream replayed on the GPU: identical accept/reject sequence (translations, insertions through the
     sphere branch of InsertParticle, hard-sphere deletions that are always accepted, volume moves against the as-shipped running energy),
@@ -96,7 +102,7 @@ def test_replay_traces_match_the_reference(mcpm, f4, golden, name, mkey, start, 
             assert np.allclose(v[:, 6], rv[:, 6], rtol=1e-9, atol=0)                       # the reference's running box energy, as shipped
             assert e.get_system(0).width[2] == pytest.approx(rv[-1, 1], rel=1e-13)         # the chain's system follows its box
         fx, fy, fz = e.get_positions(0)
-        tol = dict(rtol=1e-13, atol=1e-12) if name in ("spht", "nptt") else dict(rtol=0, atol=0)   # device sin / cos (sphere insertions), exp / log / cbrt (box width)
+        tol = dict(rtol=1e-13, atol=1e-12) if name in ("spht", "nptt", "cyl3t", "cyl4t") else dict(rtol=0, atol=0)   # device sin / cos (sphere insertions), exp / log / cbrt (box width)
         assert np.allclose(fx, arrays[name + "_fx"], **tol) and np.allclose(fy, arrays[name + "_fy"], **tol) and np.allclose(fz, arrays[name + "_fz"], **tol)
         box, _, _ = e.box_energy(0)
         assert close(box, arrays[name + "_fbox"])

@@ -116,12 +116,13 @@ def test_parser_recognises_what_the_engine_refuses(mcpm, tmp_path):
     p = tmp_path / "cyl.in"
     p.write_text(text.replace("Geometry sphere", "Geometry cylinder").replace("Cavity Ar VdwPotential lj", "Cavity Ar VdwPotential steele10-4-3"))
     rc, cfg = parse(mcpm, str(p))
-    assert rc == 0 and cfg.system.geometry == mcpm.GEOM_CYLINDER and cfg.system.wall_kind == 4
+    assert rc == 0 and cfg.system.geometry == mcpm.GEOM_CYLINDER and cfg.system.wall_kind == 4      # CylindricalSteele10_4_3: supported
     assert list(cfg.system.width) == [30.0, 30.0, 30.0]            # PBC length 2*rcut along x, diameter on y and z
-    assert mcpm.lib().mcpm_simulate(str(p).encode(), str(tmp_path).encode(), 2) == 4
     p = tmp_path / "eam.in"
     p.write_text(text.replace("Ar Ar VdwPotential lj", "Ar Ar VdwPotential eam_na"))
     assert mcpm.lib().mcpm_simulate(str(p).encode(), str(tmp_path).encode(), 2) == 4
+    assert b"EAM" in mcpm.lib().mcpm_last_error()
     p = tmp_path / "gibbs.in"
     p.write_text(open(os.path.join(GOLDEN, "lj_npt.in")).read().replace("ExternalPressure 3.0e7\n", ""))
     assert mcpm.lib().mcpm_simulate(str(p).encode(), str(tmp_path).encode(), 2) == 4
+    assert b"Gibbs" in mcpm.lib().mcpm_last_error()
