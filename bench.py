@@ -570,7 +570,7 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the short C1/C3/C4/C5 runs and the K3/K1 records")
     ap.add_argument("--no-literal", action="store_true", help="skip the literal 40-chain isotherm sub-record")
     ap.add_argument("--speculation", type=int, default=None, help="mcpm_use_speculation mode (experiments)")
-    ap.add_argument("--pool", type=int, default=None, help="mcpm_use_pool: 16 / 20 warps per persistent CTA, 0 = one CTA per chain (experiments)")
+    ap.add_argument("--pool", type=int, default=None, help="mcpm_use_pool (experiments build, MCPM_EXPERIMENTS=1): warps per persistent CTA, 0 = one CTA per chain")
     args = ap.parse_args()
     if args.warmup < MIN_WARMUP:
         print(f"bench.py: --warmup {args.warmup} raised to {MIN_WARMUP} (timing rule: at least 3 warm-up steps; both arms)", file=sys.stderr)

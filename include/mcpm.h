@@ -202,13 +202,6 @@ int mcpm_get_stats(mcpm_ctx* ctx, mcpm_chain_stats* stats /* [n_chains] */);
  * 1.5 N pair evaluations per step at 20 % translation acceptance.  enable = 0 re-sums both energies every move, exactly
  * like MC::MoveParticle / MC::SwapParticle. */
 int mcpm_use_energy_cache(mcpm_ctx* ctx, int enable);
-/* OPT-IN alternative for one-warp chains (the choice when many chains share an SM): k2_pool, one persistent CTA per SM whose warps own
- * shared-memory slots of up to three capacity classes and take chains from work queues, longest first; a chain that outgrows its slot
- * pauses and is finished by a follow-up launch.  warps = 12 (168 registers per thread), 14, 16 (128) or 20 (96); 0 = off (default: the
- * one-CTA-per-chain kernel k2_chains, whose shared memory is sized for the largest chain).  Same chains, same results.  Measured on
- * B200 (round 2, profiles/r02_pool.md): equal to k2_chains at 12 warps, SLOWER at 16 — the claim loop around the chain loop costs the
- * registers the scan's instruction-level parallelism needs — so it is not the default. */
-int mcpm_use_pool(mcpm_ctx* ctx, int warps);
 /* The cache itself, for drift checks: pair[j] = the pairPotE (K) the engine currently carries for particle j of `chain`
  * (what MC::EnergyOfParticle would store, src/energy.cpp:102-104); *valid = 0 if no K2 launch has left a consistent cache
  * for the chain's present configuration (then pair[] is not written).  Compare with mcpm_box_energy's per_pair. */

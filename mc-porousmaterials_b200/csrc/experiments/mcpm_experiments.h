@@ -7,7 +7,10 @@
  *                             1.7-2x slower than one warp per chain (round 1, config C2).
  *   mcpm_use_dual_candidates  one warp per chain evaluates TWO consecutive steps against the same configuration in one
  *                             interleaved instruction stream; the second is used only if the first is rejected.  25 % slower
- *                             (168 registers cost a resident chain per SM; selection and decision stay serial). */
+ *                             (168 registers cost a resident chain per SM; selection and decision stay serial).
+ *   mcpm_use_pool             (round 2) k2_pool: one persistent CTA per SM whose warps own shared-memory slots of up to three capacity
+ *                             classes and take chains from work queues, longest first; warps = 12 / 14 / 16 / 20 per CTA, 0 = off.  Equal to
+ *                             k2_chains at 12 warps, slower at 16 (register pressure): profiles/r02_pool.md. */
 #ifndef MCPM_EXPERIMENTS_H
 #define MCPM_EXPERIMENTS_H
 #include "../../../include/mcpm.h"
@@ -16,6 +19,7 @@ extern "C" {
 #endif
 int mcpm_use_subwarp(mcpm_ctx* ctx, int enable);
 int mcpm_use_dual_candidates(mcpm_ctx* ctx, int enable);
+int mcpm_use_pool(mcpm_ctx* ctx, int warps);
 #ifdef __cplusplus
 }
 #endif

@@ -678,6 +678,7 @@ static int pick_threads(const mcpm_ctx* c, int maxn) {
     return t;
 }
 
+#ifdef MCPM_EXPERIMENTS
 // ---- k2_pool: capacity classes, slot mix and queues ---------------------------------------------------------------------
 // Slot a chain of n particles needs for one launch: headroom for the fluctuations of N (a chain that still outgrows it pauses and
 // is finished in a full-size slot).
@@ -744,6 +745,8 @@ static size_t pool_layout(const mcpm_ctx* c, const std::vector<int>& chains, boo
     n_ctas = std::min(c->num_sms, (n_chains + slots - 1) / slots);
     return (off + (size_t)slots * stride) * sizeof(double) + ((sizeof(RunArgs) + 15) / 16) * 16;
 }
+
+#endif  // MCPM_EXPERIMENTS
 
 int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     if (!c || !p) return fail(MCPM_ERR_ARG, "null argument");
@@ -889,8 +892,13 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     const bool use_dual = false;
 #endif
     // One warp per chain on the energy cache: the persistent pooled kernel (shared-memory slots per capacity class, work queues).
+#ifdef MCPM_EXPERIMENTS
     const bool use_pool = c->use_pool && !use_k2c && !use_pair && !use_spec && !use_sub && !use_dual && threads == 32 && cache_now && all_fast && !sample && !global_path && same_pbz;
+#else
+    const bool use_pool = false;
+#endif
     c->last_kernel = use_pool ? "k2_pool" : use_k2c ? "k2_cells" : use_pair ? (lean_width == 4 ? "k2_quad" : "k2_pair") : use_spec ? "k2_spec" : (use_sub ? "k2_sub" : (use_dual ? "k2_dual" : "k2_chains"));
+#ifdef MCPM_EXPERIMENTS
     if (use_pool) {
         if (!c->d_pool_next) CU(cudaMalloc(&c->d_pool_next, sizeof(int) * MCPM_POOL_MAX_CLASSES));
         for (int k = 0; k < c->n_chains; k++) c->h_state[k].res.paused = 0;
@@ -914,7 +922,9 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
             todo.clear();
             for (int k = 0; k < c->n_chains; k++) if (c->h_state[k].res.paused) todo.push_back(k);
         }
-    } else if (use_k2c) {
+    } else
+#endif
+    if (use_k2c) {
         bool widom = false;
         for (int k = 0; k < c->n_chains; k++) widom = widom || (c->h_params[k].n_swap == 0 && !p->no_sampling);
         CU(launch_k2_cells(p->rng_mode, widom, c->n_chains, c->d_params, c->d_state, c->d_order, c->d_x, c->d_y, c->d_z, a, c->d_kc_items,
@@ -1101,6 +1111,7 @@ int mcpm_use_subwarp(mcpm_ctx* c, int enable) {
 }
 #endif
 
+#ifdef MCPM_EXPERIMENTS
 int mcpm_use_pool(mcpm_ctx* c, int warps) {
     if (!c) return fail(MCPM_ERR_ARG, "null context");
     if (warps != 0 && warps != 12 && warps != 14 && warps != 16 && warps != 20) return fail(MCPM_ERR_ARG, "k2_pool runs 12, 16 or 20 warps per CTA (0: the one-CTA-per-chain kernel)");
@@ -1108,6 +1119,7 @@ int mcpm_use_pool(mcpm_ctx* c, int warps) {
     if (warps) c->pool_warps = warps;
     return MCPM_OK;
 }
+#endif
 
 int mcpm_use_energy_cache(mcpm_ctx* c, int enable) {
     if (!c) return fail(MCPM_ERR_ARG, "null context");

@@ -538,8 +538,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k2_chains(const ChainParams* __res
     if (tid == 0) states[chain] = S;
 }
 
+#ifdef MCPM_EXPERIMENTS
 // ================================================================================================
-// K2p — k2_pool: the one-warp-per-chain hot kernel as ONE PERSISTENT CTA PER SM with a shared-memory pool.
+// K2p — k2_pool (EXPERIMENT, built only by `make EXPERIMENTS=1`; measured not faster: profiles/r02_pool.md):
+// the one-warp-per-chain hot kernel as ONE PERSISTENT CTA PER SM with a shared-memory pool.
 //
 // k2_chains sizes every CTA's shared memory for the LARGEST chain of the launch (17 KB at capacity 704), which caps the residency at
 // 12 chains per SM although the isotherm's mean loading is half of that and a third of its state points hold < 150 particles.  Here a CTA
@@ -641,6 +643,8 @@ cudaError_t launch_k2_pool(int rng_mode, bool pbz, int warps, int n_ctas, size_t
     MCPM_POOL_GO(20);                      // 96 registers per thread: more warps per scheduler, less instruction-level parallelism
 #undef MCPM_POOL_GO
 }
+
+#endif  // MCPM_EXPERIMENTS
 
 // ================================================================================================
 // K3 — full box energy (MC::BoxEnergy, src/energy.cpp:106-124).

@@ -11,7 +11,7 @@ void set_last_error(const char* msg);   // mcpm_api.cu: the per-thread message b
 cudaError_t launch_k2(int rng_mode, int n_chains, int threads, bool fast, bool sample, bool cache, const ChainParams* params, ChainState* states, const int* order,
                       double* X, double* Y, double* Z, const RunArgs& a, int max_smem_optin, cudaStream_t stream);
 size_t k2_smem_limit_cap(int max_smem_optin);
-// k2_pool: persistent CTAs, one warp per chain, shared-memory slots of several capacity classes (see mcpm_kernels.cu)
+// k2_pool (EXPERIMENTS build only): persistent CTAs, one warp per chain, shared-memory slots of several capacity classes
 size_t pool_state_stride_doubles();
 cudaError_t launch_k2_pool(int rng_mode, bool pbz, int warps, int n_ctas, size_t smem, const ChainParams* params, ChainState* states, const int* order,
                            double* X, double* Y, double* Z, const RunArgs& a, const PoolLayout& L, cudaStream_t stream);

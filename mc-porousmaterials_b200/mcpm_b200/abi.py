@@ -132,7 +132,6 @@ PROTOTYPES = {
     "mcpm_box_energy_all": (C.c_int, [C.c_void_p, C.POINTER(BoxEnergy)]),
     "mcpm_use_speculation": (C.c_int, [C.c_void_p, C.c_int]),
     "mcpm_use_energy_cache": (C.c_int, [C.c_void_p, C.c_int]),
-    "mcpm_use_pool": (C.c_int, [C.c_void_p, C.c_int]),
     "mcpm_get_energy_cache": (C.c_int, [C.c_void_p, C.c_int, _dp, _ip]),
     "mcpm_use_cell_list": (C.c_int, [C.c_void_p, C.c_int]),
     "mcpm_apply_move": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp]),
@@ -163,6 +162,7 @@ PROTOTYPES = {
 EXPERIMENTAL = {
     "mcpm_use_subwarp": (C.c_int, [C.c_void_p, C.c_int]),
     "mcpm_use_dual_candidates": (C.c_int, [C.c_void_p, C.c_int]),
+    "mcpm_use_pool": (C.c_int, [C.c_void_p, C.c_int]),
 }
 
 

@@ -141,7 +141,9 @@ class Engine:
         check(self.L.mcpm_set_stream_ids(self.h, ids.ctypes.data_as(C.POINTER(C.c_uint))))
 
     def use_pool(self, warps=16):
-        check(self.L.mcpm_use_pool(self.h, int(warps)))
+        """Experimental pooled kernel (libmcpm_exp.so only); switching it off is a no-op on the product library."""
+        if warps or abi.has_experiments():
+            check(self.L.mcpm_use_pool(self.h, int(warps)))
 
     def use_energy_cache(self, enable=True):
         check(self.L.mcpm_use_energy_cache(self.h, 1 if enable else 0))

@@ -28,8 +28,8 @@ def first_divergence(a, b):
 def test_replay_trace_matches_reference_golden(mcpm, golden, name, threads, cache):
     """'cache' at 32 threads = the pooled persistent kernel k2_pool, 'classic' = one CTA per chain (k2_chains) for one-warp chains too;
     'dual' = the opt-in dual-candidate kernel (k2_dual, one warp per chain, two steps per round)."""
-    if cache == "classic" and threads != 32:
-        pytest.skip("the pooled kernel only replaces the one-warp variant")
+    if cache == "classic" and (threads != 32 or not mcpm.has_experiments()):
+        pytest.skip("'classic' only differs from 'cache' in the experiments build, where the pooled kernel replaces the one-warp variant")
     if cache in ("subwarp", "dual") and not mcpm.has_experiments():
         pytest.skip("experimental kernels: build with `make EXPERIMENTS=1` and run with MCPM_EXPERIMENTS=1")
     if cache == "subwarp" and threads != 32:
@@ -50,7 +50,7 @@ def test_replay_trace_matches_reference_golden(mcpm, golden, name, threads, cach
         e.use_subwarp(cache == "subwarp")
         e.use_speculation({"spec": 1, "pair": 2}.get(cache, 0))
         e.use_dual_candidates(cache == "dual")
-        e.use_pool(0 if cache == "classic" else 16)
+        e.use_pool(16 if (cache is True and mcpm.has_experiments()) else 0)
         e.set_system(s)
         e.set_positions(0, x, y, z)
         per_set, traces = [], []
@@ -69,7 +69,7 @@ def test_replay_trace_matches_reference_golden(mcpm, golden, name, threads, cach
             assert st.energy == pytest.approx(st.energy_check, rel=RTOL)
             assert st.pair == pytest.approx(st.pair_check, rel=RTOL, abs=1e-9)
         if cache in (True, "classic") and threads == 32:
-            assert e.last_kernel_name() == ("k2_pool" if (cache is True and name != "bulkt") else "k2_chains")   # (NVT samples Widom: never pooled)
+            assert e.last_kernel_name() == ("k2_pool" if (cache is True and name != "bulkt" and mcpm.has_experiments()) else "k2_chains")   # (NVT samples Widom: never pooled)
         got = np.concatenate(traces)
         div = first_divergence(got, arrays[name + "_trace"])
         assert div == -1, f"first divergence at step {div}"
@@ -123,12 +123,13 @@ def test_philox_chain_follows_oracle(mcpm, golden, threads, cache):
         e.use_energy_cache(bool(cache))
         e.use_speculation({"spec": 1, "pair": 2}.get(cache, 0))
         e.use_dual_candidates(cache == "dual")
-        e.use_pool(16 if (cache is True and threads == 32) else 0)       # the pooled one-warp kernel is opt-in
+        pooled = cache is True and threads == 32 and mcpm.has_experiments()
+        e.use_pool(16 if pooled else 0)                                   # the pooled one-warp kernel: experiments build only
         e.set_system(s)
         for c in range(nchains):
             e.set_positions(c, x, y, z)
         stats, tr = e.run(1, sets, sps, seed=seed, trace=True, threads=threads, check_energy=1)
-        assert e.last_kernel_name() == {True: "k2_pool" if threads == 32 else "k2_chains", False: "k2_chains", "spec": "k2_spec", "dual": "k2_dual", "pair": "k2_pair"}[cache]
+        assert e.last_kernel_name() == {True: "k2_pool" if pooled else "k2_chains", False: "k2_chains", "spec": "k2_spec", "dual": "k2_dual", "pair": "k2_pair"}[cache]
         for c in range(nchains):
             o = O.COracle(s, 1024)
             o.set_positions(x, y, z)
@@ -650,6 +651,8 @@ def test_lean_speculation_is_chosen_by_chains_per_sm(mcpm, golden, nch, kernel):
 
 @pytest.mark.parametrize("warps", [16, 20])
 def test_pooled_kernel_mixed_loadings_and_slot_classes(mcpm, golden, warps):
+    if not mcpm.has_experiments():
+        pytest.skip("experimental kernel: build with `make EXPERIMENTS=1` and run with MCPM_EXPERIMENTS=1")
     """k2_pool: 40 chains of very different size (3 ... 504 particles: three slot classes in one CTA mix) against the C oracle on
     the same Philox streams — traces, configurations, counters, accumulators — and bit-identical to the one-CTA-per-chain kernel."""
     arrays, meta = golden
@@ -696,6 +699,8 @@ def test_pooled_kernel_mixed_loadings_and_slot_classes(mcpm, golden, warps):
 
 @pytest.mark.parametrize("mode", ["philox", "replay"])
 def test_pooled_chain_outgrows_its_slot(mcpm, golden, mode):
+    if not mcpm.has_experiments():
+        pytest.skip("experimental kernel: build with `make EXPERIMENTS=1` and run with MCPM_EXPERIMENTS=1")
     """Chains that start with 20 particles get a small slot; at mu = -1134 K they fill up to ~550 during the launch, pause when the slot
     is full and are finished by a follow-up launch in full-size slots.  The result is the chain the oracle produces (same trace, counters
     of the interrupted set, accumulators, dr adaptation, replay cursor)."""

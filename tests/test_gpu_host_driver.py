@@ -182,3 +182,35 @@ def test_npt_input_moves_the_box(tmp_path):
     assert len(set(widths)) > 1 and all(v == pytest.approx(w ** 3, rel=1e-6) for w, v in zip(widths, vols))
     assert all(int(r[7]) == 300 for r in rows)
     assert all(25.0 < w < 60.0 for w in widths)
+
+
+def test_driver_isotherm_matches_loadings_of_the_compiled_reference(tmp_path):
+    """The C++ host driver end to end (its own random initial configurations, minimisation, Philox chains, final gather) on BASELINE config
+    C2: `ChemicalPotentialSweep -1800 -1134 40` is exactly the 40-point grid.  Its isotherm file is compared with the loadings of the
+    COMPILED reference at the 8 fixture points (tests/golden/isotherm_reference.json).  The driver starts from N0 = 50 random particles,
+    not from the fixture's equilibrated configurations, so 100 of 180 sets are equilibration (the condensed branch densifies slowly: after only
+    6e5 steps the mu = -1134 K point still sat 8 particles low).  Criterion: 3 standard errors of the reference, or 1.2 %, or 0.6 particles —
+    whichever is largest."""
+    import json
+    ref = json.load(open(os.path.join(GOLDEN, "isotherm_reference.json")))
+    text = open(os.path.join(GOLDEN, "ar_cfg1.in")).read()
+    text = text.replace("ProductionSets 40", "ProductionSets 180").replace("EquilibriumSets 10", "EquilibriumSets 100")
+    text = text.replace("StepsPerSet 5000", "StepsPerSet 10000").replace("PrintEveryNSets 10", "PrintEveryNSets 180").replace("NumberOfParticles 450", "NumberOfParticles 50")
+    assert "ProductionSets 180" in text and "NumberOfParticles 50" in text and "StepsPerSet 10000" in text
+    inp = tmp_path / "iso.in"
+    R = 6
+    inp.write_text(text + f"ChemicalPotentialSweep -1800 -1134 40\nReplicas {R}\nSeed 20261020\nCapacity 704\n")
+    run_driver(tmp_path, str(inp), "--quiet")
+    iso = np.loadtxt(tmp_path / "ar_cfg1_isotherm.dat", skiprows=1)
+    assert iso.shape == (40, 6) and np.all(np.diff(iso[:, 0]) > 0)
+    bad = []
+    for pt in ref["points"]:
+        k = pt["k"]
+        assert iso[k, 0] == pytest.approx(pt["mu"], abs=1e-5)               # (the file prints 10 significant digits)
+        tol = max(3.0 * pt["sem"], 0.012 * pt["mean_n"], 0.6)          # measured deviations in round 2: 0.05 ... 1.6 particles
+        if abs(iso[k, 1] - pt["mean_n"]) > tol:
+            bad.append((k, iso[k, 1], pt["mean_n"], tol))
+        print("k=%2d  driver <N> = %8.3f  reference %8.3f +- %.3f  tol %.3f" % (k, iso[k, 1], pt["mean_n"], pt["sem"], tol))
+    assert not bad, bad
+    assert np.all(np.diff(iso[:, 1]) > -8.0)                       # a monotone isotherm up to noise, with the condensation jump
+    assert iso[-1, 1] > 2.0 * iso[20, 1]
