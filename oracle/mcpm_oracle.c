@@ -60,6 +60,10 @@ struct orc_chain {
     uint32_t ph_chain;
     int ph_slot;
     int sample_rdf;
+    /* two-box Gibbs system (thermoSys.nBoxes == 2): box 1 draws from box 0's uniform source; the global swap counters live in box 0 */
+    orc_chain* rng_src;
+    orc_chain* peer;
+    int box_id;
 };
 
 /* ---------------------------------------------------------------- uniform sources ---------- */
@@ -132,6 +136,7 @@ void orc_rng_philox(orc_chain* c, uint64_t seed, uint32_t chain_id, uint64_t fir
     c->ph_slot = 0; c->draws = 0;
 }
 double orc_random(orc_chain* c) {
+    if (c->rng_src) c = c->rng_src;
     c->draws++;
     if (c->rng_mode == RNG_MT) return q1_map(mt_next(c));
     if (c->rng_mode == RNG_REPLAY) return (c->draws <= c->replay_n) ? c->replay[c->draws - 1] : 0.0;
@@ -432,9 +437,13 @@ void orc_initial_config(orc_chain* c, int n) {
     for (int k = 0; k < n; k++) insert_particle(c, k);
 }
 /* MC::MoveParticle, moves.cpp:118-186.  Seven draws: box, species, index, dx, dy, dz, accept. */
+static int move_particle_in_box(orc_chain* c);
 static int move_particle(orc_chain* c) {
-    double T = c->sys.temperature;
     (void)(int)(orc_random(c) * c->n); /* box selection, :128-137 — single box */
+    return move_particle_in_box(c);
+}
+static int move_particle_in_box(orc_chain* c) {
+    double T = c->sys.temperature;
     (void)(int)(orc_random(c) * c->n); /* species selection, :138-147 — single species */
     c->n_displacements++; c->tot_disp++;
     c->b_old = c->b_energy;
@@ -550,6 +559,98 @@ static int change_volume(orc_chain* c) {
     }
     free(sp);
     return (4 << 1) | acc;
+}
+/* ---- two boxes (Gibbs ensemble, thermoSys.nBoxes == 2) ------------------------------------------------------------------
+ * Scope: the branches the stock build can run — MoveParticle's box selection and SwapParticle's Gibbs branch.  ChangeVolume's
+ * Gibbs branch cannot be reached in the stock build (it aborts on entry, quirk Q19) and is not restated: n_vol must be 0. */
+void orc_link_boxes(orc_chain* a, orc_chain* b) {
+    a->peer = b; b->peer = a; a->box_id = 0; b->box_id = 1; b->rng_src = a; a->rng_src = NULL;
+}
+/* MC::MoveParticle with two boxes, moves.cpp:127-137: rand = int(u*N_total); the first box with rand <= cumulative count. */
+static int gibbs_move(orc_chain* a) {
+    orc_chain* box[2] = {a, a->peer};
+    double rnd = (int)(orc_random(a) * (box[0]->n + box[1]->n));
+    int tmp = 0, ith = 0;
+    for (int i = 0; i < 2; i++) {
+        tmp += box[i]->n;
+        if (rnd <= tmp) { ith = i; break; }
+    }
+    return move_particle_in_box(box[ith]) | (ith << 4);
+}
+static double bar_weight(const orc_chain* c, double barC, double energy);
+/* MC::SwapParticle, Gibbs branch, moves.cpp:342-400.  Returns (5<<1)|accepted (6<<1 when the donor box is empty), box bit = inBox. */
+static int gibbs_swap(orc_chain* a) {
+    orc_chain* box[2] = {a, a->peer};
+    double T = a->sys.temperature;
+    a->n_swaps++; a->tot_swap++;
+    int in = (orc_random(a) < 0.5) ? 0 : 1, out = 1 - in;
+    orc_chain *ci = box[in], *co = box[out];
+    if (co->n <= 0) return (6 << 1) | (in << 4);
+    (void)(int)(orc_random(a) * ci->n);                 /* species selection, :352-360 */
+    int slot = ci->n;                                   /* inIndex = nParts+1 */
+    ci->b_old = ci->b_energy; co->b_old = co->b_energy;
+    insert_particle(ci, slot);
+    energy_of_slot(ci, slot);
+    double inEnergy = ci->pe_tot[slot];
+    ci->widom_insert += bar_weight(ci, ci->bar_c, inEnergy) * ci->volume * exp(-0.5 * inEnergy / T) / (ci->n + 1);
+    ci->widom_insertions++;
+    int o = (int)(orc_random(a) * co->n + 1) - 1;       /* :370 */
+    energy_of_slot(co, o);
+    double outEnergy = co->pe_tot[o];
+    co->widom_delete += bar_weight(co, co->bar_c, outEnergy) * co->volume * exp(0.5 * outEnergy / T) / (co->n + 1);
+    co->widom_deletions++;
+    double deltaE = inEnergy - outEnergy;
+    double arg = deltaE + log(co->volume * (ci->n + 1) / (ci->volume * co->n)) * T;   /* :376 */
+    if (orc_random(a) < exp(-arg / T)) {
+        a->accept_swap++; a->tot_swap_acc++;
+        ci->n++;
+        double pairE = 0.5 * ci->pe_pair[slot], wallE = ci->pe_wall[slot];
+        ci->b_pair += pairE; ci->b_wall += wallE; ci->b_energy += 0. + pairE + wallE;
+        ci->e_pair += ci->pe_pair[slot]; ci->e_wall += wallE; ci->e_energy += ci->pe_pair[slot] + wallE;
+        double fPair = co->pe_pair[o], fWall = co->pe_wall[o];
+        int last = co->n - 1;
+        co->x[o] = co->x[last]; co->y[o] = co->y[last]; co->z[o] = co->z[last];
+        co->pe_pair[o] = co->pe_pair[last]; co->pe_wall[o] = co->pe_wall[last]; co->pe_tot[o] = co->pe_tot[last];
+        co->n--;
+        pairE = 0.5 * co->pe_pair[o]; wallE = co->pe_wall[o];          /* read after the overwrite (Q3), :392-398 */
+        co->b_pair -= pairE; co->b_wall -= wallE; co->b_energy -= 0. + pairE + wallE;
+        co->e_pair -= fPair; co->e_wall -= fWall; co->e_energy -= fPair + fWall;
+        return (5 << 1) | 1 | (in << 4);
+    }
+    a->reject_swap++;
+    return (5 << 1) | (in << 4);
+}
+/* Body of the step loop for a linked pair (call on box 0), main.cpp:67-71. */
+int orc_gibbs_step(orc_chain* a, int correct) {
+    int nD = a->sys.n_disp, nV = a->sys.n_vol, nS = a->sys.n_swap, code = 0;
+    if (a->rng_mode == RNG_PHILOX) a->ph_slot = 0;
+    double r = orc_random(a) * (nD + nV + nS);
+    if (r <= nD) code = gibbs_move(a);
+    else if (r <= nD + nV) code = (4 << 1);             /* not restated, see above */
+    else if (r <= nD + nV + nS) code = gibbs_swap(a);
+    if (correct) { correct_energy(a); correct_energy(a->peer); }
+    if (a->rng_mode == RNG_PHILOX) a->ph_step++;
+    return code;
+}
+/* Sets of a linked pair: ResetStats and AdjustMCMoves act on both boxes (MC.cpp:81-98, moves.cpp:68-87); ComputeWidom is a no-op
+ * with two boxes (moves.cpp:415). */
+void orc_gibbs_run_sets(orc_chain* a, int first_set, int n_sets, long long steps_per_set, int correct, unsigned char* trace) {
+    orc_chain* b = a->peer;
+    for (int set = first_set; set < first_set + n_sets; set++) {
+        orc_reset_stats(a); orc_reset_stats(b);
+        for (long long s = 0; s < steps_per_set; s++) {
+            int code = orc_gibbs_step(a, correct);
+            if (trace) *trace++ = (unsigned char)code;
+            if (set > a->sys.n_equil_sets) {
+                for (int k = 0; k < 2; k++) {
+                    orc_chain* c = k ? b : a;
+                    double n = (double)c->n, e = c->e_energy;
+                    c->sum_n += n; c->sum_n2 += n * n; c->sum_e += e; c->sum_e2 += e * e; c->samples++;
+                }
+            }
+        }
+        orc_adjust(a, set); orc_adjust(b, set);
+    }
 }
 /* Body of the step loop, main.cpp:67-71. */
 int orc_step(orc_chain* c, int correct) {

@@ -87,6 +87,13 @@ void orc_adjust(orc_chain* c, int set);                                    /* mo
 void orc_run_sets(orc_chain* c, int first_set, int n_sets, long long steps_per_set, int correct_energy,
                   unsigned char* trace);
 
+/* Two boxes (Gibbs ensemble, thermoSys.nBoxes == 2): `b` becomes box 1 of `a`'s system and draws from a's uniform source; the
+ * global swap counters live in a.  moves.cpp:127-137 (box selection of MoveParticle), 342-400 (SwapParticle's Gibbs branch).
+ * Codes: translation | box<<4; (5<<1)|acc | inBox<<4 transfer attempt; (6<<1) | inBox<<4 donor box empty.  n_vol must be 0. */
+void orc_link_boxes(orc_chain* a, orc_chain* b);
+int orc_gibbs_step(orc_chain* a, int correct_energy);
+void orc_gibbs_run_sets(orc_chain* a, int first_set, int n_sets, long long steps_per_set, int correct_energy, unsigned char* trace);
+
 /* dout = {pairPotE, manyBodyE, boxE, energy, dr, volume, oldEnergy, temperature,
  *         exact pair (halved), exact wall, exact energy, sumN, sumN2, sumE, sumE2, samples}
  * iout = {n, acceptance, rejection, nDisplacements, acceptSwap, rejectSwap, nSwaps, n,

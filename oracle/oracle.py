@@ -143,6 +143,10 @@ class COracle:
             L.orc_set_sample_rdf.argtypes = [C.c_void_p, C.c_int]
             L.orc_get_rdf.argtypes = [C.c_void_p, _dp]
             L.orc_get_widom.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_longlong)]
+            L.orc_link_boxes.argtypes = [C.c_void_p, C.c_void_p]
+            L.orc_gibbs_step.argtypes = [C.c_void_p, C.c_int]
+            L.orc_gibbs_step.restype = C.c_int
+            L.orc_gibbs_run_sets.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_void_p]
             cls._lib = L
         return cls._lib
 
@@ -249,6 +253,22 @@ class COracle:
     def run_sets(self, first_set, n_sets, steps_per_set, correct_energy=0, trace=False):
         buf = np.zeros(n_sets * steps_per_set if trace else 1, dtype=np.uint8)
         self.L.orc_run_sets(self.h, first_set, n_sets, steps_per_set, correct_energy, buf.ctypes.data if trace else None)
+        return buf if trace else None
+
+    # -- two boxes (Gibbs ensemble): `other` becomes box 1 of this oracle's system and draws from this oracle's uniform source
+    def link(self, other):
+        self.peer = other
+        self.L.orc_link_boxes(self.h, other.h)
+
+    def gibbs_step(self, correct_energy=0):
+        return self.L.orc_gibbs_step(self.h, correct_energy)
+
+    def gibbs_run(self, nsteps, correct_energy=0):
+        return np.array([self.L.orc_gibbs_step(self.h, correct_energy) for _ in range(nsteps)], dtype=np.uint8)
+
+    def gibbs_run_sets(self, first_set, n_sets, steps_per_set, correct_energy=0, trace=False):
+        buf = np.zeros(n_sets * steps_per_set if trace else 1, dtype=np.uint8)
+        self.L.orc_gibbs_run_sets(self.h, first_set, n_sets, steps_per_set, correct_energy, buf.ctypes.data if trace else None)
         return buf if trace else None
 
     def state(self):
@@ -365,6 +385,17 @@ class RefOracle:
             L.mcref_volume.restype = C.c_double
             L.mcref_swap_zz.argtypes = [C.c_void_p]
             L.mcref_swap_zz.restype = C.c_double
+            L.mcref_add_box.argtypes = [C.c_void_p, C.POINTER(System)]
+            L.mcref_set_positions_box.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp]
+            L.mcref_get_positions_box.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
+            L.mcref_get_positions_box.restype = C.c_int
+            L.mcref_box_energy_box.argtypes = [C.c_void_p, C.c_int, _dp]
+            L.mcref_get_state_box.argtypes = [C.c_void_p, C.c_int, _dp, C.POINTER(C.c_int)]
+            L.mcref_widom_box.argtypes = [C.c_void_p, C.c_int, _dp, C.POINTER(C.c_int)]
+            L.mcref_gibbs_step.argtypes = [C.c_void_p, C.c_int]
+            L.mcref_gibbs_step.restype = C.c_int
+            L.mcref_gibbs_run.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]
+            L.mcref_gibbs_run.restype = C.c_longlong
             L.mcref_is_bound.argtypes = [_dp]
             L.mcref_is_bound.restype = C.c_int
             cls._libs[path] = L
@@ -450,6 +481,39 @@ class RefOracle:
         d = np.zeros(8); i = np.zeros(8, dtype=np.int32)
         self.L.mcref_get_state(self.h, d.ctypes.data_as(_dp), i.ctypes.data_as(C.POINTER(C.c_int)))
         return decode_state(d, i)
+
+    # -- two boxes (Gibbs ensemble)
+    def add_box(self, system: System):
+        self.system1 = system
+        self.L.mcref_add_box(self.h, C.byref(system))
+
+    def set_positions_box(self, ib, x, y, z):
+        x, px = _arr(x); y, py = _arr(y); z, pz = _arr(z)
+        self.L.mcref_set_positions_box(self.h, ib, len(x), px, py, pz)
+
+    def get_positions_box(self, ib):
+        n = self.state_box(ib)["n"]
+        x = np.zeros(n + 1); y = np.zeros(n + 1); z = np.zeros(n + 1)
+        self.L.mcref_get_positions_box(self.h, ib, x.ctypes.data_as(_dp), y.ctypes.data_as(_dp), z.ctypes.data_as(_dp))
+        return x[:n].copy(), y[:n].copy(), z[:n].copy()
+
+    def box_energy_box(self, ib):
+        out = np.zeros(4); self.L.mcref_box_energy_box(self.h, ib, out.ctypes.data_as(_dp)); return out
+
+    def state_box(self, ib):
+        d = np.zeros(8); i = np.zeros(8, dtype=np.int32)
+        self.L.mcref_get_state_box(self.h, ib, d.ctypes.data_as(_dp), i.ctypes.data_as(C.POINTER(C.c_int)))
+        return decode_state(d, i)
+
+    def widom_box(self, ib):
+        out = np.zeros(2); i = np.zeros(2, dtype=np.int32)
+        self.L.mcref_widom_box(self.h, ib, out.ctypes.data_as(_dp), i.ctypes.data_as(C.POINTER(C.c_int)))
+        return out, i
+
+    def gibbs_run(self, nsteps, correct_energy=0):
+        buf = np.zeros(nsteps, dtype=np.uint8)
+        self.L.mcref_gibbs_run(self.h, nsteps, correct_energy, buf.ctypes.data)
+        return buf
 
     def widom(self):
         out = np.zeros(2); i = np.zeros(2, dtype=np.int32)

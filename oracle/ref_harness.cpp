@@ -249,6 +249,87 @@ struct Oracle : public MC {
         sets[0] = sim.nSets; sets[1] = sim.nEquilSets; sets[2] = sim.nStepsPerSet; sets[3] = sim.printEvery;
         return 0;
     }
+    // ---- two boxes (Gibbs ensemble): box 1 of the same species.  Only what the two-box branches of MoveParticle (src/moves.cpp:127-137)
+    // and SwapParticle (src/moves.cpp:342-400) read is configured.
+    void add_box(const mcref_system& s) {
+        thermoSys.nBoxes = 2;
+        Box& b = box(1);
+        b.name = "box1";
+        b.geometry = s.geometry == 1 ? "slit" : (s.geometry == 2 ? "cylinder" : (s.geometry == 3 ? "sphere" : "bulk"));
+        for (int k = 0; k < 3; k++) b.width(k) = s.width[k];
+        b.PBC(0) = s.geometry != 3; b.PBC(1) = (s.geometry == 0 || s.geometry == 1); b.PBC(2) = s.geometry == 0;
+        b.fix = false;
+        sim.dv(1) = s.dv > 0 ? s.dv : 1e-3;
+        b.volume = ComputeVolume(b);
+        thermoSys.volume = box(0).volume + b.volume;
+        b.maxRcut = s.rcut;
+        b.solidDens = s.rho_s; b.nLayersPerWall = s.n_layers; b.deltaLayers = s.delta;
+        b.fluid(0).vdwPot(0) = (s.wall_kind == 1 || s.wall_kind == 2) ? "lj" : (s.wall_kind == 3 ? "lj10-4" : (s.wall_kind == 4 ? "steele10-4-3" : ""));
+        b.fluid(0).sigma(0) = s.sig_sf; b.fluid(0).epsilon(0) = s.eps_sf; b.fluid(0).mu = s.mu;
+        b.fluid(0).nParts = 0; b.nParts = 0;
+        b.energy = b.oldEnergy = b.pairPotE = b.boxE = b.manyBodyE = 0.;
+        sim.dr(1) = s.dr;
+    }
+    void set_positions_box(int ib, int n, const double* x, const double* y, const double* z) {
+        for (int k = 0; k < n; k++) {
+            Particle& p = box(ib).fluid(0).particle(k + 1);
+            p.x = x[k]; p.y = y[k]; p.z = z[k];
+            p.energy = p.manyBodyE = p.pairPotE = p.boxE = 0.;
+        }
+        box(ib).fluid(0).nParts = n; box(ib).nParts = n;
+        thermoSys.nParts = box(0).nParts + (thermoSys.nBoxes > 1 ? box(1).nParts : 0);
+    }
+    int get_positions_box(int ib, double* x, double* y, double* z) {
+        int n = box(ib).fluid(0).nParts;
+        for (int k = 0; k < n; k++) { Particle& p = box(ib).fluid(0).particle(k + 1); x[k] = p.x; y[k] = p.y; z[k] = p.z; }
+        return n;
+    }
+    void box_energy_box(int ib, double out[4]) {
+        BoxEnergy(ib);
+        out[0] = box(ib).pairPotE; out[1] = box(ib).manyBodyE; out[2] = box(ib).boxE; out[3] = box(ib).energy;
+    }
+    void get_state_box(int ib, double out[8], int iout[8]) {
+        out[0] = box(ib).pairPotE; out[1] = box(ib).manyBodyE; out[2] = box(ib).boxE; out[3] = box(ib).energy;
+        out[4] = sim.dr(ib); out[5] = box(ib).volume; out[6] = box(ib).oldEnergy; out[7] = thermoSys.temp;
+        iout[0] = box(ib).fluid(0).nParts; iout[1] = stats.acceptance(ib); iout[2] = stats.rejection(ib);
+        iout[3] = stats.nDisplacements(ib); iout[4] = stats.acceptSwap; iout[5] = stats.rejectSwap;
+        iout[6] = stats.nSwaps; iout[7] = thermoSys.nParts;
+    }
+    void widom_box(int ib, double out[2], int iout[2]) {
+        out[0] = stats.widomInsert(ib, 0); out[1] = stats.widomDelete(ib, 0);
+        iout[0] = stats.widomInsertions(ib, 0); iout[1] = stats.widomDeletions(ib, 0);
+    }
+    // Step-loop body with two boxes.  Codes as oracle/mcpm_oracle.h::orc_gibbs_step: translation | box<<4; (5<<1)|acc | inBox<<4 for a
+    // transfer attempt; 6<<1 when the donor box was empty (the direction is then unobservable: no box bit).
+    int gibbs_step(int correct_energy) {
+        int nD = sim.nDispAttempts, nV = sim.nVolAttempts, nS = sim.nSwapAttempts;
+        int acc0[2] = {(int)stats.acceptance(0), (int)stats.acceptance(1)}, nd1 = stats.nDisplacements(1);
+        int sw0 = stats.acceptSwap, rj0 = stats.rejectSwap;
+        int n0[2] = {box(0).nParts, box(1).nParts};
+        Particle free0 = box(0).fluid(0).particle(n0[0] + 1), free1 = box(1).fluid(0).particle(n0[1] + 1);
+        int code = 0;
+        double r = Random() * (nD + nV + nS);
+        if (r <= nD) {
+            MoveParticle();
+            int ib = stats.nDisplacements(1) != nd1 ? 1 : 0;
+            code = (stats.acceptance(ib) - acc0[ib]) | (ib << 4);
+        } else if (r <= nD + nV) {
+            code = 4 << 1;                       // ChangeVolume aborts on entry in the stock build (Eigen assertion): never called here
+        } else if (r <= nD + nV + nS) {
+            SwapParticle();
+            int accepted = stats.acceptSwap - sw0;
+            if (!accepted && stats.rejectSwap == rj0) code = 6 << 1;
+            else {
+                int in;
+                if (accepted) in = box(1).nParts > n0[1] ? 1 : 0;
+                else in = (box(1).fluid(0).particle(n0[1] + 1) != free1) ? 1 : 0;
+                (void)free0;
+                code = (5 << 1) | accepted | (in << 4);
+            }
+        }
+        if (correct_energy) CorrectEnergy();
+        return code;
+    }
     double volume() { return box(0).volume; }
     double swap_zz() {  // src/moves.cpp:296-298
         double particleMass = fluid(0).molarMass / na * 1e-3;
@@ -314,6 +395,22 @@ int mcref_is_bound(double out[6]) {
     if (!mcref_bound_stats) return 0;
     if (out) mcref_bound_stats(out);
     return 1;
+}
+void mcref_add_box(void* h, const mcref_system* s) { ops(h)->add_box(*s); }
+void mcref_set_positions_box(void* h, int ib, int n, const double* x, const double* y, const double* z) { ops(h)->set_positions_box(ib, n, x, y, z); }
+int mcref_get_positions_box(void* h, int ib, double* x, double* y, double* z) { return ops(h)->get_positions_box(ib, x, y, z); }
+void mcref_box_energy_box(void* h, int ib, double out[4]) { ops(h)->box_energy_box(ib, out); }
+void mcref_get_state_box(void* h, int ib, double out[8], int iout[8]) { ops(h)->get_state_box(ib, out, iout); }
+void mcref_widom_box(void* h, int ib, double out[2], int iout[2]) { ops(h)->widom_box(ib, out, iout); }
+int mcref_gibbs_step(void* h, int correct_energy) { return ops(h)->gibbs_step(correct_energy); }
+long long mcref_gibbs_run(void* h, long long nsteps, int correct_energy, unsigned char* trace) {
+    long long acc = 0;
+    for (long long s = 0; s < nsteps; s++) {
+        int c = ops(h)->gibbs_step(correct_energy);
+        if (trace) trace[s] = (unsigned char)c;
+        acc += c & 1;
+    }
+    return acc;
 }
 double mcref_volume(void* h) { return ops(h)->volume(); }
 double mcref_swap_zz(void* h) { return ops(h)->swap_zz(); }
