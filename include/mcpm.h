@@ -232,6 +232,19 @@ int mcpm_set_running_energy(mcpm_ctx* ctx, const double* pair /* [n_chains] */, 
  * the context.  A caller that shards one set of chains over several contexts / GPUs passes each chain's GLOBAL id here,
  * so that no two chains of the job share a stream whatever the sharding (and results do not depend on it). */
 int mcpm_set_stream_ids(mcpm_ctx* ctx, const unsigned int* ids /* [n_chains] */);
+/* Two-box Gibbs ensemble (thermoSys.nBoxes == 2).  Chains `box0` and `box1` — both with their systems set: same fluid, temperature,
+ * move weights and n_equil_sets, n_vol == 0, any geometry / wall each (e.g. a slit pore and a bulk reservoir) — become box 0 and box 1
+ * of ONE system, advanced together by mcpm_run:
+ *   n_disp  MC::MoveParticle with its box selection (src/moves.cpp:127-137: rand = int(u*N_total), the first box with rand <= cumulative count)
+ *   n_swap  MC::SwapParticle's Gibbs branch (src/moves.cpp:342-400): a particle transfer between the boxes, accepted with
+ *           exp(-(E_in - E_out)/T) * V_in N_out / (V_out (N_in + 1)); the Widom/BAR sums of both boxes are accumulated on the way
+ *           (mcpm_chemical_potential then gives each box's mu as MC::ComputeChemicalPotential does)
+ * The system draws from ONE uniform stream — box 0's (stream id, replay row); its trace is box 0's row:
+ *   translation: accepted | box<<4;  transfer attempt: (5<<1) | accepted | inBox<<4;  transfer with an empty donor box: (6<<1) | inBox<<4.
+ * Per-box statistics come back in each chain's mcpm_chain_stats (accept_swap / reject_swap / n_swaps are the system's, tot_ins / tot_del the
+ * transfers into / out of the box).  A context holds either single-box chains or linked pairs, not both.  The Gibbs branches of
+ * MC::ChangeVolume (src/moves.cpp:232-283) are out of scope — the stock reference aborts on entering ChangeVolume — MCPM_ERR_UNSUPPORTED. */
+int mcpm_link_boxes(mcpm_ctx* ctx, int box0, int box1);
 /* Override a chain's translation amplitude / global step counter (restart, tests). */
 int mcpm_set_dr(mcpm_ctx* ctx, int chain, double dr);
 int mcpm_set_step_counter(mcpm_ctx* ctx, int chain, unsigned long long step);

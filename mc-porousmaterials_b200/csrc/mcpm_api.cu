@@ -89,6 +89,9 @@ struct mcpm_ctx {
     std::vector<ChainState> h_state;
     std::vector<mcpm_system_desc> h_desc;
     std::vector<char> has_system;
+    std::vector<int> peer;           // two-box Gibbs systems (mcpm_link_boxes): the other box of the chain's system, or -1
+    std::vector<char> box_id;        // 0 / 1 inside a linked pair
+    int2* d_pairs = nullptr;
     std::vector<char> cache_fresh;   // the device cache belongs to the configuration now on the device (no host write since the last K2 launch)
     float last_ms = 0.f;
     unsigned long long launches = 0;
@@ -152,6 +155,7 @@ static int digest(const mcpm_system_desc& d, ChainParams& P) {
     P.pair_kind = d.pair_kind;
     P.sig_ff = d.sig_ff; P.eps_sf = d.eps_sf; P.rho_s = d.rho_s;
     P.press_k = d.pressure > 0 ? d.pressure / kb * 1e-30 : 0.0;   // src/moves.cpp:198
+    P.volume = volume;
     // everything beyond "Lennard-Jones fluid, bulk or slit with the layered 10-4 wall, fixed volume" runs through the general kernels
     P.exotic = (d.geometry == MCPM_GEOM_CYLINDER || d.geometry == MCPM_GEOM_SPHERE || d.wall_kind >= MCPM_WALL_SPHERE_LJ || d.pair_kind == MCPM_PAIR_HS || d.n_vol > 0) ? 1 : 0;
     return MCPM_OK;
@@ -241,6 +245,8 @@ int mcpm_create(int device, int n_chains, int capacity, mcpm_ctx** out) {
     c->h_desc.assign(n_chains, mcpm_system_desc());
     c->has_system.assign(n_chains, 0);
     c->cache_fresh.assign(n_chains, 0);
+    c->peer.assign(n_chains, -1);
+    c->box_id.assign(n_chains, 0);
     CU(cudaMemcpyAsync(c->d_state, c->h_state.data(), sizeof(ChainState) * n_chains, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     *out = c;
@@ -252,7 +258,7 @@ int mcpm_destroy(mcpm_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_params); cudaFree(c->d_state); cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_z);
-    cudaFree(c->d_pool_next);
+    cudaFree(c->d_pool_next); cudaFree(c->d_pairs);
     cudaFree(c->d_k1_reqs); cudaFree(c->d_k1_out); cudaFree(c->d_k1_scratch); cudaFree(c->d_k1_counters);
     if (c->h_k1_reqs) cudaFreeHost(c->h_k1_reqs);
     if (c->h_k1) cudaFreeHost(c->h_k1);
@@ -340,6 +346,29 @@ int mcpm_get_system(const mcpm_ctx* c, int chain, mcpm_system_desc* desc) {
     if (!desc) return fail(MCPM_ERR_ARG, "null desc");
     if (!c->has_system[chain]) return fail(MCPM_ERR_ARG, "chain %d has no system yet", chain);
     *desc = c->h_desc[chain];
+    return MCPM_OK;
+}
+
+// Two boxes of ONE system (thermoSys.nBoxes == 2): same fluid, temperature and move weights; fixed volumes (see mcpm_gibbs.cu).
+static int check_pair(const mcpm_ctx* c, int a, int b) {
+    const mcpm_system_desc &da = c->h_desc[a], &db = c->h_desc[b];
+    if (da.temperature != db.temperature || da.eps_ff != db.eps_ff || da.sig_ff != db.sig_ff || da.rcut != db.rcut || da.molar_mass != db.molar_mass ||
+        da.pair_kind != db.pair_kind)
+        return fail(MCPM_ERR_ARG, "linked boxes %d and %d hold the same fluid at the same temperature (one species, one ThermodynamicSystem)", a, b);
+    if (da.n_disp != db.n_disp || da.n_swap != db.n_swap || da.n_vol != db.n_vol || da.n_equil_sets != db.n_equil_sets)
+        return fail(MCPM_ERR_ARG, "linked boxes %d and %d share the move weights and the number of equilibration sets (Simulation, src/MC.h)", a, b);
+    if (da.n_vol != 0) return fail(MCPM_ERR_UNSUPPORTED, "volume moves between two boxes (the Gibbs branches of MC::ChangeVolume) are out of scope: the stock reference aborts in ChangeVolume");
+    if (da.pair_kind != MCPM_PAIR_LJ) return fail(MCPM_ERR_UNSUPPORTED, "linked boxes support the Lennard-Jones fluid only");
+    return MCPM_OK;
+}
+int mcpm_link_boxes(mcpm_ctx* c, int box0, int box1) {
+    int rc = check_chain(c, box0); if (rc) return rc;
+    rc = check_chain(c, box1); if (rc) return rc;
+    if (box0 == box1) return fail(MCPM_ERR_ARG, "a box cannot be linked to itself");
+    if (!c->has_system[box0] || !c->has_system[box1]) return fail(MCPM_ERR_ARG, "set the systems of both boxes first");
+    if (c->peer[box0] >= 0 || c->peer[box1] >= 0) return fail(MCPM_ERR_ARG, "chain %d is linked already", c->peer[box0] >= 0 ? box0 : box1);
+    rc = check_pair(c, box0, box1); if (rc) return rc;
+    c->peer[box0] = box1; c->peer[box1] = box0; c->box_id[box0] = 0; c->box_id[box1] = 1;
     return MCPM_OK;
 }
 
@@ -775,6 +804,64 @@ int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
     if (need_init) {  // exact bookkeeping starts from a full BoxEnergy evaluation (src/energy.cpp:20)
         int rc0 = box_energy_range(c, 0, c->n_chains, nullptr, nullptr); if (rc0) return rc0;
         CU(cudaMemcpyAsync(c->d_state, c->h_state.data(), sizeof(ChainState) * c->n_chains, cudaMemcpyHostToDevice, c->stream));
+    }
+    bool any_linked = false, all_linked = true;
+    for (int k = 0; k < c->n_chains; k++) { any_linked = any_linked || c->peer[k] >= 0; all_linked = all_linked && c->peer[k] >= 0; }
+    if (any_linked) {
+        // Two-box Gibbs systems (mcpm_link_boxes): one CTA per pair of boxes, mcpm_gibbs.cu
+        if (!all_linked) return fail(MCPM_ERR_UNSUPPORTED, "a context holds either single-box chains or linked pairs of boxes, not both");
+        if (p->sample_rdf) return fail(MCPM_ERR_UNSUPPORTED, "RDF sampling of linked boxes is not supported");
+        std::vector<int2> pairs;
+        for (int k = 0; k < c->n_chains; k++) {
+            if (c->box_id[k] != 0) continue;
+            int rcp = check_pair(c, k, c->peer[k]); if (rcp) return rcp;
+            pairs.push_back(make_int2(k, c->peer[k]));
+        }
+        std::stable_sort(pairs.begin(), pairs.end(), [&](const int2& u, const int2& v) {
+            return c->h_state[u.x].st.n + c->h_state[u.y].st.n > c->h_state[v.x].st.n + c->h_state[v.y].st.n; });
+        if (!c->d_pairs) CU(cudaMalloc(&c->d_pairs, sizeof(int2) * (size_t)c->n_chains));
+        CU(cudaMemcpyAsync(c->d_pairs, pairs.data(), sizeof(int2) * pairs.size(), cudaMemcpyHostToDevice, c->stream));
+        RunArgs ga;
+        memset(&ga, 0, sizeof(ga));
+        ga.first_set = p->first_set; ga.n_sets = p->n_sets; ga.steps_per_set = p->steps_per_set; ga.seed = p->seed;
+        ga.check_energy = p->check_energy; ga.cap = c->cap; ga.no_sampling = p->no_sampling ? 1 : 0;
+        const unsigned long long gsteps = (unsigned long long)p->n_sets * (unsigned long long)p->steps_per_set;
+        if (p->rng_mode == MCPM_RNG_REPLAY) {
+            const size_t need = (size_t)c->n_chains * p->replay_stride;
+            if (need > c->replay_doubles) {
+                cudaFree(c->d_replay); c->d_replay = nullptr; c->replay_doubles = 0;
+                CU(cudaMalloc(&c->d_replay, sizeof(double) * need));
+                c->replay_doubles = need;
+            }
+            CU(cudaMemcpyAsync(c->d_replay, p->replay_u, sizeof(double) * need, cudaMemcpyHostToDevice, c->stream));
+            ga.replay_u = c->d_replay; ga.replay_stride = p->replay_stride;
+        }
+        if (p->trace) {
+            const size_t need = (size_t)c->n_chains * gsteps;
+            if (need > c->trace_bytes) {
+                cudaFree(c->d_trace); c->d_trace = nullptr; c->trace_bytes = 0;
+                CU(cudaMalloc(&c->d_trace, std::max<size_t>(need, 1)));
+                c->trace_bytes = need;
+            }
+            CU(cudaMemsetAsync(c->d_trace, 0xff, std::max<size_t>(need, 1), c->stream));
+            ga.trace = c->d_trace; ga.trace_stride = gsteps;
+        }
+        CU(cudaEventRecord(c->ev0, c->stream));
+        c->last_kernel = "k2_gibbs";
+        CU(launch_k2_gibbs(p->rng_mode, (int)pairs.size(), c->d_params, c->d_state, c->d_pairs, c->d_x, c->d_y, c->d_z, ga, c->stream));
+        c->launches++;
+        CU(cudaEventRecord(c->ev1, c->stream));
+        if (p->trace) CU(cudaMemcpyAsync(p->trace, c->d_trace, (size_t)c->n_chains * gsteps, cudaMemcpyDeviceToHost, c->stream));
+        int rcg = pull_states(c); if (rcg) return rcg;
+        CU(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+        int full = -1;
+        for (int k = 0; k < c->n_chains; k++) {
+            c->cache_fresh[k] = 0;
+            if (stats) stats[k] = c->h_state[k].st;
+            if (c->h_state[k].st.overflow && full < 0) full = k;
+        }
+        if (full >= 0) return fail(MCPM_ERR_CAPACITY, "a box of the system of chain %d reached its capacity of %d particles and the system stopped", full, c->cap);
+        return MCPM_OK;
     }
     // longest chains first (cost per step ~ n)
     std::vector<int> order(c->n_chains);

@@ -50,6 +50,10 @@ cudaError_t launch_k2_cells(int rng_mode, bool sample, int n_chains, const Chain
                             size_t smem_items, cudaStream_t stream);
 size_t k2_cells_smem_items_bytes(int cap, int cells_stride, int ccap, int max_smem_optin);
 
+// mcpm_gibbs.cu: two linked boxes (Gibbs ensemble) per CTA; pairs[k] = (box 0's chain, box 1's chain)
+cudaError_t launch_k2_gibbs(int rng_mode, int n_pairs, const ChainParams* params, ChainState* states, const int2* pairs, double* X, double* Y,
+                            double* Z, const RunArgs& a, cudaStream_t stream);
+
 cudaError_t launch_in_box(int n_chains, const ChainParams* params, const int* n_of, const double* X, const double* Y, const double* Z, int cap,
                           int* flags, cudaStream_t stream);
 size_t k3c_cells_per_chain();

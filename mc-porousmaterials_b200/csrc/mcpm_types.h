@@ -26,6 +26,7 @@ struct ChainParams {
     int pair_kind, exotic;
     double sig_ff, eps_sf, rho_s;
     double press_k;       // ExternalPressure / kB * 1e-30, K/AA^3 (src/moves.cpp:198)
+    double volume;        // Box::volume (MC::ComputeVolume, src/read.cpp:26-35): the Gibbs transfer's acceptance and Widom sums
 };
 
 // Where a chain that outgrew its sub-warp slot (mcpm_subwarp.cu) stopped, and the counters of the interrupted set.

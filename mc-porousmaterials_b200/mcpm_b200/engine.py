@@ -140,6 +140,10 @@ class Engine:
         assert len(ids) == self.n_chains
         check(self.L.mcpm_set_stream_ids(self.h, ids.ctypes.data_as(C.POINTER(C.c_uint))))
 
+    def link_boxes(self, box0, box1):
+        """Chains box0 / box1 become the two boxes of one Gibbs-ensemble system (mcpm_link_boxes)."""
+        check(self.L.mcpm_link_boxes(self.h, box0, box1))
+
     def use_pool(self, warps=16):
         """Experimental pooled kernel (libmcpm_exp.so only); switching it off is a no-op on the product library."""
         if warps or abi.has_experiments():
