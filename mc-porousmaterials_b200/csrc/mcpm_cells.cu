@@ -23,7 +23,11 @@ namespace mcpm {
 
 namespace {
 
-constexpr int KC_THREADS = 256, KC_WARPS = 8;
+#ifndef MCPM_KC_WARPS
+#define MCPM_KC_WARPS 8
+#endif
+constexpr int KC_WARPS = MCPM_KC_WARPS, KC_THREADS = 32 * KC_WARPS;
+constexpr int KC_Q = (27 + KC_WARPS - 1) / KC_WARPS;   // neighbour cells per warp
 constexpr int KC_MAXCELLS = K3C_MAXC * K3C_MAXC * K3C_MAXC;
 
 template <typename ItemT>   // unsigned short: lists in shared memory (capacity <= 65536 and they fit); int: lists in global memory
@@ -76,9 +80,9 @@ __device__ __forceinline__ void cell_scan(const CellList& cl, const double* xs, 
                                           double xa, double ya, double za, double xb, double yb, double zb, int self, int warp, int lane,
                                           double& ea, double& eb, double& nev) {
     const int cx = c0 & 0xff, cy = (c0 >> 8) & 0xff, cz = (c0 >> 16) & 0xff;       // c0: packed cell coordinates
-    int base[4], cnt[4], maxc = 0;
+    int base[KC_Q], cnt[KC_Q], maxc = 0;
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < KC_Q; q++) {
         const int k = warp + q * KC_WARPS;
         base[q] = 0; cnt[q] = 0;
         if (k < 27) {
@@ -91,33 +95,39 @@ __device__ __forceinline__ void cell_scan(const CellList& cl, const double* xs, 
         }
         maxc = max(maxc, cnt[q]);
     }
-    double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
+    double a[KC_Q], b[KC_Q];
+#pragma unroll
+    for (int q = 0; q < KC_Q; q++) { a[q] = 0.0; b[q] = 0.0; }
     int ne = 0;
     // Two slots of each of the warp's four cells per trip: the 8 index loads and 24 position loads (L2, ~800 cycles) are all
     // in flight before the first evaluation needs them.
     for (int s = lane; s < maxc; s += 64) {
-        int j[8];
-        bool on[8];
-        double xj[8], yj[8], zj[8];
+        int j[2 * KC_Q];
+        bool on[2 * KC_Q];
+        double xj[2 * KC_Q], yj[2 * KC_Q], zj[2 * KC_Q];
 #pragma unroll
-        for (int q = 0; q < 4; q++)
+        for (int q = 0; q < KC_Q; q++)
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 on[2 * q + h] = (s + 32 * h) < cnt[q];
                 j[2 * q + h] = on[2 * q + h] ? (int)cl.items[base[q] + s + 32 * h] : 0;
             }
 #pragma unroll
-        for (int t = 0; t < 8; t++) { xj[t] = xs[j[t]]; yj[t] = ys[j[t]]; zj[t] = zs[j[t]]; }
+        for (int t = 0; t < 2 * KC_Q; t++) { xj[t] = xs[j[t]]; yj[t] = ys[j[t]]; zj[t] = zs[j[t]]; }
 #pragma unroll
-        for (int t = 0; t < 8; t++) {
+        for (int t = 0; t < 2 * KC_Q; t++) {
             const int ex = on[t] ? self : j[t];              // inactive slots mask themselves out
             pair_acc(a[t >> 1], dist2<true, PBZ>(g, xa, ya, za, xj[t], yj[t], zj[t]), g, j[t], ex);
             if (TWO) pair_acc(b[t >> 1], dist2<true, PBZ>(g, xb, yb, zb, xj[t], yj[t], zj[t]), g, j[t], ex);
             ne += on[t] ? (TWO ? 2 : 1) : 0;
         }
     }
-    ea += (a[0] + a[1]) + (a[2] + a[3]);
-    if (TWO) eb += (b[0] + b[1]) + (b[2] + b[3]);
+#pragma unroll
+    for (int w = 1; w < KC_Q; w *= 2)
+#pragma unroll
+        for (int q = 0; q + w < KC_Q; q += 2 * w) { a[q] += a[q + w]; b[q] += b[q + w]; }   // (a0+a1)+(a2+a3)
+    ea += a[0];
+    if (TWO) eb += b[0];
     nev += (double)ne;
 }
 
