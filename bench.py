@@ -79,10 +79,10 @@ def build_workload(config, replicas, steps_per_set):
         w["start"] = "tests/golden/c3_start.npz"
     elif config == "c4":
         cx, cy, cz = workloads.c4_lattice()
-        w["workload"] = "C4 dense NVT LJ argon, bulk L=100A, rcut=12A, T=120K, N=20000, translations + Widom sampling (K2 through a cell list: 27 cells of ~39 particles per scan instead of the reference's N)"
+        w["workload"] = "C4 dense NVT LJ argon, bulk L=100A, rcut=12A, T=120K, N=20000, translations + Widom sampling, one sweep (20000 trial moves) per set (K2 through a cell list: 27 cells of ~39 particles per scan instead of the reference's N)"
         w["points"] = [(workloads.argon_bulk(n_equil_sets=0), cx, cy, cz, 0.5)]
         w["replicas"] = replicas or 148
-        w["steps_per_set"] = steps_per_set or 500
+        w["steps_per_set"] = steps_per_set or 20000      # one sweep: the end-to-end copies (71 MB each way) are paid once per set, as the reference prints once per set
         w["flop_per_pair"] = 25
         w["start"] = "simple-cubic 28^3 lattice, first 20000 sites, +-0.2A jitter (numpy default_rng(2024))"
     elif config == "c5":

@@ -23,10 +23,21 @@ namespace mcpm {
 
 namespace {
 
+// Build parameters, measured on C4 (148 chains of N = 20 000, B200, round 2; moves/s with / without Widom sampling):
+//   8 warps, 2 slots per trip, 1 CTA/SM (default)  2.94e7 / 5.31e7      12 warps 2.63e7      16 warps (128 registers) 2.29e7
+//   1 slot per trip 3.03e7 / 5.26e7                __launch_bounds__(256, 2) with 296 chains: 2.2e7 / 4.2e7 (spills at 128 registers)
+//   positions kept a second time in cell order (coalesced scans, no index gather): 2.69e7 / 4.36e7 — the extra stores of an accepted move
+//   sit on the serial path.  The step is a chain of dependent latencies (4 L2 round trips) around an FP64-throughput-bound scan.
 #ifndef MCPM_KC_WARPS
 #define MCPM_KC_WARPS 8
 #endif
-constexpr int KC_WARPS = MCPM_KC_WARPS, KC_THREADS = 32 * KC_WARPS;
+#ifndef MCPM_KC_MINB
+#define MCPM_KC_MINB 1
+#endif
+#ifndef MCPM_KC_H
+#define MCPM_KC_H 2      // slots of each of the warp's cells per trip
+#endif
+constexpr int KC_WARPS = MCPM_KC_WARPS, KC_THREADS = 32 * KC_WARPS, KC_H = MCPM_KC_H;
 constexpr int KC_Q = (27 + KC_WARPS - 1) / KC_WARPS;   // neighbour cells per warp
 constexpr int KC_MAXCELLS = K3C_MAXC * K3C_MAXC * K3C_MAXC;
 
@@ -101,24 +112,24 @@ __device__ __forceinline__ void cell_scan(const CellList& cl, const double* xs, 
     int ne = 0;
     // Two slots of each of the warp's four cells per trip: the 8 index loads and 24 position loads (L2, ~800 cycles) are all
     // in flight before the first evaluation needs them.
-    for (int s = lane; s < maxc; s += 64) {
-        int j[2 * KC_Q];
-        bool on[2 * KC_Q];
-        double xj[2 * KC_Q], yj[2 * KC_Q], zj[2 * KC_Q];
+    for (int s = lane; s < maxc; s += 32 * KC_H) {
+        int j[KC_H * KC_Q];
+        bool on[KC_H * KC_Q];
+        double xj[KC_H * KC_Q], yj[KC_H * KC_Q], zj[KC_H * KC_Q];
 #pragma unroll
         for (int q = 0; q < KC_Q; q++)
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                on[2 * q + h] = (s + 32 * h) < cnt[q];
-                j[2 * q + h] = on[2 * q + h] ? (int)cl.items[base[q] + s + 32 * h] : 0;
+            for (int h = 0; h < KC_H; h++) {
+                on[KC_H * q + h] = (s + 32 * h) < cnt[q];
+                j[KC_H * q + h] = on[KC_H * q + h] ? (int)cl.items[base[q] + s + 32 * h] : 0;
             }
 #pragma unroll
-        for (int t = 0; t < 2 * KC_Q; t++) { xj[t] = xs[j[t]]; yj[t] = ys[j[t]]; zj[t] = zs[j[t]]; }
+        for (int t = 0; t < KC_H * KC_Q; t++) { xj[t] = xs[j[t]]; yj[t] = ys[j[t]]; zj[t] = zs[j[t]]; }
 #pragma unroll
-        for (int t = 0; t < 2 * KC_Q; t++) {
+        for (int t = 0; t < KC_H * KC_Q; t++) {
             const int ex = on[t] ? self : j[t];              // inactive slots mask themselves out
-            pair_acc(a[t >> 1], dist2<true, PBZ>(g, xa, ya, za, xj[t], yj[t], zj[t]), g, j[t], ex);
-            if (TWO) pair_acc(b[t >> 1], dist2<true, PBZ>(g, xb, yb, zb, xj[t], yj[t], zj[t]), g, j[t], ex);
+            pair_acc(a[t / KC_H], dist2<true, PBZ>(g, xa, ya, za, xj[t], yj[t], zj[t]), g, j[t], ex);
+            if (TWO) pair_acc(b[t / KC_H], dist2<true, PBZ>(g, xb, yb, zb, xj[t], yj[t], zj[t]), g, j[t], ex);
             ne += on[t] ? (TWO ? 2 : 1) : 0;
         }
     }
@@ -391,7 +402,7 @@ __device__ void chain_loop_cells(const ChainParams& P, ChainState& S, Source& rn
 // SMEM_ITEMS: the index lists (16-bit entries) live in dynamic shared memory; else 32-bit entries in global memory.
 // (round 2: __launch_bounds__(KC_THREADS, 2) — two chains per SM at 128 registers — spills 450 bytes and was measured 22-37 % slower)
 template <int RNG_MODE, bool SAMPLE, bool SMEM_ITEMS>
-__global__ void __launch_bounds__(KC_THREADS, 1) k2_cells(const ChainParams* __restrict__ params, ChainState* __restrict__ states,
+__global__ void __launch_bounds__(KC_THREADS, MCPM_KC_MINB) k2_cells(const ChainParams* __restrict__ params, ChainState* __restrict__ states,
                                                           const int* __restrict__ order, double* X, double* Y, double* Z, RunArgs a, int* items,
                                                           int* cell_of, int* slot_of, int cells_stride, int ccap) {
     typedef typename std::conditional<SMEM_ITEMS, unsigned short, int>::type ItemT;

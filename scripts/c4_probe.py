@@ -8,7 +8,7 @@ from mcpm_b200 import workloads
 
 x, y, z = workloads.c4_lattice()
 nch = int(os.environ.get("CHAINS", "148"))
-for dr in (0.5, 0.05):
+for dr in (0.5,):
     for nos in (0, 1):
         with M.Engine(nch, 20032) as e:
             d = workloads.argon_bulk(n_equil_sets=0); d.dr = dr
