@@ -286,7 +286,7 @@ class Job:
         self.eng.close()
 
     def one_step(self):
-        st = self.eng.run(self.set_index, 1, self.S, seed=self.seed, threads=self.threads, check_energy=0)
+        st = self.eng.run(self.set_index, 1, self.S, seed=self.seed, threads=self.threads, check_energy=0, no_sampling=getattr(self, "no_sampling", 0))
         self.set_index += 1
         return st
 
@@ -526,6 +526,10 @@ def gpu_arm(args, world, rank, local, dist):
             k = min(args.steps, 3)
             rc = jc.time_resident(k, MIN_WARMUP, flush, None)
             es, hb, db = jc.time_e2e(k, None)
+            moves_only = None
+            if cfg == "c4":      # the same sets as EQUILIBRATION sets (set <= nEquilSets: no ComputeWidom after the move, src/main.cpp:72-75)
+                jc.no_sampling = 1
+                moves_only = float(len(chains_c)) * wc["steps_per_set"] * k / jc.time_resident(k, 1, flush, None)["dev_s"]
             jc.close()
             mv = float(len(chains_c)) * wc["steps_per_set"] * k
             rf = roofline_record(wc, rc, peak_tflops)
@@ -534,6 +538,8 @@ def gpu_arm(args, world, rank, local, dist):
                          "e2e": {"value": mv / es, "unit": UNIT, "h2d_bytes_per_step": hb, "d2h_bytes_per_step": db},
                          "kernel": rc["kernel"], "roofline_frac": rf["frac"], "roofline_frac_executed": rf["frac_executed"],
                          "pair_evals_per_s": rf["pair_evals_per_s"]})
+            if moves_only is not None:
+                recs[-1]["value_equilibration_sets"] = moves_only
         line["configs"] = recs
         line.update(k3_k1_records(m, torch, local))
     if world == 1 and not args.no_cpu:
