@@ -271,15 +271,15 @@ int mcpm_philox_uniforms(mcpm_ctx* ctx, unsigned long long seed, unsigned int ch
                          unsigned long long first_step, int n_steps, double* out /* n_steps*8 */);
 
 /* ---- host driver (C++ in csrc/host/, re-hosting the reference's main/read/print) ------------- *
- * Parsed input file == the state MC::ReadInputFile leaves behind (src/read.cpp:36-172), single box and
- * single species.  Counts are doubles because the reference parses them with stod (src/read.cpp:56-59). */
+ * Parsed input file == the state MC::ReadInputFile leaves behind (src/read.cpp:36-172), single species, one box
+ * or two (the two-box Gibbs ensemble at fixed volumes: `system2`, see mcpm_link_boxes).  Counts are doubles because the reference parses them with stod (src/read.cpp:56-59). */
 typedef struct mcpm_sim_config {
     char project[64], fluid[64], box[64];       /* lower-cased like the reference (src/tools.h:19-30) */
     double n_sets, n_equil_sets, steps_per_set, print_every;
     double pressure;                            /* ExternalPressure, unused (NPT out of scope), -1 if absent */
     int n_particles;                            /* <Box> <Fluid> NumberOfParticles */
     int sample_rdf, print_trajectory, continue_after_crash;
-    int n_boxes, n_species;                     /* what the file declared (must both be 1) */
+    int n_boxes, n_species;                     /* what the file declared (1 or 2 boxes, 1 species) */
     /* extensions of this engine (ignored by the reference, which skips unknown lines) */
     int has_seed; unsigned long long seed;      /* Seed <n>: reproducible runs (quirk Q2) */
     int replicas;                               /* Replicas <n>: independent replica chains per state point */
@@ -287,6 +287,11 @@ typedef struct mcpm_sim_config {
     int capacity;                               /* Capacity <n>: particle slots per chain (default: from N) */
     int devices;                                /* Devices <n>: GPUs to shard the chains over */
     mcpm_system_desc system;                    /* derived widths, PBC, dr as in src/read.cpp:122-168 */
+    /* a second BoxName block: box 1 of a two-box (Gibbs ensemble) system — same fluid, its own geometry / size / wall */
+    char box2[64];
+    int n_particles2;
+    int fix_volume[2];                          /* FixVolume of box 0 / box 1 (echoed by PrintParams) */
+    mcpm_system_desc system2;
 } mcpm_sim_config;
 
 /* MC::ReadInputFile (src/read.cpp:36-172).  No GPU needed. */

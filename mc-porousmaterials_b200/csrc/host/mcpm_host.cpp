@@ -88,10 +88,13 @@ static int read_input_file(const char* path, mcpm_sim_config* cfg) {
     cfg->pressure = -1.;
     cfg->replicas = 1;
     cfg->devices = 1;
+    // box-independent fields are parsed into box 0's description and copied to box 1's afterwards
     mcpm_system_desc& d = cfg->system;
     d.temperature = -1.;
-    std::string fluid_name, box_name, geometry = "bulk", ff_pot, sf_pot;   // defaults of MC::MC(), src/MC.cpp:56
-    double size = 0.;
+    std::string fluid_name, box_name[2], geometry[2] = {"bulk", "bulk"}, ff_pot, sf_pot[2];   // defaults of MC::MC(), src/MC.cpp:56
+    double size[2] = {0., 0.}, rho_s[2] = {0., 0.}, delta[2] = {0., 0.}, sig_sf[2] = {0., 0.}, eps_sf[2] = {0., 0.};
+    int n_layers[2] = {0, 0}, n_parts[2] = {0, 0};
+    int bi = 0;                                    // the box the box-level keywords refer to: the last BoxName (src/read.cpp:72-80)
     std::string line;
     while (std::getline(in, line)) {
         auto c = split(line);
@@ -111,22 +114,31 @@ static int read_input_file(const char* path, mcpm_sim_config* cfg) {
         else if (k == "fluidname") { cfg->n_species++; fluid_name = c[1]; }
         else if (k == "molarmass") d.molar_mass = std::stod(c[1]);
         else if (k == "chemicalpotential") d.mu = std::stod(c[1]);
-        else if (k == "boxname") { cfg->n_boxes++; box_name = c[1]; }
-        else if (k == "geometry") geometry = c[1];
-        else if (k == "surfacedensity") d.rho_s = std::stod(c[1]);
-        else if (k == "nlayersperwall") d.n_layers = std::stoi(c[1]);
-        else if (k == "distancebetweenlayers") d.delta = std::stod(c[1]);
-        else if (k == "size") size = std::stod(c[1]);
-        else if (k == "fixvolume") {}
+        else if (k == "boxname") { cfg->n_boxes++; bi = std::min(cfg->n_boxes - 1, 1); box_name[bi] = c[1]; }
+        else if (k == "geometry") geometry[bi] = c[1];
+        else if (k == "surfacedensity") rho_s[bi] = std::stod(c[1]);
+        else if (k == "nlayersperwall") n_layers[bi] = std::stoi(c[1]);
+        else if (k == "distancebetweenlayers") delta[bi] = std::stod(c[1]);
+        else if (k == "size") size[bi] = std::stod(c[1]);
+        else if (k == "fixvolume") cfg->fix_volume[bi] = 1;
         else if (c[2] == "vdwpotential" || c[2] == "sigma" || c[2] == "epsilon" || c[2] == "rcut" || c[2] == "numberofparticles") {
             // addressing rule of src/read.cpp:82-111: "<fluid> <fluid> …" = pair term, "<box> <fluid> …" = wall term
             const bool a_fluid = (c[0] == fluid_name && !fluid_name.empty()), b_fluid = (c[1] == fluid_name && !fluid_name.empty());
-            const bool a_box = (c[0] == box_name && !box_name.empty());
-            if (c[2] == "vdwpotential") { if (a_fluid && b_fluid) ff_pot = c[3]; if (a_box && b_fluid) sf_pot = c[3]; }
-            else if (c[2] == "sigma") { if (a_fluid && b_fluid) d.sig_ff = std::stod(c[3]); if (a_box && b_fluid) d.sig_sf = std::stod(c[3]); }
-            else if (c[2] == "epsilon") { if (a_fluid && b_fluid) d.eps_ff = std::stod(c[3]); if (a_box && b_fluid) d.eps_sf = std::stod(c[3]); }
-            else if (c[2] == "rcut") { if (a_fluid && b_fluid) d.rcut = std::stod(c[3]); }
-            else if (c[2] == "numberofparticles") { if (a_box && b_fluid) cfg->n_particles = std::stoi(c[3]); }
+            for (int b = 0; b < 2; b++) {
+                const bool a_box = (c[0] == box_name[b] && !box_name[b].empty());
+                if (!(a_box && b_fluid)) continue;
+                if (c[2] == "vdwpotential") sf_pot[b] = c[3];
+                else if (c[2] == "sigma") sig_sf[b] = std::stod(c[3]);
+                else if (c[2] == "epsilon") eps_sf[b] = std::stod(c[3]);
+                else if (c[2] == "numberofparticles") n_parts[b] = std::stoi(c[3]);
+                break;                             // Tools::FindIndex returns the first box of that name
+            }
+            if (a_fluid && b_fluid) {
+                if (c[2] == "vdwpotential") ff_pot = c[3];
+                else if (c[2] == "sigma") d.sig_ff = std::stod(c[3]);
+                else if (c[2] == "epsilon") d.eps_ff = std::stod(c[3]);
+                else if (c[2] == "rcut") d.rcut = std::stod(c[3]);
+            }
         }
         else if (k == "samplerdf") cfg->sample_rdf = (c[1] == fluid_name && c[2] == fluid_name) ? 1 : 0;
         else if (k == "printtrajectory") cfg->print_trajectory = 1;
@@ -138,26 +150,34 @@ static int read_input_file(const char* path, mcpm_sim_config* cfg) {
         else if (k == "devices") cfg->devices = std::max(1, std::stoi(c[1]));
     }
     copy_name(cfg->fluid, fluid_name);
-    copy_name(cfg->box, box_name);
-    // post-processing, src/read.cpp:122-168
-    const double maxRcut = d.rcut;
-    d.width[2] = size;
-    if (geometry == "slit") { d.geometry = MCPM_GEOM_SLIT; d.width[0] = d.width[1] = 2 * maxRcut; }   // :134
-    else if (geometry == "bulk") { d.geometry = MCPM_GEOM_BULK; d.width[0] = d.width[1] = d.width[2]; } // :135
-    else if (geometry == "sphere") { d.geometry = MCPM_GEOM_SPHERE; d.width[0] = d.width[1] = d.width[2]; }   // :130
-    else if (geometry == "cylinder") { d.geometry = MCPM_GEOM_CYLINDER; d.width[0] = 2 * maxRcut; d.width[1] = d.width[2]; }   // :131-133
-    else d.geometry = -1;
-    // wall dispatch of src/energy.cpp:69-77: ("lj", slit) -> SlitLJ_Pot, ("lj", sphere) -> SphericalLJ_Pot, ("lj10-4" | "steele10-4-3", cylinder)
-    // -> the two cylindrical walls; anything else matches nothing, e.g. "steele10-4-3" + slit
-    d.wall_kind = (sf_pot == "lj" && geometry == "slit") ? MCPM_WALL_SLIT_LJ : (sf_pot == "lj" && geometry == "sphere") ? MCPM_WALL_SPHERE_LJ :
-                  (sf_pot == "lj10-4" && geometry == "cylinder") ? MCPM_WALL_CYL_LJ104 : (sf_pot == "steele10-4-3" && geometry == "cylinder") ? MCPM_WALL_CYL_STEELE : MCPM_WALL_NONE;
+    copy_name(cfg->box, box_name[0]);
+    copy_name(cfg->box2, box_name[1]);
+    cfg->n_particles = n_parts[0]; cfg->n_particles2 = n_parts[1];
     // pair dispatch of src/energy.cpp:79-101: "lj", "hs"; the EAM potentials are recognised and refused; anything else gives no pair energy
     d.pair_kind = ff_pot == "hs" ? MCPM_PAIR_HS : (ff_pot.rfind("eam_", 0) == 0 ? 2 : MCPM_PAIR_LJ);
     if (ff_pot != "lj" && ff_pot != "hs" && d.pair_kind == MCPM_PAIR_LJ) d.eps_ff = 0.0;      // no potential matched: an ideal gas
     d.pressure = cfg->pressure;
     d.dv = 1e-3;               // src/MC.cpp:33
-    d.dr = 0.1 * d.width[2];   // :168
     d.n_equil_sets = (int)cfg->n_equil_sets;
+    cfg->system2 = d;          // the fluid, temperature and move weights are the system's
+    // per-box post-processing, src/read.cpp:122-168
+    const double maxRcut = d.rcut;
+    for (int b = 0; b < 2; b++) {
+        mcpm_system_desc& x = b ? cfg->system2 : cfg->system;
+        const std::string& geo = geometry[b];
+        x.rho_s = rho_s[b]; x.n_layers = n_layers[b]; x.delta = delta[b]; x.sig_sf = sig_sf[b]; x.eps_sf = eps_sf[b];
+        x.width[2] = size[b];
+        if (geo == "slit") { x.geometry = MCPM_GEOM_SLIT; x.width[0] = x.width[1] = 2 * maxRcut; }   // :134
+        else if (geo == "bulk") { x.geometry = MCPM_GEOM_BULK; x.width[0] = x.width[1] = x.width[2]; } // :135
+        else if (geo == "sphere") { x.geometry = MCPM_GEOM_SPHERE; x.width[0] = x.width[1] = x.width[2]; }   // :130
+        else if (geo == "cylinder") { x.geometry = MCPM_GEOM_CYLINDER; x.width[0] = 2 * maxRcut; x.width[1] = x.width[2]; }   // :131-133
+        else x.geometry = -1;
+        // wall dispatch of src/energy.cpp:69-77: ("lj", slit) -> SlitLJ_Pot, ("lj", sphere) -> SphericalLJ_Pot, ("lj10-4" | "steele10-4-3", cylinder)
+        // -> the two cylindrical walls; anything else matches nothing, e.g. "steele10-4-3" + slit
+        x.wall_kind = (sf_pot[b] == "lj" && geo == "slit") ? MCPM_WALL_SLIT_LJ : (sf_pot[b] == "lj" && geo == "sphere") ? MCPM_WALL_SPHERE_LJ :
+                      (sf_pot[b] == "lj10-4" && geo == "cylinder") ? MCPM_WALL_CYL_LJ104 : (sf_pot[b] == "steele10-4-3" && geo == "cylinder") ? MCPM_WALL_CYL_STEELE : MCPM_WALL_NONE;
+        x.dr = 0.1 * x.width[2];   // :168
+    }
     return MCPM_OK;
 }
 
@@ -199,9 +219,16 @@ void print_params(const mcpm_sim_config& c, std::ostream& os) {
     os << "\tNum. of change volume attempts: " << d.n_vol << std::endl;
     os << "\tNum. of swap attempts: " << d.n_swap << std::endl;
     os << std::endl;
+    const int nb = c.n_boxes == 2 ? 2 : 1;
+    const mcpm_system_desc* bd[2] = {&c.system, &c.system2};
+    const char* bname[2] = {c.box, c.box2};
+    const int bn[2] = {c.n_particles, c.n_particles2};
+    double vol_total = -1.;                                          // thermoSys.volume starts at -1 and is += per box (src/MC.cpp:37, src/read.cpp:137)
+    int n_total = 0;
+    for (int b = 0; b < nb; b++) { vol_total += box_volume(*bd[b]); n_total += bn[b]; }
     os << "System parameters:" << std::endl;
-    os << "\tNum. of particles: " << c.n_particles << std::endl;
-    os << "\tVolume (AA^3): " << box_volume(d) - 1. << std::endl;   // thermoSys.volume starts at -1 and is += (src/MC.cpp:37, src/read.cpp:137)
+    os << "\tNum. of particles: " << n_total << std::endl;
+    os << "\tVolume (AA^3): " << vol_total << std::endl;
     os << "\tExternal temperature (K): " << d.temperature << std::endl;
     if (c.pressure >= 0) os << "\tExternal pressure (Pa): " << c.pressure << std::endl;
     os << std::endl;
@@ -218,22 +245,29 @@ void print_params(const mcpm_sim_config& c, std::ostream& os) {
     os << "\trcut (AA): " << d.rcut << std::endl;
     os << std::endl;
     os << "Box parameters:" << std::endl;
-    os << "Box 0: " << c.box << std::endl;
-    os << "\tGeometry: " << geometry_name(d.geometry) << std::endl;
-    os << "\tInitial width (AA): " << d.width[2] << std::endl;
-    if (d.rho_s > 0) os << "\tSurface density (AA^-2): " << d.rho_s << std::endl;
-    if (d.n_layers > 1) os << "\tLayers per wall: " << d.n_layers << std::endl;
-    if (d.delta > 0) os << "\tDistance between layers (AA): " << d.delta << std::endl;
-    os << "\tInitial number of particles: " << c.n_particles << std::endl;
+    for (int b = 0; b < nb; b++) {
+        const mcpm_system_desc& x = *bd[b];
+        os << "Box " << b << ": " << bname[b] << std::endl;
+        os << "\tGeometry: " << geometry_name(x.geometry) << std::endl;
+        os << "\tInitial width (AA): " << x.width[2] << std::endl;
+        if (x.rho_s > 0) os << "\tSurface density (AA^-2): " << x.rho_s << std::endl;
+        if (x.n_layers > 1) os << "\tLayers per wall: " << x.n_layers << std::endl;
+        if (x.delta > 0) os << "\tDistance between layers (AA): " << x.delta << std::endl;
+        os << "\tInitial number of particles: " << bn[b] << std::endl;
+        if (c.fix_volume[b]) os << "\tVolume fixed." << std::endl;
+    }
     os << std::endl;
     os << "Box-fluid interaction parameters:" << std::endl;
-    os << c.box << "-" << c.fluid << std::endl;
-    if (d.wall_kind == MCPM_WALL_SLIT_LJ || d.wall_kind == MCPM_WALL_SPHERE_LJ) os << "\tVdW potential: lj" << std::endl;
-    else if (d.wall_kind == MCPM_WALL_CYL_LJ104) os << "\tVdW potential: lj10-4" << std::endl;
-    else if (d.wall_kind == MCPM_WALL_CYL_STEELE) os << "\tVdW potential: steele10-4-3" << std::endl;
-    if (d.sig_sf > 0) os << "\tsigma (AA): " << d.sig_sf << std::endl;
-    if (d.eps_sf > 0) os << "\tepsilon (K): " << d.eps_sf << std::endl;
-    os << "\tInitial number of particles: " << c.n_particles << std::endl;
+    for (int b = 0; b < nb; b++) {
+        const mcpm_system_desc& x = *bd[b];
+        os << bname[b] << "-" << c.fluid << std::endl;
+        if (x.wall_kind == MCPM_WALL_SLIT_LJ || x.wall_kind == MCPM_WALL_SPHERE_LJ) os << "\tVdW potential: lj" << std::endl;
+        else if (x.wall_kind == MCPM_WALL_CYL_LJ104) os << "\tVdW potential: lj10-4" << std::endl;
+        else if (x.wall_kind == MCPM_WALL_CYL_STEELE) os << "\tVdW potential: steele10-4-3" << std::endl;
+        if (x.sig_sf > 0) os << "\tsigma (AA): " << x.sig_sf << std::endl;
+        if (x.eps_sf > 0) os << "\tepsilon (K): " << x.eps_sf << std::endl;
+        os << "\tInitial number of particles: " << bn[b] << std::endl;
+    }
     os << std::endl;
     if (c.sample_rdf) os << "Sample RDF: " << c.fluid << "-" << c.fluid << std::endl;
     os << (c.print_trajectory ? "Print Trajectory: Yes" : "Print Trajectory: No") << std::endl;
@@ -295,12 +329,9 @@ void print_log(const Outputs& o, const mcpm_sim_config& c, const mcpm_system_des
     else f << "nan" << "\t" << "-nan" << "\n";
 }
 
-// MC::PrintStats, src/print.cpp:234-264
-void print_stats(const mcpm_sim_config& c, const mcpm_system_desc& d, size_t set, const mcpm_chain_stats* st, std::ostream& os) {
-    os << std::fixed << std::setprecision(7);
-    if (set < c.n_equil_sets) os << "Equilibrium set: " << set << std::endl;
-    else os << "Set: " << set << std::endl;
-    os << "Box " << c.box << ":" << std::endl;
+// MC::PrintStats, src/print.cpp:234-264: a header, one block per box, a blank line
+void print_stats_box(const mcpm_sim_config& c, const char* box, const mcpm_system_desc& d, size_t set, const mcpm_chain_stats* st, std::ostream& os) {
+    os << "Box " << box << ":" << std::endl;
     if (d.n_vol > 0) {
         os << "\tAcceptVolRatio; RejectVolRatio:\t";
         os << st->accept_vol * 1. / st->n_vol_changes << "; " << st->reject_vol * 1. / st->n_vol_changes << std::endl;
@@ -317,6 +348,15 @@ void print_stats(const mcpm_sim_config& c, const mcpm_system_desc& d, size_t set
     }
     os << "\tNumParticles; BoxSize; Energy/Particle:\t";
     os << st->n << "; " << ((d.n_vol > 0 && st->width > 0) ? st->width : d.width[2]) << "; " << st->energy / st->n << std::endl;
+}
+void print_stats_header(const mcpm_sim_config& c, size_t set, std::ostream& os) {
+    os << std::fixed << std::setprecision(7);
+    if (set < c.n_equil_sets) os << "Equilibrium set: " << set << std::endl;
+    else os << "Set: " << set << std::endl;
+}
+void print_stats(const mcpm_sim_config& c, const mcpm_system_desc& d, size_t set, const mcpm_chain_stats* st, std::ostream& os) {
+    print_stats_header(c, set, os);
+    print_stats_box(c, c.box, d, set, st, os);
     os << std::endl;   // like the reference, the stream stays fixed/7 for everything printed afterwards
 }
 
@@ -352,6 +392,172 @@ extern "C" int mcpm_simulate(const char* input_path, const char* out_dir, int fl
     }
 }
 
+// Two boxes (thermoSys.nBoxes == 2, the Gibbs ensemble at fixed volumes): the same program for a PAIR of linked chains per replica
+// (mcpm_link_boxes, k2_gibbs): InitialConfig and MinimizeEnergy per box, the set loop with PrintStats / PrintTrajectory / PrintLog for both
+// boxes in the reference's formats (src/main.cpp:16-97, src/energy.cpp:13-34, src/print.cpp).  Replica r is the pair of chains (2r, 2r+1).
+static int simulate_two_boxes(mcpm_sim_config& cfg, const char* out_dir, int flags, std::ostream& log, std::chrono::system_clock::time_point start) {
+    using clock = std::chrono::system_clock;
+    const bool q5 = flags & 1;
+    mcpm_system_desc* sys[2] = {&cfg.system, &cfg.system2};
+    const char* bname[2] = {cfg.box, cfg.box2};
+    const int n0[2] = {cfg.n_particles, cfg.n_particles2};
+    for (int b = 0; b < 2; b++) {
+        if (sys[b]->geometry < 0) return host_fail(MCPM_ERR_UNSUPPORTED, "unknown geometry");
+        if (sys[b]->pair_kind != MCPM_PAIR_LJ) return host_fail(MCPM_ERR_UNSUPPORTED, "two boxes: the Lennard-Jones fluid only");
+    }
+    if (cfg.system.n_vol != 0) return host_fail(MCPM_ERR_UNSUPPORTED, "volume moves between two boxes (the Gibbs branches of MC::ChangeVolume) are out of scope");
+    if (cfg.sweep_points > 0 || cfg.sample_rdf) return host_fail(MCPM_ERR_UNSUPPORTED, "two boxes: no chemical-potential sweep and no RDF sampling");
+    print_params(cfg, log);
+    for (int b = 0; b < 2; b++)
+        if (sys[b]->geometry == MCPM_GEOM_BULK && sys[b]->width[2] < 2 * sys[b]->rcut) {   // src/print.cpp:96-103
+            std::cout << "Error: Box size must be larger than twice the cut-off radius." << std::endl;
+            std::cout << "Box: " << bname[b] << std::endl << std::endl;
+            mcpm::set_last_error("box size must be larger than twice the cut-off radius");
+            return MCPM_ERR_ARG;
+        }
+    const int n_sets = (int)cfg.n_sets, n_equil = (int)cfg.n_equil_sets, print_every = std::max(1, (int)cfg.print_every);
+    const long long steps_per_set = (long long)cfg.steps_per_set;
+    const int replicas = std::max(1, cfg.replicas), n_chains = 2 * replicas;
+    const int total = n0[0] + n0[1];
+    const int capacity = cfg.capacity > 0 ? cfg.capacity : std::max(1024, ((total + 64 + 31) / 32) * 32);   // a box can at most hold every particle of the system
+    const std::string base = out_dir ? std::string(out_dir) : std::string(".");
+    std::vector<Outputs> outs(n_chains);
+    for (int r = 0; r < replicas; r++) {
+        std::string project = cfg.project;
+        if (replicas > 1) project += "_r" + std::to_string(r);
+        for (int b = 0; b < 2; b++) outs[2 * r + b] = output_directory(base, project, bname[b]);
+    }
+    int ndev = 0;
+    if (mcpm_device_count(&ndev) != MCPM_OK || ndev < 1) return host_fail(MCPM_ERR_CUDA, std::string("no CUDA device: ") + mcpm_last_error());
+    ContextSet guard;
+    guard.ctx.assign(1, nullptr);
+    mcpm_ctx*& ctx = guard.ctx[0];
+    int rc = mcpm_create(0, n_chains, capacity, &ctx);
+    if (rc) return host_fail(rc, mcpm_last_error());
+    auto set_systems = [&](bool moves_only) -> int {
+        for (int c = 0; c < n_chains; c++) {
+            mcpm_system_desc m = *sys[c & 1];
+            m.n_equil_sets = moves_only ? 0 : n_equil;
+            if (moves_only) { m.n_swap = 0; m.n_vol = 0; m.n_disp = 1; }    // MinimizeEnergy: MoveParticle only, no dr adaptation
+            int r2 = mcpm_set_system(ctx, c, &m);
+            if (r2) return r2;
+        }
+        return MCPM_OK;
+    };
+    rc = set_systems(false);
+    if (rc) return host_fail(rc, mcpm_last_error());
+    std::vector<unsigned int> ids(n_chains);
+    for (int c = 0; c < n_chains; c++) ids[c] = (unsigned int)(c / 2);       // one stream per system: box 0's id
+    rc = mcpm_set_stream_ids(ctx, ids.data());
+    for (int r = 0; r < replicas && !rc; r++) rc = mcpm_link_boxes(ctx, 2 * r, 2 * r + 1);
+    if (rc) return host_fail(rc, mcpm_last_error());
+
+    // MC::InitialConfig, src/moves.cpp:56-67: box after box, three draws per particle
+    std::random_device rd;
+    const unsigned long long seed = cfg.has_seed ? cfg.seed : rd();
+    std::vector<std::vector<double>> X(n_chains), Y(n_chains), Z(n_chains);
+    for (int r = 0; r < replicas; r++) {
+        RefRandom rnd(seed + 7919ull * (unsigned long long)r);
+        for (int b = 0; b < 2; b++) {
+            const int c = 2 * r + b;
+            X[c].resize(capacity); Y[c].resize(capacity); Z[c].resize(capacity);
+            for (int k = 0; k < n0[b]; k++) insert_particle(*sys[b], rnd, X[c][k], Y[c][k], Z[c][k]);
+            rc = mcpm_set_positions(ctx, c, n0[b], X[c].data(), Y[c].data(), Z[c].data());
+            if (rc) return host_fail(rc, mcpm_last_error());
+        }
+    }
+    log << "Initial configuration set." << std::endl << std::endl;
+    for (int c = 0; c < n_chains; c++) print_trajectory(outs[c], cfg, *sys[c & 1], 0, sys[c & 1]->dr, n0[c & 1], X[c].data(), Y[c].data(), Z[c].data());
+
+    std::vector<mcpm_chain_stats> stats(n_chains);
+    // MC::MinimizeEnergy, src/energy.cpp:13-34: for every non-empty box, BoxEnergy, 200 * N_box calls of MoveParticle — which picks ITS box
+    // among both, src/moves.cpp:127-137 — and BoxEnergy again
+    log << "Starting minimization..." << std::endl;
+    auto t0 = clock::now();
+    rc = set_systems(true);
+    if (rc) return host_fail(rc, mcpm_last_error());
+    for (int b = 0; b < 2; b++) {
+        if (n0[b] <= 0) continue;
+        mcpm_box_energy_t be;
+        rc = mcpm_box_energy(ctx, b, &be, nullptr, nullptr);
+        if (rc) return host_fail(rc, mcpm_last_error());
+        log << "Minimizing initial configuration of box \"" << bname[b] << "\"..." << std::endl;
+        log << "\tEnergy/part. of box \"" << bname[b] << "\" before minimization: " << be.energy / n0[b] << " K" << std::endl;
+        mcpm_run_params mp;
+        memset(&mp, 0, sizeof(mp));
+        mp.first_set = 1; mp.n_sets = 1; mp.steps_per_set = 200LL * n0[b]; mp.rng_mode = MCPM_RNG_PHILOX;
+        mp.seed = seed ^ (0x6d696e696d697a65ull + (unsigned long long)b); mp.check_energy = 2; mp.no_sampling = 1;
+        rc = mcpm_run(ctx, &mp, stats.data());
+        if (rc) return host_fail(rc, mcpm_last_error());
+        log << "\tEnergy/part. of box \"" << bname[b] << "\" after minimization (" << n0[b] * 200 << " moves): ";
+        log << stats[b].energy_check / std::max(1, stats[b].n) << " K" << std::endl;
+    }
+    rc = set_systems(false);                                             // the real move weights; same energetics: positions and energies stay
+    for (int c = 0; c < n_chains && !rc; c++) {
+        rc = mcpm_set_dr(ctx, c, sys[c & 1]->dr);
+        if (!rc) rc = mcpm_set_step_counter(ctx, c, 0);
+    }
+    if (!rc) rc = mcpm_reset_accumulators(ctx);
+    if (rc) return host_fail(rc, mcpm_last_error());
+    std::vector<int> nn(n_chains, 0);
+    auto download = [&]() -> int {
+        for (int c = 0; c < n_chains; c++) {
+            int r2 = mcpm_get_positions(ctx, c, &nn[c], X[c].data(), Y[c].data(), Z[c].data());
+            if (r2) return r2;
+        }
+        return MCPM_OK;
+    };
+    rc = download();
+    if (rc) return host_fail(rc, mcpm_last_error());
+    auto t1 = clock::now();
+    log << "Minimization finished" << std::endl;
+    log << "Elapsed time of minimization: " << std::chrono::duration<double>(t1 - t0).count() << " s" << std::endl << std::endl;
+    for (int c = 0; c < n_chains; c++) {
+        print_trajectory(outs[c], cfg, *sys[c & 1], 0, sys[c & 1]->dr, nn[c], X[c].data(), Y[c].data(), Z[c].data());
+        print_log(outs[c], cfg, *sys[c & 1], 0, nullptr, q5);
+    }
+
+    // the set loop, src/main.cpp:63-84: one mcpm_run per print interval
+    auto ts = clock::now();
+    for (int set = 1; set <= n_sets;) {
+        const int next_print = ((set + print_every - 1) / print_every) * print_every;
+        const int last = std::min(n_sets, next_print);
+        mcpm_run_params rp;
+        memset(&rp, 0, sizeof(rp));
+        rp.first_set = set; rp.n_sets = last - set + 1; rp.steps_per_set = steps_per_set; rp.rng_mode = MCPM_RNG_PHILOX; rp.seed = seed;
+        rp.check_energy = 2;
+        rc = mcpm_run(ctx, &rp, stats.data());
+        if (rc) return host_fail(rc, mcpm_last_error());
+        if (last % print_every == 0) {
+            rc = download();
+            if (rc) return host_fail(rc, mcpm_last_error());
+            print_stats_header(cfg, (size_t)last, log);
+            for (int c = 0; c < n_chains; c++) {
+                mcpm_chain_stats shown = stats[c];
+                shown.dr = shown.dr_used;                                   // printed BEFORE AdjustMCMoves, src/main.cpp:77-83
+                if (c < 2) print_stats_box(cfg, bname[c], *sys[c], (size_t)last, &shown, log);
+                print_trajectory(outs[c], cfg, *sys[c & 1], (size_t)last, shown.dr, nn[c], X[c].data(), Y[c].data(), Z[c].data());
+                // ComputeChemicalPotential from the Widom/BAR sums the transfers of the last set left in both boxes (src/moves.cpp:368-374)
+                double mu_ex = 0., mu = 0.;
+                const bool have_mu = cfg.system.n_swap > 0;
+                if (have_mu) { rc = mcpm_chemical_potential(ctx, c, &mu_ex, &mu); if (rc) return host_fail(rc, mcpm_last_error()); }
+                print_log(outs[c], cfg, *sys[c & 1], (size_t)last, &stats[c], q5, have_mu, mu_ex, mu);
+            }
+            log << std::endl;
+        }
+        set = last + 1;
+    }
+    auto te = clock::now();
+    std::time_t endTime = clock::to_time_t(te);
+    log << std::endl;
+    log << "Simulation finished" << std::endl;
+    log << "Elapsed time of simulation: " << std::chrono::duration<double>(te - ts).count() << " s" << std::endl;
+    log << "Computation finished at " << std::ctime(&endTime) << std::endl;
+    log << std::endl;
+    (void)start;
+    return MCPM_OK;
+}
+
 static int simulate(const char* input_path, const char* out_dir, int flags) {
     using clock = std::chrono::system_clock;
     const bool q5 = flags & 1, quiet = flags & 2;
@@ -366,9 +572,10 @@ static int simulate(const char* input_path, const char* out_dir, int flags) {
     int rc = mcpm_read_input_file(input_path, &cfg);
     if (rc == MCPM_ERR_IO) { std::cout << "Error opening file: " << (input_path ? input_path : "") << std::endl; return rc; }
     if (rc) return host_fail(rc, std::string("could not parse the input file: ") + mcpm_last_error());
-    if (cfg.n_boxes != 1 || cfg.n_species != 1) return host_fail(MCPM_ERR_UNSUPPORTED, "exactly one box and one species are supported");
+    if (cfg.n_boxes < 1 || cfg.n_boxes > 2 || cfg.n_species != 1) return host_fail(MCPM_ERR_UNSUPPORTED, "one or two boxes and exactly one species are supported");
     if (cfg.continue_after_crash)   // the reference restarts from ReadTrajectory/ReadLogFile (src/read.cpp:173-281): out of scope, say so
         return host_fail(MCPM_ERR_UNSUPPORTED, "ContinueAfterCrash (restart from trajectory/log files) is not supported");
+    if (cfg.n_boxes == 2) return simulate_two_boxes(cfg, out_dir, flags, log, start);
     mcpm_system_desc& sys = cfg.system;
     if (sys.geometry < 0) return host_fail(MCPM_ERR_UNSUPPORTED, "unknown geometry");
     if (sys.pair_kind > MCPM_PAIR_HS) return host_fail(MCPM_ERR_UNSUPPORTED, "EAM potentials are out of scope");

@@ -95,6 +95,7 @@ class SimConfig(C.Structure):
         ("replicas", C.c_int), ("sweep_points", C.c_int), ("sweep_mu0", C.c_double), ("sweep_mu1", C.c_double),
         ("capacity", C.c_int), ("devices", C.c_int),
         ("system", SystemDesc),
+        ("box2", C.c_char * 64), ("n_particles2", C.c_int), ("fix_volume", C.c_int * 2), ("system2", SystemDesc),
     ]
 
 

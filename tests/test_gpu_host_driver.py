@@ -1,4 +1,5 @@
 """GPU: the C++ host driver (mcpm_simulate) — reference-format outputs and ensemble parity."""
+import json
 import os
 import re
 import subprocess
@@ -214,3 +215,41 @@ def test_driver_isotherm_matches_loadings_of_the_compiled_reference(tmp_path):
     assert not bad, bad
     assert np.all(np.diff(iso[:, 1]) > -8.0)                       # a monotone isotherm up to noise, with the condensation jump
     assert iso[-1, 1] > 2.0 * iso[20, 1]
+
+
+def test_two_boxes_through_the_driver(tmp_path):
+    """A two-box input in the reference's grammar (the Gibbs ensemble at fixed volumes, tests/golden/gibbs_ar.in): the PrintParams echo equals the
+    reference program's byte for byte, both boxes get their directory / log / trajectory in the reference's formats, transfers conserve the
+    particle number, and the loadings of the boxes agree with runs of the compiled reference (tests/golden/gibbs_driver_reference.json, made by
+    tests/golden/make_gibbs_driver_reference.py)."""
+    ref = json.load(open(os.path.join(GOLDEN, "gibbs_driver_reference.json")))
+    text = open(os.path.join(GOLDEN, "gibbs_ar.in")).read()
+    text = re.sub(r"ProductionSets \d+", "ProductionSets 15", text) + "Replicas 8\nSeed 4242\n"
+    inp = tmp_path / "gibbs.in"
+    inp.write_text(text)
+    stdout = run_driver(tmp_path, str(inp))
+    echo = stdout[stdout.index("Simulation parameters:"):stdout.index("Initial configuration set.")]
+    assert echo.replace("Production sets: 15", "Production sets: 6") == ref["print_params"]
+    assert 'Minimizing initial configuration of box "liquid"...' in stdout and 'Minimizing initial configuration of box "vapour"...' in stdout
+    blocks = stdout.split("\nSet: ")[1:]
+    assert len(blocks) == 13 and all("Box liquid:" in b and "Box vapour:" in b and "AcceptSwapRatio; RejectSwapRatio:" in b for b in blocks)
+    means = {"liquid": [], "vapour": []}
+    for r in range(8):
+        n_of = {}
+        for box in ("liquid", "vapour"):
+            d = tmp_path / f"gibbs_ar_r{r}" / box
+            log = open(d / "simulation_ar.log").read().splitlines()
+            assert log[0].startswith("Set\tTemp(K)\twidth(AA)\tVolume(AA^3)") and len(log) == 16
+            rows = [row.split("\t") for row in log[1:]]
+            assert all(len(row) == 11 for row in rows)
+            assert all(row[9] not in ("nan", "-nan") for row in rows[3:])        # mu from the transfers' Widom / BAR sums
+            n_of[box] = np.array([int(row[7]) for row in rows])
+            traj = open(d / "trajectory.exyz").read().splitlines()
+            assert int(traj[0]) == n_of[box][-1] and len(traj) == n_of[box][-1] + 2          # PrintTrajectory absent: the last frame only
+            assert traj[1].startswith('Lattice=" %g 0 0 0 %g 0 0 0 %g"' % ((24, 24, 24) if box == "liquid" else (40, 40, 40)))
+            means[box].append(n_of[box][2:].mean())                              # sets 3..15, as the reference fixture counts them
+        assert np.all(n_of["liquid"] + n_of["vapour"] == 290)
+    for box in ("liquid", "vapour"):
+        got, sem = np.mean(means[box]), np.std(means[box], ddof=1) / np.sqrt(8)
+        tol = max(3.0 * np.hypot(sem, ref[box]["sem_n"]), 1.5)
+        assert abs(got - ref[box]["mean_n"]) < tol, (box, got, sem, ref[box]["mean_n"], ref[box]["sem_n"])

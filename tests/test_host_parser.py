@@ -126,3 +126,17 @@ def test_parser_recognises_what_the_engine_refuses(mcpm, tmp_path):
     p.write_text(open(os.path.join(GOLDEN, "lj_npt.in")).read().replace("ExternalPressure 3.0e7\n", ""))
     assert mcpm.lib().mcpm_simulate(str(p).encode(), str(tmp_path).encode(), 2) == 4
     assert b"Gibbs" in mcpm.lib().mcpm_last_error()
+
+
+def test_two_box_input(mcpm):
+    """A second BoxName block: box 1 of a two-box (Gibbs) system with its own geometry / size / wall; fluid, temperature and move weights shared."""
+    import ctypes as C
+    cfg = mcpm.SimConfig()
+    assert mcpm.lib().mcpm_read_input_file(os.path.join(GOLDEN, "gibbs_ar.in").encode(), C.byref(cfg)) == 0
+    assert (cfg.n_boxes, cfg.n_species) == (2, 1)
+    assert (cfg.box.decode(), cfg.box2.decode()) == ("liquid", "vapour") and (cfg.n_particles, cfg.n_particles2) == (230, 60)
+    assert list(cfg.fix_volume) == [1, 1]
+    assert list(cfg.system.width) == [24.0, 24.0, 24.0] and list(cfg.system2.width) == [40.0, 40.0, 40.0]
+    assert cfg.system.dr == pytest.approx(2.4) and cfg.system2.dr == pytest.approx(4.0)               # 0.1 * width, src/read.cpp:168
+    for s in (cfg.system, cfg.system2):
+        assert (s.n_disp, s.n_vol, s.n_swap, s.temperature, s.rcut, s.eps_ff, s.sig_ff) == (4, 0, 1, 120.0, 10.0, 119.8, 3.405)
