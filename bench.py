@@ -443,7 +443,16 @@ def k3_k1_records(m, torch, local):
                 t0 = time.perf_counter()
                 e.particle_energy_batch(0, idx.astype(np.int32), trial)
                 dtb = time.perf_counter() - t0
+                e.k1_resident(0, True)                        # the persistent one-CTA service: no launch per call
+                for i in range(20):
+                    e.particle_energy(0, int(idx[i]), trial[i])
+                t0 = time.perf_counter()
+                for i in range(200):
+                    e.particle_energy(0, int(idx[i]), trial[i])
+                dtr = time.perf_counter() - t0
+                e.k1_resident(0, False)
                 out["k1"].append({"case": name, "n": n, "us_per_call_through_abi": 1e6 * dt / 200, "us_device_per_call": 1e3 * dev_ms / 200,
+                                  "us_per_call_resident_service": 1e6 * dtr / 200,
                                   "us_per_request_in_a_batch_of_200": 1e6 * dtb / 200, "pair_evals_per_call": 2 * n,
                                   "what": "mcpm_particle_energy: stored + displaced position in one launch (positions staged by TMA bulk copies, "
                                           "results through mapped host memory); ctypes call overhead included"})

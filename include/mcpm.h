@@ -168,6 +168,14 @@ int mcpm_get_positions_all(mcpm_ctx* ctx, int* n, double* x, double* y, double* 
  * mapped host memory (no device->host copy, no stream synchronisation per call). */
 int mcpm_particle_energy(mcpm_ctx* ctx, int chain, int index, const double* trial,
                          mcpm_particle_energy_t* cur, mcpm_particle_energy_t* moved);
+/* K1 as a RESIDENT service for one chain: after mcpm_k1_resident(ctx, chain, 1), mcpm_particle_energy / mcpm_apply_move / mcpm_append /
+ * mcpm_remove_swap_last on that chain no longer launch anything — a persistent one-CTA kernel that keeps the chain's positions staged in
+ * shared memory answers through a mailbox in mapped host memory (a few microseconds per MC::EnergyOfParticle call, below the reference's
+ * own ~7 us at N = 500).  The kernel starts with the first request, leaves after ~5 ms without one and whenever any other entry point
+ * touches the context (it is restarted on demand), and writes accepted moves through to global memory, so results never depend on it.
+ * This is the mode a host-driven move loop runs in.  enable = 0 disarms. */
+int mcpm_k1_resident(mcpm_ctx* ctx, int chain, int enable);
+int mcpm_k1_resident_stats(const mcpm_ctx* ctx, unsigned long long* starts, unsigned long long* requests);
 /* The same for `count` requests against the chain's PRESENT configuration in one launch (a host loop that speculates on several
  * trial moves, Widom ghost batches, ...): index[count]; trial = NULL or [count][3]; cur / moved = NULL or [count].  The launch
  * latency that bounds a single call is paid once per batch. */

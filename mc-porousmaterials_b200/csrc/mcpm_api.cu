@@ -64,6 +64,14 @@ struct mcpm_ctx {
     double* h_k1 = nullptr;                    // [MCPM_K1_MAX_BATCH][8] records + the flag word
     double* d_k1_alias = nullptr;              // device address of h_k1
     unsigned long long k1_seq = 0;
+    // resident K1 (k1_server): mailbox in mapped pinned host memory, its own stream; armed for one chain by mcpm_k1_resident
+    cudaStream_t srv_stream = nullptr;
+    K1Mail* h_mail = nullptr; K1Mail* d_mail = nullptr;
+    K1Reply* h_reply = nullptr; K1Reply* d_reply = nullptr;
+    int srv_chain = -1;                        // chain the service is armed for, or -1
+    bool srv_running = false, srv_fast = false;
+    unsigned long long srv_seq = 0;
+    unsigned long long srv_starts = 0, srv_requests = 0;
     // cell-list K3 workspace, allocated on first use
     int *d_cell_of = nullptr, *d_cell_counts = nullptr, *d_cell_starts = nullptr, *d_orig = nullptr;
     double *d_sx = nullptr, *d_sy = nullptr, *d_sz = nullptr;
@@ -185,6 +193,25 @@ static int pull_states(mcpm_ctx* c) {
     return MCPM_OK;
 }
 
+// ---- resident K1: quiescing (the service itself lives beside K1 below) ----
+// Stop the service (if it runs) and bring the device copy of the chain's record up to date: every API entry point that reads or
+// writes device state outside the mailbox calls this first.
+static int k1_server_stop(mcpm_ctx* c) {
+    if (!c->srv_running) return MCPM_OK;
+    c->srv_running = false;
+    if (__atomic_load_n(&c->h_reply->alive, __ATOMIC_ACQUIRE)) {
+        const unsigned long long s = ++c->srv_seq;
+        c->h_mail->what = K1_CMD_STOP;
+        c->h_mail->seq_tail = s;
+        __atomic_store_n(&c->h_mail->seq, s, __ATOMIC_RELEASE);
+    }
+    CU(cudaStreamSynchronize(c->srv_stream));            // at most the idle time-out away
+    CU(cudaMemcpyAsync(c->d_state + c->srv_chain, &c->h_state[c->srv_chain], sizeof(ChainState), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return MCPM_OK;
+}
+#define QUIESCE(c) do { if ((c) && (c)->srv_running) { int rq_ = k1_server_stop(c); if (rq_) return rq_; } } while (0)
+
 extern "C" {
 
 int mcpm_version(void) { return MCPM_VERSION; }
@@ -256,6 +283,10 @@ int mcpm_create(int device, int n_chains, int capacity, mcpm_ctx** out) {
 int mcpm_destroy(mcpm_ctx* c) {
     if (!c) return MCPM_OK;
     cudaSetDevice(c->device);
+    if (c->srv_running) k1_server_stop(c);
+    if (c->srv_stream) { cudaStreamSynchronize(c->srv_stream); cudaStreamDestroy(c->srv_stream); }
+    if (c->h_mail) cudaFreeHost(c->h_mail);
+    if (c->h_reply) cudaFreeHost(c->h_reply);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_params); cudaFree(c->d_state); cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_z);
     cudaFree(c->d_pool_next); cudaFree(c->d_pairs);
@@ -306,6 +337,7 @@ static int refresh_fast_image(mcpm_ctx* c) {
 }
 
 int mcpm_set_system(mcpm_ctx* c, int chain, const mcpm_system_desc* desc) {
+    QUIESCE(c);
     if (!c || !desc) return fail(MCPM_ERR_ARG, "null argument");
     if (chain != -1) { int rc = check_chain(c, chain); if (rc) return rc; }
     ChainParams P;
@@ -373,6 +405,7 @@ int mcpm_link_boxes(mcpm_ctx* c, int box0, int box1) {
 }
 
 int mcpm_set_positions(mcpm_ctx* c, int chain, int n, const double* x, const double* y, const double* z) {
+    QUIESCE(c);
     int rc = check_chain(c, chain); if (rc) return rc;
     if (n < 0 || n > c->cap) return fail(MCPM_ERR_CAPACITY, "n=%d exceeds capacity %d", n, c->cap);
     if (n > 0 && (!x || !y || !z)) return fail(MCPM_ERR_ARG, "null coordinate array");
@@ -395,6 +428,7 @@ int mcpm_set_positions(mcpm_ctx* c, int chain, int n, const double* x, const dou
 }
 
 int mcpm_get_positions(mcpm_ctx* c, int chain, int* n, double* x, double* y, double* z) {
+    QUIESCE(c);
     int rc = check_chain(c, chain); if (rc) return rc;
     CU(cudaSetDevice(c->device));
     const int m = c->h_state[chain].st.n;
@@ -410,6 +444,7 @@ int mcpm_get_positions(mcpm_ctx* c, int chain, int* n, double* x, double* y, dou
 }
 
 int mcpm_set_positions_all(mcpm_ctx* c, const int* n, const double* x, const double* y, const double* z) {
+    QUIESCE(c);
     if (!c || !n || !x || !y || !z) return fail(MCPM_ERR_ARG, "null argument");
     CU(cudaSetDevice(c->device));
     const size_t np = (size_t)c->n_chains * c->cap;
@@ -446,6 +481,7 @@ int mcpm_set_positions_all(mcpm_ctx* c, const int* n, const double* x, const dou
 }
 
 int mcpm_get_positions_all(mcpm_ctx* c, int* n, double* x, double* y, double* z) {
+    QUIESCE(c);
     if (!c || !n || !x || !y || !z) return fail(MCPM_ERR_ARG, "null argument");
     CU(cudaSetDevice(c->device));
     const size_t np = (size_t)c->n_chains * c->cap;
@@ -512,6 +548,81 @@ static int k1_launch(mcpm_ctx* c, int chain, int count, const K1Request* host_re
     return MCPM_OK;
 }
 
+
+// ---- resident K1 ------------------------------------------------------------------------------------
+static int k1_server_start(mcpm_ctx* c) {
+    const int chain = c->srv_chain;
+    if (!c->srv_stream) {
+        CU(cudaStreamCreateWithFlags(&c->srv_stream, cudaStreamNonBlocking));
+        CU(cudaHostAlloc(&c->h_mail, sizeof(K1Mail), cudaHostAllocMapped));
+        CU(cudaHostAlloc(&c->h_reply, sizeof(K1Reply), cudaHostAllocMapped));
+        memset(c->h_mail, 0, sizeof(K1Mail)); memset(c->h_reply, 0, sizeof(K1Reply));
+        CU(cudaHostGetDevicePointer((void**)&c->d_mail, c->h_mail, 0));
+        CU(cudaHostGetDevicePointer((void**)&c->d_reply, c->h_reply, 0));
+    }
+    CU(cudaStreamSynchronize(c->srv_stream));            // a previous instance that timed out has left by now
+    CU(cudaMemcpyAsync(c->d_state + chain, &c->h_state[chain], sizeof(ChainState), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));                // every earlier write to the chain has landed
+    c->srv_fast = c->h_state[chain].fast_image != 0 && !c->h_params[chain].exotic;
+    c->h_reply->alive = 1ull;
+    c->h_reply->seq = c->srv_seq; c->h_reply->seq_tail = c->srv_seq;
+    c->h_mail->seq = c->srv_seq; c->h_mail->seq_tail = c->srv_seq;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    const long long idle = 10000000ll;                   // ~5 ms of SM clocks without a request
+    CU(launch_k1_server(c->srv_fast, c->h_params[chain].pbc[2] != 0, c->d_params, c->d_state, c->d_x, c->d_y, c->d_z, chain, c->cap,
+                        k1_server_smem_bytes(c->cap, c->max_smem), c->d_mail, c->d_reply, c->srv_seq, idle, c->srv_stream));
+    c->launches++; c->srv_starts++;
+    c->srv_running = true;
+    return MCPM_OK;
+}
+
+// Wait until the service has answered command `s` (both copies of the sequence number in the reply line).  false: it left before taking it.
+static int k1_server_wait(mcpm_ctx* c, unsigned long long s, bool& answered) {
+    answered = false;
+    const volatile K1Reply* r = c->h_reply;
+    for (unsigned long long spins = 1;; spins++) {
+        if (__atomic_load_n(&r->seq, __ATOMIC_ACQUIRE) == s && __atomic_load_n(&r->seq_tail, __ATOMIC_ACQUIRE) == s) { answered = true; return MCPM_OK; }
+        if ((spins & 0xfffull) == 0) {
+            if (!__atomic_load_n(&r->alive, __ATOMIC_ACQUIRE)) {                  // it left (idle) — before or after this command?
+                answered = __atomic_load_n(&r->seq, __ATOMIC_ACQUIRE) == s && __atomic_load_n(&r->seq_tail, __ATOMIC_ACQUIRE) == s;
+                return MCPM_OK;
+            }
+            if ((spins & 0xfffffull) == 0) {
+                cudaError_t q = cudaStreamQuery(c->srv_stream);
+                if (q != cudaErrorNotReady && q != cudaSuccess) { c->srv_running = false; return fail(MCPM_ERR_CUDA, "resident K1 failed: %s", cudaGetErrorString(q)); }
+                if (spins > (1ull << 34)) { c->srv_running = false; return fail(MCPM_ERR_CUDA, "resident K1 does not answer"); }
+            }
+        }
+    }
+}
+// One command through the mailbox, waited for; restarts the service if it has timed out in the meantime.  rec: 8 doubles or null.
+static int k1_server_call(mcpm_ctx* c, int cmd, int index, const double* t, double* rec) {
+    for (int attempt = 0; attempt < 3; attempt++) {
+        if (!c->srv_running) { int rc = k1_server_start(c); if (rc) return rc; }
+        const unsigned long long s = ++c->srv_seq;
+        K1Mail* m = c->h_mail;
+        m->what = (unsigned long long)cmd | ((t ? 1ull : 0ull) << 8) | ((unsigned long long)(unsigned)index << 32);
+        for (int k = 0; k < 3; k++) m->t[k] = t ? t[k] : 0.0;
+        m->seq_tail = s;
+        __atomic_store_n(&m->seq, s, __ATOMIC_RELEASE);
+        c->srv_requests++;
+        bool answered = false;
+        int rc = k1_server_wait(c, s, answered); if (rc) return rc;
+        if (answered) {
+            if (rec) {
+                const volatile double* r = c->h_reply->r;
+                rec[0] = r[0]; rec[1] = 0.0; rec[2] = r[1]; rec[3] = r[2]; rec[4] = r[3]; rec[5] = 0.0; rec[6] = r[4]; rec[7] = r[5];
+            }
+            return MCPM_OK;
+        }
+        c->srv_running = false;                          // it left before taking the command: start again and ask again (srv_seq goes back)
+        c->srv_seq = s - 1;
+        c->srv_requests--;
+    }
+    return fail(MCPM_ERR_CUDA, "resident K1 keeps timing out");
+}
+static bool k1_served(const mcpm_ctx* c, int chain) { return c->srv_chain == chain && chain >= 0; }
+
 static bool trial_in_box(const ChainParams& P, const double* t) {
     for (int k = 0; k < 3; k++) if (P.pbc[k] && !(t[k] >= 0.0 && t[k] <= P.L[k])) return false;
     return true;
@@ -534,13 +645,44 @@ int mcpm_particle_energy(mcpm_ctx* c, int chain, int index, const double* trial,
     for (int k = 0; k < 3; k++) rq.t[k] = trial ? trial[k] : 0.0;
     // the trial position must satisfy the fast-image precondition too
     const bool fast = c->h_state[chain].fast_image != 0 && (!trial || trial_in_box(c->h_params[chain], trial));
+    if (k1_served(c, chain)) {
+        // a service instantiated for coordinates inside the box (fast minimum image) cannot take a trial position outside it: such a
+        // request falls back to a launch; a general service takes anything
+        const bool chain_fast = c->h_state[chain].fast_image != 0 && !c->h_params[chain].exotic;
+        const bool srv_fast = c->srv_running ? c->srv_fast : chain_fast;
+        if (!srv_fast || fast) {
+            double rec[8];
+            rc = k1_server_call(c, K1_CMD_ENERGY, index, trial, rec); if (rc) return rc;
+            k1_record(rec, cur, moved);
+            return MCPM_OK;
+        }
+    }
+    QUIESCE(c);
     rc = k1_launch(c, chain, 1, &rq, fast); if (rc) return rc;
     k1_record(c->h_k1, cur, moved);
     return MCPM_OK;
 }
 
+int mcpm_k1_resident(mcpm_ctx* c, int chain, int enable) {
+    if (!c) return fail(MCPM_ERR_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    QUIESCE(c);
+    if (!enable) { c->srv_chain = -1; return MCPM_OK; }
+    int rc = check_chain(c, chain); if (rc) return rc;
+    if (!c->has_system[chain]) return fail(MCPM_ERR_ARG, "set the system of chain %d first", chain);
+    c->srv_chain = chain;                                // armed: the first mcpm_particle_energy starts the service
+    return MCPM_OK;
+}
+int mcpm_k1_resident_stats(const mcpm_ctx* c, unsigned long long* starts, unsigned long long* requests) {
+    if (!c) return fail(MCPM_ERR_ARG, "null context");
+    if (starts) *starts = c->srv_starts;
+    if (requests) *requests = c->srv_requests;
+    return MCPM_OK;
+}
+
 int mcpm_particle_energy_batch(mcpm_ctx* c, int chain, int count, const int* index, const double* trial, mcpm_particle_energy_t* cur,
                                mcpm_particle_energy_t* moved) {
+    QUIESCE(c);
     int rc = check_chain(c, chain); if (rc) return rc;
     if (!c->has_system[chain]) return fail(MCPM_ERR_ARG, "set the system of chain %d first", chain);
     if (count < 0 || (count > 0 && !index)) return fail(MCPM_ERR_ARG, "bad request list");
@@ -618,6 +760,7 @@ static int box_energy_range(mcpm_ctx* c, int chain0, int count, double* per_pair
 }
 
 int mcpm_box_energy(mcpm_ctx* c, int chain, mcpm_box_energy_t* out, double* per_pair, double* per_wall) {
+    QUIESCE(c);
     int rc = check_chain(c, chain); if (rc) return rc;
     CU(cudaSetDevice(c->device));
     rc = box_energy_range(c, chain, 1, c->d_pp, c->d_pw); if (rc) return rc;
@@ -630,6 +773,7 @@ int mcpm_box_energy(mcpm_ctx* c, int chain, mcpm_box_energy_t* out, double* per_
 }
 
 int mcpm_box_energy_all(mcpm_ctx* c, mcpm_box_energy_t* out) {
+    QUIESCE(c);
     if (!c) return fail(MCPM_ERR_ARG, "null context");
     CU(cudaSetDevice(c->device));
     int rc = box_energy_range(c, 0, c->n_chains, nullptr, nullptr); if (rc) return rc;
@@ -655,6 +799,11 @@ int mcpm_apply_move(mcpm_ctx* c, int chain, int index, const double xyz[3]) {
     int rc = check_chain(c, chain); if (rc) return rc;
     if (!xyz || index < 0 || index >= c->h_state[chain].st.n) return fail(MCPM_ERR_ARG, "bad index %d", index);
     CU(cudaSetDevice(c->device));
+    if (k1_served(c, chain) && c->srv_running && (!c->srv_fast || trial_in_box(c->h_params[chain], xyz))) {
+        c->h_state[chain].energy_valid = 0; c->cache_fresh[chain] = 0;
+        return k1_server_call(c, K1_CMD_APPLY, index, xyz, nullptr);
+    }
+    QUIESCE(c);
     rc = write_slot(c, chain, index, xyz); if (rc) return rc;
     rc = push_state(c, chain); if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));
@@ -666,6 +815,13 @@ int mcpm_append(mcpm_ctx* c, int chain, const double xyz[3]) {
     const int n = c->h_state[chain].st.n;
     if (n >= c->cap) return fail(MCPM_ERR_CAPACITY, "chain %d is full (%d)", chain, c->cap);
     CU(cudaSetDevice(c->device));
+    if (k1_served(c, chain) && c->srv_running && (!c->srv_fast || trial_in_box(c->h_params[chain], xyz))) {
+        c->h_state[chain].energy_valid = 0; c->cache_fresh[chain] = 0;
+        rc = k1_server_call(c, K1_CMD_APPEND, -1, xyz, nullptr); if (rc) return rc;
+        c->h_state[chain].st.n = n + 1;
+        return MCPM_OK;
+    }
+    QUIESCE(c);
     rc = write_slot(c, chain, n, xyz); if (rc) return rc;
     c->h_state[chain].st.n = n + 1;
     rc = push_state(c, chain); if (rc) return rc;
@@ -677,6 +833,13 @@ int mcpm_remove_swap_last(mcpm_ctx* c, int chain, int index) {
     const int n = c->h_state[chain].st.n;
     if (index < 0 || index >= n) return fail(MCPM_ERR_ARG, "bad index %d (n=%d)", index, n);
     CU(cudaSetDevice(c->device));
+    if (k1_served(c, chain) && c->srv_running) {
+        c->h_state[chain].energy_valid = 0; c->cache_fresh[chain] = 0;
+        rc = k1_server_call(c, K1_CMD_REMOVE, index, nullptr, nullptr); if (rc) return rc;
+        c->h_state[chain].st.n = n - 1;
+        return MCPM_OK;
+    }
+    QUIESCE(c);
     const size_t off = (size_t)chain * c->cap;
     if (index != n - 1) {
         CU(cudaMemcpyAsync(c->d_x + off + index, c->d_x + off + n - 1, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
@@ -778,6 +941,7 @@ static size_t pool_layout(const mcpm_ctx* c, const std::vector<int>& chains, boo
 #endif  // MCPM_EXPERIMENTS
 
 int mcpm_run(mcpm_ctx* c, const mcpm_run_params* p, mcpm_chain_stats* stats) {
+    QUIESCE(c);
     if (!c || !p) return fail(MCPM_ERR_ARG, "null argument");
     if (p->n_sets < 0 || p->steps_per_set < 0 || p->steps_per_set > 2000000000LL) return fail(MCPM_ERR_ARG, "set count must be >= 0 and steps_per_set in [0, 2e9]");
     if (p->rng_mode != MCPM_RNG_PHILOX && p->rng_mode != MCPM_RNG_REPLAY) return fail(MCPM_ERR_ARG, "bad rng_mode %d", p->rng_mode);
@@ -1121,6 +1285,7 @@ int mcpm_get_stats(mcpm_ctx* c, mcpm_chain_stats* stats) {
 }
 
 int mcpm_reset_accumulators(mcpm_ctx* c) {
+    QUIESCE(c);
     if (!c) return fail(MCPM_ERR_ARG, "null context");
     CU(cudaSetDevice(c->device));
     for (int k = 0; k < c->n_chains; k++) {
@@ -1136,6 +1301,7 @@ int mcpm_reset_accumulators(mcpm_ctx* c) {
 }
 
 int mcpm_get_rdf(mcpm_ctx* c, int chain, double* hist) {
+    QUIESCE(c);
     int rc = check_chain(c, chain); if (rc) return rc;
     if (!hist) return fail(MCPM_ERR_ARG, "null hist");
     CU(cudaSetDevice(c->device));
@@ -1163,6 +1329,7 @@ int mcpm_chemical_potential(mcpm_ctx* c, int chain, double* mu_ex, double* mu) {
 }
 
 int mcpm_set_running_energy(mcpm_ctx* c, const double* pair, const double* wall) {
+    QUIESCE(c);
     if (!c || !pair || !wall) return fail(MCPM_ERR_ARG, "null argument");
     CU(cudaSetDevice(c->device));
     for (int k = 0; k < c->n_chains; k++) {
@@ -1215,6 +1382,7 @@ int mcpm_use_energy_cache(mcpm_ctx* c, int enable) {
 }
 
 int mcpm_get_energy_cache(mcpm_ctx* c, int chain, double* pair, int* valid) {
+    QUIESCE(c);
     int rc = check_chain(c, chain); if (rc) return rc;
     if (!pair || !valid) return fail(MCPM_ERR_ARG, "null argument");
     const ChainState& S = c->h_state[chain];
@@ -1236,6 +1404,7 @@ int mcpm_use_cell_list(mcpm_ctx* c, int enable) {
 }
 
 int mcpm_set_stream_ids(mcpm_ctx* c, const unsigned int* ids) {
+    QUIESCE(c);
     if (!c || !ids) return fail(MCPM_ERR_ARG, "null argument");
     CU(cudaSetDevice(c->device));
     for (int k = 0; k < c->n_chains; k++) c->h_state[k].stream_id = ids[k];
@@ -1245,6 +1414,7 @@ int mcpm_set_stream_ids(mcpm_ctx* c, const unsigned int* ids) {
 }
 
 int mcpm_set_dr(mcpm_ctx* c, int chain, double dr) {
+    QUIESCE(c);
     int rc = check_chain(c, chain); if (rc) return rc;
     CU(cudaSetDevice(c->device));
     c->h_state[chain].st.dr = dr;
@@ -1253,6 +1423,7 @@ int mcpm_set_dr(mcpm_ctx* c, int chain, double dr) {
     return MCPM_OK;
 }
 int mcpm_set_step_counter(mcpm_ctx* c, int chain, unsigned long long step) {
+    QUIESCE(c);
     int rc = check_chain(c, chain); if (rc) return rc;
     CU(cudaSetDevice(c->device));
     c->h_state[chain].st.steps_done = step;
@@ -1322,6 +1493,7 @@ int mcpm_fp64_peak(int device, double* tflops, double* ms_out) {
 }
 
 int mcpm_metropolis_probe(mcpm_ctx* c, int kind, int count, const double* u, const double* x, const int* n, double zzV, int* out) {
+    QUIESCE(c);
     if (!c || !u || !x || !out || count <= 0 || kind < 0 || kind > 2 || (kind > 0 && !n)) return fail(MCPM_ERR_ARG, "bad argument");
     CU(cudaSetDevice(c->device));
     double *du = nullptr, *dx = nullptr; int *dn = nullptr, *dout = nullptr;
@@ -1340,6 +1512,7 @@ int mcpm_metropolis_probe(mcpm_ctx* c, int kind, int count, const double* u, con
 }
 
 int mcpm_philox_uniforms(mcpm_ctx* c, unsigned long long seed, unsigned int chain, unsigned long long first_step, int n_steps, double* out) {
+    QUIESCE(c);
     if (!c || !out || n_steps <= 0) return fail(MCPM_ERR_ARG, "bad argument");
     CU(cudaSetDevice(c->device));
     double* d = nullptr;

@@ -176,6 +176,151 @@ cudaError_t launch_k1(bool fast, int n, int count, const ChainParams* params, co
     return cudaGetLastError();
 }
 
+
+// ================================================================================================
+// K1r — k1_server: K1 as a RESIDENT service for one chain (what north_star asks of K1, taken one step further: the chain's SoA fp64
+// positions are staged into shared memory ONCE and stay there across calls).  One CTA of 256 threads; thread 0 polls the mailbox
+// (system-scope acquire load of mapped host memory), the request is broadcast through shared memory, every thread scans its partners
+// j == t (mod 256) for the stored AND the trial position, warp-shuffle butterflies + one shared-memory stage reduce the two sums, and
+// thread 0 writes the record and then the sequence number straight into mapped host memory (system-scope release).  Accepted moves of
+// the host's loop (mcpm_apply_move / mcpm_append / mcpm_remove_swap_last) arrive through the same mailbox and are written through to
+// global memory, so every other kernel keeps seeing the current configuration.  The kernel leaves on STOP or after `idle` cycles
+// without a request (it can never outlive its caller by more than that); the host restarts it lazily.
+// Chains too large for one SM's shared memory are served from global memory (L2).
+// ================================================================================================
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+template <bool FAST, bool PBZ, bool STAGED>
+__global__ void __launch_bounds__(K1_THREADS) k1_server(const ChainParams* __restrict__ params, const ChainState* __restrict__ states,
+                                                        double* X, double* Y, double* Z, int chain, int cap, K1Mail* mail, K1Reply* reply,
+                                                        unsigned long long seq0, long long idle) {
+    extern __shared__ double srv_pos[];                   // STAGED: x[cap] | y[cap] | z[cap]
+    __shared__ ChainParams P;
+    __shared__ int cmd, rq_index, rq_has_trial;
+    __shared__ double rq_t[3];
+    __shared__ double red[K1_THREADS / 32][2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t off = (size_t)chain * (size_t)cap;
+    double* gx = X + off; double* gy = Y + off; double* gz = Z + off;
+    double* xs = STAGED ? srv_pos : gx;
+    double* ys = STAGED ? srv_pos + cap : gy;
+    double* zs = STAGED ? srv_pos + 2 * cap : gz;
+    if (tid == 0) P = params[chain];
+    if (STAGED) for (int j = tid; j < cap; j += K1_THREADS) { xs[j] = gx[j]; ys[j] = gy[j]; zs[j] = gz[j]; }   // every slot: stale ones are observable (Q12)
+    int n = states[chain].st.n;
+    __syncthreads();
+    const PairGeom g = make_geom<FAST>(P);
+    unsigned long long expected = seq0 + 1ull;
+    for (;;) {
+        if (warp == 0) {
+            // poll: the 8 words of the mailbox line in ONE warp-wide load (lanes 8..31 repeat the addresses of lanes 0..7)
+            const volatile unsigned long long* line = reinterpret_cast<const volatile unsigned long long*>(mail);
+            const long long t0 = clock64();
+            int c = 0;
+            for (;;) {
+                const unsigned long long v = line[lane & 7];
+                const unsigned long long head = __shfl_sync(MCPM_FULL_MASK, v, 0), tail = __shfl_sync(MCPM_FULL_MASK, v, 7);
+                if (head == expected && tail == expected) {
+                    const unsigned long long what = __shfl_sync(MCPM_FULL_MASK, v, 1);
+                    const unsigned long long t0b = __shfl_sync(MCPM_FULL_MASK, v, 2), t1b = __shfl_sync(MCPM_FULL_MASK, v, 3), t2b = __shfl_sync(MCPM_FULL_MASK, v, 4);
+                    c = (int)(what & 0xffull);
+                    if (lane == 0) {
+                        rq_has_trial = (int)((what >> 8) & 1ull); rq_index = (int)(unsigned)(what >> 32);
+                        rq_t[0] = __longlong_as_double((long long)t0b); rq_t[1] = __longlong_as_double((long long)t1b); rq_t[2] = __longlong_as_double((long long)t2b);
+                    }
+                    break;
+                }
+                if (__shfl_sync(MCPM_FULL_MASK, clock64() - t0, 0) > idle) break;   // c == 0: nobody has asked for a while
+            }
+            if (lane == 0) cmd = c;
+        }
+        __syncthreads();
+        const int c = cmd;
+        if (c == 0 || c == K1_CMD_STOP) {
+            if (tid == 0) {
+                ((volatile K1Reply*)reply)->alive = 0ull;
+                __threadfence_system();
+                if (c == K1_CMD_STOP) { st_release_sys(&reply->seq_tail, expected); st_release_sys(&reply->seq, expected); }
+            }
+            return;
+        }
+        const int index = rq_index;
+        if (c == K1_CMD_ENERGY) {
+            double ax = 0., ay = 0., az = 0., bx = rq_t[0], by = rq_t[1], bz = rq_t[2];
+            if (index >= 0) { ax = xs[index]; ay = ys[index]; az = zs[index]; }
+            if (!rq_has_trial) { bx = ax; by = ay; bz = az; }
+            if (index < 0) { ax = bx; ay = by; az = bz; }
+            double sa = 0.0, sb = 0.0;
+            pair_sum2<FAST, PBZ>(xs, ys, zs, n, index, g, ax, ay, az, bx, by, bz, tid, K1_THREADS, sa, sb);
+            sa = warp_allsum(sa); sb = warp_allsum(sb);
+            if (lane == 0) { red[warp][0] = sa; red[warp][1] = sb; }
+            __syncthreads();
+            if (warp == 0) {
+                double wa, wb;
+                wall_pair<FAST>(P, ax, ay, az, bx, by, bz, wa, wb, lane);
+                double ta = 0.0, tb = 0.0;
+                for (int w = 0; w < K1_THREADS / 32; w++) { ta += red[w][0]; tb += red[w][1]; }
+                double pa = P.eps4 * ta, pb = P.eps4 * tb;
+                if (index < 0) { pa = 0.0; wa = 0.0; }
+                // the sequence number, the six numbers and the sequence number again leave in ONE warp-wide store of the 64-byte line
+                const double mine = lane == 1 ? pa : lane == 2 ? wa : lane == 3 ? pa + wa : lane == 4 ? pb : lane == 5 ? wb : pb + wb;
+                const unsigned long long word = (lane == 0 || lane == 7) ? expected : (unsigned long long)__double_as_longlong(mine);
+                if (lane < 8) reinterpret_cast<volatile unsigned long long*>(reply)[lane] = word;
+            }
+        } else {
+            // state changes of the host's move loop, written through to global memory
+            if (tid == 0) {
+                if (c == K1_CMD_APPLY || c == K1_CMD_APPEND) {
+                    const int slot = (c == K1_CMD_APPEND) ? n : index;
+                    xs[slot] = rq_t[0]; ys[slot] = rq_t[1]; zs[slot] = rq_t[2];
+                    if (STAGED) { gx[slot] = rq_t[0]; gy[slot] = rq_t[1]; gz[slot] = rq_t[2]; }
+                } else if (c == K1_CMD_REMOVE && index != n - 1) {   // swap-with-last, src/moves.cpp:329
+                    const double lx = xs[n - 1], ly = ys[n - 1], lz = zs[n - 1];
+                    xs[index] = lx; ys[index] = ly; zs[index] = lz;
+                    if (STAGED) { gx[index] = lx; gy[index] = ly; gz[index] = lz; }
+                }
+                __threadfence_system();
+                st_release_sys(&reply->seq_tail, expected);
+                st_release_sys(&reply->seq, expected);
+            }
+            if (c == K1_CMD_APPEND) n++;
+            if (c == K1_CMD_REMOVE) n--;
+        }
+        __syncthreads();                                     // the request buffer and `red` are free again; slot writes are visible
+        expected++;
+    }
+}
+
+size_t k1_server_smem_bytes(int cap, int max_smem_optin) {
+    const size_t need = (size_t)3 * cap * sizeof(double);
+    return need + 4096 <= (size_t)max_smem_optin ? need : 0;   // 0: serve from global memory
+}
+
+cudaError_t launch_k1_server(bool fast, bool pbz, const ChainParams* params, const ChainState* states, double* X, double* Y, double* Z, int chain,
+                             int cap, size_t smem, K1Mail* mail, K1Reply* reply, unsigned long long seq0, long long idle_cycles, cudaStream_t stream) {
+    auto go = [&](auto kern) -> cudaError_t {
+        if (smem) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<1, K1_THREADS, smem, stream>>>(params, states, X, Y, Z, chain, cap, mail, reply, seq0, idle_cycles);
+        return cudaGetLastError();
+    };
+    if (smem) {
+        if (!fast) return go(k1_server<false, false, true>);
+        return pbz ? go(k1_server<true, true, true>) : go(k1_server<true, false, true>);
+    }
+    if (!fast) return go(k1_server<false, false, false>);
+    return pbz ? go(k1_server<true, true, false>) : go(k1_server<true, false, false>);
+}
+
 int k1_slices(int n) { return std::max(1, (n + K1_TILE - 1) / K1_TILE); }
 
 }  // namespace mcpm

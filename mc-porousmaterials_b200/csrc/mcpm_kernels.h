@@ -24,6 +24,10 @@ cudaError_t launch_k1(bool fast, int n, int count, const ChainParams* params, co
                       unsigned int* counters, double* out, double* host_out, unsigned long long* host_flag, unsigned long long seq,
                       unsigned int* done_groups, cudaStream_t stream);
 int k1_slices(int n);
+// resident K1: one persistent CTA serving one chain through a mailbox in mapped host memory
+size_t k1_server_smem_bytes(int cap, int max_smem_optin);
+cudaError_t launch_k1_server(bool fast, bool pbz, const ChainParams* params, const ChainState* states, double* X, double* Y, double* Z, int chain,
+                             int cap, size_t smem, K1Mail* mail, K1Reply* reply, unsigned long long seq0, long long idle_cycles, cudaStream_t stream);
 
 cudaError_t launch_k3(int tiles, int n_chains, int chain0, const ChainParams* params, ChainState* states, const double* X, const double* Y,
                       const double* Z, int cap, double* per_pair, double* per_wall, double* scratch, unsigned int* counters, double* out,

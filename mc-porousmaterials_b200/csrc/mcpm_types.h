@@ -74,6 +74,24 @@ struct K1Request {
 };
 #define MCPM_K1_MAX_BATCH 1024   // requests per launch
 
+// Resident K1 (k1_server in mcpm_k1.cu): a one-CTA persistent kernel that keeps ONE chain's positions staged in shared memory and is
+// driven through a mailbox in mapped pinned host memory — no kernel launch per MC::EnergyOfParticle call.  The host fills the
+// payload and then publishes `seq`; the kernel answers in K1Reply (records first, then `seq`).
+enum { K1_CMD_ENERGY = 1, K1_CMD_APPLY = 2, K1_CMD_APPEND = 3, K1_CMD_REMOVE = 4, K1_CMD_STOP = 5 };
+struct __align__(64) K1Mail {   // ONE 64-byte line: the kernel's warp 0 fetches it with a single coalesced read per poll (one PCIe round trip)
+    unsigned long long seq;      // written last by the host (release); the kernel waits for its next expected value
+    unsigned long long what;     // cmd | has_trial << 8 | (unsigned)index << 32
+    double t[3];
+    unsigned long long pad[2];
+    unsigned long long seq_tail; // == seq: both ends of the line must agree before the payload is believed
+};
+struct __align__(64) K1Reply {  // ONE 64-byte line written by ONE warp-wide store; each 32-byte sector carries its own copy of the sequence
+    unsigned long long seq;      // number, so the host believes the numbers only when both copies have arrived
+    double r[6];                 // {pair, wall, E} of the stored particle, then of the trial position (the many-body terms are 0)
+    unsigned long long seq_tail;
+    unsigned long long alive;    // (next line) 1 while the kernel serves; 0 once it has decided to exit (idle time-out or STOP) — it takes no request after that
+};
+
 // k2_pool (mcpm_kernels.cu): one persistent CTA per SM whose warps each own a shared-memory SLOT and take chains from per-class
 // work queues.  Slots come in up to three capacity classes (largest first) so that small chains do not reserve the shared memory of
 // the largest state point; a slot of class k serves the queues of classes >= k.

@@ -140,6 +140,15 @@ class Engine:
         assert len(ids) == self.n_chains
         check(self.L.mcpm_set_stream_ids(self.h, ids.ctypes.data_as(C.POINTER(C.c_uint))))
 
+    def k1_resident(self, chain, enable=True):
+        """Serve mcpm_particle_energy / apply_move / append / remove_swap_last of `chain` from a persistent kernel (mcpm_k1_resident)."""
+        check(self.L.mcpm_k1_resident(self.h, chain, 1 if enable else 0))
+
+    def k1_resident_stats(self):
+        a, b = C.c_ulonglong(0), C.c_ulonglong(0)
+        check(self.L.mcpm_k1_resident_stats(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def link_boxes(self, box0, box1):
         """Chains box0 / box1 become the two boxes of one Gibbs-ensemble system (mcpm_link_boxes)."""
         check(self.L.mcpm_link_boxes(self.h, box0, box1))

@@ -86,6 +86,8 @@ void MC::EnergyOfParticle(int ithBox, int ithSpecies, int index) {
         d.dr = sim.dr(ithBox);
         OK(mcpm_create(0, 1, g.capacity, &g.ctx));
         OK(mcpm_set_system(g.ctx, 0, &d));
+        // the mode a host-driven move loop runs in: K1 as a resident service (no launch per call); MCREF_BOUND_LAUNCH=1 keeps one launch per call
+        if (!getenv("MCREF_BOUND_LAUNCH")) OK(mcpm_k1_resident(g.ctx, 0, 1));
     }
     // ---- reconcile the device copy with what the reference's moves did since the last call ----
     const int n = fl.nParts;

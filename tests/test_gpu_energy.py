@@ -218,3 +218,74 @@ def test_k1_batch_matches_oracle_and_single_calls(mcpm, n, outside):
         cur3, _ = e.particle_energy_batch(0, big.astype(np.int32))
         assert np.array_equal(cur3[:n][: min(n, 50)], cur3[n:2 * n][: min(n, 50)]) if 2 * n <= 2500 else True
         assert close(cur3[0], o.particle_energy(0))
+
+
+@pytest.mark.parametrize("n,outside,cap", [(1, False, 64), (333, False, 512), (2600, False, 4096), (9000, False, 12000), (700, True, 1024)])
+def test_k1_resident_service_matches_oracle_and_launches(mcpm, n, outside, cap):
+    """mcpm_k1_resident: the persistent one-CTA kernel (positions staged once in shared memory — or served from global memory when the
+    capacity does not fit one SM: cap = 12000 — requests through a mailbox in mapped host memory) gives what the per-call launches and the
+    oracle give, follows a host-driven move loop (apply_move / append / remove_swap_last through the same mailbox, written through to
+    global memory), survives its idle time-out, and steps aside for every other entry point."""
+    import time
+    s = O.methane_slit(rcut=40.0, n_equil_sets=0)
+    rng = np.random.default_rng(100 + n)
+    x, y, z = rng.random(n) * 80.0, rng.random(n) * 80.0, 3.0 + rng.random(n) * 14.0
+    if outside:
+        x += 80.0 * rng.integers(-2, 3, size=n)
+    o = O.COracle(s, cap)
+    o.set_positions(x, y, z)
+    m = 25
+    idx = rng.integers(-1, n, size=m)
+    trial = np.column_stack([rng.random(m) * 80.0 + (160.0 if outside else 0.0), rng.random(m) * 80.0, 2.0 + rng.random(m) * 16.0])
+    with mcpm.Engine(1, cap) as e:
+        e.set_system(s)
+        e.set_positions(0, x, y, z)
+        launched = [e.particle_energy(0, int(i), t) for i, t in zip(idx, trial)]
+        l0 = e.launch_count()
+        e.k1_resident(0, True)
+        for r in range(m):
+            i = int(idx[r])
+            cur, moved = e.particle_energy(0, i, trial[r])
+            assert close(moved, launched[r][1], 1e-11) and (i < 0 or close(cur, launched[r][0], 1e-11))
+            assert close(moved, o.moved_energy(i, *trial[r]) if i >= 0 else o.trial_energy(*trial[r]))
+        assert e.launch_count() == l0 + 1 and e.k1_resident_stats() == (1, m)            # ONE launch for all the calls
+        # a host-driven move loop: accepted translations, insertions and deletions mirrored through the mailbox
+        px, py, pz = x.copy(), y.copy(), z.copy()
+        for k in range(30):
+            kind = k % 3 if len(px) > 1 else 1
+            if kind == 0:
+                i = int(rng.integers(0, len(px))); t = np.array([rng.random() * 80.0, rng.random() * 80.0, 3.0 + rng.random() * 14.0])
+                e.apply_move(0, i, t); px[i], py[i], pz[i] = t
+            elif kind == 1:
+                t = np.array([rng.random() * 80.0, rng.random() * 80.0, 3.0 + rng.random() * 14.0])
+                e.append(0, t); px = np.append(px, t[0]); py = np.append(py, t[1]); pz = np.append(pz, t[2])
+            else:
+                i = int(rng.integers(0, len(px)))
+                e.remove_swap_last(0, i)
+                px[i], py[i], pz[i] = px[-1], py[-1], pz[-1]; px, py, pz = px[:-1], py[:-1], pz[:-1]
+            o.set_positions(px, py, pz)
+            j = int(rng.integers(0, len(px))); t = np.array([rng.random() * 80.0, rng.random() * 80.0, 2.0 + rng.random() * 16.0])
+            cur, moved = e.particle_energy(0, j, t)
+            assert close(cur, o.particle_energy(j)) and close(moved, o.moved_energy(j, *t)), k
+        if outside:
+            assert e.k1_resident_stats()[0] == 1                                          # the general service took everything
+        time.sleep(0.05)                                                                  # longer than the idle time-out: the kernel has left
+        starts = e.k1_resident_stats()[0]
+        cur, _ = e.particle_energy(0, 0)
+        assert close(cur, o.particle_energy(0)) and e.k1_resident_stats()[0] == starts + 1     # restarted on demand
+        # other entry points see the current configuration (write-through) and quiesce the service
+        gx, gy, gz = e.get_positions(0)
+        assert np.array_equal(gx, px) and np.array_equal(gy, py) and np.array_equal(gz, pz)
+        box, pp, pw = e.box_energy(0)
+        ob, opp, opw = o.box_energy()
+        assert close(box, ob) and close(pp, opp)
+        cur, _ = e.particle_energy(0, 0)                                                  # and the service comes back afterwards
+        assert close(cur, o.particle_energy(0))
+        if not outside and n > 1:
+            # a trial position outside the box cannot go to a service built on the fast minimum image: that request is launched instead
+            far = np.array([250.0, 40.0, 10.0])
+            cur, moved = e.particle_energy(0, 0, far)
+            assert close(moved, o.moved_energy(0, *far))
+        st = e.run(1, 1, 200, seed=3, check_energy=1)                                     # K2 on the same context
+        assert st[0].energy == pytest.approx(st[0].energy_check, rel=1e-9)
+        e.k1_resident(0, False)
