@@ -156,3 +156,43 @@ def test_link_rules(mcpm, gibbs):
         with pytest.raises(mcpm.McpmError) as ei:
             e.run(1, 1, 10, seed=1)                              # chain 2 is a single box: not in the same context
         assert ei.value.code == 4
+
+
+@pytest.mark.parametrize("pore", ["sphere", "cylinder"])
+def test_pore_geometries_exchange_with_a_bulk_box(mcpm, pore):
+    """Box 0 a spherical cavity (SphericalLJ_Pot, no periodic axis) or a cylindrical pore (CylindricalLJ10_4, periodic along x), box 1 a bulk
+    reservoir: transfers insert through InsertParticle's sphere / cylinder branch of the receiving box.  Device Philox vs the C oracle on the
+    same stream (the oracle's single-box restatement of these geometries is pinned to the compiled reference in tests/test_oracle_f4.py)."""
+    kw = dict(n_layers=1, n_disp=3, n_vol=0, n_swap=1, n_equil_sets=1, pair_kind=0, temperature=87.0, eps_ff=119.8, sig_ff=3.405, rcut=12.0,
+              molar_mass=39.948, mu=0.0, eps_sf=57.92, sig_sf=3.4025, rho_s=0.382, delta=0.0, pressure=-1.0, dv=1e-3)
+    if pore == "sphere":
+        a = O.make_system(geometry=3, wall_kind=2, width=(30.0, 30.0, 30.0), dr=2.0, **kw)
+    else:
+        a = O.make_system(geometry=2, wall_kind=3, width=(24.0, 26.0, 26.0), dr=2.0, **kw)
+    b = O.make_system(geometry=0, wall_kind=0, width=(40.0, 40.0, 40.0), dr=8.0, **{**kw, "eps_sf": 0.0, "sig_sf": 0.0, "rho_s": 0.0})
+    rng = np.random.default_rng(17)
+    # a loose start inside the pore (within 7 A of the axis / centre) and a dilute reservoir
+    pa = np.array(a.width)[:, None] * 0.5 + (rng.random((3, 40)) - 0.5) * 9.0
+    if pore == "cylinder":
+        pa[0] = rng.random(40) * 24.0
+    pb = rng.random((3, 120)) * 40.0
+    oa, ob = O.COracle(a, 1024), O.COracle(b, 1024)
+    oa.link(ob)
+    oa.set_positions(*pa); ob.set_positions(*pb); oa.box_energy(); ob.box_energy()
+    oa.philox(77, 0, 0)
+    otr = oa.gibbs_run_sets(1, 2, 2500, 0, True)
+    with mcpm.Engine(2, 1024) as e:
+        e.set_system(a, 0); e.set_system(b, 1)
+        e.set_positions(0, *pa); e.set_positions(1, *pb)
+        e.link_boxes(0, 1)
+        stats, tr = e.run(1, 2, 2500, seed=77, trace=True, check_energy=1)
+        d = np.nonzero(tr[0] != otr)[0]
+        assert len(d) == 0, f"first divergence at step {d[0]}: {tr[0][d[0]]} vs {otr[d[0]]}"
+        assert ((tr[0] >> 1) & 7 == 5).sum() > 500 and (tr[0] & 0x1F == ((5 << 1) | 1)).sum() > 5      # transfers INTO the pore were accepted
+        for ib, o in ((0, oa), (1, ob)):
+            so, st = o.state(), stats[ib]
+            assert (st.n, st.acceptance, st.n_displacements) == (so["n"], so["acceptance"], so["n_displacements"]) and st.dr == so["dr"]
+            assert st.energy == pytest.approx(st.energy_check, rel=1e-9, abs=1e-6) and st.energy == pytest.approx(so["exact_energy"], rel=1e-9, abs=1e-6)
+            gx, gy, gz = e.get_positions(ib)
+            ox, oy, oz = o.get_positions()
+            assert np.allclose(gx, ox, rtol=1e-13, atol=1e-12) and np.allclose(gy, oy, rtol=1e-13, atol=1e-12) and np.allclose(gz, oz, rtol=1e-13, atol=1e-12)
