@@ -450,9 +450,12 @@ def k3_k1_records(m, torch, local):
                 for i in range(200):
                     e.particle_energy(0, int(idx[i]), trial[i])
                 dtr = time.perf_counter() - t0
+                native_resident = e.k1_latency(0, 2000, trial[0])
                 e.k1_resident(0, False)
+                native_launch = e.k1_latency(0, 500, trial[0])
                 out["k1"].append({"case": name, "n": n, "us_per_call_through_abi": 1e6 * dt / 200, "us_device_per_call": 1e3 * dev_ms / 200,
                                   "us_per_call_resident_service": 1e6 * dtr / 200,
+                                  "us_per_call_native_caller": {"launch_per_call": native_launch, "resident_service": native_resident},
                                   "us_per_request_in_a_batch_of_200": 1e6 * dtb / 200, "pair_evals_per_call": 2 * n,
                                   "what": "mcpm_particle_energy: stored + displaced position in one launch (positions staged by TMA bulk copies, "
                                           "results through mapped host memory); ctypes call overhead included"})

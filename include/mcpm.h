@@ -176,6 +176,9 @@ int mcpm_particle_energy(mcpm_ctx* ctx, int chain, int index, const double* tria
  * This is the mode a host-driven move loop runs in.  enable = 0 disarms. */
 int mcpm_k1_resident(mcpm_ctx* ctx, int chain, int enable);
 int mcpm_k1_resident_stats(const mcpm_ctx* ctx, unsigned long long* starts, unsigned long long* requests);
+/* Measurement support: wall-clock microseconds per mcpm_particle_energy call for a native caller (`reps` calls, stored particle r mod n
+ * displaced to `trial`), in whatever mode the chain is in. */
+int mcpm_k1_latency(mcpm_ctx* ctx, int chain, int reps, const double* trial /* 3 or NULL */, double* us_per_call);
 /* The same for `count` requests against the chain's PRESENT configuration in one launch (a host loop that speculates on several
  * trial moves, Widom ghost batches, ...): index[count]; trial = NULL or [count][3]; cur / moved = NULL or [count].  The launch
  * latency that bounds a single call is paid once per batch. */

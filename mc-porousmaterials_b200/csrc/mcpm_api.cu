@@ -1,6 +1,7 @@
 // C-ABI implementation (include/mcpm.h): context, state transfer, launches.  No torch types, no CPU
 // fallback: every compute entry point needs a CUDA device and fails with MCPM_ERR_CUDA otherwise.
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -1458,6 +1459,21 @@ int mcpm_timer_stop(mcpm_ctx* c, float* ms) {
     CU(cudaEventRecord(c->tm1, c->stream));
     CU(cudaEventSynchronize(c->tm1));
     CU(cudaEventElapsedTime(ms, c->tm0, c->tm1));
+    return MCPM_OK;
+}
+
+// Host-side latency of mcpm_particle_energy as a native caller sees it (no interpreter in the loop): `reps` calls on stored particles
+// 0, 1, 2, ... displaced to `trial`, wall-clock microseconds per call.  Uses whatever mode the chain is in (launch per call or resident).
+int mcpm_k1_latency(mcpm_ctx* c, int chain, int reps, const double* trial, double* us_per_call) {
+    int rc = check_chain(c, chain); if (rc) return rc;
+    if (reps <= 0 || !us_per_call) return fail(MCPM_ERR_ARG, "bad arguments");
+    const int n = std::max(1, c->h_state[chain].st.n);
+    mcpm_particle_energy_t cur, moved;
+    for (int r = 0; r < 16; r++) { rc = mcpm_particle_energy(c, chain, r % n, trial, &cur, &moved); if (rc) return rc; }
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int r = 0; r < reps; r++) { rc = mcpm_particle_energy(c, chain, r % n, trial, &cur, &moved); if (rc) return rc; }
+    const auto t1 = std::chrono::steady_clock::now();
+    *us_per_call = std::chrono::duration<double, std::micro>(t1 - t0).count() / reps;
     return MCPM_OK;
 }
 

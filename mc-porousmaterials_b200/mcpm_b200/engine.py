@@ -144,6 +144,13 @@ class Engine:
         """Serve mcpm_particle_energy / apply_move / append / remove_swap_last of `chain` from a persistent kernel (mcpm_k1_resident)."""
         check(self.L.mcpm_k1_resident(self.h, chain, 1 if enable else 0))
 
+    def k1_latency(self, chain, reps, trial=None):
+        """Microseconds per mcpm_particle_energy call measured inside the library (no interpreter in the loop)."""
+        us = C.c_double(0.0)
+        t = None if trial is None else np.ascontiguousarray(trial, dtype=np.float64)
+        check(self.L.mcpm_k1_latency(self.h, chain, reps, None if t is None else _p(t), C.byref(us)))
+        return us.value
+
     def k1_resident_stats(self):
         a, b = C.c_ulonglong(0), C.c_ulonglong(0)
         check(self.L.mcpm_k1_resident_stats(self.h, C.byref(a), C.byref(b)))
