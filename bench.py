@@ -462,6 +462,41 @@ def k3_k1_records(m, torch, local):
     return out
 
 
+def gibbs_record(m):
+    """Row f4: two linked boxes exchanging particles (the Gibbs ensemble at fixed volumes, k2_gibbs), 148 systems = 296 chains from the
+    liquid + vapour start of tests/golden/reference_gibbs.npz; one step = 2500 trial moves (translations in either box + transfers) per system."""
+    import json
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_gibbs.npz"))
+    meta = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_gibbs.json")))["vle"]
+    pairs, sps = 148, 2500
+    with m.Engine(2 * pairs, 1024) as e:
+        for k in range(pairs):
+            for b in (0, 1):
+                d = m.SystemDesc()
+                for key, val in meta[f"box{b}"].items():
+                    if key == "width":
+                        for a in range(3):
+                            d.width[a] = val[a]
+                    else:
+                        setattr(d, key, val)
+                e.set_system(d, 2 * k + b)
+                e.set_positions(2 * k + b, g[f"vle_x{b}"], g[f"vle_y{b}"], g[f"vle_z{b}"])
+            e.link_boxes(2 * k, 2 * k + 1)
+        ids = np.arange(2 * pairs, dtype=np.uint32)
+        e.set_stream_ids(ids)
+        e.run(1, 1, sps, seed=99)
+        ms = []
+        for it in range(3):
+            e.run(2 + it, 1, sps, seed=99)
+            ms.append(e.last_kernel_ms())
+        st = e.stats()
+        t = float(np.mean(ms)) * 1e-3
+        return {"what": "two linked boxes per system (Gibbs ensemble at fixed volumes: translations in either box + particle transfers), LJ argon liquid + vapour boxes, "
+                        "148 systems = 296 chains, 2500 trial moves per system per step", "systems": pairs, "mean_particles_box0": float(np.mean([st[2 * k].n for k in range(pairs)])),
+                "mean_particles_box1": float(np.mean([st[2 * k + 1].n for k in range(pairs)])), "value": pairs * sps / t, "unit": UNIT, "kernel": e.last_kernel_name(),
+                "kernel_ms": t * 1e3}
+
+
 def dbg(*a):
     if os.environ.get("BENCH_DEBUG"):
         print("[bench]", *a, file=sys.stderr, flush=True)
@@ -554,6 +589,7 @@ def gpu_arm(args, world, rank, local, dist):
                 recs[-1]["value_equilibration_sets"] = moves_only
         line["configs"] = recs
         line.update(k3_k1_records(m, torch, local))
+        line["f4_two_boxes"] = gibbs_record(m)
     if world == 1 and not args.no_cpu:
         from oracle import cpu_baseline
         pool = cpu_baseline.CpuPool()
