@@ -69,6 +69,7 @@ struct mcpm_ctx {
     cudaStream_t srv_stream = nullptr;
     K1Mail* h_mail = nullptr; K1Mail* d_mail = nullptr;
     K1Reply* h_reply = nullptr; K1Reply* d_reply = nullptr;
+    double* h_box = nullptr; double* d_box = nullptr;   // per-particle results of a BoxEnergy answered by the service: [cap] pair | [cap] wall
     int srv_chain = -1;                        // chain the service is armed for, or -1
     bool srv_running = false, srv_fast = false;
     unsigned long long srv_seq = 0;
@@ -288,6 +289,7 @@ int mcpm_destroy(mcpm_ctx* c) {
     if (c->srv_stream) { cudaStreamSynchronize(c->srv_stream); cudaStreamDestroy(c->srv_stream); }
     if (c->h_mail) cudaFreeHost(c->h_mail);
     if (c->h_reply) cudaFreeHost(c->h_reply);
+    if (c->h_box) cudaFreeHost(c->h_box);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_params); cudaFree(c->d_state); cudaFree(c->d_x); cudaFree(c->d_y); cudaFree(c->d_z);
     cudaFree(c->d_pool_next); cudaFree(c->d_pairs);
@@ -560,6 +562,8 @@ static int k1_server_start(mcpm_ctx* c) {
         memset(c->h_mail, 0, sizeof(K1Mail)); memset(c->h_reply, 0, sizeof(K1Reply));
         CU(cudaHostGetDevicePointer((void**)&c->d_mail, c->h_mail, 0));
         CU(cudaHostGetDevicePointer((void**)&c->d_reply, c->h_reply, 0));
+        CU(cudaHostAlloc(&c->h_box, sizeof(double) * 2 * (size_t)c->cap, cudaHostAllocMapped));
+        CU(cudaHostGetDevicePointer((void**)&c->d_box, c->h_box, 0));
     }
     CU(cudaStreamSynchronize(c->srv_stream));            // a previous instance that timed out has left by now
     CU(cudaMemcpyAsync(c->d_state + chain, &c->h_state[chain], sizeof(ChainState), cudaMemcpyHostToDevice, c->stream));
@@ -571,7 +575,7 @@ static int k1_server_start(mcpm_ctx* c) {
     std::atomic_thread_fence(std::memory_order_seq_cst);
     const long long idle = 10000000ll;                   // ~5 ms of SM clocks without a request
     CU(launch_k1_server(c->srv_fast, c->h_params[chain].pbc[2] != 0, c->d_params, c->d_state, c->d_x, c->d_y, c->d_z, chain, c->cap,
-                        k1_server_smem_bytes(c->cap, c->max_smem), c->d_mail, c->d_reply, c->srv_seq, idle, c->srv_stream));
+                        k1_server_smem_bytes(c->cap, c->max_smem), c->d_mail, c->d_reply, c->d_box, c->srv_seq, idle, c->srv_stream));
     c->launches++; c->srv_starts++;
     c->srv_running = true;
     return MCPM_OK;
@@ -761,9 +765,22 @@ static int box_energy_range(mcpm_ctx* c, int chain0, int count, double* per_pair
 }
 
 int mcpm_box_energy(mcpm_ctx* c, int chain, mcpm_box_energy_t* out, double* per_pair, double* per_wall) {
-    QUIESCE(c);
     int rc = check_chain(c, chain); if (rc) return rc;
     CU(cudaSetDevice(c->device));
+    if (c->srv_running && k1_served(c, chain) && c->h_state[chain].st.n > 0 && c->h_state[chain].st.n <= MCPM_K1_SERVER_BOX_MAX) {
+        // a host loop that interleaves BoxEnergy with its moves (CorrectEnergy as shipped): answered by the resident service
+        double rec[8];
+        rc = k1_server_call(c, K1_CMD_BOX, -1, nullptr, rec); if (rc) return rc;
+        const int n = c->h_state[chain].st.n;
+        mcpm_chain_stats& st = c->h_state[chain].st;
+        st.pair = st.pair_check = rec[0]; st.wall = st.wall_check = rec[2]; st.energy = st.energy_check = rec[3];
+        c->h_state[chain].energy_valid = 1;
+        if (out) { out->pair = rec[0]; out->many_body = 0.0; out->wall = rec[2]; out->energy = rec[3]; }
+        if (per_pair) for (int k = 0; k < n; k++) per_pair[k] = ((volatile double*)c->h_box)[k];
+        if (per_wall) for (int k = 0; k < n; k++) per_wall[k] = ((volatile double*)c->h_box)[c->cap + k];
+        return MCPM_OK;
+    }
+    QUIESCE(c);
     rc = box_energy_range(c, chain, 1, c->d_pp, c->d_pw); if (rc) return rc;
     if (out) { out->pair = c->h_pin[0]; out->many_body = 0.0; out->wall = c->h_pin[2]; out->energy = c->h_pin[3]; }
     const int n = c->h_state[chain].st.n;

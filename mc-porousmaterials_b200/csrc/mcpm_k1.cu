@@ -200,7 +200,7 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 template <bool FAST, bool PBZ, bool STAGED>
 __global__ void __launch_bounds__(K1_THREADS) k1_server(const ChainParams* __restrict__ params, const ChainState* __restrict__ states,
                                                         double* X, double* Y, double* Z, int chain, int cap, K1Mail* mail, K1Reply* reply,
-                                                        unsigned long long seq0, long long idle) {
+                                                        double* host_box, unsigned long long seq0, long long idle) {
     extern __shared__ double srv_pos[];                   // STAGED: x[cap] | y[cap] | z[cap]
     __shared__ ChainParams P;
     __shared__ int cmd, rq_index, rq_has_trial;
@@ -274,6 +274,38 @@ __global__ void __launch_bounds__(K1_THREADS) k1_server(const ChainParams* __res
                 const unsigned long long word = (lane == 0 || lane == 7) ? expected : (unsigned long long)__double_as_longlong(mine);
                 if (lane < 8) reinterpret_cast<volatile unsigned long long*>(reply)[lane] = word;
             }
+        } else if (c == K1_CMD_BOX) {
+            // MC::BoxEnergy (src/energy.cpp:106-124) for a host loop that asks for it every few steps (CorrectEnergy as shipped): per-particle
+            // pair and wall energies into mapped host memory (host_box: [cap] pair | [cap] wall), the box totals in the reply line
+            double tp = 0.0, tw = 0.0;
+            for (int i = tid; i < n; i += K1_THREADS) {
+                const double xi = xs[i], yi = ys[i], zi = zs[i];
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;           // four independent dependency chains per thread
+                int j = 0;
+                for (; j + 3 < n; j += 4) {
+                    pair_add<FAST>(s0, dist2<FAST, PBZ>(g, xi, yi, zi, xs[j], ys[j], zs[j]), g, j, i);
+                    pair_add<FAST>(s1, dist2<FAST, PBZ>(g, xi, yi, zi, xs[j + 1], ys[j + 1], zs[j + 1]), g, j + 1, i);
+                    pair_add<FAST>(s2, dist2<FAST, PBZ>(g, xi, yi, zi, xs[j + 2], ys[j + 2], zs[j + 2]), g, j + 2, i);
+                    pair_add<FAST>(s3, dist2<FAST, PBZ>(g, xi, yi, zi, xs[j + 3], ys[j + 3], zs[j + 3]), g, j + 3, i);
+                }
+                for (; j < n; j++) pair_add<FAST>(s0, dist2<FAST, PBZ>(g, xi, yi, zi, xs[j], ys[j], zs[j]), g, j, i);
+                const double sum = (s0 + s1) + (s2 + s3);
+                const double pe = P.eps4 * sum, we = wall_single<FAST>(P, xi, yi, zi);
+                ((volatile double*)host_box)[i] = pe; ((volatile double*)host_box)[cap + i] = we;
+                tp += pe; tw += we;
+            }
+            tp = warp_allsum(tp); tw = warp_allsum(tw);
+            if (lane == 0) { red[warp][0] = tp; red[warp][1] = tw; }
+            __threadfence_system();                              // the per-particle records are in host memory before the reply line is
+            __syncthreads();
+            if (warp == 0) {
+                double ta = 0.0, tb = 0.0;
+                for (int w = 0; w < K1_THREADS / 32; w++) { ta += red[w][0]; tb += red[w][1]; }
+                const double half = 0.5 * ta;
+                const double mine = lane == 1 ? half : lane == 2 ? tb : lane == 3 ? half + tb : 0.0;
+                const unsigned long long word = (lane == 0 || lane == 7) ? expected : (unsigned long long)__double_as_longlong(mine);
+                if (lane < 8) reinterpret_cast<volatile unsigned long long*>(reply)[lane] = word;
+            }
         } else {
             // state changes of the host's move loop, written through to global memory
             if (tid == 0) {
@@ -304,13 +336,14 @@ size_t k1_server_smem_bytes(int cap, int max_smem_optin) {
 }
 
 cudaError_t launch_k1_server(bool fast, bool pbz, const ChainParams* params, const ChainState* states, double* X, double* Y, double* Z, int chain,
-                             int cap, size_t smem, K1Mail* mail, K1Reply* reply, unsigned long long seq0, long long idle_cycles, cudaStream_t stream) {
+                             int cap, size_t smem, K1Mail* mail, K1Reply* reply, double* host_box, unsigned long long seq0, long long idle_cycles,
+                             cudaStream_t stream) {
     auto go = [&](auto kern) -> cudaError_t {
         if (smem) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
-        kern<<<1, K1_THREADS, smem, stream>>>(params, states, X, Y, Z, chain, cap, mail, reply, seq0, idle_cycles);
+        kern<<<1, K1_THREADS, smem, stream>>>(params, states, X, Y, Z, chain, cap, mail, reply, host_box, seq0, idle_cycles);
         return cudaGetLastError();
     };
     if (smem) {

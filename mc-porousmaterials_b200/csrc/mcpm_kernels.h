@@ -27,7 +27,8 @@ int k1_slices(int n);
 // resident K1: one persistent CTA serving one chain through a mailbox in mapped host memory
 size_t k1_server_smem_bytes(int cap, int max_smem_optin);
 cudaError_t launch_k1_server(bool fast, bool pbz, const ChainParams* params, const ChainState* states, double* X, double* Y, double* Z, int chain,
-                             int cap, size_t smem, K1Mail* mail, K1Reply* reply, unsigned long long seq0, long long idle_cycles, cudaStream_t stream);
+                             int cap, size_t smem, K1Mail* mail, K1Reply* reply, double* host_box, unsigned long long seq0, long long idle_cycles,
+                             cudaStream_t stream);
 
 cudaError_t launch_k3(int tiles, int n_chains, int chain0, const ChainParams* params, ChainState* states, const double* X, const double* Y,
                       const double* Z, int cap, double* per_pair, double* per_wall, double* scratch, unsigned int* counters, double* out,

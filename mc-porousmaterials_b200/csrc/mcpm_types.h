@@ -77,7 +77,8 @@ struct K1Request {
 // Resident K1 (k1_server in mcpm_k1.cu): a one-CTA persistent kernel that keeps ONE chain's positions staged in shared memory and is
 // driven through a mailbox in mapped pinned host memory — no kernel launch per MC::EnergyOfParticle call.  The host fills the
 // payload and then publishes `seq`; the kernel answers in K1Reply (records first, then `seq`).
-enum { K1_CMD_ENERGY = 1, K1_CMD_APPLY = 2, K1_CMD_APPEND = 3, K1_CMD_REMOVE = 4, K1_CMD_STOP = 5 };
+enum { K1_CMD_ENERGY = 1, K1_CMD_APPLY = 2, K1_CMD_APPEND = 3, K1_CMD_REMOVE = 4, K1_CMD_STOP = 5, K1_CMD_BOX = 6 };
+#define MCPM_K1_SERVER_BOX_MAX 1536   // MC::BoxEnergy is answered by the one-CTA service up to this many particles (beyond: K3 on the whole GPU)
 struct __align__(64) K1Mail {   // ONE 64-byte line: the kernel's warp 0 fetches it with a single coalesced read per poll (one PCIe round trip)
     unsigned long long seq;      // written last by the host (release); the kernel waits for its next expected value
     unsigned long long what;     // cmd | has_trial << 8 | (unsigned)index << 32

@@ -277,10 +277,13 @@ def test_k1_resident_service_matches_oracle_and_launches(mcpm, n, outside, cap):
         # other entry points see the current configuration (write-through) and quiesce the service
         gx, gy, gz = e.get_positions(0)
         assert np.array_equal(gx, px) and np.array_equal(gy, py) and np.array_equal(gz, pz)
-        box, pp, pw = e.box_energy(0)
+        e.particle_energy(0, 0)                                                           # (get_positions has quiesced the service: back on)
+        l1 = e.launch_count()
+        box, pp, pw = e.box_energy(0)                                                     # up to 1536 particles the service answers BoxEnergy itself
         ob, opp, opw = o.box_energy()
-        assert close(box, ob) and close(pp, opp)
-        cur, _ = e.particle_energy(0, 0)                                                  # and the service comes back afterwards
+        assert close(box, ob) and close(pp, opp) and close(pw, opw)
+        assert (e.launch_count() == l1) == (len(px) <= 1536)
+        cur, _ = e.particle_energy(0, 0)                                                  # and the service is there (or comes back) afterwards
         assert close(cur, o.particle_energy(0))
         if not outside and n > 1:
             # a trial position outside the box cannot go to a service built on the fast minimum image: that request is launched instead
