@@ -286,7 +286,10 @@ class Job:
         self.eng.close()
 
     def one_step(self):
-        st = self.eng.run(self.set_index, 1, self.S, seed=self.seed, threads=self.threads, check_energy=0, no_sampling=getattr(self, "no_sampling", 0))
+        if getattr(self, "_stats", None) is None:
+            self._stats = (self.m.ChainStats * self.eng.n_chains)()      # one record buffer for the whole job (2 MB for 5120 chains)
+        st = self.eng.run(self.set_index, 1, self.S, seed=self.seed, threads=self.threads, check_energy=0, no_sampling=getattr(self, "no_sampling", 0),
+                          stats_out=self._stats)
         self.set_index += 1
         return st
 

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -97,6 +98,7 @@ struct mcpm_ctx {
     double* h_pin = nullptr;       // pinned staging, 4*n_chains+8 doubles
     std::vector<ChainParams> h_params;
     std::vector<ChainState> h_state;
+    bool state_pinned = false;
     std::vector<mcpm_system_desc> h_desc;
     std::vector<char> has_system;
     std::vector<int> peer;           // two-box Gibbs systems (mcpm_link_boxes): the other box of the chain's system, or -1
@@ -270,6 +272,10 @@ int mcpm_create(int device, int n_chains, int capacity, mcpm_ctx** out) {
     memset(&zero, 0, sizeof(zero));
     zero.fast_image = 1;
     c->h_state.assign(n_chains, zero);
+    // the records come back after every mcpm_run (2.5 MB for 5120 chains): page-locked, the copy runs at PCIe speed instead of through the
+    // driver's bounce buffer (the vector is never resized)
+    c->state_pinned = !getenv("MCPM_NO_PIN") && cudaHostRegister(c->h_state.data(), sizeof(ChainState) * (size_t)n_chains, cudaHostRegisterDefault) == cudaSuccess;
+    if (!c->state_pinned) cudaGetLastError();
     for (int k = 0; k < n_chains; k++) c->h_state[k].stream_id = (unsigned int)k;
     c->h_desc.assign(n_chains, mcpm_system_desc());
     c->has_system.assign(n_chains, 0);
@@ -288,6 +294,7 @@ int mcpm_destroy(mcpm_ctx* c) {
     if (c->srv_running) k1_server_stop(c);
     if (c->srv_stream) { cudaStreamSynchronize(c->srv_stream); cudaStreamDestroy(c->srv_stream); }
     if (c->h_mail) cudaFreeHost(c->h_mail);
+    if (c->state_pinned) cudaHostUnregister(c->h_state.data());
     if (c->h_reply) cudaFreeHost(c->h_reply);
     if (c->h_box) cudaFreeHost(c->h_box);
     if (c->stream) cudaStreamSynchronize(c->stream);

@@ -191,8 +191,9 @@ class Engine:
         check(self.L.mcpm_remove_swap_last(self.h, chain, index))
 
     # ---- K2
-    def run(self, first_set, n_sets, steps_per_set, seed=0, replay=None, trace=False, threads=0, check_energy=0, sample_rdf=0, no_sampling=0):
-        """Advance every chain n_sets*steps_per_set trial moves.  replay: float64[n_chains, stride] or None."""
+    def run(self, first_set, n_sets, steps_per_set, seed=0, replay=None, trace=False, threads=0, check_energy=0, sample_rdf=0, no_sampling=0, stats_out=None):
+        """Advance every chain n_sets*steps_per_set trial moves.  replay: float64[n_chains, stride] or None.
+        stats_out: a (ChainStats * n_chains) array to fill instead of a fresh one (a caller in a timing loop)."""
         p = RunParams()
         p.first_set, p.n_sets, p.steps_per_set = first_set, n_sets, steps_per_set
         p.seed = seed
@@ -215,7 +216,7 @@ class Engine:
         if trace:
             tr = np.zeros((self.n_chains, n_sets * steps_per_set), dtype=np.uint8)
             p.trace = tr.ctypes.data_as(C.POINTER(C.c_ubyte))
-        stats = (ChainStats * self.n_chains)()
+        stats = stats_out if stats_out is not None else (ChainStats * self.n_chains)()
         check(self.L.mcpm_run(self.h, C.byref(p), stats))
         return (stats, tr) if trace else stats
 
