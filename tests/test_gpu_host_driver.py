@@ -253,3 +253,20 @@ def test_two_boxes_through_the_driver(tmp_path):
         got, sem = np.mean(means[box]), np.std(means[box], ddof=1) / np.sqrt(8)
         tol = max(3.0 * np.hypot(sem, ref[box]["sem_n"]), 1.5)
         assert abs(got - ref[box]["mean_n"]) < tol, (box, got, sem, ref[box]["mean_n"], ref[box]["sem_n"])
+
+
+def test_pore_and_reservoir_through_the_driver(tmp_path):
+    """Box 0 a graphite slit pore (its own wall potential, 2*rcut lateral size), box 1 a bulk gas reservoir: the pore fills from the reservoir,
+    the particle number is conserved, and each box's log carries its own width / volume / wall-energy column."""
+    stdout = run_driver(tmp_path, os.path.join(GOLDEN, "gibbs_pore.in"))
+    assert "Box 0: pore" in stdout and "\tGeometry: slit" in stdout and "Box 1: gas" in stdout and "pore-ar\n\tVdW potential: lj" in stdout
+    rows = {}
+    for box in ("pore", "gas"):
+        log = open(tmp_path / "gibbs_pore" / box / "simulation_ar.log").read().splitlines()
+        assert len(log) == 4                                                              # header + sets 2, 4, 6
+        rows[box] = [r.split("\t") for r in log[1:]]
+    for rp, rg in zip(rows["pore"], rows["gas"]):
+        assert int(rp[7]) + int(rg[7]) == 260
+        assert (rp[2], rp[3]) == ("20.0000000", "18000.0000000") and (rg[2], rg[3]) == ("60.0000000", "216000.0000000")
+        assert float(rp[5]) < -100.0 and float(rg[5]) == 0.0                              # wall energy per particle: only in the pore
+    assert int(rows["pore"][-1][7]) > 100                                                 # adsorption: the pore has filled from the gas
