@@ -913,6 +913,9 @@ static size_t k2_smem_bytes(int cap, bool multi, bool sample) { return (size_t)(
 size_t k2_smem_limit_cap(int max_smem_optin) { return ((size_t)max_smem_optin / sizeof(double) - 128 - MCPM_RDF_SMEM_DOUBLES - 64) / 3; }
 
 template <int RNG_MODE>
+#ifndef MCPM_K2_MINB
+#define MCPM_K2_MINB 8      // CTAs per SM ptxas plans for in the one-warp hot kernel: 8 -> 128 registers
+#endif
 static cudaError_t launch_k2_rng(int n_chains, int threads, bool global, bool fast, bool sample, bool cache, size_t smem,
                                  const ChainParams* params, ChainState* states, const int* order, double* X, double* Y, double* Z,
                                  const RunArgs& a, cudaStream_t stream) {
@@ -936,7 +939,7 @@ static cudaError_t launch_k2_rng(int n_chains, int threads, bool global, bool fa
     }
     if (global) return cache ? go(k2_chains<RNG_MODE, 512, 1, true, true, false, true>) : go(k2_chains<RNG_MODE, 512, 1, true, true, false, false>);
     if (cache) {
-        if (threads <= 64) return go(k2_chains<RNG_MODE, 64, 8, false, true, false, true>);
+        if (threads <= 64) return go(k2_chains<RNG_MODE, 64, MCPM_K2_MINB, false, true, false, true>);
         if (threads <= 256) return go(k2_chains<RNG_MODE, 256, 2, false, true, false, true>);
         return go(k2_chains<RNG_MODE, 512, 1, false, true, false, true>);
     }
