@@ -75,7 +75,7 @@ def build_workload(config, replicas, steps_per_set):
         w["workload"] = "C3 CH4 in slit, 300 K, mu=-3050 K, Rcut 92 (L=184A), N~5.4k, disp:swap=1:3"
         w["points"] = [(workloads.methane_slit(n_equil_sets=0), g["x"], g["y"], g["z"], float(g["dr"]))]
         w["replicas"] = replicas or 148
-        w["steps_per_set"] = steps_per_set or 2000
+        w["steps_per_set"] = steps_per_set or 10000      # as C1 / C2 / C5 (round 1 used 2000 here only to keep its run short)
         w["start"] = "tests/golden/c3_start.npz"
     elif config == "c4":
         cx, cy, cz = workloads.c4_lattice()
