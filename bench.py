@@ -56,7 +56,7 @@ def load_start():
 
 def build_workload(config, replicas, steps_per_set):
     """BASELINE.json configs -> dict(points=[(SystemDesc, x, y, z, dr)], replicas, steps_per_set, ...).
-    Chains are laid out replica-major: chain = replica * n_points + point."""
+    Chains are laid out point-major: chain = point * replicas + replica (see expand())."""
     from mcpm_b200 import workloads
     w = {"config": config, "flop_per_pair": FLOP_PER_PAIR_SLIT, "steps_per_set": steps_per_set, "equil_steps": 0}
     if config in ("c1", "c2"):
@@ -334,6 +334,7 @@ class Job:
         e_pair = sv["pair"].copy(); e_wall = sv["wall"].copy()   # the host owns the state
         barrier(dist, local)
         e2e_s = 0.0
+        b0 = eng.transfer_bytes()
         for _ in range(steps):
             torch.cuda.synchronize(local)
             t0 = time.perf_counter()
@@ -346,17 +347,18 @@ class Job:
             e_pair = sv["pair"].copy(); e_wall = sv["wall"].copy()
             e2e_s += time.perf_counter() - t0
         barrier(dist, local)
-        wcols = min(self.cap, (int(max(nbuf)) + 1 + 31) // 32 * 32)       # columns actually copied (mcpm_set/get_positions_all)
+        b1 = eng.transfer_bytes()                                         # position bytes as the library counted them (runs of similar chains)
         stat_bytes = ctypes.sizeof(m.ChainStats)
-        h2d = 3 * self.n_chains * wcols * 8 + self.n_chains * (4 + 16 + stat_bytes)
-        d2h = 3 * self.n_chains * wcols * 8 + self.n_chains * stat_bytes
+        h2d = (b1[0] - b0[0]) // max(1, steps) + self.n_chains * (4 + 16 + stat_bytes)
+        d2h = (b1[1] - b0[1]) // max(1, steps) + self.n_chains * stat_bytes
         return e2e_s, h2d, d2h
 
 
 def expand(w):
-    """Replica-major chain list of a workload."""
+    """Point-major chain list of a workload (the replicas of a state point are neighbours, as in the host driver: chain = point * R + replica):
+    neighbouring chains then have similar loadings, which is what the bulk position transfers exploit."""
     pts, R = w["points"], w["replicas"]
-    return [pts[c % len(pts)] for c in range(len(pts) * R)]
+    return [pts[c // R] for c in range(len(pts) * R)]
 
 
 def roofline_record(w, r, peak_tflops, traffic=None, traffic_source=None):

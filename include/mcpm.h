@@ -265,6 +265,9 @@ int mcpm_set_step_counter(mcpm_ctx* ctx, int chain, unsigned long long step);
 int mcpm_last_kernel_ms(const mcpm_ctx* ctx, float* ms);
 /* Which K2 kernel the last mcpm_run launched: "k2_chains", "k2_spec", "k2_pair", "k2_quad" or "k2_cells" ("" before the first run). */
 const char* mcpm_last_kernel_name(const mcpm_ctx* ctx);
+/* Position bytes the bulk transfers (mcpm_set_positions_all / mcpm_get_positions_all) have moved so far, host -> device and back:
+ * chains are copied in runs of neighbours with similar loadings, each run as wide as its largest chain. */
+int mcpm_transfer_bytes(const mcpm_ctx* ctx, unsigned long long* h2d, unsigned long long* d2h);
 int mcpm_launch_count(const mcpm_ctx* ctx, unsigned long long* launches);
 /* CUDA-event stopwatch on the context's stream: start records an event, stop records a second one,
  * waits for it and returns the device time between the two in milliseconds. */

@@ -147,6 +147,7 @@ PROTOTYPES = {
     "mcpm_set_stream_ids": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint)]),
     "mcpm_link_boxes": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "mcpm_k1_resident": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "mcpm_transfer_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "mcpm_k1_latency": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp]),
     "mcpm_k1_resident_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "mcpm_set_dr": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),

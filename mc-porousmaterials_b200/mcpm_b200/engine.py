@@ -144,6 +144,12 @@ class Engine:
         """Serve mcpm_particle_energy / apply_move / append / remove_swap_last of `chain` from a persistent kernel (mcpm_k1_resident)."""
         check(self.L.mcpm_k1_resident(self.h, chain, 1 if enable else 0))
 
+    def transfer_bytes(self):
+        """(host -> device, device -> host) position bytes moved so far by set_positions_all / get_positions_all."""
+        a, b = C.c_ulonglong(0), C.c_ulonglong(0)
+        check(self.L.mcpm_transfer_bytes(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def k1_latency(self, chain, reps, trial=None):
         """Microseconds per mcpm_particle_energy call measured inside the library (no interpreter in the loop)."""
         us = C.c_double(0.0)

@@ -120,3 +120,40 @@ def test_moves_only_run_skips_widom(mcpm, golden):
     assert all(np.array_equal(a, b) for a, b in zip(out[0][1], out[1][1]))
     assert out[0][2] == 3000 + 2 and out[1][2] == 2                          # counts start at one (ResetStats)
     assert out[1][3] < out[0][3]
+
+
+def test_bulk_transfers_of_ragged_chains(mcpm):
+    """mcpm_set_positions_all / mcpm_get_positions_all copy runs of neighbouring chains with similar loadings, each run as wide as its largest
+    chain: every live particle (and the free slot) of every chain must arrive and come back whatever the mix, and the byte counters must
+    show the saving over one copy as wide as the largest chain."""
+    import numpy as np
+    from conftest import O
+    s = O.argon_slit(n_equil_sets=0)
+    rng = np.random.default_rng(3)
+    cap = 512
+    loadings = np.concatenate([np.full(40, 30), np.full(40, 450), [0, 511, 1, 300], rng.integers(0, 500, size=36)]).astype(np.int32)
+    nch = len(loadings)
+    with mcpm.Engine(nch, cap) as e:
+        e.set_system(s)
+        X = np.zeros((nch, e.capacity)); Y = np.zeros_like(X); Z = np.zeros_like(X)
+        for k, n in enumerate(loadings):
+            X[k, :n + 1] = rng.random(n + 1) * 40.0; Y[k, :n + 1] = rng.random(n + 1) * 40.0; Z[k, :n + 1] = 3.0 + rng.random(n + 1) * 14.0
+        b0 = e.transfer_bytes()
+        e.set_positions_all(loadings, X, Y, Z)
+        b1 = e.transfer_bytes()
+        for k in (0, 39, 40, 79, 80, 81, 82, 83, 100, nch - 1):
+            x, y, z = e.get_positions(k)
+            n = int(loadings[k])
+            assert np.array_equal(x, X[k, :n]) and np.array_equal(y, Y[k, :n]) and np.array_equal(z, Z[k, :n]), k
+        n2, X2, Y2, Z2 = e.get_positions_all()
+        assert np.array_equal(n2, loadings)
+        for k, n in enumerate(loadings):
+            assert np.array_equal(X2[k, :n + 1], X[k, :n + 1]) and np.array_equal(Z2[k, :n + 1], Z[k, :n + 1]), k   # incl. the free slot
+        one_wide_copy = 3 * nch * 512 * 8
+        assert 0 < b1[0] - b0[0] < 0.75 * one_wide_copy and e.transfer_bytes()[1] - b1[1] == b1[0] - b0[0]
+        box = e.box_energy_all()
+        o = O.COracle(s, cap + 8)
+        for k in (0, 40, 83, nch - 1):
+            n = int(loadings[k])
+            o.set_positions(X[k, :n], Y[k, :n], Z[k, :n])
+            assert np.allclose(np.asarray(box[k]), o.box_energy()[0], rtol=1e-10, atol=1e-9)
